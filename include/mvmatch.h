@@ -1,0 +1,174 @@
+/*
+ * mvmatch.h -- C ABI of libmvmatch.so: the B200 (sm_100a) dense-correspondence matching path.
+ *
+ * This is the drop-in boundary for the matching step of midvision-probe
+ * (reference: evals/utils/correspondence.py, evaluate_spair_correspondence.py:59-103).
+ * The reference has no FFI of its own on this path -- it calls torch CPU ops and
+ * faiss-gpu (correspondence.py:14-23) -- so the entry points below are what a ctypes
+ * binding of that path binds: plain pointers, sizes and a CUDA stream handle.
+ * No torch types cross this boundary.  INTEGRATION.md shows the reference-side stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success; <0 = argument error (MV_E_*), >0 = cudaError_t.
+ *     mv_last_error() returns a thread-local description of the last non-zero return.
+ *   - all pointers are DEVICE pointers unless the parameter is documented "host".
+ *   - all launches go to `stream`; nothing synchronises the host.
+ *   - feature rows are row-major (n, C); feature maps are channel-last (h*w, C).
+ *   - "n_dev" parameters are optional device-resident int32 counts (produced by
+ *     mv_compact_valid) so a whole pair can be queued without a host round trip;
+ *     when NULL the host-side maximum is the live count.
+ */
+#ifndef MVMATCH_H_
+#define MVMATCH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* mv_stream_t; /* cudaStream_t */
+
+/* ---- error codes -------------------------------------------------------------------- */
+#define MV_OK 0
+#define MV_E_ARG (-1)       /* bad argument (null pointer, non-positive size, bad enum)   */
+#define MV_E_ALIGN (-2)     /* pointer / leading dimension alignment requirement violated  */
+#define MV_E_RANGE (-3)     /* size outside the supported range                           */
+#define MV_E_WORKSPACE (-4) /* workspace too small                                        */
+#define MV_E_ARCH (-5)      /* device is not sm_100                                       */
+#define MV_E_DRIVER (-6)    /* driver entry point (cuTensorMapEncodeTiled) unavailable     */
+
+/* ---- enums -------------------------------------------------------------------------- */
+/* sampling modes of kernel 1 */
+#define MV_SAMPLE_BILINEAR_ZEROS 0 /* F.grid_sample(mode=bilinear, padding_mode=zeros): correspondence.py:173, spair:76-78 */
+#define MV_SAMPLE_BICUBIC_CLAMP 1  /* F.interpolate(mode=bicubic, align_corners=False):  correspondence.py:240-241        */
+#define MV_SAMPLE_ROWS 2           /* no resampling, rows are taken as they are:          correspondence.py:47-48           */
+
+/* operand types of kernel 2 */
+#define MV_DTYPE_BF16 0 /* tcgen05.mma kind::f16, bf16 inputs, fp32 accumulate  */
+#define MV_DTYPE_TF32 1 /* tcgen05.mma kind::tf32, fp32 inputs, fp32 accumulate */
+
+/* value written in masked / empty slots of similarity outputs */
+#define MV_SIM_MASKED (-3.0e38f)
+
+#define MV_MAX_THRESHOLDS 16
+
+/* ---- library ------------------------------------------------------------------------ */
+int mv_version(void);
+const char* mv_last_error(void);
+/* sm count, compute capability and L2 size of `device` (host out-params, any may be NULL) */
+int mv_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int* l2_bytes);
+
+/* ---- layout helpers ------------------------------------------------------------------ */
+/* (C, hw) channel-major fp32 map -> (hw, C) channel-last.  prenorm != 0 additionally divides
+ * every pixel's C-vector by max(||.||_2, 1e-12)  (SPair: F.normalize(feats, p=2, dim=1),
+ * evaluate_spair_correspondence.py:59).  norm_scratch: hw floats, required when prenorm. */
+int mv_chw_to_hwc(const float* src_chw, float* dst_hwc, int C, int hw, int prenorm, float* norm_scratch,
+                  mv_stream_t stream);
+
+/* Row-major stable compaction of the indices i in [0, n) with z[i * z_stride] > 0
+ * (correspondence.py:221-222 `xyz[:, 2] > 0`, :247-252 `xyz_grid[2] > 0`).
+ * valid_idx: n int32 (first *n_valid are live, ascending); n_valid: 1 int32.  n <= 2^20. */
+int mv_compact_valid(const float* z, int z_stride, int n, int32_t* valid_idx, int32_t* n_valid, mv_stream_t stream);
+
+/* ---- geometry: per-point source coordinates for kernel 1 ------------------------------- */
+/* ScanNet path: grid_to_pointcloud (correspondence.py:147-161) + the projection and NDC
+ * normalisation of sample_pointcloud_features (:164-170) + grid_sample's align_corners=False
+ * un-normalisation.  For every pixel of the (H, W) depth map:
+ *   xyz_all (H*W, 3) = Kinv @ (depth * pixel-centre grid)            [always written]
+ * and for the live points listed in valid_idx (after mv_compact_valid on xyz_all[:,2]):
+ *   xyz (n, 3) compacted, coords (n, 2) = (ix, iy) in feature-map pixels.
+ * Two entry points because the compaction sits between them.  K, Kinv: host, row-major 3x3. */
+int mv_geom_backproject(const float* depth, int H, int W, const float* Kinv_host, float* xyz_all, mv_stream_t stream);
+int mv_geom_project_coords(const float* xyz_all, const int32_t* valid_idx, const int32_t* n_dev, int n_max,
+                           const float* K_host, int H, int W, int h, int w, float* xyz, float* coords,
+                           mv_stream_t stream);
+
+/* NAVI path (correspondence.py:240-252): compacted xyz (n,3), uv (n,2) = pixel centres (x+.5, y+.5)
+ * of the live pixels of the (3,H,W) xyz grid, and coords (n,2) = bicubic source index
+ * (h/H)*(dst+0.5)-0.5 in the (h, w) feature map. */
+int mv_geom_grid_coords(const float* xyz_grid, const int32_t* valid_idx, const int32_t* n_dev, int n_max, int H,
+                        int W, int h, int w, float* xyz, float* uv, float* coords, mv_stream_t stream);
+
+/* SPair path (evaluate_spair_correspondence.py:71-78): keypoints (n, kp_stride) in image pixels ->
+ * kp/image_size*2-1 -> grid_sample align_corners=True un-normalisation ((g+1)/2*(size-1)). */
+int mv_geom_keypoint_coords(const float* kps, int kp_stride, int n, float image_size, int h, int w, float* coords,
+                            mv_stream_t stream);
+
+/* ---- kernel 1: sample + L2-normalise + cast (HBM-bound) -------------------------------- */
+/* For point p < n: row = sample(src, coords[p]) (4-tap bilinear with zero padding, 16-tap Keys
+ * cubic A=-0.75 with border clamp, or row p of src itself); if normalize: row /= max(||row||,1e-12)
+ * (F.normalize, correspondence.py:47-48).  Writes bf16 and/or fp32 rows.  C % 8 == 0, C <= 8192.
+ * taps (optional, (n,2) int32): the (x0, y0) = floor(ix), floor(iy) tap origin, for parity tests. */
+int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, const float* coords,
+                           const int32_t* n_dev, int n_max, int normalize, uint16_t* out_bf16, float* out_f32,
+                           int32_t* taps, mv_stream_t stream);
+
+/* ---- kernel 2: similarity GEMM with fused row top-2 / column arg-max (tensor-core bound) -- */
+/* S = A @ B^T (n x m, never written).  Replaces faiss GpuIndexFlatL2.search(k<=2)
+ * (correspondence.py:14-23) for L2-normalised rows, where the L2 order equals the cosine order
+ * (correspondence.py:27-43).
+ *   row_val/row_idx (n_max, 2): the two largest S[i, :] and their columns, best first, ties to the
+ *                               lower column; missing entries = MV_SIM_MASKED / -1.
+ *   col_best (m_max) optional : packed arg-max over rows of S[:, j]; decode with mv_k2_unpack_col.
+ * A, B: bf16 (MV_DTYPE_BF16) or fp32 (MV_DTYPE_TF32), 16-byte aligned, C % 8 == 0 (bf16) / C % 4 == 0.
+ * cta_pair != 0 selects the cta_group::2 (two-SM) schedule.  workspace from mv_k2_workspace_bytes. */
+size_t mv_k2_workspace_bytes(int n_max, int m_max);
+int mv_k2_sim_top2(const void* A, const void* B, int n_max, int m_max, int C, const int32_t* n_dev,
+                   const int32_t* m_dev, int dtype, int cta_pair, float* row_val, int32_t* row_idx,
+                   unsigned long long* col_best, void* workspace, size_t workspace_bytes, mv_stream_t stream);
+int mv_k2_unpack_col(const unsigned long long* col_best, int m, float* col_val, int32_t* col_idx, mv_stream_t stream);
+
+/* ---- kernel 3: fp32 distance recompute, ratio test, mutual check, selection, scoring ---- */
+/* Per query row i with candidates j0, j1 = row_idx[i]:  d_k = 1 - cos(A32[i], B32[j_k]) in fp32
+ * (knn_points, correspondence.py:53-58); candidates are re-ranked so d_0 <= d_1 (row_idx is updated
+ * in place); weight = 1 - max(d0,1e-9)/max(d1,1e-9) if ratio_test else d0  (correspondence.py:72-77,
+ * :105-121); mutual[i] = (argmax_i' S[i', j0] == i) from col_best (may be NULL -> all 0). */
+int mv_k3_ratio_mutual(const float* A32, const float* B32, int C, const int32_t* n_dev, int n_max,
+                       int32_t* row_idx, const unsigned long long* col_best, int ratio_test, float* dists,
+                       float* weight, uint8_t* mutual, mv_stream_t stream);
+
+/* get_topk_matches (correspondence.py:125-129): the k = min(num_corr, n) largest weights, sorted
+ * descending (ties: lower row first).  sel_* have num_corr entries; k_dev receives k.
+ * num_corr <= 16384, n_max <= 2^20. */
+int mv_k3_topk_matches(const float* weight, const int32_t* row_idx, const int32_t* n_dev, int n_max,
+                       int num_corr, int32_t* sel_src, int32_t* sel_dst, float* sel_weight, int32_t* k_dev,
+                       mv_stream_t stream);
+
+/* Scoring of the selected matches (callers: evaluate_navi_correspondence.py:183-212,
+ * render_scannet_correspondence.py:211-217, :253-264, :131-147):
+ *   p0 = xyz0[sel_src], p1 = xyz1[sel_dst]; p0in1 = p0 @ R^T + t (transformations.py:27-36);
+ *   err3d = ||p0in1 - p1||; err2d = ||proj(p0in1) - proj(p1)||, proj = project_3dto2d (:193-196).
+ * Integer hit counts are ACCUMULATED (atomicAdd) into hits[]:
+ *   hits[0]                      += k                      (matches scored)
+ *   hits[1]                      += #mutual among them
+ *   hits[2 + t]                  += #(err3d < thr3d[t])            t < n3
+ *   hits[2 + n3 + t]             += #(err2d < thr2d[t])            t < n2
+ *   hits[2 + n3 + n2 + t]        += #(mutual & err3d < thr3d[t])
+ *   hits[2 + 2*n3 + n2 + t]      += #(mutual & err2d < thr2d[t])
+ * Rt (3x4), Kproj (3x3), thr3d, thr2d are host arrays.  c_* / err* outputs are optional (NULL). */
+int mv_k3_score(const int32_t* sel_src, const int32_t* sel_dst, const int32_t* k_dev, int k_max,
+                const float* xyz0, const float* xyz1, const uint8_t* mutual, const float* Rt_host,
+                const float* Kproj_host, const float* thr3d_host, int n3, const float* thr2d_host, int n2,
+                float* c_xyz0, float* c_xyz1, float* err3d, float* err2d, unsigned long long* hits,
+                mv_stream_t stream);
+
+/* Plain gather of rows: dst[i, :] = src[idx[i], :] for i < *k_dev (k_max if NULL); width floats. */
+int mv_gather_rows(const float* src, int width, const int32_t* idx, const int32_t* k_dev, int k_max, float* dst,
+                   mv_stream_t stream);
+
+/* SPair scoring (evaluate_spair_correspondence.py:83-98, :121): pred (K) = arg-max column of the
+ * heat map in the (h, w) feature map -> (col,row)/w; errors (K,K) = ||pred_k - kps_j[l,:2]/image_size||
+ * / thresh_scale, 1e3 where kps_i[k,2]*kps_j[l,2] != 1.  Outputs error matrix (K,K, optional),
+ * error_same (K; -1 where the keypoint is not in both), error_nn / index_nn (K; -1 likewise) and
+ * ACCUMULATES hits[0] += #in_both, hits[1] += #(error_same < pck_thresh). K <= 64. */
+int mv_k3_spair_errors(const int32_t* pred_flat, int K, int w, const float* kps_i, const float* kps_j,
+                       int kp_stride, float image_size, float thresh_scale, float pck_thresh, float* errors,
+                       float* error_same, float* error_nn, int32_t* index_nn, unsigned long long* hits,
+                       mv_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVMATCH_H_ */

@@ -1,0 +1,501 @@
+// k1_sample.cu -- kernel 1 of the matching path and its small producers.
+//
+//   mv_chw_to_hwc            (C,h,w) backbone map -> channel-last (h*w, C), optional per-pixel L2 norm
+//   mv_compact_valid         stable compaction of the live (z > 0) pixels
+//   mv_geom_*                per-point source coordinates for the three reference call sites
+//   mv_k1_sample_normalize   gather/upsample + L2-normalise + bf16/fp32 row writer   (HBM-bound)
+//
+// Reference behaviour being reproduced (file:line in /root/reference):
+//   evals/utils/correspondence.py:132-176  get_grid / grid_to_pointcloud / sample_pointcloud_features
+//   evals/utils/correspondence.py:240-252  bicubic upsample + valid-pixel gather
+//   evals/utils/correspondence.py:47-48    F.normalize of the sampled rows
+//   evaluate_spair_correspondence.py:59-79 per-pixel normalise + keypoint grid_sample(align_corners=True)
+//
+// Data layout: the source map is channel-last so that every tap is one contiguous C-vector read with
+// 128-bit loads; consecutive live points are handled by the same CTA so their shared taps hit L1
+// instead of L2 (an 8x upsample re-uses each tap ~8 times along x).
+#include "common.cuh"
+
+namespace {
+
+constexpr int K1_THREADS_MAX = 256;
+constexpr int K1_POINTS_PER_CTA = 16;
+constexpr float K1_NORM_EPS = 1e-12f;  // F.normalize default eps
+
+// ------------------------------------------------------------------------------------------
+// (C, hw) -> (hw, C) transpose, optional scale by 1/max(norm, eps)
+// ------------------------------------------------------------------------------------------
+__global__ void pixel_norm_kernel(const float* __restrict__ src, float* __restrict__ norm, int C, int hw) {
+  // block = (32 pixels, 8 channel slices)
+  __shared__ float part[8][33];
+  const int px = blockIdx.x * 32 + threadIdx.x;
+  float ss = 0.f;
+  if (px < hw) {
+    for (int c = threadIdx.y; c < C; c += 8) {
+      float v = __ldg(src + (size_t)c * hw + px);
+      ss = fmaf(v, v, ss);
+    }
+  }
+  part[threadIdx.y][threadIdx.x] = ss;
+  __syncthreads();
+  if (threadIdx.y == 0 && px < hw) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][threadIdx.x];
+    norm[px] = sqrtf(t);
+  }
+}
+
+__global__ void chw_to_hwc_kernel(const float* __restrict__ src, float* __restrict__ dst, int C, int hw,
+                                  const float* __restrict__ norm) {
+  __shared__ float tile[32][33];
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  // read: x = pixel (contiguous in src), y = channel
+  for (int dy = threadIdx.y; dy < 32; dy += 8) {
+    int c = c0 + dy, p = p0 + threadIdx.x;
+    float v = 0.f;
+    if (c < C && p < hw) v = __ldg(src + (size_t)c * hw + p);
+    tile[dy][threadIdx.x] = v;
+  }
+  __syncthreads();
+  // write: x = channel (contiguous in dst), y = pixel
+  for (int dy = threadIdx.y; dy < 32; dy += 8) {
+    int p = p0 + dy, c = c0 + threadIdx.x;
+    if (c < C && p < hw) {
+      float v = tile[threadIdx.x][dy];
+      if (norm) v = __fdiv_rn(v, fmaxf(__ldg(norm + p), K1_NORM_EPS));
+      dst[(size_t)p * C + c] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// stable compaction (single CTA; n <= 2^20)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) compact_valid_kernel(const float* __restrict__ z, int z_stride, int n,
+                                                             int32_t* __restrict__ valid_idx,
+                                                             int32_t* __restrict__ n_valid) {
+  __shared__ int warp_tot[32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int per = (n + 1023) / 1024;
+  const int beg = min(tid * per, n), end = min(beg + per, n);
+  int cnt = 0;
+  for (int i = beg; i < end; ++i) cnt += (__ldg(z + (size_t)i * z_stride) > 0.f) ? 1 : 0;
+  // inclusive warp scan
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int t = warp_tot[lane];
+    int s = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int u = __shfl_up_sync(0xffffffffu, s, o);
+      if (lane >= o) s += u;
+    }
+    warp_tot[lane] = s - t;  // exclusive prefix of warp totals
+    if (lane == 31) *n_valid = s;
+  }
+  __syncthreads();
+  int pos = warp_tot[wid] + incl - cnt;
+  for (int i = beg; i < end; ++i)
+    if (__ldg(z + (size_t)i * z_stride) > 0.f) valid_idx[pos++] = i;
+}
+
+// ------------------------------------------------------------------------------------------
+// geometry
+// ------------------------------------------------------------------------------------------
+struct Mat3 {
+  float m[9];
+};
+
+// correspondence.py:132-161: points = depth * (x+.5, y+.5, 1); xyz = Kinv @ points
+__global__ void backproject_kernel(const float* __restrict__ depth, int H, int W, Mat3 Ki,
+                                   float* __restrict__ xyz_all) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= H * W) return;
+  int y = p / W, x = p - y * W;
+  float d = __ldg(depth + p);
+  float px = __fmul_rn(d, (float)x + 0.5f), py = __fmul_rn(d, (float)y + 0.5f), pz = d;  // depth * grid
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    float a = __fmul_rn(Ki.m[3 * r + 0], px);
+    a = fmaf(Ki.m[3 * r + 1], py, a);
+    a = fmaf(Ki.m[3 * r + 2], pz, a);
+    xyz_all[(size_t)p * 3 + r] = a;
+  }
+}
+
+// correspondence.py:164-170 + ATen CPU grid_sampler (align_corners=False): ix = (g+1)*(size/2) - 0.5
+__global__ void project_coords_kernel(const float* __restrict__ xyz_all, const int32_t* __restrict__ valid_idx,
+                                      const int32_t* __restrict__ n_dev, int n_max, Mat3 K, int H, int W, int h,
+                                      int w, float* __restrict__ xyz, float* __restrict__ coords) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int n = n_dev ? min(*n_dev, n_max) : n_max;
+  if (i >= n) return;
+  int p = valid_idx ? valid_idx[i] : i;
+  float X = xyz_all[(size_t)p * 3 + 0], Y = xyz_all[(size_t)p * 3 + 1], Z = xyz_all[(size_t)p * 3 + 2];
+  xyz[(size_t)i * 3 + 0] = X;
+  xyz[(size_t)i * 3 + 1] = Y;
+  xyz[(size_t)i * 3 + 2] = Z;
+  float uvd[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {  // uvd = pc @ K^T
+    float a = __fmul_rn(X, K.m[3 * r + 0]);
+    a = fmaf(Y, K.m[3 * r + 1], a);
+    a = fmaf(Z, K.m[3 * r + 2], a);
+    uvd[r] = a;
+  }
+  float den = fmaxf(uvd[2], 1e-9f);
+  float u = __fdiv_rn(uvd[0], den), v = __fdiv_rn(uvd[1], den);
+  float gx = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, u), (float)W), 1.f);
+  float gy = __fsub_rn(__fdiv_rn(__fmul_rn(2.f, v), (float)H), 1.f);
+  coords[(size_t)i * 2 + 0] = __fsub_rn(__fmul_rn(__fadd_rn(gx, 1.f), (float)w * 0.5f), 0.5f);
+  coords[(size_t)i * 2 + 1] = __fsub_rn(__fmul_rn(__fadd_rn(gy, 1.f), (float)h * 0.5f), 0.5f);
+}
+
+// correspondence.py:240-252: bicubic source index scale*(dst+0.5)-0.5, uv = pixel centre, xyz gather
+__global__ void grid_coords_kernel(const float* __restrict__ xyz_grid, const int32_t* __restrict__ valid_idx,
+                                   const int32_t* __restrict__ n_dev, int n_max, int H, int W, int h, int w,
+                                   float* __restrict__ xyz, float* __restrict__ uv, float* __restrict__ coords) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int n = n_dev ? min(*n_dev, n_max) : n_max;
+  if (i >= n) return;
+  int p = valid_idx ? valid_idx[i] : i;
+  int y = p / W, x = p - y * W;
+  const size_t HW = (size_t)H * W;
+  if (xyz) {
+    xyz[(size_t)i * 3 + 0] = __ldg(xyz_grid + p);
+    xyz[(size_t)i * 3 + 1] = __ldg(xyz_grid + HW + p);
+    xyz[(size_t)i * 3 + 2] = __ldg(xyz_grid + 2 * HW + p);
+  }
+  if (uv) {
+    uv[(size_t)i * 2 + 0] = (float)x + 0.5f;
+    uv[(size_t)i * 2 + 1] = (float)y + 0.5f;
+  }
+  float sx = (float)w / (float)W, sy = (float)h / (float)H;
+  coords[(size_t)i * 2 + 0] = __fsub_rn(__fmul_rn(sx, (float)x + 0.5f), 0.5f);
+  coords[(size_t)i * 2 + 1] = __fsub_rn(__fmul_rn(sy, (float)y + 0.5f), 0.5f);
+}
+
+// evaluate_spair_correspondence.py:71-78 + ATen CUDA grid_sampler (align_corners=True):
+//   g = kp/size*2-1 ; ix = ((g+1)/2)*(w-1)
+__global__ void keypoint_coords_kernel(const float* __restrict__ kps, int stride, int n, float image_size, int h,
+                                       int w, float* __restrict__ coords) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float kx = __fdiv_rn(kps[(size_t)i * stride + 0], image_size);
+  float ky = __fdiv_rn(kps[(size_t)i * stride + 1], image_size);
+  float gx = __fsub_rn(__fmul_rn(kx, 2.f), 1.f), gy = __fsub_rn(__fmul_rn(ky, 2.f), 1.f);
+  coords[(size_t)i * 2 + 0] = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(w - 1));
+  coords[(size_t)i * 2 + 1] = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.f), 2.f), (float)(h - 1));
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel 1
+// ------------------------------------------------------------------------------------------
+struct K1Params {
+  const float* src;
+  const float* coords;
+  const int32_t* n_dev;
+  int n_max, C, h, w, normalize;
+  __nv_bfloat16* out_bf16;
+  float* out_f32;
+  int32_t* taps;
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {
+  a.x = fmaf(w, v.x, a.x);
+  a.y = fmaf(w, v.y, a.y);
+  a.z = fmaf(w, v.z, a.z);
+  a.w = fmaf(w, v.w, a.w);
+}
+
+// Keys cubic convolution, A = -0.75 (ATen UpSample.h cubic_convolution1/2)
+__device__ __forceinline__ void cubic_coeffs(float t, float c[4]) {
+  const float A = -0.75f;
+  float x0 = t + 1.f, x1 = t, x2 = 1.f - t, x3 = 2.f - t;
+  c[0] = ((A * x0 - 5.f * A) * x0 + 8.f * A) * x0 - 4.f * A;
+  c[1] = ((A + 2.f) * x1 - (A + 3.f)) * x1 * x1 + 1.f;
+  c[2] = ((A + 2.f) * x2 - (A + 3.f)) * x2 * x2 + 1.f;
+  c[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
+}
+
+template <int MODE, int NV>
+__global__ void __launch_bounds__(K1_THREADS_MAX) k1_sample_normalize_kernel(K1Params p) {
+  __shared__ float red[K1_THREADS_MAX / 32];
+  __shared__ float bcast;
+  const int n = p.n_dev ? min(*p.n_dev, p.n_max) : p.n_max;
+  const int C4 = p.C >> 2;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
+  const int pt_beg = blockIdx.x * K1_POINTS_PER_CTA;
+  const int pt_end = min(pt_beg + K1_POINTS_PER_CTA, n);
+
+  for (int pt = pt_beg; pt < pt_end; ++pt) {
+    float4 acc[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    if (MODE == MV_SAMPLE_ROWS) {
+      const float* row = p.src + (size_t)pt * p.C;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        int c4 = tid + v * blockDim.x;
+        if (c4 < C4) acc[v] = ld4(row + 4 * c4);
+      }
+    } else if (MODE == MV_SAMPLE_BILINEAR_ZEROS) {
+      // ATen GridSamplerKernel.cpp (bilinear, zeros): w = ix - floor(ix), e = 1 - w, n = iy - floor(iy), s = 1 - n
+      const float ix = __ldg(p.coords + 2 * (size_t)pt), iy = __ldg(p.coords + 2 * (size_t)pt + 1);
+      const float fx = floorf(ix), fy = floorf(iy);
+      const int x0 = (int)fx, y0 = (int)fy;
+      const float ww = ix - fx, we = 1.f - ww, wn = iy - fy, ws = 1.f - wn;
+      if (p.taps && tid == 0) {
+        p.taps[2 * (size_t)pt] = x0;
+        p.taps[2 * (size_t)pt + 1] = y0;
+      }
+      const float wt[4] = {ws * we, ws * ww, wn * we, wn * ww};  // nw, ne, sw, se
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int xx = x0 + (k & 1), yy = y0 + (k >> 1);
+        if (xx >= 0 && xx < p.w && yy >= 0 && yy < p.h) {  // uniform across the CTA
+          const float* row = p.src + ((size_t)yy * p.w + xx) * p.C;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            int c4 = tid + v * blockDim.x;
+            if (c4 < C4) fma4(acc[v], wt[k], ld4(row + 4 * c4));
+          }
+        }
+      }
+    } else {  // MV_SAMPLE_BICUBIC_CLAMP
+      const float ix = __ldg(p.coords + 2 * (size_t)pt), iy = __ldg(p.coords + 2 * (size_t)pt + 1);
+      const float fx = floorf(ix), fy = floorf(iy);
+      const int x0 = (int)fx, y0 = (int)fy;
+      if (p.taps && tid == 0) {
+        p.taps[2 * (size_t)pt] = x0;
+        p.taps[2 * (size_t)pt + 1] = y0;
+      }
+      float cx[4], cy[4];
+      cubic_coeffs(ix - fx, cx);
+      cubic_coeffs(iy - fy, cy);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int yy = min(max(y0 - 1 + i, 0), p.h - 1);
+        float4 r[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) r[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int xx = min(max(x0 - 1 + j, 0), p.w - 1);
+          const float* row = p.src + ((size_t)yy * p.w + xx) * p.C;
+#pragma unroll
+          for (int v = 0; v < NV; ++v) {
+            int c4 = tid + v * blockDim.x;
+            if (c4 < C4) fma4(r[v], cx[j], ld4(row + 4 * c4));
+          }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) fma4(acc[v], cy[i], r[v]);
+      }
+    }
+
+    float denom = 1.f;
+    if (p.normalize) {
+      float ss = 0.f;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        ss = fmaf(acc[v].x, acc[v].x, ss);
+        ss = fmaf(acc[v].y, acc[v].y, ss);
+        ss = fmaf(acc[v].z, acc[v].z, ss);
+        ss = fmaf(acc[v].w, acc[v].w, ss);
+      }
+      ss = warp_sum(ss);
+      if (lane == 0) red[wid] = ss;
+      __syncthreads();
+      if (wid == 0) {
+        float t = (lane < nwarp) ? red[lane] : 0.f;
+        t = warp_sum(t);
+        if (lane == 0) bcast = fmaxf(sqrtf(t), K1_NORM_EPS);
+      }
+      __syncthreads();
+      denom = bcast;
+    }
+
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      int c4 = tid + v * blockDim.x;
+      if (c4 < C4) {
+        float4 o = acc[v];
+        if (p.normalize) {
+          o.x = __fdiv_rn(o.x, denom);
+          o.y = __fdiv_rn(o.y, denom);
+          o.z = __fdiv_rn(o.z, denom);
+          o.w = __fdiv_rn(o.w, denom);
+        }
+        if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)pt * p.C + 4 * c4) = o;
+        if (p.out_bf16) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&lo);
+          pk.y = *reinterpret_cast<uint32_t*>(&hi);
+          *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)pt * p.C + 4 * c4) = pk;
+        }
+      }
+    }
+    // `red`/`bcast` are rewritten next iteration only after the first __syncthreads there,
+    // and every thread has read `bcast` before it can pass that barrier: no extra barrier needed.
+  }
+}
+
+template <int MODE>
+int launch_k1(const K1Params& p, int threads, int nv, int grid, cudaStream_t st) {
+  switch (nv) {
+#define MV_K1_CASE(NV)                                                      \
+  case NV:                                                                  \
+    k1_sample_normalize_kernel<MODE, NV><<<grid, threads, 0, st>>>(p);      \
+    break;
+    MV_K1_CASE(1)
+    MV_K1_CASE(2)
+    MV_K1_CASE(3)
+    MV_K1_CASE(4)
+    MV_K1_CASE(5)
+    MV_K1_CASE(6)
+    MV_K1_CASE(7)
+    MV_K1_CASE(8)
+#undef MV_K1_CASE
+    default:
+      mv_set_error("mv_k1_sample_normalize: C too large");
+      return MV_E_RANGE;
+  }
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+Mat3 load_mat3(const float* host) {
+  Mat3 m;
+  for (int i = 0; i < 9; ++i) m.m[i] = host[i];
+  return m;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mv_chw_to_hwc(const float* src_chw, float* dst_hwc, int C, int hw, int prenorm, float* norm_scratch,
+                  mv_stream_t stream) {
+  MV_REQUIRE(src_chw && dst_hwc, MV_E_ARG, "mv_chw_to_hwc: null pointer");
+  MV_REQUIRE(C > 0 && hw > 0, MV_E_ARG, "mv_chw_to_hwc: C and hw must be positive");
+  MV_REQUIRE(!prenorm || norm_scratch, MV_E_ARG, "mv_chw_to_hwc: prenorm needs norm_scratch (hw floats)");
+  cudaStream_t st = mv_cuda_stream(stream);
+  if (prenorm) {
+    pixel_norm_kernel<<<(hw + 31) / 32, dim3(32, 8), 0, st>>>(src_chw, norm_scratch, C, hw);
+    MV_LAUNCH_CHECK();
+  }
+  dim3 grid((hw + 31) / 32, (C + 31) / 32);
+  chw_to_hwc_kernel<<<grid, dim3(32, 8), 0, st>>>(src_chw, dst_hwc, C, hw, prenorm ? norm_scratch : nullptr);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+int mv_compact_valid(const float* z, int z_stride, int n, int32_t* valid_idx, int32_t* n_valid,
+                     mv_stream_t stream) {
+  MV_REQUIRE(z && valid_idx && n_valid, MV_E_ARG, "mv_compact_valid: null pointer");
+  MV_REQUIRE(n >= 0 && n <= (1 << 20) && z_stride >= 1, MV_E_RANGE, "mv_compact_valid: n must be in [0, 2^20]");
+  compact_valid_kernel<<<1, 1024, 0, mv_cuda_stream(stream)>>>(z, z_stride, n, valid_idx, n_valid);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+int mv_geom_backproject(const float* depth, int H, int W, const float* Kinv_host, float* xyz_all,
+                        mv_stream_t stream) {
+  MV_REQUIRE(depth && Kinv_host && xyz_all, MV_E_ARG, "mv_geom_backproject: null pointer");
+  MV_REQUIRE(H > 0 && W > 0, MV_E_ARG, "mv_geom_backproject: H and W must be positive");
+  int n = H * W;
+  backproject_kernel<<<(n + 255) / 256, 256, 0, mv_cuda_stream(stream)>>>(depth, H, W, load_mat3(Kinv_host),
+                                                                         xyz_all);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+int mv_geom_project_coords(const float* xyz_all, const int32_t* valid_idx, const int32_t* n_dev, int n_max,
+                           const float* K_host, int H, int W, int h, int w, float* xyz, float* coords,
+                           mv_stream_t stream) {
+  MV_REQUIRE(xyz_all && K_host && xyz && coords, MV_E_ARG, "mv_geom_project_coords: null pointer");
+  MV_REQUIRE(n_max >= 0 && H > 0 && W > 0 && h > 0 && w > 0, MV_E_ARG, "mv_geom_project_coords: bad sizes");
+  if (n_max == 0) return MV_OK;
+  project_coords_kernel<<<(n_max + 255) / 256, 256, 0, mv_cuda_stream(stream)>>>(
+      xyz_all, valid_idx, n_dev, n_max, load_mat3(K_host), H, W, h, w, xyz, coords);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+int mv_geom_grid_coords(const float* xyz_grid, const int32_t* valid_idx, const int32_t* n_dev, int n_max, int H,
+                        int W, int h, int w, float* xyz, float* uv, float* coords, mv_stream_t stream) {
+  MV_REQUIRE(coords && (xyz_grid || !xyz), MV_E_ARG, "mv_geom_grid_coords: null pointer");
+  MV_REQUIRE(n_max >= 0 && H > 0 && W > 0 && h > 0 && w > 0, MV_E_ARG, "mv_geom_grid_coords: bad sizes");
+  if (n_max == 0) return MV_OK;
+  grid_coords_kernel<<<(n_max + 255) / 256, 256, 0, mv_cuda_stream(stream)>>>(xyz_grid, valid_idx, n_dev, n_max, H,
+                                                                             W, h, w, xyz, uv, coords);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+int mv_geom_keypoint_coords(const float* kps, int kp_stride, int n, float image_size, int h, int w,
+                            float* coords, mv_stream_t stream) {
+  MV_REQUIRE(kps && coords, MV_E_ARG, "mv_geom_keypoint_coords: null pointer");
+  MV_REQUIRE(n >= 0 && kp_stride >= 2 && h > 0 && w > 0 && image_size > 0.f, MV_E_ARG,
+             "mv_geom_keypoint_coords: bad sizes");
+  if (n == 0) return MV_OK;
+  keypoint_coords_kernel<<<(n + 127) / 128, 128, 0, mv_cuda_stream(stream)>>>(kps, kp_stride, n, image_size, h, w,
+                                                                            coords);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, const float* coords,
+                           const int32_t* n_dev, int n_max, int normalize, uint16_t* out_bf16, float* out_f32,
+                           int32_t* taps, mv_stream_t stream) {
+  MV_REQUIRE(src && (out_bf16 || out_f32), MV_E_ARG, "mv_k1_sample_normalize: null src or no output");
+  MV_REQUIRE(mode == MV_SAMPLE_BILINEAR_ZEROS || mode == MV_SAMPLE_BICUBIC_CLAMP || mode == MV_SAMPLE_ROWS,
+             MV_E_ARG, "mv_k1_sample_normalize: unknown mode %d", mode);
+  MV_REQUIRE(mode == MV_SAMPLE_ROWS || (coords && h > 0 && w > 0), MV_E_ARG,
+             "mv_k1_sample_normalize: sampling modes need coords and a map size");
+  MV_REQUIRE(C > 0 && C % 8 == 0 && C <= 8192, MV_E_RANGE, "mv_k1_sample_normalize: C=%d must be a multiple of 8, <= 8192", C);
+  MV_REQUIRE(n_max >= 0, MV_E_ARG, "mv_k1_sample_normalize: negative n_max");
+  MV_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0, MV_E_ALIGN, "mv_k1_sample_normalize: src must be 16-byte aligned");
+  MV_REQUIRE(!out_f32 || (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0, MV_E_ALIGN,
+             "mv_k1_sample_normalize: out_f32 must be 16-byte aligned");
+  MV_REQUIRE(!out_bf16 || (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0, MV_E_ALIGN,
+             "mv_k1_sample_normalize: out_bf16 must be 8-byte aligned");
+  if (n_max == 0) return MV_OK;
+
+  K1Params p;
+  p.src = src;
+  p.coords = coords;
+  p.n_dev = n_dev;
+  p.n_max = n_max;
+  p.C = C;
+  p.h = h;
+  p.w = w;
+  p.normalize = normalize;
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  p.out_f32 = out_f32;
+  p.taps = taps;
+
+  const int C4 = C / 4;
+  int threads = ((C4 + 31) / 32) * 32;
+  if (threads > K1_THREADS_MAX) threads = K1_THREADS_MAX;
+  const int nv = (C4 + threads - 1) / threads;
+  const int grid = (n_max + K1_POINTS_PER_CTA - 1) / K1_POINTS_PER_CTA;
+  cudaStream_t st = mv_cuda_stream(stream);
+  if (mode == MV_SAMPLE_BILINEAR_ZEROS) return launch_k1<MV_SAMPLE_BILINEAR_ZEROS>(p, threads, nv, grid, st);
+  if (mode == MV_SAMPLE_BICUBIC_CLAMP) return launch_k1<MV_SAMPLE_BICUBIC_CLAMP>(p, threads, nv, grid, st);
+  return launch_k1<MV_SAMPLE_ROWS>(p, threads, nv, grid, st);
+}
+
+}  // extern "C"
