@@ -158,6 +158,10 @@ int mv_k3_score(const int32_t* sel_src, const int32_t* sel_dst, const int32_t* k
 int mv_gather_rows(const float* src, int width, const int32_t* idx, const int32_t* k_dev, int k_max, float* dst,
                    mv_stream_t stream);
 
+/* argmax_2d (correspondence.py:179-190): flat arg-max (or arg-min) of every row of x (rows, cols),
+ * first occurrence on ties; out_flat (rows) int32.  The caller turns flat into (col, row). */
+int mv_argmax_rows(const float* x, int rows, int cols, int max_value, int32_t* out_flat, mv_stream_t stream);
+
 /* SPair scoring (evaluate_spair_correspondence.py:83-98, :121): pred (K) = arg-max column of the
  * heat map in the (h, w) feature map -> (col,row)/w; errors (K,K) = ||pred_k - kps_j[l,:2]/image_size||
  * / thresh_scale, 1e3 where kps_i[k,2]*kps_j[l,2] != 1.  Outputs error matrix (K,K, optional),

@@ -1,0 +1,91 @@
+"""ctypes binding of libmvmatch.so (C ABI declared in include/mvmatch.h).
+
+Only raw pointers, sizes and a CUDA stream handle cross this boundary.  There is no fallback:
+if the library is missing the import of any compute entry point raises.
+"""
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_size_t, c_void_p
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libmvmatch.so")
+
+P = c_void_p  # every device / host pointer
+
+# name -> (restype, argtypes); mirrors include/mvmatch.h one to one
+PROTOTYPES = {
+    "mv_version": (c_int, []),
+    "mv_last_error": (c_char_p, []),
+    "mv_device_info": (c_int, [c_int, P, P, P, P]),
+    "mv_chw_to_hwc": (c_int, [P, P, c_int, c_int, c_int, P, P]),
+    "mv_compact_valid": (c_int, [P, c_int, c_int, P, P, P]),
+    "mv_geom_backproject": (c_int, [P, c_int, c_int, P, P, P]),
+    "mv_geom_project_coords": (c_int, [P, P, P, c_int, P, c_int, c_int, c_int, c_int, P, P, P]),
+    "mv_geom_grid_coords": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
+    "mv_geom_keypoint_coords": (c_int, [P, c_int, c_int, c_float, c_int, c_int, P, P]),
+    "mv_k1_sample_normalize": (c_int, [c_int, P, c_int, c_int, c_int, P, P, c_int, c_int, P, P, P, P]),
+    "mv_k2_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "mv_k2_sim_top2": (c_int, [P, P, c_int, c_int, c_int, P, P, c_int, c_int, P, P, P, P, c_size_t, P]),
+    "mv_k2_unpack_col": (c_int, [P, c_int, P, P, P]),
+    "mv_k3_ratio_mutual": (c_int, [P, P, c_int, P, c_int, P, P, c_int, P, P, P, P]),
+    "mv_k3_topk_matches": (c_int, [P, P, P, c_int, c_int, P, P, P, P, P]),
+    "mv_k3_score": (c_int, [P, P, P, c_int, P, P, P, P, P, P, c_int, P, c_int, P, P, P, P, P, P]),
+    "mv_gather_rows": (c_int, [P, c_int, P, P, c_int, P, P]),
+    "mv_argmax_rows": (c_int, [P, c_int, c_int, c_int, P, P]),
+    "mv_k3_spair_errors": (c_int, [P, c_int, c_int, P, P, c_int, c_float, c_float, c_float, P, P, P, P, P, P]),
+}
+
+# enums of include/mvmatch.h
+MV_SAMPLE_BILINEAR_ZEROS = 0
+MV_SAMPLE_BICUBIC_CLAMP = 1
+MV_SAMPLE_ROWS = 2
+MV_DTYPE_BF16 = 0
+MV_DTYPE_TF32 = 1
+MV_SIM_MASKED = -3.0e38
+MV_MAX_THRESHOLDS = 16
+
+_lib = None
+
+
+class MvMatchError(RuntimeError):
+    pass
+
+
+def load(build_if_missing=True):
+    """dlopen libmvmatch.so (building it first when nvcc is available and the file is absent)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise MvMatchError(f"{LIB_PATH} not found; run `python {HERE}/build.py`")
+        from .build import build_lib
+
+        build_lib()
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError here = header / library mismatch: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point; raise MvMatchError with mv_last_error() on failure."""
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        msg = lib.mv_last_error()
+        raise MvMatchError(f"{name} failed with code {rc}: {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    """data pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def host_floats(values):
+    """Small host float array (K, Rt, thresholds) as a ctypes buffer; keep a reference while in use."""
+    vals = [float(v) for v in values]
+    return (c_float * len(vals))(*vals)

@@ -1,0 +1,480 @@
+"""Drop-in for the reference's ``evals/utils/correspondence.py`` backed by libmvmatch.so (sm_100a).
+
+Same function names, argument meaning and return tuples as the reference module
+(/root/reference/evals/utils/correspondence.py, cited per function below); the arithmetic runs in
+three hand-written CUDA kernels reached through the C ABI of include/mvmatch.h:
+
+    kernel 1  sample / upsample + L2-normalise            (csrc/k1_sample.cu)
+    kernel 2  tcgen05 similarity GEMM + row top-2 / column arg-max   (csrc/k2_sim.cu)
+    kernel 3  fp32 distance recompute, ratio test, mutual check, top-k, scoring   (csrc/k3_score.cu)
+
+Inputs may live on the CPU (NAVI / ScanNet callers, evaluate_navi_correspondence.py:149-150,
+render_scannet_correspondence.py:201) or on a CUDA device (SPair caller); results come back on the
+device of the first feature argument, indices as int64, like the reference.  There is no CPU
+implementation here: without a CUDA device every compute entry point raises.
+"""
+import os
+from ctypes import c_float, c_int, c_size_t, c_void_p
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+__all__ = [
+    "faiss_knn", "knn_points", "get_correspondences_ratio_test", "calculate_ratio_test", "get_topk_matches",
+    "get_grid", "grid_to_pointcloud", "sample_pointcloud_features", "argmax_2d", "project_3dto2d", "error_auc",
+    "estimate_correspondence_depth", "estimate_correspondence_xyz", "compute_binned_performance",
+    "set_match_precision", "match_rows", "prepare_depth_side", "prepare_xyz_side", "MatchResult",
+]
+
+# operand type of kernel 2: "bf16" (tcgen05 kind::f16) or "tf32" (kind::tf32); cluster = B-tile multicast width
+_CFG = {
+    "dtype": os.environ.get("MVMATCH_DTYPE", "bf16"),
+    "cluster": int(os.environ.get("MVMATCH_CLUSTER", "1")),
+}
+
+
+def set_match_precision(dtype=None, cluster=None):
+    """Choose kernel 2's operand type ("bf16" | "tf32") and its cluster width (1, 2 or 4)."""
+    if dtype is not None:
+        if dtype not in ("bf16", "tf32"):
+            raise ValueError("dtype must be 'bf16' or 'tf32'")
+        _CFG["dtype"] = dtype
+    if cluster is not None:
+        if cluster not in (1, 2, 4):
+            raise ValueError("cluster must be 1, 2 or 4")
+        _CFG["cluster"] = cluster
+    return dict(_CFG)
+
+
+# ------------------------------------------------------------------------------------------------
+# plumbing
+# ------------------------------------------------------------------------------------------------
+def _device():
+    if not torch.cuda.is_available():
+        raise RuntimeError("mvmatch has no CPU path: a CUDA (sm_100a) device is required")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t, dev):
+    return t.detach().to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+def _empty(shape, dtype, dev):
+    return torch.empty(shape, dtype=dtype, device=dev)
+
+
+def _hwc(feat, prenorm=False):
+    """(C, h, w) fp32 device map -> channel-last (h*w, C); prenorm = F.normalize(feat, dim=channel)."""
+    C, h, w = feat.shape
+    out = _empty((h * w, C), torch.float32, feat.device)
+    scratch = _empty((h * w,), torch.float32, feat.device) if prenorm else None
+    L.call("mv_chw_to_hwc", L.ptr(feat), L.ptr(out), C, h * w, int(prenorm), L.ptr(scratch), _stream())
+    return out
+
+
+def _check_C(C):
+    if C % 8 != 0:
+        raise ValueError(f"feature dimension {C} must be a multiple of 8 for the tensor-core path")
+
+
+def _sample(mode, src, C, h, w, coords, n_dev, n_max, normalize, want_bf16, want_f32, taps=None):
+    """kernel 1.  src: (h*w, C) channel-last (or (n, C) rows for MV_SAMPLE_ROWS)."""
+    dev = src.device
+    o16 = _empty((max(n_max, 1), C), torch.bfloat16, dev) if want_bf16 else None
+    o32 = _empty((max(n_max, 1), C), torch.float32, dev) if want_f32 else None
+    if n_max > 0:
+        L.call("mv_k1_sample_normalize", mode, L.ptr(src), C, h, w, L.ptr(coords), L.ptr(n_dev), n_max, int(normalize),
+               L.ptr(o16), L.ptr(o32), L.ptr(taps), _stream())
+    return o16, o32
+
+
+class MatchResult:
+    """Device-side outputs of one directional match (kernels 2 + 3)."""
+
+    __slots__ = ("k", "k_dev", "sel_src", "sel_dst", "sel_weight", "mutual", "row_idx", "dists", "weight", "col_best")
+
+
+def match_rows(A16, A32, B16, B32, n, m, num_corr, ratio_test=True, n_dev=None, m_dev=None, want_topk=True):
+    """kernel 2 + kernel 3 on prepared rows.
+
+    A16/B16: (n, C)/(m, C) bf16 rows (None when the tf32 path is selected), A32/B32: fp32 rows.
+    Mirrors get_correspondences_ratio_test (correspondence.py:63-102, bidirectional=False):
+    2-NN -> fp32 cosine distances -> ratio weights -> top-num_corr, plus the mutual-NN flag.
+    n, m are the live counts when n_dev/m_dev are None, otherwise upper bounds.
+    """
+    dev = A32.device
+    C = A32.shape[1]
+    tf32 = _CFG["dtype"] == "tf32"
+    st = _stream()
+    res = MatchResult()
+    row_val = _empty((n, 2), torch.float32, dev)
+    row_idx = _empty((n, 2), torch.int32, dev)
+    col_best = _empty((m,), torch.int64, dev)
+    lib = L.load()
+    ws_bytes = lib.mv_k2_workspace_bytes(n, m)
+    ws = _empty((ws_bytes,), torch.uint8, dev)
+    A = A32 if tf32 else A16
+    B = B32 if tf32 else B16
+    L.call("mv_k2_sim_top2", L.ptr(A), L.ptr(B), n, m, C, L.ptr(n_dev), L.ptr(m_dev),
+           L.MV_DTYPE_TF32 if tf32 else L.MV_DTYPE_BF16, _CFG["cluster"], L.ptr(row_val), L.ptr(row_idx),
+           L.ptr(col_best), L.ptr(ws), c_size_t(ws_bytes), st)
+    dists = _empty((n, 2), torch.float32, dev)
+    weight = _empty((n,), torch.float32, dev)
+    mutual = _empty((n,), torch.uint8, dev)
+    L.call("mv_k3_ratio_mutual", L.ptr(A32), L.ptr(B32), C, L.ptr(n_dev), n, L.ptr(row_idx), L.ptr(col_best),
+           int(ratio_test), L.ptr(dists), L.ptr(weight), L.ptr(mutual), st)
+    res.row_idx, res.dists, res.weight, res.mutual, res.col_best = row_idx, dists, weight, mutual, col_best
+    if want_topk:
+        k = min(int(num_corr), n)
+        res.k = k
+        res.sel_src = _empty((max(k, 1),), torch.int32, dev)
+        res.sel_dst = _empty((max(k, 1),), torch.int32, dev)
+        res.sel_weight = _empty((max(k, 1),), torch.float32, dev)
+        res.k_dev = _empty((1,), torch.int32, dev)
+        L.call("mv_k3_topk_matches", L.ptr(weight), L.ptr(row_idx), L.ptr(n_dev), n, int(num_corr), L.ptr(res.sel_src),
+               L.ptr(res.sel_dst), L.ptr(res.sel_weight), L.ptr(res.k_dev), st)
+    return res
+
+
+def _gather(src, idx, k):
+    """rows src[idx[:k]] through the library (src (n, width) fp32, idx int32)."""
+    width = src.shape[1]
+    out = _empty((k, width), torch.float32, src.device)
+    if k > 0:
+        L.call("mv_gather_rows", L.ptr(src), width, L.ptr(idx), None, k, L.ptr(out), _stream())
+    return out
+
+
+def _rows_from_features(F, normalize, dev):
+    """(N, C) features -> (bf16 rows or None, fp32 rows), optionally L2-normalised (correspondence.py:47-48)."""
+    F = _f32(F, dev)
+    n, C = F.shape
+    _check_C(C)
+    want16 = _CFG["dtype"] == "bf16"
+    if not normalize and not want16:
+        return None, F
+    return _sample(L.MV_SAMPLE_ROWS, F, C, 0, 0, None, None, n, normalize, want16, True)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference interface: nearest neighbours
+# ------------------------------------------------------------------------------------------------
+def faiss_knn(query, target, k):
+    """Exact L2 k-NN, k <= 2: (squared L2 distances ascending, int64 indices).  correspondence.py:14-23.
+
+    The search runs on kernel 2 through the identity ||q-t||^2 = ||q||^2 + ||t||^2 - 2 q.t : the rows are
+    extended by (1, -||t||^2/2) split into tf32-exact pieces so that the inner-product order is the L2
+    order; the returned distances are recomputed in fp32 for the winners.
+    """
+    if k not in (1, 2):
+        raise NotImplementedError("the B200 path keeps the two nearest neighbours per query (k <= 2)")
+    dev = _device()
+    in_dev = query.device
+    q = _f32(query, dev)
+    t = _f32(target, dev)
+    n, C = q.shape
+    m = t.shape[0]
+    # extra columns: q' = [q, 1, 1, 1, 0..], t' = [t, h0, h1, h2, 0..] with h0+h1+h2 = -||t||^2/2, each piece
+    # holding <= 10 mantissa bits so the tf32 tensor-core product does not round it
+    half = -0.5 * (t * t).sum(dim=1)
+    pieces = []
+    rem = half.clone()
+    for _ in range(3):
+        mant, expo = torch.frexp(rem)
+        p = torch.ldexp(torch.round(mant * 1024.0) / 1024.0, expo)
+        pieces.append(p)
+        rem = rem - p
+    Cp = ((C + 3 + 7) // 8) * 8
+    qe = torch.zeros((n, Cp), dtype=torch.float32, device=dev)
+    te = torch.zeros((m, Cp), dtype=torch.float32, device=dev)
+    qe[:, :C] = q
+    qe[:, C:C + 3] = 1.0
+    te[:, :C] = t
+    for i, p in enumerate(pieces):
+        te[:, C + i] = p
+    saved = dict(_CFG)
+    try:
+        _CFG["dtype"] = "tf32"
+        r = match_rows(None, qe, None, te, n, m, 0, want_topk=False)
+    finally:
+        _CFG.update(saved)
+    idx = r.row_idx[:, :k].long()
+    d = ((q[:, None, :] - t[idx]) ** 2).sum(dim=-1)
+    if k == 2:  # ascending, like faiss
+        swap = d[:, 1] < d[:, 0]
+        d = torch.where(swap[:, None], d.flip(1), d)
+        idx = torch.where(swap[:, None], idx.flip(1), idx)
+    return d.to(in_dev), idx.to(in_dev)
+
+
+def knn_points(X_f, Y_f, K=1, metric="euclidean"):
+    """(dists (N, K), idx (N, K) int64), K <= 2.  correspondence.py:26-60.
+
+    cosine: rows are L2-normalised, neighbours come from kernel 2 and the distances 1 - cos are
+    recomputed in fp32 by kernel 3, exactly the reference's order of operations (:47-58).
+    euclidean: exact L2 neighbours through faiss_knn, distances = ||x - y||_2 (:55-56).
+    """
+    assert metric in ["cosine", "euclidean"]
+    if K not in (1, 2):
+        raise NotImplementedError("the B200 path keeps the two nearest neighbours per query (K <= 2)")
+    dev = _device()
+    in_dev = X_f.device
+    if metric == "euclidean":
+        _, idx = faiss_knn(X_f, Y_f, K)
+        X = _f32(X_f, dev)
+        Y = _f32(Y_f, dev)
+        d = (Y[idx.to(dev)] - X[:, None, :]).norm(p=2, dim=2)
+        return d.to(in_dev), idx
+    A16, A32 = _rows_from_features(X_f, True, dev)
+    B16, B32 = _rows_from_features(Y_f, True, dev)
+    r = match_rows(A16, A32, B16, B32, A32.shape[0], B32.shape[0], 0, want_topk=False)
+    return r.dists[:, :K].to(in_dev), r.row_idx[:, :K].long().to(in_dev)
+
+
+def get_correspondences_ratio_test(P1_F, P2_F, num_corres, metric="cosine", bidirectional=False, ratio_test=True):
+    """(idx1, idx2, weight): the num_corres best matches by ratio weight.  correspondence.py:63-102.
+
+    bidirectional=True follows the evident intent of the reference's (crashing, :96-98) branch: half the
+    budget in each direction, concatenated.
+    """
+    assert metric in ["cosine", "euclidean"]
+    if metric != "cosine":
+        raise NotImplementedError("only the cosine metric (every reference call site) runs on the B200 path")
+    dev = _device()
+    in_dev = P1_F.device
+    A16, A32 = _rows_from_features(P1_F, True, dev)
+    B16, B32 = _rows_from_features(P2_F, True, dev)
+    n, m = A32.shape[0], B32.shape[0]
+    if not bidirectional:
+        r = match_rows(A16, A32, B16, B32, n, m, num_corres, ratio_test)
+        k = r.k
+        return (r.sel_src[:k].long().to(in_dev), r.sel_dst[:k].long().to(in_dev), r.sel_weight[:k].to(in_dev))
+    r12 = match_rows(A16, A32, B16, B32, n, m, num_corres // 2, ratio_test)
+    r21 = match_rows(B16, B32, A16, A32, m, n, num_corres // 2, ratio_test)
+    idx1 = torch.cat((r12.sel_src[:r12.k], r21.sel_dst[:r21.k])).long()
+    idx2 = torch.cat((r12.sel_dst[:r12.k], r21.sel_src[:r21.k])).long()
+    w = torch.cat((r12.sel_weight[:r12.k], r21.sel_weight[:r21.k]))
+    return idx1.to(in_dev), idx2.to(in_dev), w.to(in_dev)
+
+
+def calculate_ratio_test(dists):
+    """weight = 1 - d0 / d1 with both 1e-9 clamps.  correspondence.py:105-121 (runs inside kernel 3 on the
+    matching path; this torch form serves callers that hold a (…, 2) distance tensor)."""
+    d = dists.clamp(min=1e-9)
+    return 1 - d[..., 0] / d[..., 1].clamp(min=1e-9)
+
+
+def get_topk_matches(dists, idx, num_corres):
+    """(idx_source, idx_target, dist) of the num_corres largest entries, sorted.  correspondence.py:125-129."""
+    dev = _device()
+    in_dev = dists.device
+    w = _f32(dists, dev)
+    n = w.shape[-1]
+    pairs = torch.stack((idx.to(dev).to(torch.int32), torch.zeros(n, dtype=torch.int32, device=dev)), dim=1).contiguous()
+    k = min(int(num_corres), n)
+    src = _empty((max(k, 1),), torch.int32, dev)
+    dst = _empty((max(k, 1),), torch.int32, dev)
+    val = _empty((max(k, 1),), torch.float32, dev)
+    L.call("mv_k3_topk_matches", L.ptr(w), L.ptr(pairs), None, n, int(num_corres), L.ptr(src), L.ptr(dst), L.ptr(val),
+           None, _stream())
+    return src[:k].long().to(in_dev), dst[:k].long().to(in_dev), val[:k].to(in_dev)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference interface: geometry helpers
+# ------------------------------------------------------------------------------------------------
+def get_grid(H, W):
+    """(3, H, W) pixel-centre grid (x + .5, y + .5, 1).  correspondence.py:132-144."""
+    xs = torch.linspace(0.5, W - 0.5, W).view(1, W).expand(H, W)
+    ys = torch.linspace(0.5, H - 0.5, H).view(H, 1).expand(H, W)
+    return torch.stack((xs, ys, torch.ones(H, W)), dim=0).contiguous()
+
+
+def grid_to_pointcloud(K_inv, depth, grid=None):
+    """(H*W, 3) back-projection K^-1 (depth * grid).  correspondence.py:147-161."""
+    _, H, W = depth.shape
+    if grid is not None:  # caller-supplied grid: plain torch, same formula
+        return (K_inv @ (depth * grid).reshape(3, H * W)).permute(1, 0)
+    dev = _device()
+    in_dev = depth.device
+    d = _f32(depth, dev)
+    Ki = L.host_floats(K_inv.detach().float().cpu().reshape(-1).tolist())
+    out = _empty((H * W, 3), torch.float32, dev)
+    L.call("mv_geom_backproject", L.ptr(d), H, W, Ki, L.ptr(out), _stream())
+    return out.to(in_dev)
+
+
+def sample_pointcloud_features(feats, K, pc, image_shape):
+    """(n, C) bilinear samples of feats (C, h, w) at the projections of pc.  correspondence.py:164-176."""
+    H, W = image_shape
+    dev = _device()
+    in_dev = feats.device
+    f = _f32(feats, dev)
+    C, h, w = f.shape
+    _check_C(C)
+    p = _f32(pc, dev)
+    n = p.shape[0]
+    Kh = L.host_floats(K.detach().float().cpu().reshape(-1).tolist())
+    xyz = _empty((max(n, 1), 3), torch.float32, dev)
+    coords = _empty((max(n, 1), 2), torch.float32, dev)
+    if n > 0:
+        L.call("mv_geom_project_coords", L.ptr(p), None, None, n, Kh, int(H), int(W), h, w, L.ptr(xyz), L.ptr(coords),
+               _stream())
+    _, o32 = _sample(L.MV_SAMPLE_BILINEAR_ZEROS, _hwc(f), C, h, w, coords, None, n, False, False, True)
+    return o32[:n].to(in_dev)
+
+
+def argmax_2d(x, max_value=True):
+    """(…, 2) int64 (col, row) of the arg-max (arg-min) over the last two dims.  correspondence.py:179-190."""
+    dev = _device()
+    in_dev = x.device
+    h, w = x.shape[-2:]
+    lead = x.shape[:-2]
+    flat = _f32(x, dev).reshape(-1, h * w)
+    rows = flat.shape[0]
+    out = _empty((max(rows, 1),), torch.int32, dev)
+    L.call("mv_argmax_rows", L.ptr(flat), rows, h * w, int(bool(max_value)), L.ptr(out), _stream())
+    idx = out[:rows].long()
+    xy = torch.stack((idx % w, idx // w), dim=-1).reshape(*lead, 2)
+    return xy.to(in_dev)
+
+
+def project_3dto2d(xyz, K_mat):
+    """uv = (xyz K^T)[:, :2] / max(z', 1e-9).  correspondence.py:193-196 (same arithmetic inside mv_k3_score)."""
+    uvd = xyz @ K_mat.transpose(-1, -2)
+    return uvd[:, :2] / uvd[:, 2:3].clamp(min=1e-9)
+
+
+def error_auc(errors, thresholds):
+    """Area under the recall-vs-error curve up to each threshold, normalised.  correspondence.py:199-215."""
+    errs = [0] + sorted(list(errors))
+    recall = list(np.linspace(0, 1, len(errs)))
+    trapz = getattr(np, "trapezoid", None) or np.trapz
+    out = []
+    for thr in thresholds:
+        last = np.searchsorted(errs, thr)
+        ys = recall[:last] + [recall[last - 1]]
+        xs = errs[:last] + [thr]
+        out.append(trapz(ys, xs) / thr)
+    return out
+
+
+def compute_binned_performance(y, x, x_bins):
+    """mean of y over x in [x_bins[i], x_bins[i+1]).  correspondence.py:266-277."""
+    return [y[(x >= lo) * (x < hi)].mean() for lo, hi in zip(x_bins[:-1], x_bins[1:])]
+
+
+# ------------------------------------------------------------------------------------------------
+# reference interface: the two dense helpers
+# ------------------------------------------------------------------------------------------------
+class _Side:
+    """One image of a pair after kernel 1: compacted geometry + feature rows."""
+
+    __slots__ = ("n", "n_dev", "xyz", "uv", "rows16", "rows32", "valid_idx", "taps")
+
+
+def prepare_depth_side(feat, depth, K, Kinv, dev, sync=True, want_taps=False):
+    """ScanNet-style preparation of one image.  correspondence.py:219-225, :147-176, :47-48.
+
+    back-project depth -> keep z > 0 (row-major) -> project with K -> bilinear grid_sample coordinates
+    (align_corners=False) -> kernel 1 (sample + L2 normalise).  sync=False keeps n on the device.
+    """
+    f = _f32(feat, dev)
+    d = _f32(depth, dev)
+    C, h, w = f.shape
+    _check_C(C)
+    H, W = d.shape[-2:]
+    st = _stream()
+    xyz_all = _empty((H * W, 3), torch.float32, dev)
+    L.call("mv_geom_backproject", L.ptr(d), H, W, Kinv, L.ptr(xyz_all), st)
+    valid_idx = _empty((H * W,), torch.int32, dev)
+    n_dev = _empty((1,), torch.int32, dev)
+    L.call("mv_compact_valid", c_void_p(xyz_all.data_ptr() + 8), 3, H * W, L.ptr(valid_idx), L.ptr(n_dev), st)
+    s = _Side()
+    s.n_dev = n_dev
+    s.valid_idx = valid_idx
+    s.n = int(n_dev.item()) if sync else H * W
+    nd = None if sync else n_dev
+    s.xyz = _empty((max(s.n, 1), 3), torch.float32, dev)
+    coords = _empty((max(s.n, 1), 2), torch.float32, dev)
+    if s.n > 0:
+        L.call("mv_geom_project_coords", L.ptr(xyz_all), L.ptr(valid_idx), L.ptr(nd), s.n, K, H, W, h, w, L.ptr(s.xyz),
+               L.ptr(coords), st)
+    s.taps = _empty((max(s.n, 1), 2), torch.int32, dev) if want_taps else None
+    s.uv = None
+    s.rows16, s.rows32 = _sample(L.MV_SAMPLE_BILINEAR_ZEROS, _hwc(f), C, h, w, coords, nd, s.n, True,
+                                 _CFG["dtype"] == "bf16", True, s.taps)
+    return s
+
+
+def prepare_xyz_side(feat, xyz_grid, dev, sync=True, want_taps=False):
+    """NAVI-style preparation of one image.  correspondence.py:240-252, :47-48.
+
+    bicubic upsample of feat to the xyz grid's size evaluated only at the pixels with xyz_grid[2] > 0
+    (row-major), + their xyz and pixel-centre uv, + kernel 1's L2 normalisation.
+    """
+    f = _f32(feat, dev)
+    g = _f32(xyz_grid, dev)
+    C, h, w = f.shape
+    _check_C(C)
+    _, H, W = g.shape
+    st = _stream()
+    valid_idx = _empty((H * W,), torch.int32, dev)
+    n_dev = _empty((1,), torch.int32, dev)
+    L.call("mv_compact_valid", c_void_p(g.data_ptr() + 2 * H * W * 4), 1, H * W, L.ptr(valid_idx), L.ptr(n_dev), st)
+    s = _Side()
+    s.n_dev = n_dev
+    s.valid_idx = valid_idx
+    s.n = int(n_dev.item()) if sync else H * W
+    nd = None if sync else n_dev
+    s.xyz = _empty((max(s.n, 1), 3), torch.float32, dev)
+    s.uv = _empty((max(s.n, 1), 2), torch.float32, dev)
+    coords = _empty((max(s.n, 1), 2), torch.float32, dev)
+    if s.n > 0:
+        L.call("mv_geom_grid_coords", L.ptr(g), L.ptr(valid_idx), L.ptr(nd), s.n, H, W, h, w, L.ptr(s.xyz), L.ptr(s.uv),
+               L.ptr(coords), st)
+    s.taps = _empty((max(s.n, 1), 2), torch.int32, dev) if want_taps else None
+    s.rows16, s.rows32 = _sample(L.MV_SAMPLE_BICUBIC_CLAMP, _hwc(f), C, h, w, coords, nd, s.n, True,
+                                 _CFG["dtype"] == "bf16", True, s.taps)
+    return s
+
+
+def _host_mat(M):
+    return L.host_floats(M.detach().float().cpu().reshape(-1).tolist())
+
+
+def estimate_correspondence_depth(feat_0, feat_1, depth_0, depth_1, K, num_corr=500):
+    """(corr_xyz0 (k, 3), corr_xyz1 (k, 3), corr_dist (k,)).  correspondence.py:218-232."""
+    dev = _device()
+    in_dev = feat_0.device
+    Kc = K.detach().float().cpu()
+    Kh, Kinv = _host_mat(Kc), _host_mat(Kc.inverse())
+    s0 = prepare_depth_side(feat_0, depth_0, Kh, Kinv, dev)
+    s1 = prepare_depth_side(feat_1, depth_1, Kh, Kinv, dev)
+    if s0.n == 0 or s1.n < 2:
+        raise RuntimeError(f"too few valid points to match ({s0.n} vs {s1.n})")
+    r = match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, s0.n, s1.n, num_corr)
+    k = r.k
+    return (_gather(s0.xyz, r.sel_src, k).to(in_dev), _gather(s1.xyz, r.sel_dst, k).to(in_dev),
+            r.sel_weight[:k].to(in_dev))
+
+
+def estimate_correspondence_xyz(feat_0, feat_1, xyz_grid_0, xyz_grid_1, num_corr=500, ratio_test=True):
+    """(c_xyz0, c_xyz1, c_dist, c_uv0, c_uv1).  correspondence.py:235-263."""
+    dev = _device()
+    in_dev = feat_0.device
+    s0 = prepare_xyz_side(feat_0, xyz_grid_0, dev)
+    s1 = prepare_xyz_side(feat_1, xyz_grid_1, dev)
+    if s0.n == 0 or s1.n < 2:
+        raise RuntimeError(f"too few valid points to match ({s0.n} vs {s1.n})")
+    r = match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, s0.n, s1.n, num_corr, ratio_test)
+    k = r.k
+    return (_gather(s0.xyz, r.sel_src, k).to(in_dev), _gather(s1.xyz, r.sel_dst, k).to(in_dev),
+            r.sel_weight[:k].to(in_dev), _gather(s0.uv, r.sel_src, k).to(in_dev),
+            _gather(s1.uv, r.sel_dst, k).to(in_dev))

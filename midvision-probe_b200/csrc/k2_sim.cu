@@ -1,0 +1,496 @@
+// k2_sim.cu -- kernel 2: S = A @ B^T on tcgen05 tensor cores with the row top-2 and the column arg-max
+// fused into the epilogue.  The n x m similarity matrix only ever exists as 128 x 256 fp32 tiles in TMEM.
+//
+// Replaces, for L2-normalised rows (where the L2 order is the cosine order, correspondence.py:27-43):
+//   evals/utils/correspondence.py:14-23   faiss.GpuIndexFlatL2(res, C).add(target).search(query, k<=2)
+//   evaluate_spair_correspondence.py:82-83 einsum("k f, f h w -> k h w") + argmax_2d   (row arg-max)
+//
+// Structure (one persistent CTA per SM, 8 warps, warp-specialised):
+//   warp 0      TMA producer : A tile 128 x 128B and B tile 256 x 128B per k-block into a 4-stage
+//                              128B-swizzled shared-memory ring; with MC > 1 the B tile is loaded in MC
+//                              slices, each multicast to the MC CTAs of the cluster (they work on MC
+//                              consecutive row blocks and the same column tile)
+//   warp 1      MMA issuer   : one thread, tcgen05.mma M=128 N=256 K=16 (bf16) / K=8 (tf32), fp32
+//                              accumulators in TMEM, two accumulator buffers (2 x 256 = all 512 columns)
+//   warp 2      TMEM allocator
+//   warps 4..7  epilogue     : tcgen05.ld 32 rows x 32 columns per warp; thread = one row of S.
+//                              rows   : running (max1, idx1, max2, idx2) in registers across the column
+//                                       tiles of a row block; a chunk is only scanned when its maximum
+//                                       beats the current second best
+//                              columns: warp-wide max in one CREDUX.MAX.F32 + ballot for the owning row,
+//                                       4 warps combined through shared memory, then one packed
+//                                       (orderable value << 32 | ~row) atomicMax per column per tile,
+//                                       skipped when a plain load already shows a better entry
+// Scheduling: the (super row block, column tile) list is cut into gridDim/MC equal contiguous ranges, so
+// every SM gets the same number of tiles (+-1); a row block that is split between CTAs leaves partial
+// top-2 records in the workspace which k2_merge_rows_kernel folds (ties: lower column).
+#include <cuda.h>
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "sm100_ptx.cuh"
+
+namespace {
+
+using namespace sm100;
+
+constexpr int BM = 128;           // rows of S per tile (UMMA M)
+constexpr int BN = 256;           // columns of S per tile (UMMA N)
+constexpr int ROW_BYTES = 128;    // one swizzle-128B row: 64 bf16 or 32 fp32 along K
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * ROW_BYTES;  // 16 KB
+constexpr int B_STAGE_BYTES = BN * ROW_BYTES;  // 32 KB
+constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+constexpr int K2_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr int COL_SMEM_BYTES = 2 * 4 * BN * 8;  // [2 buffers][4 warps][256 columns] (max bits, ballot)
+constexpr int K2_SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + COL_SMEM_BYTES + 256 /*barriers*/;
+
+struct K2Sched {
+  // tiles are numbered t = sb * n_ct + ct; cluster c owns [c*T/G, (c+1)*T/G)
+  unsigned long long T;  // n_sb * n_ct
+  int G;                 // clusters in the grid
+  int n_ct;              // column tiles
+  int n_sb;              // super row blocks (MC * 128 rows)
+  int p_max;             // most partial records any row can have
+};
+
+struct K2Params {
+  K2Sched s;
+  const int32_t* n_dev;
+  const int32_t* m_dev;
+  int n_max, m_max, kblocks;
+  float4* partial;  // (n_sb * MC * 128, p_max) records {max1, idx1, max2, idx2}
+  unsigned long long* col_best;
+};
+
+__host__ __device__ inline unsigned long long sched_begin(const K2Sched& s, int c) {
+  return (unsigned long long)c * s.T / (unsigned long long)s.G;
+}
+// cluster that owns tile t
+__host__ __device__ inline int sched_owner(const K2Sched& s, unsigned long long t) {
+  return (int)(((t + 1) * (unsigned long long)s.G + s.T - 1) / s.T) - 1;
+}
+
+__device__ __forceinline__ bool better(float x, int j, float y, int k) {
+  return x > y || (x == y && (unsigned)j < (unsigned)k);
+}
+
+struct __align__(8) Barriers {
+  unsigned long long full[STAGES];
+  unsigned long long empty[STAGES];
+  unsigned long long tmem_full[2];
+  unsigned long long tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+template <bool TF32, int MC>
+__global__ void __launch_bounds__(K2_THREADS, 1)
+    k2_sim_top2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, K2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  uint2* col_smem = reinterpret_cast<uint2*>(smem_al + STAGES * STAGE_BYTES);
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_al + STAGES * STAGE_BYTES + COL_SMEM_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (MC > 1) ? (int)cluster_ctarank() : 0;
+  const int cluster_id = blockIdx.x / MC;
+  const int n = p.n_dev ? min(*p.n_dev, p.n_max) : p.n_max;
+  const int m = p.m_dev ? min(*p.m_dev, p.m_max) : p.m_max;
+
+  const unsigned long long t_beg = sched_begin(p.s, cluster_id), t_end = sched_begin(p.s, cluster_id + 1);
+  constexpr int KE = TF32 ? 32 : 64;  // K elements per 128-byte row
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(smem_u32(&bars->full[s]), 1);
+      mbar_init(smem_u32(&bars->empty[s]), MC);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(smem_u32(&bars->tmem_full[a]), 1);
+      mbar_init(smem_u32(&bars->tmem_empty[a]), 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 2) tmem_alloc_512(smem_u32(&bars->tmem_base));
+  tc_fence_before();
+  if (MC > 1) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(&bars->tmem_base);
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (unsigned long long t = t_beg; t < t_end; ++t) {
+        const int sb = (int)(t / (unsigned)p.s.n_ct), ct = (int)(t - (unsigned long long)sb * p.s.n_ct);
+        const int row0 = (sb * MC + rank) * BM, col0 = ct * BN;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u);
+          const uint32_t full = smem_u32(&bars->full[stage]);
+          const uint32_t sa = smem_base + stage * STAGE_BYTES, sbm = sa + A_STAGE_BYTES;
+          mbar_arrive_expect_tx(full, STAGE_BYTES);
+          tma_load_2d(sa, &tmA, full, kb * KE, row0);
+          if (MC == 1) {
+            tma_load_2d(sbm, &tmB, full, kb * KE, col0);
+          } else {
+            constexpr int SLICE = BN / MC;
+            tma_load_2d_mc(sbm + rank * SLICE * ROW_BYTES, &tmB, full, kb * KE, col0 + rank * SLICE,
+                           (uint16_t)((1u << MC) - 1));
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(TF32 ? 2 : 1, BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (unsigned long long t = t_beg; t < t_end; ++t) {
+        mbar_wait(smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+        for (int kb = 0; kb < p.kblocks; ++kb) {
+          mbar_wait(smem_u32(&bars->full[stage]), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * STAGE_BYTES, sbm = sa + A_STAGE_BYTES;
+          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sbm);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // 4 x 32 bytes along K inside the 128-byte swizzle row
+            umma_ss<TF32>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
+          if (MC == 1) umma_commit(smem_u32(&bars->empty[stage]));
+          else umma_commit_mc(smem_u32(&bars->empty[stage]), (uint16_t)((1u << MC) - 1));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(smem_u32(&bars->tmem_full[acc]));
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===================================== epilogue =========================================
+    const int ew = warp & 3;           // TMEM lane quarter this warp may read
+    const int e = ew * 32 + lane;      // row inside the tile; also column-combine slot
+    float m1 = -CUDART_INF_F, m2 = -CUDART_INF_F;
+    int i1 = -1, i2 = -1;
+    int cur_sb = -1;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+
+    auto flush = [&](int sb) {
+      const int c_first = sched_owner(p.s, (unsigned long long)sb * p.s.n_ct);
+      const size_t row = (size_t)(sb * MC + rank) * BM + e;
+      p.partial[row * p.s.p_max + (cluster_id - c_first)] =
+          make_float4(m1, __int_as_float(i1), m2, __int_as_float(i2));
+    };
+
+    for (unsigned long long t = t_beg; t < t_end; ++t) {
+      const int sb = (int)(t / (unsigned)p.s.n_ct), ct = (int)(t - (unsigned long long)sb * p.s.n_ct);
+      if (sb != cur_sb) {
+        if (cur_sb >= 0) flush(cur_sb);
+        m1 = m2 = -CUDART_INF_F;
+        i1 = i2 = -1;
+        cur_sb = sb;
+      }
+      const int row0 = (sb * MC + rank) * BM, col0 = ct * BN;
+      const bool edge = (row0 + BM > n) || (col0 + BN > m);
+      const bool row_ok = row0 + e < n;
+      uint2* colw = col_smem + (size_t)acc * (4 * BN) + ew * BN;
+
+      mbar_wait(smem_u32(&bars->tmem_full[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)acc * BN + ((uint32_t)(ew * 32) << 16);
+
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 32; ++ch) {
+        float v[32];
+        tmem_ld_32x32(taddr + ch * 32, v);
+        const int cb = col0 + ch * 32;
+        if (edge) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = (row_ok && cb + q < m) ? v[q] : -CUDART_INF_F;
+        }
+        // ---- rows: this thread's row against its running top-2
+        float cm = v[0];
+#pragma unroll
+        for (int q = 1; q < 32; ++q) cm = fmaxf(cm, v[q]);
+        if (cm > m2) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) {
+            const float x = v[q];
+            if (x > m2) {
+              if (x > m1) { m2 = m1; i2 = i1; m1 = x; i1 = cb + q; }
+              else { m2 = x; i2 = cb + q; }
+            }
+          }
+        }
+        // ---- columns: max over the warp's 32 rows and which row holds it
+#pragma unroll
+        for (int q = 0; q < 32; q += 2) {
+          const float x0 = warp_max_f32(v[q]), x1 = warp_max_f32(v[q + 1]);
+          const uint32_t b0 = __ballot_sync(0xffffffffu, v[q] == x0);
+          const uint32_t b1 = __ballot_sync(0xffffffffu, v[q + 1] == x1);
+          if (lane == 0)
+            *reinterpret_cast<uint4*>(colw + ch * 32 + q) = make_uint4(__float_as_uint(x0), b0, __float_as_uint(x1), b1);
+        }
+      }
+      // accumulator drained: hand the TMEM buffer back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[acc]));
+
+      // combine the 4 warps' column results; thread e owns columns e and e + 128
+      named_bar_sync(1, 128);
+      const uint2* colr = col_smem + (size_t)acc * (4 * BN);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int c = e + h * 128;
+        float best = -CUDART_INF_F;
+        int brow = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          const uint2 r = colr[w * BN + c];
+          const float x = __uint_as_float(r.x);
+          if (x > best) { best = x; brow = w * 32 + __ffs((int)r.y) - 1; }
+        }
+        const int col = col0 + c;
+        if (best > -CUDART_INF_F && col < m) {
+          const unsigned long long packed =
+              ((unsigned long long)f32_orderable(best) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)(row0 + brow));
+          unsigned long long* dst = p.col_best + col;
+          if (packed > __ldcg(dst)) atomicMax(dst, packed);
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+    if (cur_sb >= 0) flush(cur_sb);
+  }
+
+  // ---- teardown
+  __syncwarp();
+  tc_fence_before();
+  if (MC > 1) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_512(tmem_base);
+  }
+}
+
+// fold the partial top-2 records of every row; write (n_max, 2) value / index pairs
+template <int MC>
+__global__ void k2_merge_rows_kernel(K2Sched s, const float4* __restrict__ partial, const int32_t* __restrict__ n_dev,
+                                     int n_max, float* __restrict__ row_val, int32_t* __restrict__ row_idx) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_max) return;
+  const int n = n_dev ? min(*n_dev, n_max) : n_max;
+  float m1 = -CUDART_INF_F, m2 = -CUDART_INF_F;
+  int i1 = -1, i2 = -1;
+  if (i < n) {
+    const int sb = i / (BM * MC);
+    const int c_first = sched_owner(s, (unsigned long long)sb * s.n_ct);
+    const int c_last = sched_owner(s, (unsigned long long)(sb + 1) * s.n_ct - 1);
+    for (int q = 0; q <= c_last - c_first; ++q) {
+      const float4 r = partial[(size_t)i * s.p_max + q];
+      const float xs[2] = {r.x, r.z};
+      const int js[2] = {__float_as_int(r.y), __float_as_int(r.w)};
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (js[u] < 0) continue;
+        if (better(xs[u], js[u], m1, i1)) { m2 = m1; i2 = i1; m1 = xs[u]; i1 = js[u]; }
+        else if (better(xs[u], js[u], m2, i2)) { m2 = xs[u]; i2 = js[u]; }
+      }
+    }
+  }
+  row_val[2 * (size_t)i + 0] = i1 >= 0 ? m1 : MV_MASKED_F;
+  row_val[2 * (size_t)i + 1] = i2 >= 0 ? m2 : MV_MASKED_F;
+  row_idx[2 * (size_t)i + 0] = i1;
+  row_idx[2 * (size_t)i + 1] = i2;
+}
+
+__global__ void k2_unpack_col_kernel(const unsigned long long* __restrict__ col_best, int m, float* __restrict__ col_val,
+                                     int32_t* __restrict__ col_idx) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const unsigned long long pk = col_best[j];
+  if (pk == 0ull) {
+    if (col_val) col_val[j] = MV_MASKED_F;
+    if (col_idx) col_idx[j] = -1;
+  } else {
+    if (col_val) col_val[j] = orderable_f32((uint32_t)(pk >> 32));
+    if (col_idx) col_idx[j] = (int32_t)(0xffffffffu - (uint32_t)(pk & 0xffffffffull));
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// (rows, C) row-major operand -> tensor map with a (box_rows x 128 bytes) 128B-swizzled box
+int make_operand_map(CUtensorMap* tm, const void* base, int rows, int C, bool tf32, int box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  MV_REQUIRE(enc, MV_E_DRIVER, "mv_k2_sim_top2: cuTensorMapEncodeTiled is not available from this driver");
+  const int esz = tf32 ? 4 : 2;
+  cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)C * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(ROW_BYTES / esz), (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  MV_REQUIRE(r == CUDA_SUCCESS, MV_E_DRIVER, "mv_k2_sim_top2: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
+  return MV_OK;
+}
+
+K2Sched make_sched(int n_max, int m_max, int mc, int grid) {
+  K2Sched s;
+  s.n_sb = (n_max + BM * mc - 1) / (BM * mc);
+  s.n_ct = (m_max + BN - 1) / BN;
+  s.T = (unsigned long long)s.n_sb * s.n_ct;
+  s.G = grid / mc;
+  s.p_max = 1;
+  for (int sb = 0; sb < s.n_sb; ++sb) {
+    const int a = sched_owner(s, (unsigned long long)sb * s.n_ct);
+    const int b = sched_owner(s, (unsigned long long)(sb + 1) * s.n_ct - 1);
+    if (b - a + 1 > s.p_max) s.p_max = b - a + 1;
+  }
+  return s;
+}
+
+int pick_mc(int cta_pair) { return cta_pair == 0 ? 1 : (cta_pair >= 4 ? 4 : 2); }
+
+int k2_grid(int mc) {
+  int sms = mv_sm_count();
+  return (sms / mc) * mc;
+}
+
+template <bool TF32, int MC>
+int launch_k2(const CUtensorMap& tmA, const CUtensorMap& tmB, const K2Params& p, int grid, cudaStream_t st) {
+  auto kern = k2_sim_top2_kernel<TF32, MC>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    MV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_BYTES));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(K2_THREADS);
+  cfg.dynamicSmemBytes = K2_SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = MC;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MV_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, p));
+  return MV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t mv_k2_workspace_bytes(int n_max, int m_max) {
+  if (n_max <= 0 || m_max <= 0) return 256;
+  size_t worst = 0;
+  for (int mc = 1; mc <= 4; mc *= 2) {
+    K2Sched s = make_sched(n_max, m_max, mc, k2_grid(mc));
+    size_t b = (size_t)s.n_sb * mc * BM * s.p_max * sizeof(float4);
+    if (b > worst) worst = b;
+  }
+  return worst + 256;
+}
+
+int mv_k2_sim_top2(const void* A, const void* B, int n_max, int m_max, int C, const int32_t* n_dev,
+                   const int32_t* m_dev, int dtype, int cta_pair, float* row_val, int32_t* row_idx,
+                   unsigned long long* col_best, void* workspace, size_t workspace_bytes, mv_stream_t stream) {
+  MV_REQUIRE(A && B && row_val && row_idx && col_best && workspace, MV_E_ARG, "mv_k2_sim_top2: null pointer");
+  MV_REQUIRE(dtype == MV_DTYPE_BF16 || dtype == MV_DTYPE_TF32, MV_E_ARG, "mv_k2_sim_top2: unknown dtype %d", dtype);
+  MV_REQUIRE(n_max > 0 && m_max > 0 && C > 0, MV_E_ARG, "mv_k2_sim_top2: sizes must be positive");
+  MV_REQUIRE(n_max <= (1 << 20) && m_max <= (1 << 20), MV_E_RANGE, "mv_k2_sim_top2: at most 2^20 rows per side");
+  const bool tf32 = dtype == MV_DTYPE_TF32;
+  MV_REQUIRE(C % (tf32 ? 4 : 8) == 0, MV_E_ALIGN, "mv_k2_sim_top2: C=%d must be a multiple of %d", C, tf32 ? 4 : 8);
+  MV_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)workspace & 15) == 0, MV_E_ALIGN,
+             "mv_k2_sim_top2: A, B and workspace must be 16-byte aligned");
+  int dev = 0, cc = 0;
+  MV_CUDA(cudaGetDevice(&dev));
+  MV_CUDA(cudaDeviceGetAttribute(&cc, cudaDevAttrComputeCapabilityMajor, dev));
+  MV_REQUIRE(cc == 10, MV_E_ARCH, "mv_k2_sim_top2: needs an sm_100 device (found compute capability %d.x)", cc);
+
+  const int mc = pick_mc(cta_pair);
+  const int grid = k2_grid(mc);
+  K2Params p;
+  p.s = make_sched(n_max, m_max, mc, grid);
+  const size_t need = (size_t)p.s.n_sb * mc * BM * p.s.p_max * sizeof(float4);
+  MV_REQUIRE(workspace_bytes >= need, MV_E_WORKSPACE, "mv_k2_sim_top2: workspace has %zu bytes, %zu needed",
+             workspace_bytes, need);
+  p.n_dev = n_dev;
+  p.m_dev = m_dev;
+  p.n_max = n_max;
+  p.m_max = m_max;
+  const int ke = tf32 ? 32 : 64;
+  p.kblocks = (C + ke - 1) / ke;
+  p.partial = reinterpret_cast<float4*>(workspace);
+  p.col_best = col_best;
+
+  CUtensorMap tmA, tmB;
+  int rc = make_operand_map(&tmA, A, n_max, C, tf32, BM);
+  if (rc) return rc;
+  rc = make_operand_map(&tmB, B, m_max, C, tf32, BN / mc);
+  if (rc) return rc;
+
+  cudaStream_t st = mv_cuda_stream(stream);
+  MV_CUDA(cudaMemsetAsync(col_best, 0, (size_t)m_max * sizeof(unsigned long long), st));
+  if (tf32) {
+    if (mc == 1) rc = launch_k2<true, 1>(tmA, tmB, p, grid, st);
+    else if (mc == 2) rc = launch_k2<true, 2>(tmA, tmB, p, grid, st);
+    else rc = launch_k2<true, 4>(tmA, tmB, p, grid, st);
+  } else {
+    if (mc == 1) rc = launch_k2<false, 1>(tmA, tmB, p, grid, st);
+    else if (mc == 2) rc = launch_k2<false, 2>(tmA, tmB, p, grid, st);
+    else rc = launch_k2<false, 4>(tmA, tmB, p, grid, st);
+  }
+  if (rc) return rc;
+  const int mt = 256;
+  if (mc == 1) k2_merge_rows_kernel<1><<<(n_max + mt - 1) / mt, mt, 0, st>>>(p.s, p.partial, n_dev, n_max, row_val, row_idx);
+  else if (mc == 2) k2_merge_rows_kernel<2><<<(n_max + mt - 1) / mt, mt, 0, st>>>(p.s, p.partial, n_dev, n_max, row_val, row_idx);
+  else k2_merge_rows_kernel<4><<<(n_max + mt - 1) / mt, mt, 0, st>>>(p.s, p.partial, n_dev, n_max, row_val, row_idx);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+int mv_k2_unpack_col(const unsigned long long* col_best, int m, float* col_val, int32_t* col_idx, mv_stream_t stream) {
+  MV_REQUIRE(col_best && (col_val || col_idx), MV_E_ARG, "mv_k2_unpack_col: null pointer");
+  MV_REQUIRE(m >= 0, MV_E_ARG, "mv_k2_unpack_col: negative m");
+  if (m == 0) return MV_OK;
+  k2_unpack_col_kernel<<<(m + 255) / 256, 256, 0, mv_cuda_stream(stream)>>>(col_best, m, col_val, col_idx);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,456 @@
+// k3_score.cu -- kernel 3 of the matching path: everything after the nearest-neighbour search.
+//
+//   mv_k3_ratio_mutual   fp32 recompute of the two cosine distances per query, re-rank, Lowe ratio
+//                        weight, mutual-nearest-neighbour flag
+//   mv_k3_topk_matches   the num_corr largest weights, sorted (radix select + bitonic sort, one CTA)
+//   mv_k3_score          Rt transform, K projection, 3-D / 2-D errors, integer threshold hit counts
+//   mv_gather_rows       row gather for the helper's return tuples
+//   mv_k3_spair_errors   SPair keypoint error matrix, error_same / error_nn, PCK hit counts
+//
+// Reference behaviour being reproduced (file:line in /root/reference):
+//   evals/utils/correspondence.py:53-58    X_f_nn = Y_f[X_nn]; dists = 1 - cosine_similarity(...)
+//   evals/utils/correspondence.py:72-77    idx_1[..., 0]; ratio weights or dists[:, 0]
+//   evals/utils/correspondence.py:105-121  calculate_ratio_test (both clamps at 1e-9)
+//   evals/utils/correspondence.py:125-129  get_topk_matches (torch.topk, sorted descending)
+//   evals/utils/correspondence.py:193-196  project_3dto2d
+//   evals/utils/transformations.py:27-36   transform_points_Rt
+//   evaluate_navi_correspondence.py:186-212, render_scannet_correspondence.py:211-217, :253-264  errors, recall
+//   evaluate_spair_correspondence.py:83-98, :121  SPair errors and PCK
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr float COS_EPS = 1e-8f;     // torch.nn.functional.cosine_similarity default eps
+constexpr float RATIO_CLAMP = 1e-9f; // calculate_ratio_test clamps
+constexpr float MISSING_DIST = 2.0f; // distance reported for a candidate that does not exist (m < 2)
+
+// ------------------------------------------------------------------------------------------
+// ratio / mutual: one warp per query row
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k3_ratio_mutual_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                              int C, const int32_t* __restrict__ n_dev, int n_max,
+                                                              int32_t* __restrict__ row_idx,
+                                                              const unsigned long long* __restrict__ col_best,
+                                                              int ratio_test, float* __restrict__ dists,
+                                                              float* __restrict__ weight, uint8_t* __restrict__ mutual) {
+  const int n = n_dev ? min(*n_dev, n_max) : n_max;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= n) return;
+  int j0 = row_idx[2 * (size_t)i], j1 = row_idx[2 * (size_t)i + 1];
+  const float4* x = reinterpret_cast<const float4*>(A + (size_t)i * C);
+  const float4* y0 = reinterpret_cast<const float4*>(B + (size_t)max(j0, 0) * C);
+  const float4* y1 = reinterpret_cast<const float4*>(B + (size_t)max(j1, 0) * C);
+  float xx = 0.f, aa = 0.f, bb = 0.f, xa = 0.f, xb = 0.f;
+  for (int c = lane; c < (C >> 2); c += 32) {
+    const float4 v = __ldg(x + c), a = __ldg(y0 + c), b = __ldg(y1 + c);
+    xx = fmaf(v.x, v.x, xx); xx = fmaf(v.y, v.y, xx); xx = fmaf(v.z, v.z, xx); xx = fmaf(v.w, v.w, xx);
+    aa = fmaf(a.x, a.x, aa); aa = fmaf(a.y, a.y, aa); aa = fmaf(a.z, a.z, aa); aa = fmaf(a.w, a.w, aa);
+    bb = fmaf(b.x, b.x, bb); bb = fmaf(b.y, b.y, bb); bb = fmaf(b.z, b.z, bb); bb = fmaf(b.w, b.w, bb);
+    xa = fmaf(v.x, a.x, xa); xa = fmaf(v.y, a.y, xa); xa = fmaf(v.z, a.z, xa); xa = fmaf(v.w, a.w, xa);
+    xb = fmaf(v.x, b.x, xb); xb = fmaf(v.y, b.y, xb); xb = fmaf(v.z, b.z, xb); xb = fmaf(v.w, b.w, xb);
+  }
+  xx = warp_sum(xx); aa = warp_sum(aa); bb = warp_sum(bb); xa = warp_sum(xa); xb = warp_sum(xb);
+  if (lane != 0) return;
+  const float nx = fmaxf(sqrtf(xx), COS_EPS);
+  float d0 = j0 >= 0 ? 1.f - xa / (nx * fmaxf(sqrtf(aa), COS_EPS)) : MISSING_DIST;
+  float d1 = j1 >= 0 ? 1.f - xb / (nx * fmaxf(sqrtf(bb), COS_EPS)) : MISSING_DIST;
+  if (j1 >= 0 && (d1 < d0 || (d1 == d0 && j1 < j0))) {  // fp32 order wins over the tensor-core order
+    const float td = d0; d0 = d1; d1 = td;
+    const int tj = j0; j0 = j1; j1 = tj;
+    row_idx[2 * (size_t)i] = j0;
+    row_idx[2 * (size_t)i + 1] = j1;
+  }
+  if (dists) {
+    dists[2 * (size_t)i] = d0;
+    dists[2 * (size_t)i + 1] = d1;
+  }
+  if (weight) {
+    float w = d0;
+    if (ratio_test) w = 1.f - __fdiv_rn(fmaxf(d0, RATIO_CLAMP), fmaxf(fmaxf(d1, RATIO_CLAMP), RATIO_CLAMP));
+    weight[i] = w;
+  }
+  if (mutual) {
+    uint8_t f = 0;
+    if (col_best && j0 >= 0) {
+      const unsigned long long pk = col_best[j0];
+      f = (pk != 0ull && (0xffffffffu - (uint32_t)(pk & 0xffffffffull)) == (uint32_t)i) ? 1 : 0;
+    }
+    mutual[i] = f;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// top-k of the weights (single CTA, 1024 threads): radix select the k-th key, stable pick among the
+// ties, bitonic sort of the k winners by (weight desc, row asc)
+// ------------------------------------------------------------------------------------------
+constexpr int TOPK_THREADS = 1024;
+
+__global__ void __launch_bounds__(TOPK_THREADS) k3_topk_kernel(const float* __restrict__ weight,
+                                                               const int32_t* __restrict__ row_idx,
+                                                               const int32_t* __restrict__ n_dev, int n_max, int num_corr,
+                                                               int kpad, int32_t* __restrict__ sel_src,
+                                                               int32_t* __restrict__ sel_dst, float* __restrict__ sel_weight,
+                                                               int32_t* __restrict__ k_dev) {
+  extern __shared__ unsigned long long sortbuf[];  // kpad entries
+  __shared__ int hist[256];
+  __shared__ int warp_tot[32];
+  __shared__ uint32_t s_prefix;
+  __shared__ int s_remaining, s_gt;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int n = n_dev ? min(*n_dev, n_max) : n_max;
+  const int k = min(num_corr, n);
+  if (tid == 0 && k_dev) *k_dev = k;
+  if (k <= 0) return;
+
+  // ---- radix select, most significant byte first
+  uint32_t prefix = 0, mask = 0;
+  int remaining = k;
+  for (int pass = 3; pass >= 0; --pass) {
+    for (int b = tid; b < 256; b += TOPK_THREADS) hist[b] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += TOPK_THREADS) {
+      const uint32_t key = f32_orderable(weight[i]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int acc = 0, b = 255;
+      for (; b > 0; --b) {
+        if (acc + hist[b] >= remaining) break;
+        acc += hist[b];
+      }
+      s_prefix = prefix | ((uint32_t)b << (8 * pass));
+      s_remaining = remaining - acc;
+    }
+    __syncthreads();
+    prefix = s_prefix;
+    remaining = s_remaining;
+    mask |= 0xffu << (8 * pass);
+  }
+  const uint32_t T = prefix;          // k-th largest key
+  const int n_gt = k - remaining;     // keys strictly above it; `remaining` ties are taken in row order
+  if (tid == 0) s_gt = 0;
+  for (int q = tid; q < kpad; q += TOPK_THREADS) sortbuf[q] = 0ull;
+  __syncthreads();
+
+  int eq_seen = 0;  // ties in earlier chunks (uniform)
+  for (int base = 0; base < n; base += TOPK_THREADS) {
+    const int i = base + tid;
+    uint32_t key = 0;
+    bool gt = false, eq = false;
+    if (i < n) {
+      key = f32_orderable(weight[i]);
+      gt = key > T;
+      eq = key == T;
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, eq);
+    if (lane == 0) warp_tot[wid] = __popc(bal);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll 8
+    for (int w = 0; w < 32; ++w) {
+      const int c = warp_tot[w];
+      before += (w < wid) ? c : 0;
+      total += c;
+    }
+    const unsigned long long packed = ((unsigned long long)key << 32) | (unsigned long long)(0xffffffffu - (uint32_t)i);
+    if (gt) sortbuf[atomicAdd(&s_gt, 1)] = packed;
+    if (eq) {
+      const int r = eq_seen + before + __popc(bal & ((1u << lane) - 1u));
+      if (r < remaining) sortbuf[n_gt + r] = packed;
+    }
+    eq_seen += total;
+    __syncthreads();
+  }
+
+  // ---- bitonic sort, descending
+  for (int size = 2; size <= kpad; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int q = tid; q < (kpad >> 1); q += TOPK_THREADS) {
+        const int lo = 2 * q - (q & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const unsigned long long a = sortbuf[lo], b = sortbuf[hi];
+        if ((a < b) == desc) {
+          sortbuf[lo] = b;
+          sortbuf[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int r = tid; r < k; r += TOPK_THREADS) {
+    const int i = (int)(0xffffffffu - (uint32_t)(sortbuf[r] & 0xffffffffull));
+    sel_src[r] = i;
+    sel_dst[r] = row_idx[2 * (size_t)i];
+    sel_weight[r] = weight[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// scoring
+// ------------------------------------------------------------------------------------------
+struct ScoreParams {
+  float Rt[12];
+  float K[9];
+  float thr3d[MV_MAX_THRESHOLDS];
+  float thr2d[MV_MAX_THRESHOLDS];
+  int n3, n2;
+};
+
+__device__ __forceinline__ void project(const float* K, float x, float y, float z, float& u, float& v) {
+  // xyz @ K^T, then / clamp(z', 1e-9)   (project_3dto2d)
+  const float a = fmaf(z, K[2], fmaf(y, K[1], x * K[0]));
+  const float b = fmaf(z, K[5], fmaf(y, K[4], x * K[3]));
+  const float c = fmaxf(fmaf(z, K[8], fmaf(y, K[7], x * K[6])), 1e-9f);
+  u = __fdiv_rn(a, c);
+  v = __fdiv_rn(b, c);
+}
+
+__global__ void __launch_bounds__(256) k3_score_kernel(const int32_t* __restrict__ sel_src,
+                                                       const int32_t* __restrict__ sel_dst,
+                                                       const int32_t* __restrict__ k_dev, int k_max,
+                                                       const float* __restrict__ xyz0, const float* __restrict__ xyz1,
+                                                       const uint8_t* __restrict__ mutual, ScoreParams sp,
+                                                       float* __restrict__ c_xyz0, float* __restrict__ c_xyz1,
+                                                       float* __restrict__ err3d, float* __restrict__ err2d,
+                                                       unsigned long long* __restrict__ hits) {
+  __shared__ unsigned int cnt[2 + 4 * MV_MAX_THRESHOLDS];
+  const int ncnt = 2 + 2 * (sp.n3 + sp.n2);
+  for (int q = threadIdx.x; q < ncnt; q += blockDim.x) cnt[q] = 0;
+  __syncthreads();
+  const int k = k_dev ? min(*k_dev, k_max) : k_max;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = r < k;
+  float e3 = CUDART_INF_F, e2 = CUDART_INF_F;
+  bool mu = false;
+  if (live) {
+    const int s = sel_src[r], d = sel_dst[r];
+    const float px = xyz0[3 * (size_t)s], py = xyz0[3 * (size_t)s + 1], pz = xyz0[3 * (size_t)s + 2];
+    const float qx = xyz1[3 * (size_t)d], qy = xyz1[3 * (size_t)d + 1], qz = xyz1[3 * (size_t)d + 2];
+    // points @ R^T + t  (transform_points_Rt)
+    const float tx = fmaf(pz, sp.Rt[2], fmaf(py, sp.Rt[1], px * sp.Rt[0])) + sp.Rt[3];
+    const float ty = fmaf(pz, sp.Rt[6], fmaf(py, sp.Rt[5], px * sp.Rt[4])) + sp.Rt[7];
+    const float tz = fmaf(pz, sp.Rt[10], fmaf(py, sp.Rt[9], px * sp.Rt[8])) + sp.Rt[11];
+    const float dx = tx - qx, dy = ty - qy, dz = tz - qz;
+    e3 = sqrtf(fmaf(dz, dz, fmaf(dy, dy, dx * dx)));
+    float u0, v0, u1, v1;
+    project(sp.K, tx, ty, tz, u0, v0);
+    project(sp.K, qx, qy, qz, u1, v1);
+    const float du = u0 - u1, dv = v0 - v1;
+    e2 = sqrtf(fmaf(dv, dv, du * du));
+    mu = mutual ? mutual[s] != 0 : false;
+    if (c_xyz0) { c_xyz0[3 * (size_t)r] = px; c_xyz0[3 * (size_t)r + 1] = py; c_xyz0[3 * (size_t)r + 2] = pz; }
+    if (c_xyz1) { c_xyz1[3 * (size_t)r] = qx; c_xyz1[3 * (size_t)r + 1] = qy; c_xyz1[3 * (size_t)r + 2] = qz; }
+    if (err3d) err3d[r] = e3;
+    if (err2d) err2d[r] = e2;
+  }
+  const int lane = threadIdx.x & 31;
+  auto tally = [&](int slot, bool flag) {
+    const unsigned b = __ballot_sync(0xffffffffu, flag);
+    if (lane == 0 && b) atomicAdd(&cnt[slot], (unsigned)__popc(b));
+  };
+  tally(0, live);
+  tally(1, live && mu);
+  for (int t = 0; t < sp.n3; ++t) {
+    const bool h = live && e3 < sp.thr3d[t];
+    tally(2 + t, h);
+    tally(2 + sp.n3 + sp.n2 + t, h && mu);
+  }
+  for (int t = 0; t < sp.n2; ++t) {
+    const bool h = live && e2 < sp.thr2d[t];
+    tally(2 + sp.n3 + t, h);
+    tally(2 + 2 * sp.n3 + sp.n2 + t, h && mu);
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < ncnt; q += blockDim.x)
+    if (cnt[q]) atomicAdd(&hits[q], (unsigned long long)cnt[q]);
+}
+
+__global__ void gather_rows_kernel(const float* __restrict__ src, int width, const int32_t* __restrict__ idx,
+                                   const int32_t* __restrict__ k_dev, int k_max, float* __restrict__ dst) {
+  const int k = k_dev ? min(*k_dev, k_max) : k_max;
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)k * width) return;
+  const int r = (int)(t / width), c = (int)(t - (long long)r * width);
+  dst[t] = src[(size_t)idx[r] * width + c];
+}
+
+// argmax_2d: one warp per row, first occurrence wins
+__global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restrict__ x, int rows, int cols, int max_value,
+                                                          int32_t* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const float* row = x + (size_t)r * cols;
+  float best = max_value ? -CUDART_INF_F : CUDART_INF_F;
+  int bi = 0x7fffffff;
+  for (int c = lane; c < cols; c += 32) {
+    const float v = __ldg(row + c);
+    if (max_value ? (v > best) : (v < best)) { best = v; bi = c; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    const bool take = max_value ? (ov > best || (ov == best && oi < bi)) : (ov < best || (ov == best && oi < bi));
+    if (take) { best = ov; bi = oi; }
+  }
+  if (lane == 0) out[r] = bi == 0x7fffffff ? 0 : bi;
+}
+
+// ------------------------------------------------------------------------------------------
+// SPair
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k3_spair_kernel(const int32_t* __restrict__ pred_flat, int K, int w,
+                                                       const float* __restrict__ kps_i, const float* __restrict__ kps_j,
+                                                       int stride, float image_size, float thresh_scale, float pck,
+                                                       float* __restrict__ errors, float* __restrict__ error_same,
+                                                       float* __restrict__ error_nn, int32_t* __restrict__ index_nn,
+                                                       unsigned long long* __restrict__ hits) {
+  __shared__ float err[64][65];
+  __shared__ unsigned int cnt[2];
+  if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
+  for (int t = threadIdx.x; t < K * K; t += blockDim.x) {
+    const int k = t / K, l = t - k * K;
+    const int flat = pred_flat[k];
+    // argmax_2d -> (col, row); both divided by feats.shape[-1]  (spair:83)
+    const float px = __fdiv_rn((float)(flat % w), (float)w), py = __fdiv_rn((float)(flat / w), (float)w);
+    const float jx = __fdiv_rn(kps_j[(size_t)l * stride], image_size), jy = __fdiv_rn(kps_j[(size_t)l * stride + 1], image_size);
+    const float dx = px - jx, dy = py - jy;
+    float e = __fdiv_rn(sqrtf(fmaf(dy, dy, dx * dx)), thresh_scale);
+    const bool valid = (kps_i[(size_t)k * stride + 2] * kps_j[(size_t)l * stride + 2]) == 1.f;
+    if (!valid) e = 1e3f;
+    err[k][l] = e;
+    if (errors) errors[t] = e;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const bool in_both = (kps_i[(size_t)k * stride + 2] * kps_j[(size_t)k * stride + 2]) == 1.f;
+    float es = -1.f, en = -1.f;
+    int in = -1;
+    if (in_both) {
+      es = err[k][k];
+      en = err[k][0];
+      in = 0;
+      for (int l = 1; l < K; ++l)
+        if (err[k][l] < en) { en = err[k][l]; in = l; }
+      atomicAdd(&cnt[0], 1u);
+      if (es < pck) atomicAdd(&cnt[1], 1u);
+    }
+    if (error_same) error_same[k] = es;
+    if (error_nn) error_nn[k] = en;
+    if (index_nn) index_nn[k] = in;
+  }
+  __syncthreads();
+  if (hits && threadIdx.x < 2 && cnt[threadIdx.x]) atomicAdd(&hits[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mv_k3_ratio_mutual(const float* A32, const float* B32, int C, const int32_t* n_dev, int n_max, int32_t* row_idx,
+                       const unsigned long long* col_best, int ratio_test, float* dists, float* weight,
+                       uint8_t* mutual, mv_stream_t stream) {
+  MV_REQUIRE(A32 && B32 && row_idx, MV_E_ARG, "mv_k3_ratio_mutual: null pointer");
+  MV_REQUIRE(C > 0 && C % 4 == 0, MV_E_ALIGN, "mv_k3_ratio_mutual: C=%d must be a positive multiple of 4", C);
+  MV_REQUIRE(((uintptr_t)A32 & 15) == 0 && ((uintptr_t)B32 & 15) == 0, MV_E_ALIGN,
+             "mv_k3_ratio_mutual: A32 and B32 must be 16-byte aligned");
+  MV_REQUIRE(n_max >= 0, MV_E_ARG, "mv_k3_ratio_mutual: negative n_max");
+  if (n_max == 0) return MV_OK;
+  const int rows_per_cta = 8;
+  k3_ratio_mutual_kernel<<<(n_max + rows_per_cta - 1) / rows_per_cta, 32 * rows_per_cta, 0, mv_cuda_stream(stream)>>>(
+      A32, B32, C, n_dev, n_max, row_idx, col_best, ratio_test, dists, weight, mutual);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+int mv_k3_topk_matches(const float* weight, const int32_t* row_idx, const int32_t* n_dev, int n_max, int num_corr,
+                       int32_t* sel_src, int32_t* sel_dst, float* sel_weight, int32_t* k_dev, mv_stream_t stream) {
+  MV_REQUIRE(weight && row_idx && sel_src && sel_dst && sel_weight, MV_E_ARG, "mv_k3_topk_matches: null pointer");
+  MV_REQUIRE(n_max >= 0 && n_max <= (1 << 20), MV_E_RANGE, "mv_k3_topk_matches: n_max must be in [0, 2^20]");
+  MV_REQUIRE(num_corr >= 0 && num_corr <= 16384, MV_E_RANGE, "mv_k3_topk_matches: num_corr must be in [0, 16384]");
+  cudaStream_t st = mv_cuda_stream(stream);
+  const int kmax = num_corr < n_max ? num_corr : n_max;
+  if (kmax == 0) {
+    if (k_dev) MV_CUDA(cudaMemsetAsync(k_dev, 0, sizeof(int32_t), st));
+    return MV_OK;
+  }
+  int kpad = 2;
+  while (kpad < kmax) kpad <<= 1;
+  const size_t smem = (size_t)kpad * sizeof(unsigned long long);
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    MV_CUDA(cudaFuncSetAttribute(k3_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  k3_topk_kernel<<<1, TOPK_THREADS, smem, st>>>(weight, row_idx, n_dev, n_max, num_corr, kpad, sel_src, sel_dst,
+                                                sel_weight, k_dev);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+int mv_k3_score(const int32_t* sel_src, const int32_t* sel_dst, const int32_t* k_dev, int k_max, const float* xyz0,
+                const float* xyz1, const uint8_t* mutual, const float* Rt_host, const float* Kproj_host,
+                const float* thr3d_host, int n3, const float* thr2d_host, int n2, float* c_xyz0, float* c_xyz1,
+                float* err3d, float* err2d, unsigned long long* hits, mv_stream_t stream) {
+  MV_REQUIRE(sel_src && sel_dst && xyz0 && xyz1 && Rt_host && Kproj_host && hits, MV_E_ARG, "mv_k3_score: null pointer");
+  MV_REQUIRE(n3 >= 0 && n3 <= MV_MAX_THRESHOLDS && n2 >= 0 && n2 <= MV_MAX_THRESHOLDS, MV_E_RANGE,
+             "mv_k3_score: at most %d thresholds per list", MV_MAX_THRESHOLDS);
+  MV_REQUIRE((n3 == 0 || thr3d_host) && (n2 == 0 || thr2d_host), MV_E_ARG, "mv_k3_score: null threshold list");
+  MV_REQUIRE(k_max >= 0, MV_E_ARG, "mv_k3_score: negative k_max");
+  if (k_max == 0) return MV_OK;
+  ScoreParams sp;
+  for (int i = 0; i < 12; ++i) sp.Rt[i] = Rt_host[i];
+  for (int i = 0; i < 9; ++i) sp.K[i] = Kproj_host[i];
+  for (int i = 0; i < MV_MAX_THRESHOLDS; ++i) {
+    sp.thr3d[i] = i < n3 ? thr3d_host[i] : 0.f;
+    sp.thr2d[i] = i < n2 ? thr2d_host[i] : 0.f;
+  }
+  sp.n3 = n3;
+  sp.n2 = n2;
+  k3_score_kernel<<<(k_max + 255) / 256, 256, 0, mv_cuda_stream(stream)>>>(sel_src, sel_dst, k_dev, k_max, xyz0, xyz1,
+                                                                          mutual, sp, c_xyz0, c_xyz1, err3d, err2d, hits);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+int mv_gather_rows(const float* src, int width, const int32_t* idx, const int32_t* k_dev, int k_max, float* dst,
+                   mv_stream_t stream) {
+  MV_REQUIRE(src && idx && dst, MV_E_ARG, "mv_gather_rows: null pointer");
+  MV_REQUIRE(width > 0 && k_max >= 0, MV_E_ARG, "mv_gather_rows: bad sizes");
+  if (k_max == 0) return MV_OK;
+  const long long total = (long long)k_max * width;
+  gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, mv_cuda_stream(stream)>>>(src, width, idx, k_dev, k_max, dst);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+int mv_argmax_rows(const float* x, int rows, int cols, int max_value, int32_t* out_flat, mv_stream_t stream) {
+  MV_REQUIRE(x && out_flat, MV_E_ARG, "mv_argmax_rows: null pointer");
+  MV_REQUIRE(rows >= 0 && cols > 0, MV_E_ARG, "mv_argmax_rows: bad sizes");
+  if (rows == 0) return MV_OK;
+  argmax_rows_kernel<<<(rows + 7) / 8, 256, 0, mv_cuda_stream(stream)>>>(x, rows, cols, max_value, out_flat);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+int mv_k3_spair_errors(const int32_t* pred_flat, int K, int w, const float* kps_i, const float* kps_j, int kp_stride,
+                       float image_size, float thresh_scale, float pck_thresh, float* errors, float* error_same,
+                       float* error_nn, int32_t* index_nn, unsigned long long* hits, mv_stream_t stream) {
+  MV_REQUIRE(pred_flat && kps_i && kps_j, MV_E_ARG, "mv_k3_spair_errors: null pointer");
+  MV_REQUIRE(K >= 0 && K <= 64, MV_E_RANGE, "mv_k3_spair_errors: K=%d must be in [0, 64]", K);
+  MV_REQUIRE(w > 0 && kp_stride >= 3 && image_size > 0.f, MV_E_ARG, "mv_k3_spair_errors: bad sizes");
+  if (K == 0) return MV_OK;
+  k3_spair_kernel<<<1, 256, 0, mv_cuda_stream(stream)>>>(pred_flat, K, w, kps_i, kps_j, kp_stride, image_size,
+                                                         thresh_scale, pck_thresh, errors, error_same, error_nn,
+                                                         index_nn, hits);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+"""Pair-sharded evaluation of the dense-correspondence benchmarks on one or more B200s.
+
+Every image pair is independent (loops at evaluate_navi_correspondence.py:178,
+render_scannet_correspondence.py:188, evaluate_spair_correspondence.py:108), so pair i runs on rank
+i mod world; each rank accumulates integer hit counts on its device (mv_k3_score) and ONE NCCL
+all-reduce of that small int64 vector at the end makes the recalls identical on every rank and equal
+to the single-GPU run.  No other collective exists on this path.
+"""
+from ctypes import c_void_p
+
+import torch
+
+from . import _lib as L
+from . import correspondence as C_
+
+__all__ = ["RecallAccumulator", "shard_pairs", "match_and_score_depth", "match_and_score_xyz"]
+
+
+def shard_pairs(num_pairs, rank, world):
+    """indices of the pairs this rank owns (round-robin keeps variable-size pairs balanced)."""
+    return range(rank, num_pairs, world)
+
+
+class RecallAccumulator:
+    """Integer hit counters for 3-D (metres) and 2-D (pixels) thresholds.
+
+    Layout of ``hits`` (include/mvmatch.h, mv_k3_score): [scored, mutual, 3d[n3], 2d[n2],
+    mutual&3d[n3], mutual&2d[n2]].  recall = 100 * hits / scored reproduces
+    ``100 * (err < th).float().mean()`` (evaluate_navi_correspondence.py:200-212,
+    render_scannet_correspondence.py:253-264) without floating-point accumulation.
+    """
+
+    def __init__(self, thr3d, thr2d, device=None):
+        if len(thr3d) > L.MV_MAX_THRESHOLDS or len(thr2d) > L.MV_MAX_THRESHOLDS:
+            raise ValueError(f"at most {L.MV_MAX_THRESHOLDS} thresholds per list")
+        self.thr3d = [float(t) for t in thr3d]
+        self.thr2d = [float(t) for t in thr2d]
+        self.n3, self.n2 = len(self.thr3d), len(self.thr2d)
+        self.device = device
+        self.hits = torch.zeros(2 + 2 * (self.n3 + self.n2), dtype=torch.int64, device=device)
+        self._t3 = L.host_floats(self.thr3d) if self.n3 else None
+        self._t2 = L.host_floats(self.thr2d) if self.n2 else None
+
+    def score(self, match, xyz0, xyz1, Rt, K, want_errors=False):
+        """Accumulate the counts of one pair. Rt: (3|4, 4), K: (3, 3) host or device tensors."""
+        dev = xyz0.device
+        Rt_h = L.host_floats(Rt.detach().float().cpu()[:3, :4].reshape(-1).tolist())
+        K_h = L.host_floats(K.detach().float().cpu().reshape(-1).tolist())
+        k = match.k
+        e3 = torch.empty((max(k, 1),), dtype=torch.float32, device=dev) if want_errors else None
+        e2 = torch.empty((max(k, 1),), dtype=torch.float32, device=dev) if want_errors else None
+        L.call("mv_k3_score", L.ptr(match.sel_src), L.ptr(match.sel_dst), L.ptr(match.k_dev), k, L.ptr(xyz0),
+               L.ptr(xyz1), L.ptr(match.mutual), Rt_h, K_h, self._t3, self.n3, self._t2, self.n2, None, None,
+               L.ptr(e3), L.ptr(e2), L.ptr(self.hits), C_._stream())
+        return (e3, e2) if want_errors else None
+
+    def all_reduce(self):
+        """Sum the counters over all ranks (the path's only collective)."""
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            torch.distributed.all_reduce(self.hits, op=torch.distributed.ReduceOp.SUM)
+        return self
+
+    def merge_(self, other_hits):
+        self.hits += other_hits.to(self.hits.device)
+        return self
+
+    def summary(self):
+        h = self.hits.tolist()
+        tot = max(h[0], 1)
+        mut = max(h[1], 1)
+        n3, n2 = self.n3, self.n2
+        return {
+            "scored": h[0],
+            "mutual": h[1],
+            "recall_3d": {t: 100.0 * h[2 + i] / tot for i, t in enumerate(self.thr3d)},
+            "recall_2d": {t: 100.0 * h[2 + n3 + i] / tot for i, t in enumerate(self.thr2d)},
+            "mutual_recall_3d": {t: 100.0 * h[2 + n3 + n2 + i] / mut for i, t in enumerate(self.thr3d)},
+            "mutual_recall_2d": {t: 100.0 * h[2 + 2 * n3 + n2 + i] / mut for i, t in enumerate(self.thr2d)},
+        }
+
+
+def match_and_score_depth(feat_0, feat_1, depth_0, depth_1, K, Rt, num_corr, acc, sync=False):
+    """ScanNet-shaped pair, end to end on the device: estimate_correspondence_depth
+    (correspondence.py:218-232) + the caller's error / recall block
+    (render_scannet_correspondence.py:211-217, :253-264) with no host round trip when sync=False."""
+    dev = C_._device()
+    Kc = K.detach().float().cpu()
+    Kh, Kinv = C_._host_mat(Kc), C_._host_mat(Kc.inverse())
+    s0 = C_.prepare_depth_side(feat_0, depth_0, Kh, Kinv, dev, sync=sync)
+    s1 = C_.prepare_depth_side(feat_1, depth_1, Kh, Kinv, dev, sync=sync)
+    r = C_.match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, s0.n, s1.n, num_corr,
+                      n_dev=None if sync else s0.n_dev, m_dev=None if sync else s1.n_dev)
+    acc.score(r, s0.xyz, s1.xyz, Rt, Kc)
+    return r
+
+
+def match_and_score_xyz(feat_0, feat_1, xyz_grid_0, xyz_grid_1, intrinsics, Rt, num_corr, acc, sync=False):
+    """NAVI-shaped pair: estimate_correspondence_xyz (correspondence.py:235-263) + the caller's error /
+    recall block (evaluate_navi_correspondence.py:186-212)."""
+    dev = C_._device()
+    s0 = C_.prepare_xyz_side(feat_0, xyz_grid_0, dev, sync=sync)
+    s1 = C_.prepare_xyz_side(feat_1, xyz_grid_1, dev, sync=sync)
+    r = C_.match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, s0.n, s1.n, num_corr,
+                      n_dev=None if sync else s0.n_dev, m_dev=None if sync else s1.n_dev)
+    acc.score(r, s0.xyz, s1.xyz, Rt, intrinsics)
+    return r

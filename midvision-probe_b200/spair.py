@@ -1,0 +1,66 @@
+"""SPair-71k keypoint transfer on the B200 path: the matching lines that the reference inlines in
+``evaluate_spair_correspondence.py:compute_errors`` (:59-103), taking the backbone's features instead
+of the model so that the frozen forward stays in PyTorch.
+
+    feats (2, C, h, w)  ->  per-pixel L2 normalise (:59)  ->  bilinear keypoint gather, align_corners=True
+    (:71-79)  ->  K x (h*w) similarity + arg-max (:82-83, kernel 2)  ->  error matrix / thresh_scale,
+    validity, error_same / error_nn (:86-98, kernel 3)  ->  PCK hit counts (:121)
+"""
+from ctypes import c_float, c_size_t
+
+import torch
+
+from . import _lib as L
+from . import correspondence as C_
+
+__all__ = ["compute_errors_from_features", "pck_recall"]
+
+
+def compute_errors_from_features(feats, kps_i, kps_j, thresh_scale, image_size, pck_thresh=0.10, hits=None,
+                                 return_heatmap_argmax=False):
+    """(error_same, error_nn, index_same, index_nn), as compute_errors (evaluate_spair_correspondence.py:45-103).
+
+    feats: (2, C, h, w) backbone output for (image_i, image_j); kps_*: (K, 3) = (x, y, valid) in image
+    pixels; image_size: side of the (square) input image.  hits: optional int64[2] device tensor that
+    accumulates (#keypoints in both images, #of those with error_same < pck_thresh).
+    """
+    dev = C_._device()
+    in_dev = kps_i.device
+    st = C_._stream()
+    f = C_._f32(feats, dev)
+    _, C, h, w = f.shape
+    C_._check_C(C)
+    ki = C_._f32(kps_i, dev)
+    kj = C_._f32(kps_j, dev)
+    K = ki.shape[0]
+    if K > 64:
+        raise ValueError("at most 64 keypoint slots")
+    want16 = C_._CFG["dtype"] == "bf16"
+    src_i = C_._hwc(f[0], prenorm=True)
+    rows_j32 = C_._hwc(f[1], prenorm=True)  # (h*w, C): the heat-map columns, pixel p = y*w + x
+    coords = torch.empty((K, 2), dtype=torch.float32, device=dev)
+    L.call("mv_geom_keypoint_coords", L.ptr(ki), ki.shape[1], K, c_float(float(image_size)), h, w, L.ptr(coords), st)
+    a16, a32 = C_._sample(L.MV_SAMPLE_BILINEAR_ZEROS, src_i, C, h, w, coords, None, K, False, want16, True)
+    b16 = None
+    if want16:
+        b16, _ = C_._sample(L.MV_SAMPLE_ROWS, rows_j32, C, 0, 0, None, None, h * w, False, True, False)
+    r = C_.match_rows(a16, a32, b16, rows_j32, K, h * w, 0, want_topk=False)
+    pred = r.row_idx[:, 0].contiguous()
+    err_same = torch.empty((K,), dtype=torch.float32, device=dev)
+    err_nn = torch.empty((K,), dtype=torch.float32, device=dev)
+    idx_nn = torch.empty((K,), dtype=torch.int32, device=dev)
+    L.call("mv_k3_spair_errors", L.ptr(pred), K, w, L.ptr(ki), L.ptr(kj), ki.shape[1], c_float(float(image_size)),
+           c_float(float(thresh_scale)), c_float(float(pck_thresh)), None, L.ptr(err_same), L.ptr(err_nn),
+           L.ptr(idx_nn), L.ptr(hits), st)
+    in_both = err_same >= 0
+    out = (err_same[in_both].to(in_dev), err_nn[in_both].to(in_dev), in_both.nonzero().squeeze(1).to(in_dev),
+           idx_nn[in_both].long().to(in_dev))
+    if return_heatmap_argmax:
+        return out + (pred.long().to(in_dev),)
+    return out
+
+
+def pck_recall(hits):
+    """100 * hits[1] / hits[0]  (evaluate_spair_correspondence.py:121 on the integer counts)."""
+    h = hits.tolist()
+    return 100.0 * h[1] / max(h[0], 1)

@@ -1,0 +1,208 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU restatement (fp32 torch on the host) of the reference's matching path.
+
+Each function names the reference lines it follows (paths relative to /root/reference).  The k-NN
+backend of the reference, faiss-gpu 1.8.0 GpuIndexFlatL2 (not in the tree; README.md:60), is restated
+from its published behaviour: exact brute-force squared-L2 search, ascending, int64 labels.
+
+Checked against (a) the reference's own module imported from /root/reference and (b) the golden vectors
+under tests/golden/ by tests/test_oracle.py.  Never imported by the product.
+"""
+import torch
+import torch.nn.functional as F
+
+
+# ---- k-NN ------------------------------------------------------------------------------------------
+def exact_l2_knn(query, target, k):
+    """faiss.GpuIndexFlatL2(res, d).add(target).search(query, k) -- evals/utils/correspondence.py:14-23."""
+    q = query.contiguous().float()
+    t = target.contiguous().float()
+    d2 = (q * q).sum(1, keepdim=True) - 2.0 * (q @ t.t()) + (t * t).sum(1)[None, :]
+    dist, idx = torch.topk(d2, k, dim=1, largest=False, sorted=True)
+    return dist, idx
+
+
+def knn_points(X_f, Y_f, K=1, metric="euclidean"):
+    """evals/utils/correspondence.py:26-60: normalise (cosine), faiss indices, distances recomputed
+    from the gathered rows (the faiss distances are discarded at :50)."""
+    assert metric in ["cosine", "euclidean"]
+    if metric == "cosine":
+        X_f = F.normalize(X_f, dim=-1)
+        Y_f = F.normalize(Y_f, dim=-1)
+    _, nn_idx = exact_l2_knn(X_f, Y_f, K)
+    gathered = Y_f[nn_idx]                                   # (N, K, C)   :53
+    if metric == "euclidean":
+        dists = (gathered - X_f[:, None, :]).norm(p=2, dim=2)  # :55-56 (the reference's dim=3 is a bug there)
+    else:
+        dists = 1 - F.cosine_similarity(gathered, X_f[:, None, :], dim=-1)  # :58
+    return dists, nn_idx
+
+
+def ratio_weights(dists):
+    """calculate_ratio_test, evals/utils/correspondence.py:105-121."""
+    d = dists.clamp(min=1e-9)
+    return 1 - d[..., 0] / d[..., 1].clamp(min=1e-9)
+
+
+def topk_matches(weights, idx, num_corres):
+    """get_topk_matches, evals/utils/correspondence.py:125-129."""
+    k = min(num_corres, weights.shape[-1])
+    w, src = torch.topk(weights, k=k, dim=-1)
+    return src, idx[src], w
+
+
+def correspondences_ratio_test(P1_F, P2_F, num_corres, ratio_test=True, return_all=False):
+    """get_correspondences_ratio_test with bidirectional=False, evals/utils/correspondence.py:63-102."""
+    dists, idx = knn_points(P1_F, P2_F, 2, "cosine")
+    w = ratio_weights(dists) if ratio_test else dists[:, 0]
+    out = topk_matches(w, idx[:, 0], num_corres)
+    if return_all:
+        return out + (dists, idx, w)
+    return out
+
+
+def similarity_top2_and_mutual(X_f, Y_f):
+    """What kernel 2 adds on top of the reference: fp32 cosine similarities of the normalised rows, the
+    two best columns per row (ties to the lower column), the best row per column, the mutual flag and
+    the top-2 similarity gap used by the north-star tolerance."""
+    Xn = F.normalize(X_f.float(), dim=-1)
+    Yn = F.normalize(Y_f.float(), dim=-1)
+    S = Xn @ Yn.t()
+    val, idx = torch.topk(S, min(2, S.shape[1]), dim=1)
+    col_val, col_idx = S.max(dim=0)
+    mutual = col_idx[idx[:, 0]] == torch.arange(S.shape[0])
+    gap = val[:, 0] - val[:, 1] if S.shape[1] > 1 else torch.full((S.shape[0],), float("inf"))
+    col_sorted = torch.topk(S, min(2, S.shape[0]), dim=0).values
+    col_gap = col_sorted[0] - col_sorted[1] if S.shape[0] > 1 else torch.full((S.shape[1],), float("inf"))
+    return {"S": S, "row_val": val, "row_idx": idx, "col_val": col_val, "col_idx": col_idx, "mutual": mutual,
+            "row_gap": gap, "col_gap": col_gap}
+
+
+# ---- geometry + sampling ---------------------------------------------------------------------------
+def pixel_grid(H, W):
+    """get_grid, evals/utils/correspondence.py:132-144."""
+    xs = torch.linspace(0.5, W - 0.5, W).view(1, W).repeat(H, 1)
+    ys = torch.linspace(0.5, H - 0.5, H).view(H, 1).repeat(1, W)
+    return torch.stack((xs, ys, torch.ones_like(xs)), dim=0)
+
+
+def backproject(K_inv, depth):
+    """grid_to_pointcloud, evals/utils/correspondence.py:147-161."""
+    _, H, W = depth.shape
+    pts = (depth * pixel_grid(H, W)).view(3, H * W)
+    return (K_inv @ pts).permute(1, 0)
+
+
+def depth_side_coords(K, pc, image_shape, feat_hw):
+    """The projection + NDC step of sample_pointcloud_features (:164-170) followed by grid_sample's own
+    align_corners=False un-normalisation on the CPU (ATen GridSamplerKernel.cpp: (g + 1) * (size / 2) - 0.5).
+    Returns the continuous source coordinates (ix, iy) whose floor is the tap origin."""
+    H, W = image_shape
+    h, w = feat_hw
+    uvd = pc @ K.transpose(-1, -2)
+    uv = uvd[:, :2] / uvd[:, 2:3].clamp(min=1e-9)
+    gx = (2 * uv[:, 0] / W) - 1
+    gy = (2 * uv[:, 1] / H) - 1
+    return torch.stack(((gx + 1) * (w / 2) - 0.5, (gy + 1) * (h / 2) - 0.5), dim=1)
+
+
+def sample_pointcloud_features(feats, K, pc, image_shape):
+    """evals/utils/correspondence.py:164-176."""
+    H, W = image_shape
+    uvd = pc @ K.transpose(-1, -2)
+    uv = uvd[:, :2] / uvd[:, 2:3].clamp(min=1e-9)
+    uv = torch.stack(((2 * uv[:, 0] / W) - 1, (2 * uv[:, 1] / H) - 1), dim=1)
+    out = F.grid_sample(feats[None], uv[None, None], align_corners=False)
+    return out[:, :, 0].transpose(1, 2)[0]
+
+
+def depth_side(feat, depth, K):
+    """One image of estimate_correspondence_depth (:219-225): (xyz (n, 3), features (n, C), valid index)."""
+    xyz_all = backproject(K.inverse(), depth)
+    keep = xyz_all[:, 2] > 0
+    xyz = xyz_all[keep]
+    return xyz, sample_pointcloud_features(feat, K.clone(), xyz, depth.shape[-2:]), keep.nonzero().squeeze(1)
+
+
+def xyz_side(feat, xyz_grid):
+    """One image of estimate_correspondence_xyz (:239-252): bicubic upsample, keep xyz_grid[2] > 0."""
+    _, h, w = xyz_grid.shape
+    up = F.interpolate(feat[None], size=(h, w), mode="bicubic")[0]
+    keep = xyz_grid[2] > 0
+    uvd = pixel_grid(h, w).to(xyz_grid)
+    return (xyz_grid.permute(1, 2, 0)[keep], up.permute(1, 2, 0)[keep], uvd.permute(1, 2, 0)[keep][:, :2],
+            keep.flatten().nonzero().squeeze(1))
+
+
+def estimate_correspondence_depth(feat_0, feat_1, depth_0, depth_1, K, num_corr=500):
+    """evals/utils/correspondence.py:218-232."""
+    xyz_0, f_0, _ = depth_side(feat_0, depth_0, K)
+    xyz_1, f_1, _ = depth_side(feat_1, depth_1, K)
+    i0, i1, w = correspondences_ratio_test(f_0, f_1, num_corr)
+    return xyz_0[i0], xyz_1[i1], w
+
+
+def estimate_correspondence_xyz(feat_0, feat_1, xyz_grid_0, xyz_grid_1, num_corr=500, ratio_test=True):
+    """evals/utils/correspondence.py:235-263."""
+    xyz_0, f_0, uv_0, _ = xyz_side(feat_0, xyz_grid_0)
+    xyz_1, f_1, uv_1, _ = xyz_side(feat_1, xyz_grid_1)
+    i0, i1, w = correspondences_ratio_test(f_0, f_1, num_corr, ratio_test)
+    return xyz_0[i0], xyz_1[i1], w, uv_0[i0], uv_1[i1]
+
+
+def argmax_2d(x, max_value=True):
+    """evals/utils/correspondence.py:179-190."""
+    w = x.shape[-1]
+    flat = torch.flatten(x, start_dim=-2)
+    idx = flat.argmax(dim=-1) if max_value else flat.argmin(dim=-1)
+    return torch.stack((idx % w, idx // w), dim=-1)
+
+
+# ---- errors / recall --------------------------------------------------------------------------------
+def transform_points_Rt(points, Rt):
+    """evals/utils/transformations.py:27-36 (inverse=False)."""
+    return points @ Rt[..., :3, :3].transpose(-2, -1) + Rt[..., None, :3, 3]
+
+
+def project_3dto2d(xyz, K_mat):
+    """evals/utils/correspondence.py:193-196."""
+    uvd = xyz @ K_mat.transpose(-1, -2)
+    return uvd[:, :2] / uvd[:, 2:3].clamp(min=1e-9)
+
+
+def pair_errors(c_xyz0, c_xyz1, Rt, K_mat):
+    """3-D and 2-D errors of one pair: evaluate_navi_correspondence.py:186-191,
+    render_scannet_correspondence.py:211-217."""
+    x0in1 = transform_points_Rt(c_xyz0, Rt.float())
+    e3 = (x0in1 - c_xyz1).norm(p=2, dim=1)
+    e2 = (project_3dto2d(x0in1, K_mat) - project_3dto2d(c_xyz1, K_mat)).norm(p=2, dim=1)
+    return e3, e2
+
+
+def recall(errors, thresholds):
+    """100 * (err < th).float().mean(): evaluate_navi_correspondence.py:200-212."""
+    return [100.0 * (errors < t).float().mean().item() for t in thresholds]
+
+
+# ---- SPair -------------------------------------------------------------------------------------------
+def spair_compute_errors(feats, kps_i, kps_j, thresh_scale, image_size, return_pred=False):
+    """evaluate_spair_correspondence.py:59-103 with the backbone output `feats` (2, C, h, w) as input."""
+    feats = F.normalize(feats.float(), p=2, dim=1)                      # :59
+    fi, fj = feats[0], feats[1]
+    kps_i = kps_i.clone().float()
+    kps_j = kps_j.clone().float()
+    kps_i[:, :2] = kps_i[:, :2] / image_size                            # :71-72
+    kps_j[:, :2] = kps_j[:, :2] / image_size
+    ndc = (kps_i[:, :2] * 2 - 1)[None, None]                            # :75
+    kp_F = F.grid_sample(fi[None], ndc, mode="bilinear", align_corners=True)[0, :, 0].t()  # :76-79
+    heat = torch.einsum("kf,fhw->khw", kp_F, fj)                        # :82
+    pred = argmax_2d(heat).float() / feats.shape[-1]                    # :83
+    errors = (pred[:, None, :] - kps_j[None, :, :2]).norm(p=2, dim=-1) / thresh_scale  # :86-87
+    valid = (kps_i[:, None, 2] * kps_j[None, :, 2]) == 1                # :90
+    in_both = valid.diagonal()
+    errors[valid.logical_not()] = 1e3                                   # :94
+    error_same = errors.diagonal()[in_both]                             # :96
+    error_nn, index_nn = errors[in_both].min(dim=1)                     # :97
+    index_same = in_both.nonzero().squeeze(1)                           # :98
+    if return_pred:
+        return error_same, error_nn, index_same, index_nn, heat
+    return error_same, error_nn, index_same, index_nn

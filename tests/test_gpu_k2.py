@@ -1,0 +1,143 @@
+"""Kernel 2 (tcgen05 similarity GEMM + fused row top-2 / column arg-max) against fp32 torch on the same
+rounded operands, across tile-edge shapes, operand types and cluster widths."""
+from ctypes import c_size_t
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def round_operand(x, dtype):
+    if dtype == "bf16":
+        return x.to(torch.bfloat16).float()
+    # tf32-exact: keep 10 explicit mantissa bits so the tensor core neither rounds nor truncates
+    bits = x.contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def run_k2(mv, A, B, dtype, cluster, n_live=None, m_live=None):
+    L = mv._lib
+    C_ = mv.correspondence
+    n, C = A.shape
+    m = B.shape[0]
+    dev = torch.device("cuda")
+    Ad = A.cuda().to(torch.bfloat16).contiguous() if dtype == "bf16" else A.cuda().contiguous()
+    Bd = B.cuda().to(torch.bfloat16).contiguous() if dtype == "bf16" else B.cuda().contiguous()
+    row_val = torch.full((n, 2), 7.0, device=dev)
+    row_idx = torch.full((n, 2), -9, dtype=torch.int32, device=dev)
+    col_best = torch.empty(m, dtype=torch.int64, device=dev)
+    ws_bytes = L.load().mv_k2_workspace_bytes(n, m)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    nd = torch.tensor([n_live], dtype=torch.int32, device=dev) if n_live is not None else None
+    md = torch.tensor([m_live], dtype=torch.int32, device=dev) if m_live is not None else None
+    L.call("mv_k2_sim_top2", L.ptr(Ad), L.ptr(Bd), n, m, C, L.ptr(nd), L.ptr(md),
+           L.MV_DTYPE_BF16 if dtype == "bf16" else L.MV_DTYPE_TF32, cluster, L.ptr(row_val), L.ptr(row_idx),
+           L.ptr(col_best), L.ptr(ws), c_size_t(ws_bytes), C_._stream())
+    col_val = torch.empty(m, device=dev)
+    col_idx = torch.empty(m, dtype=torch.int32, device=dev)
+    L.call("mv_k2_unpack_col", L.ptr(col_best), m, L.ptr(col_val), L.ptr(col_idx), C_._stream())
+    torch.cuda.synchronize()
+    return row_val.cpu(), row_idx.cpu().long(), col_val.cpu(), col_idx.cpu().long()
+
+
+def check(mv, n, m, C, dtype, cluster, seed=0, n_live=None, m_live=None, scale=1.0):
+    g = torch.Generator().manual_seed(1000 * n + m + C + seed)
+    A = round_operand(torch.randn(n, C, generator=g) * scale, dtype)
+    B = round_operand(torch.randn(m, C, generator=g) * scale, dtype)
+    rv, ri, cv, ci = run_k2(mv, A, B, dtype, cluster, n_live, m_live)
+    nl = n if n_live is None else n_live
+    ml = m if m_live is None else m_live
+    S = (A[:nl].double() @ B[:ml].double().t())
+    tol = 1e-4 * max(1.0, float(S.abs().max()))
+    k = min(2, ml)
+    val, idx = torch.topk(S, k, dim=1)
+    # values: fp32 accumulation of exact products
+    assert (rv[:nl, :k].double() - val).abs().max() <= tol, (rv[:nl, :k].double() - val).abs().max()
+    # indices: identical unless the competing similarities are within accumulation noise
+    srt = torch.sort(S, dim=1, descending=True).values
+    clear1 = (srt[:, 0] - srt[:, 1] > 2 * tol) if ml > 1 else torch.ones(nl, dtype=torch.bool)
+    assert torch.equal(ri[:nl, 0][clear1], idx[:, 0][clear1])
+    if ml > 2:
+        clear2 = clear1 & (srt[:, 1] - srt[:, 2] > 2 * tol)
+        assert torch.equal(ri[:nl, 1][clear2], idx[:, 1][clear2])
+    # whatever index was returned must own the returned value
+    got = S.gather(1, ri[:nl, :k].clamp(min=0))
+    assert (got - rv[:nl, :k].double()).abs().max() <= tol
+    if ml < 2:
+        assert (ri[:nl, 1] == -1).all() and (rv[:nl, 1] < -1e38).all()
+    if nl < n:
+        assert (ri[nl:] == -1).all()
+    # columns
+    cval, cidx = S.max(dim=0)
+    assert (cv[:ml].double() - cval).abs().max() <= tol
+    csrt = torch.sort(S, dim=0, descending=True).values
+    cclear = (csrt[0] - csrt[1] > 2 * tol) if nl > 1 else torch.ones(ml, dtype=torch.bool)
+    assert torch.equal(ci[:ml][cclear], cidx[cclear])
+    if ml < m:
+        assert (ci[ml:] == -1).all()
+    return float(clear1.float().mean())
+
+
+SHAPES = [
+    (1, 1, 8), (1, 2, 8), (5, 3, 16), (128, 256, 64), (129, 257, 64), (300, 280, 64), (127, 255, 72),
+    (700, 1500, 128), (1000, 777, 768), (2048, 2048, 256), (196, 20, 768), (20, 196, 768),
+]
+
+
+@pytest.mark.parametrize("n,m,C", SHAPES)
+@pytest.mark.parametrize("dtype", ["bf16", "tf32"])
+def test_k2_single_cta_schedule(mv, n, m, C, dtype):
+    check(mv, n, m, C, dtype, cluster=0)
+
+
+@pytest.mark.parametrize("n,m,C", [(1, 2, 8), (129, 257, 64), (700, 1500, 128), (1000, 777, 768), (2048, 2048, 256)])
+@pytest.mark.parametrize("dtype", ["bf16", "tf32"])
+@pytest.mark.parametrize("cluster", [2, 4])
+def test_k2_multicast_clusters(mv, n, m, C, dtype, cluster):
+    check(mv, n, m, C, dtype, cluster=cluster)
+
+
+@pytest.mark.parametrize("cluster", [0, 2])
+def test_k2_device_resident_counts_mask_stale_rows(mv, cluster):
+    # live counts on the device, garbage beyond them
+    check(mv, 900, 1100, 64, "bf16", cluster, n_live=611, m_live=1023)
+    check(mv, 900, 1100, 64, "tf32", cluster, n_live=1, m_live=2)
+
+
+def test_k2_exact_ties_go_to_the_lower_index(mv):
+    A = torch.zeros(130, 64)
+    A[:, 0] = 1.0
+    B = torch.zeros(600, 64)
+    B[:, 0] = 1.0  # every similarity is exactly 1
+    rv, ri, cv, ci = run_k2(mv, A, B, "bf16", 0)
+    assert (ri[:, 0] == 0).all() and (ri[:, 1] == 1).all() and (ci == 0).all()
+    assert (rv == 1).all() and (cv == 1).all()
+
+
+def test_k2_repeatable(mv):
+    g = torch.Generator().manual_seed(5)
+    A = torch.randn(1500, 128, generator=g)
+    B = torch.randn(1300, 128, generator=g)
+    a = run_k2(mv, A, B, "bf16", 0)
+    b = run_k2(mv, A, B, "bf16", 0)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("dtype,cluster", [("bf16", 0), ("bf16", 2), ("tf32", 0)])
+def test_k2_full_size_properties(mv, syn, dtype, cluster):
+    """19200 x 19200 x 768 (BASELINE.json stress config): too big for an element-wise CPU check, so
+    size-independent properties: B = A => every row's arg-max is itself, mutual everywhere; and a sampled
+    block of rows against fp32 torch on the device."""
+    A, _ = syn.stress_rows(0, n=19200, m=8, C=768)
+    A = round_operand(A, dtype)
+    rv, ri, cv, ci = run_k2(mv, A, A.clone(), dtype, cluster)
+    ar = torch.arange(19200)
+    assert torch.equal(ri[:, 0], ar) and torch.equal(ci, ar)
+    assert (rv[:, 0] - 1).abs().max() < 1e-2
+    rows = torch.arange(0, 19200, 97)
+    S = A[rows].cuda() @ A.cuda().t()
+    val, idx = torch.topk(S, 3, dim=1)
+    clear = ((val[:, 1] - val[:, 2]) > 1e-3).cpu()
+    assert torch.equal(ri[rows, 1][clear], idx[:, 1].cpu()[clear])
+    assert (rv[rows].cuda() - val[:, :2]).abs().max() < 1e-3

@@ -1,0 +1,163 @@
+"""Kernel 3 pieces against torch / the oracle: distances, ratio weights, mutual flags, top-k, scoring, SPair."""
+from ctypes import c_float, c_void_p
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import restated
+
+pytestmark = pytest.mark.gpu
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.mark.parametrize("n,m,C", [(300, 280, 64), (1, 2, 8), (1000, 900, 768), (257, 513, 2048)])
+@pytest.mark.parametrize("ratio_test", [True, False])
+def test_ratio_mutual(mv, n, m, C, ratio_test):
+    L = mv._lib
+    g = torch.Generator().manual_seed(n + C)
+    X = F.normalize(torch.randn(n, C, generator=g), dim=1)
+    Y = F.normalize(torch.randn(m, C, generator=g), dim=1)
+    o = restated.similarity_top2_and_mutual(X, Y)
+    idx = o["row_idx"].clone()
+    idx[::3] = idx[::3].flip(1)  # hand the kernel some pairs in the wrong order: it must re-rank in fp32
+    col_best = ((o["col_val"].view(torch.int32).long() ^ 0x80000000) << 32)  # placeholder order bits (positive sims)
+    col_best = col_best | (0xFFFFFFFF - o["col_idx"])
+    ridx = idx.to(torch.int32).cuda().contiguous()
+    d = torch.empty(n, 2, device="cuda")
+    w = torch.empty(n, device="cuda")
+    mu = torch.empty(n, dtype=torch.uint8, device="cuda")
+    L.call("mv_k3_ratio_mutual", L.ptr(X.cuda()), L.ptr(Y.cuda()), C, None, n, L.ptr(ridx), L.ptr(col_best.cuda()),
+           int(ratio_test), L.ptr(d), L.ptr(w), L.ptr(mu), stream())
+    want_d = 1 - F.cosine_similarity(Y[o["row_idx"]], X[:, None, :], dim=-1)
+    torch.testing.assert_close(d.cpu(), want_d, rtol=0, atol=1e-6)
+    assert torch.equal(ridx.cpu().long(), o["row_idx"])
+    want_w = restated.ratio_weights(want_d) if ratio_test else want_d[:, 0]
+    torch.testing.assert_close(w.cpu(), want_w, rtol=0, atol=2e-4 if ratio_test else 1e-6)
+    # the weight must be exactly the reference formula applied to the kernel's own distances
+    if ratio_test:
+        torch.testing.assert_close(w.cpu(), restated.ratio_weights(d.cpu()), rtol=0, atol=1e-7)
+    assert torch.equal(mu.cpu().bool(), o["mutual"])
+
+
+@pytest.mark.parametrize("n,k", [(1, 1), (5, 10), (1000, 1000), (19200, 1000), (12544, 500), (3000, 1), (70000, 16384), (1024, 1024)])
+def test_topk_matches(mv, n, k):
+    L = mv._lib
+    g = torch.Generator().manual_seed(n + k)
+    w = torch.randn(n, generator=g)
+    w[n // 2:] = w[: n - n // 2].clone() if n > 3 else w[n // 2:]  # exact duplicates: ties
+    if n > 10:
+        w[3] = float("-inf")
+        w[5] = 1e30
+    idx = torch.randint(0, 1 << 20, (n, 2), generator=g, dtype=torch.int32)
+    kk = min(k, n)
+    src = torch.empty(kk, dtype=torch.int32, device="cuda")
+    dst = torch.empty(kk, dtype=torch.int32, device="cuda")
+    val = torch.empty(kk, device="cuda")
+    kd = torch.zeros(1, dtype=torch.int32, device="cuda")
+    L.call("mv_k3_topk_matches", L.ptr(w.cuda()), L.ptr(idx.cuda()), None, n, k, L.ptr(src), L.ptr(dst), L.ptr(val), L.ptr(kd), stream())
+    assert int(kd.item()) == kk
+    want_v, _ = torch.topk(w, kk)
+    assert torch.equal(val.cpu(), want_v)                       # same multiset, sorted descending
+    s = src.cpu().long()
+    assert torch.equal(w[s], val.cpu()) and s.unique().numel() == kk
+    assert torch.equal(dst.cpu(), idx[s, 0])
+    # ties resolved towards the lower row, and rows ascending inside a tie group
+    same = val.cpu()[1:] == val.cpu()[:-1]
+    assert (s[1:][same] > s[:-1][same]).all()
+    if kk < n:
+        thr = want_v[-1]
+        tied_rows = (w == thr).nonzero().squeeze(1)
+        taken = s[val.cpu() == thr]
+        assert torch.equal(taken, tied_rows[: taken.numel()])
+
+
+def test_topk_device_count(mv):
+    L = mv._lib
+    w = torch.arange(100, dtype=torch.float32)
+    idx = torch.zeros(100, 2, dtype=torch.int32)
+    nd = torch.tensor([40], dtype=torch.int32, device="cuda")
+    src = torch.empty(10, dtype=torch.int32, device="cuda")
+    dst = torch.empty(10, dtype=torch.int32, device="cuda")
+    val = torch.empty(10, device="cuda")
+    L.call("mv_k3_topk_matches", L.ptr(w.cuda()), L.ptr(idx.cuda()), L.ptr(nd), 100, 10, L.ptr(src), L.ptr(dst), L.ptr(val), None, stream())
+    assert src.cpu().tolist() == list(range(39, 29, -1))
+
+
+@pytest.mark.parametrize("k", [1, 100, 1000, 5000])
+def test_score_counts_equal_oracle_recall(mv, syn, k):
+    ev = mv.evaluation
+    g = torch.Generator().manual_seed(k)
+    n0, n1 = 3000, 2500
+    xyz0 = torch.randn(n0, 3, generator=g) + torch.tensor([0.0, 0.0, 4.0])
+    xyz1 = torch.randn(n1, 3, generator=g) + torch.tensor([0.0, 0.0, 4.0])
+    Rt = syn.random_rt(g, max_deg=10.0, t_sigma=0.01)
+    Kmat = torch.tensor([[300.0, 0.0, 80.0], [0.0, 300.0, 60.0], [0.0, 0.0, 1.0]])
+    src = torch.randint(0, n0, (k,), generator=g, dtype=torch.int32)
+    dst = torch.randint(0, n1, (k,), generator=g, dtype=torch.int32)
+    xyz1[dst.long()] = restated.transform_points_Rt(xyz0[src.long()], Rt) + 0.02 * torch.randn(k, 3, generator=g)
+    mutual = (torch.rand(n0, generator=g) < 0.5).to(torch.uint8)
+    thr3 = [0.01, 0.02, 0.05, 0.1, 0.2, 0.3, 0.4, 0.5]
+    thr2 = [1, 2, 5, 15, 25, 35, 50]
+    acc = ev.RecallAccumulator(thr3, thr2, device="cuda")
+    m = mv.correspondence.MatchResult()
+    m.k, m.k_dev = k, None
+    m.sel_src, m.sel_dst, m.mutual = src.cuda(), dst.cuda(), mutual.cuda()
+    e3, e2 = acc.score(m, xyz0.cuda(), xyz1.cuda(), Rt, Kmat, want_errors=True)
+    o3, o2 = restated.pair_errors(xyz0[src.long()], xyz1[dst.long()], Rt, Kmat)
+    torch.testing.assert_close(e3.cpu()[:k], o3, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(e2.cpu()[:k], o2, rtol=1e-4, atol=1e-4)
+    h = acc.hits.cpu().tolist()
+    assert h[0] == k and h[1] == int(mutual[src.long()].sum())
+    # integer counts == counts of the kernel's own errors (exact), and within 0.1 pp of the oracle's recall
+    for i, t in enumerate(thr3):
+        assert h[2 + i] == int((e3.cpu()[:k] < t).sum())
+        assert abs(100.0 * h[2 + i] / k - restated.recall(o3, [t])[0]) <= 0.1 + 100.0 / k
+    for i, t in enumerate(thr2):
+        assert h[2 + len(thr3) + i] == int((e2.cpu()[:k] < t).sum())
+    mu = mutual[src.long()].bool()
+    assert h[2 + len(thr3) + len(thr2)] == int(((e3.cpu()[:k] < thr3[0]) & mu).sum())
+    acc.score(m, xyz0.cuda(), xyz1.cuda(), Rt, Kmat)  # counters accumulate
+    assert acc.hits.cpu().tolist() == [2 * v for v in h]
+
+
+@pytest.mark.parametrize("shape", [(5, 7, 9), (30, 50, 50), (1, 1, 1), (20, 14, 14)])
+def test_argmax_2d(mv, shape):
+    g = torch.Generator().manual_seed(sum(shape))
+    x = torch.randn(*shape, generator=g)
+    x[0].flatten()[::2] = x[0].max() + 1  # ties: first occurrence
+    for mx in (True, False):
+        got = mv.correspondence.argmax_2d(x.cuda(), max_value=mx)
+        assert got.dtype == torch.int64 and got.is_cuda
+        assert torch.equal(got.cpu(), restated.argmax_2d(x, max_value=mx))
+    assert mv.correspondence.argmax_2d(x).device.type == "cpu"
+
+
+@pytest.mark.parametrize("idx", [1, 2, 3])
+@pytest.mark.parametrize("shape", [dict(C=768, h=14, w=14, K=20, image_size=224), dict(C=64, h=50, w=50, K=30, image_size=800)])
+def test_spair_errors(mv, syn, idx, shape):
+    p = syn.spair_pair(idx, **shape)
+    mv.correspondence.set_match_precision(dtype="tf32")
+    try:
+        hits = torch.zeros(2, dtype=torch.int64, device="cuda")
+        es, en, isame, inn, pred = mv.spair.compute_errors_from_features(
+            p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"], p["image_size"], hits=hits, return_heatmap_argmax=True)
+    finally:
+        mv.correspondence.set_match_precision(dtype="bf16")
+    oes, oen, oisame, oinn, heat = restated.spair_compute_errors(p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"],
+                                                                 p["image_size"], return_pred=True)
+    # arg-max identical wherever the oracle's top-2 heat-map gap exceeds 1e-3 (north-star tolerance)
+    flat = heat.flatten(1)
+    top2 = torch.topk(flat, 2, dim=1).values
+    clear = (top2[:, 0] - top2[:, 1]) > 1e-3
+    assert torch.equal(pred[clear], flat.argmax(1)[clear])
+    assert torch.equal(isame, oisame)
+    ok = clear[oisame]
+    torch.testing.assert_close(es[ok], oes[ok], rtol=0, atol=1e-5)
+    torch.testing.assert_close(en[ok], oen[ok], rtol=0, atol=1e-5)
+    assert torch.equal(inn[ok], oinn[ok])
+    h = hits.cpu().tolist()
+    assert h[0] == oisame.numel() and h[1] == int((es < 0.10).sum())

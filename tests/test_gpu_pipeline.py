@@ -1,0 +1,187 @@
+"""End-to-end parity of the reference-facing helpers (called with HOST tensors, like the NAVI / ScanNet
+callers do) against the golden vectors of the reference and against the oracle at BASELINE.json sizes.
+
+Tolerances (north star): NN indices identical wherever the oracle's fp32 top-2 similarity gap exceeds 1e-3;
+recall within 0.1 percentage points; ratio weights to 2e-3 absolute where the neighbours agree."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import restated
+
+pytestmark = pytest.mark.gpu
+
+SCANNET_SMALL = dict(C=64, h=6, w=8, H=24, W=32)
+NAVI_SMALL = dict(C=64, h=8, w=8, H=32, W=32, radius=12.0)
+THR3 = [0.01, 0.02, 0.05, 0.1, 0.2, 0.3, 0.4, 0.5]
+THR2 = [1, 2, 5, 15, 25, 35, 50]
+
+
+def t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def set_equal_modulo_ties(w_got, w_ref, tol):
+    """top-k by weight: the sorted weight vectors must agree to tol (the selected sets can only differ among
+    candidates whose weights are within tol of each other)."""
+    assert w_got.shape == w_ref.shape
+    assert (w_got - w_ref).abs().max() <= tol, float((w_got - w_ref).abs().max())
+
+
+@pytest.mark.parametrize("dtype", ["tf32", "bf16"])
+@pytest.mark.parametrize("tag,coherent", [("coh", True), ("rnd", False)])
+def test_depth_helper_vs_reference_golden(mv, syn, golden, dtype, tag, coherent):
+    g = golden(f"scannet_small_{tag}")
+    p = syn.scannet_pair(7, coherent=coherent, **SCANNET_SMALL)
+    mv.correspondence.set_match_precision(dtype=dtype)
+    try:
+        x0, x1, w = mv.correspondence.estimate_correspondence_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], p["K"].clone(), 100)
+    finally:
+        mv.correspondence.set_match_precision(dtype="bf16")
+    assert x0.device.type == "cpu" and x0.shape == (100, 3) and w.shape == (100,)
+    assert (w[1:] <= w[:-1]).all()
+    tol = 2e-3 if dtype == "tf32" else 2e-2
+    set_equal_modulo_ties(w, t(g["corr_dist"]), tol)
+    # every returned match whose weight is clear of the k-th weight by tol must be in the reference's set
+    ref0 = {tuple(np.round(r, 5)) for r in g["corr_xyz0"]}
+    clear = w > (w[-1] + tol)
+    got0 = [tuple(np.round(r, 5)) for r in x0[clear].numpy()]
+    assert sum(r in ref0 for r in got0) >= 0.97 * len(got0)
+    e3, _ = restated.pair_errors(x0, x1, p["Rt"], p["K"])
+    for th in THR3:
+        r_got = 100.0 * (e3 < th).float().mean().item()
+        r_ref = 100.0 * float((g["err3d"] < th).mean())
+        assert abs(r_got - r_ref) <= 2.0  # k = 100 matches: one match = 1 pp; the 0.1 pp gate is tested at full size
+
+
+@pytest.mark.parametrize("tag,coherent", [("coh", True), ("rnd", False)])
+def test_xyz_helper_vs_reference_golden(mv, syn, golden, tag, coherent):
+    g = golden(f"navi_small_{tag}")
+    p = syn.navi_pair(7, coherent=coherent, **NAVI_SMALL)
+    mv.correspondence.set_match_precision(dtype="tf32")
+    try:
+        out = mv.correspondence.estimate_correspondence_xyz(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], 100)
+        nr = mv.correspondence.estimate_correspondence_xyz(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], 100, ratio_test=False)
+    finally:
+        mv.correspondence.set_match_precision(dtype="bf16")
+    assert [tuple(o.shape) for o in out] == [(100, 3), (100, 3), (100,), (100, 2), (100, 2)]
+    set_equal_modulo_ties(out[2], t(g["c_dist"]), 2e-3)
+    set_equal_modulo_ties(nr[2], t(g["nr_dist"]), 1e-5)
+    # uv are pixel centres of the gathered grid positions
+    assert ((out[3] - 0.5) == (out[3] - 0.5).round()).all()
+
+
+def test_rows_helper_vs_reference_golden(mv, golden):
+    g = golden("rows_small")
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    X = torch.randn(300, 64, generator=gen)
+    Y = torch.randn(280, 64, generator=gen)
+    C_ = mv.correspondence
+    C_.set_match_precision(dtype="tf32")
+    try:
+        d, i = C_.knn_points(X, Y, 2, "cosine")
+        i1, i2, w = C_.get_correspondences_ratio_test(X, Y, 50)
+        b1, b2, bw = C_.get_correspondences_ratio_test(X, Y, 50, bidirectional=True)
+    finally:
+        C_.set_match_precision(dtype="bf16")
+    o = restated.similarity_top2_and_mutual(X, Y)
+    clear = o["row_gap"] > 1e-3
+    assert i.dtype == torch.int64 and torch.equal(i[clear, 0], t(g["idx"])[clear, 0])
+    both = torch.equal(i, t(g["idx"]))
+    if both:
+        torch.testing.assert_close(d, t(g["dists"]), rtol=0, atol=1e-6)
+        assert torch.equal(i1, t(g["idx1"])) and torch.equal(i2, t(g["idx2"]))
+        torch.testing.assert_close(w, t(g["weight"]), rtol=0, atol=1e-5)
+    assert b1.shape == (50,) and bw.shape == (50,)
+    s, tg, v = C_.get_topk_matches(t(g["ratio"]), t(g["idx"])[:, 0], 50)
+    assert torch.equal(s, t(g["idx1"])) and torch.equal(tg, t(g["idx2"]))
+    torch.testing.assert_close(v, t(g["weight"]), rtol=0, atol=0)
+    torch.testing.assert_close(C_.calculate_ratio_test(t(g["dists"])), t(g["ratio"]), rtol=0, atol=0)
+    torch.testing.assert_close(C_.get_grid(3, 5), t(g["grid"]), rtol=0, atol=0)
+
+
+def test_faiss_knn_and_euclidean(mv):
+    gen = torch.Generator().manual_seed(9)
+    X = torch.randn(200, 40, generator=gen) * 3
+    Y = torch.randn(150, 40, generator=gen) * 3
+    d, i = mv.correspondence.faiss_knn(X, Y, 2)
+    od, oi = restated.exact_l2_knn(X, Y, 3)
+    clear = (od[:, 2] - od[:, 1] > 0.05 * od[:, 1]) & (od[:, 1] - od[:, 0] > 0.05 * od[:, 0])
+    assert torch.equal(i[clear], oi[clear][:, :2])
+    torch.testing.assert_close(d[clear], od[clear][:, :2], rtol=1e-4, atol=1e-3)
+    de, ie = mv.correspondence.knn_points(X, Y, 1, "euclidean")
+    assert torch.equal(ie[clear, 0], oi[clear, 0])
+
+
+def full_size_case(mv, kind, dtype, syn):
+    C_ = mv.correspondence
+    if kind == "scannet":
+        p = syn.scannet_pair(1, coherent=True)
+        _, f0, _ = restated.depth_side(p["feat_0"], p["depth_0"], p["K"])
+        _, f1, _ = restated.depth_side(p["feat_1"], p["depth_1"], p["K"])
+        Kmat = p["K"]
+    else:
+        p = syn.navi_pair(1, coherent=True)
+        _, f0, _, _ = restated.xyz_side(p["feat_0"], p["xyz_grid_0"])
+        _, f1, _, _ = restated.xyz_side(p["feat_1"], p["xyz_grid_1"])
+        Kmat = p["intrinsics"]
+    C_.set_match_precision(dtype=dtype)
+    try:
+        if kind == "scannet":
+            got = C_.estimate_correspondence_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], p["K"].clone(), 1000)
+            ref = restated.estimate_correspondence_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], p["K"].clone(), 1000)
+        else:
+            got = C_.estimate_correspondence_xyz(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], 1000)
+            ref = restated.estimate_correspondence_xyz(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], 1000)
+        d, i = C_.knn_points(f0, f1, 2, "cosine")
+    finally:
+        C_.set_match_precision(dtype="bf16")
+    o = restated.similarity_top2_and_mutual(f0, f1)
+    clear = o["row_gap"] > 1e-3
+    frac = float(clear.float().mean())
+    # NN indices identical wherever the reference's top-2 similarity gap exceeds 1e-3
+    assert torch.equal(i[clear, 0], o["row_idx"][clear, 0]), f"{(i[clear,0] != o['row_idx'][clear,0]).sum()} mismatches"
+    e3g, e2g = restated.pair_errors(got[0], got[1], p["Rt"], Kmat)
+    e3r, e2r = restated.pair_errors(ref[0], ref[1], p["Rt"], Kmat)
+    rec = {}
+    for th in THR3:
+        a, b = 100.0 * (e3g < th).float().mean().item(), 100.0 * (e3r < th).float().mean().item()
+        rec[th] = (a, b)
+        assert abs(a - b) <= 0.1 + 1e-6, (kind, dtype, th, a, b)
+    for th in THR2:
+        a, b = 100.0 * (e2g < th).float().mean().item(), 100.0 * (e2r < th).float().mean().item()
+        assert abs(a - b) <= 0.1 + 1e-6, (kind, dtype, th, a, b)
+    return frac, rec
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "tf32"])
+def test_scannet_full_size_parity(mv, syn, dtype):
+    frac, rec = full_size_case(mv, "scannet", dtype, syn)
+    print(f"scannet-shaped {dtype}: rows compared (gap > 1e-3) = {100 * frac:.1f}%, recall@thr (got, ref) = {rec}")
+    assert frac > 0.05
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "tf32"])
+def test_navi_full_size_parity(mv, syn, dtype):
+    frac, rec = full_size_case(mv, "navi", dtype, syn)
+    print(f"navi-shaped {dtype}: rows compared (gap > 1e-3) = {100 * frac:.1f}%, recall@thr (got, ref) = {rec}")
+    assert frac > 0.05
+
+
+def test_fused_scoring_equals_helper_plus_oracle_errors(mv, syn):
+    """evaluation.match_and_score_depth (no host sync, device-resident counts) must give the same integer
+    counts as the synced helper followed by the oracle's error computation."""
+    ev = mv.evaluation
+    p = syn.scannet_pair(2, coherent=True, C=256, h=15, w=20, H=60, W=80)
+    acc_a = ev.RecallAccumulator(THR3, THR2, device="cuda")
+    acc_b = ev.RecallAccumulator(THR3, THR2, device="cuda")
+    ra = ev.match_and_score_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], p["K"], p["Rt"], 500, acc_a, sync=False)
+    rb = ev.match_and_score_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], p["K"], p["Rt"], 500, acc_b, sync=True)
+    assert acc_a.hits.cpu().tolist() == acc_b.hits.cpu().tolist()
+    x0, x1, w = mv.correspondence.estimate_correspondence_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], p["K"].clone(), 500)
+    e3, e2 = restated.pair_errors(x0, x1, p["Rt"], p["K"])
+    s = acc_a.summary()
+    for th in THR3:
+        assert abs(s["recall_3d"][th] - 100.0 * (e3 < th).float().mean().item()) <= 0.2 + 1e-6
+    assert s["scored"] == 500

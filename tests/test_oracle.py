@@ -1,0 +1,96 @@
+"""Pin oracle/restated.py: against the golden vectors produced by the reference's own module
+(tests/golden, made by oracle/make_golden.py) and, where /root/reference is present, against that
+module directly on fresh inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import reference_loader, restated
+
+SCANNET_SMALL = dict(C=64, h=6, w=8, H=24, W=32)
+NAVI_SMALL = dict(C=64, h=8, w=8, H=32, W=32, radius=12.0)
+SPAIR_SMALL = dict(C=64, h=14, w=14, K=20, image_size=224)
+
+
+def t(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+@pytest.mark.parametrize("tag,coherent", [("coh", True), ("rnd", False)])
+def test_scannet_golden(golden, syn, tag, coherent):
+    g = golden(f"scannet_small_{tag}")
+    p = syn.scannet_pair(7, coherent=coherent, **SCANNET_SMALL)
+    assert np.isclose(p["feat_0"].double().sum().item(), float(g["feat_checksum"]), rtol=0, atol=1e-6)
+    x0, x1, w = restated.estimate_correspondence_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], p["K"].clone(), 100)
+    torch.testing.assert_close(w, t(g["corr_dist"]), rtol=0, atol=2e-6)
+    torch.testing.assert_close(x0, t(g["corr_xyz0"]), rtol=0, atol=0)
+    torch.testing.assert_close(x1, t(g["corr_xyz1"]), rtol=0, atol=0)
+    pc = restated.backproject(p["K"].inverse(), p["depth_0"])
+    torch.testing.assert_close(pc, t(g["pointcloud"]), rtol=0, atol=0)
+    xyz, f, _ = restated.depth_side(p["feat_0"], p["depth_0"], p["K"])
+    torch.testing.assert_close(f, t(g["sampled"]), rtol=0, atol=1e-6)
+    e3, _ = restated.pair_errors(x0, x1, p["Rt"], p["K"])
+    torch.testing.assert_close(e3, t(g["err3d"]), rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("tag,coherent", [("coh", True), ("rnd", False)])
+def test_navi_golden(golden, syn, tag, coherent):
+    g = golden(f"navi_small_{tag}")
+    p = syn.navi_pair(7, coherent=coherent, **NAVI_SMALL)
+    out = restated.estimate_correspondence_xyz(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], 100)
+    for a, key in zip(out, ["c_xyz0", "c_xyz1", "c_dist", "c_uv0", "c_uv1"]):
+        torch.testing.assert_close(a, t(g[key]), rtol=0, atol=2e-6 if key == "c_dist" else 0)
+    nr = restated.estimate_correspondence_xyz(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], 100, ratio_test=False)
+    torch.testing.assert_close(nr[2], t(g["nr_dist"]), rtol=0, atol=2e-6)
+
+
+def test_rows_golden(golden):
+    g = golden("rows_small")
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    X = torch.randn(300, 64, generator=gen)
+    Y = torch.randn(280, 64, generator=gen)
+    d, i = restated.knn_points(X, Y, 2, "cosine")
+    assert torch.equal(i, t(g["idx"]))
+    torch.testing.assert_close(d, t(g["dists"]), rtol=0, atol=1e-6)
+    i1, i2, w = restated.correspondences_ratio_test(X, Y, 50)
+    assert torch.equal(i1, t(g["idx1"])) and torch.equal(i2, t(g["idx2"]))
+    torch.testing.assert_close(w, t(g["weight"]), rtol=0, atol=2e-6)
+    torch.testing.assert_close(restated.ratio_weights(t(g["dists"])), t(g["ratio"]), rtol=0, atol=0)
+    hm = t(g["heat"])
+    assert torch.equal(restated.argmax_2d(hm), t(g["argmax"]))
+    assert torch.equal(restated.argmax_2d(hm, max_value=False), t(g["argmin"]))
+    torch.testing.assert_close(restated.pixel_grid(3, 5), t(g["grid"]), rtol=0, atol=0)
+
+
+def test_spair_golden(golden, syn):
+    g = golden("spair_small")
+    p = syn.spair_pair(7, **SPAIR_SMALL)
+    es, en, isame, inn = restated.spair_compute_errors(p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"], p["image_size"])
+    torch.testing.assert_close(es, t(g["error_same"]), rtol=0, atol=1e-6)
+    torch.testing.assert_close(en, t(g["error_nn"]), rtol=0, atol=1e-6)
+    assert torch.equal(isame, t(g["index_same"])) and torch.equal(inn, t(g["index_nn"]))
+
+
+@pytest.mark.skipif(not reference_loader.available(), reason="reference tree not on this machine")
+def test_restated_equals_reference_on_fresh_inputs(syn):
+    ref, ref_tr = reference_loader.load()
+    p = syn.scannet_pair(11, coherent=False, C=32, h=5, w=7, H=20, W=28)
+    a = ref.estimate_correspondence_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], p["K"].clone(), 64)
+    b = restated.estimate_correspondence_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], p["K"].clone(), 64)
+    for x, y in zip(a, b):
+        torch.testing.assert_close(x, y, rtol=0, atol=2e-6)
+    p = syn.navi_pair(11, coherent=False, C=32, h=6, w=6, H=24, W=24, radius=9.0)
+    a = ref.estimate_correspondence_xyz(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], 64)
+    b = restated.estimate_correspondence_xyz(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], 64)
+    for x, y in zip(a, b):
+        torch.testing.assert_close(x, y, rtol=0, atol=2e-6)
+    pts = torch.randn(9, 3)
+    Rt = syn.random_rt(torch.Generator().manual_seed(3))
+    torch.testing.assert_close(ref_tr.transform_points_Rt(pts, Rt), restated.transform_points_Rt(pts, Rt), rtol=0, atol=0)
+
+
+def test_mutual_oracle_is_self_consistent():
+    gen = torch.Generator().manual_seed(1)
+    X = torch.randn(50, 16, generator=gen)
+    r = restated.similarity_top2_and_mutual(X, X.clone())
+    assert r["mutual"].all() and torch.equal(r["row_idx"][:, 0], torch.arange(50))
