@@ -46,6 +46,15 @@ MV_MAX_THRESHOLDS = 16
 
 _lib = None
 
+# kernels launched per entry point (for bench.py's gpu_launches claim); memsets are not counted
+KERNELS_PER_CALL = {
+    "mv_chw_to_hwc": 1, "mv_compact_valid": 1, "mv_geom_backproject": 1, "mv_geom_project_coords": 1,
+    "mv_geom_grid_coords": 1, "mv_geom_keypoint_coords": 1, "mv_k1_sample_normalize": 1, "mv_k2_sim_top2": 2,
+    "mv_k2_unpack_col": 1, "mv_k3_ratio_mutual": 1, "mv_k3_topk_matches": 1, "mv_k3_score": 1, "mv_gather_rows": 1,
+    "mv_argmax_rows": 1, "mv_k3_spair_errors": 1,
+}
+LAUNCHES = {"count": 0}
+
 
 class MvMatchError(RuntimeError):
     pass
@@ -75,6 +84,7 @@ def call(name, *args):
     """Invoke an int-returning entry point; raise MvMatchError with mv_last_error() on failure."""
     lib = load()
     rc = getattr(lib, name)(*args)
+    LAUNCHES["count"] += KERNELS_PER_CALL.get(name, 0)
     if rc != 0:
         msg = lib.mv_last_error()
         raise MvMatchError(f"{name} failed with code {rc}: {msg.decode() if msg else ''}")

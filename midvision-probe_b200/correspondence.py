@@ -35,6 +35,10 @@ _CFG = {
 }
 
 
+# bench.py sets _PROFILE["k2_events"] = [] to collect (start, end, flop) CUDA-event records of kernel 2
+_PROFILE = {}
+
+
 def set_match_precision(dtype=None, cluster=None):
     """Choose kernel 2's operand type ("bf16" | "tf32") and its cluster width (1, 2 or 4)."""
     if dtype is not None:
@@ -121,9 +125,16 @@ def match_rows(A16, A32, B16, B32, n, m, num_corr, ratio_test=True, n_dev=None, 
     ws = _empty((ws_bytes,), torch.uint8, dev)
     A = A32 if tf32 else A16
     B = B32 if tf32 else B16
+    prof = _PROFILE.get("k2_events")
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     L.call("mv_k2_sim_top2", L.ptr(A), L.ptr(B), n, m, C, L.ptr(n_dev), L.ptr(m_dev),
            L.MV_DTYPE_TF32 if tf32 else L.MV_DTYPE_BF16, _CFG["cluster"], L.ptr(row_val), L.ptr(row_idx),
            L.ptr(col_best), L.ptr(ws), c_size_t(ws_bytes), st)
+    if prof is not None:
+        ev1.record()
+        prof.append((ev0, ev1, (n, m, C, n_dev, m_dev)))
     dists = _empty((n, 2), torch.float32, dev)
     weight = _empty((n,), torch.float32, dev)
     mutual = _empty((n,), torch.uint8, dev)

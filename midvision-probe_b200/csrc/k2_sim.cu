@@ -49,7 +49,7 @@ constexpr int K2_SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + COL_
 struct K2Sched {
   // tiles are numbered t = sb * n_ct + ct; cluster c owns [c*T/G, (c+1)*T/G)
   unsigned long long T;  // n_sb * n_ct
-  int G;                 // clusters in the grid
+  int G;                 // clusters that own tiles: min(clusters in the grid, T)
   int n_ct;              // column tiles
   int n_sb;              // super row blocks (MC * 128 rows)
   int p_max;             // most partial records any row can have
@@ -99,7 +99,10 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
   const int n = p.n_dev ? min(*p.n_dev, p.n_max) : p.n_max;
   const int m = p.m_dev ? min(*p.m_dev, p.m_max) : p.m_max;
 
-  const unsigned long long t_beg = sched_begin(p.s, cluster_id), t_end = sched_begin(p.s, cluster_id + 1);
+  // clusters beyond s.G (fewer tiles than clusters) own nothing
+  const bool has_work = cluster_id < p.s.G;
+  const unsigned long long t_beg = has_work ? sched_begin(p.s, cluster_id) : 0ull;
+  const unsigned long long t_end = has_work ? sched_begin(p.s, cluster_id + 1) : 0ull;
   constexpr int KE = TF32 ? 32 : 64;  // K elements per 128-byte row
 
   if (threadIdx.x == 0) {
@@ -370,7 +373,9 @@ K2Sched make_sched(int n_max, int m_max, int mc, int grid) {
   s.n_sb = (n_max + BM * mc - 1) / (BM * mc);
   s.n_ct = (m_max + BN - 1) / BN;
   s.T = (unsigned long long)s.n_sb * s.n_ct;
+  // every cluster below G owns at least one tile, so the clusters that share a row block are consecutive
   s.G = grid / mc;
+  if ((unsigned long long)s.G > s.T) s.G = (int)s.T;
   s.p_max = 1;
   for (int sb = 0; sb < s.n_sb; ++sb) {
     const int a = sched_owner(s, (unsigned long long)sb * s.n_ct);
@@ -382,9 +387,40 @@ K2Sched make_sched(int n_max, int m_max, int mc, int grid) {
 
 int pick_mc(int cta_pair) { return cta_pair == 0 ? 1 : (cta_pair >= 4 ? 4 : 2); }
 
-int k2_grid(int mc) {
-  int sms = mv_sm_count();
-  return (sms / mc) * mc;
+// persistent grid: one CTA per SM, but never more clusters than can be resident at once (GPC
+// boundaries strand SMs for cluster sizes that do not divide a GPC), or the grid runs in two waves
+template <bool TF32, int MC>
+int k2_max_clusters() {
+  static int cached = 0;
+  if (cached) return cached;
+  auto kern = k2_sim_top2_kernel<TF32, MC>;
+  int n = mv_sm_count() / MC;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_BYTES) == cudaSuccess && MC > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(mv_sm_count() / MC * MC);
+    cfg.blockDim = dim3(K2_THREADS);
+    cfg.dynamicSmemBytes = K2_SMEM_BYTES;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = MC;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int act = 0;
+    if (cudaOccupancyMaxActiveClusters(&act, kern, &cfg) == cudaSuccess && act > 0 && act < n) n = act;
+  }
+  (void)cudaGetLastError();
+  cached = n > 0 ? n : 1;
+  return cached;
+}
+
+int k2_grid(int mc, bool tf32) {
+  int clusters;
+  if (mc == 1) clusters = mv_sm_count();
+  else if (mc == 2) clusters = tf32 ? k2_max_clusters<true, 2>() : k2_max_clusters<false, 2>();
+  else clusters = tf32 ? k2_max_clusters<true, 4>() : k2_max_clusters<false, 4>();
+  return clusters * mc;
 }
 
 template <bool TF32, int MC>
@@ -419,7 +455,7 @@ size_t mv_k2_workspace_bytes(int n_max, int m_max) {
   if (n_max <= 0 || m_max <= 0) return 256;
   size_t worst = 0;
   for (int mc = 1; mc <= 4; mc *= 2) {
-    K2Sched s = make_sched(n_max, m_max, mc, k2_grid(mc));
+    K2Sched s = make_sched(n_max, m_max, mc, k2_grid(mc, false));
     size_t b = (size_t)s.n_sb * mc * BM * s.p_max * sizeof(float4);
     if (b > worst) worst = b;
   }
@@ -443,7 +479,7 @@ int mv_k2_sim_top2(const void* A, const void* B, int n_max, int m_max, int C, co
   MV_REQUIRE(cc == 10, MV_E_ARCH, "mv_k2_sim_top2: needs an sm_100 device (found compute capability %d.x)", cc);
 
   const int mc = pick_mc(cta_pair);
-  const int grid = k2_grid(mc);
+  const int grid = k2_grid(mc, tf32);
   K2Params p;
   p.s = make_sched(n_max, m_max, mc, grid);
   const size_t need = (size_t)p.s.n_sb * mc * BM * p.s.p_max * sizeof(float4);
