@@ -113,10 +113,12 @@ int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, cons
  *                               lower column; missing entries = MV_SIM_MASKED / -1.
  *   col_best (m_max) optional : packed arg-max over rows of S[:, j]; decode with mv_k2_unpack_col.
  * A, B: bf16 (MV_DTYPE_BF16) or fp32 (MV_DTYPE_TF32), 16-byte aligned, C % 8 == 0 (bf16) / C % 4 == 0.
- * cta_pair != 0 selects the cta_group::2 (two-SM) schedule.  workspace from mv_k2_workspace_bytes. */
+ * cluster: 0 or 1 = one CTA per SM on its own; 2 or 4 = thread-block clusters of that many CTAs working on
+ * consecutive row blocks with the B tile loaded once and TMA-multicast to all of them.
+ * workspace from mv_k2_workspace_bytes. */
 size_t mv_k2_workspace_bytes(int n_max, int m_max);
 int mv_k2_sim_top2(const void* A, const void* B, int n_max, int m_max, int C, const int32_t* n_dev,
-                   const int32_t* m_dev, int dtype, int cta_pair, float* row_val, int32_t* row_idx,
+                   const int32_t* m_dev, int dtype, int cluster, float* row_val, int32_t* row_idx,
                    unsigned long long* col_best, void* workspace, size_t workspace_bytes, mv_stream_t stream);
 int mv_k2_unpack_col(const unsigned long long* col_best, int m, float* col_val, int32_t* col_idx, mv_stream_t stream);
 

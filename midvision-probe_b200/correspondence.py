@@ -104,7 +104,7 @@ class MatchResult:
     __slots__ = ("k", "k_dev", "sel_src", "sel_dst", "sel_weight", "mutual", "row_idx", "dists", "weight", "col_best")
 
 
-def match_rows(A16, A32, B16, B32, n, m, num_corr, ratio_test=True, n_dev=None, m_dev=None, want_topk=True):
+def match_rows(A16, A32, B16, B32, n, m, num_corr, ratio_test=True, n_dev=None, m_dev=None, want_topk=True, run_k3=True):
     """kernel 2 + kernel 3 on prepared rows.
 
     A16/B16: (n, C)/(m, C) bf16 rows (None when the tf32 path is selected), A32/B32: fp32 rows.
@@ -135,6 +135,9 @@ def match_rows(A16, A32, B16, B32, n, m, num_corr, ratio_test=True, n_dev=None, 
     if prof is not None:
         ev1.record()
         prof.append((ev0, ev1, (n, m, C, n_dev, m_dev)))
+    res.row_idx, res.col_best = row_idx, col_best
+    if not run_k3:  # raw kernel-2 neighbours (inner-product order), no cosine re-ranking
+        return res
     dists = _empty((n, 2), torch.float32, dev)
     weight = _empty((n,), torch.float32, dev)
     mutual = _empty((n,), torch.uint8, dev)
@@ -177,8 +180,9 @@ def _rows_from_features(F, normalize, dev):
 # reference interface: nearest neighbours
 # ------------------------------------------------------------------------------------------------
 def faiss_knn(query, target, k):
-    """Exact L2 k-NN, k <= 2: (squared L2 distances ascending, int64 indices).  correspondence.py:14-23.
+    """L2 k-NN, k <= 2: (squared L2 distances ascending, int64 indices).  correspondence.py:14-23.
 
+    Neighbours are ranked at tf32 precision (kernel 2), their distances recomputed in fp32.
     The search runs on kernel 2 through the identity ||q-t||^2 = ||q||^2 + ||t||^2 - 2 q.t : the rows are
     extended by (1, -||t||^2/2) split into tf32-exact pieces so that the inner-product order is the L2
     order; the returned distances are recomputed in fp32 for the winners.
@@ -212,7 +216,7 @@ def faiss_knn(query, target, k):
     saved = dict(_CFG)
     try:
         _CFG["dtype"] = "tf32"
-        r = match_rows(None, qe, None, te, n, m, 0, want_topk=False)
+        r = match_rows(None, qe, None, te, n, m, 0, want_topk=False, run_k3=False)
     finally:
         _CFG.update(saved)
     idx = r.row_idx[:, :k].long()

@@ -12,14 +12,16 @@
 //   evaluate_spair_correspondence.py:59-79 per-pixel normalise + keypoint grid_sample(align_corners=True)
 //
 // Data layout: the source map is channel-last so that every tap is one contiguous C-vector read with
-// 128-bit loads; consecutive live points are handled by the same CTA so their shared taps hit L1
-// instead of L2 (an 8x upsample re-uses each tap ~8 times along x).
+// 128-bit loads; consecutive live points are handled by the same CTA, which keeps the taps they share
+// in registers (an 8x upsample re-uses each tap ~8 times along x), so the kernel's traffic is the
+// row writes: C*h*w*4 bytes read + n*C*(2 [+4]) bytes written.
+#include <limits.h>
+
 #include "common.cuh"
 
 namespace {
 
-constexpr int K1_THREADS_MAX = 256;
-constexpr int K1_POINTS_PER_CTA = 16;
+constexpr int K1_THREADS_MAX = 1024;
 constexpr float K1_NORM_EPS = 1e-12f;  // F.normalize default eps
 
 // ------------------------------------------------------------------------------------------
@@ -203,7 +205,7 @@ struct K1Params {
   const float* src;
   const float* coords;
   const int32_t* n_dev;
-  int n_max, C, h, w, normalize;
+  int n_max, C, h, w, normalize, pts_per_cta;
   __nv_bfloat16* out_bf16;
   float* out_f32;
   int32_t* taps;
@@ -227,6 +229,12 @@ __device__ __forceinline__ void cubic_coeffs(float t, float c[4]) {
   c[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
 }
 
+// One CTA owns a run of consecutive points and all C channels (thread = 4 * NV channels), so the taps that
+// neighbouring points share stay in REGISTERS instead of being re-read through L1/L2:
+//   bilinear: the raw 2 x 2 tap window is kept; an 8x upsample re-uses it for ~8 consecutive points and a
+//             step to the next source cell loads 2 new taps instead of 4 (same arithmetic as a cold point);
+//   bicubic : the 4 columns of the 4 x 4 window are pre-blended along y (consecutive points of an output row
+//             have the bit-identical y coordinate), so a step in x costs 4 tap loads instead of 16.
 template <int MODE, int NV>
 __global__ void __launch_bounds__(K1_THREADS_MAX) k1_sample_normalize_kernel(K1Params p) {
   __shared__ float red[K1_THREADS_MAX / 32];
@@ -234,8 +242,39 @@ __global__ void __launch_bounds__(K1_THREADS_MAX) k1_sample_normalize_kernel(K1P
   const int n = p.n_dev ? min(*p.n_dev, p.n_max) : p.n_max;
   const int C4 = p.C >> 2;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
-  const int pt_beg = blockIdx.x * K1_POINTS_PER_CTA;
-  const int pt_end = min(pt_beg + K1_POINTS_PER_CTA, n);
+  const int pt_beg = blockIdx.x * p.pts_per_cta;
+  const int pt_end = min(pt_beg + p.pts_per_cta, n);
+
+  // tap cache (see above)
+  constexpr int NWIN = (MODE == MV_SAMPLE_BILINEAR_ZEROS) ? 4 : (MODE == MV_SAMPLE_BICUBIC_CLAMP ? 4 : 1);
+  float4 win[NWIN][NV];
+  int wx = INT_MIN, wy = INT_MIN;
+  float wiy = 0.f;
+
+  auto load_tap = [&](int xx, int yy, float4 (&dst)[NV]) {  // zero outside the map (bilinear zero padding)
+    const bool in = xx >= 0 && xx < p.w && yy >= 0 && yy < p.h;
+    const float* row = p.src + ((size_t)(in ? yy : 0) * p.w + (in ? xx : 0)) * p.C;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      const int c4 = tid + v * blockDim.x;
+      dst[v] = (in && c4 < C4) ? ld4(row + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto load_cubic_col = [&](int xx, int y0, const float (&cy)[4], float4 (&dst)[NV]) {  // sum_i cy[i] * src[clamp(y0-1+i)][clamp(xx)]
+    const int xc = min(max(xx, 0), p.w - 1);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) dst[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int yc = min(max(y0 - 1 + i, 0), p.h - 1);
+      const float* row = p.src + ((size_t)yc * p.w + xc) * p.C;
+#pragma unroll
+      for (int v = 0; v < NV; ++v) {
+        const int c4 = tid + v * blockDim.x;
+        if (c4 < C4) fma4(dst[v], cy[i], ld4(row + 4 * c4));
+      }
+    }
+  };
 
   for (int pt = pt_beg; pt < pt_end; ++pt) {
     float4 acc[NV];
@@ -259,18 +298,27 @@ __global__ void __launch_bounds__(K1_THREADS_MAX) k1_sample_normalize_kernel(K1P
         p.taps[2 * (size_t)pt] = x0;
         p.taps[2 * (size_t)pt + 1] = y0;
       }
+      // window layout: win[0] = (x0, y0) nw, win[1] = (x0+1, y0) ne, win[2] = (x0, y0+1) sw, win[3] = (x0+1, y0+1) se
+      if (y0 == wy && x0 == wx) {
+        // same source cell: every tap is already in registers
+      } else if (y0 == wy && x0 == wx + 1) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) { win[0][v] = win[1][v]; win[2][v] = win[3][v]; }
+        load_tap(x0 + 1, y0, win[1]);
+        load_tap(x0 + 1, y0 + 1, win[3]);
+      } else {
+        load_tap(x0, y0, win[0]);
+        load_tap(x0 + 1, y0, win[1]);
+        load_tap(x0, y0 + 1, win[2]);
+        load_tap(x0 + 1, y0 + 1, win[3]);
+      }
+      wx = x0;
+      wy = y0;
       const float wt[4] = {ws * we, ws * ww, wn * we, wn * ww};  // nw, ne, sw, se
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const int xx = x0 + (k & 1), yy = y0 + (k >> 1);
-        if (xx >= 0 && xx < p.w && yy >= 0 && yy < p.h) {  // uniform across the CTA
-          const float* row = p.src + ((size_t)yy * p.w + xx) * p.C;
 #pragma unroll
-          for (int v = 0; v < NV; ++v) {
-            int c4 = tid + v * blockDim.x;
-            if (c4 < C4) fma4(acc[v], wt[k], ld4(row + 4 * c4));
-          }
-        }
+        for (int v = 0; v < NV; ++v) fma4(acc[v], wt[k], win[k][v]);
       }
     } else {  // MV_SAMPLE_BICUBIC_CLAMP
       const float ix = __ldg(p.coords + 2 * (size_t)pt), iy = __ldg(p.coords + 2 * (size_t)pt + 1);
@@ -283,24 +331,24 @@ __global__ void __launch_bounds__(K1_THREADS_MAX) k1_sample_normalize_kernel(K1P
       float cx[4], cy[4];
       cubic_coeffs(ix - fx, cx);
       cubic_coeffs(iy - fy, cy);
+      // win[j] = y-blended column x0 - 1 + j; valid while iy is bit-identical
+      const bool same_row = (wy == y0) && (__float_as_uint(wiy) == __float_as_uint(iy));
+      if (same_row && x0 == wx) {
+      } else if (same_row && x0 == wx + 1) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int yy = min(max(y0 - 1 + i, 0), p.h - 1);
-        float4 r[NV];
+        for (int v = 0; v < NV; ++v) { win[0][v] = win[1][v]; win[1][v] = win[2][v]; win[2][v] = win[3][v]; }
+        load_cubic_col(x0 + 2, y0, cy, win[3]);
+      } else {
 #pragma unroll
-        for (int v = 0; v < NV; ++v) r[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < 4; ++j) load_cubic_col(x0 - 1 + j, y0, cy, win[j]);
+      }
+      wx = x0;
+      wy = y0;
+      wiy = iy;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int xx = min(max(x0 - 1 + j, 0), p.w - 1);
-          const float* row = p.src + ((size_t)yy * p.w + xx) * p.C;
+      for (int j = 0; j < 4; ++j) {
 #pragma unroll
-          for (int v = 0; v < NV; ++v) {
-            int c4 = tid + v * blockDim.x;
-            if (c4 < C4) fma4(r[v], cx[j], ld4(row + 4 * c4));
-          }
-        }
-#pragma unroll
-        for (int v = 0; v < NV; ++v) fma4(acc[v], cy[i], r[v]);
+        for (int v = 0; v < NV; ++v) fma4(acc[v], cx[j], win[j][v]);
       }
     }
 
@@ -337,7 +385,7 @@ __global__ void __launch_bounds__(K1_THREADS_MAX) k1_sample_normalize_kernel(K1P
           o.z = __fdiv_rn(o.z, denom);
           o.w = __fdiv_rn(o.w, denom);
         }
-        if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (size_t)pt * p.C + 4 * c4) = o;
+        if (p.out_f32) __stcs(reinterpret_cast<float4*>(p.out_f32 + (size_t)pt * p.C + 4 * c4), o);
         if (p.out_bf16) {
           __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
           uint2 pk;
@@ -361,12 +409,6 @@ int launch_k1(const K1Params& p, int threads, int nv, int grid, cudaStream_t st)
     break;
     MV_K1_CASE(1)
     MV_K1_CASE(2)
-    MV_K1_CASE(3)
-    MV_K1_CASE(4)
-    MV_K1_CASE(5)
-    MV_K1_CASE(6)
-    MV_K1_CASE(7)
-    MV_K1_CASE(8)
 #undef MV_K1_CASE
     default:
       mv_set_error("mv_k1_sample_normalize: C too large");
@@ -487,11 +529,16 @@ int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, cons
   p.out_f32 = out_f32;
   p.taps = taps;
 
+  // thread = 4 * nv channels; one CTA = all channels of a run of consecutive points
   const int C4 = C / 4;
-  int threads = ((C4 + 31) / 32) * 32;
-  if (threads > K1_THREADS_MAX) threads = K1_THREADS_MAX;
-  const int nv = (C4 + threads - 1) / threads;
-  const int grid = (n_max + K1_POINTS_PER_CTA - 1) / K1_POINTS_PER_CTA;
+  const int nv = (C4 + K1_THREADS_MAX - 1) / K1_THREADS_MAX;
+  int threads = (((C4 + nv - 1) / nv + 31) / 32) * 32;
+  // long runs amortise the tap loads; at least ~one CTA per SM keeps the machine busy
+  int ppc = (n_max + mv_sm_count() - 1) / mv_sm_count();
+  if (ppc < 8) ppc = 8;
+  if (ppc > 64) ppc = 64;
+  p.pts_per_cta = ppc;
+  const int grid = (n_max + ppc - 1) / ppc;
   cudaStream_t st = mv_cuda_stream(stream);
   if (mode == MV_SAMPLE_BILINEAR_ZEROS) return launch_k1<MV_SAMPLE_BILINEAR_ZEROS>(p, threads, nv, grid, st);
   if (mode == MV_SAMPLE_BICUBIC_CLAMP) return launch_k1<MV_SAMPLE_BICUBIC_CLAMP>(p, threads, nv, grid, st);

@@ -5,7 +5,7 @@
 //   evals/utils/correspondence.py:14-23   faiss.GpuIndexFlatL2(res, C).add(target).search(query, k<=2)
 //   evaluate_spair_correspondence.py:82-83 einsum("k f, f h w -> k h w") + argmax_2d   (row arg-max)
 //
-// Structure (one persistent CTA per SM, 8 warps, warp-specialised):
+// Structure (one persistent CTA per SM, 12 warps, warp-specialised):
 //   warp 0      TMA producer : A tile 128 x 128B and B tile 256 x 128B per k-block into a 4-stage
 //                              128B-swizzled shared-memory ring; with MC > 1 the B tile is loaded in MC
 //                              slices, each multicast to the MC CTAs of the cluster (they work on MC
@@ -13,7 +13,8 @@
 //   warp 1      MMA issuer   : one thread, tcgen05.mma M=128 N=256 K=16 (bf16) / K=8 (tf32), fp32
 //                              accumulators in TMEM, two accumulator buffers (2 x 256 = all 512 columns)
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue     : tcgen05.ld 32 rows x 32 columns per warp; thread = one row of S.
+//   warps 4..11 epilogue     : two warps per TMEM lane quarter, each owning half of the tile's columns;
+//                              tcgen05.ld 32 rows x 32 columns per warp; thread = one row of S.
 //                              rows   : running (max1, idx1, max2, idx2) in registers across the column
 //                                       tiles of a row block; a chunk is only scanned when its maximum
 //                                       beats the current second best
@@ -41,28 +42,40 @@ constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * ROW_BYTES;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * ROW_BYTES;  // 32 KB
 constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-constexpr int K2_THREADS = 256;
+constexpr int K2_THREADS = 384;   // 4 control warps + 8 epilogue warps
 constexpr int EPI_WARP0 = 4;
 constexpr int COL_SMEM_BYTES = 2 * 4 * BN * 8;  // [2 buffers][4 warps][256 columns] (max bits, ballot)
 constexpr int K2_SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + COL_SMEM_BYTES + 256 /*barriers*/;
 
 struct K2Sched {
-  // tiles are numbered t = sb * n_ct + ct; cluster c owns [c*T/G, (c+1)*T/G)
+  // tiles are numbered t = sb * n_ct + ct; cluster c owns [c*T/G, (c+1)*T/G).  Built on the device from the
+  // LIVE row counts, so a problem whose counts only exist in device memory is balanced like any other.
   unsigned long long T;  // n_sb * n_ct
   int G;                 // clusters that own tiles: min(clusters in the grid, T)
   int n_ct;              // column tiles
   int n_sb;              // super row blocks (MC * 128 rows)
-  int p_max;             // most partial records any row can have
 };
 
 struct K2Params {
-  K2Sched s;
   const int32_t* n_dev;
   const int32_t* m_dev;
   int n_max, m_max, kblocks;
-  float4* partial;  // (n_sb * MC * 128, p_max) records {max1, idx1, max2, idx2}
+  int clusters;     // clusters in the grid
+  float4* partial;  // (clusters + n_sb_max) slots of MC * 128 rows x 2 column halves of {max1, idx1, max2, idx2}; slot = cluster + sb
   unsigned long long* col_best;
 };
+
+__host__ __device__ inline K2Sched make_sched(int n, int m, int mc, int clusters) {
+  K2Sched s;
+  s.n_sb = (n + 128 * mc - 1) / (128 * mc);
+  s.n_ct = (m + 256 - 1) / 256;
+  s.T = (unsigned long long)s.n_sb * s.n_ct;
+  // every cluster below G owns at least one tile, so the clusters that share a row block are consecutive
+  s.G = clusters;
+  if ((unsigned long long)s.G > s.T) s.G = (int)s.T;
+  if (s.G < 1) s.G = 1;
+  return s;
+}
 
 __host__ __device__ inline unsigned long long sched_begin(const K2Sched& s, int c) {
   return (unsigned long long)c * s.T / (unsigned long long)s.G;
@@ -99,10 +112,11 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
   const int n = p.n_dev ? min(*p.n_dev, p.n_max) : p.n_max;
   const int m = p.m_dev ? min(*p.m_dev, p.m_max) : p.m_max;
 
-  // clusters beyond s.G (fewer tiles than clusters) own nothing
-  const bool has_work = cluster_id < p.s.G;
-  const unsigned long long t_beg = has_work ? sched_begin(p.s, cluster_id) : 0ull;
-  const unsigned long long t_end = has_work ? sched_begin(p.s, cluster_id + 1) : 0ull;
+  // clusters beyond sch.G (fewer tiles than clusters) own nothing
+  const K2Sched sch = make_sched(n, m, MC, p.clusters);
+  const bool has_work = cluster_id < sch.G && sch.T > 0;
+  const unsigned long long t_beg = has_work ? sched_begin(sch, cluster_id) : 0ull;
+  const unsigned long long t_end = has_work ? sched_begin(sch, cluster_id + 1) : 0ull;
   constexpr int KE = TF32 ? 32 : 64;  // K elements per 128-byte row
 
   if (threadIdx.x == 0) {
@@ -112,7 +126,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&bars->tmem_full[a]), 1);
-      mbar_init(smem_u32(&bars->tmem_empty[a]), 4);
+      mbar_init(smem_u32(&bars->tmem_empty[a]), 8);
     }
     mbar_fence_init();
   }
@@ -132,7 +146,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
       int stage = 0;
       uint32_t phase = 0;
       for (unsigned long long t = t_beg; t < t_end; ++t) {
-        const int sb = (int)(t / (unsigned)p.s.n_ct), ct = (int)(t - (unsigned long long)sb * p.s.n_ct);
+        const int sb = (int)(t / (unsigned)sch.n_ct), ct = (int)(t - (unsigned long long)sb * sch.n_ct);
         const int row0 = (sb * MC + rank) * BM, col0 = ct * BN;
         for (int kb = 0; kb < p.kblocks; ++kb) {
           mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u);
@@ -182,7 +196,10 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
     }
   } else if (warp >= EPI_WARP0) {
     // ===================================== epilogue =========================================
+    // two warps per TMEM lane quarter (one per SM sub-partition pair), each owning half of the tile's columns:
+    // with a single epilogue warp per scheduler the dependent-issue latencies of the reduce chain are exposed
     const int ew = warp & 3;           // TMEM lane quarter this warp may read
+    const int half = (warp - EPI_WARP0) >> 2;  // columns [128 * half, 128 * half + 128) of the tile
     const int e = ew * 32 + lane;      // row inside the tile; also column-combine slot
     float m1 = -CUDART_INF_F, m2 = -CUDART_INF_F;
     int i1 = -1, i2 = -1;
@@ -191,14 +208,12 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
     uint32_t acc_phase = 0;
 
     auto flush = [&](int sb) {
-      const int c_first = sched_owner(p.s, (unsigned long long)sb * p.s.n_ct);
-      const size_t row = (size_t)(sb * MC + rank) * BM + e;
-      p.partial[row * p.s.p_max + (cluster_id - c_first)] =
+      p.partial[((size_t)(cluster_id + sb) * (BM * MC) + rank * BM + e) * 2 + half] =
           make_float4(m1, __int_as_float(i1), m2, __int_as_float(i2));
     };
 
     for (unsigned long long t = t_beg; t < t_end; ++t) {
-      const int sb = (int)(t / (unsigned)p.s.n_ct), ct = (int)(t - (unsigned long long)sb * p.s.n_ct);
+      const int sb = (int)(t / (unsigned)sch.n_ct), ct = (int)(t - (unsigned long long)sb * sch.n_ct);
       if (sb != cur_sb) {
         if (cur_sb >= 0) flush(cur_sb);
         m1 = m2 = -CUDART_INF_F;
@@ -215,7 +230,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
       const uint32_t taddr = tmem_base + (uint32_t)acc * BN + ((uint32_t)(ew * 32) << 16);
 
 #pragma unroll 1
-      for (int ch = 0; ch < BN / 32; ++ch) {
+      for (int ch = half * 4; ch < half * 4 + 4; ++ch) {
         float v[32];
         tmem_ld_32x32(taddr + ch * 32, v);
         const int cb = col0 + ch * 32;
@@ -223,17 +238,27 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
 #pragma unroll
           for (int q = 0; q < 32; ++q) v[q] = (row_ok && cb + q < m) ? v[q] : -CUDART_INF_F;
         }
-        // ---- rows: this thread's row against its running top-2
-        float cm = v[0];
+        // ---- rows: this thread's row against its running top-2.  Only groups of 8 columns whose maximum
+        // beats the current second best are scanned (rare after the first tiles of a row block).
+        float g[4];
 #pragma unroll
-        for (int q = 1; q < 32; ++q) cm = fmaxf(cm, v[q]);
-        if (cm > m2) {
+        for (int u = 0; u < 4; ++u) {
+          const float a = fmaxf(fmaxf(v[8 * u], v[8 * u + 1]), fmaxf(v[8 * u + 2], v[8 * u + 3]));
+          const float b = fmaxf(fmaxf(v[8 * u + 4], v[8 * u + 5]), fmaxf(v[8 * u + 6], v[8 * u + 7]));
+          g[u] = fmaxf(a, b);
+        }
+        if (fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])) > m2) {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            const float x = v[q];
-            if (x > m2) {
-              if (x > m1) { m2 = m1; i2 = i1; m1 = x; i1 = cb + q; }
-              else { m2 = x; i2 = cb + q; }
+          for (int u = 0; u < 4; ++u) {
+            if (g[u] > m2) {
+#pragma unroll
+              for (int q = 8 * u; q < 8 * u + 8; ++q) {
+                const float x = v[q];
+                if (x > m2) {
+                  if (x > m1) { m2 = m1; i2 = i1; m1 = x; i1 = cb + q; }
+                  else { m2 = x; i2 = cb + q; }
+                }
+              }
             }
           }
         }
@@ -252,12 +277,11 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[acc]));
 
-      // combine the 4 warps' column results; thread e owns columns e and e + 128
-      named_bar_sync(1, 128);
+      // combine the 4 warps' column results of this half; thread e owns column e + 128 * half
+      named_bar_sync(1 + half, 128);
       const uint2* colr = col_smem + (size_t)acc * (4 * BN);
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int c = e + h * 128;
+      {
+        const int c = e + half * 128;
         float best = -CUDART_INF_F;
         int brow = 0;
 #pragma unroll
@@ -292,23 +316,27 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
 
 // fold the partial top-2 records of every row; write (n_max, 2) value / index pairs
 template <int MC>
-__global__ void k2_merge_rows_kernel(K2Sched s, const float4* __restrict__ partial, const int32_t* __restrict__ n_dev,
-                                     int n_max, float* __restrict__ row_val, int32_t* __restrict__ row_idx) {
+__global__ void k2_merge_rows_kernel(int clusters, const float4* __restrict__ partial, const int32_t* __restrict__ n_dev,
+                                     int n_max, const int32_t* __restrict__ m_dev, int m_max, float* __restrict__ row_val,
+                                     int32_t* __restrict__ row_idx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_max) return;
   const int n = n_dev ? min(*n_dev, n_max) : n_max;
+  const int m = m_dev ? min(*m_dev, m_max) : m_max;
   float m1 = -CUDART_INF_F, m2 = -CUDART_INF_F;
   int i1 = -1, i2 = -1;
-  if (i < n) {
+  if (i < n && m > 0) {
+    const K2Sched s = make_sched(n, m, MC, clusters);
     const int sb = i / (BM * MC);
     const int c_first = sched_owner(s, (unsigned long long)sb * s.n_ct);
     const int c_last = sched_owner(s, (unsigned long long)(sb + 1) * s.n_ct - 1);
-    for (int q = 0; q <= c_last - c_first; ++q) {
-      const float4 r = partial[(size_t)i * s.p_max + q];
-      const float xs[2] = {r.x, r.z};
-      const int js[2] = {__float_as_int(r.y), __float_as_int(r.w)};
+    for (int c = c_first; c <= c_last; ++c) {
+      const float4* rec = partial + ((size_t)(c + sb) * (BM * MC) + (i - sb * BM * MC)) * 2;
+      const float4 r = rec[0], r2 = rec[1];  // the two column halves of every tile
+      const float xs[4] = {r.x, r.z, r2.x, r2.z};
+      const int js[4] = {__float_as_int(r.y), __float_as_int(r.w), __float_as_int(r2.y), __float_as_int(r2.w)};
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < 4; ++u) {
         if (js[u] < 0) continue;
         if (better(xs[u], js[u], m1, i1)) { m2 = m1; i2 = i1; m1 = xs[u]; i1 = js[u]; }
         else if (better(xs[u], js[u], m2, i2)) { m2 = xs[u]; i2 = js[u]; }
@@ -368,24 +396,12 @@ int make_operand_map(CUtensorMap* tm, const void* base, int rows, int C, bool tf
   return MV_OK;
 }
 
-K2Sched make_sched(int n_max, int m_max, int mc, int grid) {
-  K2Sched s;
-  s.n_sb = (n_max + BM * mc - 1) / (BM * mc);
-  s.n_ct = (m_max + BN - 1) / BN;
-  s.T = (unsigned long long)s.n_sb * s.n_ct;
-  // every cluster below G owns at least one tile, so the clusters that share a row block are consecutive
-  s.G = grid / mc;
-  if ((unsigned long long)s.G > s.T) s.G = (int)s.T;
-  s.p_max = 1;
-  for (int sb = 0; sb < s.n_sb; ++sb) {
-    const int a = sched_owner(s, (unsigned long long)sb * s.n_ct);
-    const int b = sched_owner(s, (unsigned long long)(sb + 1) * s.n_ct - 1);
-    if (b - a + 1 > s.p_max) s.p_max = b - a + 1;
-  }
-  return s;
+size_t k2_partial_bytes(int n_max, int mc, int clusters) {
+  const int n_sb_max = (n_max + BM * mc - 1) / (BM * mc);
+  return (size_t)(clusters + n_sb_max) * (BM * mc) * 2 * sizeof(float4);
 }
 
-int pick_mc(int cta_pair) { return cta_pair == 0 ? 1 : (cta_pair >= 4 ? 4 : 2); }
+int pick_mc(int cluster) { return cluster <= 1 ? 1 : (cluster >= 4 ? 4 : 2); }
 
 // persistent grid: one CTA per SM, but never more clusters than can be resident at once (GPC
 // boundaries strand SMs for cluster sizes that do not divide a GPC), or the grid runs in two waves
@@ -452,18 +468,18 @@ int launch_k2(const CUtensorMap& tmA, const CUtensorMap& tmB, const K2Params& p,
 extern "C" {
 
 size_t mv_k2_workspace_bytes(int n_max, int m_max) {
-  if (n_max <= 0 || m_max <= 0) return 256;
+  (void)m_max;
+  if (n_max <= 0) return 256;
   size_t worst = 0;
   for (int mc = 1; mc <= 4; mc *= 2) {
-    K2Sched s = make_sched(n_max, m_max, mc, k2_grid(mc, false));
-    size_t b = (size_t)s.n_sb * mc * BM * s.p_max * sizeof(float4);
+    const size_t b = k2_partial_bytes(n_max, mc, mv_sm_count() / mc);
     if (b > worst) worst = b;
   }
   return worst + 256;
 }
 
 int mv_k2_sim_top2(const void* A, const void* B, int n_max, int m_max, int C, const int32_t* n_dev,
-                   const int32_t* m_dev, int dtype, int cta_pair, float* row_val, int32_t* row_idx,
+                   const int32_t* m_dev, int dtype, int cluster, float* row_val, int32_t* row_idx,
                    unsigned long long* col_best, void* workspace, size_t workspace_bytes, mv_stream_t stream) {
   MV_REQUIRE(A && B && row_val && row_idx && col_best && workspace, MV_E_ARG, "mv_k2_sim_top2: null pointer");
   MV_REQUIRE(dtype == MV_DTYPE_BF16 || dtype == MV_DTYPE_TF32, MV_E_ARG, "mv_k2_sim_top2: unknown dtype %d", dtype);
@@ -478,11 +494,11 @@ int mv_k2_sim_top2(const void* A, const void* B, int n_max, int m_max, int C, co
   MV_CUDA(cudaDeviceGetAttribute(&cc, cudaDevAttrComputeCapabilityMajor, dev));
   MV_REQUIRE(cc == 10, MV_E_ARCH, "mv_k2_sim_top2: needs an sm_100 device (found compute capability %d.x)", cc);
 
-  const int mc = pick_mc(cta_pair);
+  const int mc = pick_mc(cluster);
   const int grid = k2_grid(mc, tf32);
   K2Params p;
-  p.s = make_sched(n_max, m_max, mc, grid);
-  const size_t need = (size_t)p.s.n_sb * mc * BM * p.s.p_max * sizeof(float4);
+  p.clusters = grid / mc;
+  const size_t need = k2_partial_bytes(n_max, mc, p.clusters);
   MV_REQUIRE(workspace_bytes >= need, MV_E_WORKSPACE, "mv_k2_sim_top2: workspace has %zu bytes, %zu needed",
              workspace_bytes, need);
   p.n_dev = n_dev;
@@ -513,9 +529,9 @@ int mv_k2_sim_top2(const void* A, const void* B, int n_max, int m_max, int C, co
   }
   if (rc) return rc;
   const int mt = 256;
-  if (mc == 1) k2_merge_rows_kernel<1><<<(n_max + mt - 1) / mt, mt, 0, st>>>(p.s, p.partial, n_dev, n_max, row_val, row_idx);
-  else if (mc == 2) k2_merge_rows_kernel<2><<<(n_max + mt - 1) / mt, mt, 0, st>>>(p.s, p.partial, n_dev, n_max, row_val, row_idx);
-  else k2_merge_rows_kernel<4><<<(n_max + mt - 1) / mt, mt, 0, st>>>(p.s, p.partial, n_dev, n_max, row_val, row_idx);
+  if (mc == 1) k2_merge_rows_kernel<1><<<(n_max + mt - 1) / mt, mt, 0, st>>>(p.clusters, p.partial, n_dev, n_max, m_dev, m_max, row_val, row_idx);
+  else if (mc == 2) k2_merge_rows_kernel<2><<<(n_max + mt - 1) / mt, mt, 0, st>>>(p.clusters, p.partial, n_dev, n_max, m_dev, m_max, row_val, row_idx);
+  else k2_merge_rows_kernel<4><<<(n_max + mt - 1) / mt, mt, 0, st>>>(p.clusters, p.partial, n_dev, n_max, m_dev, m_max, row_val, row_idx);
   MV_LAUNCH_CHECK();
   return MV_OK;
 }

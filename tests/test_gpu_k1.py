@@ -110,7 +110,8 @@ def test_keypoint_sampling_align_corners_true(mv, C_, C, h, w, K):
     want = F.grid_sample(fn[None], ndc, mode="bilinear", align_corners=True)[0, :, 0].t()
     src = C_._hwc(feats.cuda(), prenorm=True)
     coords = torch.empty(K, 2, device="cuda")
-    L.call("mv_geom_keypoint_coords", L.ptr(kps.cuda()), 3, K, c_float(size), h, w, L.ptr(coords), C_._stream())
+    kd = kps.cuda()
+    L.call("mv_geom_keypoint_coords", L.ptr(kd), 3, K, c_float(size), h, w, L.ptr(coords), C_._stream())
     _, got = C_._sample(L.MV_SAMPLE_BILINEAR_ZEROS, src, C, h, w, coords, None, K, False, False, True)
     torch.testing.assert_close(got[:K].cpu(), want, rtol=0, atol=ATOL)
 

@@ -27,10 +27,11 @@ def test_ratio_mutual(mv, n, m, C, ratio_test):
     col_best = ((o["col_val"].view(torch.int32).long() ^ 0x80000000) << 32)  # placeholder order bits (positive sims)
     col_best = col_best | (0xFFFFFFFF - o["col_idx"])
     ridx = idx.to(torch.int32).cuda().contiguous()
+    Xd, Yd, cbd = X.cuda(), Y.cuda(), col_best.cuda()  # keep the device copies alive across the launch
     d = torch.empty(n, 2, device="cuda")
     w = torch.empty(n, device="cuda")
     mu = torch.empty(n, dtype=torch.uint8, device="cuda")
-    L.call("mv_k3_ratio_mutual", L.ptr(X.cuda()), L.ptr(Y.cuda()), C, None, n, L.ptr(ridx), L.ptr(col_best.cuda()),
+    L.call("mv_k3_ratio_mutual", L.ptr(Xd), L.ptr(Yd), C, None, n, L.ptr(ridx), L.ptr(cbd),
            int(ratio_test), L.ptr(d), L.ptr(w), L.ptr(mu), stream())
     want_d = 1 - F.cosine_similarity(Y[o["row_idx"]], X[:, None, :], dim=-1)
     torch.testing.assert_close(d.cpu(), want_d, rtol=0, atol=1e-6)
@@ -58,7 +59,8 @@ def test_topk_matches(mv, n, k):
     dst = torch.empty(kk, dtype=torch.int32, device="cuda")
     val = torch.empty(kk, device="cuda")
     kd = torch.zeros(1, dtype=torch.int32, device="cuda")
-    L.call("mv_k3_topk_matches", L.ptr(w.cuda()), L.ptr(idx.cuda()), None, n, k, L.ptr(src), L.ptr(dst), L.ptr(val), L.ptr(kd), stream())
+    wd, idxd = w.cuda(), idx.cuda()
+    L.call("mv_k3_topk_matches", L.ptr(wd), L.ptr(idxd), None, n, k, L.ptr(src), L.ptr(dst), L.ptr(val), L.ptr(kd), stream())
     assert int(kd.item()) == kk
     want_v, _ = torch.topk(w, kk)
     assert torch.equal(val.cpu(), want_v)                       # same multiset, sorted descending
@@ -83,7 +85,8 @@ def test_topk_device_count(mv):
     src = torch.empty(10, dtype=torch.int32, device="cuda")
     dst = torch.empty(10, dtype=torch.int32, device="cuda")
     val = torch.empty(10, device="cuda")
-    L.call("mv_k3_topk_matches", L.ptr(w.cuda()), L.ptr(idx.cuda()), L.ptr(nd), 100, 10, L.ptr(src), L.ptr(dst), L.ptr(val), None, stream())
+    wd, idxd = w.cuda(), idx.cuda()
+    L.call("mv_k3_topk_matches", L.ptr(wd), L.ptr(idxd), L.ptr(nd), 100, 10, L.ptr(src), L.ptr(dst), L.ptr(val), None, stream())
     assert src.cpu().tolist() == list(range(39, 29, -1))
 
 
