@@ -394,6 +394,40 @@ class _Side:
     __slots__ = ("n", "n_dev", "xyz", "uv", "rows16", "rows32", "valid_idx", "taps")
 
 
+def _stage_depth(depth_dev, Kinv):
+    """back-projection + valid-pixel compaction of one image (launches only; the count stays on the device)."""
+    H, W = depth_dev.shape[-2:]
+    dev = depth_dev.device
+    st = _stream()
+    xyz_all = _empty((H * W, 3), torch.float32, dev)
+    L.call("mv_geom_backproject", L.ptr(depth_dev), H, W, Kinv, L.ptr(xyz_all), st)
+    valid_idx = _empty((H * W,), torch.int32, dev)
+    n_dev = _empty((1,), torch.int32, dev)
+    L.call("mv_compact_valid", c_void_p(xyz_all.data_ptr() + 8), 3, H * W, L.ptr(valid_idx), L.ptr(n_dev), st)
+    return xyz_all, valid_idx, n_dev
+
+
+def _finish_depth(f, d, K, staged, n, synced, want_taps=False):
+    """projection to feature-map coordinates + kernel 1 for the n (live or upper-bound) points of one image."""
+    xyz_all, valid_idx, n_dev = staged
+    dev = f.device
+    C, h, w = f.shape
+    H, W = d.shape[-2:]
+    s = _Side()
+    s.n_dev, s.valid_idx, s.n = n_dev, valid_idx, n
+    nd = None if synced else n_dev
+    s.xyz = _empty((max(n, 1), 3), torch.float32, dev)
+    coords = _empty((max(n, 1), 2), torch.float32, dev)
+    if n > 0:
+        L.call("mv_geom_project_coords", L.ptr(xyz_all), L.ptr(valid_idx), L.ptr(nd), n, K, H, W, h, w, L.ptr(s.xyz),
+               L.ptr(coords), _stream())
+    s.taps = _empty((max(n, 1), 2), torch.int32, dev) if want_taps else None
+    s.uv = None
+    s.rows16, s.rows32 = _sample(L.MV_SAMPLE_BILINEAR_ZEROS, _hwc(f), C, h, w, coords, nd, n, True,
+                                 _CFG["dtype"] == "bf16", True, s.taps)
+    return s
+
+
 def prepare_depth_side(feat, depth, K, Kinv, dev, sync=True, want_taps=False):
     """ScanNet-style preparation of one image.  correspondence.py:219-225, :147-176, :47-48.
 
@@ -402,28 +436,37 @@ def prepare_depth_side(feat, depth, K, Kinv, dev, sync=True, want_taps=False):
     """
     f = _f32(feat, dev)
     d = _f32(depth, dev)
+    _check_C(f.shape[0])
+    staged = _stage_depth(d, Kinv)
+    n = int(staged[2].item()) if sync else d.shape[-2] * d.shape[-1]
+    return _finish_depth(f, d, K, staged, n, sync, want_taps)
+
+
+def _stage_xyz(g):
+    """valid-pixel compaction of one (3, H, W) xyz grid (launch only)."""
+    _, H, W = g.shape
+    valid_idx = _empty((H * W,), torch.int32, g.device)
+    n_dev = _empty((1,), torch.int32, g.device)
+    L.call("mv_compact_valid", c_void_p(g.data_ptr() + 2 * H * W * 4), 1, H * W, L.ptr(valid_idx), L.ptr(n_dev), _stream())
+    return valid_idx, n_dev
+
+
+def _finish_xyz(f, g, staged, n, synced, want_taps=False):
+    valid_idx, n_dev = staged
+    dev = f.device
     C, h, w = f.shape
-    _check_C(C)
-    H, W = d.shape[-2:]
-    st = _stream()
-    xyz_all = _empty((H * W, 3), torch.float32, dev)
-    L.call("mv_geom_backproject", L.ptr(d), H, W, Kinv, L.ptr(xyz_all), st)
-    valid_idx = _empty((H * W,), torch.int32, dev)
-    n_dev = _empty((1,), torch.int32, dev)
-    L.call("mv_compact_valid", c_void_p(xyz_all.data_ptr() + 8), 3, H * W, L.ptr(valid_idx), L.ptr(n_dev), st)
+    _, H, W = g.shape
     s = _Side()
-    s.n_dev = n_dev
-    s.valid_idx = valid_idx
-    s.n = int(n_dev.item()) if sync else H * W
-    nd = None if sync else n_dev
-    s.xyz = _empty((max(s.n, 1), 3), torch.float32, dev)
-    coords = _empty((max(s.n, 1), 2), torch.float32, dev)
-    if s.n > 0:
-        L.call("mv_geom_project_coords", L.ptr(xyz_all), L.ptr(valid_idx), L.ptr(nd), s.n, K, H, W, h, w, L.ptr(s.xyz),
-               L.ptr(coords), st)
-    s.taps = _empty((max(s.n, 1), 2), torch.int32, dev) if want_taps else None
-    s.uv = None
-    s.rows16, s.rows32 = _sample(L.MV_SAMPLE_BILINEAR_ZEROS, _hwc(f), C, h, w, coords, nd, s.n, True,
+    s.n_dev, s.valid_idx, s.n = n_dev, valid_idx, n
+    nd = None if synced else n_dev
+    s.xyz = _empty((max(n, 1), 3), torch.float32, dev)
+    s.uv = _empty((max(n, 1), 2), torch.float32, dev)
+    coords = _empty((max(n, 1), 2), torch.float32, dev)
+    if n > 0:
+        L.call("mv_geom_grid_coords", L.ptr(g), L.ptr(valid_idx), L.ptr(nd), n, H, W, h, w, L.ptr(s.xyz), L.ptr(s.uv),
+               L.ptr(coords), _stream())
+    s.taps = _empty((max(n, 1), 2), torch.int32, dev) if want_taps else None
+    s.rows16, s.rows32 = _sample(L.MV_SAMPLE_BICUBIC_CLAMP, _hwc(f), C, h, w, coords, nd, n, True,
                                  _CFG["dtype"] == "bf16", True, s.taps)
     return s
 
@@ -436,28 +479,30 @@ def prepare_xyz_side(feat, xyz_grid, dev, sync=True, want_taps=False):
     """
     f = _f32(feat, dev)
     g = _f32(xyz_grid, dev)
-    C, h, w = f.shape
-    _check_C(C)
-    _, H, W = g.shape
-    st = _stream()
-    valid_idx = _empty((H * W,), torch.int32, dev)
-    n_dev = _empty((1,), torch.int32, dev)
-    L.call("mv_compact_valid", c_void_p(g.data_ptr() + 2 * H * W * 4), 1, H * W, L.ptr(valid_idx), L.ptr(n_dev), st)
-    s = _Side()
-    s.n_dev = n_dev
-    s.valid_idx = valid_idx
-    s.n = int(n_dev.item()) if sync else H * W
-    nd = None if sync else n_dev
-    s.xyz = _empty((max(s.n, 1), 3), torch.float32, dev)
-    s.uv = _empty((max(s.n, 1), 2), torch.float32, dev)
-    coords = _empty((max(s.n, 1), 2), torch.float32, dev)
-    if s.n > 0:
-        L.call("mv_geom_grid_coords", L.ptr(g), L.ptr(valid_idx), L.ptr(nd), s.n, H, W, h, w, L.ptr(s.xyz), L.ptr(s.uv),
-               L.ptr(coords), st)
-    s.taps = _empty((max(s.n, 1), 2), torch.int32, dev) if want_taps else None
-    s.rows16, s.rows32 = _sample(L.MV_SAMPLE_BICUBIC_CLAMP, _hwc(f), C, h, w, coords, nd, s.n, True,
-                                 _CFG["dtype"] == "bf16", True, s.taps)
-    return s
+    _check_C(f.shape[0])
+    staged = _stage_xyz(g)
+    n = int(staged[1].item()) if sync else g.shape[-2] * g.shape[-1]
+    return _finish_xyz(f, g, staged, n, sync, want_taps)
+
+
+def _two_counts(a, b):
+    """both live counts with a single device -> host read."""
+    n0, n1 = torch.cat((a, b)).tolist()
+    return int(n0), int(n1)
+
+
+def _return_packed(parts, in_dev):
+    """the helper's return tuple; for host callers one packed device -> host copy instead of one per tensor."""
+    if in_dev.type == "cuda":
+        return tuple(parts)
+    widths = [p.shape[1] if p.dim() == 2 else 1 for p in parts]
+    host = torch.cat([p.reshape(p.shape[0], -1) for p in parts], dim=1).to(in_dev)
+    out, c = [], 0
+    for p, wd in zip(parts, widths):
+        blk = host[:, c:c + wd]
+        out.append(blk.contiguous() if p.dim() == 2 else blk[:, 0].contiguous())
+        c += wd
+    return tuple(out)
 
 
 def _host_mat(M):
@@ -470,26 +515,33 @@ def estimate_correspondence_depth(feat_0, feat_1, depth_0, depth_1, K, num_corr=
     in_dev = feat_0.device
     Kc = K.detach().float().cpu()
     Kh, Kinv = _host_mat(Kc), _host_mat(Kc.inverse())
-    s0 = prepare_depth_side(feat_0, depth_0, Kh, Kinv, dev)
-    s1 = prepare_depth_side(feat_1, depth_1, Kh, Kinv, dev)
-    if s0.n == 0 or s1.n < 2:
-        raise RuntimeError(f"too few valid points to match ({s0.n} vs {s1.n})")
-    r = match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, s0.n, s1.n, num_corr)
+    # queue every host -> device copy first, then the geometry of both images, then read both counts at once
+    f0, f1, d0, d1 = _f32(feat_0, dev), _f32(feat_1, dev), _f32(depth_0, dev), _f32(depth_1, dev)
+    _check_C(f0.shape[0])
+    a0, a1 = _stage_depth(d0, Kinv), _stage_depth(d1, Kinv)
+    n0, n1 = _two_counts(a0[2], a1[2])
+    if n0 == 0 or n1 < 2:
+        raise RuntimeError(f"too few valid points to match ({n0} vs {n1})")
+    s0 = _finish_depth(f0, d0, Kh, a0, n0, True)
+    s1 = _finish_depth(f1, d1, Kh, a1, n1, True)
+    r = match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, n0, n1, num_corr)
     k = r.k
-    return (_gather(s0.xyz, r.sel_src, k).to(in_dev), _gather(s1.xyz, r.sel_dst, k).to(in_dev),
-            r.sel_weight[:k].to(in_dev))
+    return _return_packed([_gather(s0.xyz, r.sel_src, k), _gather(s1.xyz, r.sel_dst, k), r.sel_weight[:k]], in_dev)
 
 
 def estimate_correspondence_xyz(feat_0, feat_1, xyz_grid_0, xyz_grid_1, num_corr=500, ratio_test=True):
     """(c_xyz0, c_xyz1, c_dist, c_uv0, c_uv1).  correspondence.py:235-263."""
     dev = _device()
     in_dev = feat_0.device
-    s0 = prepare_xyz_side(feat_0, xyz_grid_0, dev)
-    s1 = prepare_xyz_side(feat_1, xyz_grid_1, dev)
-    if s0.n == 0 or s1.n < 2:
-        raise RuntimeError(f"too few valid points to match ({s0.n} vs {s1.n})")
-    r = match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, s0.n, s1.n, num_corr, ratio_test)
+    f0, f1, g0, g1 = _f32(feat_0, dev), _f32(feat_1, dev), _f32(xyz_grid_0, dev), _f32(xyz_grid_1, dev)
+    _check_C(f0.shape[0])
+    a0, a1 = _stage_xyz(g0), _stage_xyz(g1)
+    n0, n1 = _two_counts(a0[1], a1[1])
+    if n0 == 0 or n1 < 2:
+        raise RuntimeError(f"too few valid points to match ({n0} vs {n1})")
+    s0 = _finish_xyz(f0, g0, a0, n0, True)
+    s1 = _finish_xyz(f1, g1, a1, n1, True)
+    r = match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, n0, n1, num_corr, ratio_test)
     k = r.k
-    return (_gather(s0.xyz, r.sel_src, k).to(in_dev), _gather(s1.xyz, r.sel_dst, k).to(in_dev),
-            r.sel_weight[:k].to(in_dev), _gather(s0.uv, r.sel_src, k).to(in_dev),
-            _gather(s1.uv, r.sel_dst, k).to(in_dev))
+    return _return_packed([_gather(s0.xyz, r.sel_src, k), _gather(s1.xyz, r.sel_dst, k), r.sel_weight[:k],
+                           _gather(s0.uv, r.sel_src, k), _gather(s1.uv, r.sel_dst, k)], in_dev)

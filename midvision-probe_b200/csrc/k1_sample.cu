@@ -21,7 +21,9 @@
 
 namespace {
 
-constexpr int K1_THREADS_MAX = 1024;
+constexpr int K1_THREADS_MAX = 768;  // 85 registers per thread: the tap window + a batch of accumulators fit
+constexpr int K1_BATCH = 4;     // points per block-level reduction
+constexpr int K1_MAX_RUN = 64;  // most points one CTA owns
 constexpr float K1_NORM_EPS = 1e-12f;  // F.normalize default eps
 
 // ------------------------------------------------------------------------------------------
@@ -205,7 +207,7 @@ struct K1Params {
   const float* src;
   const float* coords;
   const int32_t* n_dev;
-  int n_max, C, h, w, normalize, pts_per_cta;
+  int n_max, C, h, w, normalize;
   __nv_bfloat16* out_bf16;
   float* out_f32;
   int32_t* taps;
@@ -237,13 +239,18 @@ __device__ __forceinline__ void cubic_coeffs(float t, float c[4]) {
 //             have the bit-identical y coordinate), so a step in x costs 4 tap loads instead of 16.
 template <int MODE, int NV>
 __global__ void __launch_bounds__(K1_THREADS_MAX) k1_sample_normalize_kernel(K1Params p) {
-  __shared__ float red[K1_THREADS_MAX / 32];
-  __shared__ float bcast;
+  __shared__ float red[K1_BATCH][K1_THREADS_MAX / 32];
+  __shared__ float bcast[K1_BATCH];
+  __shared__ float2 s_coords[K1_MAX_RUN];
   const int n = p.n_dev ? min(*p.n_dev, p.n_max) : p.n_max;
   const int C4 = p.C >> 2;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
-  const int pt_beg = blockIdx.x * p.pts_per_cta;
-  const int pt_end = min(pt_beg + p.pts_per_cta, n);
+  // run length from the LIVE point count: every CTA of the (host-sized) grid gets an equal share, so a
+  // device-resident count far below n_max does not leave most SMs idle
+  int ppc = (n + (int)gridDim.x - 1) / (int)gridDim.x;
+  ppc = min(max((ppc + K1_BATCH - 1) / K1_BATCH * K1_BATCH, K1_BATCH), K1_MAX_RUN);
+  const int pt_beg = blockIdx.x * ppc;
+  const int pt_end = min(pt_beg + ppc, n);
 
   // tap cache (see above)
   constexpr int NWIN = (MODE == MV_SAMPLE_BILINEAR_ZEROS) ? 4 : (MODE == MV_SAMPLE_BICUBIC_CLAMP ? 4 : 1);
@@ -276,127 +283,151 @@ __global__ void __launch_bounds__(K1_THREADS_MAX) k1_sample_normalize_kernel(K1P
     }
   };
 
-  for (int pt = pt_beg; pt < pt_end; ++pt) {
-    float4 acc[NV];
-#pragma unroll
-    for (int v = 0; v < NV; ++v) acc[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+  // source coordinates of the whole run, once, coalesced (kills the coords -> address latency per point)
+  if (MODE != MV_SAMPLE_ROWS) {
+    for (int q = tid; q < pt_end - pt_beg; q += blockDim.x)
+      s_coords[q] = __ldg(reinterpret_cast<const float2*>(p.coords) + pt_beg + q);
+    __syncthreads();
+  }
 
-    if (MODE == MV_SAMPLE_ROWS) {
-      const float* row = p.src + (size_t)pt * p.C;
+  // points are processed K1_BATCH at a time: one pair of block barriers (the L2-norm reduction) per batch
+  for (int pt0 = pt_beg; pt0 < pt_end; pt0 += K1_BATCH) {
+    float4 acc[K1_BATCH][NV];
+#pragma unroll
+    for (int b = 0; b < K1_BATCH; ++b) {
+#pragma unroll
+      for (int v = 0; v < NV; ++v) acc[b][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int pt = pt0 + b;
+      if (pt >= pt_end) continue;
+
+      if (MODE == MV_SAMPLE_ROWS) {
+        const float* row = p.src + (size_t)pt * p.C;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          int c4 = tid + v * blockDim.x;
+          if (c4 < C4) acc[b][v] = ld4(row + 4 * c4);
+        }
+      } else if (MODE == MV_SAMPLE_BILINEAR_ZEROS) {
+        // ATen GridSamplerKernel.cpp (bilinear, zeros): w = ix - floor(ix), e = 1 - w, n = iy - floor(iy), s = 1 - n
+        const float ix = s_coords[pt - pt_beg].x, iy = s_coords[pt - pt_beg].y;
+        const float fx = floorf(ix), fy = floorf(iy);
+        const int x0 = (int)fx, y0 = (int)fy;
+        const float ww = ix - fx, we = 1.f - ww, wn = iy - fy, ws = 1.f - wn;
+        if (p.taps && tid == 0) {
+          p.taps[2 * (size_t)pt] = x0;
+          p.taps[2 * (size_t)pt + 1] = y0;
+        }
+        // window layout: win[0] = (x0, y0) nw, win[1] = (x0+1, y0) ne, win[2] = (x0, y0+1) sw, win[3] = (x0+1, y0+1) se
+        if (y0 == wy && x0 == wx) {
+          // same source cell: every tap is already in registers
+        } else if (y0 == wy && x0 == wx + 1) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) { win[0][v] = win[1][v]; win[2][v] = win[3][v]; }
+          load_tap(x0 + 1, y0, win[1]);
+          load_tap(x0 + 1, y0 + 1, win[3]);
+        } else {
+          load_tap(x0, y0, win[0]);
+          load_tap(x0 + 1, y0, win[1]);
+          load_tap(x0, y0 + 1, win[2]);
+          load_tap(x0 + 1, y0 + 1, win[3]);
+        }
+        wx = x0;
+        wy = y0;
+        const float wt[4] = {ws * we, ws * ww, wn * we, wn * ww};  // nw, ne, sw, se
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) fma4(acc[b][v], wt[k], win[k][v]);
+        }
+      } else {  // MV_SAMPLE_BICUBIC_CLAMP
+        const float ix = s_coords[pt - pt_beg].x, iy = s_coords[pt - pt_beg].y;
+        const float fx = floorf(ix), fy = floorf(iy);
+        const int x0 = (int)fx, y0 = (int)fy;
+        if (p.taps && tid == 0) {
+          p.taps[2 * (size_t)pt] = x0;
+          p.taps[2 * (size_t)pt + 1] = y0;
+        }
+        float cx[4], cy[4];
+        cubic_coeffs(ix - fx, cx);
+        cubic_coeffs(iy - fy, cy);
+        // win[j] = y-blended column x0 - 1 + j; valid while iy is bit-identical
+        const bool same_row = (wy == y0) && (__float_as_uint(wiy) == __float_as_uint(iy));
+        if (same_row && x0 == wx) {
+        } else if (same_row && x0 == wx + 1) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) { win[0][v] = win[1][v]; win[1][v] = win[2][v]; win[2][v] = win[3][v]; }
+          load_cubic_col(x0 + 2, y0, cy, win[3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) load_cubic_col(x0 - 1 + j, y0, cy, win[j]);
+        }
+        wx = x0;
+        wy = y0;
+        wiy = iy;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+          for (int v = 0; v < NV; ++v) fma4(acc[b][v], cx[j], win[j][v]);
+        }
+      }
+    }
+
+    float denom[K1_BATCH];
+#pragma unroll
+    for (int b = 0; b < K1_BATCH; ++b) denom[b] = 1.f;
+    if (p.normalize) {
+#pragma unroll
+      for (int b = 0; b < K1_BATCH; ++b) {
+        float ss = 0.f;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          ss = fmaf(acc[b][v].x, acc[b][v].x, ss);
+          ss = fmaf(acc[b][v].y, acc[b][v].y, ss);
+          ss = fmaf(acc[b][v].z, acc[b][v].z, ss);
+          ss = fmaf(acc[b][v].w, acc[b][v].w, ss);
+        }
+        ss = warp_sum(ss);
+        if (lane == 0) red[b][wid] = ss;
+      }
+      __syncthreads();
+      for (int b = wid; b < K1_BATCH; b += nwarp) {  // warp b finishes point b
+        float t = (lane < nwarp) ? red[b][lane] : 0.f;
+        t = warp_sum(t);
+        if (lane == 0) bcast[b] = __frcp_rn(fmaxf(sqrtf(t), K1_NORM_EPS));
+      }
+      __syncthreads();
+#pragma unroll
+      for (int b = 0; b < K1_BATCH; ++b) denom[b] = bcast[b];
+    }
+
+#pragma unroll
+    for (int b = 0; b < K1_BATCH; ++b) {
+      const int pt = pt0 + b;
+      if (pt >= pt_end) continue;
 #pragma unroll
       for (int v = 0; v < NV; ++v) {
         int c4 = tid + v * blockDim.x;
-        if (c4 < C4) acc[v] = ld4(row + 4 * c4);
-      }
-    } else if (MODE == MV_SAMPLE_BILINEAR_ZEROS) {
-      // ATen GridSamplerKernel.cpp (bilinear, zeros): w = ix - floor(ix), e = 1 - w, n = iy - floor(iy), s = 1 - n
-      const float ix = __ldg(p.coords + 2 * (size_t)pt), iy = __ldg(p.coords + 2 * (size_t)pt + 1);
-      const float fx = floorf(ix), fy = floorf(iy);
-      const int x0 = (int)fx, y0 = (int)fy;
-      const float ww = ix - fx, we = 1.f - ww, wn = iy - fy, ws = 1.f - wn;
-      if (p.taps && tid == 0) {
-        p.taps[2 * (size_t)pt] = x0;
-        p.taps[2 * (size_t)pt + 1] = y0;
-      }
-      // window layout: win[0] = (x0, y0) nw, win[1] = (x0+1, y0) ne, win[2] = (x0, y0+1) sw, win[3] = (x0+1, y0+1) se
-      if (y0 == wy && x0 == wx) {
-        // same source cell: every tap is already in registers
-      } else if (y0 == wy && x0 == wx + 1) {
-#pragma unroll
-        for (int v = 0; v < NV; ++v) { win[0][v] = win[1][v]; win[2][v] = win[3][v]; }
-        load_tap(x0 + 1, y0, win[1]);
-        load_tap(x0 + 1, y0 + 1, win[3]);
-      } else {
-        load_tap(x0, y0, win[0]);
-        load_tap(x0 + 1, y0, win[1]);
-        load_tap(x0, y0 + 1, win[2]);
-        load_tap(x0 + 1, y0 + 1, win[3]);
-      }
-      wx = x0;
-      wy = y0;
-      const float wt[4] = {ws * we, ws * ww, wn * we, wn * ww};  // nw, ne, sw, se
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-#pragma unroll
-        for (int v = 0; v < NV; ++v) fma4(acc[v], wt[k], win[k][v]);
-      }
-    } else {  // MV_SAMPLE_BICUBIC_CLAMP
-      const float ix = __ldg(p.coords + 2 * (size_t)pt), iy = __ldg(p.coords + 2 * (size_t)pt + 1);
-      const float fx = floorf(ix), fy = floorf(iy);
-      const int x0 = (int)fx, y0 = (int)fy;
-      if (p.taps && tid == 0) {
-        p.taps[2 * (size_t)pt] = x0;
-        p.taps[2 * (size_t)pt + 1] = y0;
-      }
-      float cx[4], cy[4];
-      cubic_coeffs(ix - fx, cx);
-      cubic_coeffs(iy - fy, cy);
-      // win[j] = y-blended column x0 - 1 + j; valid while iy is bit-identical
-      const bool same_row = (wy == y0) && (__float_as_uint(wiy) == __float_as_uint(iy));
-      if (same_row && x0 == wx) {
-      } else if (same_row && x0 == wx + 1) {
-#pragma unroll
-        for (int v = 0; v < NV; ++v) { win[0][v] = win[1][v]; win[1][v] = win[2][v]; win[2][v] = win[3][v]; }
-        load_cubic_col(x0 + 2, y0, cy, win[3]);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 4; ++j) load_cubic_col(x0 - 1 + j, y0, cy, win[j]);
-      }
-      wx = x0;
-      wy = y0;
-      wiy = iy;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-#pragma unroll
-        for (int v = 0; v < NV; ++v) fma4(acc[v], cx[j], win[j][v]);
-      }
-    }
-
-    float denom = 1.f;
-    if (p.normalize) {
-      float ss = 0.f;
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        ss = fmaf(acc[v].x, acc[v].x, ss);
-        ss = fmaf(acc[v].y, acc[v].y, ss);
-        ss = fmaf(acc[v].z, acc[v].z, ss);
-        ss = fmaf(acc[v].w, acc[v].w, ss);
-      }
-      ss = warp_sum(ss);
-      if (lane == 0) red[wid] = ss;
-      __syncthreads();
-      if (wid == 0) {
-        float t = (lane < nwarp) ? red[lane] : 0.f;
-        t = warp_sum(t);
-        if (lane == 0) bcast = fmaxf(sqrtf(t), K1_NORM_EPS);
-      }
-      __syncthreads();
-      denom = bcast;
-    }
-
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      int c4 = tid + v * blockDim.x;
-      if (c4 < C4) {
-        float4 o = acc[v];
-        if (p.normalize) {
-          o.x = __fdiv_rn(o.x, denom);
-          o.y = __fdiv_rn(o.y, denom);
-          o.z = __fdiv_rn(o.z, denom);
-          o.w = __fdiv_rn(o.w, denom);
-        }
-        if (p.out_f32) __stcs(reinterpret_cast<float4*>(p.out_f32 + (size_t)pt * p.C + 4 * c4), o);
-        if (p.out_bf16) {
-          __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
-          uint2 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&lo);
-          pk.y = *reinterpret_cast<uint32_t*>(&hi);
-          *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)pt * p.C + 4 * c4) = pk;
+        if (c4 < C4) {
+          float4 o = acc[b][v];
+          if (p.normalize) {  // x * (1 / max(||x||, eps)): within 1 ulp of F.normalize's division
+            o.x *= denom[b];
+            o.y *= denom[b];
+            o.z *= denom[b];
+            o.w *= denom[b];
+          }
+          if (p.out_f32) __stcs(reinterpret_cast<float4*>(p.out_f32 + (size_t)pt * p.C + 4 * c4), o);
+          if (p.out_bf16) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&lo);
+            pk.y = *reinterpret_cast<uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)pt * p.C + 4 * c4) = pk;
+          }
         }
       }
     }
-    // `red`/`bcast` are rewritten next iteration only after the first __syncthreads there,
-    // and every thread has read `bcast` before it can pass that barrier: no extra barrier needed.
+    // `red`/`bcast` are rewritten next batch only after the first __syncthreads there, and every thread
+    // has read `bcast` before it can pass that barrier: no extra barrier needed.
   }
 }
 
@@ -533,12 +564,13 @@ int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, cons
   const int C4 = C / 4;
   const int nv = (C4 + K1_THREADS_MAX - 1) / K1_THREADS_MAX;
   int threads = (((C4 + nv - 1) / nv + 31) / 32) * 32;
-  // long runs amortise the tap loads; at least ~one CTA per SM keeps the machine busy
-  int ppc = (n_max + mv_sm_count() - 1) / mv_sm_count();
-  if (ppc < 8) ppc = 8;
-  if (ppc > 64) ppc = 64;
-  p.pts_per_cta = ppc;
-  const int grid = (n_max + ppc - 1) / ppc;
+  // long runs amortise the tap loads, ~one CTA per SM keeps the machine busy; the kernel re-derives the run
+  // length from the live count, the grid only has to cover n_max at the longest run (K1_MAX_RUN)
+  int grid = mv_sm_count() * (threads <= 384 ? 2 : 1);
+  const int need = (n_max + K1_MAX_RUN - 1) / K1_MAX_RUN;
+  if (grid < need) grid = need;
+  const int most = (n_max + K1_BATCH - 1) / K1_BATCH;
+  if (grid > most) grid = most;
   cudaStream_t st = mv_cuda_stream(stream);
   if (mode == MV_SAMPLE_BILINEAR_ZEROS) return launch_k1<MV_SAMPLE_BILINEAR_ZEROS>(p, threads, nv, grid, st);
   if (mode == MV_SAMPLE_BICUBIC_CLAMP) return launch_k1<MV_SAMPLE_BICUBIC_CLAMP>(p, threads, nv, grid, st);

@@ -13,7 +13,7 @@ import torch
 from . import _lib as L
 from . import correspondence as C_
 
-__all__ = ["RecallAccumulator", "shard_pairs", "match_and_score_depth", "match_and_score_xyz"]
+__all__ = ["RecallAccumulator", "shard_pairs", "match_and_score_depth", "match_and_score_xyz", "GraphedPairMatcher"]
 
 
 def shard_pairs(num_pairs, rank, world):
@@ -104,3 +104,80 @@ def match_and_score_xyz(feat_0, feat_1, xyz_grid_0, xyz_grid_1, intrinsics, Rt, 
                       n_dev=None if sync else s0.n_dev, m_dev=None if sync else s1.n_dev)
     acc.score(r, s0.xyz, s1.xyz, Rt, intrinsics)
     return r
+
+
+class GraphedPairMatcher:
+    """The per-pair device pipeline (kernel 1 for both images, kernel 2, kernel 3 ratio / mutual / top-k)
+    captured ONCE into a CUDA graph and replayed per pair: the ~25 launches of a pair cost one graph launch,
+    so small pairs are no longer bound by host launch overhead.
+
+    Shapes are fixed at construction; live point counts stay on the device (n_dev), so no host sync is
+    needed between pairs.  Inputs are copied into static buffers (device -> device, or straight from
+    pinned host memory), then `run()` replays the graph and scores the pair into a RecallAccumulator.
+
+    kind = "xyz"   NAVI-shaped   : feats (C, h, w) x2 + xyz grids (3, H, W) x2
+    kind = "depth" ScanNet-shaped: feats (C, h, w) x2 + depth (1, H, W) x2 + K (fixed for the matcher)
+    """
+
+    def __init__(self, kind, feat_shape, grid_shape, num_corr, K=None, device=None):
+        if kind not in ("xyz", "depth"):
+            raise ValueError(kind)
+        self.kind, self.num_corr = kind, int(num_corr)
+        self.dev = device or C_._device()
+        self.f0 = torch.zeros(feat_shape, dtype=torch.float32, device=self.dev)
+        self.f1 = torch.zeros(feat_shape, dtype=torch.float32, device=self.dev)
+        self.g0 = torch.zeros(grid_shape, dtype=torch.float32, device=self.dev)
+        self.g1 = torch.zeros(grid_shape, dtype=torch.float32, device=self.dev)
+        if kind == "depth":
+            Kc = K.detach().float().cpu()
+            self.Kc, self.Kh, self.Kinv = Kc, C_._host_mat(Kc), C_._host_mat(Kc.inverse())
+        self.graph = None
+        self.out = None
+
+    def _body(self):
+        if self.kind == "xyz":
+            s0 = C_.prepare_xyz_side(self.f0, self.g0, self.dev, sync=False)
+            s1 = C_.prepare_xyz_side(self.f1, self.g1, self.dev, sync=False)
+        else:
+            s0 = C_.prepare_depth_side(self.f0, self.g0, self.Kh, self.Kinv, self.dev, sync=False)
+            s1 = C_.prepare_depth_side(self.f1, self.g1, self.Kh, self.Kinv, self.dev, sync=False)
+        r = C_.match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, s0.n, s1.n, self.num_corr, n_dev=s0.n_dev, m_dev=s1.n_dev)
+        return s0, s1, r
+
+    def capture(self):
+        """warm up (first-call attribute / entry-point initialisation must not happen under capture), then capture."""
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self._body()
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = self._body()
+        return self
+
+    def load(self, feat_0, feat_1, grid_0, grid_1):
+        """stage one pair's inputs (any device; pinned host memory makes the copies asynchronous)."""
+        self.f0.copy_(feat_0, non_blocking=True)
+        self.f1.copy_(feat_1, non_blocking=True)
+        self.g0.copy_(grid_0, non_blocking=True)
+        self.g1.copy_(grid_1, non_blocking=True)
+
+    def run(self, acc=None, Rt=None, K=None):
+        """replay the captured pipeline on the staged inputs; optionally score into `acc`."""
+        if self.graph is None:
+            self.capture()
+        self.graph.replay()
+        L.LAUNCHES["count"] += self.launches_per_replay
+        s0, s1, r = self.out
+        if acc is not None:
+            acc.score(r, s0.xyz, s1.xyz, Rt, K if K is not None else self.Kc)
+        return r
+
+    @property
+    def launches_per_replay(self):
+        # per image: (backproject) + compact + coords + chw_to_hwc + kernel 1; per pair: kernel 2 (2) + ratio + top-k
+        per_side = 5 if self.kind == "depth" else 4
+        return 2 * per_side + 4

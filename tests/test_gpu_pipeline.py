@@ -185,3 +185,30 @@ def test_fused_scoring_equals_helper_plus_oracle_errors(mv, syn):
     for th in THR3:
         assert abs(s["recall_3d"][th] - 100.0 * (e3 < th).float().mean().item()) <= 0.2 + 1e-6
     assert s["scored"] == 500
+
+
+@pytest.mark.parametrize("kind", ["xyz", "depth"])
+def test_cuda_graph_replay_equals_eager(mv, syn, kind):
+    """GraphedPairMatcher (captured once, replayed per pair with inputs staged into static buffers) must give
+    the same integer counts and the same selected matches as the eager launches, pair after pair."""
+    ev = mv.evaluation
+    if kind == "xyz":
+        pairs = [syn.navi_pair(i, C=256, h=14, w=14, H=56, W=56, radius=20.0) for i in range(3)]
+        gk = ("xyz_grid_0", "xyz_grid_1", "intrinsics")
+    else:
+        pairs = [syn.scannet_pair(i, C=256, h=15, w=20, H=60, W=80) for i in range(3)]
+        gk = ("depth_0", "depth_1", "K")
+    gm = ev.GraphedPairMatcher(kind, tuple(pairs[0]["feat_0"].shape), tuple(pairs[0][gk[0]].shape), 300, K=pairs[0].get("K")).capture()
+    for p in pairs + pairs[:1]:
+        a = ev.RecallAccumulator(THR3, THR2, device="cuda")
+        b = ev.RecallAccumulator(THR3, THR2, device="cuda")
+        gm.load(p["feat_0"], p["feat_1"], p[gk[0]], p[gk[1]])
+        rg = gm.run(a, p["Rt"], p[gk[2]])
+        if kind == "xyz":
+            re_ = ev.match_and_score_xyz(p["feat_0"], p["feat_1"], p[gk[0]], p[gk[1]], p[gk[2]], p["Rt"], 300, b, sync=True)
+        else:
+            re_ = ev.match_and_score_depth(p["feat_0"], p["feat_1"], p[gk[0]], p[gk[1]], p[gk[2]], p["Rt"], 300, b, sync=True)
+        assert a.hits.cpu().tolist() == b.hits.cpu().tolist()
+        k = re_.k
+        assert int(rg.k_dev.item()) == k
+        assert torch.equal(rg.sel_src[:k], re_.sel_src[:k]) and torch.equal(rg.sel_weight[:k], re_.sel_weight[:k])
