@@ -8,8 +8,8 @@ CUDA path, the oracle and the committed golden vectors see bit-identical inputs 
     C3 scannet_pair  feats (2048, 15, 20) x2, depth (1, 120, 160)    ResNet-50 layer4 @ 480x640
     C5 stress_rows   A, B (19200, 768) L2-normalised rows
 
-`coherent=True` makes image 1 a noisy, rigidly moved copy of image 0 so that recall is neither 0 nor 100 and
-a wrong match changes it.
+`coherent=True` makes image 1 a noisy copy of image 0 over a smooth surface, so that recall is neither 0 nor 100,
+near-miss matches land between the thresholds and a wrong match changes the counts.
 """
 import math
 
@@ -33,7 +33,7 @@ def random_rt(g, max_deg=120.0, t_sigma=0.1):
     return torch.cat((R, t[:, None]), dim=1).float()
 
 
-def _feature_pair(g, C, h, w, coherent, noise=0.5):
+def _feature_pair(g, C, h, w, coherent, noise=3.0):
     f0 = torch.randn(C, h, w, generator=g)
     if coherent:
         f1 = f0 + noise * torch.randn(C, h, w, generator=g)
@@ -46,12 +46,14 @@ def scannet_pair(index, C=2048, h=15, w=20, H=120, W=160, zero_frac=0.05, cohere
     """ScanNet-shaped pair (render_scannet_correspondence.py:188-208 after the 0.25 rescale)."""
     g = _gen(config, index)
     f0, f1 = _feature_pair(g, C, h, w, coherent)
-    d0 = 0.3 + 4.0 * torch.rand(1, H, W, generator=g)
+    ys, xs = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
+    # smooth surface + a little roughness: a one-pixel mismatch is centimetres, not metres
+    d0 = (2.0 + 0.8 * torch.sin(xs / 17.0) * torch.cos(ys / 13.0) + 0.01 * torch.rand(H, W, generator=g))[None]
     if coherent:
         d1 = d0.clone()
         Rt = torch.cat((torch.eye(3), torch.zeros(3, 1)), dim=1)
     else:
-        d1 = 0.3 + 4.0 * torch.rand(1, H, W, generator=g)
+        d1 = (2.2 + 0.7 * torch.cos(xs / 15.0) * torch.sin(ys / 11.0) + 0.01 * torch.rand(H, W, generator=g))[None]
         Rt = random_rt(g)
     d0[torch.rand(1, H, W, generator=g) < zero_frac] = 0.0
     d1[torch.rand(1, H, W, generator=g) < zero_frac] = 0.0
@@ -63,12 +65,16 @@ def scannet_pair(index, C=2048, h=15, w=20, H=120, W=160, zero_frac=0.05, cohere
 def navi_pair(index, C=3072, h=28, w=28, H=112, W=112, radius=40.0, coherent=True, config=2):
     """NAVI-shaped pair (evaluate_navi_correspondence.py:143-181): xyz grid valid inside a disc."""
     g = _gen(config, index)
-    f0, f1 = _feature_pair(g, C, h, w, coherent)
+    f0, f1 = _feature_pair(g, C, h, w, coherent, noise=0.2 * math.sqrt(C))  # ~11 at C = 3072: recall@1cm ~ 80 %
     ys, xs = torch.meshgrid(torch.arange(H).float(), torch.arange(W).float(), indexing="ij")
 
     def grid(cx, cy):
+        # a smooth object surface seen through a pinhole of focal length 1.2 * W (in grid pixels): neighbouring
+        # pixels are ~5 mm apart, so the 1 / 2 / 5 cm thresholds separate exact, near and far matches
         inside = ((xs - cx) ** 2 + (ys - cy) ** 2) < radius * radius
-        xyz = 0.1 + torch.rand(3, H, W, generator=g)
+        z = 0.6 + 0.15 * torch.sin(xs / 9.0) * torch.cos(ys / 7.0) + 0.002 * torch.rand(H, W, generator=g)
+        f = 1.2 * W
+        xyz = torch.stack(((xs + 0.5 - W / 2) * z / f, (ys + 0.5 - H / 2) * z / f, z), dim=0)
         xyz[:, ~inside] = 0.0
         return xyz.contiguous()
 
@@ -79,15 +85,15 @@ def navi_pair(index, C=3072, h=28, w=28, H=112, W=112, radius=40.0, coherent=Tru
     else:
         x1 = grid(W / 2 + 3.5, H / 2 - 2.5)
         Rt = random_rt(g)
-    fx = 400.0 + 200.0 * torch.rand(1, generator=g).item()
-    intr = torch.tensor([[fx, 0.0, 0.0], [0.0, fx, 0.0], [0.0, 0.0, 1.0]])
+    fx = 4.0 * 1.2 * W * (0.9 + 0.2 * torch.rand(1, generator=g).item())  # full-resolution intrinsics (grid = 1/4 scale)
+    intr = torch.tensor([[fx, 0.0, 2.0 * W], [0.0, fx, 2.0 * H], [0.0, 0.0, 1.0]])
     return {"feat_0": f0, "feat_1": f1, "xyz_grid_0": x0, "xyz_grid_1": x1, "Rt": Rt.float(), "intrinsics": intr}
 
 
 def spair_pair(index, C=768, h=14, w=14, K=20, image_size=224, valid_p=0.8, coherent=True, config=1):
     """SPair-shaped pair (evaluate_spair_correspondence.py:45-79): features of both images + keypoints."""
     g = _gen(config, index)
-    f0, f1 = _feature_pair(g, C, h, w, coherent, noise=0.3)
+    f0, f1 = _feature_pair(g, C, h, w, coherent, noise=1.0)
     kps_i = torch.zeros(K, 3)
     kps_j = torch.zeros(K, 3)
     kps_i[:, :2] = torch.randint(0, image_size, (K, 2), generator=g).float()
