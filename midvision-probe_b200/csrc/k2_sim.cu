@@ -167,32 +167,34 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(TF32 ? 2 : 1, BM, BN);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (unsigned long long t = t_beg; t < t_end; ++t) {
-        mbar_wait(smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
+    // The whole warp walks the (warp-uniform) loop; one elected lane issues.  Everything the issuing thread
+    // executes per k-block is a barrier wait, two integer multiply-adds and ONE asm block.
+    constexpr uint32_t idesc = umma_idesc(TF32 ? 2 : 1, BM, BN);
+    const uint64_t desc0 = umma_desc_sw128(smem_base);  // stage 0, A tile; later tiles add (bytes >> 4) to the low word
+    const bool leader = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (unsigned long long t = t_beg; t < t_end; ++t) {
+      mbar_wait(smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
+      for (int kb = 0; kb < p.kblocks; ++kb) {
+        mbar_wait(smem_u32(&bars->full[stage]), phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
-        for (int kb = 0; kb < p.kblocks; ++kb) {
-          mbar_wait(smem_u32(&bars->full[stage]), phase);
-          tc_fence_after();
-          const uint32_t sa = smem_base + stage * STAGE_BYTES, sbm = sa + A_STAGE_BYTES;
-          const uint64_t da = umma_desc_sw128(sa), db = umma_desc_sw128(sbm);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)  // 4 x 32 bytes along K inside the 128-byte swizzle row
-            umma_ss<TF32>(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (uint32_t)((kb | k) != 0));
-          if (MC == 1) umma_commit(smem_u32(&bars->empty[stage]));
-          else umma_commit_mc(smem_u32(&bars->empty[stage]), (uint16_t)((1u << MC) - 1));
-          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        if (leader) {
+          const uint64_t da = desc0 + (uint64_t)((uint32_t)stage * (STAGE_BYTES >> 4));
+          const uint64_t db = da + (uint64_t)(A_STAGE_BYTES >> 4);
+          if (MC == 1) umma_kblock<TF32>(d_tmem, da, db, idesc, (uint32_t)(kb != 0), smem_u32(&bars->empty[stage]));
+          else umma_kblock_mc<TF32>(d_tmem, da, db, idesc, (uint32_t)(kb != 0), smem_u32(&bars->empty[stage]),
+                                    (uint16_t)((1u << MC) - 1));
         }
-        umma_commit(smem_u32(&bars->tmem_full[acc]));
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
+      if (leader) umma_commit(smem_u32(&bars->tmem_full[acc]));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
     }
   } else if (warp >= EPI_WARP0) {
     // ===================================== epilogue =========================================

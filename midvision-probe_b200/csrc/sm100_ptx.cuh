@@ -132,6 +132,84 @@ __device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64
   }
 }
 
+// One k-block in a single asm block: four MMAs that walk the 128-byte swizzle row in 32-byte steps (descriptor
+// start address + 2 per step), then the commit that releases the shared-memory slot.  Keeping this in one
+// block stops the compiler from re-deriving uniform registers (ELECT / R2UR / PLOP3 chains) around every
+// instruction -- the issuing thread's own instruction latency was the kernel's bound before (profiles/).
+template <bool TF32>
+__device__ __forceinline__ void umma_kblock(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                            uint32_t accumulate_first, uint32_t empty_bar) {
+  if (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p, pt;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "add.u64 da, %1, 2;\n\tadd.u64 db, %2, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, pt;\n\t"
+        "add.u64 da, %1, 4;\n\tadd.u64 db, %2, 4;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, pt;\n\t"
+        "add.u64 da, %1, 6;\n\tadd.u64 db, %2, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, pt;\n\t"
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first), "r"(empty_bar)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, pt;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "add.u64 da, %1, 2;\n\tadd.u64 db, %2, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+        "add.u64 da, %1, 4;\n\tadd.u64 db, %2, 4;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+        "add.u64 da, %1, 6;\n\tadd.u64 db, %2, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first), "r"(empty_bar)
+        : "memory");
+  }
+}
+// same with the commit multicast to every CTA of `mask`
+template <bool TF32>
+__device__ __forceinline__ void umma_kblock_mc(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate_first, uint32_t empty_bar, uint16_t mask) {
+  if (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p, pt;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "add.u64 da, %1, 2;\n\tadd.u64 db, %2, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, pt;\n\t"
+        "add.u64 da, %1, 4;\n\tadd.u64 db, %2, 4;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, pt;\n\t"
+        "add.u64 da, %1, 6;\n\tadd.u64 db, %2, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, pt;\n\t"
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%5], %6;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first), "r"(empty_bar), "h"(mask)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, pt;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "add.u64 da, %1, 2;\n\tadd.u64 db, %2, 2;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+        "add.u64 da, %1, 4;\n\tadd.u64 db, %2, 4;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+        "add.u64 da, %1, 6;\n\tadd.u64 db, %2, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, pt;\n\t"
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%5], %6;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first), "r"(empty_bar), "h"(mask)
+        : "memory");
+  }
+}
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // arrive on `bar` (this CTA) once every tcgen05 op issued so far by this thread has completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
