@@ -21,8 +21,8 @@
 
 namespace {
 
-constexpr int K1_THREADS_MAX = 768;  // 85 registers per thread: the tap window + a batch of accumulators fit
-constexpr int K1_BATCH = 4;     // points per block-level reduction
+constexpr int K1_THREADS_MAX = 512;  // 128 registers per thread: the tap window + a batch of accumulators fit
+constexpr int K1_BATCH_MAX = 4;  // points per block-level reduction (template parameter K1_BATCH <= this)
 constexpr int K1_MAX_RUN = 64;  // most points one CTA owns
 constexpr float K1_NORM_EPS = 1e-12f;  // F.normalize default eps
 
@@ -237,10 +237,10 @@ __device__ __forceinline__ void cubic_coeffs(float t, float c[4]) {
 //             step to the next source cell loads 2 new taps instead of 4 (same arithmetic as a cold point);
 //   bicubic : the 4 columns of the 4 x 4 window are pre-blended along y (consecutive points of an output row
 //             have the bit-identical y coordinate), so a step in x costs 4 tap loads instead of 16.
-template <int MODE, int NV>
-__global__ void __launch_bounds__(K1_THREADS_MAX) k1_sample_normalize_kernel(K1Params p) {
-  __shared__ float red[K1_BATCH][K1_THREADS_MAX / 32];
-  __shared__ float bcast[K1_BATCH];
+template <int MODE, int NV, int K1_BATCH, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k1_sample_normalize_kernel(K1Params p) {
+  __shared__ float red[K1_BATCH_MAX][K1_THREADS_MAX / 32];
+  __shared__ float bcast[K1_BATCH_MAX];
   __shared__ float2 s_coords[K1_MAX_RUN];
   const int n = p.n_dev ? min(*p.n_dev, p.n_max) : p.n_max;
   const int C4 = p.C >> 2;
@@ -433,16 +433,18 @@ __global__ void __launch_bounds__(K1_THREADS_MAX) k1_sample_normalize_kernel(K1P
 
 template <int MODE>
 int launch_k1(const K1Params& p, int threads, int nv, int grid, cudaStream_t st) {
+  // thread = 4 * NV channels.  NV = 4 amortises the per-point scalar work (coordinates, cubic weights, window
+  // bookkeeping, reduction) over 16 outputs; its batch is 2 points to stay inside 128 registers.
   switch (nv) {
-#define MV_K1_CASE(NV)                                                      \
-  case NV:                                                                  \
-    k1_sample_normalize_kernel<MODE, NV><<<grid, threads, 0, st>>>(p);      \
-    break;
-    MV_K1_CASE(1)
-    MV_K1_CASE(2)
-#undef MV_K1_CASE
+    case 1: k1_sample_normalize_kernel<MODE, 1, 4, 128, 1><<<grid, threads, 0, st>>>(p); break;
+    case 2: k1_sample_normalize_kernel<MODE, 2, 4, 128, 1><<<grid, threads, 0, st>>>(p); break;
+    case 4:
+      // C <= 4096: at most 256 threads, registers to spare for the loads in flight; wider rows still run (512 threads)
+      if (threads <= 256) k1_sample_normalize_kernel<MODE, 4, 2, 256, 2><<<grid, threads, 0, st>>>(p);
+      else k1_sample_normalize_kernel<MODE, 4, 2, 512, 1><<<grid, threads, 0, st>>>(p);
+      break;
     default:
-      mv_set_error("mv_k1_sample_normalize: C too large");
+      mv_set_error("mv_k1_sample_normalize: unsupported channel split");
       return MV_E_RANGE;
   }
   MV_LAUNCH_CHECK();
@@ -562,15 +564,19 @@ int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, cons
 
   // thread = 4 * nv channels; one CTA = all channels of a run of consecutive points
   const int C4 = C / 4;
-  const int nv = (C4 + K1_THREADS_MAX - 1) / K1_THREADS_MAX;
-  int threads = (((C4 + nv - 1) / nv + 31) / 32) * 32;
-  // long runs amortise the tap loads, ~one CTA per SM keeps the machine busy; the kernel re-derives the run
+  const int nv = C4 >= 256 ? 4 : (C4 >= 128 ? 2 : 1);
+  const int threads = (((C4 + nv - 1) / nv + 31) / 32) * 32;  // <= 512 for C <= 8192
+  // long runs amortise the tap loads, a few CTAs per SM overlap their barriers; the kernel re-derives the run
   // length from the live count, the grid only has to cover n_max at the longest run (K1_MAX_RUN)
-  int grid = mv_sm_count() * (threads <= 384 ? 2 : 1);
+  int per_sm = 512 / threads;
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  int grid = mv_sm_count() * per_sm;
   const int need = (n_max + K1_MAX_RUN - 1) / K1_MAX_RUN;
   if (grid < need) grid = need;
-  const int most = (n_max + K1_BATCH - 1) / K1_BATCH;
+  const int most = (n_max + 1) / 2;
   if (grid > most) grid = most;
+  if (grid < 1) grid = 1;
   cudaStream_t st = mv_cuda_stream(stream);
   if (mode == MV_SAMPLE_BILINEAR_ZEROS) return launch_k1<MV_SAMPLE_BILINEAR_ZEROS>(p, threads, nv, grid, st);
   if (mode == MV_SAMPLE_BICUBIC_CLAMP) return launch_k1<MV_SAMPLE_BICUBIC_CLAMP>(p, threads, nv, grid, st);

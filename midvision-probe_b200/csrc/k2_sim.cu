@@ -117,6 +117,15 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
   const bool has_work = cluster_id < sch.G && sch.T > 0;
   const unsigned long long t_beg = has_work ? sched_begin(sch, cluster_id) : 0ull;
   const unsigned long long t_end = has_work ? sched_begin(sch, cluster_id + 1) : 0ull;
+  // The range is walked starting at its first row-block boundary and wrapping around, so that every CTA sweeps
+  // the column tiles in phase (all at column ~s mod n_ct at step s): the B tiles in flight are then the same
+  // few for the whole chip and the L2 working set is the active A blocks + a narrow window of B, instead of
+  // all of B (which overflows the 126 MB L2 once (n + m) * C * 2 bytes does).
+  const unsigned long long t_len = t_end - t_beg;
+  unsigned long long t_rot = (t_beg + (unsigned)sch.n_ct - 1) / (unsigned)sch.n_ct * (unsigned)sch.n_ct;
+  if (t_rot >= t_end) t_rot = t_beg;
+  const unsigned long long t_head = t_end - t_rot;  // steps [0, t_head) map to [t_rot, t_end), the rest to [t_beg, t_rot)
+#define MV_K2_TILE_AT(step) ((step) < t_head ? t_rot + (step) : t_beg + ((step) - t_head))
   constexpr int KE = TF32 ? 32 : 64;  // K elements per 128-byte row
 
   if (threadIdx.x == 0) {
@@ -145,7 +154,8 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (unsigned long long t = t_beg; t < t_end; ++t) {
+      for (unsigned long long step = 0; step < t_len; ++step) {
+        const unsigned long long t = MV_K2_TILE_AT(step);
         const int sb = (int)(t / (unsigned)sch.n_ct), ct = (int)(t - (unsigned long long)sb * sch.n_ct);
         const int row0 = (sb * MC + rank) * BM, col0 = ct * BN;
         for (int kb = 0; kb < p.kblocks; ++kb) {
@@ -176,7 +186,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (unsigned long long t = t_beg; t < t_end; ++t) {
+    for (unsigned long long step = 0; step < t_len; ++step) {
       mbar_wait(smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
@@ -214,7 +224,8 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
           make_float4(m1, __int_as_float(i1), m2, __int_as_float(i2));
     };
 
-    for (unsigned long long t = t_beg; t < t_end; ++t) {
+    for (unsigned long long step = 0; step < t_len; ++step) {
+      const unsigned long long t = MV_K2_TILE_AT(step);
       const int sb = (int)(t / (unsigned)sch.n_ct), ct = (int)(t - (unsigned long long)sb * sch.n_ct);
       if (sb != cur_sb) {
         if (cur_sb >= 0) flush(cur_sb);
