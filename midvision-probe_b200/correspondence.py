@@ -485,6 +485,40 @@ def prepare_xyz_side(feat, xyz_grid, dev, sync=True, want_taps=False):
     return _finish_xyz(f, g, staged, n, sync, want_taps)
 
 
+_SIDE_STREAMS = {}
+
+
+def _on_side_stream(fn, dev):
+    """run fn() (uploads + launches for the second image) on a side stream forked from the current stream, so
+    its host -> device copies overlap the first image's kernels; the caller joins with _join_side()."""
+    cur = torch.cuda.current_stream(dev)
+    side = _SIDE_STREAMS.get(dev.index)
+    if side is None:
+        side = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    side.wait_stream(cur)
+    with torch.cuda.stream(side):
+        out = fn()
+    return out, side
+
+
+def _join_side(side, dev, *objs):
+    cur = torch.cuda.current_stream(dev)
+    cur.wait_stream(side)
+
+    def rec(o):
+        if torch.is_tensor(o):
+            o.record_stream(cur)
+        elif isinstance(o, (tuple, list)):
+            for x in o:
+                rec(x)
+        elif hasattr(o, "__slots__"):
+            for nme in o.__slots__:
+                rec(getattr(o, nme, None))
+
+    for o in objs:
+        rec(o)
+
+
 def _two_counts(a, b):
     """both live counts with a single device -> host read."""
     n0, n1 = torch.cat((a, b)).tolist()
@@ -515,15 +549,20 @@ def estimate_correspondence_depth(feat_0, feat_1, depth_0, depth_1, K, num_corr=
     in_dev = feat_0.device
     Kc = K.detach().float().cpu()
     Kh, Kinv = _host_mat(Kc), _host_mat(Kc.inverse())
-    # queue every host -> device copy first, then the geometry of both images, then read both counts at once
-    f0, f1, d0, d1 = _f32(feat_0, dev), _f32(feat_1, dev), _f32(depth_0, dev), _f32(depth_1, dev)
-    _check_C(f0.shape[0])
+    _check_C(feat_0.shape[0])
+    # the small depth maps go first (their compaction decides the point counts: one host read for both), then
+    # image 1's feature upload rides a side stream and overlaps image 0's kernels
+    d0, d1 = _f32(depth_0, dev), _f32(depth_1, dev)
     a0, a1 = _stage_depth(d0, Kinv), _stage_depth(d1, Kinv)
     n0, n1 = _two_counts(a0[2], a1[2])
     if n0 == 0 or n1 < 2:
         raise RuntimeError(f"too few valid points to match ({n0} vs {n1})")
+    f0 = _f32(feat_0, dev)
+    f1, side = _on_side_stream(lambda: _f32(feat_1, dev), dev)
     s0 = _finish_depth(f0, d0, Kh, a0, n0, True)
-    s1 = _finish_depth(f1, d1, Kh, a1, n1, True)
+    with torch.cuda.stream(side):
+        s1 = _finish_depth(f1, d1, Kh, a1, n1, True)
+    _join_side(side, dev, f1, s1)
     r = match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, n0, n1, num_corr)
     k = r.k
     return _return_packed([_gather(s0.xyz, r.sel_src, k), _gather(s1.xyz, r.sel_dst, k), r.sel_weight[:k]], in_dev)
@@ -533,14 +572,18 @@ def estimate_correspondence_xyz(feat_0, feat_1, xyz_grid_0, xyz_grid_1, num_corr
     """(c_xyz0, c_xyz1, c_dist, c_uv0, c_uv1).  correspondence.py:235-263."""
     dev = _device()
     in_dev = feat_0.device
-    f0, f1, g0, g1 = _f32(feat_0, dev), _f32(feat_1, dev), _f32(xyz_grid_0, dev), _f32(xyz_grid_1, dev)
-    _check_C(f0.shape[0])
+    _check_C(feat_0.shape[0])
+    g0, g1 = _f32(xyz_grid_0, dev), _f32(xyz_grid_1, dev)
     a0, a1 = _stage_xyz(g0), _stage_xyz(g1)
     n0, n1 = _two_counts(a0[1], a1[1])
     if n0 == 0 or n1 < 2:
         raise RuntimeError(f"too few valid points to match ({n0} vs {n1})")
+    f0 = _f32(feat_0, dev)
+    f1, side = _on_side_stream(lambda: _f32(feat_1, dev), dev)
     s0 = _finish_xyz(f0, g0, a0, n0, True)
-    s1 = _finish_xyz(f1, g1, a1, n1, True)
+    with torch.cuda.stream(side):
+        s1 = _finish_xyz(f1, g1, a1, n1, True)
+    _join_side(side, dev, f1, s1)
     r = match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, n0, n1, num_corr, ratio_test)
     k = r.k
     return _return_packed([_gather(s0.xyz, r.sel_src, k), _gather(s1.xyz, r.sel_dst, k), r.sel_weight[:k],

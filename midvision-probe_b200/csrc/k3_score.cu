@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(TOPK_THREADS) k3_topk_kernel(const float* __re
   extern __shared__ unsigned long long sortbuf[];  // kpad entries
   __shared__ int hist[256];
   __shared__ int warp_tot[32];
+  __shared__ int s_incl[256];
   __shared__ uint32_t s_prefix;
   __shared__ int s_remaining, s_gt;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -116,14 +117,27 @@ __global__ void __launch_bounds__(TOPK_THREADS) k3_topk_kernel(const float* __re
       if ((key & mask) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255], 1);
     }
     __syncthreads();
-    if (tid == 0) {
-      int acc = 0, b = 255;
-      for (; b > 0; --b) {
-        if (acc + hist[b] >= remaining) break;
-        acc += hist[b];
+    // suffix sums of the 256 bins by the first 8 warps: bin b is the pivot when above(b) < remaining <= above(b) + hist[b]
+    if (tid < 256) {
+      const int h = hist[tid];
+      int incl = h;  // inclusive suffix sum inside the warp (towards higher bins)
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t2 = __shfl_down_sync(0xffffffffu, incl, o);
+        if (lane + o < 32) incl += t2;
       }
-      s_prefix = prefix | ((uint32_t)b << (8 * pass));
-      s_remaining = remaining - acc;
+      if (lane == 0) warp_tot[wid] = incl;  // total of this warp's 32 bins
+      __syncwarp();
+      s_incl[tid] = incl;
+    }
+    __syncthreads();
+    if (tid < 256) {
+      int above = s_incl[tid] - hist[tid];
+      for (int w = wid + 1; w < 8; ++w) above += warp_tot[w];
+      if (above < remaining && remaining <= above + hist[tid]) {
+        s_prefix = prefix | ((uint32_t)tid << (8 * pass));
+        s_remaining = remaining - above;
+      }
     }
     __syncthreads();
     prefix = s_prefix;
@@ -166,6 +180,38 @@ __global__ void __launch_bounds__(TOPK_THREADS) k3_topk_kernel(const float* __re
     __syncthreads();
   }
 
+  if (kpad <= TOPK_THREADS) {
+    // ---- bitonic sort with one element per thread: compare-exchange distances below 32 are warp shuffles,
+    // the 15 longer ones go through (ping-pong) shared memory with one barrier each -- 15 barriers, not 55
+    unsigned long long v = (tid < kpad) ? sortbuf[tid] : 0ull;
+    __syncthreads();
+    unsigned long long* pp = sortbuf;  // 2 x 1024 entries (the launch sizes shared memory for that)
+    int flip = 0;
+    for (int size = 2; size <= TOPK_THREADS; size <<= 1) {
+      const bool desc = (tid & size) == 0;
+      for (int stride = size >> 1; stride > 0; stride >>= 1) {
+        unsigned long long o;
+        if (stride < 32) {
+          o = __shfl_xor_sync(0xffffffffu, v, stride);
+        } else {
+          unsigned long long* buf = pp + flip * TOPK_THREADS;
+          buf[tid] = v;
+          __syncthreads();
+          o = buf[tid ^ stride];
+          flip ^= 1;
+        }
+        const bool keep_max = (((tid & stride) == 0) == desc);
+        v = keep_max ? (v > o ? v : o) : (v < o ? v : o);
+      }
+    }
+    if (tid < k) {
+      const int i = (int)(0xffffffffu - (uint32_t)(v & 0xffffffffull));
+      sel_src[tid] = i;
+      sel_dst[tid] = row_idx[2 * (size_t)i];
+      sel_weight[tid] = weight[i];
+    }
+    return;
+  }
   // ---- bitonic sort, descending
   for (int size = 2; size <= kpad; size <<= 1) {
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -382,7 +428,7 @@ int mv_k3_topk_matches(const float* weight, const int32_t* row_idx, const int32_
   }
   int kpad = 2;
   while (kpad < kmax) kpad <<= 1;
-  const size_t smem = (size_t)kpad * sizeof(unsigned long long);
+  const size_t smem = (size_t)(kpad > 2 * TOPK_THREADS ? kpad : 2 * TOPK_THREADS) * sizeof(unsigned long long);
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     MV_CUDA(cudaFuncSetAttribute(k3_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -79,6 +79,29 @@ class RecallAccumulator:
         }
 
 
+_SIDE_STREAMS = {}
+
+
+def _both_sides(fn0, fn1, dev):
+    """Prepare the two images of a pair concurrently: image 1 runs on a side stream forked from, and joined
+    back into, the current stream (inside a CUDA-graph capture this becomes a fork / join in the graph), so
+    its single-CTA compaction and small geometry kernels overlap image 0's work."""
+    cur = torch.cuda.current_stream(dev)
+    side = _SIDE_STREAMS.get(dev.index)
+    if side is None:
+        side = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    side.wait_stream(cur)
+    s0 = fn0()
+    with torch.cuda.stream(side):
+        s1 = fn1()
+    cur.wait_stream(side)
+    for name in s1.__slots__:  # allocated on the side stream, consumed on the current one
+        t = getattr(s1, name, None)
+        if torch.is_tensor(t):
+            t.record_stream(cur)
+    return s0, s1
+
+
 def match_and_score_depth(feat_0, feat_1, depth_0, depth_1, K, Rt, num_corr, acc, sync=False):
     """ScanNet-shaped pair, end to end on the device: estimate_correspondence_depth
     (correspondence.py:218-232) + the caller's error / recall block
@@ -86,8 +109,8 @@ def match_and_score_depth(feat_0, feat_1, depth_0, depth_1, K, Rt, num_corr, acc
     dev = C_._device()
     Kc = K.detach().float().cpu()
     Kh, Kinv = C_._host_mat(Kc), C_._host_mat(Kc.inverse())
-    s0 = C_.prepare_depth_side(feat_0, depth_0, Kh, Kinv, dev, sync=sync)
-    s1 = C_.prepare_depth_side(feat_1, depth_1, Kh, Kinv, dev, sync=sync)
+    s0, s1 = _both_sides(lambda: C_.prepare_depth_side(feat_0, depth_0, Kh, Kinv, dev, sync=sync),
+                         lambda: C_.prepare_depth_side(feat_1, depth_1, Kh, Kinv, dev, sync=sync), dev)
     r = C_.match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, s0.n, s1.n, num_corr,
                       n_dev=None if sync else s0.n_dev, m_dev=None if sync else s1.n_dev)
     acc.score(r, s0.xyz, s1.xyz, Rt, Kc)
@@ -98,8 +121,8 @@ def match_and_score_xyz(feat_0, feat_1, xyz_grid_0, xyz_grid_1, intrinsics, Rt, 
     """NAVI-shaped pair: estimate_correspondence_xyz (correspondence.py:235-263) + the caller's error /
     recall block (evaluate_navi_correspondence.py:186-212)."""
     dev = C_._device()
-    s0 = C_.prepare_xyz_side(feat_0, xyz_grid_0, dev, sync=sync)
-    s1 = C_.prepare_xyz_side(feat_1, xyz_grid_1, dev, sync=sync)
+    s0, s1 = _both_sides(lambda: C_.prepare_xyz_side(feat_0, xyz_grid_0, dev, sync=sync),
+                         lambda: C_.prepare_xyz_side(feat_1, xyz_grid_1, dev, sync=sync), dev)
     r = C_.match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, s0.n, s1.n, num_corr,
                       n_dev=None if sync else s0.n_dev, m_dev=None if sync else s1.n_dev)
     acc.score(r, s0.xyz, s1.xyz, Rt, intrinsics)
@@ -136,11 +159,11 @@ class GraphedPairMatcher:
 
     def _body(self):
         if self.kind == "xyz":
-            s0 = C_.prepare_xyz_side(self.f0, self.g0, self.dev, sync=False)
-            s1 = C_.prepare_xyz_side(self.f1, self.g1, self.dev, sync=False)
+            s0, s1 = _both_sides(lambda: C_.prepare_xyz_side(self.f0, self.g0, self.dev, sync=False),
+                                 lambda: C_.prepare_xyz_side(self.f1, self.g1, self.dev, sync=False), self.dev)
         else:
-            s0 = C_.prepare_depth_side(self.f0, self.g0, self.Kh, self.Kinv, self.dev, sync=False)
-            s1 = C_.prepare_depth_side(self.f1, self.g1, self.Kh, self.Kinv, self.dev, sync=False)
+            s0, s1 = _both_sides(lambda: C_.prepare_depth_side(self.f0, self.g0, self.Kh, self.Kinv, self.dev, sync=False),
+                                 lambda: C_.prepare_depth_side(self.f1, self.g1, self.Kh, self.Kinv, self.dev, sync=False), self.dev)
         r = C_.match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, s0.n, s1.n, self.num_corr, n_dev=s0.n_dev, m_dev=s1.n_dev)
         return s0, s1, r
 
