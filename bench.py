@@ -197,6 +197,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stress", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
+    ap.add_argument("--lanes", type=int, default=3, help="pairs in flight on separate streams (CUDA-graph arm)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -222,7 +223,8 @@ def main():
 
     pool_host = make_pool(syn, args.workload, rank, world, POOL)
     keys = [k for k in pool_host[0] if torch.is_tensor(pool_host[0][k])]
-    pool_dev = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in p.items()} for p in pool_host]
+    big = ("feat_0", "feat_1", "xyz_grid_0", "xyz_grid_1", "depth_0", "depth_1")  # Rt / K are 3x4 host parameters, like in the callers
+    pool_dev = [{k: (v.to(dev) if k in big else v) for k, v in p.items()} for p in pool_host]
     pool_pin = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in p.items()} for p in pool_host]
     acc = ev.RecallAccumulator(THR3, THR2, device=dev)
 
@@ -235,14 +237,13 @@ def main():
     gm = None
     if not args.no_graph:
         p0 = pool_dev[0]
-        gm = ev.GraphedPairMatcher("xyz" if args.workload == "navi" else "depth", tuple(p0["feat_0"].shape), tuple(p0[gk[0]].shape),
-                                   NUM_CORR, K=p0.get("K"), device=dev).capture()
+        gm = ev.PairPipeline("xyz" if args.workload == "navi" else "depth", tuple(p0["feat_0"].shape), tuple(p0[gk[0]].shape),
+                             NUM_CORR, K=p0.get("K"), device=dev, lanes=args.lanes)
 
     def pair_device(p):
         if gm is None:
             return pair_eager(p)
-        gm.load(p["feat_0"], p["feat_1"], p[gk[0]], p[gk[1]])
-        return gm.run(acc, p["Rt"], p[gk[2]])
+        return gm.submit(p["feat_0"], p["feat_1"], p[gk[0]], p[gk[1]], acc, p["Rt"], p[gk[2]])
 
     def step_device(s):
         for j in range(PAIRS_PER_STEP):
@@ -256,6 +257,8 @@ def main():
     # ---------------- device-resident arm (value) ----------------
     for s in range(args.warmup):
         step_device(s)
+    if gm is not None:
+        gm.join()
     barrier()
     acc.hits.zero_()
     L.LAUNCHES["count"] = 0
@@ -266,6 +269,8 @@ def main():
     e0.record()
     for s in range(args.steps):
         step_device(s)
+    if gm is not None:
+        gm.join()
     acc.all_reduce()  # the path's only collective: int64 hit counts
     e1.record()
     barrier()
@@ -342,7 +347,7 @@ def main():
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload_name(args.workload), "pairs_per_step": PAIRS_PER_STEP, "pool_pairs": POOL,
                        "l2": "inputs larger than L2: 16 distinct pairs cycled, ~190 MB of features + rows touched per pair vs 126 MB L2",
-                       "k2_cluster": args.cluster, "cuda_graph": gm is not None, "features": "seeded N(0,1) maps of the backbone's output shape"},
+                       "k2_cluster": args.cluster, "cuda_graph": gm is not None, "pairs_in_flight": args.lanes if gm is not None else 1, "features": "seeded N(0,1) maps of the backbone's output shape"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "correspondence.estimate_correspondence_xyz(host tensors)" if args.workload == "navi"

@@ -13,7 +13,8 @@ import torch
 from . import _lib as L
 from . import correspondence as C_
 
-__all__ = ["RecallAccumulator", "shard_pairs", "match_and_score_depth", "match_and_score_xyz", "GraphedPairMatcher"]
+__all__ = ["RecallAccumulator", "shard_pairs", "match_and_score_depth", "match_and_score_xyz", "GraphedPairMatcher",
+           "PairPipeline"]
 
 
 def shard_pairs(num_pairs, rank, world):
@@ -204,3 +205,40 @@ class GraphedPairMatcher:
         # per image: (backproject) + compact + coords + chw_to_hwc + kernel 1; per pair: kernel 2 (2) + ratio + top-k
         per_side = 5 if self.kind == "depth" else 4
         return 2 * per_side + 4
+
+
+class PairPipeline:
+    """Several GraphedPairMatchers, each on its own stream, fed round-robin: while one pair sits in its
+    low-occupancy phases (single-CTA compaction and top-k, the small geometry / ratio / scoring kernels) the
+    next pair's kernel 1 / kernel 2 use the idle SMs.  All lanes accumulate into the same RecallAccumulator
+    (device atomics), so the result is independent of the interleaving.
+
+        pipe = PairPipeline("xyz", feat_shape, grid_shape, num_corr, lanes=2)
+        for p in pairs: pipe.submit(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], acc, p["Rt"], p["intrinsics"])
+        pipe.join()
+    """
+
+    def __init__(self, kind, feat_shape, grid_shape, num_corr, K=None, device=None, lanes=2):
+        self.dev = device or C_._device()
+        self.lanes = []
+        for _ in range(max(1, int(lanes))):
+            st = torch.cuda.Stream(device=self.dev)
+            with torch.cuda.stream(st):
+                gm = GraphedPairMatcher(kind, feat_shape, grid_shape, num_corr, K=K, device=self.dev).capture()
+            self.lanes.append((st, gm))
+        torch.cuda.synchronize(self.dev)
+        self.turn = 0
+
+    def submit(self, feat_0, feat_1, grid_0, grid_1, acc=None, Rt=None, K=None):
+        st, gm = self.lanes[self.turn % len(self.lanes)]
+        self.turn += 1
+        st.wait_stream(torch.cuda.current_stream(self.dev))  # inputs produced on the caller's stream
+        with torch.cuda.stream(st):
+            gm.load(feat_0, feat_1, grid_0, grid_1)
+            return gm.run(acc, Rt, K)
+
+    def join(self):
+        """make the caller's stream wait for every lane (call before reading the accumulator)."""
+        cur = torch.cuda.current_stream(self.dev)
+        for st, _ in self.lanes:
+            cur.wait_stream(st)

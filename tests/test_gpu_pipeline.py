@@ -212,3 +212,20 @@ def test_cuda_graph_replay_equals_eager(mv, syn, kind):
         k = re_.k
         assert int(rg.k_dev.item()) == k
         assert torch.equal(rg.sel_src[:k], re_.sel_src[:k]) and torch.equal(rg.sel_weight[:k], re_.sel_weight[:k])
+
+
+def test_pair_pipeline_counts_equal_sequential(mv, syn):
+    """Two pairs in flight on separate streams must accumulate exactly the counts of the sequential run."""
+    ev = mv.evaluation
+    pairs = [syn.navi_pair(i, C=256, h=14, w=14, H=56, W=56, radius=20.0) for i in range(5)]
+    shape_f, shape_g = tuple(pairs[0]["feat_0"].shape), tuple(pairs[0]["xyz_grid_0"].shape)
+    seq = ev.RecallAccumulator(THR3, THR2, device="cuda")
+    for p in pairs:
+        ev.match_and_score_xyz(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], p["intrinsics"], p["Rt"], 300, seq, sync=True)
+    for lanes in (1, 2, 3):
+        acc = ev.RecallAccumulator(THR3, THR2, device="cuda")
+        pipe = ev.PairPipeline("xyz", shape_f, shape_g, 300, lanes=lanes)
+        for p in pairs:
+            pipe.submit(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], acc, p["Rt"], p["intrinsics"])
+        pipe.join()
+        assert acc.hits.cpu().tolist() == seq.hits.cpu().tolist()
