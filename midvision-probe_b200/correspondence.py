@@ -32,15 +32,22 @@ __all__ = [
 _CFG = {
     "dtype": os.environ.get("MVMATCH_DTYPE", "bf16"),
     "cluster": int(os.environ.get("MVMATCH_CLUSTER", "1")),
+    # host-tensor calls of the two dense helpers replay a CUDA graph cached per input shape (0 = launch eagerly)
+    "helper_graphs": int(os.environ.get("MVMATCH_HELPER_GRAPHS", "1")),
 }
+_HELPER_GRAPHS = {}  # (kind, shapes, num_corr, ratio_test, dtype, cluster, K bytes) -> evaluation.GraphedPairMatcher
+_HELPER_GRAPHS_MAX = 8
 
 
 # bench.py sets _PROFILE["k2_events"] = [] to collect (start, end, flop) CUDA-event records of kernel 2
 _PROFILE = {}
 
 
-def set_match_precision(dtype=None, cluster=None):
-    """Choose kernel 2's operand type ("bf16" | "tf32") and its cluster width (1, 2 or 4)."""
+def set_match_precision(dtype=None, cluster=None, helper_graphs=None):
+    """Choose kernel 2's operand type ("bf16" | "tf32"), its cluster width (1, 2 or 4) and whether the dense
+    helpers replay cached CUDA graphs for host-tensor calls."""
+    if helper_graphs is not None:
+        _CFG["helper_graphs"] = int(bool(helper_graphs))
     if dtype is not None:
         if dtype not in ("bf16", "tf32"):
             raise ValueError("dtype must be 'bf16' or 'tf32'")
@@ -156,12 +163,13 @@ def match_rows(A16, A32, B16, B32, n, m, num_corr, ratio_test=True, n_dev=None, 
     return res
 
 
-def _gather(src, idx, k):
-    """rows src[idx[:k]] through the library (src (n, width) fp32, idx int32)."""
+def _gather(src, idx, k, k_dev=None):
+    """rows src[idx[:k]] through the library (src (n, width) fp32, idx int32); with k_dev only the first
+    *k_dev (<= k) rows are gathered, the rest of the output is left as allocated."""
     width = src.shape[1]
     out = _empty((k, width), torch.float32, src.device)
     if k > 0:
-        L.call("mv_gather_rows", L.ptr(src), width, L.ptr(idx), None, k, L.ptr(out), _stream())
+        L.call("mv_gather_rows", L.ptr(src), width, L.ptr(idx), L.ptr(k_dev), k, L.ptr(out), _stream())
     return out
 
 
@@ -543,10 +551,47 @@ def _host_mat(M):
     return L.host_floats(M.detach().float().cpu().reshape(-1).tolist())
 
 
+def _graphed_helper(kind, feat_0, feat_1, grid_0, grid_1, num_corr, ratio_test, K=None):
+    """Host-tensor fast path of the two dense helpers: the whole pair (kernels 1-3 + the gathers of the return
+    tuple) is one cached CUDA graph; a call is 4 uploads into static buffers, one replay and ONE packed
+    device -> host copy (results + the three live counts), i.e. a single host sync."""
+    import importlib
+
+    ev = importlib.import_module(__package__ + ".evaluation")
+    dev = _device()
+    key = (kind, tuple(feat_0.shape), tuple(grid_0.shape), int(num_corr), bool(ratio_test), _CFG["dtype"], _CFG["cluster"],
+           None if K is None else tuple(K.detach().float().cpu().reshape(-1).tolist()), dev.index)
+    gm = _HELPER_GRAPHS.get(key)
+    if gm is None:
+        if len(_HELPER_GRAPHS) >= _HELPER_GRAPHS_MAX:
+            _HELPER_GRAPHS.pop(next(iter(_HELPER_GRAPHS)))
+        gm = ev.GraphedPairMatcher(kind, tuple(feat_0.shape), tuple(grid_0.shape), num_corr, K=K, device=dev,
+                                   ratio_test=ratio_test, with_outputs=True).capture()
+        _HELPER_GRAPHS[key] = gm
+    gm.load(feat_0, feat_1, grid_0, grid_1)
+    gm.graph.replay()
+    L.LAUNCHES["count"] += gm.launches_per_replay
+    gm.host_packed.copy_(gm.packed, non_blocking=True)
+    gm.host_counts.copy_(gm.counts, non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    n0, n1, k = (int(v) for v in gm.host_counts.tolist())
+    if n0 == 0 or n1 < 2:
+        raise RuntimeError(f"too few valid points to match ({n0} vs {n1})")
+    res = gm.host_packed[:k].clone()
+    widths = (3, 3, 1, 2, 2) if kind == "xyz" else (3, 3, 1)
+    out, c = [], 0
+    for wd in widths:
+        out.append(res[:, c:c + wd].contiguous() if wd > 1 else res[:, c].contiguous())
+        c += wd
+    return tuple(out)
+
+
 def estimate_correspondence_depth(feat_0, feat_1, depth_0, depth_1, K, num_corr=500):
     """(corr_xyz0 (k, 3), corr_xyz1 (k, 3), corr_dist (k,)).  correspondence.py:218-232."""
     dev = _device()
     in_dev = feat_0.device
+    if _CFG["helper_graphs"] and in_dev.type == "cpu":
+        return _graphed_helper("depth", feat_0, feat_1, depth_0, depth_1, num_corr, True, K=K)
     Kc = K.detach().float().cpu()
     Kh, Kinv = _host_mat(Kc), _host_mat(Kc.inverse())
     _check_C(feat_0.shape[0])
@@ -572,6 +617,8 @@ def estimate_correspondence_xyz(feat_0, feat_1, xyz_grid_0, xyz_grid_1, num_corr
     """(c_xyz0, c_xyz1, c_dist, c_uv0, c_uv1).  correspondence.py:235-263."""
     dev = _device()
     in_dev = feat_0.device
+    if _CFG["helper_graphs"] and in_dev.type == "cpu":
+        return _graphed_helper("xyz", feat_0, feat_1, xyz_grid_0, xyz_grid_1, num_corr, ratio_test)
     _check_C(feat_0.shape[0])
     g0, g1 = _f32(xyz_grid_0, dev), _f32(xyz_grid_1, dev)
     a0, a1 = _stage_xyz(g0), _stage_xyz(g1)

@@ -143,10 +143,13 @@ class GraphedPairMatcher:
     kind = "depth" ScanNet-shaped: feats (C, h, w) x2 + depth (1, H, W) x2 + K (fixed for the matcher)
     """
 
-    def __init__(self, kind, feat_shape, grid_shape, num_corr, K=None, device=None):
+    def __init__(self, kind, feat_shape, grid_shape, num_corr, K=None, device=None, ratio_test=True, with_outputs=False):
         if kind not in ("xyz", "depth"):
             raise ValueError(kind)
+        C_._check_C(feat_shape[0])
         self.kind, self.num_corr = kind, int(num_corr)
+        self.ratio_test, self.with_outputs = bool(ratio_test), bool(with_outputs)
+        self.packed = self.counts = self.host_packed = self.host_counts = None
         self.dev = device or C_._device()
         self.f0 = torch.zeros(feat_shape, dtype=torch.float32, device=self.dev)
         self.f1 = torch.zeros(feat_shape, dtype=torch.float32, device=self.dev)
@@ -165,7 +168,17 @@ class GraphedPairMatcher:
         else:
             s0, s1 = _both_sides(lambda: C_.prepare_depth_side(self.f0, self.g0, self.Kh, self.Kinv, self.dev, sync=False),
                                  lambda: C_.prepare_depth_side(self.f1, self.g1, self.Kh, self.Kinv, self.dev, sync=False), self.dev)
-        r = C_.match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, s0.n, s1.n, self.num_corr, n_dev=s0.n_dev, m_dev=s1.n_dev)
+        r = C_.match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, s0.n, s1.n, self.num_corr, self.ratio_test,
+                          n_dev=s0.n_dev, m_dev=s1.n_dev)
+        if self.with_outputs:
+            # the helper's return tuple, packed row-wise for a single device -> host copy:
+            # [xyz0 (3) | xyz1 (3) | weight (1) | uv0 (2) | uv1 (2)]; rows beyond the live k are not written
+            k = r.k
+            parts = [C_._gather(s0.xyz, r.sel_src, k, r.k_dev), C_._gather(s1.xyz, r.sel_dst, k, r.k_dev), r.sel_weight[:k, None]]
+            if self.kind == "xyz":
+                parts += [C_._gather(s0.uv, r.sel_src, k, r.k_dev), C_._gather(s1.uv, r.sel_dst, k, r.k_dev)]
+            self.packed = torch.cat(parts, dim=1)
+            self.counts = torch.cat((s0.n_dev, s1.n_dev, r.k_dev))
         return s0, s1, r
 
     def capture(self):
@@ -180,6 +193,9 @@ class GraphedPairMatcher:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.out = self._body()
+        if self.with_outputs:
+            self.host_packed = torch.empty(self.packed.shape, dtype=torch.float32, pin_memory=True)
+            self.host_counts = torch.empty(3, dtype=torch.int32, pin_memory=True)
         return self
 
     def load(self, feat_0, feat_1, grid_0, grid_1):
@@ -204,7 +220,8 @@ class GraphedPairMatcher:
     def launches_per_replay(self):
         # per image: (backproject) + compact + coords + chw_to_hwc + kernel 1; per pair: kernel 2 (2) + ratio + top-k
         per_side = 5 if self.kind == "depth" else 4
-        return 2 * per_side + 4
+        gathers = (4 if self.kind == "xyz" else 2) if self.with_outputs else 0
+        return 2 * per_side + 4 + gathers
 
 
 class PairPipeline:
