@@ -334,8 +334,14 @@ def main():
         k2_avg_flop = sum(k2_flops) / max(len(k2_flops), 1)
         achieved = k2_avg_flop / (k2_avg_ms * 1e-3) / 1e12 if k2_ms else None
         # the kernel runs inside a long step: the sustained figure is the denominator
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "k2_traffic.json")
+        if os.path.exists(tpath) and args.dtype == "bf16":
+            traffic = json.load(open(tpath)).get(args.workload, {}).get("dram_bytes")
         roof = {"bound": "tensor", "achieved": achieved, "peak": tc_sustained, "unit": "TFLOP/s",
-                "frac": achieved / tc_sustained if achieved else None, "traffic": None, "peak_kind": f"{peak_kind} sustained bf16",
+                "frac": achieved / tc_sustained if achieved else None, "traffic": traffic,
+                "traffic_note": "dram read+write bytes per launch from the committed ncu --set full capture of this shape (profiles/k2_traffic.json)",
+                "peak_kind": f"{peak_kind} sustained bf16",
                 "kernel": "k2_sim_top2_kernel (event pair around mv_k2_sim_top2: memset + GEMM/top-2 kernel + row merge)",
                 "launches_timed": len(k2_ms), "avg_ms": k2_avg_ms, "flop_per_launch": k2_avg_flop,
                 "k2_share_of_step": sum(k2_ms) / ms_total if ms_total else None,
