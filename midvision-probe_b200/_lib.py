@@ -8,7 +8,8 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_size_t, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libmvmatch.so")
+# MVMATCH_LIB_PATH: load another build of the same ABI (same-box A/B of kernel variants)
+LIB_PATH = os.environ.get("MVMATCH_LIB_PATH") or os.path.join(HERE, "lib", "libmvmatch.so")
 
 P = c_void_p  # every device / host pointer
 
