@@ -168,11 +168,13 @@ int mv_argmax_rows(const float* x, int rows, int cols, int max_value, int32_t* o
  * heat map in the (h, w) feature map -> (col,row)/w; errors (K,K) = ||pred_k - kps_j[l,:2]/image_size||
  * / thresh_scale, 1e3 where kps_i[k,2]*kps_j[l,2] != 1.  Outputs error matrix (K,K, optional),
  * error_same (K; -1 where the keypoint is not in both), error_nn / index_nn (K; -1 likewise) and
- * ACCUMULATES hits[0] += #in_both, hits[1] += #(error_same < pck_thresh). K <= 64. */
+ * ACCUMULATES hits[0] += #in_both, hits[1] += #(error_same < pck_thresh) and, when `confusion` is given
+ * ((conf_dim, conf_dim) counters, conf_dim >= K), confusion[k][index_nn[k]] += 1 for every keypoint in both
+ * images (the matrix evaluate_dataset builds at evaluate_spair_correspondence.py:115-118). K <= 64. */
 int mv_k3_spair_errors(const int32_t* pred_flat, int K, int w, const float* kps_i, const float* kps_j,
                        int kp_stride, float image_size, float thresh_scale, float pck_thresh, float* errors,
                        float* error_same, float* error_nn, int32_t* index_nn, unsigned long long* hits,
-                       mv_stream_t stream);
+                       unsigned long long* confusion, int conf_dim, mv_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -5,7 +5,7 @@
 pairs over GPUs and reduces integer hit counts.  All arithmetic is in ``lib/libmvmatch.so``
 (sources in ``csrc/``, C ABI in ``include/mvmatch.h``).
 """
-from . import _lib, correspondence, evaluation, spair  # noqa: F401
+from . import _lib, correspondence, evaluation, spair, transformations  # noqa: F401
 from ._lib import MvMatchError, load  # noqa: F401
 from .build import build_lib  # noqa: F401
 

@@ -33,7 +33,7 @@ PROTOTYPES = {
     "mv_k3_score": (c_int, [P, P, P, c_int, P, P, P, P, P, P, c_int, P, c_int, P, P, P, P, P, P]),
     "mv_gather_rows": (c_int, [P, c_int, P, P, c_int, P, P]),
     "mv_argmax_rows": (c_int, [P, c_int, c_int, c_int, P, P]),
-    "mv_k3_spair_errors": (c_int, [P, c_int, c_int, P, P, c_int, c_float, c_float, c_float, P, P, P, P, P, P]),
+    "mv_k3_spair_errors": (c_int, [P, c_int, c_int, P, P, c_int, c_float, c_float, c_float, P, P, P, P, P, P, c_int, P]),
 }
 
 # enums of include/mvmatch.h

@@ -158,7 +158,7 @@ def match_rows(A16, A32, B16, B32, n, m, num_corr, ratio_test=True, n_dev=None, 
         res.sel_dst = _empty((max(k, 1),), torch.int32, dev)
         res.sel_weight = _empty((max(k, 1),), torch.float32, dev)
         res.k_dev = _empty((1,), torch.int32, dev)
-        L.call("mv_k3_topk_matches", L.ptr(weight), L.ptr(row_idx), L.ptr(n_dev), n, int(num_corr), L.ptr(res.sel_src),
+        L.call("mv_k3_topk_matches", L.ptr(weight), L.ptr(row_idx), L.ptr(n_dev), n, k, L.ptr(res.sel_src),
                L.ptr(res.sel_dst), L.ptr(res.sel_weight), L.ptr(res.k_dev), st)
     return res
 

@@ -356,7 +356,8 @@ __global__ void __launch_bounds__(256) k3_spair_kernel(const int32_t* __restrict
                                                        int stride, float image_size, float thresh_scale, float pck,
                                                        float* __restrict__ errors, float* __restrict__ error_same,
                                                        float* __restrict__ error_nn, int32_t* __restrict__ index_nn,
-                                                       unsigned long long* __restrict__ hits) {
+                                                       unsigned long long* __restrict__ hits,
+                                                       unsigned long long* __restrict__ confusion, int conf_dim) {
   __shared__ float err[64][65];
   __shared__ unsigned int cnt[2];
   if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
@@ -386,6 +387,7 @@ __global__ void __launch_bounds__(256) k3_spair_kernel(const int32_t* __restrict
         if (err[k][l] < en) { en = err[k][l]; in = l; }
       atomicAdd(&cnt[0], 1u);
       if (es < pck) atomicAdd(&cnt[1], 1u);
+      if (confusion) atomicAdd(&confusion[(size_t)k * conf_dim + in], 1ull);
     }
     if (error_same) error_same[k] = es;
     if (error_nn) error_nn[k] = en;
@@ -487,14 +489,16 @@ int mv_argmax_rows(const float* x, int rows, int cols, int max_value, int32_t* o
 
 int mv_k3_spair_errors(const int32_t* pred_flat, int K, int w, const float* kps_i, const float* kps_j, int kp_stride,
                        float image_size, float thresh_scale, float pck_thresh, float* errors, float* error_same,
-                       float* error_nn, int32_t* index_nn, unsigned long long* hits, mv_stream_t stream) {
+                       float* error_nn, int32_t* index_nn, unsigned long long* hits, unsigned long long* confusion,
+                       int conf_dim, mv_stream_t stream) {
   MV_REQUIRE(pred_flat && kps_i && kps_j, MV_E_ARG, "mv_k3_spair_errors: null pointer");
   MV_REQUIRE(K >= 0 && K <= 64, MV_E_RANGE, "mv_k3_spair_errors: K=%d must be in [0, 64]", K);
   MV_REQUIRE(w > 0 && kp_stride >= 3 && image_size > 0.f, MV_E_ARG, "mv_k3_spair_errors: bad sizes");
+  MV_REQUIRE(!confusion || conf_dim >= K, MV_E_ARG, "mv_k3_spair_errors: conf_dim=%d must be >= K=%d", conf_dim, K);
   if (K == 0) return MV_OK;
   k3_spair_kernel<<<1, 256, 0, mv_cuda_stream(stream)>>>(pred_flat, K, w, kps_i, kps_j, kp_stride, image_size,
                                                          thresh_scale, pck_thresh, errors, error_same, error_nn,
-                                                         index_nn, hits);
+                                                         index_nn, hits, confusion, conf_dim);
   MV_LAUNCH_CHECK();
   return MV_OK;
 }

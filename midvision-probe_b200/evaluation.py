@@ -31,7 +31,12 @@ class RecallAccumulator:
     render_scannet_correspondence.py:253-264) without floating-point accumulation.
     """
 
-    def __init__(self, thr3d, thr2d, device=None):
+    def __init__(self, thr3d, thr2d, device=None, angle_bins=None, bin_threshold=0.02):
+        """angle_bins: optional edges in degrees (e.g. [0, 30, 60, 90, 120]); every scored pair then also adds its
+        (#err3d < bin_threshold, #matches) to the bin of its relative rotation angle -- the integer form of
+        compute_binned_performance(rec_2cm, rel_ang, bins) (evaluate_navi_correspondence.py:214-223; identical to
+        the reference's mean of per-pair recalls whenever every pair yields the same number of matches, which
+        the reference's torch.stack requires)."""
         if len(thr3d) > L.MV_MAX_THRESHOLDS or len(thr2d) > L.MV_MAX_THRESHOLDS:
             raise ValueError(f"at most {L.MV_MAX_THRESHOLDS} thresholds per list")
         self.thr3d = [float(t) for t in thr3d]
@@ -41,6 +46,12 @@ class RecallAccumulator:
         self.hits = torch.zeros(2 + 2 * (self.n3 + self.n2), dtype=torch.int64, device=device)
         self._t3 = L.host_floats(self.thr3d) if self.n3 else None
         self._t2 = L.host_floats(self.thr2d) if self.n2 else None
+        self.angle_bins = [float(a) for a in angle_bins] if angle_bins is not None else None
+        self.bin_threshold = float(bin_threshold)
+        self._tb = L.host_floats([self.bin_threshold])
+        nb = len(self.angle_bins) - 1 if self.angle_bins else 0
+        # per bin the 4 counters mv_k3_score writes for one 3-D threshold: [scored, mutual, hits, mutual&hits]
+        self.bin_hits = torch.zeros((max(nb, 1), 4), dtype=torch.int64, device=device)
 
     def score(self, match, xyz0, xyz1, Rt, K, want_errors=False):
         """Accumulate the counts of one pair. Rt: (3|4, 4), K: (3, 3) host or device tensors."""
@@ -53,13 +64,31 @@ class RecallAccumulator:
         L.call("mv_k3_score", L.ptr(match.sel_src), L.ptr(match.sel_dst), L.ptr(match.k_dev), k, L.ptr(xyz0),
                L.ptr(xyz1), L.ptr(match.mutual), Rt_h, K_h, self._t3, self.n3, self._t2, self.n2, None, None,
                L.ptr(e3), L.ptr(e2), L.ptr(self.hits), C_._stream())
+        if self.angle_bins:
+            from .transformations import so3_rotation_angle
+
+            ang = float(so3_rotation_angle(Rt.detach().float().cpu()[None, :3, :3])[0]) * 180.0 / 3.141592653589793
+            for b in range(len(self.angle_bins) - 1):
+                if self.angle_bins[b] <= ang < self.angle_bins[b + 1]:
+                    L.call("mv_k3_score", L.ptr(match.sel_src), L.ptr(match.sel_dst), L.ptr(match.k_dev), k, L.ptr(xyz0),
+                           L.ptr(xyz1), L.ptr(match.mutual), Rt_h, K_h, self._tb, 1, None, 0, None, None, None, None,
+                           c_void_p(self.bin_hits.data_ptr() + 32 * b), C_._stream())
+                    break
         return (e3, e2) if want_errors else None
 
     def all_reduce(self):
         """Sum the counters over all ranks (the path's only collective)."""
         if torch.distributed.is_available() and torch.distributed.is_initialized():
             torch.distributed.all_reduce(self.hits, op=torch.distributed.ReduceOp.SUM)
+            if self.angle_bins:
+                torch.distributed.all_reduce(self.bin_hits, op=torch.distributed.ReduceOp.SUM)
         return self
+
+    def binned_recall(self):
+        """[100 * hits / scored per angle bin] (nan for an empty bin, like the reference's mean of nothing)."""
+        if not self.angle_bins:
+            return []
+        return [100.0 * h[2] / h[0] if h[0] else float("nan") for h in self.bin_hits.tolist()]
 
     def merge_(self, other_hits):
         self.hits += other_hits.to(self.hits.device)

@@ -13,16 +13,18 @@ import torch
 from . import _lib as L
 from . import correspondence as C_
 
-__all__ = ["compute_errors_from_features", "pck_recall"]
+__all__ = ["compute_errors_from_features", "evaluate_pairs", "pck_recall"]
 
 
 def compute_errors_from_features(feats, kps_i, kps_j, thresh_scale, image_size, pck_thresh=0.10, hits=None,
-                                 return_heatmap_argmax=False):
+                                 return_heatmap_argmax=False, confusion=None):
     """(error_same, error_nn, index_same, index_nn), as compute_errors (evaluate_spair_correspondence.py:45-103).
 
     feats: (2, C, h, w) backbone output for (image_i, image_j); kps_*: (K, 3) = (x, y, valid) in image
     pixels; image_size: side of the (square) input image.  hits: optional int64[2] device tensor that
-    accumulates (#keypoints in both images, #of those with error_same < pck_thresh).
+    accumulates (#keypoints in both images, #of those with error_same < pck_thresh).  confusion: optional
+    (D, D) int64 device tensor, D >= K, accumulating confusion[src, tgt] += 1 over (index_same, index_nn)
+    (evaluate_dataset, evaluate_spair_correspondence.py:115-118).
     """
     dev = C_._device()
     in_dev = kps_i.device
@@ -51,13 +53,28 @@ def compute_errors_from_features(feats, kps_i, kps_j, thresh_scale, image_size, 
     idx_nn = torch.empty((K,), dtype=torch.int32, device=dev)
     L.call("mv_k3_spair_errors", L.ptr(pred), K, w, L.ptr(ki), L.ptr(kj), ki.shape[1], c_float(float(image_size)),
            c_float(float(thresh_scale)), c_float(float(pck_thresh)), None, L.ptr(err_same), L.ptr(err_nn),
-           L.ptr(idx_nn), L.ptr(hits), st)
+           L.ptr(idx_nn), L.ptr(hits), L.ptr(confusion), 0 if confusion is None else confusion.shape[1], st)
     in_both = err_same >= 0
     out = (err_same[in_both].to(in_dev), err_nn[in_both].to(in_dev), in_both.nonzero().squeeze(1).to(in_dev),
            idx_nn[in_both].long().to(in_dev))
     if return_heatmap_argmax:
         return out + (pred.long().to(in_dev),)
     return out
+
+
+def evaluate_pairs(pairs, pck_thresh=0.10, kp_max=None):
+    """(recall, confusion) over an iterable of dicts with keys feats, kps_i, kps_j, thresh_scale, image_size:
+    evaluate_dataset (evaluate_spair_correspondence.py:106-123) on integer counts, nothing leaves the device
+    until the end."""
+    dev = C_._device()
+    pairs = list(pairs)
+    D = kp_max or max(int(p["kps_i"].shape[0]) for p in pairs)
+    hits = torch.zeros(2, dtype=torch.int64, device=dev)
+    conf = torch.zeros((D, D), dtype=torch.int64, device=dev)
+    for p in pairs:
+        compute_errors_from_features(p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"], p["image_size"],
+                                     pck_thresh=pck_thresh, hits=hits, confusion=conf)
+    return pck_recall(hits), conf.cpu()
 
 
 def pck_recall(hits):

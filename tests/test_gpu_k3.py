@@ -164,3 +164,51 @@ def test_spair_errors(mv, syn, idx, shape):
     assert torch.equal(inn[ok], oinn[ok])
     h = hits.cpu().tolist()
     assert h[0] == oisame.numel() and h[1] == int((es < 0.10).sum())
+
+
+def test_spair_confusion_and_dataset_recall(mv, syn):
+    """spair.evaluate_pairs == evaluate_dataset (evaluate_spair_correspondence.py:106-123) on the oracle's outputs."""
+    pairs = [syn.spair_pair(i) for i in range(6)]
+    mv.correspondence.set_match_precision(dtype="tf32")
+    try:
+        recall, conf = mv.spair.evaluate_pairs(pairs, pck_thresh=0.10)
+    finally:
+        mv.correspondence.set_match_precision(dtype="bf16")
+    errs, src, tgt = [], [], []
+    for p in pairs:
+        es, en, isame, inn = restated.spair_compute_errors(p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"], p["image_size"])
+        errs.append(es); src.append(isame); tgt.append(inn)
+    errs, src, tgt = torch.cat(errs), torch.cat(src), torch.cat(tgt)
+    want = torch.zeros_like(conf)
+    for a, b in zip(src.tolist(), tgt.tolist()):
+        want[a, b] += 1
+    assert int(conf.sum()) == src.numel()
+    assert (conf - want).abs().sum() <= 2          # a near-tie in one heat map may move one entry
+    assert abs(recall - 100.0 * (errs < 0.10).float().mean().item()) <= 100.0 / errs.numel() + 1e-6
+
+
+def test_angle_binned_recall(mv, syn):
+    """integer per-bin counts == compute_binned_performance on per-pair recall@2cm (equal k per pair)."""
+    ev = mv.evaluation
+    tr = mv.transformations
+    g = torch.Generator().manual_seed(3)
+    acc = ev.RecallAccumulator([0.01, 0.02, 0.05], [5, 25, 50], device="cuda", angle_bins=[0, 30, 60, 90, 120])
+    k, n = 200, 1000
+    rec, ang = [], []
+    for i in range(12):
+        Rt = syn.random_rt(g, max_deg=119.0, t_sigma=0.05)
+        xyz0 = torch.randn(n, 3, generator=g) + torch.tensor([0.0, 0.0, 4.0])
+        src = torch.randperm(n, generator=g)[:k].to(torch.int32)
+        dst = torch.randperm(n, generator=g)[:k].to(torch.int32)
+        xyz1 = torch.randn(n, 3, generator=g)
+        xyz1[dst.long()] = restated.transform_points_Rt(xyz0[src.long()], Rt) + 0.02 * torch.randn(k, 3, generator=g)
+        m = mv.correspondence.MatchResult()
+        m.k, m.k_dev, m.sel_src, m.sel_dst, m.mutual = k, None, src.cuda(), dst.cuda(), None
+        e3, _ = acc.score(m, xyz0.cuda(), xyz1.cuda(), Rt, torch.eye(3), want_errors=True)
+        rec.append((e3.cpu()[:k] < 0.02).float().mean())
+        ang.append(tr.so3_rotation_angle(Rt[None, :3, :3])[0] * 180.0 / 3.141592653589793)
+    want = mv.correspondence.compute_binned_performance(torch.stack(rec), torch.stack(ang), [0, 30, 60, 90, 120])
+    got = acc.binned_recall()
+    for a, b in zip(got, want):
+        assert (a != a and b != b) or abs(a - 100.0 * float(b)) < 1e-3
+    torch.testing.assert_close(tr.so3_rotation_angle(Rt[None, :3, :3]), tr.so3_relative_angle(Rt[None, :3, :3], torch.eye(3)[None]))

@@ -229,3 +229,33 @@ def test_pair_pipeline_counts_equal_sequential(mv, syn):
             pipe.submit(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], acc, p["Rt"], p["intrinsics"])
         pipe.join()
         assert acc.hits.cpu().tolist() == seq.hits.cpu().tolist()
+
+
+def test_edge_cases_of_the_helpers(mv, syn):
+    C_ = mv.correspondence
+    g = torch.Generator().manual_seed(0)
+    # fewer points than requested correspondences: k = N (correspondence.py:126)
+    X, Y = torch.randn(7, 16, generator=g), torch.randn(40, 16, generator=g)
+    i1, i2, w = C_.get_correspondences_ratio_test(X, Y, 50)
+    assert i1.shape == (7,) and sorted(i1.tolist()) == list(range(7)) and (w[1:] <= w[:-1]).all()
+    o1, o2, ow = restated.correspondences_ratio_test(X, Y, 50)
+    assert torch.equal(i1, o1) and torch.equal(i2, o2)
+    torch.testing.assert_close(w, ow, rtol=0, atol=1e-5)
+    # CUDA tensors in -> CUDA tensors out (the SPair caller keeps everything on the device)
+    d, i = C_.knn_points(X.cuda(), Y.cuda(), 2, "cosine")
+    assert d.is_cuda and i.is_cuda and i.dtype == torch.int64
+    # a pair without valid geometry raises instead of returning garbage
+    p = syn.navi_pair(0, C=64, h=8, w=8, H=32, W=32, radius=12.0)
+    with pytest.raises(RuntimeError, match="too few valid points"):
+        C_.estimate_correspondence_xyz(p["feat_0"], p["feat_1"], torch.zeros_like(p["xyz_grid_0"]), p["xyz_grid_1"], 10)
+    with pytest.raises(RuntimeError, match="too few valid points"):
+        C_.estimate_correspondence_xyz(p["feat_0"].cuda(), p["feat_1"].cuda(), torch.zeros_like(p["xyz_grid_0"]).cuda(), p["xyz_grid_1"].cuda(), 10)
+    # ragged: every other pixel valid, odd sizes, k larger than the live count
+    grid = p["xyz_grid_0"].clone()
+    grid[2, ::2, :] = 0
+    out = C_.estimate_correspondence_xyz(p["feat_0"], p["feat_1"], grid, p["xyz_grid_1"], 100000)
+    ref = restated.estimate_correspondence_xyz(p["feat_0"], p["feat_1"], grid, p["xyz_grid_1"], 100000)
+    assert out[0].shape == ref[0].shape
+    assert (out[2] - ref[2]).abs().max() < 2e-2
+    with pytest.raises(ValueError):
+        C_.estimate_correspondence_xyz(torch.zeros(7, 4, 4), torch.zeros(7, 4, 4), p["xyz_grid_0"], p["xyz_grid_1"], 10)

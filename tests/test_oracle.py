@@ -94,3 +94,18 @@ def test_mutual_oracle_is_self_consistent():
     X = torch.randn(50, 16, generator=gen)
     r = restated.similarity_top2_and_mutual(X, X.clone())
     assert r["mutual"].all() and torch.equal(r["row_idx"][:, 0], torch.arange(50))
+
+
+@pytest.mark.skipif(not reference_loader.available(), reason="reference tree not on this machine")
+def test_transformations_mirror_equals_reference(mv, syn):
+    _, ref_tr = reference_loader.load()
+    tr = mv.transformations
+    g = torch.Generator().manual_seed(5)
+    Rt = torch.stack([syn.random_rt(g) for _ in range(6)])
+    pts = torch.randn(6, 17, 3, generator=g)
+    assert torch.equal(tr.transform_points_Rt(pts, Rt), ref_tr.transform_points_Rt(pts, Rt))
+    assert torch.equal(tr.transform_points_Rt(pts, Rt, inverse=True), ref_tr.transform_points_Rt(pts, Rt, inverse=True))
+    assert torch.equal(tr.so3_rotation_angle(Rt[:, :3, :3]), ref_tr.so3_rotation_angle(Rt[:, :3, :3]))
+    assert torch.equal(tr.so3_relative_angle(Rt[:3, :3, :3], Rt[3:, :3, :3]), ref_tr.so3_relative_angle(Rt[:3, :3, :3], Rt[3:, :3, :3]))
+    with pytest.raises(ValueError):
+        tr.so3_rotation_angle(torch.eye(3)[None] * 5)
