@@ -193,7 +193,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="navi", choices=["navi", "scannet"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "tf32"])
-    ap.add_argument("--cluster", type=int, default=int(os.environ.get("MVMATCH_CLUSTER", "1")))
+    ap.add_argument("--cluster", type=int, default=int(os.environ.get("MVMATCH_CLUSTER", "-1")),
+                    help="kernel 2 cluster mode: -1 auto, 1 single CTA, 2 / 4 B-tile multicast, 20 CTA pair (cta_group::2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stress", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")

@@ -49,6 +49,11 @@ typedef void* mv_stream_t; /* cudaStream_t */
 #define MV_DTYPE_BF16 0 /* tcgen05.mma kind::f16, bf16 inputs, fp32 accumulate  */
 #define MV_DTYPE_TF32 1 /* tcgen05.mma kind::tf32, fp32 inputs, fp32 accumulate */
 
+/* `cluster` argument of kernel 2: 0 / 1 = every SM on its own; 2 / 4 = clusters of that many CTAs with the B tile
+ * TMA-multicast; MV_CLUSTER_PAIR = CTA pairs (tcgen05 cta_group::2): one 256 x 256 MMA tile per two SMs */
+#define MV_CLUSTER_PAIR 20
+#define MV_CLUSTER_AUTO (-1) /* pick between 2-CTA multicast and the CTA pair from the operand type and C */
+
 /* value written in masked / empty slots of similarity outputs */
 #define MV_SIM_MASKED (-3.0e38f)
 
@@ -114,7 +119,8 @@ int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, cons
  *   col_best (m_max) optional : packed arg-max over rows of S[:, j]; decode with mv_k2_unpack_col.
  * A, B: bf16 (MV_DTYPE_BF16) or fp32 (MV_DTYPE_TF32), 16-byte aligned, C % 8 == 0 (bf16) / C % 4 == 0.
  * cluster: 0 or 1 = one CTA per SM on its own; 2 or 4 = thread-block clusters of that many CTAs working on
- * consecutive row blocks with the B tile loaded once and TMA-multicast to all of them.
+ * consecutive row blocks with the B tile loaded once and TMA-multicast to all of them; MV_CLUSTER_PAIR = the two
+ * CTAs of a cluster issue ONE 256-row MMA (cta_group::2), each holding half of the B tile.
  * workspace from mv_k2_workspace_bytes. */
 size_t mv_k2_workspace_bytes(int n_max, int m_max);
 int mv_k2_sim_top2(const void* A, const void* B, int n_max, int m_max, int C, const int32_t* n_dev,

@@ -31,7 +31,7 @@ __all__ = [
 # operand type of kernel 2: "bf16" (tcgen05 kind::f16) or "tf32" (kind::tf32); cluster = B-tile multicast width
 _CFG = {
     "dtype": os.environ.get("MVMATCH_DTYPE", "bf16"),
-    "cluster": int(os.environ.get("MVMATCH_CLUSTER", "1")),
+    "cluster": int(os.environ.get("MVMATCH_CLUSTER", "-1")),  # -1 = let the library choose (MV_CLUSTER_AUTO)
     # host-tensor calls of the two dense helpers replay a CUDA graph cached per input shape (0 = launch eagerly)
     "helper_graphs": int(os.environ.get("MVMATCH_HELPER_GRAPHS", "1")),
 }
@@ -53,8 +53,8 @@ def set_match_precision(dtype=None, cluster=None, helper_graphs=None):
             raise ValueError("dtype must be 'bf16' or 'tf32'")
         _CFG["dtype"] = dtype
     if cluster is not None:
-        if cluster not in (1, 2, 4):
-            raise ValueError("cluster must be 1, 2 or 4")
+        if cluster not in (-1, 1, 2, 4, 20):
+            raise ValueError("cluster must be -1 (auto), 1, 2, 4 (B-tile multicast width) or 20 (CTA pairs, cta_group::2)")
         _CFG["cluster"] = cluster
     return dict(_CFG)
 

@@ -38,14 +38,20 @@ using namespace sm100;
 constexpr int BM = 128;           // rows of S per tile (UMMA M)
 constexpr int BN = 256;           // columns of S per tile (UMMA N)
 constexpr int ROW_BYTES = 128;    // one swizzle-128B row: 64 bf16 or 32 fp32 along K
-constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * ROW_BYTES;  // 16 KB
-constexpr int B_STAGE_BYTES = BN * ROW_BYTES;  // 32 KB
-constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+// single-CTA tiles keep the whole 256-row B tile per stage (48 KB, 4 stages); a CTA pair (cta_group::2) keeps
+// only its half of B (32 KB, 6 stages): the tensor cores of both SMs read both halves
+constexpr int MAX_STAGES = 6;
+constexpr int RING_BYTES = 192 * 1024;
+template <bool PAIR> struct Ring {
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_ROWS * ROW_BYTES;
+  static constexpr int STAGES = RING_BYTES / STAGE_BYTES;
+};
 constexpr int K2_THREADS = 384;   // 4 control warps + 8 epilogue warps
 constexpr int EPI_WARP0 = 4;
 constexpr int COL_SMEM_BYTES = 2 * 4 * BN * 8;  // [2 buffers][4 warps][256 columns] (max bits, ballot)
-constexpr int K2_SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + COL_SMEM_BYTES + 256 /*barriers*/;
+constexpr int K2_SMEM_BYTES = 1024 /*align slack*/ + RING_BYTES + COL_SMEM_BYTES + 256 /*barriers*/;
 
 struct K2Sched {
   // tiles are numbered t = sb * n_ct + ct; cluster c owns [c*T/G, (c+1)*T/G).  Built on the device from the
@@ -90,21 +96,27 @@ __device__ __forceinline__ bool better(float x, int j, float y, int k) {
 }
 
 struct __align__(8) Barriers {
-  unsigned long long full[STAGES];
-  unsigned long long empty[STAGES];
+  unsigned long long full[MAX_STAGES];
+  unsigned long long empty[MAX_STAGES];
   unsigned long long tmem_full[2];
   unsigned long long tmem_empty[2];
   uint32_t tmem_base;
 };
 
-template <bool TF32, int MC>
+// MC: CTAs per cluster (consecutive row blocks of one super row block).  PAIR (MC == 2): the two CTAs form a
+// cta_group::2 pair -- ONE 256 x 256 MMA per k-step issued by the rank-0 CTA, each CTA supplying its 128 rows of
+// A and its 128 of the 256 columns of B and receiving its 128 rows of the accumulator in its own TMEM.
+template <bool TF32, int MC, bool PAIR>
 __global__ void __launch_bounds__(K2_THREADS, 1)
     k2_sim_top2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, K2Params p) {
+  static_assert(!PAIR || MC == 2, "a CTA pair is a cluster of two");
+  constexpr int STAGES = Ring<PAIR>::STAGES;
+  constexpr int STAGE_BYTES = Ring<PAIR>::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
-  uint2* col_smem = reinterpret_cast<uint2*>(smem_al + STAGES * STAGE_BYTES);
-  Barriers* bars = reinterpret_cast<Barriers*>(smem_al + STAGES * STAGE_BYTES + COL_SMEM_BYTES);
+  uint2* col_smem = reinterpret_cast<uint2*>(smem_al + RING_BYTES);
+  Barriers* bars = reinterpret_cast<Barriers*>(smem_al + RING_BYTES + COL_SMEM_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (MC > 1) ? (int)cluster_ctarank() : 0;
@@ -131,11 +143,11 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_u32(&bars->full[s]), 1);
-      mbar_init(smem_u32(&bars->empty[s]), MC);
+      mbar_init(smem_u32(&bars->empty[s]), PAIR ? 1 : MC);  // PAIR: one multicast commit of the pair's MMA
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&bars->tmem_full[a]), 1);
-      mbar_init(smem_u32(&bars->tmem_empty[a]), 8);
+      mbar_init(smem_u32(&bars->tmem_empty[a]), PAIR ? 16 : 8);  // PAIR: the epilogue warps of BOTH CTAs (rank 0's barrier)
     }
     mbar_fence_init();
   }
@@ -143,7 +155,10 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
-  if (warp == 2) tmem_alloc_512(smem_u32(&bars->tmem_base));
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_512_pair(smem_u32(&bars->tmem_base));
+    else tmem_alloc_512(smem_u32(&bars->tmem_base));
+  }
   tc_fence_before();
   if (MC > 1) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
@@ -162,6 +177,15 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
           mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u);
           const uint32_t full = smem_u32(&bars->full[stage]);
           const uint32_t sa = smem_base + stage * STAGE_BYTES, sbm = sa + A_STAGE_BYTES;
+          if (PAIR) {
+            // both CTAs' loads complete on rank 0's barrier, which expects the bytes of the whole pair
+            const uint32_t full0 = map_to_cta(full, 0);
+            if (rank == 0) mbar_arrive_expect_tx(full, 2 * STAGE_BYTES);
+            tma_load_2d_pair(sa, &tmA, full0, kb * KE, row0);
+            tma_load_2d_pair(sbm, &tmB, full0, kb * KE, col0 + rank * (BN / 2));
+            if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+            continue;
+          }
           mbar_arrive_expect_tx(full, STAGE_BYTES);
           tma_load_2d(sa, &tmA, full, kb * KE, row0);
           if (MC == 1) {
@@ -179,14 +203,14 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
     // ===================================== MMA issuer =======================================
     // The whole warp walks the (warp-uniform) loop; one elected lane issues.  Everything the issuing thread
     // executes per k-block is a barrier wait, two integer multiply-adds and ONE asm block.
-    constexpr uint32_t idesc = umma_idesc(TF32 ? 2 : 1, BM, BN);
+    constexpr uint32_t idesc = umma_idesc(TF32 ? 2 : 1, PAIR ? 2 * BM : BM, BN);
     const uint64_t desc0 = umma_desc_sw128(smem_base);  // stage 0, A tile; later tiles add (bytes >> 4) to the low word
-    const bool leader = elect_one();
+    const bool leader = elect_one() && (!PAIR || rank == 0);  // PAIR: only the rank-0 CTA issues
     int stage = 0;
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (unsigned long long step = 0; step < t_len; ++step) {
+    for (unsigned long long step = 0; (!PAIR || rank == 0) && step < t_len; ++step) {
       mbar_wait(smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
@@ -196,13 +220,17 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
         if (leader) {
           const uint64_t da = desc0 + (uint64_t)((uint32_t)stage * (STAGE_BYTES >> 4));
           const uint64_t db = da + (uint64_t)(A_STAGE_BYTES >> 4);
-          if (MC == 1) umma_kblock<TF32>(d_tmem, da, db, idesc, (uint32_t)(kb != 0), smem_u32(&bars->empty[stage]));
+          if (PAIR) umma_kblock_pair<TF32>(d_tmem, da, db, idesc, (uint32_t)(kb != 0), smem_u32(&bars->empty[stage]));
+          else if (MC == 1) umma_kblock<TF32>(d_tmem, da, db, idesc, (uint32_t)(kb != 0), smem_u32(&bars->empty[stage]));
           else umma_kblock_mc<TF32>(d_tmem, da, db, idesc, (uint32_t)(kb != 0), smem_u32(&bars->empty[stage]),
                                     (uint16_t)((1u << MC) - 1));
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
       }
-      if (leader) umma_commit(smem_u32(&bars->tmem_full[acc]));
+      if (leader) {
+        if (PAIR) umma_commit_pair(smem_u32(&bars->tmem_full[acc]), (uint16_t)3);
+        else umma_commit(smem_u32(&bars->tmem_full[acc]));
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
@@ -288,7 +316,10 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars->tmem_empty[acc]));
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(map_to_cta(smem_u32(&bars->tmem_empty[acc]), 0));  // the MMA issuer lives in rank 0
+        else mbar_arrive(smem_u32(&bars->tmem_empty[acc]));
+      }
 
       // combine the 4 warps' column results of this half; thread e owns column e + 128 * half
       named_bar_sync(1 + half, 128);
@@ -323,7 +354,8 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
   if (MC > 1) cluster_sync_all(); else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc_512(tmem_base);
+    if (PAIR) tmem_dealloc_512_pair(tmem_base);
+    else tmem_dealloc_512(tmem_base);
   }
 }
 
@@ -418,11 +450,11 @@ int pick_mc(int cluster) { return cluster <= 1 ? 1 : (cluster >= 4 ? 4 : 2); }
 
 // persistent grid: one CTA per SM, but never more clusters than can be resident at once (GPC
 // boundaries strand SMs for cluster sizes that do not divide a GPC), or the grid runs in two waves
-template <bool TF32, int MC>
+template <bool TF32, int MC, bool PAIR = false>
 int k2_max_clusters() {
   static int cached = 0;
   if (cached) return cached;
-  auto kern = k2_sim_top2_kernel<TF32, MC>;
+  auto kern = k2_sim_top2_kernel<TF32, MC, PAIR>;
   int n = mv_sm_count() / MC;
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_BYTES) == cudaSuccess && MC > 1) {
     cudaLaunchConfig_t cfg = {};
@@ -444,17 +476,18 @@ int k2_max_clusters() {
   return cached;
 }
 
-int k2_grid(int mc, bool tf32) {
+int k2_grid(int mc, bool tf32, bool pair = false) {
   int clusters;
   if (mc == 1) clusters = mv_sm_count();
+  else if (pair) clusters = tf32 ? k2_max_clusters<true, 2, true>() : k2_max_clusters<false, 2, true>();
   else if (mc == 2) clusters = tf32 ? k2_max_clusters<true, 2>() : k2_max_clusters<false, 2>();
   else clusters = tf32 ? k2_max_clusters<true, 4>() : k2_max_clusters<false, 4>();
   return clusters * mc;
 }
 
-template <bool TF32, int MC>
+template <bool TF32, int MC, bool PAIR = false>
 int launch_k2(const CUtensorMap& tmA, const CUtensorMap& tmB, const K2Params& p, int grid, cudaStream_t st) {
-  auto kern = k2_sim_top2_kernel<TF32, MC>;
+  auto kern = k2_sim_top2_kernel<TF32, MC, PAIR>;
   static bool attr_done = false;
   if (!attr_done) {
     MV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_BYTES));
@@ -507,8 +540,15 @@ int mv_k2_sim_top2(const void* A, const void* B, int n_max, int m_max, int C, co
   MV_CUDA(cudaDeviceGetAttribute(&cc, cudaDevAttrComputeCapabilityMajor, dev));
   MV_REQUIRE(cc == 10, MV_E_ARCH, "mv_k2_sim_top2: needs an sm_100 device (found compute capability %d.x)", cc);
 
-  const int mc = pick_mc(cluster);
-  const int grid = k2_grid(mc, tf32);
+  if (cluster == MV_CLUSTER_AUTO) {
+    // measured on B200 (tools/k2_sweep.sh): once a tile's MMA time clearly exceeds its epilogue time (K >= 1536
+    // bf16 / 768 tf32 elements) the CTA pair wins (1612 vs 1520 TFLOP/s at 19200^2 x 2048); below that the
+    // epilogue co-limits and the looser coupling of two multicast CTAs is faster (1423 vs 1343 at K = 768)
+    cluster = (C >= (tf32 ? 768 : 1536)) ? MV_CLUSTER_PAIR : 2;
+  }
+  const bool pair = cluster == MV_CLUSTER_PAIR;  // cta_group::2: two SMs on one 256 x 256 MMA tile
+  const int mc = pair ? 2 : pick_mc(cluster);
+  const int grid = k2_grid(mc, tf32, pair);
   K2Params p;
   p.clusters = grid / mc;
   const size_t need = k2_partial_bytes(n_max, mc, p.clusters);
@@ -531,7 +571,9 @@ int mv_k2_sim_top2(const void* A, const void* B, int n_max, int m_max, int C, co
 
   cudaStream_t st = mv_cuda_stream(stream);
   MV_CUDA(cudaMemsetAsync(col_best, 0, (size_t)m_max * sizeof(unsigned long long), st));
-  if (tf32) {
+  if (pair) {
+    rc = tf32 ? launch_k2<true, 2, true>(tmA, tmB, p, grid, st) : launch_k2<false, 2, true>(tmA, tmB, p, grid, st);
+  } else if (tf32) {
     if (mc == 1) rc = launch_k2<true, 1>(tmA, tmB, p, grid, st);
     else if (mc == 2) rc = launch_k2<true, 2>(tmA, tmB, p, grid, st);
     else rc = launch_k2<true, 4>(tmA, tmB, p, grid, st);

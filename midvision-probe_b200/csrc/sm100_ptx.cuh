@@ -204,6 +204,74 @@ __device__ __forceinline__ void umma_kblock_mc(uint32_t d_tmem, uint64_t a_desc,
   }
 }
 
+// ---- CTA pair (cta_group::2): two SMs of a cluster work on one 256-row MMA tile ------------------------
+// address of the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+// arrive on a barrier that may live in another CTA of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// one warp of EACH CTA of the pair executes these
+__device__ __forceinline__ void tmem_alloc_512_pair(uint32_t dst_smem) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(dst_smem) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_512_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(taddr) : "memory");
+}
+// tile load into THIS CTA's shared memory, completion signalled on a barrier that may live in the peer CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const void* tmap, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"((uint64_t)tmap), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"(mask)
+      : "memory");
+}
+// one k-block of the 256 x 256 pair tile: 4 MMAs (A: 128 rows per CTA, B: 128 of the 256 columns per CTA), then the
+// commit that frees the shared-memory slot in BOTH CTAs
+template <bool TF32>
+__device__ __forceinline__ void umma_kblock_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate_first, uint32_t empty_bar) {
+  if (TF32) {
+    asm volatile(
+        "{\n\t.reg .pred p, pt;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "add.u64 da, %1, 2;\n\tadd.u64 db, %2, 2;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %3, pt;\n\t"
+        "add.u64 da, %1, 4;\n\tadd.u64 db, %2, 4;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %3, pt;\n\t"
+        "add.u64 da, %1, 6;\n\tadd.u64 db, %2, 6;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %3, pt;\n\t"
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%5], %6;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first), "r"(empty_bar), "h"((uint16_t)3)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p, pt;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "add.u64 da, %1, 2;\n\tadd.u64 db, %2, 2;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, pt;\n\t"
+        "add.u64 da, %1, 4;\n\tadd.u64 db, %2, 4;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, pt;\n\t"
+        "add.u64 da, %1, 6;\n\tadd.u64 db, %2, 6;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, pt;\n\t"
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%5], %6;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first), "r"(empty_bar), "h"((uint16_t)3)
+        : "memory");
+  }
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));

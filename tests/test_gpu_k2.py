@@ -93,12 +93,12 @@ def test_k2_single_cta_schedule(mv, n, m, C, dtype):
 
 @pytest.mark.parametrize("n,m,C", [(1, 2, 8), (129, 257, 64), (700, 1500, 128), (1000, 777, 768), (2048, 2048, 256)])
 @pytest.mark.parametrize("dtype", ["bf16", "tf32"])
-@pytest.mark.parametrize("cluster", [2, 4])
+@pytest.mark.parametrize("cluster", [2, 4, 20])  # 20 = MV_CLUSTER_PAIR: cta_group::2, one 256 x 256 MMA per two SMs
 def test_k2_multicast_clusters(mv, n, m, C, dtype, cluster):
     check(mv, n, m, C, dtype, cluster=cluster)
 
 
-@pytest.mark.parametrize("cluster", [0, 2])
+@pytest.mark.parametrize("cluster", [0, 2, 20])
 def test_k2_device_resident_counts_mask_stale_rows(mv, cluster):
     # live counts on the device, garbage beyond them
     check(mv, 900, 1100, 64, "bf16", cluster, n_live=611, m_live=1023)
@@ -124,7 +124,7 @@ def test_k2_repeatable(mv):
     assert all(torch.equal(x, y) for x, y in zip(a, b))
 
 
-@pytest.mark.parametrize("dtype,cluster", [("bf16", 0), ("bf16", 2), ("tf32", 0)])
+@pytest.mark.parametrize("dtype,cluster", [("bf16", 0), ("bf16", 2), ("tf32", 0), ("bf16", 20), ("tf32", 20)])
 def test_k2_full_size_properties(mv, syn, dtype, cluster):
     """19200 x 19200 x 768 (BASELINE.json stress config): too big for an element-wise CPU check, so
     size-independent properties: B = A => every row's arg-max is itself, mutual everywhere; and a sampled

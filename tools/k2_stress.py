@@ -18,7 +18,7 @@ ap.add_argument("--n", type=int, default=19200)
 ap.add_argument("--m", type=int, default=19200)
 ap.add_argument("--C", type=int, default=768)
 ap.add_argument("--dtype", default="bf16")
-ap.add_argument("--cluster", type=int, default=0)
+ap.add_argument("--cluster", type=int, default=-1)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--variant", default="iid")
 a = ap.parse_args()
