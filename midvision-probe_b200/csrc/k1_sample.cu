@@ -12,18 +12,14 @@
 //   evaluate_spair_correspondence.py:59-79 per-pixel normalise + keypoint grid_sample(align_corners=True)
 //
 // Data layout: the source map is channel-last so that every tap is one contiguous C-vector read with
-// 128-bit loads; consecutive live points are handled by the same CTA, which keeps the taps they share
-// in registers (an 8x upsample re-uses each tap ~8 times along x), so the kernel's traffic is the
-// row writes: C*h*w*4 bytes read + n*C*(2 [+4]) bytes written.
-#include <limits.h>
+// 128-bit loads; consecutive live points are handled by the same CTA, which stages the source columns they
+// share in shared memory once (an 8x upsample re-uses each tap ~8 times along x), so the kernel's traffic is
+// the row writes: C*h*w*4 bytes read + n*C*(2 [+4]) bytes written.
 
 #include "common.cuh"
 
 namespace {
 
-constexpr int K1_THREADS_MAX = 512;  // 128 registers per thread: the tap window + a batch of accumulators fit
-constexpr int K1_BATCH_MAX = 4;  // points per block-level reduction (template parameter K1_BATCH <= this)
-constexpr int K1_MAX_RUN = 64;  // most points one CTA owns
 constexpr float K1_NORM_EPS = 1e-12f;  // F.normalize default eps
 
 // ------------------------------------------------------------------------------------------
@@ -231,224 +227,267 @@ __device__ __forceinline__ void cubic_coeffs(float t, float c[4]) {
   c[3] = ((A * x3 - 5.f * A) * x3 + 8.f * A) * x3 - 4.f * A;
 }
 
-// One CTA owns a run of consecutive points and all C channels (thread = 4 * NV channels), so the taps that
-// neighbouring points share stay in REGISTERS instead of being re-read through L1/L2:
-//   bilinear: the raw 2 x 2 tap window is kept; an 8x upsample re-uses it for ~8 consecutive points and a
-//             step to the next source cell loads 2 new taps instead of 4 (same arithmetic as a cold point);
-//   bicubic : the 4 columns of the 4 x 4 window are pre-blended along y (consecutive points of an output row
-//             have the bit-identical y coordinate), so a step in x costs 4 tap loads instead of 16.
-template <int MODE, int NV, int K1_BATCH, int MAXT, int MINB>
-__global__ void __launch_bounds__(MAXT, MINB) k1_sample_normalize_kernel(K1Params p) {
-  __shared__ float red[K1_BATCH_MAX][K1_THREADS_MAX / 32];
-  __shared__ float bcast[K1_BATCH_MAX];
-  __shared__ float2 s_coords[K1_MAX_RUN];
+// ------------------------------------------------------------------------------------------
+// kernel 1: one warp per output point over a shared-memory window of source columns
+// ------------------------------------------------------------------------------------------
+// A CTA owns a range of consecutive live points and cuts it into SUB-RUNS: maximal prefixes of points that
+// lie on one output row and whose taps fall into a window of source columns that fits shared memory.
+//   phase S (warp 0): per point scalars (tap origin, 4 blend weights, 4 shared-memory offsets) + the window
+//   phase A (all threads): fill the window in shared memory from the L2-resident channel-last map --
+//            bicubic: the 4 source rows blended along y ONCE per column (every point of the sub-run has the
+//            bit-identical y coordinate), bilinear: the two raw source rows (zeros outside the map)
+//   phase B (one WARP per point): 4 x LDS.128 + 16 FMA per 4 channels, the whole row of C channels stays in
+//            the warp's registers, the sum of squares needs 5 shuffles per POINT (not per warp of a
+//            block-wide reduction) and no block barrier, then scale + bf16 / fp32 row stores (512 B and
+//            256 B contiguous per warp instruction).
+// Per output element: 1 LDS + 6 FMA/FMUL + ~1 convert/store, and no barrier inside the per-point loop (the
+// first version -- one CTA per point, taps in registers, block-wide reduction -- issued ~37 instructions per
+// element and ran at 2.6 TB/s; this form runs at the write-bandwidth limit of the part).
+constexpr int K1W_PMAX = 32;                // points per sub-run: one warp inspects them with a ballot
+constexpr int K1W_SMEM_BUDGET = 108 << 10;  // window bytes per CTA: two CTAs per SM
+constexpr int K1W_OUT_BOTH = 0, K1W_OUT_F32 = 1, K1W_OUT_ANY = 2;  // which row outputs exist (ANY: checked at run time)
+
+struct K1WShared {
+  float wt[K1W_PMAX][4];
+  int off[K1W_PMAX][4];  // float offsets into the window
+  float cy[4];
+  int npts, ncols, xbase, y0;
+};
+
+__device__ __forceinline__ float4 lds4(const float* q) { return *reinterpret_cast<const float4*>(q); }
+__device__ __forceinline__ float dot4(const float4& v, float ss) {
+  ss = fmaf(v.x, v.x, ss);
+  ss = fmaf(v.y, v.y, ss);
+  ss = fmaf(v.z, v.z, ss);
+  return fmaf(v.w, v.w, ss);
+}
+
+// NIT > 0: C == 128 * NIT exactly, the row lives in NIT float4 registers per lane, no channel predicates.
+// NIT == 0: any C (multiple of 4): two passes over the window (sum of squares, then values), nothing held.
+template <int MODE, int NIT, int OUTS, int THREADS>
+__global__ void __launch_bounds__(THREADS, 2) k1_warp_rows_kernel(K1Params p, int nslots, uint32_t c4_magic) {
+  extern __shared__ float4 k1w_dyn[];
+  float* win = reinterpret_cast<float*>(k1w_dyn);
+  __shared__ K1WShared sh;
   const int n = p.n_dev ? min(*p.n_dev, p.n_max) : p.n_max;
-  const int C4 = p.C >> 2;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = blockDim.x >> 5;
-  // run length from the LIVE point count: every CTA of the (host-sized) grid gets an equal share, so a
-  // device-resident count far below n_max does not leave most SMs idle
-  int ppc = (n + (int)gridDim.x - 1) / (int)gridDim.x;
-  ppc = min(max((ppc + K1_BATCH - 1) / K1_BATCH * K1_BATCH, K1_BATCH), K1_MAX_RUN);
-  const int pt_beg = blockIdx.x * ppc;
+  const int C = (NIT > 0) ? NIT * 128 : p.C, C4 = C >> 2;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  constexpr int NWARP = THREADS / 32;
+  const int ppc = (n + (int)gridDim.x - 1) / (int)gridDim.x;  // from the LIVE count: no idle SMs for a small n
+  const int pt_beg = min(blockIdx.x * ppc, n);
   const int pt_end = min(pt_beg + ppc, n);
+  const bool has32 = (OUTS != K1W_OUT_ANY) || p.out_f32 != nullptr;
+  const bool has16 = (OUTS == K1W_OUT_BOTH) || (OUTS == K1W_OUT_ANY && p.out_bf16 != nullptr);
+  const bool normalize = p.normalize != 0;
 
-  // tap cache (see above)
-  constexpr int NWIN = (MODE == MV_SAMPLE_BILINEAR_ZEROS) ? 4 : (MODE == MV_SAMPLE_BICUBIC_CLAMP ? 4 : 1);
-  float4 win[NWIN][NV];
-  int wx = INT_MIN, wy = INT_MIN;
-  float wiy = 0.f;
-
-  auto load_tap = [&](int xx, int yy, float4 (&dst)[NV]) {  // zero outside the map (bilinear zero padding)
-    const bool in = xx >= 0 && xx < p.w && yy >= 0 && yy < p.h;
-    const float* row = p.src + ((size_t)(in ? yy : 0) * p.w + (in ? xx : 0)) * p.C;
-#pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int c4 = tid + v * blockDim.x;
-      dst[v] = (in && c4 < C4) ? ld4(row + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+  auto put = [&](int pt, int c, float4 o, float inv) {
+    o.x *= inv;  // inv == 1 when not normalising: exact
+    o.y *= inv;
+    o.z *= inv;
+    o.w *= inv;
+    if (has32) __stcs(reinterpret_cast<float4*>(p.out_f32 + (size_t)pt * C + c), o);
+    if (has16) {
+      __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&lo);
+      pk.y = *reinterpret_cast<uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)pt * C + c) = pk;
     }
   };
-  auto load_cubic_col = [&](int xx, int y0, const float (&cy)[4], float4 (&dst)[NV]) {  // sum_i cy[i] * src[clamp(y0-1+i)][clamp(xx)]
-    const int xc = min(max(xx, 0), p.w - 1);
+  // value_at(c) -> un-normalised float4 of channels [c, c + 4)
+  auto finish_point = [&](int pt, auto&& value_at) {
+    if (NIT > 0) {
+      float4 acc[NIT > 0 ? NIT : 1];
+      float ss = 0.f;
 #pragma unroll
-    for (int v = 0; v < NV; ++v) dst[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int yc = min(max(y0 - 1 + i, 0), p.h - 1);
-      const float* row = p.src + ((size_t)yc * p.w + xc) * p.C;
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        const int c4 = tid + v * blockDim.x;
-        if (c4 < C4) fma4(dst[v], cy[i], ld4(row + 4 * c4));
+      for (int it = 0; it < NIT; ++it) {
+        acc[it] = value_at((it * 32 + lane) * 4);
+        ss = dot4(acc[it], ss);
       }
+      float inv = 1.f;
+      if (normalize) inv = __frcp_rn(fmaxf(sqrtf(warp_sum(ss)), K1_NORM_EPS));  // x * (1 / max(||x||, eps))
+#pragma unroll
+      for (int it = 0; it < NIT; ++it) put(pt, (it * 32 + lane) * 4, acc[it], inv);
+    } else {
+      float inv = 1.f;
+      if (normalize) {
+        float ss = 0.f;
+        for (int c = lane * 4; c < C; c += 128) ss = dot4(value_at(c), ss);
+        inv = __frcp_rn(fmaxf(sqrtf(warp_sum(ss)), K1_NORM_EPS));
+      }
+      for (int c = lane * 4; c < C; c += 128) put(pt, c, value_at(c), inv);
     }
   };
 
-  // source coordinates of the whole run, once, coalesced (kills the coords -> address latency per point)
-  if (MODE != MV_SAMPLE_ROWS) {
-    for (int q = tid; q < pt_end - pt_beg; q += blockDim.x)
-      s_coords[q] = __ldg(reinterpret_cast<const float2*>(p.coords) + pt_beg + q);
-    __syncthreads();
+  if (MODE == MV_SAMPLE_ROWS) {  // rows as they are: one warp per row, no window
+    for (int pt = pt_beg + wid; pt < pt_end; pt += NWARP) {
+      const float* row = p.src + (size_t)pt * C;
+      finish_point(pt, [&](int c) { return ld4(row + c); });
+    }
+    return;
   }
 
-  // points are processed K1_BATCH at a time: one pair of block barriers (the L2-norm reduction) per batch
-  for (int pt0 = pt_beg; pt0 < pt_end; pt0 += K1_BATCH) {
-    float4 acc[K1_BATCH][NV];
-#pragma unroll
-    for (int b = 0; b < K1_BATCH; ++b) {
-#pragma unroll
-      for (int v = 0; v < NV; ++v) acc[b][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      const int pt = pt0 + b;
-      if (pt >= pt_end) continue;
+  constexpr bool CUBIC = (MODE == MV_SAMPLE_BICUBIC_CLAMP);
+  const int max_cols = CUBIC ? nslots : (nslots >> 1);
+  const int max_dx = max_cols - (CUBIC ? 4 : 2);  // tap origins x0 .. x0 + max_dx share one window
 
-      if (MODE == MV_SAMPLE_ROWS) {
-        const float* row = p.src + (size_t)pt * p.C;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          int c4 = tid + v * blockDim.x;
-          if (c4 < C4) acc[b][v] = ld4(row + 4 * c4);
-        }
-      } else if (MODE == MV_SAMPLE_BILINEAR_ZEROS) {
-        // ATen GridSamplerKernel.cpp (bilinear, zeros): w = ix - floor(ix), e = 1 - w, n = iy - floor(iy), s = 1 - n
-        const float ix = s_coords[pt - pt_beg].x, iy = s_coords[pt - pt_beg].y;
-        const float fx = floorf(ix), fy = floorf(iy);
-        const int x0 = (int)fx, y0 = (int)fy;
-        const float ww = ix - fx, we = 1.f - ww, wn = iy - fy, ws = 1.f - wn;
-        if (p.taps && tid == 0) {
+  int cur = pt_beg;
+  while (cur < pt_end) {  // uniform across the CTA
+    // ---- phase S ----
+    if (wid == 0) {
+      const int pt = cur + lane;
+      const bool live = pt < pt_end;
+      float2 xy = make_float2(0.f, 0.f);
+      if (live) xy = __ldg(reinterpret_cast<const float2*>(p.coords) + pt);
+      const float fx = floorf(xy.x), fy = floorf(xy.y);
+      const int x0 = (int)fx, y0 = (int)fy;
+      const int x0f = __shfl_sync(0xffffffffu, x0, 0), y0f = __shfl_sync(0xffffffffu, y0, 0);
+      const uint32_t iyf = __shfl_sync(0xffffffffu, __float_as_uint(xy.y), 0);
+      const int dx = x0 - x0f;
+      bool ok = live && y0 == y0f && dx >= 0 && dx <= max_dx;
+      if (CUBIC) ok = ok && (__float_as_uint(xy.y) == iyf);  // one y blend serves the whole sub-run
+      const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+      const int npts = (bal == 0xffffffffu) ? 32 : (__ffs(~bal) - 1);  // leading run of ok lanes (lane 0 always is)
+      const int dxmax = __reduce_max_sync(0xffffffffu, lane < npts ? dx : 0);
+      const int ncols = dxmax + (CUBIC ? 4 : 2);
+      if (lane < npts) {
+        if (p.taps) {
           p.taps[2 * (size_t)pt] = x0;
           p.taps[2 * (size_t)pt + 1] = y0;
         }
-        // window layout: win[0] = (x0, y0) nw, win[1] = (x0+1, y0) ne, win[2] = (x0, y0+1) sw, win[3] = (x0+1, y0+1) se
-        if (y0 == wy && x0 == wx) {
-          // same source cell: every tap is already in registers
-        } else if (y0 == wy && x0 == wx + 1) {
+        if (CUBIC) {
+          float cx[4];
+          cubic_coeffs(xy.x - fx, cx);
 #pragma unroll
-          for (int v = 0; v < NV; ++v) { win[0][v] = win[1][v]; win[2][v] = win[3][v]; }
-          load_tap(x0 + 1, y0, win[1]);
-          load_tap(x0 + 1, y0 + 1, win[3]);
-        } else {
-          load_tap(x0, y0, win[0]);
-          load_tap(x0 + 1, y0, win[1]);
-          load_tap(x0, y0 + 1, win[2]);
-          load_tap(x0 + 1, y0 + 1, win[3]);
-        }
-        wx = x0;
-        wy = y0;
-        const float wt[4] = {ws * we, ws * ww, wn * we, wn * ww};  // nw, ne, sw, se
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-#pragma unroll
-          for (int v = 0; v < NV; ++v) fma4(acc[b][v], wt[k], win[k][v]);
-        }
-      } else {  // MV_SAMPLE_BICUBIC_CLAMP
-        const float ix = s_coords[pt - pt_beg].x, iy = s_coords[pt - pt_beg].y;
-        const float fx = floorf(ix), fy = floorf(iy);
-        const int x0 = (int)fx, y0 = (int)fy;
-        if (p.taps && tid == 0) {
-          p.taps[2 * (size_t)pt] = x0;
-          p.taps[2 * (size_t)pt + 1] = y0;
-        }
-        float cx[4], cy[4];
-        cubic_coeffs(ix - fx, cx);
-        cubic_coeffs(iy - fy, cy);
-        // win[j] = y-blended column x0 - 1 + j; valid while iy is bit-identical
-        const bool same_row = (wy == y0) && (__float_as_uint(wiy) == __float_as_uint(iy));
-        if (same_row && x0 == wx) {
-        } else if (same_row && x0 == wx + 1) {
-#pragma unroll
-          for (int v = 0; v < NV; ++v) { win[0][v] = win[1][v]; win[1][v] = win[2][v]; win[2][v] = win[3][v]; }
-          load_cubic_col(x0 + 2, y0, cy, win[3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) load_cubic_col(x0 - 1 + j, y0, cy, win[j]);
-        }
-        wx = x0;
-        wy = y0;
-        wiy = iy;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-#pragma unroll
-          for (int v = 0; v < NV; ++v) fma4(acc[b][v], cx[j], win[j][v]);
-        }
-      }
-    }
-
-    float denom[K1_BATCH];
-#pragma unroll
-    for (int b = 0; b < K1_BATCH; ++b) denom[b] = 1.f;
-    if (p.normalize) {
-#pragma unroll
-      for (int b = 0; b < K1_BATCH; ++b) {
-        float ss = 0.f;
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          ss = fmaf(acc[b][v].x, acc[b][v].x, ss);
-          ss = fmaf(acc[b][v].y, acc[b][v].y, ss);
-          ss = fmaf(acc[b][v].z, acc[b][v].z, ss);
-          ss = fmaf(acc[b][v].w, acc[b][v].w, ss);
-        }
-        ss = warp_sum(ss);
-        if (lane == 0) red[b][wid] = ss;
-      }
-      __syncthreads();
-      for (int b = wid; b < K1_BATCH; b += nwarp) {  // warp b finishes point b
-        float t = (lane < nwarp) ? red[b][lane] : 0.f;
-        t = warp_sum(t);
-        if (lane == 0) bcast[b] = __frcp_rn(fmaxf(sqrtf(t), K1_NORM_EPS));
-      }
-      __syncthreads();
-#pragma unroll
-      for (int b = 0; b < K1_BATCH; ++b) denom[b] = bcast[b];
-    }
-
-#pragma unroll
-    for (int b = 0; b < K1_BATCH; ++b) {
-      const int pt = pt0 + b;
-      if (pt >= pt_end) continue;
-#pragma unroll
-      for (int v = 0; v < NV; ++v) {
-        int c4 = tid + v * blockDim.x;
-        if (c4 < C4) {
-          float4 o = acc[b][v];
-          if (p.normalize) {  // x * (1 / max(||x||, eps)): within 1 ulp of F.normalize's division
-            o.x *= denom[b];
-            o.y *= denom[b];
-            o.z *= denom[b];
-            o.w *= denom[b];
+          for (int j = 0; j < 4; ++j) {  // window slot s holds source column clamp(x0f - 1 + s)
+            sh.wt[lane][j] = cx[j];
+            sh.off[lane][j] = (dx + j) * C;
           }
-          if (p.out_f32) __stcs(reinterpret_cast<float4*>(p.out_f32 + (size_t)pt * p.C + 4 * c4), o);
-          if (p.out_bf16) {
-            __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
-            uint2 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&lo);
-            pk.y = *reinterpret_cast<uint32_t*>(&hi);
-            *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)pt * p.C + 4 * c4) = pk;
-          }
+        } else {
+          // ATen GridSamplerKernel.cpp (bilinear, zeros): w = ix - floor(ix), e = 1 - w, n = iy - floor(iy), s = 1 - n
+          const float ww = xy.x - fx, we = 1.f - ww, wn = xy.y - fy, ws = 1.f - wn;
+          sh.wt[lane][0] = ws * we;  // nw
+          sh.wt[lane][1] = ws * ww;  // ne
+          sh.wt[lane][2] = wn * we;  // sw
+          sh.wt[lane][3] = wn * ww;  // se
+          sh.off[lane][0] = dx * C;
+          sh.off[lane][1] = (dx + 1) * C;
+          sh.off[lane][2] = (ncols + dx) * C;
+          sh.off[lane][3] = (ncols + dx + 1) * C;
         }
       }
+      if (lane == 0) {
+        sh.npts = npts;
+        sh.ncols = ncols;
+        sh.xbase = CUBIC ? x0 - 1 : x0;
+        sh.y0 = y0;
+        if (CUBIC) cubic_coeffs(xy.y - fy, sh.cy);
+      }
     }
-    // `red`/`bcast` are rewritten next batch only after the first __syncthreads there, and every thread
-    // has read `bcast` before it can pass that barrier: no extra barrier needed.
+    __syncthreads();
+    const int npts = sh.npts, ncols = sh.ncols, xbase = sh.xbase, y0 = sh.y0;
+
+    // ---- phase A: one flat loop over (window slot, 4 channels), 4 items = up to 16 loads in flight per thread ----
+    if (CUBIC) {
+      const float cy0 = sh.cy[0], cy1 = sh.cy[1], cy2 = sh.cy[2], cy3 = sh.cy[3];
+      const size_t rs = (size_t)p.w * C;
+      const float* r0 = p.src + (size_t)min(max(y0 - 1, 0), p.h - 1) * rs;
+      const float* r1 = p.src + (size_t)min(max(y0, 0), p.h - 1) * rs;
+      const float* r2 = p.src + (size_t)min(max(y0 + 1, 0), p.h - 1) * rs;
+      const float* r3 = p.src + (size_t)min(max(y0 + 2, 0), p.h - 1) * rs;
+      const int items = ncols * C4;
+#pragma unroll 4
+      for (int idx = tid; idx < items; idx += THREADS) {
+        const int s = (int)__umulhi((uint32_t)idx, c4_magic);  // idx / C4
+        const int c = (idx - s * C4) * 4;
+        const int xo = min(max(xbase + s, 0), p.w - 1) * C + c;
+        const float4 a = ld4(r0 + xo), b = ld4(r1 + xo), cc = ld4(r2 + xo), d = ld4(r3 + xo);
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        fma4(o, cy0, a);
+        fma4(o, cy1, b);
+        fma4(o, cy2, cc);
+        fma4(o, cy3, d);
+        *reinterpret_cast<float4*>(win + idx * 4) = o;  // slot s, channel c  ==  float offset s * C + c
+      }
+    } else {
+      const int items = 2 * ncols * C4;
+#pragma unroll 8
+      for (int idx = tid; idx < items; idx += THREADS) {
+        const int slot = (int)__umulhi((uint32_t)idx, c4_magic);  // r * ncols + s
+        const int c = (idx - slot * C4) * 4;
+        const int r = slot >= ncols ? 1 : 0;
+        const int yy = y0 + r, xx = xbase + slot - r * ncols;
+        const bool in = yy >= 0 && yy < p.h && xx >= 0 && xx < p.w;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (in) v = ld4(p.src + ((size_t)yy * p.w + xx) * C + c);
+        *reinterpret_cast<float4*>(win + idx * 4) = v;
+      }
+    }
+    __syncthreads();
+
+    // ---- phase B ----
+    for (int t = wid; t < npts; t += NWARP) {
+      const float w0 = sh.wt[t][0], w1 = sh.wt[t][1], w2 = sh.wt[t][2], w3 = sh.wt[t][3];
+      const float* q0 = win + sh.off[t][0];
+      const float* q1 = win + sh.off[t][1];
+      const float* q2 = win + sh.off[t][2];
+      const float* q3 = win + sh.off[t][3];
+      finish_point(cur + t, [&](int c) {
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        fma4(o, w0, lds4(q0 + c));
+        fma4(o, w1, lds4(q1 + c));
+        fma4(o, w2, lds4(q2 + c));
+        fma4(o, w3, lds4(q3 + c));
+        return o;
+      });
+    }
+    __syncthreads();  // the window and the per-point scalars are rewritten by the next sub-run
+    cur += npts;
   }
 }
 
-template <int MODE>
-int launch_k1(const K1Params& p, int threads, int nv, int grid, cudaStream_t st) {
-  // thread = 4 * NV channels.  NV = 4 amortises the per-point scalar work (coordinates, cubic weights, window
-  // bookkeeping, reduction) over 16 outputs; its batch is 2 points to stay inside 128 registers.
-  switch (nv) {
-    case 1: k1_sample_normalize_kernel<MODE, 1, 4, 128, 1><<<grid, threads, 0, st>>>(p); break;
-    case 2: k1_sample_normalize_kernel<MODE, 2, 4, 128, 1><<<grid, threads, 0, st>>>(p); break;
-    case 4:
-      // C <= 4096: at most 256 threads, registers to spare for the loads in flight; wider rows still run (512 threads)
-      if (threads <= 256) k1_sample_normalize_kernel<MODE, 4, 2, 256, 2><<<grid, threads, 0, st>>>(p);
-      else k1_sample_normalize_kernel<MODE, 4, 2, 512, 1><<<grid, threads, 0, st>>>(p);
-      break;
-    default:
-      mv_set_error("mv_k1_sample_normalize: unsupported channel split");
-      return MV_E_RANGE;
+template <int MODE, int NIT, int OUTS, int THREADS>
+int launch_k1_warp_inst(const K1Params& p, int grid, size_t smem, int nslots, cudaStream_t st) {
+  auto kern = k1_warp_rows_kernel<MODE, NIT, OUTS, THREADS>;
+  static size_t opted_in = 48 << 10;  // per instantiation: the attribute belongs to the device function
+  if (smem > opted_in) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      mv_set_error("mv_k1_sample_normalize: cannot opt in to %zu bytes of shared memory: %s", smem,
+                   cudaGetErrorString(e));
+      return (int)e;
+    }
+    opted_in = smem;
   }
+  const uint32_t C4 = (uint32_t)p.C / 4;
+  const uint32_t magic = (uint32_t)((0x100000000ull + C4 - 1) / C4);  // idx / C4 == umulhi(idx, magic) for idx * C4 < 2^32
+  kern<<<grid, THREADS, smem, st>>>(p, nslots, magic);
   MV_LAUNCH_CHECK();
   return MV_OK;
+}
+
+template <int MODE>
+int launch_k1_warp(const K1Params& p, cudaStream_t st) {
+  const int C = p.C;
+  int nslots = K1W_SMEM_BUDGET / (C * 4);
+  if (nslots < 4) nslots = 4;    // C <= 8192: 4 slots = 128 KB, one CTA per SM
+  if (nslots > 40) nslots = 40;  // more than any 32-point sub-run can use
+  const size_t smem = (MODE == MV_SAMPLE_ROWS) ? 0 : (size_t)nslots * C * 4;
+  int grid = mv_sm_count() * 2;
+  if (grid > p.n_max) grid = p.n_max;
+  if (grid < 1) grid = 1;
+  const int outs = (p.out_f32 && p.out_bf16) ? K1W_OUT_BOTH : (p.out_f32 ? K1W_OUT_F32 : K1W_OUT_ANY);
+#define K1W_CASE(NIT, THREADS)                                                                                     \
+  if (C == 128 * NIT && outs == K1W_OUT_BOTH)                                                                      \
+    return launch_k1_warp_inst<MODE, NIT, K1W_OUT_BOTH, THREADS>(p, grid, smem, nslots, st);                       \
+  if (C == 128 * NIT && outs == K1W_OUT_F32)                                                                       \
+    return launch_k1_warp_inst<MODE, NIT, K1W_OUT_F32, THREADS>(p, grid, smem, nslots, st);
+  K1W_CASE(6, 256)   // ViT-B   768
+  K1W_CASE(8, 256)   // ViT-L   1024
+  K1W_CASE(16, 256)  // ResNet-50 layer4 2048
+  K1W_CASE(24, 192)  // ViT-B 4-block concat 3072: 96 row registers per lane -> 6 warps x 168 registers
+#undef K1W_CASE
+  return launch_k1_warp_inst<MODE, 0, K1W_OUT_ANY, 256>(p, grid, smem, nslots, st);
 }
 
 Mat3 load_mat3(const float* host) {
@@ -562,25 +601,10 @@ int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, cons
   p.out_f32 = out_f32;
   p.taps = taps;
 
-  // thread = 4 * nv channels; one CTA = all channels of a run of consecutive points
-  const int C4 = C / 4;
-  const int nv = C4 >= 256 ? 4 : (C4 >= 128 ? 2 : 1);
-  const int threads = (((C4 + nv - 1) / nv + 31) / 32) * 32;  // <= 512 for C <= 8192
-  // long runs amortise the tap loads, a few CTAs per SM overlap their barriers; the kernel re-derives the run
-  // length from the live count, the grid only has to cover n_max at the longest run (K1_MAX_RUN)
-  int per_sm = 512 / threads;
-  if (per_sm < 1) per_sm = 1;
-  if (per_sm > 4) per_sm = 4;
-  int grid = mv_sm_count() * per_sm;
-  const int need = (n_max + K1_MAX_RUN - 1) / K1_MAX_RUN;
-  if (grid < need) grid = need;
-  const int most = (n_max + 1) / 2;
-  if (grid > most) grid = most;
-  if (grid < 1) grid = 1;
   cudaStream_t st = mv_cuda_stream(stream);
-  if (mode == MV_SAMPLE_BILINEAR_ZEROS) return launch_k1<MV_SAMPLE_BILINEAR_ZEROS>(p, threads, nv, grid, st);
-  if (mode == MV_SAMPLE_BICUBIC_CLAMP) return launch_k1<MV_SAMPLE_BICUBIC_CLAMP>(p, threads, nv, grid, st);
-  return launch_k1<MV_SAMPLE_ROWS>(p, threads, nv, grid, st);
+  if (mode == MV_SAMPLE_BILINEAR_ZEROS) return launch_k1_warp<MV_SAMPLE_BILINEAR_ZEROS>(p, st);
+  if (mode == MV_SAMPLE_BICUBIC_CLAMP) return launch_k1_warp<MV_SAMPLE_BICUBIC_CLAMP>(p, st);
+  return launch_k1_warp<MV_SAMPLE_ROWS>(p, st);
 }
 
 }  // extern "C"

@@ -3,6 +3,7 @@
     python tools/k1_probe.py [--kind navi|scannet] [--reps R] [--nosync]
 """
 import argparse
+import ctypes
 import importlib
 import os
 import sys
@@ -30,6 +31,25 @@ else:
     f, g = p["feat_0"].cuda(), p["depth_0"].cuda()
     Kh, Kinv = C_._host_mat(p["K"]), C_._host_mat(p["K"].inverse())
     run = lambda: C_.prepare_depth_side(f, g, Kh, Kinv, dev, sync=not a.nosync)
+# CUDA events around the kernel-1 launch itself (the rest of `prepare` is the small producers)
+_k1_events = []
+_orig_sample = C_._sample
+
+
+_k1_args = []
+
+
+def _timed_sample(*args, **kw):
+    _k1_args.append(args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = _orig_sample(*args, **kw)
+    e1.record()
+    _k1_events.append((e0, e1))
+    return out
+
+
+C_._sample = _timed_sample
 s = run()
 n = int(s.n_dev.item())
 C = f.shape[0]
@@ -44,6 +64,38 @@ for _ in range(a.reps):
     torch.cuda.synchronize()
     times.append(e0.elapsed_time(e1))
 ms = sorted(times)[len(times) // 2]
+k1 = sorted(a_.elapsed_time(b_) for a_, b_ in _k1_events[1:])
+k1_ms = k1[len(k1) // 2]
 byts = C * f.shape[1] * f.shape[2] * 4 + n * C * (6 if s.rows16 is not None else 4)
 print(f"{a.kind} side: n={n} C={C} whole prepare (compact + coords + transpose + kernel 1) {ms * 1e3:.1f} us; "
-      f"kernel-1 algorithmic bytes {byts / 1e6:.1f} MB")
+      f"kernel-1 algorithmic bytes {byts / 1e6:.1f} MB; kernel 1 alone {k1_ms * 1e3:.1f} us = "
+      f"{byts / k1_ms / 1e6:.0f} GB/s (L2 flushed before each call)")
+
+# kernel 1 alone, device-bound: 4 rotating output sets (> L2) so no launch finds its rows in L2, 24 launches
+# replayed from one CUDA graph so the host is out of the picture
+mode, src, C_, h, w, coords, n_dev, n_max, normalize, want16, want32 = _k1_args[0][:11]
+L = mv._lib
+outs = [(torch.empty((n_max, C_), dtype=torch.bfloat16, device=dev), torch.empty((n_max, C_), dtype=torch.float32, device=dev))
+        for _ in range(4)]
+st = torch.cuda.Stream()
+with torch.cuda.stream(st):
+    def launch(i):
+        o16, o32 = outs[i % 4]
+        L.call("mv_k1_sample_normalize", mode, L.ptr(src), C_, h, w, L.ptr(coords), L.ptr(n_dev), n_max, int(normalize),
+               L.ptr(o16), L.ptr(o32), None, ctypes.c_void_p(st.cuda_stream))
+    launch(0)
+    st.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g, stream=st):
+        for i in range(24):
+            launch(i)
+    g.replay()
+    st.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    g.replay()
+    e1.record(st)
+    st.synchronize()
+us = e0.elapsed_time(e1) / 24 * 1e3
+print(f"kernel 1 device time (graph of 24 launches, rotating outputs): {us:.1f} us = {byts / us / 1e3:.0f} GB/s "
+      f"= {100 * byts / us / 1e3 / 6544:.0f} % of 6544 GB/s")
