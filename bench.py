@@ -199,6 +199,9 @@ def main():
     ap.add_argument("--no-stress", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     ap.add_argument("--lanes", type=int, default=3, help="pairs in flight on separate streams (CUDA-graph arm)")
+    ap.add_argument("--feat-layout", default="chw", choices=["chw", "hwc"],
+                    help="memory layout of the (C, h, w) feature tensors handed to the path: chw = contiguous, as the "
+                         "reference's tokens_to_output returns them; hwc = channel-last views (ViT token order), no transpose kernel")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -225,8 +228,18 @@ def main():
     pool_host = make_pool(syn, args.workload, rank, world, POOL)
     keys = [k for k in pool_host[0] if torch.is_tensor(pool_host[0][k])]
     big = ("feat_0", "feat_1", "xyz_grid_0", "xyz_grid_1", "depth_0", "depth_1")  # Rt / K are 3x4 host parameters, like in the callers
+    if args.feat_layout == "hwc":
+        for p in pool_host:
+            for k in ("feat_0", "feat_1"):
+                p[k] = p[k].permute(1, 2, 0).contiguous().permute(2, 0, 1)  # same (C, h, w) tensor, channel-last memory
+
+    def pin(v):
+        if v.dim() == 3 and not v.is_contiguous():  # keep the channel-last strides in pinned memory
+            return v.permute(1, 2, 0).contiguous().pin_memory().permute(2, 0, 1)
+        return v.pin_memory()
+
     pool_dev = [{k: (v.to(dev) if k in big else v) for k, v in p.items()} for p in pool_host]
-    pool_pin = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in p.items()} for p in pool_host]
+    pool_pin = [{k: (pin(v) if torch.is_tensor(v) else v) for k, v in p.items()} for p in pool_host]
     acc = ev.RecallAccumulator(THR3, THR2, device=dev)
 
     def pair_eager(p):
@@ -239,7 +252,7 @@ def main():
     if not args.no_graph:
         p0 = pool_dev[0]
         gm = ev.PairPipeline("xyz" if args.workload == "navi" else "depth", tuple(p0["feat_0"].shape), tuple(p0[gk[0]].shape),
-                             NUM_CORR, K=p0.get("K"), device=dev, lanes=args.lanes)
+                             NUM_CORR, K=p0.get("K"), device=dev, lanes=args.lanes, feat_layout=args.feat_layout)
 
     def pair_device(p):
         if gm is None:
@@ -354,7 +367,7 @@ def main():
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload_name(args.workload), "pairs_per_step": PAIRS_PER_STEP, "pool_pairs": POOL,
                        "l2": "inputs larger than L2: 16 distinct pairs cycled, ~190 MB of features + rows touched per pair vs 126 MB L2",
-                       "k2_cluster": args.cluster, "cuda_graph": gm is not None, "pairs_in_flight": args.lanes if gm is not None else 1, "features": "seeded N(0,1) maps of the backbone's output shape"},
+                       "k2_cluster": args.cluster, "cuda_graph": gm is not None, "pairs_in_flight": args.lanes if gm is not None else 1, "features": "seeded N(0,1) maps of the backbone's output shape", "feat_layout": args.feat_layout},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "correspondence.estimate_correspondence_xyz(host tensors)" if args.workload == "navi"

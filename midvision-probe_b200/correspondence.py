@@ -89,6 +89,27 @@ def _hwc(feat, prenorm=False):
     return out
 
 
+def _is_channel_last(feat):
+    """True when a (C, h, w) tensor is a permuted view of contiguous (h, w, C) memory -- the layout ViT tokens
+    have before tokens_to_output's .contiguous() (evals/models/utils.py:111-114) and channels_last CNN outputs."""
+    C, h, w = feat.shape
+    return feat.dtype == torch.float32 and feat.stride() == (1, w * C, C) and not (h * w == 1 or C == 1)
+
+
+def _feature_map(feat, dev, prenorm=False):
+    """(C, h, w) features (any device) -> (channel-last (h*w, C) fp32 device map, C, h, w).
+
+    A channel-last view is used as it is (no copy, no transpose kernel); the reference's contiguous (C, h, w)
+    layout goes through mv_chw_to_hwc.  prenorm always runs the kernel (it rescales every pixel)."""
+    C, h, w = feat.shape
+    _check_C(C)
+    if _is_channel_last(feat) and not prenorm:
+        f = feat.detach().to(device=dev, non_blocking=True)
+        if _is_channel_last(f):
+            return f.permute(1, 2, 0).reshape(h * w, C), C, h, w
+    return _hwc(_f32(feat, dev), prenorm), C, h, w
+
+
 def _check_C(C):
     if C % 8 != 0:
         raise ValueError(f"feature dimension {C} must be a multiple of 8 for the tensor-core path")
@@ -338,9 +359,7 @@ def sample_pointcloud_features(feats, K, pc, image_shape):
     H, W = image_shape
     dev = _device()
     in_dev = feats.device
-    f = _f32(feats, dev)
-    C, h, w = f.shape
-    _check_C(C)
+    src, C, h, w = _feature_map(feats, dev)
     p = _f32(pc, dev)
     n = p.shape[0]
     Kh = L.host_floats(K.detach().float().cpu().reshape(-1).tolist())
@@ -349,7 +368,7 @@ def sample_pointcloud_features(feats, K, pc, image_shape):
     if n > 0:
         L.call("mv_geom_project_coords", L.ptr(p), None, None, n, Kh, int(H), int(W), h, w, L.ptr(xyz), L.ptr(coords),
                _stream())
-    _, o32 = _sample(L.MV_SAMPLE_BILINEAR_ZEROS, _hwc(f), C, h, w, coords, None, n, False, False, True)
+    _, o32 = _sample(L.MV_SAMPLE_BILINEAR_ZEROS, src, C, h, w, coords, None, n, False, False, True)
     return o32[:n].to(in_dev)
 
 
@@ -416,10 +435,11 @@ def _stage_depth(depth_dev, Kinv):
 
 
 def _finish_depth(f, d, K, staged, n, synced, want_taps=False):
-    """projection to feature-map coordinates + kernel 1 for the n (live or upper-bound) points of one image."""
+    """projection to feature-map coordinates + kernel 1 for the n (live or upper-bound) points of one image.
+    f: the (C, h, w) feature map in either layout (see _feature_map)."""
     xyz_all, valid_idx, n_dev = staged
-    dev = f.device
-    C, h, w = f.shape
+    dev = d.device
+    src, C, h, w = _feature_map(f, dev)
     H, W = d.shape[-2:]
     s = _Side()
     s.n_dev, s.valid_idx, s.n = n_dev, valid_idx, n
@@ -431,7 +451,7 @@ def _finish_depth(f, d, K, staged, n, synced, want_taps=False):
                L.ptr(coords), _stream())
     s.taps = _empty((max(n, 1), 2), torch.int32, dev) if want_taps else None
     s.uv = None
-    s.rows16, s.rows32 = _sample(L.MV_SAMPLE_BILINEAR_ZEROS, _hwc(f), C, h, w, coords, nd, n, True,
+    s.rows16, s.rows32 = _sample(L.MV_SAMPLE_BILINEAR_ZEROS, src, C, h, w, coords, nd, n, True,
                                  _CFG["dtype"] == "bf16", True, s.taps)
     return s
 
@@ -442,12 +462,11 @@ def prepare_depth_side(feat, depth, K, Kinv, dev, sync=True, want_taps=False):
     back-project depth -> keep z > 0 (row-major) -> project with K -> bilinear grid_sample coordinates
     (align_corners=False) -> kernel 1 (sample + L2 normalise).  sync=False keeps n on the device.
     """
-    f = _f32(feat, dev)
     d = _f32(depth, dev)
-    _check_C(f.shape[0])
+    _check_C(feat.shape[0])
     staged = _stage_depth(d, Kinv)
     n = int(staged[2].item()) if sync else d.shape[-2] * d.shape[-1]
-    return _finish_depth(f, d, K, staged, n, sync, want_taps)
+    return _finish_depth(feat, d, K, staged, n, sync, want_taps)
 
 
 def _stage_xyz(g):
@@ -461,8 +480,8 @@ def _stage_xyz(g):
 
 def _finish_xyz(f, g, staged, n, synced, want_taps=False):
     valid_idx, n_dev = staged
-    dev = f.device
-    C, h, w = f.shape
+    dev = g.device
+    src, C, h, w = _feature_map(f, dev)
     _, H, W = g.shape
     s = _Side()
     s.n_dev, s.valid_idx, s.n = n_dev, valid_idx, n
@@ -474,7 +493,7 @@ def _finish_xyz(f, g, staged, n, synced, want_taps=False):
         L.call("mv_geom_grid_coords", L.ptr(g), L.ptr(valid_idx), L.ptr(nd), n, H, W, h, w, L.ptr(s.xyz), L.ptr(s.uv),
                L.ptr(coords), _stream())
     s.taps = _empty((max(n, 1), 2), torch.int32, dev) if want_taps else None
-    s.rows16, s.rows32 = _sample(L.MV_SAMPLE_BICUBIC_CLAMP, _hwc(f), C, h, w, coords, nd, n, True,
+    s.rows16, s.rows32 = _sample(L.MV_SAMPLE_BICUBIC_CLAMP, src, C, h, w, coords, nd, n, True,
                                  _CFG["dtype"] == "bf16", True, s.taps)
     return s
 
@@ -485,12 +504,11 @@ def prepare_xyz_side(feat, xyz_grid, dev, sync=True, want_taps=False):
     bicubic upsample of feat to the xyz grid's size evaluated only at the pixels with xyz_grid[2] > 0
     (row-major), + their xyz and pixel-centre uv, + kernel 1's L2 normalisation.
     """
-    f = _f32(feat, dev)
     g = _f32(xyz_grid, dev)
-    _check_C(f.shape[0])
+    _check_C(feat.shape[0])
     staged = _stage_xyz(g)
     n = int(staged[1].item()) if sync else g.shape[-2] * g.shape[-1]
-    return _finish_xyz(f, g, staged, n, sync, want_taps)
+    return _finish_xyz(feat, g, staged, n, sync, want_taps)
 
 
 _SIDE_STREAMS = {}
@@ -527,6 +545,13 @@ def _join_side(side, dev, *objs):
         rec(o)
 
 
+def _upload_feat(feat, dev):
+    """feature map to the device as fp32, keeping a channel-last layout if it has one."""
+    if _is_channel_last(feat):
+        return feat.detach().to(device=dev, non_blocking=True)
+    return _f32(feat, dev)
+
+
 def _two_counts(a, b):
     """both live counts with a single device -> host read."""
     n0, n1 = torch.cat((a, b)).tolist()
@@ -559,14 +584,15 @@ def _graphed_helper(kind, feat_0, feat_1, grid_0, grid_1, num_corr, ratio_test, 
 
     ev = importlib.import_module(__package__ + ".evaluation")
     dev = _device()
+    layout = "hwc" if (_is_channel_last(feat_0) and _is_channel_last(feat_1)) else "chw"
     key = (kind, tuple(feat_0.shape), tuple(grid_0.shape), int(num_corr), bool(ratio_test), _CFG["dtype"], _CFG["cluster"],
-           None if K is None else tuple(K.detach().float().cpu().reshape(-1).tolist()), dev.index)
+           None if K is None else tuple(K.detach().float().cpu().reshape(-1).tolist()), dev.index, layout)
     gm = _HELPER_GRAPHS.get(key)
     if gm is None:
         if len(_HELPER_GRAPHS) >= _HELPER_GRAPHS_MAX:
             _HELPER_GRAPHS.pop(next(iter(_HELPER_GRAPHS)))
         gm = ev.GraphedPairMatcher(kind, tuple(feat_0.shape), tuple(grid_0.shape), num_corr, K=K, device=dev,
-                                   ratio_test=ratio_test, with_outputs=True).capture()
+                                   ratio_test=ratio_test, with_outputs=True, feat_layout=layout).capture()
         _HELPER_GRAPHS[key] = gm
     gm.load(feat_0, feat_1, grid_0, grid_1)
     gm.graph.replay()
@@ -602,8 +628,8 @@ def estimate_correspondence_depth(feat_0, feat_1, depth_0, depth_1, K, num_corr=
     n0, n1 = _two_counts(a0[2], a1[2])
     if n0 == 0 or n1 < 2:
         raise RuntimeError(f"too few valid points to match ({n0} vs {n1})")
-    f0 = _f32(feat_0, dev)
-    f1, side = _on_side_stream(lambda: _f32(feat_1, dev), dev)
+    f0 = _upload_feat(feat_0, dev)
+    f1, side = _on_side_stream(lambda: _upload_feat(feat_1, dev), dev)
     s0 = _finish_depth(f0, d0, Kh, a0, n0, True)
     with torch.cuda.stream(side):
         s1 = _finish_depth(f1, d1, Kh, a1, n1, True)
@@ -625,8 +651,8 @@ def estimate_correspondence_xyz(feat_0, feat_1, xyz_grid_0, xyz_grid_1, num_corr
     n0, n1 = _two_counts(a0[1], a1[1])
     if n0 == 0 or n1 < 2:
         raise RuntimeError(f"too few valid points to match ({n0} vs {n1})")
-    f0 = _f32(feat_0, dev)
-    f1, side = _on_side_stream(lambda: _f32(feat_1, dev), dev)
+    f0 = _upload_feat(feat_0, dev)
+    f1, side = _on_side_stream(lambda: _upload_feat(feat_1, dev), dev)
     s0 = _finish_xyz(f0, g0, a0, n0, True)
     with torch.cuda.stream(side):
         s1 = _finish_xyz(f1, g1, a1, n1, True)

@@ -69,6 +69,43 @@ __global__ void chw_to_hwc_kernel(const float* __restrict__ src, float* __restri
   }
 }
 
+// The same transpose with 128-bit accesses on both sides (hw % 4 == 0, C % 4 == 0): a CTA moves a tile of
+// 64 channels x 64 pixels; 16 lanes read one channel's 256 contiguous bytes, 16 lanes write one pixel's.
+__global__ void __launch_bounds__(256) chw_to_hwc_vec_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                             int C, int hw, const float* __restrict__ norm) {
+  __shared__ float tile[64][65];  // [channel][pixel]
+  const int p0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const int q = threadIdx.x & 15, r = threadIdx.x >> 4;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = c0 + r + 16 * k, p = p0 + 4 * q;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C && p < hw) v = __ldg(reinterpret_cast<const float4*>(src + (size_t)c * hw + p));
+    float* t = &tile[r + 16 * k][4 * q];
+    t[0] = v.x;
+    t[1] = v.y;
+    t[2] = v.z;
+    t[3] = v.w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int p = p0 + r + 16 * k, c = c0 + 4 * q;
+    if (p < hw && c < C) {
+      float4 v = make_float4(tile[4 * q][r + 16 * k], tile[4 * q + 1][r + 16 * k], tile[4 * q + 2][r + 16 * k],
+                             tile[4 * q + 3][r + 16 * k]);
+      if (norm) {
+        const float d = fmaxf(__ldg(norm + p), K1_NORM_EPS);
+        v.x = __fdiv_rn(v.x, d);
+        v.y = __fdiv_rn(v.y, d);
+        v.z = __fdiv_rn(v.z, d);
+        v.w = __fdiv_rn(v.w, d);
+      }
+      *reinterpret_cast<float4*>(dst + (size_t)p * C + c) = v;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // stable compaction (single CTA; n <= 2^20)
 // ------------------------------------------------------------------------------------------
@@ -510,8 +547,16 @@ int mv_chw_to_hwc(const float* src_chw, float* dst_hwc, int C, int hw, int preno
     pixel_norm_kernel<<<(hw + 31) / 32, dim3(32, 8), 0, st>>>(src_chw, norm_scratch, C, hw);
     MV_LAUNCH_CHECK();
   }
-  dim3 grid((hw + 31) / 32, (C + 31) / 32);
-  chw_to_hwc_kernel<<<grid, dim3(32, 8), 0, st>>>(src_chw, dst_hwc, C, hw, prenorm ? norm_scratch : nullptr);
+  const float* norm = prenorm ? norm_scratch : nullptr;
+  const bool vec = (hw % 4 == 0) && (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(src_chw) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(dst_hwc) & 15) == 0);
+  if (vec) {
+    dim3 grid((hw + 63) / 64, (C + 63) / 64);
+    chw_to_hwc_vec_kernel<<<grid, 256, 0, st>>>(src_chw, dst_hwc, C, hw, norm);
+  } else {
+    dim3 grid((hw + 31) / 32, (C + 31) / 32);
+    chw_to_hwc_kernel<<<grid, dim3(32, 8), 0, st>>>(src_chw, dst_hwc, C, hw, norm);
+  }
   MV_LAUNCH_CHECK();
   return MV_OK;
 }

@@ -172,16 +172,28 @@ class GraphedPairMatcher:
     kind = "depth" ScanNet-shaped: feats (C, h, w) x2 + depth (1, H, W) x2 + K (fixed for the matcher)
     """
 
-    def __init__(self, kind, feat_shape, grid_shape, num_corr, K=None, device=None, ratio_test=True, with_outputs=False):
+    def __init__(self, kind, feat_shape, grid_shape, num_corr, K=None, device=None, ratio_test=True, with_outputs=False,
+                 feat_layout="chw"):
+        """feat_layout: memory layout of the static feature buffers -- "chw" (the reference's contiguous
+        (C, h, w)) or "hwc" (channel-last views, the layout ViT tokens / channels_last CNN outputs already have:
+        loading such features is a flat copy and the transpose kernel is skipped)."""
         if kind not in ("xyz", "depth"):
             raise ValueError(kind)
+        if feat_layout not in ("chw", "hwc"):
+            raise ValueError(feat_layout)
+        self.feat_layout = feat_layout
         C_._check_C(feat_shape[0])
         self.kind, self.num_corr = kind, int(num_corr)
         self.ratio_test, self.with_outputs = bool(ratio_test), bool(with_outputs)
         self.packed = self.counts = self.host_packed = self.host_counts = None
         self.dev = device or C_._device()
-        self.f0 = torch.zeros(feat_shape, dtype=torch.float32, device=self.dev)
-        self.f1 = torch.zeros(feat_shape, dtype=torch.float32, device=self.dev)
+        if feat_layout == "hwc":
+            C, h, w = feat_shape
+            self.f0 = torch.zeros((h, w, C), dtype=torch.float32, device=self.dev).permute(2, 0, 1)
+            self.f1 = torch.zeros((h, w, C), dtype=torch.float32, device=self.dev).permute(2, 0, 1)
+        else:
+            self.f0 = torch.zeros(feat_shape, dtype=torch.float32, device=self.dev)
+            self.f1 = torch.zeros(feat_shape, dtype=torch.float32, device=self.dev)
         self.g0 = torch.zeros(grid_shape, dtype=torch.float32, device=self.dev)
         self.g1 = torch.zeros(grid_shape, dtype=torch.float32, device=self.dev)
         if kind == "depth":
@@ -248,7 +260,7 @@ class GraphedPairMatcher:
     @property
     def launches_per_replay(self):
         # per image: (backproject) + compact + coords + chw_to_hwc + kernel 1; per pair: kernel 2 (2) + ratio + top-k
-        per_side = 5 if self.kind == "depth" else 4
+        per_side = (5 if self.kind == "depth" else 4) - (1 if self.feat_layout == "hwc" else 0)
         gathers = (4 if self.kind == "xyz" else 2) if self.with_outputs else 0
         return 2 * per_side + 4 + gathers
 
@@ -264,13 +276,14 @@ class PairPipeline:
         pipe.join()
     """
 
-    def __init__(self, kind, feat_shape, grid_shape, num_corr, K=None, device=None, lanes=2):
+    def __init__(self, kind, feat_shape, grid_shape, num_corr, K=None, device=None, lanes=2, feat_layout="chw"):
         self.dev = device or C_._device()
         self.lanes = []
         for _ in range(max(1, int(lanes))):
             st = torch.cuda.Stream(device=self.dev)
             with torch.cuda.stream(st):
-                gm = GraphedPairMatcher(kind, feat_shape, grid_shape, num_corr, K=K, device=self.dev).capture()
+                gm = GraphedPairMatcher(kind, feat_shape, grid_shape, num_corr, K=K, device=self.dev,
+                                        feat_layout=feat_layout).capture()
             self.lanes.append((st, gm))
         torch.cuda.synchronize(self.dev)
         self.turn = 0

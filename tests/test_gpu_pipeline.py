@@ -259,3 +259,36 @@ def test_edge_cases_of_the_helpers(mv, syn):
     assert (out[2] - ref[2]).abs().max() < 2e-2
     with pytest.raises(ValueError):
         C_.estimate_correspondence_xyz(torch.zeros(7, 4, 4), torch.zeros(7, 4, 4), p["xyz_grid_0"], p["xyz_grid_1"], 10)
+
+
+def test_channel_last_features_take_the_zero_copy_path(mv, syn):
+    """a (C, h, w) view of channel-last memory (ViT tokens before tokens_to_output's .contiguous()) gives the same
+    results as the reference's contiguous layout, through the eager helper, the cached-graph helper and the
+    pipeline's static buffers."""
+    C_, ev = mv.correspondence, mv.evaluation
+    p = syn.navi_pair(11, C=256, h=12, w=12, H=48, W=48, radius=18.0)
+    cl = lambda t: t.permute(1, 2, 0).contiguous().permute(2, 0, 1)
+    assert C_._is_channel_last(cl(p["feat_0"])) and not C_._is_channel_last(p["feat_0"])
+    for graphs in (0, 1):
+        C_.set_match_precision(helper_graphs=graphs)
+        try:
+            a = C_.estimate_correspondence_xyz(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], 200)
+            b = C_.estimate_correspondence_xyz(cl(p["feat_0"]), cl(p["feat_1"]), p["xyz_grid_0"], p["xyz_grid_1"], 200)
+        finally:
+            C_.set_match_precision(helper_graphs=1)
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    d = syn.scannet_pair(12, C=64, h=6, w=8, H=24, W=32)
+    a = C_.estimate_correspondence_depth(d["feat_0"].cuda(), d["feat_1"].cuda(), d["depth_0"].cuda(), d["depth_1"].cuda(), d["K"], 100)
+    b = C_.estimate_correspondence_depth(cl(d["feat_0"]).cuda(), cl(d["feat_1"]).cuda(), d["depth_0"].cuda(), d["depth_1"].cuda(), d["K"], 100)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    accs = []
+    for layout in ("chw", "hwc"):
+        acc = ev.RecallAccumulator([0.01, 0.02], [5, 25], device=torch.device("cuda"))
+        gm = ev.GraphedPairMatcher("xyz", tuple(p["feat_0"].shape), tuple(p["xyz_grid_0"].shape), 200, feat_layout=layout).capture()
+        f0, f1 = (cl(p["feat_0"]), cl(p["feat_1"])) if layout == "hwc" else (p["feat_0"], p["feat_1"])
+        gm.load(f0.cuda(), f1.cuda(), p["xyz_grid_0"].cuda(), p["xyz_grid_1"].cuda())
+        gm.run(acc, p["Rt"], p["intrinsics"])
+        accs.append(acc.hits.cpu())
+    assert torch.equal(accs[0], accs[1]) and int(accs[0][0]) == 200
