@@ -182,6 +182,19 @@ int mv_k3_spair_errors(const int32_t* pred_flat, int K, int w, const float* kps_
                        float* error_same, float* error_nn, int32_t* index_nn, unsigned long long* hits,
                        unsigned long long* confusion, int conf_dim, mv_stream_t stream);
 
+/* SPair matching for a BATCH of pairs in one launch (evaluate_spair_correspondence.py:59-103 for every pair of
+ * the loop at :108): feats (B, 2, C, h, w) = the backbone output for (image_i, image_j) of each pair, fp32,
+ * contiguous; kps_i / kps_j (B, K, kp_stride) = (x, y, valid, ...) in image pixels; thresh_scale (B) on the
+ * device.  Per pair: per-pixel L2 normalisation (:59), bilinear key-point gather with align_corners=True
+ * (:71-79), K x (h*w) heat map and its arg-max (:82-83) -- all fp32, the heat map never leaves registers --
+ * then the scoring of mv_k3_spair_errors.  Outputs (each optional): pred_flat (B, K) int32 flat arg-max pixel,
+ * error_same / error_nn (B, K; -1 where the key point is not in both images), index_nn (B, K); hits[0..1] and
+ * confusion accumulate as in mv_k3_spair_errors.  K <= 64. */
+int mv_spair_match_batch(const float* feats, int B, int C, int h, int w, const float* kps_i, const float* kps_j, int K,
+                         int kp_stride, const float* thresh_scale, float image_size, float pck_thresh,
+                         int32_t* pred_flat, float* error_same, float* error_nn, int32_t* index_nn,
+                         unsigned long long* hits, unsigned long long* confusion, int conf_dim, mv_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -34,6 +34,8 @@ PROTOTYPES = {
     "mv_gather_rows": (c_int, [P, c_int, P, P, c_int, P, P]),
     "mv_argmax_rows": (c_int, [P, c_int, c_int, c_int, P, P]),
     "mv_k3_spair_errors": (c_int, [P, c_int, c_int, P, P, c_int, c_float, c_float, c_float, P, P, P, P, P, P, c_int, P]),
+    "mv_spair_match_batch": (c_int, [P, c_int, c_int, c_int, c_int, P, P, c_int, c_int, P, c_float, c_float, P, P, P, P, P, P,
+                                     c_int, P]),
 }
 
 # enums of include/mvmatch.h
@@ -52,7 +54,7 @@ KERNELS_PER_CALL = {
     "mv_chw_to_hwc": 1, "mv_compact_valid": 1, "mv_geom_backproject": 1, "mv_geom_project_coords": 1,
     "mv_geom_grid_coords": 1, "mv_geom_keypoint_coords": 1, "mv_k1_sample_normalize": 1, "mv_k2_sim_top2": 2,
     "mv_k2_unpack_col": 1, "mv_k3_ratio_mutual": 1, "mv_k3_topk_matches": 1, "mv_k3_score": 1, "mv_gather_rows": 1,
-    "mv_argmax_rows": 1, "mv_k3_spair_errors": 1,
+    "mv_argmax_rows": 1, "mv_k3_spair_errors": 1, "mv_spair_match_batch": 1,
 }
 LAUNCHES = {"count": 0}
 

@@ -19,6 +19,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "spair_score.cuh"
 
 namespace {
 
@@ -358,43 +359,9 @@ __global__ void __launch_bounds__(256) k3_spair_kernel(const int32_t* __restrict
                                                        float* __restrict__ error_nn, int32_t* __restrict__ index_nn,
                                                        unsigned long long* __restrict__ hits,
                                                        unsigned long long* __restrict__ confusion, int conf_dim) {
-  __shared__ float err[64][65];
-  __shared__ unsigned int cnt[2];
-  if (threadIdx.x < 2) cnt[threadIdx.x] = 0;
-  for (int t = threadIdx.x; t < K * K; t += blockDim.x) {
-    const int k = t / K, l = t - k * K;
-    const int flat = pred_flat[k];
-    // argmax_2d -> (col, row); both divided by feats.shape[-1]  (spair:83)
-    const float px = __fdiv_rn((float)(flat % w), (float)w), py = __fdiv_rn((float)(flat / w), (float)w);
-    const float jx = __fdiv_rn(kps_j[(size_t)l * stride], image_size), jy = __fdiv_rn(kps_j[(size_t)l * stride + 1], image_size);
-    const float dx = px - jx, dy = py - jy;
-    float e = __fdiv_rn(sqrtf(fmaf(dy, dy, dx * dx)), thresh_scale);
-    const bool valid = (kps_i[(size_t)k * stride + 2] * kps_j[(size_t)l * stride + 2]) == 1.f;
-    if (!valid) e = 1e3f;
-    err[k][l] = e;
-    if (errors) errors[t] = e;
-  }
-  __syncthreads();
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
-    const bool in_both = (kps_i[(size_t)k * stride + 2] * kps_j[(size_t)k * stride + 2]) == 1.f;
-    float es = -1.f, en = -1.f;
-    int in = -1;
-    if (in_both) {
-      es = err[k][k];
-      en = err[k][0];
-      in = 0;
-      for (int l = 1; l < K; ++l)
-        if (err[k][l] < en) { en = err[k][l]; in = l; }
-      atomicAdd(&cnt[0], 1u);
-      if (es < pck) atomicAdd(&cnt[1], 1u);
-      if (confusion) atomicAdd(&confusion[(size_t)k * conf_dim + in], 1ull);
-    }
-    if (error_same) error_same[k] = es;
-    if (error_nn) error_nn[k] = en;
-    if (index_nn) index_nn[k] = in;
-  }
-  __syncthreads();
-  if (hits && threadIdx.x < 2 && cnt[threadIdx.x]) atomicAdd(&hits[threadIdx.x], (unsigned long long)cnt[threadIdx.x]);
+  __shared__ SpairScoreShared sh;
+  spair_score_block(sh, pred_flat, K, w, kps_i, kps_j, stride, image_size, thresh_scale, pck, errors, error_same,
+                    error_nn, index_nn, hits, confusion, conf_dim);
 }
 
 }  // namespace

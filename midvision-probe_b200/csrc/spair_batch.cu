@@ -1,0 +1,291 @@
+// spair_batch.cu -- SPair-71k keypoint transfer for a BATCH of image pairs in one launch.
+//
+//   mv_spair_match_batch   per pair: bilinear key-point features of the normalised map, K x (h*w) heat map with
+//                          the per-pixel normalisation folded in, arg-max, key-point error matrix, PCK counts
+//                          -- one CTA per pair, fp32 throughout
+//
+// Reference behaviour being reproduced (file:line in /root/reference):
+//   evaluate_spair_correspondence.py:59     feats = F.normalize(feats, p=2, dim=1)
+//   evaluate_spair_correspondence.py:71-79  key points / image size -> NDC -> grid_sample(bilinear, align_corners=True)
+//   evaluate_spair_correspondence.py:82-83  heatmaps = einsum("k f, f h w -> k h w"); argmax_2d(...) / w
+//   evaluate_spair_correspondence.py:86-98  error matrix, validity, error_same / error_nn        (spair_score.cuh)
+//   evaluate_spair_correspondence.py:108, :115-121  loop over pairs, confusion matrix, recall
+//
+// Why a separate kernel: one pair is 2 * K * h*w * C = 6 MFLOP (K = 20, 14 x 14, C = 768) -- a 128-row
+// tensor-core tile would be 84 % padding and the ten launches of the per-pair path (kernels 1-3) are pure
+// launch latency.  Here each feature map is read once (1.2 MB per pair, the HBM floor) straight from the
+// backbone's (B, 2, C, h, w) output, the heat map lives in registers and nothing but K integers per pair is
+// written, so the path is bounded by HBM, not by launches.
+#include <math_constants.h>
+
+#include "common.cuh"
+#include "spair_score.cuh"
+
+namespace {
+
+constexpr int SPB_THREADS = 256;
+constexpr int SPB_MAX_HW = 1 << 20;  // pixels per feature map (2500 at the reference's 800 x 800 input)
+constexpr float SPB_NORM_EPS = 1e-12f;  // F.normalize default eps
+
+struct SpairBatchParams {
+  const float* feats;  // (B, 2, C, h, w)
+  const float* kps_i;  // (B, K, stride)
+  const float* kps_j;
+  const float* thresh_scale;  // (B)
+  int B, C, h, w, K, stride;
+  float image_size, pck;
+  int32_t* pred;  // (B, K)
+  float* error_same;
+  float* error_nn;
+  int32_t* index_nn;
+  unsigned long long* hits;
+  unsigned long long* confusion;
+  int conf_dim;
+};
+
+// dynamic shared memory: q[C][KT], the key-point features of the current tile
+template <int KT>
+__global__ void __launch_bounds__(SPB_THREADS) spair_batch_kernel(SpairBatchParams p) {
+  extern __shared__ float4 spb_dyn[];
+  __shared__ SpairScoreShared score;
+  __shared__ int s_pred[64];
+  __shared__ float s_wt[64][4];   // bilinear weight / max(||f_i[tap]||, eps); 0 for a tap outside the map (zero padding)
+  __shared__ int s_tap[64][4];    // pixel index of the tap (clamped into the map)
+  __shared__ float s_ss[64][4];   // sum of squares of f_i at the tap
+  __shared__ float s_bv[SPB_THREADS / 32][KT];
+  __shared__ int s_bi[SPB_THREADS / 32][KT];
+  const int C = p.C, hw = p.h * p.w, K = p.K;
+  float* q = reinterpret_cast<float*>(spb_dyn);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    const float* fi = p.feats + (size_t)b * 2 * C * hw;
+    const float* fj = fi + (size_t)C * hw;
+    const float* ki = p.kps_i + (size_t)b * K * p.stride;
+    const float* kj = p.kps_j + (size_t)b * K * p.stride;
+
+    // ---- key-point taps: kp / size * 2 - 1 -> ((g + 1) / 2) * (size - 1)  (align_corners=True) ----
+    if (tid < K) {
+      const float kx = __fdiv_rn(ki[(size_t)tid * p.stride + 0], p.image_size);
+      const float ky = __fdiv_rn(ki[(size_t)tid * p.stride + 1], p.image_size);
+      const float gx = __fsub_rn(__fmul_rn(kx, 2.f), 1.f), gy = __fsub_rn(__fmul_rn(ky, 2.f), 1.f);
+      const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(p.w - 1));
+      const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.f), 2.f), (float)(p.h - 1));
+      const float fx = floorf(ix), fy = floorf(iy);
+      const int x0 = (int)fx, y0 = (int)fy;
+      const float ww = ix - fx, we = 1.f - ww, wn = iy - fy, ws = 1.f - wn;
+      const float wt[4] = {ws * we, ws * ww, wn * we, wn * ww};  // nw, ne, sw, se
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
+        const bool in = xx >= 0 && xx < p.w && yy >= 0 && yy < p.h;
+        s_wt[tid][t] = in ? wt[t] : 0.f;
+        s_tap[tid][t] = min(max(yy, 0), p.h - 1) * p.w + min(max(xx, 0), p.w - 1);
+        s_ss[tid][t] = 0.f;
+      }
+    }
+    __syncthreads();
+    // ---- ||f_i|| at the 4K tap pixels only: (tap, channel slice) per thread, 16 independent loads in flight ----
+    {
+      const int ntap = 4 * K;
+      const int slices = max(1, SPB_THREADS / ntap);
+      for (int item = tid; item < ntap * slices; item += SPB_THREADS) {
+        const int tp = item % ntap, sl = item / ntap;
+        const float* src = fi + s_tap[tp >> 2][tp & 3];
+        float ss = 0.f;
+#pragma unroll 16
+        for (int c = sl; c < C; c += slices) {
+          const float v = __ldg(src + (size_t)c * hw);
+          ss = fmaf(v, v, ss);
+        }
+        atomicAdd(&s_ss[tp >> 2][tp & 3], ss);
+      }
+    }
+    __syncthreads();
+    if (tid < 4 * K) {  // fold 1 / max(||f_i[tap]||, eps) into the blend weight
+      const int k = tid >> 2, t = tid & 3;
+      s_wt[k][t] = __fdiv_rn(s_wt[k][t], fmaxf(sqrtf(s_ss[k][t]), SPB_NORM_EPS));
+    }
+    __syncthreads();
+
+    for (int k0 = 0; k0 < K; k0 += KT) {
+      const int kt = min(KT, K - k0);
+      // ---- q[c][k] = sum_t wt * f_i[c][tap] / max(||f_i[tap]||, eps): the grid_sample of the normalised map ----
+#pragma unroll 4
+      for (int idx = tid; idx < C * KT; idx += SPB_THREADS) {
+        const int c = idx / KT, k = idx - c * KT;
+        const int kk = k0 + min(k, kt - 1);
+        const float* src = fi + (size_t)c * hw;
+        float acc = __ldg(src + s_tap[kk][0]) * s_wt[kk][0];
+        acc = fmaf(__ldg(src + s_tap[kk][1]), s_wt[kk][1], acc);
+        acc = fmaf(__ldg(src + s_tap[kk][2]), s_wt[kk][2], acc);
+        acc = fmaf(__ldg(src + s_tap[kk][3]), s_wt[kk][3], acc);
+        q[idx] = (k < kt) ? acc : 0.f;
+      }
+      __syncthreads();
+
+      // ---- heat[k][px] = (sum_c q[c][k] * f_j[c][px]) / max(||f_j[px]||, eps), f_j read ONCE: the norm is
+      //      accumulated in the same pass; running arg-max per thread ----
+      float bestv[KT];
+      int besti[KT];
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        bestv[k] = -CUDART_INF_F;
+        besti[k] = 0x7fffffff;
+      }
+      for (int px = tid; px < hw; px += SPB_THREADS) {
+        float acc[KT];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) acc[k] = 0.f;
+        float ss = 0.f;
+        const float* col = fj + px;
+        int c0 = 0;
+        for (; c0 + 16 <= C; c0 += 16) {
+          float v[16];
+#pragma unroll
+          for (int u = 0; u < 16; ++u) v[u] = __ldg(col + (size_t)(c0 + u) * hw);  // 16 loads in flight
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            ss = fmaf(v[u], v[u], ss);
+            const float4* qc = reinterpret_cast<const float4*>(q + (size_t)(c0 + u) * KT);
+#pragma unroll
+            for (int k4 = 0; k4 < KT / 4; ++k4) {
+              const float4 qq = qc[k4];  // same address in every lane: broadcast
+              acc[4 * k4 + 0] = fmaf(qq.x, v[u], acc[4 * k4 + 0]);
+              acc[4 * k4 + 1] = fmaf(qq.y, v[u], acc[4 * k4 + 1]);
+              acc[4 * k4 + 2] = fmaf(qq.z, v[u], acc[4 * k4 + 2]);
+              acc[4 * k4 + 3] = fmaf(qq.w, v[u], acc[4 * k4 + 3]);
+            }
+          }
+        }
+        for (; c0 < C; ++c0) {
+          const float v = __ldg(col + (size_t)c0 * hw);
+          ss = fmaf(v, v, ss);
+#pragma unroll
+          for (int k = 0; k < KT; ++k) acc[k] = fmaf(q[(size_t)c0 * KT + k], v, acc[k]);
+        }
+        const float nrm = fmaxf(sqrtf(ss), SPB_NORM_EPS);
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          const float hv = __fdiv_rn(acc[k], nrm);
+          if (hv > bestv[k]) {  // pixels are visited in ascending order: the first maximum wins
+            bestv[k] = hv;
+            besti[k] = px;
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        float v = bestv[k];
+        int i = besti[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+          if (ov > v || (ov == v && oi < i)) {
+            v = ov;
+            i = oi;
+          }
+        }
+        if (lane == 0) {
+          s_bv[wid][k] = v;
+          s_bi[wid][k] = i;
+        }
+      }
+      __syncthreads();
+      if (tid < kt) {
+        float v = s_bv[0][tid];
+        int i = s_bi[0][tid];
+        for (int wq = 1; wq < SPB_THREADS / 32; ++wq) {
+          const float ov = s_bv[wq][tid];
+          const int oi = s_bi[wq][tid];
+          if (ov > v || (ov == v && oi < i)) {
+            v = ov;
+            i = oi;
+          }
+        }
+        i = (i == 0x7fffffff) ? 0 : i;  // an all-NaN heat map: torch.argmax would return a NaN position; we return 0
+        s_pred[k0 + tid] = i;
+        if (p.pred) p.pred[(size_t)b * K + k0 + tid] = i;
+      }
+      __syncthreads();  // q, s_bv are rewritten by the next tile
+    }
+
+    spair_score_block(score, s_pred, K, p.w, ki, kj, p.stride, p.image_size, __ldg(p.thresh_scale + b), p.pck, nullptr,
+                      p.error_same ? p.error_same + (size_t)b * K : nullptr,
+                      p.error_nn ? p.error_nn + (size_t)b * K : nullptr,
+                      p.index_nn ? p.index_nn + (size_t)b * K : nullptr, p.hits, p.confusion, p.conf_dim);
+  }
+}
+
+template <int KT>
+int launch_spair_batch(const SpairBatchParams& p, cudaStream_t st) {
+  const size_t smem = (size_t)p.C * KT * sizeof(float);
+  auto kern = spair_batch_kernel<KT>;
+  static size_t opted_in = 24 << 10;  // static + dynamic shared memory above 48 KB needs the opt-in
+  if (smem > opted_in) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      mv_set_error("mv_spair_match_batch: cannot opt in to %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+      return (int)e;
+    }
+    opted_in = smem;
+  }
+  int per_sm = (int)((200u << 10) / (smem + (24u << 10)));  // static shared memory of the kernel is ~21 KB
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 4) per_sm = 4;
+  int grid = mv_sm_count() * per_sm;
+  if (grid > p.B) grid = p.B;
+  kern<<<grid, SPB_THREADS, smem, st>>>(p);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mv_spair_match_batch(const float* feats, int B, int C, int h, int w, const float* kps_i, const float* kps_j, int K,
+                         int kp_stride, const float* thresh_scale, float image_size, float pck_thresh,
+                         int32_t* pred_flat, float* error_same, float* error_nn, int32_t* index_nn,
+                         unsigned long long* hits, unsigned long long* confusion, int conf_dim, mv_stream_t stream) {
+  MV_REQUIRE(B >= 0 && C > 0 && h > 0 && w > 0, MV_E_ARG, "mv_spair_match_batch: bad sizes");
+  MV_REQUIRE((B == 0 || K == 0) || (feats && kps_i && kps_j && thresh_scale), MV_E_ARG,
+             "mv_spair_match_batch: null pointer");
+  MV_REQUIRE(h * w <= SPB_MAX_HW, MV_E_RANGE, "mv_spair_match_batch: h*w=%d exceeds %d pixels", h * w, SPB_MAX_HW);
+  MV_REQUIRE(K >= 0 && K <= 64, MV_E_RANGE, "mv_spair_match_batch: K=%d must be in [0, 64]", K);
+  MV_REQUIRE(kp_stride >= 3 && image_size > 0.f, MV_E_ARG, "mv_spair_match_batch: bad key-point layout");
+  MV_REQUIRE(!confusion || conf_dim >= K, MV_E_ARG, "mv_spair_match_batch: conf_dim=%d must be >= K=%d", conf_dim, K);
+  if (B == 0 || K == 0) return MV_OK;
+  SpairBatchParams p;
+  p.feats = feats;
+  p.kps_i = kps_i;
+  p.kps_j = kps_j;
+  p.thresh_scale = thresh_scale;
+  p.B = B;
+  p.C = C;
+  p.h = h;
+  p.w = w;
+  p.K = K;
+  p.stride = kp_stride;
+  p.image_size = image_size;
+  p.pck = pck_thresh;
+  p.pred = pred_flat;
+  p.error_same = error_same;
+  p.error_nn = error_nn;
+  p.index_nn = index_nn;
+  p.hits = hits;
+  p.confusion = confusion;
+  p.conf_dim = conf_dim;
+  cudaStream_t st = mv_cuda_stream(stream);
+  // key-point tile = accumulators per thread; the tile's features (C * KT floats) must fit shared memory
+  const size_t budget = 160u << 10;
+  const size_t per_k = (size_t)C * sizeof(float);
+  MV_REQUIRE(8 * per_k <= budget, MV_E_RANGE, "mv_spair_match_batch: C=%d too large for the key-point tile", C);
+  if (K > 24 && 32 * per_k <= budget) return launch_spair_batch<32>(p, st);
+  if (K > 16 && 24 * per_k <= budget) return launch_spair_batch<24>(p, st);
+  if (K > 8 && 16 * per_k <= budget) return launch_spair_batch<16>(p, st);
+  return launch_spair_batch<8>(p, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,59 @@
+// spair_score.cuh -- SPair keypoint scoring shared by mv_k3_spair_errors (one pair) and mv_spair_match_batch.
+//
+// evaluate_spair_correspondence.py:83-98, :115-121: pred = arg-max pixel of each key point's heat map ->
+// (col, row) / w; errors (K, K) = ||pred_k - kps_j[l, :2] / image_size|| / thresh_scale, 1e3 where
+// kps_i[k, 2] * kps_j[l, 2] != 1; error_same = diagonal, (error_nn, index_nn) = row minimum, both only for the
+// key points present in both images; PCK counts and the confusion matrix as integer counters.
+#pragma once
+#include <stdint.h>
+
+struct SpairScoreShared {
+  float err[64][65];
+  unsigned int cnt[2];
+};
+
+// One CTA, any block size; K <= 64.  pred_flat may point to shared or global memory.  Ends with a barrier.
+__device__ __forceinline__ void spair_score_block(SpairScoreShared& sh, const int32_t* pred_flat, int K, int w,
+                                                  const float* __restrict__ kps_i, const float* __restrict__ kps_j,
+                                                  int stride, float image_size, float thresh_scale, float pck,
+                                                  float* __restrict__ errors, float* __restrict__ error_same,
+                                                  float* __restrict__ error_nn, int32_t* __restrict__ index_nn,
+                                                  unsigned long long* __restrict__ hits,
+                                                  unsigned long long* __restrict__ confusion, int conf_dim) {
+  if (threadIdx.x < 2) sh.cnt[threadIdx.x] = 0;
+  for (int t = threadIdx.x; t < K * K; t += blockDim.x) {
+    const int k = t / K, l = t - k * K;
+    const int flat = pred_flat[k];
+    // argmax_2d -> (col, row); both divided by feats.shape[-1]  (spair:83)
+    const float px = __fdiv_rn((float)(flat % w), (float)w), py = __fdiv_rn((float)(flat / w), (float)w);
+    const float jx = __fdiv_rn(kps_j[(size_t)l * stride], image_size), jy = __fdiv_rn(kps_j[(size_t)l * stride + 1], image_size);
+    const float dx = px - jx, dy = py - jy;
+    float e = __fdiv_rn(sqrtf(fmaf(dy, dy, dx * dx)), thresh_scale);
+    const bool valid = (kps_i[(size_t)k * stride + 2] * kps_j[(size_t)l * stride + 2]) == 1.f;
+    if (!valid) e = 1e3f;
+    sh.err[k][l] = e;
+    if (errors) errors[t] = e;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const bool in_both = (kps_i[(size_t)k * stride + 2] * kps_j[(size_t)k * stride + 2]) == 1.f;
+    float es = -1.f, en = -1.f;
+    int in = -1;
+    if (in_both) {
+      es = sh.err[k][k];
+      en = sh.err[k][0];
+      in = 0;
+      for (int l = 1; l < K; ++l)
+        if (sh.err[k][l] < en) { en = sh.err[k][l]; in = l; }
+      atomicAdd(&sh.cnt[0], 1u);
+      if (es < pck) atomicAdd(&sh.cnt[1], 1u);
+      if (confusion) atomicAdd(&confusion[(size_t)k * conf_dim + in], 1ull);
+    }
+    if (error_same) error_same[k] = es;
+    if (error_nn) error_nn[k] = en;
+    if (index_nn) index_nn[k] = in;
+  }
+  __syncthreads();
+  if (hits && threadIdx.x < 2 && sh.cnt[threadIdx.x]) atomicAdd(&hits[threadIdx.x], (unsigned long long)sh.cnt[threadIdx.x]);
+  __syncthreads();
+}

@@ -13,7 +13,7 @@ import torch
 from . import _lib as L
 from . import correspondence as C_
 
-__all__ = ["compute_errors_from_features", "evaluate_pairs", "pck_recall"]
+__all__ = ["compute_errors_from_features", "compute_errors_batch", "evaluate_pairs", "evaluate_batches", "pck_recall"]
 
 
 def compute_errors_from_features(feats, kps_i, kps_j, thresh_scale, image_size, pck_thresh=0.10, hits=None,
@@ -60,6 +60,54 @@ def compute_errors_from_features(feats, kps_i, kps_j, thresh_scale, image_size, 
     if return_heatmap_argmax:
         return out + (pred.long().to(in_dev),)
     return out
+
+
+def compute_errors_batch(feats, kps_i, kps_j, thresh_scale, image_size, pck_thresh=0.10, hits=None, confusion=None):
+    """compute_errors (evaluate_spair_correspondence.py:45-103) for a whole batch of pairs in ONE launch.
+
+    feats: (B, 2, C, h, w) backbone output of the B pairs (image_i, image_j); kps_i / kps_j: (B, K, 3);
+    thresh_scale: (B,) tensor or sequence.  Returns device tensors (error_same, error_nn, index_nn, pred), each
+    (B, K): entries of key points that are not in both images are -1 (the reference drops them, :96-98);
+    pred is the flat arg-max pixel of each heat map (:83).  hits / confusion accumulate like
+    compute_errors_from_features.  Everything is fp32 on the device (mv_spair_match_batch); nothing syncs.
+    """
+    dev = C_._device()
+    st = C_._stream()
+    f = C_._f32(feats, dev)
+    B, two, C, h, w = f.shape
+    if two != 2:
+        raise ValueError("feats must be (B, 2, C, h, w)")
+    ki = C_._f32(kps_i, dev)
+    kj = C_._f32(kps_j, dev)
+    K = ki.shape[1]
+    if K > 64:
+        raise ValueError("at most 64 keypoint slots")
+    if ki.shape != kj.shape or ki.shape[0] != B or ki.shape[2] < 3:
+        raise ValueError("kps_i / kps_j must both be (B, K, >= 3)")
+    ts = C_._f32(torch.as_tensor(thresh_scale, dtype=torch.float32).reshape(-1), dev)
+    if ts.numel() != B:
+        raise ValueError("thresh_scale needs one entry per pair")
+    pred = torch.empty((B, K), dtype=torch.int32, device=dev)
+    err_same = torch.empty((B, K), dtype=torch.float32, device=dev)
+    err_nn = torch.empty((B, K), dtype=torch.float32, device=dev)
+    idx_nn = torch.empty((B, K), dtype=torch.int32, device=dev)
+    L.call("mv_spair_match_batch", L.ptr(f), B, C, h, w, L.ptr(ki), L.ptr(kj), K, ki.shape[2], L.ptr(ts),
+           c_float(float(image_size)), c_float(float(pck_thresh)), L.ptr(pred), L.ptr(err_same), L.ptr(err_nn),
+           L.ptr(idx_nn), L.ptr(hits), L.ptr(confusion), 0 if confusion is None else confusion.shape[1], st)
+    return err_same, err_nn, idx_nn, pred
+
+
+def evaluate_batches(batches, pck_thresh=0.10, kp_max=30):
+    """(recall, confusion) over an iterable of dicts with keys feats (B, 2, C, h, w), kps_i, kps_j (B, K, 3),
+    thresh_scale (B), image_size: evaluate_dataset (evaluate_spair_correspondence.py:106-123) with one launch per
+    batch of pairs and integer counts; a single device -> host read at the end."""
+    dev = C_._device()
+    hits = torch.zeros(2, dtype=torch.int64, device=dev)
+    conf = torch.zeros((kp_max, kp_max), dtype=torch.int64, device=dev)
+    for b in batches:
+        compute_errors_batch(b["feats"], b["kps_i"], b["kps_j"], b["thresh_scale"], b["image_size"],
+                             pck_thresh=pck_thresh, hits=hits, confusion=conf)
+    return pck_recall(hits), conf.cpu()
 
 
 def evaluate_pairs(pairs, pck_thresh=0.10, kp_max=None):

@@ -212,3 +212,81 @@ def test_angle_binned_recall(mv, syn):
     for a, b in zip(got, want):
         assert (a != a and b != b) or abs(a - 100.0 * float(b)) < 1e-3
     torch.testing.assert_close(tr.so3_rotation_angle(Rt[None, :3, :3]), tr.so3_relative_angle(Rt[None, :3, :3], torch.eye(3)[None]))
+
+
+@pytest.mark.parametrize("shape,B", [(dict(C=768, h=14, w=14, K=20, image_size=224), 7), (dict(C=64, h=50, w=50, K=30, image_size=800), 3),
+                                     (dict(C=40, h=5, w=7, K=3, image_size=64), 4), (dict(C=3072, h=14, w=14, K=9, image_size=224), 2)])
+def test_spair_batch_equals_oracle_per_pair(mv, syn, shape, B):
+    """mv_spair_match_batch (one launch for B pairs, fp32) against the oracle pair by pair: arg-max identical
+    wherever the oracle's top-2 heat-map gap exceeds 1e-5 (fp32 summation order only), errors to 1e-5, the
+    key points kept (in both images) bit-exact, integer PCK counts and confusion equal to the oracle's."""
+    pairs = [syn.spair_pair(20 + i, **shape) for i in range(B)]
+    K = shape["K"]
+    hits = torch.zeros(2, dtype=torch.int64, device="cuda")
+    conf = torch.zeros((K, K), dtype=torch.int64, device="cuda")
+    es, en, inn, pred = mv.spair.compute_errors_batch(
+        torch.stack([p["feats"] for p in pairs]), torch.stack([p["kps_i"] for p in pairs]), torch.stack([p["kps_j"] for p in pairs]),
+        [p["thresh_scale"] for p in pairs], shape["image_size"], hits=hits, confusion=conf)
+    es, en, inn, pred = es.cpu(), en.cpu(), inn.cpu().long(), pred.cpu().long()
+    n_both = n_hit = 0
+    want_conf = torch.zeros((K, K), dtype=torch.int64)
+    unclear = 0
+    for b, p in enumerate(pairs):
+        oes, oen, oisame, oinn, heat = restated.spair_compute_errors(p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"],
+                                                                     p["image_size"], return_pred=True)
+        flat = heat.flatten(1)
+        top2 = torch.topk(flat, 2, dim=1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 1e-5
+        unclear += int((~clear).sum())
+        assert torch.equal(pred[b][clear], flat.argmax(1)[clear])
+        kept = (es[b] >= 0).nonzero().squeeze(1)
+        assert torch.equal(kept, oisame)                                  # which key points are in both: bit-exact
+        assert torch.equal((en[b] >= 0), (es[b] >= 0)) and torch.equal((inn[b] >= 0), (es[b] >= 0))
+        ok = clear[oisame]
+        torch.testing.assert_close(es[b][oisame][ok], oes[ok], rtol=0, atol=1e-5)
+        if bool(clear.all()):
+            torch.testing.assert_close(en[b][oisame], oen, rtol=0, atol=1e-5)
+            assert torch.equal(inn[b][oisame], oinn)
+            for a_, b_ in zip(oisame.tolist(), oinn.tolist()):
+                want_conf[a_, b_] += 1
+        else:
+            for a_, b_ in zip(oisame.tolist(), inn[b][oisame].tolist()):
+                want_conf[a_, b_] += 1
+        n_both += oisame.numel()
+        n_hit += int((es[b][oisame] < 0.10).sum())
+    assert unclear <= B  # the tolerance set is almost everything
+    assert hits.cpu().tolist() == [n_both, n_hit]
+    assert torch.equal(conf.cpu(), want_conf)
+
+
+def test_spair_batch_equals_per_pair_path_and_edge_cases(mv, syn):
+    """the batched launch and the per-pair path (kernels 1-3, tf32) agree; B = 0, K = 0 and a pair without any
+    common key point are handled; evaluate_batches == evaluate_pairs."""
+    sp = mv.spair
+    pairs = [syn.spair_pair(40 + i) for i in range(5)]
+    pairs[2]["kps_j"][:, 2] = 0.0  # nothing in both images
+    feats = torch.stack([p["feats"] for p in pairs])
+    ki, kj = torch.stack([p["kps_i"] for p in pairs]), torch.stack([p["kps_j"] for p in pairs])
+    ts = [p["thresh_scale"] for p in pairs]
+    es, en, inn, pred = sp.compute_errors_batch(feats, ki, kj, ts, 224)
+    assert bool((es[2] == -1).all()) and bool((inn[2] == -1).all())
+    mv.correspondence.set_match_precision(dtype="tf32")
+    try:
+        for b, p in enumerate(pairs):
+            a = sp.compute_errors_from_features(p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"], 224, return_heatmap_argmax=True)
+            same = a[4].cpu() == pred[b].cpu().long()
+            assert same.float().mean() >= 0.9            # tf32 ranking vs fp32: only near-ties may differ
+            keep = (es[b] >= 0).nonzero().squeeze(1).cpu()
+            assert torch.equal(a[2], keep)
+        r1, c1 = sp.evaluate_pairs(pairs, kp_max=30)
+    finally:
+        mv.correspondence.set_match_precision(dtype="bf16")
+    r2, c2 = sp.evaluate_batches([dict(feats=feats, kps_i=ki, kps_j=kj, thresh_scale=ts, image_size=224)], kp_max=30)
+    assert int(c1.sum()) == int(c2.sum()) and (c1 - c2).abs().sum() <= 4 and abs(r1 - r2) <= 100.0 * 2 / max(int(c1.sum()), 1) + 1e-6
+    # degenerate sizes
+    e = sp.compute_errors_batch(feats[:0], ki[:0], kj[:0], [], 224)
+    assert e[0].shape == (0, 20)
+    e = sp.compute_errors_batch(feats, ki[:, :0], kj[:, :0], ts, 224)
+    assert e[0].shape == (5, 0)
+    with pytest.raises(ValueError):
+        sp.compute_errors_batch(feats[0], ki, kj, ts, 224)
