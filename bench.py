@@ -114,7 +114,9 @@ def workload_name(workload):
     return {"navi": "NAVI-shaped dense correspondence, ViT-B/16 @448 4-block concat (3072, 28, 28) -> 112x112 xyz grid, "
                     "num_corr 1000 (BASELINE.json configs[1])",
             "scannet": "ScanNet-shaped, ResNet-50 layer4 (2048, 15, 20) -> 120x160 depth, 19200x19200 similarity, "
-                       "num_corr 1000 (BASELINE.json configs[2])"}[workload]
+                       "num_corr 1000 (BASELINE.json configs[2])",
+            "spair": "SPair-shaped pairs: (2, 768, 14, 14) features, 20 key points, fused batched matching "
+                     "(BASELINE.json configs[0])"}[workload]
 
 
 def cpu_pairs_per_s(syn, workload, budget_s=12.0, max_pairs=6):
@@ -142,6 +144,113 @@ def cpu_pairs_per_s(syn, workload, budget_s=12.0, max_pairs=6):
     return done / t_total, done, torch.get_num_threads()
 
 
+SPAIR_BATCH = 512  # pairs per step (one launch); 1.2 MB of features per pair -> 617 MB per step, far beyond L2
+
+
+def run_spair(args, rank, local_rank, world):
+    """--workload spair (BASELINE.json configs[0]): SPair-shaped pairs, (2, 768, 14, 14) features + 20 key points,
+    a step = SPAIR_BATCH pairs through spair.compute_errors_batch (one fused launch).  HBM-bound: the roofline
+    figure is the feature bytes read per launch."""
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = torch.distributed
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    mv = importlib.import_module("midvision-probe_b200")
+    syn = importlib.import_module("midvision-probe_b200.synthetic")
+    sp, L = mv.spair, mv._lib
+    hbm_peak, _, _, peak_kind = peaks()
+    base = [syn.spair_pair(rank + world * i) for i in range(32)]
+    B = SPAIR_BATCH
+    pick = lambda key: torch.stack([torch.as_tensor(base[i % 32][key]) for i in range(B)])
+    host = {"feats": pick("feats").pin_memory(), "kps_i": pick("kps_i").pin_memory(), "kps_j": pick("kps_j").pin_memory(),
+            "ts": pick("thresh_scale").float().pin_memory()}
+    d = {k: v.to(dev) for k, v in host.items()}
+    hits = torch.zeros(2, dtype=torch.int64, device=dev)
+
+    def step(src):
+        return sp.compute_errors_batch(src["feats"], src["kps_i"], src["kps_j"], src["ts"], 224, hits=hits)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(d)
+    barrier()
+    hits.zero_()
+    L.LAUNCHES["count"] = 0
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(d)
+    if world > 1:
+        dist.all_reduce(hits, op=dist.ReduceOp.SUM)  # the path's only collective: PCK counts
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = L.LAUNCHES["count"]
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * args.steps * B / (ms_total * 1e-3)
+    h = hits.tolist()
+    # end to end: pinned host tensors in, the four (B, K) result tensors back on the host, every step
+    for _ in range(2):
+        out = step(host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = [o.cpu() for o in step(host)]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e = world * args.steps * B / float(t.item())
+    if rank == 0:
+        byts = d["feats"].numel() * 4
+        per_launch_ms = ms_total / args.steps
+        line = {
+            "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": per_launch_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "SPair-shaped pairs: (2, 768, 14, 14) features, 20 key points, fused batched matching "
+                                   "(BASELINE.json configs[0])", "pairs_per_step": B,
+                       "l2": "inputs larger than L2: 617 MB of features per step", "features": "seeded maps of the backbone's output shape"},
+            "clocks": clocks,
+            "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()),
+                    "d2h_bytes_per_step": sum(o.numel() * o.element_size() for o in out), "steps": args.steps,
+                    "api": "spair.compute_errors_batch(host tensors)"},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": byts / (per_launch_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": byts / (per_launch_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_kind": f"{peak_kind} copy bandwidth",
+                         "kernel": "spair_batch_kernel (one launch per step; algorithmic bytes = the (B, 2, C, h, w) features, read once)",
+                         "avg_ms": per_launch_ms, "bytes_per_launch": byts},
+            "recall": {"keypoints_in_both": h[0], "pck_0.10": 100.0 * h[1] / max(h[0], 1)},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import restated
+
+            torch.set_num_threads(os.cpu_count() or 1)
+            n, t0 = 0, time.perf_counter()
+            while time.perf_counter() - t0 < 10.0:
+                p = base[n % 32]
+                restated.spair_compute_errors(p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"], p["image_size"])
+                n += 1
+            line["cpu_baseline"] = {"value": n / (time.perf_counter() - t0), "unit": "pairs/s", "cores": torch.get_num_threads(),
+                                    "kind": "port", "sample": f"{n} pairs through oracle/restated.py spair_compute_errors (fp32 torch on the CPU)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation of the path (oracle port), all host threads, on
     the same workload; each step is a bounded sample (2 pairs) so the run ends within minutes."""
@@ -153,7 +262,9 @@ def run_reference(args, rank):
     from oracle import restated
 
     def one(p):
-        if args.workload == "navi":
+        if args.workload == "spair":
+            restated.spair_compute_errors(p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"], p["image_size"])
+        elif args.workload == "navi":
             out = restated.estimate_correspondence_xyz(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], NUM_CORR)
             restated.pair_errors(out[0], out[1], p["Rt"], p["intrinsics"])
         else:
@@ -162,7 +273,9 @@ def run_reference(args, rank):
 
     warm = min(args.warmup, 2)
     steps = min(args.steps, 10)
-    gen = syn.navi_pair if args.workload == "navi" else syn.scannet_pair
+    gen = {"navi": syn.navi_pair, "scannet": syn.scannet_pair, "spair": syn.spair_pair}[args.workload]
+    if args.workload == "spair":
+        per_step = 64
     pairs = [gen(i) for i in range(min(POOL, max(warm, steps * per_step)))]  # inputs exist before the clock starts
     for w in range(warm):
         one(pairs[w % len(pairs)])
@@ -191,7 +304,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="navi", choices=["navi", "scannet"])
+    ap.add_argument("--workload", default="navi", choices=["navi", "scannet", "spair"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "tf32"])
     ap.add_argument("--cluster", type=int, default=int(os.environ.get("MVMATCH_CLUSTER", "-1")),
                     help="kernel 2 cluster mode: -1 auto, 1 single CTA, 2 / 4 B-tile multicast, 20 CTA pair (cta_group::2)")
@@ -211,6 +324,9 @@ def main():
         run_reference(args, rank)
         return
     args.warmup = max(args.warmup, 3)
+    if args.workload == "spair":
+        run_spair(args, rank, local_rank, world)
+        return
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path)"
     torch.cuda.set_device(local_rank)

@@ -288,8 +288,8 @@ def get_correspondences_ratio_test(P1_F, P2_F, num_corres, metric="cosine", bidi
     budget in each direction, concatenated.
     """
     assert metric in ["cosine", "euclidean"]
-    if metric != "cosine":
-        raise NotImplementedError("only the cosine metric (every reference call site) runs on the B200 path")
+    if metric == "euclidean":
+        return _ratio_test_euclidean(P1_F, P2_F, num_corres, bidirectional, ratio_test)
     dev = _device()
     in_dev = P1_F.device
     A16, A32 = _rows_from_features(P1_F, True, dev)
@@ -305,6 +305,21 @@ def get_correspondences_ratio_test(P1_F, P2_F, num_corres, metric="cosine", bidi
     idx2 = torch.cat((r12.sel_dst[:r12.k], r21.sel_src[:r21.k])).long()
     w = torch.cat((r12.sel_weight[:r12.k], r21.sel_weight[:r21.k]))
     return idx1.to(in_dev), idx2.to(in_dev), w.to(in_dev)
+
+
+def _ratio_test_euclidean(P1_F, P2_F, num_corres, bidirectional, ratio_test):
+    """the metric="euclidean" branch (no call site in the reference; correspondence.py:70-102 followed literally):
+    exact L2 2-NN (knn_points) -> ratio weights -> top-k through the library's selection kernel."""
+    def one_way(X, Y, k):
+        d, idx = knn_points(X, Y, 2, "euclidean")
+        w = calculate_ratio_test(d) if ratio_test else d[:, 0]
+        return get_topk_matches(w, idx[:, 0], k)
+
+    if not bidirectional:
+        return one_way(P1_F, P2_F, num_corres)
+    a1, a2, aw = one_way(P1_F, P2_F, num_corres // 2)
+    b2, b1, bw = one_way(P2_F, P1_F, num_corres // 2)
+    return torch.cat((a1, b1)), torch.cat((a2, b2)), torch.cat((aw, bw))
 
 
 def calculate_ratio_test(dists):

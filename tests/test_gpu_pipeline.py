@@ -114,6 +114,24 @@ def test_faiss_knn_and_euclidean(mv):
     assert torch.equal(ie[clear, 0], oi[clear, 0])
 
 
+def test_ratio_test_euclidean_metric(mv):
+    """metric="euclidean" of get_correspondences_ratio_test (correspondence.py:63-102; no call site in the
+    reference, kept for interface parity) against the oracle's literal restatement."""
+    gen = torch.Generator().manual_seed(21)
+    X = torch.randn(300, 48, generator=gen) * 2
+    Y = X[torch.randperm(300, generator=gen)][:260] + 0.3 * torch.randn(260, 48, generator=gen)
+    i1, i2, w = mv.correspondence.get_correspondences_ratio_test(X, Y, 50, metric="euclidean")
+    od, oi = restated.knn_points(X, Y, 2, "euclidean")
+    ow = 1 - od[:, 0].clamp(min=1e-9) / od[:, 1].clamp(min=1e-9)
+    wt, it = torch.topk(ow, 50)
+    assert i1.dtype == torch.int64 and w.shape == (50,)
+    assert set(i1.tolist()) == set(it.tolist())
+    torch.testing.assert_close(w, wt, rtol=1e-4, atol=1e-5)
+    assert torch.equal(i2, oi[i1, 0])
+    j1, j2, jw = mv.correspondence.get_correspondences_ratio_test(X, Y, 40, metric="euclidean", bidirectional=True, ratio_test=False)
+    assert j1.shape == (40,) and j2.shape == (40,) and jw.shape == (40,)
+
+
 def full_size_case(mv, kind, dtype, syn):
     C_ = mv.correspondence
     if kind == "scannet":
