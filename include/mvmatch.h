@@ -105,10 +105,13 @@ int mv_geom_keypoint_coords(const float* kps, int kp_stride, int n, float image_
 /* For point p < n: row = sample(src, coords[p]) (4-tap bilinear with zero padding, 16-tap Keys
  * cubic A=-0.75 with border clamp, or row p of src itself); if normalize: row /= max(||row||,1e-12)
  * (F.normalize, correspondence.py:47-48).  Writes bf16 and/or fp32 rows.  C % 8 == 0, C <= 8192.
+ * out_bf16_lo (optional, needs out_bf16): the SPLIT form of the fp32 row -- bf16(row - float(out_bf16)), so that
+ * out_bf16 + out_bf16_lo reproduces the fp32 row to 2^-17 relative in 4 bytes per element instead of the 6 of
+ * bf16 + fp32 (kernel 1 is bound by its row writes); consumed by mv_k3_ratio_mutual_split.
  * taps (optional, (n,2) int32): the (x0, y0) = floor(ix), floor(iy) tap origin, for parity tests. */
 int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, const float* coords,
-                           const int32_t* n_dev, int n_max, int normalize, uint16_t* out_bf16, float* out_f32,
-                           int32_t* taps, mv_stream_t stream);
+                           const int32_t* n_dev, int n_max, int normalize, uint16_t* out_bf16, uint16_t* out_bf16_lo,
+                           float* out_f32, int32_t* taps, mv_stream_t stream);
 
 /* ---- kernel 2: similarity GEMM with fused row top-2 / column arg-max (tensor-core bound) -- */
 /* S = A @ B^T (n x m, never written).  Replaces faiss GpuIndexFlatL2.search(k<=2)
@@ -136,6 +139,11 @@ int mv_k2_unpack_col(const unsigned long long* col_best, int m, float* col_val, 
 int mv_k3_ratio_mutual(const float* A32, const float* B32, int C, const int32_t* n_dev, int n_max,
                        int32_t* row_idx, const unsigned long long* col_best, int ratio_test, float* dists,
                        float* weight, uint8_t* mutual, mv_stream_t stream);
+/* The same on SPLIT rows (mv_k1_sample_normalize's out_bf16 / out_bf16_lo planes): every element is rebuilt
+ * as float(hi) + float(lo) (exact in fp32) before the identical fp32 arithmetic.  C % 8 == 0. */
+int mv_k3_ratio_mutual_split(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* B_hi, const uint16_t* B_lo, int C,
+                             const int32_t* n_dev, int n_max, int32_t* row_idx, const unsigned long long* col_best,
+                             int ratio_test, float* dists, float* weight, uint8_t* mutual, mv_stream_t stream);
 
 /* get_topk_matches (correspondence.py:125-129): the k = min(num_corr, n) largest weights, sorted
  * descending (ties: lower row first).  sel_* have num_corr entries; k_dev receives k.

@@ -34,6 +34,9 @@ _CFG = {
     "cluster": int(os.environ.get("MVMATCH_CLUSTER", "-1")),  # -1 = let the library choose (MV_CLUSTER_AUTO)
     # host-tensor calls of the two dense helpers replay a CUDA graph cached per input shape (0 = launch eagerly)
     "helper_graphs": int(os.environ.get("MVMATCH_HELPER_GRAPHS", "1")),
+    # how kernel 1 hands the fp32 rows to kernel 3 on the bf16 path: "split" = bf16 hi + bf16 residual planes
+    # (4 bytes / element, hi doubles as kernel 2's operand), "f32" = bf16 + fp32 rows (6 bytes / element)
+    "rows": os.environ.get("MVMATCH_ROWS", "split"),
 }
 _HELPER_GRAPHS = {}  # (kind, shapes, num_corr, ratio_test, dtype, cluster, K bytes) -> evaluation.GraphedPairMatcher
 _HELPER_GRAPHS_MAX = 8
@@ -43,9 +46,14 @@ _HELPER_GRAPHS_MAX = 8
 _PROFILE = {}
 
 
-def set_match_precision(dtype=None, cluster=None, helper_graphs=None):
-    """Choose kernel 2's operand type ("bf16" | "tf32"), its cluster width (1, 2 or 4) and whether the dense
-    helpers replay cached CUDA graphs for host-tensor calls."""
+def set_match_precision(dtype=None, cluster=None, helper_graphs=None, rows=None):
+    """Choose kernel 2's operand type ("bf16" | "tf32"), its cluster width (1, 2 or 4), whether the dense
+    helpers replay cached CUDA graphs for host-tensor calls, and the row format between kernels 1 and 3
+    ("split" | "f32", see _CFG)."""
+    if rows is not None:
+        if rows not in ("split", "f32"):
+            raise ValueError("rows must be 'split' or 'f32'")
+        _CFG["rows"] = rows
     if helper_graphs is not None:
         _CFG["helper_graphs"] = int(bool(helper_graphs))
     if dtype is not None:
@@ -115,15 +123,26 @@ def _check_C(C):
         raise ValueError(f"feature dimension {C} must be a multiple of 8 for the tensor-core path")
 
 
-def _sample(mode, src, C, h, w, coords, n_dev, n_max, normalize, want_bf16, want_f32, taps=None):
-    """kernel 1.  src: (h*w, C) channel-last (or (n, C) rows for MV_SAMPLE_ROWS)."""
+def _sample(mode, src, C, h, w, coords, n_dev, n_max, normalize, want_bf16, want_f32, taps=None, want_lo=False):
+    """kernel 1.  src: (h*w, C) channel-last (or (n, C) rows for MV_SAMPLE_ROWS).
+    Returns (bf16 rows, fp32 rows, bf16 residual rows); the ones not asked for are None."""
     dev = src.device
-    o16 = _empty((max(n_max, 1), C), torch.bfloat16, dev) if want_bf16 else None
+    o16 = _empty((max(n_max, 1), C), torch.bfloat16, dev) if (want_bf16 or want_lo) else None
+    olo = _empty((max(n_max, 1), C), torch.bfloat16, dev) if want_lo else None
     o32 = _empty((max(n_max, 1), C), torch.float32, dev) if want_f32 else None
     if n_max > 0:
         L.call("mv_k1_sample_normalize", mode, L.ptr(src), C, h, w, L.ptr(coords), L.ptr(n_dev), n_max, int(normalize),
-               L.ptr(o16), L.ptr(o32), L.ptr(taps), _stream())
-    return o16, o32
+               L.ptr(o16), L.ptr(olo), L.ptr(o32), L.ptr(taps), _stream())
+    return o16, o32, olo
+
+
+def _row_format(rows=None):
+    """(want_bf16, want_f32, want_lo) of kernel 1 for the configured kernel-2 operand type and row format."""
+    if _CFG["dtype"] != "bf16":
+        return False, True, False
+    if (rows or _CFG["rows"]) == "split":
+        return True, False, True
+    return True, True, False
 
 
 class MatchResult:
@@ -132,17 +151,23 @@ class MatchResult:
     __slots__ = ("k", "k_dev", "sel_src", "sel_dst", "sel_weight", "mutual", "row_idx", "dists", "weight", "col_best")
 
 
-def match_rows(A16, A32, B16, B32, n, m, num_corr, ratio_test=True, n_dev=None, m_dev=None, want_topk=True, run_k3=True):
+def match_rows(A16, A32, B16, B32, n, m, num_corr, ratio_test=True, n_dev=None, m_dev=None, want_topk=True, run_k3=True,
+               A_lo=None, B_lo=None):
     """kernel 2 + kernel 3 on prepared rows.
 
-    A16/B16: (n, C)/(m, C) bf16 rows (None when the tf32 path is selected), A32/B32: fp32 rows.
+    A16/B16: (n, C)/(m, C) bf16 rows (None when the tf32 path is selected), A32/B32: fp32 rows -- or None
+    when the split form is used: A_lo/B_lo are then the bf16 residual planes of A16/B16.
     Mirrors get_correspondences_ratio_test (correspondence.py:63-102, bidirectional=False):
     2-NN -> fp32 cosine distances -> ratio weights -> top-num_corr, plus the mutual-NN flag.
     n, m are the live counts when n_dev/m_dev are None, otherwise upper bounds.
     """
-    dev = A32.device
-    C = A32.shape[1]
+    ref = A32 if A32 is not None else A16
+    dev = ref.device
+    C = ref.shape[1]
     tf32 = _CFG["dtype"] == "tf32"
+    split = A32 is None or B32 is None
+    if split and (tf32 or A_lo is None or B_lo is None or A16 is None or B16 is None):
+        raise ValueError("split rows need the bf16 path and both residual planes")
     st = _stream()
     res = MatchResult()
     row_val = _empty((n, 2), torch.float32, dev)
@@ -169,8 +194,12 @@ def match_rows(A16, A32, B16, B32, n, m, num_corr, ratio_test=True, n_dev=None, 
     dists = _empty((n, 2), torch.float32, dev)
     weight = _empty((n,), torch.float32, dev)
     mutual = _empty((n,), torch.uint8, dev)
-    L.call("mv_k3_ratio_mutual", L.ptr(A32), L.ptr(B32), C, L.ptr(n_dev), n, L.ptr(row_idx), L.ptr(col_best),
-           int(ratio_test), L.ptr(dists), L.ptr(weight), L.ptr(mutual), st)
+    if split:
+        L.call("mv_k3_ratio_mutual_split", L.ptr(A16), L.ptr(A_lo), L.ptr(B16), L.ptr(B_lo), C, L.ptr(n_dev), n,
+               L.ptr(row_idx), L.ptr(col_best), int(ratio_test), L.ptr(dists), L.ptr(weight), L.ptr(mutual), st)
+    else:
+        L.call("mv_k3_ratio_mutual", L.ptr(A32), L.ptr(B32), C, L.ptr(n_dev), n, L.ptr(row_idx), L.ptr(col_best),
+               int(ratio_test), L.ptr(dists), L.ptr(weight), L.ptr(mutual), st)
     res.row_idx, res.dists, res.weight, res.mutual, res.col_best = row_idx, dists, weight, mutual, col_best
     if want_topk:
         k = min(int(num_corr), n)
@@ -202,7 +231,7 @@ def _rows_from_features(F, normalize, dev):
     want16 = _CFG["dtype"] == "bf16"
     if not normalize and not want16:
         return None, F
-    return _sample(L.MV_SAMPLE_ROWS, F, C, 0, 0, None, None, n, normalize, want16, True)
+    return _sample(L.MV_SAMPLE_ROWS, F, C, 0, 0, None, None, n, normalize, want16, True)[:2]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -383,7 +412,7 @@ def sample_pointcloud_features(feats, K, pc, image_shape):
     if n > 0:
         L.call("mv_geom_project_coords", L.ptr(p), None, None, n, Kh, int(H), int(W), h, w, L.ptr(xyz), L.ptr(coords),
                _stream())
-    _, o32 = _sample(L.MV_SAMPLE_BILINEAR_ZEROS, src, C, h, w, coords, None, n, False, False, True)
+    o32 = _sample(L.MV_SAMPLE_BILINEAR_ZEROS, src, C, h, w, coords, None, n, False, False, True)[1]
     return o32[:n].to(in_dev)
 
 
@@ -433,7 +462,12 @@ def compute_binned_performance(y, x, x_bins):
 class _Side:
     """One image of a pair after kernel 1: compacted geometry + feature rows."""
 
-    __slots__ = ("n", "n_dev", "xyz", "uv", "rows16", "rows32", "valid_idx", "taps")
+    __slots__ = ("n", "n_dev", "xyz", "uv", "rows16", "rows32", "rows_lo", "valid_idx", "taps")
+
+
+def _match_sides(s0, s1, n0, n1, num_corr, ratio_test=True, n_dev=None, m_dev=None):
+    return match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, n0, n1, num_corr, ratio_test, n_dev=n_dev, m_dev=m_dev,
+                      A_lo=s0.rows_lo, B_lo=s1.rows_lo)
 
 
 def _stage_depth(depth_dev, Kinv):
@@ -449,7 +483,7 @@ def _stage_depth(depth_dev, Kinv):
     return xyz_all, valid_idx, n_dev
 
 
-def _finish_depth(f, d, K, staged, n, synced, want_taps=False):
+def _finish_depth(f, d, K, staged, n, synced, want_taps=False, rows=None):
     """projection to feature-map coordinates + kernel 1 for the n (live or upper-bound) points of one image.
     f: the (C, h, w) feature map in either layout (see _feature_map)."""
     xyz_all, valid_idx, n_dev = staged
@@ -466,12 +500,13 @@ def _finish_depth(f, d, K, staged, n, synced, want_taps=False):
                L.ptr(coords), _stream())
     s.taps = _empty((max(n, 1), 2), torch.int32, dev) if want_taps else None
     s.uv = None
-    s.rows16, s.rows32 = _sample(L.MV_SAMPLE_BILINEAR_ZEROS, src, C, h, w, coords, nd, n, True,
-                                 _CFG["dtype"] == "bf16", True, s.taps)
+    w16, w32, wlo = _row_format(rows)
+    s.rows16, s.rows32, s.rows_lo = _sample(L.MV_SAMPLE_BILINEAR_ZEROS, src, C, h, w, coords, nd, n, True, w16, w32,
+                                            s.taps, wlo)
     return s
 
 
-def prepare_depth_side(feat, depth, K, Kinv, dev, sync=True, want_taps=False):
+def prepare_depth_side(feat, depth, K, Kinv, dev, sync=True, want_taps=False, rows=None):
     """ScanNet-style preparation of one image.  correspondence.py:219-225, :147-176, :47-48.
 
     back-project depth -> keep z > 0 (row-major) -> project with K -> bilinear grid_sample coordinates
@@ -481,7 +516,7 @@ def prepare_depth_side(feat, depth, K, Kinv, dev, sync=True, want_taps=False):
     _check_C(feat.shape[0])
     staged = _stage_depth(d, Kinv)
     n = int(staged[2].item()) if sync else d.shape[-2] * d.shape[-1]
-    return _finish_depth(feat, d, K, staged, n, sync, want_taps)
+    return _finish_depth(feat, d, K, staged, n, sync, want_taps, rows)
 
 
 def _stage_xyz(g):
@@ -493,7 +528,7 @@ def _stage_xyz(g):
     return valid_idx, n_dev
 
 
-def _finish_xyz(f, g, staged, n, synced, want_taps=False):
+def _finish_xyz(f, g, staged, n, synced, want_taps=False, rows=None):
     valid_idx, n_dev = staged
     dev = g.device
     src, C, h, w = _feature_map(f, dev)
@@ -508,12 +543,13 @@ def _finish_xyz(f, g, staged, n, synced, want_taps=False):
         L.call("mv_geom_grid_coords", L.ptr(g), L.ptr(valid_idx), L.ptr(nd), n, H, W, h, w, L.ptr(s.xyz), L.ptr(s.uv),
                L.ptr(coords), _stream())
     s.taps = _empty((max(n, 1), 2), torch.int32, dev) if want_taps else None
-    s.rows16, s.rows32 = _sample(L.MV_SAMPLE_BICUBIC_CLAMP, src, C, h, w, coords, nd, n, True,
-                                 _CFG["dtype"] == "bf16", True, s.taps)
+    w16, w32, wlo = _row_format(rows)
+    s.rows16, s.rows32, s.rows_lo = _sample(L.MV_SAMPLE_BICUBIC_CLAMP, src, C, h, w, coords, nd, n, True, w16, w32,
+                                            s.taps, wlo)
     return s
 
 
-def prepare_xyz_side(feat, xyz_grid, dev, sync=True, want_taps=False):
+def prepare_xyz_side(feat, xyz_grid, dev, sync=True, want_taps=False, rows=None):
     """NAVI-style preparation of one image.  correspondence.py:240-252, :47-48.
 
     bicubic upsample of feat to the xyz grid's size evaluated only at the pixels with xyz_grid[2] > 0
@@ -523,7 +559,7 @@ def prepare_xyz_side(feat, xyz_grid, dev, sync=True, want_taps=False):
     _check_C(feat.shape[0])
     staged = _stage_xyz(g)
     n = int(staged[1].item()) if sync else g.shape[-2] * g.shape[-1]
-    return _finish_xyz(feat, g, staged, n, sync, want_taps)
+    return _finish_xyz(feat, g, staged, n, sync, want_taps, rows)
 
 
 _SIDE_STREAMS = {}
@@ -600,7 +636,7 @@ def _graphed_helper(kind, feat_0, feat_1, grid_0, grid_1, num_corr, ratio_test, 
     ev = importlib.import_module(__package__ + ".evaluation")
     dev = _device()
     layout = "hwc" if (_is_channel_last(feat_0) and _is_channel_last(feat_1)) else "chw"
-    key = (kind, tuple(feat_0.shape), tuple(grid_0.shape), int(num_corr), bool(ratio_test), _CFG["dtype"], _CFG["cluster"],
+    key = (kind, tuple(feat_0.shape), tuple(grid_0.shape), int(num_corr), bool(ratio_test), _CFG["dtype"], _CFG["cluster"], _CFG["rows"],
            None if K is None else tuple(K.detach().float().cpu().reshape(-1).tolist()), dev.index, layout)
     gm = _HELPER_GRAPHS.get(key)
     if gm is None:
@@ -649,7 +685,7 @@ def estimate_correspondence_depth(feat_0, feat_1, depth_0, depth_1, K, num_corr=
     with torch.cuda.stream(side):
         s1 = _finish_depth(f1, d1, Kh, a1, n1, True)
     _join_side(side, dev, f1, s1)
-    r = match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, n0, n1, num_corr)
+    r = _match_sides(s0, s1, n0, n1, num_corr)
     k = r.k
     return _return_packed([_gather(s0.xyz, r.sel_src, k), _gather(s1.xyz, r.sel_dst, k), r.sel_weight[:k]], in_dev)
 
@@ -672,7 +708,7 @@ def estimate_correspondence_xyz(feat_0, feat_1, xyz_grid_0, xyz_grid_1, num_corr
     with torch.cuda.stream(side):
         s1 = _finish_xyz(f1, g1, a1, n1, True)
     _join_side(side, dev, f1, s1)
-    r = match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, n0, n1, num_corr, ratio_test)
+    r = _match_sides(s0, s1, n0, n1, num_corr, ratio_test)
     k = r.k
     return _return_packed([_gather(s0.xyz, r.sel_src, k), _gather(s1.xyz, r.sel_dst, k), r.sel_weight[:k],
                            _gather(s0.uv, r.sel_src, k), _gather(s1.uv, r.sel_dst, k)], in_dev)

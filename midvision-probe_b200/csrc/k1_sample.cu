@@ -242,6 +242,7 @@ struct K1Params {
   const int32_t* n_dev;
   int n_max, C, h, w, normalize;
   __nv_bfloat16* out_bf16;
+  __nv_bfloat16* out_lo;  // bf16(row - float(bf16(row))): with out_bf16 a 16-bit-mantissa copy of the fp32 row in 4 bytes
   float* out_f32;
   int32_t* taps;
 };
@@ -282,7 +283,8 @@ __device__ __forceinline__ void cubic_coeffs(float t, float c[4]) {
 // element and ran at 2.6 TB/s; this form runs at the write-bandwidth limit of the part).
 constexpr int K1W_PMAX = 32;                // points per sub-run: one warp inspects them with a ballot
 constexpr int K1W_SMEM_BUDGET = 108 << 10;  // window bytes per CTA: two CTAs per SM
-constexpr int K1W_OUT_BOTH = 0, K1W_OUT_F32 = 1, K1W_OUT_ANY = 2;  // which row outputs exist (ANY: checked at run time)
+// which row outputs exist: bf16 + fp32, fp32 only, bf16 + bf16 residual, or ANY (checked at run time)
+constexpr int K1W_OUT_BOTH = 0, K1W_OUT_F32 = 1, K1W_OUT_ANY = 2, K1W_OUT_SPLIT = 3;
 
 struct K1WShared {
   float wt[K1W_PMAX][4];
@@ -313,8 +315,9 @@ __global__ void __launch_bounds__(THREADS, 2) k1_warp_rows_kernel(K1Params p, in
   const int ppc = (n + (int)gridDim.x - 1) / (int)gridDim.x;  // from the LIVE count: no idle SMs for a small n
   const int pt_beg = min(blockIdx.x * ppc, n);
   const int pt_end = min(pt_beg + ppc, n);
-  const bool has32 = (OUTS != K1W_OUT_ANY) || p.out_f32 != nullptr;
-  const bool has16 = (OUTS == K1W_OUT_BOTH) || (OUTS == K1W_OUT_ANY && p.out_bf16 != nullptr);
+  const bool has32 = (OUTS == K1W_OUT_BOTH || OUTS == K1W_OUT_F32) || (OUTS == K1W_OUT_ANY && p.out_f32 != nullptr);
+  const bool has16 = (OUTS == K1W_OUT_BOTH || OUTS == K1W_OUT_SPLIT) || (OUTS == K1W_OUT_ANY && p.out_bf16 != nullptr);
+  const bool haslo = (OUTS == K1W_OUT_SPLIT) || (OUTS == K1W_OUT_ANY && p.out_lo != nullptr);
   const bool normalize = p.normalize != 0;
 
   auto put = [&](int pt, int c, float4 o, float inv) {
@@ -329,6 +332,13 @@ __global__ void __launch_bounds__(THREADS, 2) k1_warp_rows_kernel(K1Params p, in
       pk.x = *reinterpret_cast<uint32_t*>(&lo);
       pk.y = *reinterpret_cast<uint32_t*>(&hi);
       *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)pt * C + c) = pk;
+      if (haslo) {  // residual of the bf16 rounding, itself rounded to bf16: hi + lo carries 16 mantissa bits
+        const float2 l = __bfloat1622float2(lo), h = __bfloat1622float2(hi);
+        __nv_bfloat162 rl = __floats2bfloat162_rn(o.x - l.x, o.y - l.y), rh = __floats2bfloat162_rn(o.z - h.x, o.w - h.y);
+        pk.x = *reinterpret_cast<uint32_t*>(&rl);
+        pk.y = *reinterpret_cast<uint32_t*>(&rh);
+        *reinterpret_cast<uint2*>(p.out_lo + (size_t)pt * C + c) = pk;
+      }
     }
   };
   // value_at(c) -> un-normalised float4 of channels [c, c + 4)
@@ -513,12 +523,17 @@ int launch_k1_warp(const K1Params& p, cudaStream_t st) {
   int grid = mv_sm_count() * 2;
   if (grid > p.n_max) grid = p.n_max;
   if (grid < 1) grid = 1;
-  const int outs = (p.out_f32 && p.out_bf16) ? K1W_OUT_BOTH : (p.out_f32 ? K1W_OUT_F32 : K1W_OUT_ANY);
+  int outs = K1W_OUT_ANY;
+  if (p.out_f32 && p.out_bf16 && !p.out_lo) outs = K1W_OUT_BOTH;
+  else if (p.out_f32 && !p.out_bf16 && !p.out_lo) outs = K1W_OUT_F32;
+  else if (!p.out_f32 && p.out_bf16 && p.out_lo) outs = K1W_OUT_SPLIT;
 #define K1W_CASE(NIT, THREADS)                                                                                     \
   if (C == 128 * NIT && outs == K1W_OUT_BOTH)                                                                      \
     return launch_k1_warp_inst<MODE, NIT, K1W_OUT_BOTH, THREADS>(p, grid, smem, nslots, st);                       \
   if (C == 128 * NIT && outs == K1W_OUT_F32)                                                                       \
-    return launch_k1_warp_inst<MODE, NIT, K1W_OUT_F32, THREADS>(p, grid, smem, nslots, st);
+    return launch_k1_warp_inst<MODE, NIT, K1W_OUT_F32, THREADS>(p, grid, smem, nslots, st);                        \
+  if (C == 128 * NIT && outs == K1W_OUT_SPLIT)                                                                     \
+    return launch_k1_warp_inst<MODE, NIT, K1W_OUT_SPLIT, THREADS>(p, grid, smem, nslots, st);
   K1W_CASE(6, 256)   // ViT-B   768
   K1W_CASE(8, 256)   // ViT-L   1024
   K1W_CASE(16, 256)  // ResNet-50 layer4 2048
@@ -617,7 +632,7 @@ int mv_geom_keypoint_coords(const float* kps, int kp_stride, int n, float image_
 }
 
 int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, const float* coords,
-                           const int32_t* n_dev, int n_max, int normalize, uint16_t* out_bf16, float* out_f32,
+                           const int32_t* n_dev, int n_max, int normalize, uint16_t* out_bf16, uint16_t* out_bf16_lo, float* out_f32,
                            int32_t* taps, mv_stream_t stream) {
   MV_REQUIRE(src && (out_bf16 || out_f32), MV_E_ARG, "mv_k1_sample_normalize: null src or no output");
   MV_REQUIRE(mode == MV_SAMPLE_BILINEAR_ZEROS || mode == MV_SAMPLE_BICUBIC_CLAMP || mode == MV_SAMPLE_ROWS,
@@ -631,6 +646,8 @@ int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, cons
              "mv_k1_sample_normalize: out_f32 must be 16-byte aligned");
   MV_REQUIRE(!out_bf16 || (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0, MV_E_ALIGN,
              "mv_k1_sample_normalize: out_bf16 must be 8-byte aligned");
+  MV_REQUIRE(!out_bf16_lo || (out_bf16 && (reinterpret_cast<uintptr_t>(out_bf16_lo) & 7) == 0), MV_E_ARG,
+             "mv_k1_sample_normalize: out_bf16_lo needs out_bf16 and 8-byte alignment");
   if (n_max == 0) return MV_OK;
 
   K1Params p;
@@ -643,6 +660,7 @@ int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, cons
   p.w = w;
   p.normalize = normalize;
   p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_bf16_lo);
   p.out_f32 = out_f32;
   p.taps = taps;
 

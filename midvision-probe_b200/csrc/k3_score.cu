@@ -30,8 +30,39 @@ constexpr float MISSING_DIST = 2.0f; // distance reported for a candidate that d
 // ------------------------------------------------------------------------------------------
 // ratio / mutual: one warp per query row
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k3_ratio_mutual_kernel(const float* __restrict__ A, const float* __restrict__ B,
-                                                              int C, const int32_t* __restrict__ n_dev, int n_max,
+// Row storage: fp32 rows, or SPLIT rows = two bf16 planes hi = bf16(x), lo = bf16(x - hi) written by kernel 1;
+// hi + lo is exact in fp32 and differs from x by <= 2^-17 |x| per element, which moves 1 - cos by ~1e-7.
+struct RowsF32 {
+  const float* A;
+  const float* B;
+};
+struct RowsSplit {
+  const __nv_bfloat16* A_hi;
+  const __nv_bfloat16* A_lo;
+  const __nv_bfloat16* B_hi;
+  const __nv_bfloat16* B_lo;
+};
+
+__device__ __forceinline__ void acc5(float v, float a, float b, float& xx, float& aa, float& bb, float& xa, float& xb) {
+  xx = fmaf(v, v, xx);
+  aa = fmaf(a, a, aa);
+  bb = fmaf(b, b, bb);
+  xa = fmaf(v, a, xa);
+  xb = fmaf(v, b, xb);
+}
+
+__device__ __forceinline__ void split8(const __nv_bfloat16* hi, const __nv_bfloat16* lo, int c8, float (&out)[8]) {
+  const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi) + c8), l = __ldg(reinterpret_cast<const uint4*>(lo) + c8);
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {  // bf16 -> fp32 is a 16-bit shift
+    out[2 * k] = __uint_as_float(hw[k] << 16) + __uint_as_float(lw[k] << 16);
+    out[2 * k + 1] = __uint_as_float(hw[k] & 0xffff0000u) + __uint_as_float(lw[k] & 0xffff0000u);
+  }
+}
+
+template <typename ROWS>
+__global__ void __launch_bounds__(256) k3_ratio_mutual_kernel(ROWS rows, int C, const int32_t* __restrict__ n_dev, int n_max,
                                                               int32_t* __restrict__ row_idx,
                                                               const unsigned long long* __restrict__ col_best,
                                                               int ratio_test, float* __restrict__ dists,
@@ -41,17 +72,29 @@ __global__ void __launch_bounds__(256) k3_ratio_mutual_kernel(const float* __res
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= n) return;
   int j0 = row_idx[2 * (size_t)i], j1 = row_idx[2 * (size_t)i + 1];
-  const float4* x = reinterpret_cast<const float4*>(A + (size_t)i * C);
-  const float4* y0 = reinterpret_cast<const float4*>(B + (size_t)max(j0, 0) * C);
-  const float4* y1 = reinterpret_cast<const float4*>(B + (size_t)max(j1, 0) * C);
   float xx = 0.f, aa = 0.f, bb = 0.f, xa = 0.f, xb = 0.f;
-  for (int c = lane; c < (C >> 2); c += 32) {
-    const float4 v = __ldg(x + c), a = __ldg(y0 + c), b = __ldg(y1 + c);
-    xx = fmaf(v.x, v.x, xx); xx = fmaf(v.y, v.y, xx); xx = fmaf(v.z, v.z, xx); xx = fmaf(v.w, v.w, xx);
-    aa = fmaf(a.x, a.x, aa); aa = fmaf(a.y, a.y, aa); aa = fmaf(a.z, a.z, aa); aa = fmaf(a.w, a.w, aa);
-    bb = fmaf(b.x, b.x, bb); bb = fmaf(b.y, b.y, bb); bb = fmaf(b.z, b.z, bb); bb = fmaf(b.w, b.w, bb);
-    xa = fmaf(v.x, a.x, xa); xa = fmaf(v.y, a.y, xa); xa = fmaf(v.z, a.z, xa); xa = fmaf(v.w, a.w, xa);
-    xb = fmaf(v.x, b.x, xb); xb = fmaf(v.y, b.y, xb); xb = fmaf(v.z, b.z, xb); xb = fmaf(v.w, b.w, xb);
+  if constexpr (sizeof(ROWS) == sizeof(RowsF32)) {
+    const float4* x = reinterpret_cast<const float4*>(rows.A + (size_t)i * C);
+    const float4* y0 = reinterpret_cast<const float4*>(rows.B + (size_t)max(j0, 0) * C);
+    const float4* y1 = reinterpret_cast<const float4*>(rows.B + (size_t)max(j1, 0) * C);
+    for (int c = lane; c < (C >> 2); c += 32) {
+      const float4 v = __ldg(x + c), a = __ldg(y0 + c), b = __ldg(y1 + c);
+      xx = fmaf(v.x, v.x, xx); xx = fmaf(v.y, v.y, xx); xx = fmaf(v.z, v.z, xx); xx = fmaf(v.w, v.w, xx);
+      aa = fmaf(a.x, a.x, aa); aa = fmaf(a.y, a.y, aa); aa = fmaf(a.z, a.z, aa); aa = fmaf(a.w, a.w, aa);
+      bb = fmaf(b.x, b.x, bb); bb = fmaf(b.y, b.y, bb); bb = fmaf(b.z, b.z, bb); bb = fmaf(b.w, b.w, bb);
+      xa = fmaf(v.x, a.x, xa); xa = fmaf(v.y, a.y, xa); xa = fmaf(v.z, a.z, xa); xa = fmaf(v.w, a.w, xa);
+      xb = fmaf(v.x, b.x, xb); xb = fmaf(v.y, b.y, xb); xb = fmaf(v.z, b.z, xb); xb = fmaf(v.w, b.w, xb);
+    }
+  } else {
+    const size_t ox = (size_t)i * C, o0 = (size_t)max(j0, 0) * C, o1 = (size_t)max(j1, 0) * C;
+    for (int c8 = lane; c8 < (C >> 3); c8 += 32) {
+      float v[8], a[8], b[8];
+      split8(rows.A_hi + ox, rows.A_lo + ox, c8, v);
+      split8(rows.B_hi + o0, rows.B_lo + o0, c8, a);
+      split8(rows.B_hi + o1, rows.B_lo + o1, c8, b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc5(v[k], a[k], b[k], xx, aa, bb, xa, xb);
+    }
   }
   xx = warp_sum(xx); aa = warp_sum(aa); bb = warp_sum(bb); xa = warp_sum(xa); xb = warp_sum(xb);
   if (lane != 0) return;
@@ -378,8 +421,27 @@ int mv_k3_ratio_mutual(const float* A32, const float* B32, int C, const int32_t*
   MV_REQUIRE(n_max >= 0, MV_E_ARG, "mv_k3_ratio_mutual: negative n_max");
   if (n_max == 0) return MV_OK;
   const int rows_per_cta = 8;
-  k3_ratio_mutual_kernel<<<(n_max + rows_per_cta - 1) / rows_per_cta, 32 * rows_per_cta, 0, mv_cuda_stream(stream)>>>(
-      A32, B32, C, n_dev, n_max, row_idx, col_best, ratio_test, dists, weight, mutual);
+  RowsF32 rows{A32, B32};
+  k3_ratio_mutual_kernel<RowsF32><<<(n_max + rows_per_cta - 1) / rows_per_cta, 32 * rows_per_cta, 0, mv_cuda_stream(stream)>>>(
+      rows, C, n_dev, n_max, row_idx, col_best, ratio_test, dists, weight, mutual);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+int mv_k3_ratio_mutual_split(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* B_hi, const uint16_t* B_lo, int C,
+                             const int32_t* n_dev, int n_max, int32_t* row_idx, const unsigned long long* col_best,
+                             int ratio_test, float* dists, float* weight, uint8_t* mutual, mv_stream_t stream) {
+  MV_REQUIRE(A_hi && A_lo && B_hi && B_lo && row_idx, MV_E_ARG, "mv_k3_ratio_mutual_split: null pointer");
+  MV_REQUIRE(C > 0 && C % 8 == 0, MV_E_ALIGN, "mv_k3_ratio_mutual_split: C=%d must be a positive multiple of 8", C);
+  MV_REQUIRE((((uintptr_t)A_hi | (uintptr_t)A_lo | (uintptr_t)B_hi | (uintptr_t)B_lo) & 15) == 0, MV_E_ALIGN,
+             "mv_k3_ratio_mutual_split: the row planes must be 16-byte aligned");
+  MV_REQUIRE(n_max >= 0, MV_E_ARG, "mv_k3_ratio_mutual_split: negative n_max");
+  if (n_max == 0) return MV_OK;
+  const int rows_per_cta = 8;
+  RowsSplit rows{reinterpret_cast<const __nv_bfloat16*>(A_hi), reinterpret_cast<const __nv_bfloat16*>(A_lo),
+                 reinterpret_cast<const __nv_bfloat16*>(B_hi), reinterpret_cast<const __nv_bfloat16*>(B_lo)};
+  k3_ratio_mutual_kernel<RowsSplit><<<(n_max + rows_per_cta - 1) / rows_per_cta, 32 * rows_per_cta, 0, mv_cuda_stream(stream)>>>(
+      rows, C, n_dev, n_max, row_idx, col_best, ratio_test, dists, weight, mutual);
   MV_LAUNCH_CHECK();
   return MV_OK;
 }

@@ -141,8 +141,7 @@ def match_and_score_depth(feat_0, feat_1, depth_0, depth_1, K, Rt, num_corr, acc
     Kh, Kinv = C_._host_mat(Kc), C_._host_mat(Kc.inverse())
     s0, s1 = _both_sides(lambda: C_.prepare_depth_side(feat_0, depth_0, Kh, Kinv, dev, sync=sync),
                          lambda: C_.prepare_depth_side(feat_1, depth_1, Kh, Kinv, dev, sync=sync), dev)
-    r = C_.match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, s0.n, s1.n, num_corr,
-                      n_dev=None if sync else s0.n_dev, m_dev=None if sync else s1.n_dev)
+    r = C_._match_sides(s0, s1, s0.n, s1.n, num_corr, n_dev=None if sync else s0.n_dev, m_dev=None if sync else s1.n_dev)
     acc.score(r, s0.xyz, s1.xyz, Rt, Kc)
     return r
 
@@ -153,8 +152,7 @@ def match_and_score_xyz(feat_0, feat_1, xyz_grid_0, xyz_grid_1, intrinsics, Rt, 
     dev = C_._device()
     s0, s1 = _both_sides(lambda: C_.prepare_xyz_side(feat_0, xyz_grid_0, dev, sync=sync),
                          lambda: C_.prepare_xyz_side(feat_1, xyz_grid_1, dev, sync=sync), dev)
-    r = C_.match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, s0.n, s1.n, num_corr,
-                      n_dev=None if sync else s0.n_dev, m_dev=None if sync else s1.n_dev)
+    r = C_._match_sides(s0, s1, s0.n, s1.n, num_corr, n_dev=None if sync else s0.n_dev, m_dev=None if sync else s1.n_dev)
     acc.score(r, s0.xyz, s1.xyz, Rt, intrinsics)
     return r
 
@@ -209,8 +207,7 @@ class GraphedPairMatcher:
         else:
             s0, s1 = _both_sides(lambda: C_.prepare_depth_side(self.f0, self.g0, self.Kh, self.Kinv, self.dev, sync=False),
                                  lambda: C_.prepare_depth_side(self.f1, self.g1, self.Kh, self.Kinv, self.dev, sync=False), self.dev)
-        r = C_.match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, s0.n, s1.n, self.num_corr, self.ratio_test,
-                          n_dev=s0.n_dev, m_dev=s1.n_dev)
+        r = C_._match_sides(s0, s1, s0.n, s1.n, self.num_corr, self.ratio_test, n_dev=s0.n_dev, m_dev=s1.n_dev)
         if self.with_outputs:
             # the helper's return tuple, packed row-wise for a single device -> host copy:
             # [xyz0 (3) | xyz1 (3) | weight (1) | uv0 (2) | uv1 (2)]; rows beyond the live k are not written

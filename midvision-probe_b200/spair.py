@@ -42,10 +42,10 @@ def compute_errors_from_features(feats, kps_i, kps_j, thresh_scale, image_size, 
     rows_j32 = C_._hwc(f[1], prenorm=True)  # (h*w, C): the heat-map columns, pixel p = y*w + x
     coords = torch.empty((K, 2), dtype=torch.float32, device=dev)
     L.call("mv_geom_keypoint_coords", L.ptr(ki), ki.shape[1], K, c_float(float(image_size)), h, w, L.ptr(coords), st)
-    a16, a32 = C_._sample(L.MV_SAMPLE_BILINEAR_ZEROS, src_i, C, h, w, coords, None, K, False, want16, True)
+    a16, a32, _ = C_._sample(L.MV_SAMPLE_BILINEAR_ZEROS, src_i, C, h, w, coords, None, K, False, want16, True)
     b16 = None
     if want16:
-        b16, _ = C_._sample(L.MV_SAMPLE_ROWS, rows_j32, C, 0, 0, None, None, h * w, False, True, False)
+        b16 = C_._sample(L.MV_SAMPLE_ROWS, rows_j32, C, 0, 0, None, None, h * w, False, True, False)[0]
     r = C_.match_rows(a16, a32, b16, rows_j32, K, h * w, 0, want_topk=False)
     pred = r.row_idx[:, 0].contiguous()
     err_same = torch.empty((K,), dtype=torch.float32, device=dev)

@@ -37,7 +37,7 @@ def test_version_and_argument_errors_without_a_gpu(mv):
     lib = mv.load()
     assert lib.mv_version() == 100
     # argument validation happens before any CUDA call
-    rc = lib.mv_k1_sample_normalize(7, None, 8, 1, 1, None, None, 1, 0, None, None, None, None)
+    rc = lib.mv_k1_sample_normalize(7, None, 8, 1, 1, None, None, 1, 0, None, None, None, None, None)
     assert rc == -1
     assert b"mv_k1_sample_normalize" in lib.mv_last_error()
     rc = lib.mv_k3_topk_matches(ctypes.c_void_p(16), ctypes.c_void_p(16), None, 10, 1 << 20, ctypes.c_void_p(16),

@@ -53,7 +53,7 @@ def test_depth_side_matches_oracle(C_, mv, syn, shape):
     K = p["K"]
     xyz_o, f_o, keep_o = restated.depth_side(p["feat_0"], p["depth_0"], K)
     Kh, Kinv = C_._host_mat(K), C_._host_mat(K.inverse())
-    s = C_.prepare_depth_side(p["feat_0"], p["depth_0"], Kh, Kinv, torch.device("cuda"), want_taps=True)
+    s = C_.prepare_depth_side(p["feat_0"], p["depth_0"], Kh, Kinv, torch.device("cuda"), want_taps=True, rows="f32")
     n = s.n
     assert n == xyz_o.shape[0]
     assert torch.equal(s.valid_idx[:n].cpu().long(), keep_o)                       # gather indices: bit-exact
@@ -72,7 +72,7 @@ def test_depth_side_matches_oracle(C_, mv, syn, shape):
 def test_xyz_side_matches_oracle(C_, syn, shape):
     p = syn.navi_pair(5, coherent=False, **shape)
     xyz_o, f_o, uv_o, keep_o = restated.xyz_side(p["feat_0"], p["xyz_grid_0"])
-    s = C_.prepare_xyz_side(p["feat_0"], p["xyz_grid_0"], torch.device("cuda"), want_taps=True)
+    s = C_.prepare_xyz_side(p["feat_0"], p["xyz_grid_0"], torch.device("cuda"), want_taps=True, rows="f32")
     n = s.n
     assert n == xyz_o.shape[0]
     assert torch.equal(s.valid_idx[:n].cpu().long(), keep_o)
@@ -89,8 +89,8 @@ def test_xyz_side_matches_oracle(C_, syn, shape):
 
 def test_no_sync_variant_equals_synced(C_, syn):
     p = syn.navi_pair(6, coherent=False, C=64, h=8, w=8, H=32, W=32, radius=12.0)
-    a = C_.prepare_xyz_side(p["feat_0"], p["xyz_grid_0"], torch.device("cuda"), sync=True)
-    b = C_.prepare_xyz_side(p["feat_0"], p["xyz_grid_0"], torch.device("cuda"), sync=False)
+    a = C_.prepare_xyz_side(p["feat_0"], p["xyz_grid_0"], torch.device("cuda"), sync=True, rows="f32")
+    b = C_.prepare_xyz_side(p["feat_0"], p["xyz_grid_0"], torch.device("cuda"), sync=False, rows="f32")
     n = a.n
     assert int(b.n_dev.item()) == n and b.n == 32 * 32
     assert torch.equal(a.rows32[:n], b.rows32[:n]) and torch.equal(a.xyz[:n], b.xyz[:n])
@@ -112,7 +112,7 @@ def test_keypoint_sampling_align_corners_true(mv, C_, C, h, w, K):
     coords = torch.empty(K, 2, device="cuda")
     kd = kps.cuda()
     L.call("mv_geom_keypoint_coords", L.ptr(kd), 3, K, c_float(size), h, w, L.ptr(coords), C_._stream())
-    _, got = C_._sample(L.MV_SAMPLE_BILINEAR_ZEROS, src, C, h, w, coords, None, K, False, False, True)
+    _, got, _ = C_._sample(L.MV_SAMPLE_BILINEAR_ZEROS, src, C, h, w, coords, None, K, False, False, True)
     torch.testing.assert_close(got[:K].cpu(), want, rtol=0, atol=ATOL)
 
 
@@ -127,3 +127,20 @@ def test_sample_pointcloud_features_and_grid_to_pointcloud(C_, syn):
     f = C_.sample_pointcloud_features(p["feat_0"], K.clone(), pc_o[keep], p["depth_0"].shape[-2:])
     want = restated.sample_pointcloud_features(p["feat_0"], K.clone(), pc_o[keep], p["depth_0"].shape[-2:])
     torch.testing.assert_close(f, want, rtol=0, atol=ATOL)
+
+
+@pytest.mark.parametrize("C", [768, 2048, 3072, 200])
+def test_split_rows_rebuild_the_fp32_rows(C_, syn, C):
+    """kernel 1's split output (bf16 hi + bf16 residual) against its own fp32 rows: hi is the bf16 rounding of
+    the fp32 row bit for bit, and hi + lo rebuilds it to 2^-16 relative (the stated tolerance of the format)."""
+    p = syn.navi_pair(7, coherent=False, C=C, h=10, w=10, H=40, W=40, radius=15.0)
+    dev = torch.device("cuda")
+    a = C_.prepare_xyz_side(p["feat_0"], p["xyz_grid_0"], dev, rows="f32")
+    b = C_.prepare_xyz_side(p["feat_0"], p["xyz_grid_0"], dev, rows="split")
+    n = a.n
+    assert b.rows32 is None and b.rows_lo is not None
+    assert torch.equal(a.rows16[:n], b.rows16[:n])
+    assert torch.equal(a.rows32[:n].to(torch.bfloat16), b.rows16[:n])
+    rebuilt = b.rows16[:n].float() + b.rows_lo[:n].float()
+    err = (rebuilt - a.rows32[:n]).abs()
+    assert bool((err <= 2.0 ** -16 * a.rows32[:n].abs() + 1e-30).all())

@@ -1,0 +1,49 @@
+"""Where the time of one host-tensor helper call goes (NAVI-shaped pair): H2D, graph replay, D2H + host work."""
+import importlib
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+mv = importlib.import_module("midvision-probe_b200")
+syn = importlib.import_module("midvision-probe_b200.synthetic")
+C_ = mv.correspondence
+pairs = [{k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in syn.navi_pair(i).items()} for i in range(8)]
+call = lambda p: C_.estimate_correspondence_xyz(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], 1000)
+for p in pairs[:3]:
+    call(p)
+gm = next(iter(C_._HELPER_GRAPHS.values()))
+
+
+def timed(fn, n=40):
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(n):
+        fn(pairs[i % 8])
+    torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / n * 1e6
+
+
+def only_load(p):
+    gm.load(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"])
+    torch.cuda.current_stream().synchronize()
+
+
+def load_replay(p):
+    gm.load(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"])
+    gm.graph.replay()
+    torch.cuda.current_stream().synchronize()
+
+
+def only_replay(p):
+    gm.graph.replay()
+    torch.cuda.current_stream().synchronize()
+
+
+print(f"H2D of one pair (19.6 MB pinned) + sync : {timed(only_load):7.1f} us")
+print(f"graph replay + sync                     : {timed(only_replay):7.1f} us")
+print(f"H2D + replay + sync                     : {timed(load_replay):7.1f} us")
+print(f"full helper call                        : {timed(call):7.1f} us")

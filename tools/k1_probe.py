@@ -16,10 +16,13 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--kind", default="navi")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--nosync", action="store_true")
+ap.add_argument("--rows", default=None, choices=["split", "f32"])
 a = ap.parse_args()
 mv = importlib.import_module("midvision-probe_b200")
 syn = importlib.import_module("midvision-probe_b200.synthetic")
 C_ = mv.correspondence
+if a.rows:
+    C_.set_match_precision(rows=a.rows)
 dev = torch.device("cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 if a.kind == "navi":
@@ -66,7 +69,8 @@ for _ in range(a.reps):
 ms = sorted(times)[len(times) // 2]
 k1 = sorted(a_.elapsed_time(b_) for a_, b_ in _k1_events[1:])
 k1_ms = k1[len(k1) // 2]
-byts = C * f.shape[1] * f.shape[2] * 4 + n * C * (6 if s.rows16 is not None else 4)
+byts = C * f.shape[1] * f.shape[2] * 4 + n * C * ((2 if s.rows16 is not None else 0) + (4 if s.rows32 is not None else 0)
+                                                   + (2 if s.rows_lo is not None else 0))
 print(f"{a.kind} side: n={n} C={C} whole prepare (compact + coords + transpose + kernel 1) {ms * 1e3:.1f} us; "
       f"kernel-1 algorithmic bytes {byts / 1e6:.1f} MB; kernel 1 alone {k1_ms * 1e3:.1f} us = "
       f"{byts / k1_ms / 1e6:.0f} GB/s (L2 flushed before each call)")
@@ -74,15 +78,17 @@ print(f"{a.kind} side: n={n} C={C} whole prepare (compact + coords + transpose +
 # kernel 1 alone, device-bound: 4 rotating output sets (> L2) so no launch finds its rows in L2, 24 launches
 # replayed from one CUDA graph so the host is out of the picture
 mode, src, C_, h, w, coords, n_dev, n_max, normalize, want16, want32 = _k1_args[0][:11]
+want_lo = _k1_args[0][12] if len(_k1_args[0]) > 12 else False
 L = mv._lib
-outs = [(torch.empty((n_max, C_), dtype=torch.bfloat16, device=dev), torch.empty((n_max, C_), dtype=torch.float32, device=dev))
-        for _ in range(4)]
+outs = [(torch.empty((n_max, C_), dtype=torch.bfloat16, device=dev),
+         torch.empty((n_max, C_), dtype=torch.float32, device=dev) if want32 else None,
+         torch.empty((n_max, C_), dtype=torch.bfloat16, device=dev) if want_lo else None) for _ in range(6)]
 st = torch.cuda.Stream()
 with torch.cuda.stream(st):
     def launch(i):
-        o16, o32 = outs[i % 4]
+        o16, o32, olo = outs[i % 6]
         L.call("mv_k1_sample_normalize", mode, L.ptr(src), C_, h, w, L.ptr(coords), L.ptr(n_dev), n_max, int(normalize),
-               L.ptr(o16), L.ptr(o32), None, ctypes.c_void_p(st.cuda_stream))
+               L.ptr(o16), L.ptr(olo), L.ptr(o32), None, ctypes.c_void_p(st.cuda_stream))
     launch(0)
     st.synchronize()
     g = torch.cuda.CUDAGraph()
@@ -97,5 +103,5 @@ with torch.cuda.stream(st):
     e1.record(st)
     st.synchronize()
 us = e0.elapsed_time(e1) / 24 * 1e3
-print(f"kernel 1 device time (graph of 24 launches, rotating outputs): {us:.1f} us = {byts / us / 1e3:.0f} GB/s "
+print(f"kernel 1 device time (graph of 24 launches, 6 rotating output sets): {us:.1f} us = {byts / us / 1e3:.0f} GB/s "
       f"= {100 * byts / us / 1e3 / 6544:.0f} % of 6544 GB/s")
