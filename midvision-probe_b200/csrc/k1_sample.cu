@@ -17,6 +17,7 @@
 // the row writes: C*h*w*4 bytes read + n*C*(2 [+4]) bytes written.
 
 #include "common.cuh"
+#include "sm100_ptx.cuh"
 
 namespace {
 
@@ -266,31 +267,35 @@ __device__ __forceinline__ void cubic_coeffs(float t, float c[4]) {
 }
 
 // ------------------------------------------------------------------------------------------
-// kernel 1: one warp per output point over a shared-memory window of source columns
+// kernel 1: teams of warps over a shared-memory window of source columns
 // ------------------------------------------------------------------------------------------
 // A CTA owns a range of consecutive live points and cuts it into SUB-RUNS: maximal prefixes of points that
 // lie on one output row and whose taps fall into a window of source columns that fits shared memory.
-//   phase S (warp 0): per point scalars (tap origin, 4 blend weights, 4 shared-memory offsets) + the window
+//   phase S (warp 0): per point scalars (tap origin, 4 blend weights), the window, and GROUPS: up to G
+//            consecutive points with the same tap origin, i.e. the same four window columns
 //   phase A (all threads): fill the window in shared memory from the L2-resident channel-last map --
 //            bicubic: the 4 source rows blended along y ONCE per column (every point of the sub-run has the
 //            bit-identical y coordinate), bilinear: the two raw source rows (zeros outside the map)
-//   phase B (one WARP per point): 4 x LDS.128 + 16 FMA per 4 channels, the whole row of C channels stays in
-//            the warp's registers, the sum of squares needs 5 shuffles per POINT (not per warp of a
-//            block-wide reduction) and no block barrier, then scale + bf16 / fp32 row stores (512 B and
-//            256 B contiguous per warp instruction).
-// Per output element: 1 LDS + 6 FMA/FMUL + ~1 convert/store, and no barrier inside the per-point loop (the
-// first version -- one CTA per point, taps in registers, block-wide reduction -- issued ~37 instructions per
-// element and ran at 2.6 TB/s; this form runs at the write-bandwidth limit of the part).
-constexpr int K1W_PMAX = 32;                // points per sub-run: one warp inspects them with a ballot
-constexpr int K1W_SMEM_BUDGET = 108 << 10;  // window bytes per CTA: two CTAs per SM
+//   phase B (a TEAM of W warps per group, warp = C / W channels): each warp loads its slice of the four
+//            columns once (4 x LDS.128 per 4 channels) and blends it for all G points of the group, so the
+//            shared-memory traffic per point is 1/G of a point-at-a-time loop; the rows stay in registers
+//            (G x C / W values per warp); the sum of squares is 5 shuffles per point and warp plus one
+//            named barrier per group among the W warps; then scale + row stores, contiguous per warp.
+// History (profiles/): one CTA per point with taps in registers and a block-wide reduction issued ~37
+// instructions per element (2.6 TB/s); one warp per point over the window issued ~10 but was bound by the
+// LSU pipe (96 LDS.128 + 48 STG per point and warp); the group form cuts the LDS count by G.
+constexpr int K1W_PMAX = 32;  // points per sub-run: one warp inspects them with a ballot
 // which row outputs exist: bf16 + fp32, fp32 only, bf16 + bf16 residual, or ANY (checked at run time)
 constexpr int K1W_OUT_BOTH = 0, K1W_OUT_F32 = 1, K1W_OUT_ANY = 2, K1W_OUT_SPLIT = 3;
 
+template <int W>
 struct K1WShared {
   float wt[K1W_PMAX][4];
-  int off[K1W_PMAX][4];  // float offsets into the window
+  int off[K1W_PMAX][4];  // float offsets of the point's four columns / taps in the window
+  int g_start[K1W_PMAX], g_cnt[K1W_PMAX];
+  float part[2][4][4][4];  // [parity][team][point of the group][warp of the team]: partial sums of squares
   float cy[4];
-  int npts, ncols, xbase, y0;
+  int npts, ncols, xbase, y0, ngroups;
 };
 
 __device__ __forceinline__ float4 lds4(const float* q) { return *reinterpret_cast<const float4*>(q); }
@@ -301,17 +306,21 @@ __device__ __forceinline__ float dot4(const float4& v, float ss) {
   return fmaf(v.w, v.w, ss);
 }
 
-// NIT > 0: C == 128 * NIT exactly, the row lives in NIT float4 registers per lane, no channel predicates.
-// NIT == 0: any C (multiple of 4): two passes over the window (sum of squares, then values), nothing held.
-template <int MODE, int NIT, int OUTS, int THREADS>
-__global__ void __launch_bounds__(THREADS, 2) k1_warp_rows_kernel(K1Params p, int nslots, uint32_t c4_magic) {
+// NITW > 0: C == 128 * NITW * W exactly; a warp holds G rows of C / W channels (G * NITW float4 per lane).
+// NITW == 0: any C (multiple of 4), W = G = 1: two passes over the window (sum of squares, then values).
+template <int MODE, int NITW, int W, int G, int OUTS, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int nslots, uint32_t c4_magic) {
+  static_assert(W == 1 || W == 2 || W == 4, "team size");
+  static_assert(G >= 1 && G <= 4 && (THREADS / 32) % W == 0 && (W == 1 || THREADS / 32 / W <= 4), "team layout");
   extern __shared__ float4 k1w_dyn[];
   float* win = reinterpret_cast<float*>(k1w_dyn);
-  __shared__ K1WShared sh;
+  __shared__ K1WShared<W> sh;
   const int n = p.n_dev ? min(*p.n_dev, p.n_max) : p.n_max;
-  const int C = (NIT > 0) ? NIT * 128 : p.C, C4 = C >> 2;
+  const int C = (NITW > 0) ? NITW * W * 128 : p.C, C4 = C >> 2;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  constexpr int NWARP = THREADS / 32;
+  constexpr int NWARP = THREADS / 32, NTEAM = NWARP / W;
+  const int team = wid / W, wsub = wid % W;
+  const int cbase = wsub * (C / W);  // this warp's channel slice
   const int ppc = (n + (int)gridDim.x - 1) / (int)gridDim.x;  // from the LIVE count: no idle SMs for a small n
   const int pt_beg = min(blockIdx.x * ppc, n);
   const int pt_end = min(pt_beg + ppc, n);
@@ -319,6 +328,7 @@ __global__ void __launch_bounds__(THREADS, 2) k1_warp_rows_kernel(K1Params p, in
   const bool has16 = (OUTS == K1W_OUT_BOTH || OUTS == K1W_OUT_SPLIT) || (OUTS == K1W_OUT_ANY && p.out_bf16 != nullptr);
   const bool haslo = (OUTS == K1W_OUT_SPLIT) || (OUTS == K1W_OUT_ANY && p.out_lo != nullptr);
   const bool normalize = p.normalize != 0;
+  int parity = 0;  // of this team's group counter: double-buffers sh.part
 
   auto put = [&](int pt, int c, float4 o, float inv) {
     o.x *= inv;  // inv == 1 when not normalising: exact
@@ -341,35 +351,54 @@ __global__ void __launch_bounds__(THREADS, 2) k1_warp_rows_kernel(K1Params p, in
       }
     }
   };
-  // value_at(c) -> un-normalised float4 of channels [c, c + 4)
-  auto finish_point = [&](int pt, auto&& value_at) {
-    if (NIT > 0) {
-      float4 acc[NIT > 0 ? NIT : 1];
-      float ss = 0.f;
+  // x * (1 / max(||x||, eps)) from the per-warp partial sums of squares of the cnt rows of a group
+  auto inverse_norms = [&](float (&ss)[G], float (&inv)[G]) {
 #pragma unroll
-      for (int it = 0; it < NIT; ++it) {
-        acc[it] = value_at((it * 32 + lane) * 4);
-        ss = dot4(acc[it], ss);
-      }
-      float inv = 1.f;
-      if (normalize) inv = __frcp_rn(fmaxf(sqrtf(warp_sum(ss)), K1_NORM_EPS));  // x * (1 / max(||x||, eps))
+    for (int j = 0; j < G; ++j) inv[j] = 1.f;
+    if (!normalize) return;
 #pragma unroll
-      for (int it = 0; it < NIT; ++it) put(pt, (it * 32 + lane) * 4, acc[it], inv);
-    } else {
-      float inv = 1.f;
-      if (normalize) {
-        float ss = 0.f;
-        for (int c = lane * 4; c < C; c += 128) ss = dot4(value_at(c), ss);
-        inv = __frcp_rn(fmaxf(sqrtf(warp_sum(ss)), K1_NORM_EPS));
+    for (int j = 0; j < G; ++j) ss[j] = warp_sum(ss[j]);
+    if (W > 1) {
+      if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < G; ++j) sh.part[parity][team][j][wsub] = ss[j];
       }
-      for (int c = lane * 4; c < C; c += 128) put(pt, c, value_at(c), inv);
+      sm100::named_bar_sync(1 + team, W * 32);
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        float t = 0.f;
+#pragma unroll
+        for (int q = 0; q < W; ++q) t += sh.part[parity][team][j][q];  // fixed order: every warp gets the same bits
+        ss[j] = t;
+      }
+      parity ^= 1;  // the next group's partials go to the other buffer; its barrier orders the re-use of this one
     }
+#pragma unroll
+    for (int j = 0; j < G; ++j) inv[j] = __frcp_rn(fmaxf(sqrtf(ss[j]), K1_NORM_EPS));
   };
 
-  if (MODE == MV_SAMPLE_ROWS) {  // rows as they are: one warp per row, no window
-    for (int pt = pt_beg + wid; pt < pt_end; pt += NWARP) {
+  if (MODE == MV_SAMPLE_ROWS) {  // rows as they are, no window: a team per row
+    for (int pt = pt_beg + team; pt < pt_end; pt += NTEAM) {
       const float* row = p.src + (size_t)pt * C;
-      finish_point(pt, [&](int c) { return ld4(row + c); });
+      float ss[G], inv[G];
+#pragma unroll
+      for (int j = 0; j < G; ++j) ss[j] = 0.f;
+      if (NITW > 0) {
+        float4 acc[NITW > 0 ? NITW : 1];
+#pragma unroll
+        for (int it = 0; it < NITW; ++it) {
+          acc[it] = ld4(row + cbase + (it * 32 + lane) * 4);
+          ss[0] = dot4(acc[it], ss[0]);
+        }
+        inverse_norms(ss, inv);
+#pragma unroll
+        for (int it = 0; it < NITW; ++it) put(pt, cbase + (it * 32 + lane) * 4, acc[it], inv[0]);
+      } else {
+        if (normalize)
+          for (int c = lane * 4; c < C; c += 128) ss[0] = dot4(ld4(row + c), ss[0]);
+        inverse_norms(ss, inv);
+        for (int c = lane * 4; c < C; c += 128) put(pt, c, ld4(row + c), inv[0]);
+      }
     }
     return;
   }
@@ -397,6 +426,19 @@ __global__ void __launch_bounds__(THREADS, 2) k1_warp_rows_kernel(K1Params p, in
       const int npts = (bal == 0xffffffffu) ? 32 : (__ffs(~bal) - 1);  // leading run of ok lanes (lane 0 always is)
       const int dxmax = __reduce_max_sync(0xffffffffu, lane < npts ? dx : 0);
       const int ncols = dxmax + (CUBIC ? 4 : 2);
+      // groups: consecutive points with the same tap origin (=> the same window columns), at most G of them
+      const int x0p = __shfl_up_sync(0xffffffffu, x0, 1);
+      const uint32_t segm = __ballot_sync(0xffffffffu, lane < npts && (lane == 0 || x0 != x0p));
+      const int seg_start = 31 - __clz(segm & (0xffffffffu >> (31 - lane)));  // last segment head at or before this lane
+      const bool head = lane < npts && ((lane - seg_start) % G == 0);
+      const uint32_t headm = __ballot_sync(0xffffffffu, head);
+      if (head) {
+        const int gid = __popc(headm & ((1u << lane) - 1u));
+        const uint32_t later = (lane == 31) ? 0u : (headm >> (lane + 1));
+        const int end = later ? lane + __ffs(later) : npts;
+        sh.g_start[gid] = lane;
+        sh.g_cnt[gid] = end - lane;
+      }
       if (lane < npts) {
         if (p.taps) {
           p.taps[2 * (size_t)pt] = x0;
@@ -428,13 +470,14 @@ __global__ void __launch_bounds__(THREADS, 2) k1_warp_rows_kernel(K1Params p, in
         sh.ncols = ncols;
         sh.xbase = CUBIC ? x0 - 1 : x0;
         sh.y0 = y0;
+        sh.ngroups = __popc(headm);
         if (CUBIC) cubic_coeffs(xy.y - fy, sh.cy);
       }
     }
     __syncthreads();
-    const int npts = sh.npts, ncols = sh.ncols, xbase = sh.xbase, y0 = sh.y0;
+    const int npts = sh.npts, ncols = sh.ncols, xbase = sh.xbase, y0 = sh.y0, ngroups = sh.ngroups;
 
-    // ---- phase A: one flat loop over (window slot, 4 channels), 4 items = up to 16 loads in flight per thread ----
+    // ---- phase A: one flat loop over (window slot, 4 channels), several items = many loads in flight per thread ----
     if (CUBIC) {
       const float cy0 = sh.cy[0], cy1 = sh.cy[1], cy2 = sh.cy[2], cy3 = sh.cy[3];
       const size_t rs = (size_t)p.w * C;
@@ -473,30 +516,78 @@ __global__ void __launch_bounds__(THREADS, 2) k1_warp_rows_kernel(K1Params p, in
     __syncthreads();
 
     // ---- phase B ----
-    for (int t = wid; t < npts; t += NWARP) {
-      const float w0 = sh.wt[t][0], w1 = sh.wt[t][1], w2 = sh.wt[t][2], w3 = sh.wt[t][3];
-      const float* q0 = win + sh.off[t][0];
-      const float* q1 = win + sh.off[t][1];
-      const float* q2 = win + sh.off[t][2];
-      const float* q3 = win + sh.off[t][3];
-      finish_point(cur + t, [&](int c) {
+    for (int g = team; g < ngroups; g += NTEAM) {
+      const int t0 = sh.g_start[g], cnt = sh.g_cnt[g];
+      const float* q0 = win + sh.off[t0][0] + cbase;
+      const float* q1 = win + sh.off[t0][1] + cbase;
+      const float* q2 = win + sh.off[t0][2] + cbase;
+      const float* q3 = win + sh.off[t0][3] + cbase;
+      float wt[G][4];
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const int t = t0 + min(j, cnt - 1);  // rows beyond cnt repeat the last point and are not stored
+#pragma unroll
+        for (int k = 0; k < 4; ++k) wt[j][k] = sh.wt[t][k];
+      }
+      auto blend = [&](int j, const float4& a, const float4& b, const float4& c, const float4& d) {
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        fma4(o, w0, lds4(q0 + c));
-        fma4(o, w1, lds4(q1 + c));
-        fma4(o, w2, lds4(q2 + c));
-        fma4(o, w3, lds4(q3 + c));
+        fma4(o, wt[j][0], a);
+        fma4(o, wt[j][1], b);
+        fma4(o, wt[j][2], c);
+        fma4(o, wt[j][3], d);
         return o;
-      });
+      };
+      float ss[G], inv[G];
+#pragma unroll
+      for (int j = 0; j < G; ++j) ss[j] = 0.f;
+      if (NITW > 0) {
+        float4 acc[G][NITW > 0 ? NITW : 1];
+#pragma unroll
+        for (int it = 0; it < NITW; ++it) {
+          const int c = (it * 32 + lane) * 4;
+          const float4 a = lds4(q0 + c), b = lds4(q1 + c), cc = lds4(q2 + c), d = lds4(q3 + c);
+#pragma unroll
+          for (int j = 0; j < G; ++j) {
+            acc[j][it] = blend(j, a, b, cc, d);
+            ss[j] = dot4(acc[j][it], ss[j]);
+          }
+        }
+        inverse_norms(ss, inv);
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          if (j < cnt) {
+#pragma unroll
+            for (int it = 0; it < NITW; ++it) put(cur + t0 + j, cbase + (it * 32 + lane) * 4, acc[j][it], inv[j]);
+          }
+        }
+      } else {  // W == G == 1
+        if (normalize)
+          for (int c = lane * 4; c < C; c += 128)
+            ss[0] = dot4(blend(0, lds4(q0 + c), lds4(q1 + c), lds4(q2 + c), lds4(q3 + c)), ss[0]);
+        inverse_norms(ss, inv);
+        for (int c = lane * 4; c < C; c += 128)
+          put(cur + t0, c, blend(0, lds4(q0 + c), lds4(q1 + c), lds4(q2 + c), lds4(q3 + c)), inv[0]);
+      }
     }
     __syncthreads();  // the window and the per-point scalars are rewritten by the next sub-run
     cur += npts;
   }
 }
 
-template <int MODE, int NIT, int OUTS, int THREADS>
-int launch_k1_warp_inst(const K1Params& p, int grid, size_t smem, int nslots, cudaStream_t st) {
-  auto kern = k1_warp_rows_kernel<MODE, NIT, OUTS, THREADS>;
-  static size_t opted_in = 48 << 10;  // per instantiation: the attribute belongs to the device function
+template <int MODE, int NITW, int W, int G, int OUTS, int THREADS, int MINB>
+int launch_k1_inst(const K1Params& p, cudaStream_t st) {
+  const int C = p.C;
+  // window bytes per CTA: MINB CTAs per SM share 227 KB (minus ~3 KB static and 1 KB reserved each)
+  const int budget = (MINB >= 3 ? 72 : 108) << 10;
+  int nslots = budget / (C * 4);
+  if (nslots < 4) nslots = 4;    // C <= 8192: 4 slots = 128 KB, one CTA per SM
+  if (nslots > 40) nslots = 40;  // more than any 32-point sub-run can use
+  const size_t smem = (MODE == MV_SAMPLE_ROWS) ? 0 : (size_t)nslots * C * 4;
+  int grid = mv_sm_count() * MINB;
+  if (grid > p.n_max) grid = p.n_max;
+  if (grid < 1) grid = 1;
+  auto kern = k1_rows_kernel<MODE, NITW, W, G, OUTS, THREADS, MINB>;
+  static size_t opted_in = 44 << 10;  // per instantiation: the attribute belongs to the device function
   if (smem > opted_in) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
@@ -516,30 +607,27 @@ int launch_k1_warp_inst(const K1Params& p, int grid, size_t smem, int nslots, cu
 template <int MODE>
 int launch_k1_warp(const K1Params& p, cudaStream_t st) {
   const int C = p.C;
-  int nslots = K1W_SMEM_BUDGET / (C * 4);
-  if (nslots < 4) nslots = 4;    // C <= 8192: 4 slots = 128 KB, one CTA per SM
-  if (nslots > 40) nslots = 40;  // more than any 32-point sub-run can use
-  const size_t smem = (MODE == MV_SAMPLE_ROWS) ? 0 : (size_t)nslots * C * 4;
-  int grid = mv_sm_count() * 2;
-  if (grid > p.n_max) grid = p.n_max;
-  if (grid < 1) grid = 1;
   int outs = K1W_OUT_ANY;
   if (p.out_f32 && p.out_bf16 && !p.out_lo) outs = K1W_OUT_BOTH;
   else if (p.out_f32 && !p.out_bf16 && !p.out_lo) outs = K1W_OUT_F32;
   else if (!p.out_f32 && p.out_bf16 && p.out_lo) outs = K1W_OUT_SPLIT;
-#define K1W_CASE(NIT, THREADS)                                                                                     \
-  if (C == 128 * NIT && outs == K1W_OUT_BOTH)                                                                      \
-    return launch_k1_warp_inst<MODE, NIT, K1W_OUT_BOTH, THREADS>(p, grid, smem, nslots, st);                       \
-  if (C == 128 * NIT && outs == K1W_OUT_F32)                                                                       \
-    return launch_k1_warp_inst<MODE, NIT, K1W_OUT_F32, THREADS>(p, grid, smem, nslots, st);                        \
-  if (C == 128 * NIT && outs == K1W_OUT_SPLIT)                                                                     \
-    return launch_k1_warp_inst<MODE, NIT, K1W_OUT_SPLIT, THREADS>(p, grid, smem, nslots, st);
-  K1W_CASE(6, 256)   // ViT-B   768
-  K1W_CASE(8, 256)   // ViT-L   1024
-  K1W_CASE(16, 256)  // ResNet-50 layer4 2048
-  K1W_CASE(24, 192)  // ViT-B 4-block concat 3072: 96 row registers per lane -> 6 warps x 168 registers
+#define K1W_CASE(CC, NITW, W, GG, THREADS, MINB)                                                                      \
+  if (C == CC) {                                                                                                      \
+    constexpr int G = (MODE == MV_SAMPLE_ROWS) ? 1 : GG;                                                              \
+    if (outs == K1W_OUT_BOTH) return launch_k1_inst<MODE, NITW, W, G, K1W_OUT_BOTH, THREADS, MINB>(p, st);            \
+    if (outs == K1W_OUT_F32) return launch_k1_inst<MODE, NITW, W, G, K1W_OUT_F32, THREADS, MINB>(p, st);              \
+    if (outs == K1W_OUT_SPLIT) return launch_k1_inst<MODE, NITW, W, G, K1W_OUT_SPLIT, THREADS, MINB>(p, st);          \
+  }
+  // a warp holds G rows of C / W channels.  Measured on B200 (tools/k1_probe.py, split rows): C = 2048 (8x bilinear)
+  // 39.6 us with teams of 4 warps x 4 points vs 41.4 us point-at-a-time; C = 3072 (4x bicubic, ~12-17 points per
+  // CTA) 31.5 us with teams -- the 72 KB window of a 3-CTA/SM layout splits the short runs -- vs 27.4 us with one
+  // warp per point and the whole row (96 registers) in a 108 KB window, so that shape keeps the latter.
+  K1W_CASE(768, 6, 1, 4, 128, 3)    // ViT-B
+  K1W_CASE(1024, 4, 2, 4, 256, 2)   // ViT-L
+  K1W_CASE(2048, 4, 4, 4, 256, 2)   // ResNet-50 layer4
+  K1W_CASE(3072, 24, 1, 1, 192, 2)  // ViT-B 4-block concat
 #undef K1W_CASE
-  return launch_k1_warp_inst<MODE, 0, K1W_OUT_ANY, 256>(p, grid, smem, nslots, st);
+  return launch_k1_inst<MODE, 0, 1, 1, K1W_OUT_ANY, 256, 2>(p, st);
 }
 
 Mat3 load_mat3(const float* host) {
