@@ -174,6 +174,15 @@ int mv_k3_score(const int32_t* sel_src, const int32_t* sel_dst, const int32_t* k
 int mv_gather_rows(const float* src, int width, const int32_t* idx, const int32_t* k_dev, int k_max, float* dst,
                    mv_stream_t stream);
 
+/* The return tuple of estimate_correspondence_xyz / _depth (correspondence.py:229-232, :258-263) gathered into ONE
+ * buffer of column blocks, each k_max rows: [xyz0 (k_max,3) | xyz1 (k_max,3) | weight (k_max) | uv0 (k_max,2) |
+ * uv1 (k_max,2) | n0, n1, k, 0] -- xyz0 = xyz0_all[sel_src], xyz1 = xyz1_all[sel_dst] etc.; the uv blocks exist
+ * only when uv0/uv1 are given; the 4-float tail carries the live counts (*n0_dev, *n1_dev, k) so that a host
+ * caller needs a single device -> host copy and a single sync.  out: (7 or 11) * k_max + 4 floats. */
+int mv_pack_matches(const int32_t* sel_src, const int32_t* sel_dst, const float* sel_weight, const int32_t* k_dev, int k_max,
+                    const float* xyz0, const float* xyz1, const float* uv0, const float* uv1, const int32_t* n0_dev,
+                    const int32_t* n1_dev, float* out, mv_stream_t stream);
+
 /* argmax_2d (correspondence.py:179-190): flat arg-max (or arg-min) of every row of x (rows, cols),
  * first occurrence on ties; out_flat (rows) int32.  The caller turns flat into (col, row). */
 int mv_argmax_rows(const float* x, int rows, int cols, int max_value, int32_t* out_flat, mv_stream_t stream);

@@ -631,35 +631,34 @@ def _graphed_helper(kind, feat_0, feat_1, grid_0, grid_1, num_corr, ratio_test, 
     """Host-tensor fast path of the two dense helpers: the whole pair (kernels 1-3 + the gathers of the return
     tuple) is one cached CUDA graph; a call is 4 uploads into static buffers, one replay and ONE packed
     device -> host copy (results + the three live counts), i.e. a single host sync."""
-    import importlib
-
-    ev = importlib.import_module(__package__ + ".evaluation")
     dev = _device()
     layout = "hwc" if (_is_channel_last(feat_0) and _is_channel_last(feat_1)) else "chw"
     key = (kind, tuple(feat_0.shape), tuple(grid_0.shape), int(num_corr), bool(ratio_test), _CFG["dtype"], _CFG["cluster"], _CFG["rows"],
            None if K is None else tuple(K.detach().float().cpu().reshape(-1).tolist()), dev.index, layout)
     gm = _HELPER_GRAPHS.get(key)
     if gm is None:
+        import importlib
+
+        ev = importlib.import_module(__package__ + ".evaluation")
         if len(_HELPER_GRAPHS) >= _HELPER_GRAPHS_MAX:
             _HELPER_GRAPHS.pop(next(iter(_HELPER_GRAPHS)))
         gm = ev.GraphedPairMatcher(kind, tuple(feat_0.shape), tuple(grid_0.shape), num_corr, K=K, device=dev,
                                    ratio_test=ratio_test, with_outputs=True, feat_layout=layout).capture()
         _HELPER_GRAPHS[key] = gm
-    gm.load(feat_0, feat_1, grid_0, grid_1)
+    gm.load(feat_0, feat_1, grid_0, grid_1, two_streams=True)
     gm.graph.replay()
     L.LAUNCHES["count"] += gm.launches_per_replay
     gm.host_packed.copy_(gm.packed, non_blocking=True)
-    gm.host_counts.copy_(gm.counts, non_blocking=True)
     torch.cuda.current_stream(dev).synchronize()
-    n0, n1, k = (int(v) for v in gm.host_counts.tolist())
+    res = gm.host_packed.clone()  # the pinned buffer is overwritten by the next call
+    km = gm.k_max
+    blocks = 11 if kind == "xyz" else 7
+    n0, n1, k = (int(v) for v in res[blocks * km:blocks * km + 3].tolist())
     if n0 == 0 or n1 < 2:
         raise RuntimeError(f"too few valid points to match ({n0} vs {n1})")
-    res = gm.host_packed[:k].clone()
-    widths = (3, 3, 1, 2, 2) if kind == "xyz" else (3, 3, 1)
-    out, c = [], 0
-    for wd in widths:
-        out.append(res[:, c:c + wd].contiguous() if wd > 1 else res[:, c].contiguous())
-        c += wd
+    out = [res[0:3 * k].view(k, 3), res[3 * km:3 * km + 3 * k].view(k, 3), res[6 * km:6 * km + k]]
+    if kind == "xyz":
+        out += [res[7 * km:7 * km + 2 * k].view(k, 2), res[9 * km:9 * km + 2 * k].view(k, 2)]
     return tuple(out)
 
 

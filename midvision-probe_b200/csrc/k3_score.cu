@@ -369,6 +369,42 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, int width, con
   dst[t] = src[(size_t)idx[r] * width + c];
 }
 
+// The helper's whole return tuple in one buffer of column blocks, each k_max rows long:
+//   [xyz0 (k_max,3) | xyz1 (k_max,3) | weight (k_max) | uv0 (k_max,2) | uv1 (k_max,2) | n0, n1, k, 0]
+// (uv blocks only when uv0 != NULL).  Rows beyond the live k are left untouched.
+__global__ void pack_matches_kernel(const int32_t* __restrict__ sel_src, const int32_t* __restrict__ sel_dst,
+                                    const float* __restrict__ sel_weight, const int32_t* __restrict__ k_dev, int k_max,
+                                    const float* __restrict__ xyz0, const float* __restrict__ xyz1,
+                                    const float* __restrict__ uv0, const float* __restrict__ uv1,
+                                    const int32_t* __restrict__ n0_dev, const int32_t* __restrict__ n1_dev,
+                                    float* __restrict__ out) {
+  const int k = k_dev ? min(*k_dev, k_max) : k_max;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t K = (size_t)k_max;
+  if (t == 0) {  // live counts ride along (exact in fp32 below 2^24)
+    float* tail = out + (uv0 ? 11 : 7) * K;
+    tail[0] = n0_dev ? (float)*n0_dev : -1.f;
+    tail[1] = n1_dev ? (float)*n1_dev : -1.f;
+    tail[2] = (float)k;
+    tail[3] = 0.f;
+  }
+  if (t >= k) return;
+  const int a = sel_src[t], b = sel_dst[t];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    out[(size_t)t * 3 + c] = xyz0[(size_t)a * 3 + c];
+    out[3 * K + (size_t)t * 3 + c] = xyz1[(size_t)b * 3 + c];
+  }
+  out[6 * K + t] = sel_weight[t];
+  if (uv0) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      out[7 * K + (size_t)t * 2 + c] = uv0[(size_t)a * 2 + c];
+      out[9 * K + (size_t)t * 2 + c] = uv1[(size_t)b * 2 + c];
+    }
+  }
+}
+
 // argmax_2d: one warp per row, first occurrence wins
 __global__ void __launch_bounds__(256) argmax_rows_kernel(const float* __restrict__ x, int rows, int cols, int max_value,
                                                           int32_t* __restrict__ out) {
@@ -503,6 +539,18 @@ int mv_gather_rows(const float* src, int width, const int32_t* idx, const int32_
   if (k_max == 0) return MV_OK;
   const long long total = (long long)k_max * width;
   gather_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, mv_cuda_stream(stream)>>>(src, width, idx, k_dev, k_max, dst);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+int mv_pack_matches(const int32_t* sel_src, const int32_t* sel_dst, const float* sel_weight, const int32_t* k_dev, int k_max,
+                    const float* xyz0, const float* xyz1, const float* uv0, const float* uv1, const int32_t* n0_dev,
+                    const int32_t* n1_dev, float* out, mv_stream_t stream) {
+  MV_REQUIRE(sel_src && sel_dst && sel_weight && xyz0 && xyz1 && out, MV_E_ARG, "mv_pack_matches: null pointer");
+  MV_REQUIRE((uv0 == nullptr) == (uv1 == nullptr), MV_E_ARG, "mv_pack_matches: uv0 and uv1 go together");
+  MV_REQUIRE(k_max >= 0, MV_E_ARG, "mv_pack_matches: negative k_max");
+  pack_matches_kernel<<<(k_max + 255) / 256 + (k_max == 0 ? 1 : 0), 256, 0, mv_cuda_stream(stream)>>>(
+      sel_src, sel_dst, sel_weight, k_dev, k_max, xyz0, xyz1, uv0, uv1, n0_dev, n1_dev, out);
   MV_LAUNCH_CHECK();
   return MV_OK;
 }

@@ -183,7 +183,8 @@ class GraphedPairMatcher:
         C_._check_C(feat_shape[0])
         self.kind, self.num_corr = kind, int(num_corr)
         self.ratio_test, self.with_outputs = bool(ratio_test), bool(with_outputs)
-        self.packed = self.counts = self.host_packed = self.host_counts = None
+        self.packed = self.host_packed = None
+        self.k_max = 0
         self.dev = device or C_._device()
         if feat_layout == "hwc":
             C, h, w = feat_shape
@@ -209,14 +210,16 @@ class GraphedPairMatcher:
                                  lambda: C_.prepare_depth_side(self.f1, self.g1, self.Kh, self.Kinv, self.dev, sync=False), self.dev)
         r = C_._match_sides(s0, s1, s0.n, s1.n, self.num_corr, self.ratio_test, n_dev=s0.n_dev, m_dev=s1.n_dev)
         if self.with_outputs:
-            # the helper's return tuple, packed row-wise for a single device -> host copy:
-            # [xyz0 (3) | xyz1 (3) | weight (1) | uv0 (2) | uv1 (2)]; rows beyond the live k are not written
+            # the helper's return tuple + the live counts in one buffer of column blocks (mv_pack_matches):
+            # a single device -> host copy, and the host slices views out of it
             k = r.k
-            parts = [C_._gather(s0.xyz, r.sel_src, k, r.k_dev), C_._gather(s1.xyz, r.sel_dst, k, r.k_dev), r.sel_weight[:k, None]]
-            if self.kind == "xyz":
-                parts += [C_._gather(s0.uv, r.sel_src, k, r.k_dev), C_._gather(s1.uv, r.sel_dst, k, r.k_dev)]
-            self.packed = torch.cat(parts, dim=1)
-            self.counts = torch.cat((s0.n_dev, s1.n_dev, r.k_dev))
+            self.k_max = k
+            blocks = 11 if self.kind == "xyz" else 7
+            self.packed = torch.empty(blocks * k + 4, dtype=torch.float32, device=self.dev)
+            L.call("mv_pack_matches", L.ptr(r.sel_src), L.ptr(r.sel_dst), L.ptr(r.sel_weight), L.ptr(r.k_dev), k,
+                   L.ptr(s0.xyz), L.ptr(s1.xyz), L.ptr(s0.uv) if self.kind == "xyz" else None,
+                   L.ptr(s1.uv) if self.kind == "xyz" else None, L.ptr(s0.n_dev), L.ptr(s1.n_dev), L.ptr(self.packed),
+                   C_._stream())
         return s0, s1, r
 
     def capture(self):
@@ -233,15 +236,29 @@ class GraphedPairMatcher:
             self.out = self._body()
         if self.with_outputs:
             self.host_packed = torch.empty(self.packed.shape, dtype=torch.float32, pin_memory=True)
-            self.host_counts = torch.empty(3, dtype=torch.int32, pin_memory=True)
         return self
 
-    def load(self, feat_0, feat_1, grid_0, grid_1):
-        """stage one pair's inputs (any device; pinned host memory makes the copies asynchronous)."""
+    def load(self, feat_0, feat_1, grid_0, grid_1, two_streams=False):
+        """stage one pair's inputs (any device; pinned host memory makes the copies asynchronous).
+        two_streams: issue image 1's copies on a second stream -- two concurrent host -> device transfers use the
+        PCIe link better than one (measured: 463 -> ~390 us for the 19.6 MB of a NAVI-shaped pair)."""
+        if not two_streams:
+            self.f0.copy_(feat_0, non_blocking=True)
+            self.f1.copy_(feat_1, non_blocking=True)
+            self.g0.copy_(grid_0, non_blocking=True)
+            self.g1.copy_(grid_1, non_blocking=True)
+            return
+        cur = torch.cuda.current_stream(self.dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+        side = self._copy_stream
+        side.wait_stream(cur)  # the static buffers may still be read by the previous replay
+        with torch.cuda.stream(side):
+            self.f1.copy_(feat_1, non_blocking=True)
+            self.g1.copy_(grid_1, non_blocking=True)
         self.f0.copy_(feat_0, non_blocking=True)
-        self.f1.copy_(feat_1, non_blocking=True)
         self.g0.copy_(grid_0, non_blocking=True)
-        self.g1.copy_(grid_1, non_blocking=True)
+        cur.wait_stream(side)
 
     def run(self, acc=None, Rt=None, K=None):
         """replay the captured pipeline on the staged inputs; optionally score into `acc`."""
@@ -258,8 +275,7 @@ class GraphedPairMatcher:
     def launches_per_replay(self):
         # per image: (backproject) + compact + coords + chw_to_hwc + kernel 1; per pair: kernel 2 (2) + ratio + top-k
         per_side = (5 if self.kind == "depth" else 4) - (1 if self.feat_layout == "hwc" else 0)
-        gathers = (4 if self.kind == "xyz" else 2) if self.with_outputs else 0
-        return 2 * per_side + 4 + gathers
+        return 2 * per_side + 4 + (1 if self.with_outputs else 0)
 
 
 class PairPipeline:

@@ -43,7 +43,13 @@ def only_replay(p):
     torch.cuda.current_stream().synchronize()
 
 
+def only_load2(p):
+    gm.load(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], two_streams=True)
+    torch.cuda.current_stream().synchronize()
+
+
 print(f"H2D of one pair (19.6 MB pinned) + sync : {timed(only_load):7.1f} us")
+print(f"the same on two streams                 : {timed(only_load2):7.1f} us")
 print(f"graph replay + sync                     : {timed(only_replay):7.1f} us")
 print(f"H2D + replay + sync                     : {timed(load_replay):7.1f} us")
 print(f"full helper call                        : {timed(call):7.1f} us")
