@@ -605,7 +605,7 @@ int launch_k1_inst(const K1Params& p, cudaStream_t st) {
 }
 
 template <int MODE>
-int launch_k1_warp(const K1Params& p, cudaStream_t st) {
+int launch_k1(const K1Params& p, cudaStream_t st) {
   const int C = p.C;
   int outs = K1W_OUT_ANY;
   if (p.out_f32 && p.out_bf16 && !p.out_lo) outs = K1W_OUT_BOTH;
@@ -753,9 +753,9 @@ int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, cons
   p.taps = taps;
 
   cudaStream_t st = mv_cuda_stream(stream);
-  if (mode == MV_SAMPLE_BILINEAR_ZEROS) return launch_k1_warp<MV_SAMPLE_BILINEAR_ZEROS>(p, st);
-  if (mode == MV_SAMPLE_BICUBIC_CLAMP) return launch_k1_warp<MV_SAMPLE_BICUBIC_CLAMP>(p, st);
-  return launch_k1_warp<MV_SAMPLE_ROWS>(p, st);
+  if (mode == MV_SAMPLE_BILINEAR_ZEROS) return launch_k1<MV_SAMPLE_BILINEAR_ZEROS>(p, st);
+  if (mode == MV_SAMPLE_BICUBIC_CLAMP) return launch_k1<MV_SAMPLE_BICUBIC_CLAMP>(p, st);
+  return launch_k1<MV_SAMPLE_ROWS>(p, st);
 }
 
 }  // extern "C"
