@@ -42,16 +42,22 @@ constexpr int A_STAGE_BYTES = BM * ROW_BYTES;  // 16 KB
 // single-CTA tiles keep the whole 256-row B tile per stage (48 KB, 4 stages); a CTA pair (cta_group::2) keeps
 // only its half of B (32 KB, 6 stages): the tensor cores of both SMs read both halves
 constexpr int MAX_STAGES = 6;
-constexpr int RING_BYTES = 192 * 1024;
+#ifndef MV_K2_PAIR_STAGES
+// 6 stages = 192 KB ring.  4 stages (128 KB) run the NAVI shape equally fast (1298 vs 1303 TFLOP/s) and would let a
+// 72 KB kernel-1 CTA share the SM; measured in the 3-lane pipeline that co-residency LOSES 4 % pairs/s (the small
+// kernel-1 configuration is slower and kernel 2 drops from 1188 to 1160 TFLOP/s), so the deep ring stays.
+#define MV_K2_PAIR_STAGES 6
+#endif
 template <bool PAIR> struct Ring {
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_ROWS * ROW_BYTES;
-  static constexpr int STAGES = RING_BYTES / STAGE_BYTES;
+  static constexpr int STAGES = PAIR ? MV_K2_PAIR_STAGES : 4;
+  static constexpr int BYTES = STAGES * STAGE_BYTES;
 };
 constexpr int K2_THREADS = 384;   // 4 control warps + 8 epilogue warps
 constexpr int EPI_WARP0 = 4;
 constexpr int COL_SMEM_BYTES = 2 * 4 * BN * 8;  // [2 buffers][4 warps][256 columns] (max bits, ballot)
-constexpr int K2_SMEM_BYTES = 1024 /*align slack*/ + RING_BYTES + COL_SMEM_BYTES + 256 /*barriers*/;
+template <bool PAIR> constexpr int k2_smem_bytes() { return 1024 /*align slack*/ + Ring<PAIR>::BYTES + COL_SMEM_BYTES + 256 /*barriers*/; }
 
 struct K2Sched {
   // tiles are numbered t = sb * n_ct + ct; cluster c owns [c*T/G, (c+1)*T/G).  Built on the device from the
@@ -115,6 +121,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_al = smem_raw + (smem_base - smem_u32(smem_raw));
+  constexpr int RING_BYTES = Ring<PAIR>::BYTES;
   uint2* col_smem = reinterpret_cast<uint2*>(smem_al + RING_BYTES);
   Barriers* bars = reinterpret_cast<Barriers*>(smem_al + RING_BYTES + COL_SMEM_BYTES);
 
@@ -456,6 +463,7 @@ int k2_max_clusters() {
   if (cached) return cached;
   auto kern = k2_sim_top2_kernel<TF32, MC, PAIR>;
   int n = mv_sm_count() / MC;
+  constexpr int K2_SMEM_BYTES = k2_smem_bytes<PAIR>();
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_BYTES) == cudaSuccess && MC > 1) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(mv_sm_count() / MC * MC);
@@ -488,6 +496,7 @@ int k2_grid(int mc, bool tf32, bool pair = false) {
 template <bool TF32, int MC, bool PAIR = false>
 int launch_k2(const CUtensorMap& tmA, const CUtensorMap& tmB, const K2Params& p, int grid, cudaStream_t st) {
   auto kern = k2_sim_top2_kernel<TF32, MC, PAIR>;
+  constexpr int K2_SMEM_BYTES = k2_smem_bytes<PAIR>();
   static bool attr_done = false;
   if (!attr_done) {
     MV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_BYTES));
