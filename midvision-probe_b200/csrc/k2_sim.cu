@@ -557,6 +557,9 @@ int mv_k2_sim_top2(const void* A, const void* B, int n_max, int m_max, int C, co
   }
   const bool pair = cluster == MV_CLUSTER_PAIR;  // cta_group::2: two SMs on one 256 x 256 MMA tile
   const int mc = pair ? 2 : pick_mc(cluster);
+  // (5.4 tiles per SM at the NAVI shape leave 10 % of the last tile-time idle; running two pairs' kernel 2 side by
+  // side on half the SMs each -- 10.8 tiles per SM -- was measured: same pairs/s, the pipeline's other kernels
+  // already fill that tail)
   const int grid = k2_grid(mc, tf32, pair);
   K2Params p;
   p.clusters = grid / mc;
