@@ -61,8 +61,12 @@ __device__ __forceinline__ void split8(const __nv_bfloat16* hi, const __nv_bfloa
   }
 }
 
+// 128 threads = 4 queries per CTA: small CTAs keep the tail of the single wave short.  ncu (ratio_probe.py, NAVI
+// size): 123.5 MB of DRAM reads in 25.7 us (fp32 rows) / 32.5 us (split rows: twice the instructions for the
+// same bytes); both are latency-bound (long-scoreboard stalls), in the pipeline the two formats are within 2 %.
+constexpr int RATIO_THREADS = 128;
 template <typename ROWS>
-__global__ void __launch_bounds__(256) k3_ratio_mutual_kernel(ROWS rows, int C, const int32_t* __restrict__ n_dev, int n_max,
+__global__ void __launch_bounds__(RATIO_THREADS, 6) k3_ratio_mutual_kernel(ROWS rows, int C, const int32_t* __restrict__ n_dev, int n_max,
                                                               int32_t* __restrict__ row_idx,
                                                               const unsigned long long* __restrict__ col_best,
                                                               int ratio_test, float* __restrict__ dists,
@@ -87,6 +91,7 @@ __global__ void __launch_bounds__(256) k3_ratio_mutual_kernel(ROWS rows, int C, 
     }
   } else {
     const size_t ox = (size_t)i * C, o0 = (size_t)max(j0, 0) * C, o1 = (size_t)max(j1, 0) * C;
+#pragma unroll 2
     for (int c8 = lane; c8 < (C >> 3); c8 += 32) {
       float v[8], a[8], b[8];
       split8(rows.A_hi + ox, rows.A_lo + ox, c8, v);
@@ -456,7 +461,7 @@ int mv_k3_ratio_mutual(const float* A32, const float* B32, int C, const int32_t*
              "mv_k3_ratio_mutual: A32 and B32 must be 16-byte aligned");
   MV_REQUIRE(n_max >= 0, MV_E_ARG, "mv_k3_ratio_mutual: negative n_max");
   if (n_max == 0) return MV_OK;
-  const int rows_per_cta = 8;
+  const int rows_per_cta = RATIO_THREADS / 32;
   RowsF32 rows{A32, B32};
   k3_ratio_mutual_kernel<RowsF32><<<(n_max + rows_per_cta - 1) / rows_per_cta, 32 * rows_per_cta, 0, mv_cuda_stream(stream)>>>(
       rows, C, n_dev, n_max, row_idx, col_best, ratio_test, dists, weight, mutual);
@@ -473,7 +478,7 @@ int mv_k3_ratio_mutual_split(const uint16_t* A_hi, const uint16_t* A_lo, const u
              "mv_k3_ratio_mutual_split: the row planes must be 16-byte aligned");
   MV_REQUIRE(n_max >= 0, MV_E_ARG, "mv_k3_ratio_mutual_split: negative n_max");
   if (n_max == 0) return MV_OK;
-  const int rows_per_cta = 8;
+  const int rows_per_cta = RATIO_THREADS / 32;
   RowsSplit rows{reinterpret_cast<const __nv_bfloat16*>(A_hi), reinterpret_cast<const __nv_bfloat16*>(A_lo),
                  reinterpret_cast<const __nv_bfloat16*>(B_hi), reinterpret_cast<const __nv_bfloat16*>(B_lo)};
   k3_ratio_mutual_kernel<RowsSplit><<<(n_max + rows_per_cta - 1) / rows_per_cta, 32 * rows_per_cta, 0, mv_cuda_stream(stream)>>>(
