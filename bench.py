@@ -308,6 +308,9 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "tf32"])
     ap.add_argument("--cluster", type=int, default=int(os.environ.get("MVMATCH_CLUSTER", "-1")),
                     help="kernel 2 cluster mode: -1 auto, 1 single CTA, 2 / 4 B-tile multicast, 20 CTA pair (cta_group::2)")
+    ap.add_argument("--feat-dtype", default="f32", choices=["f32", "bf16"],
+                    help="dtype of the feature tensors handed to the path: f32 = the reference's convention (BASELINE config); "
+                         "bf16 = an autocast backbone's output, uploaded as 16-bit and widened on the device (supplementary)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stress", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
@@ -344,6 +347,11 @@ def main():
     pool_host = make_pool(syn, args.workload, rank, world, POOL)
     keys = [k for k in pool_host[0] if torch.is_tensor(pool_host[0][k])]
     big = ("feat_0", "feat_1", "xyz_grid_0", "xyz_grid_1", "depth_0", "depth_1")  # Rt / K are 3x4 host parameters, like in the callers
+    fdt = torch.bfloat16 if args.feat_dtype == "bf16" else torch.float32
+    if fdt != torch.float32:
+        for p in pool_host:
+            for k in ("feat_0", "feat_1"):
+                p[k] = p[k].to(fdt)
     if args.feat_layout == "hwc":
         for p in pool_host:
             for k in ("feat_0", "feat_1"):
@@ -368,7 +376,7 @@ def main():
     if not args.no_graph:
         p0 = pool_dev[0]
         gm = ev.PairPipeline("xyz" if args.workload == "navi" else "depth", tuple(p0["feat_0"].shape), tuple(p0[gk[0]].shape),
-                             NUM_CORR, K=p0.get("K"), device=dev, lanes=args.lanes, feat_layout=args.feat_layout)
+                             NUM_CORR, K=p0.get("K"), device=dev, lanes=args.lanes, feat_layout=args.feat_layout, feat_dtype=fdt)
 
     def pair_device(p):
         if gm is None:
@@ -511,7 +519,7 @@ def main():
             "dtype": args.dtype, "data": "synthetic",
             "config": {"workload": workload_name(args.workload), "pairs_per_step": PAIRS_PER_STEP, "pool_pairs": POOL,
                        "l2": "inputs larger than L2: 16 distinct pairs cycled, ~190 MB of features + rows touched per pair vs 126 MB L2",
-                       "k2_cluster": args.cluster, "cuda_graph": gm is not None, "pairs_in_flight": args.lanes if gm is not None else 1, "features": "seeded N(0,1) maps of the backbone's output shape", "feat_layout": args.feat_layout},
+                       "k2_cluster": args.cluster, "cuda_graph": gm is not None, "pairs_in_flight": args.lanes if gm is not None else 1, "features": "seeded N(0,1) maps of the backbone's output shape", "feat_layout": args.feat_layout, "feat_dtype": args.feat_dtype},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "api": "correspondence.estimate_correspondence_xyz(host tensors)" if args.workload == "navi"

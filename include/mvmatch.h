@@ -72,6 +72,15 @@ int mv_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int*
 int mv_chw_to_hwc(const float* src_chw, float* dst_hwc, int C, int hw, int prenorm, float* norm_scratch,
                   mv_stream_t stream);
 
+/* Backbone outputs in reduced precision (bf16 / fp16 under autocast) or already channel-last: any of
+ * {fp32, bf16, fp16} x {(C, hw) channel-major, (hw, C) channel-last} -> the fp32 channel-last map kernel 1 reads.
+ * The widening is exact: results equal the reference run on feats.float().  (the hand-off of the
+ * backbone output without the fp32 CPU round trip of evaluate_navi_correspondence.py:149-150.) */
+#define MV_FEAT_F32 0
+#define MV_FEAT_BF16 1
+#define MV_FEAT_F16 2
+int mv_feat_to_hwc_f32(const void* src, int dtype, int channel_last, int C, int hw, float* dst_hwc, mv_stream_t stream);
+
 /* Row-major stable compaction of the indices i in [0, n) with z[i * z_stride] > 0
  * (correspondence.py:221-222 `xyz[:, 2] > 0`, :247-252 `xyz_grid[2] > 0`).
  * valid_idx: n int32 (first *n_valid are live, ascending); n_valid: 1 int32.  n <= 2^20. */

@@ -19,6 +19,7 @@ PROTOTYPES = {
     "mv_last_error": (c_char_p, []),
     "mv_device_info": (c_int, [c_int, P, P, P, P]),
     "mv_chw_to_hwc": (c_int, [P, P, c_int, c_int, c_int, P, P]),
+    "mv_feat_to_hwc_f32": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
     "mv_compact_valid": (c_int, [P, c_int, c_int, P, P, P]),
     "mv_geom_backproject": (c_int, [P, c_int, c_int, P, P, P]),
     "mv_geom_project_coords": (c_int, [P, P, P, c_int, P, c_int, c_int, c_int, c_int, P, P, P]),
@@ -46,6 +47,7 @@ MV_SAMPLE_BICUBIC_CLAMP = 1
 MV_SAMPLE_ROWS = 2
 MV_DTYPE_BF16 = 0
 MV_DTYPE_TF32 = 1
+MV_FEAT_F32, MV_FEAT_BF16, MV_FEAT_F16 = 0, 1, 2
 MV_SIM_MASKED = -3.0e38
 MV_MAX_THRESHOLDS = 16
 
@@ -53,7 +55,7 @@ _lib = None
 
 # kernels launched per entry point (for bench.py's gpu_launches claim); memsets are not counted
 KERNELS_PER_CALL = {
-    "mv_chw_to_hwc": 1, "mv_compact_valid": 1, "mv_geom_backproject": 1, "mv_geom_project_coords": 1,
+    "mv_chw_to_hwc": 1, "mv_feat_to_hwc_f32": 1, "mv_compact_valid": 1, "mv_geom_backproject": 1, "mv_geom_project_coords": 1,
     "mv_geom_grid_coords": 1, "mv_geom_keypoint_coords": 1, "mv_k1_sample_normalize": 1, "mv_k2_sim_top2": 2,
     "mv_k2_unpack_col": 1, "mv_k3_ratio_mutual": 1, "mv_k3_ratio_mutual_split": 1, "mv_k3_topk_matches": 1, "mv_k3_score": 1, "mv_gather_rows": 1,
     "mv_pack_matches": 1, "mv_argmax_rows": 1, "mv_k3_spair_errors": 1, "mv_spair_match_batch": 1,

@@ -97,11 +97,14 @@ def _hwc(feat, prenorm=False):
     return out
 
 
+_FEAT_DTYPES = {torch.float32: L.MV_FEAT_F32, torch.bfloat16: L.MV_FEAT_BF16, torch.float16: L.MV_FEAT_F16}
+
+
 def _is_channel_last(feat):
     """True when a (C, h, w) tensor is a permuted view of contiguous (h, w, C) memory -- the layout ViT tokens
     have before tokens_to_output's .contiguous() (evals/models/utils.py:111-114) and channels_last CNN outputs."""
     C, h, w = feat.shape
-    return feat.dtype == torch.float32 and feat.stride() == (1, w * C, C) and not (h * w == 1 or C == 1)
+    return feat.dtype in _FEAT_DTYPES and feat.stride() == (1, w * C, C) and not (h * w == 1 or C == 1)
 
 
 def _feature_map(feat, dev, prenorm=False):
@@ -111,6 +114,14 @@ def _feature_map(feat, dev, prenorm=False):
     layout goes through mv_chw_to_hwc.  prenorm always runs the kernel (it rescales every pixel)."""
     C, h, w = feat.shape
     _check_C(C)
+    if feat.dtype in (torch.bfloat16, torch.float16) and not prenorm:
+        # autocast backbones: upload the 16-bit map as it is (half the bytes) and widen on the device (exact)
+        cl = _is_channel_last(feat)
+        f = feat.detach().to(device=dev, non_blocking=True)
+        f = f if (cl and _is_channel_last(f)) else f.contiguous()
+        out = _empty((h * w, C), torch.float32, dev)
+        L.call("mv_feat_to_hwc_f32", L.ptr(f), _FEAT_DTYPES[feat.dtype], int(cl), C, h * w, L.ptr(out), _stream())
+        return out, C, h, w
     if _is_channel_last(feat) and not prenorm:
         f = feat.detach().to(device=dev, non_blocking=True)
         if _is_channel_last(f):
@@ -597,8 +608,8 @@ def _join_side(side, dev, *objs):
 
 
 def _upload_feat(feat, dev):
-    """feature map to the device as fp32, keeping a channel-last layout if it has one."""
-    if _is_channel_last(feat):
+    """feature map to the device, keeping a channel-last layout and a 16-bit dtype if it has them."""
+    if _is_channel_last(feat) or feat.dtype in (torch.bfloat16, torch.float16):
         return feat.detach().to(device=dev, non_blocking=True)
     return _f32(feat, dev)
 
@@ -633,7 +644,8 @@ def _graphed_helper(kind, feat_0, feat_1, grid_0, grid_1, num_corr, ratio_test, 
     device -> host copy (results + the three live counts), i.e. a single host sync."""
     dev = _device()
     layout = "hwc" if (_is_channel_last(feat_0) and _is_channel_last(feat_1)) else "chw"
-    key = (kind, tuple(feat_0.shape), tuple(grid_0.shape), int(num_corr), bool(ratio_test), _CFG["dtype"], _CFG["cluster"], _CFG["rows"],
+    fdt = feat_0.dtype if (feat_0.dtype == feat_1.dtype and feat_0.dtype in _FEAT_DTYPES) else torch.float32
+    key = (kind, tuple(feat_0.shape), tuple(grid_0.shape), int(num_corr), bool(ratio_test), _CFG["dtype"], _CFG["cluster"], _CFG["rows"], fdt,
            None if K is None else tuple(K.detach().float().cpu().reshape(-1).tolist()), dev.index, layout)
     gm = _HELPER_GRAPHS.get(key)
     if gm is None:
@@ -643,7 +655,7 @@ def _graphed_helper(kind, feat_0, feat_1, grid_0, grid_1, num_corr, ratio_test, 
         if len(_HELPER_GRAPHS) >= _HELPER_GRAPHS_MAX:
             _HELPER_GRAPHS.pop(next(iter(_HELPER_GRAPHS)))
         gm = ev.GraphedPairMatcher(kind, tuple(feat_0.shape), tuple(grid_0.shape), num_corr, K=K, device=dev,
-                                   ratio_test=ratio_test, with_outputs=True, feat_layout=layout).capture()
+                                   ratio_test=ratio_test, with_outputs=True, feat_layout=layout, feat_dtype=fdt).capture()
         _HELPER_GRAPHS[key] = gm
     gm.load(feat_0, feat_1, grid_0, grid_1, two_streams=True)
     gm.graph.replay()

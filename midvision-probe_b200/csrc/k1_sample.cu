@@ -16,6 +16,8 @@
 // share in shared memory once (an 8x upsample re-uses each tap ~8 times along x), so the kernel's traffic is
 // the row writes: C*h*w*4 bytes read + n*C*(2 [+4]) bytes written.
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -105,6 +107,33 @@ __global__ void __launch_bounds__(256) chw_to_hwc_vec_kernel(const float* __rest
       *reinterpret_cast<float4*>(dst + (size_t)p * C + c) = v;
     }
   }
+}
+
+// Reduced-precision backbone outputs (bf16 / fp16 under autocast): widen to the fp32 channel-last map kernel 1
+// reads.  The widening is exact, so the result equals the reference run on feat.float().
+template <typename T> __device__ __forceinline__ float feat_to_float(T v);
+template <> __device__ __forceinline__ float feat_to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float feat_to_float<__half>(__half v) { return __half2float(v); }
+
+template <typename T>
+__global__ void chw_to_hwc_widen_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, int hw) {
+  __shared__ float tile[32][33];
+  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int dy = threadIdx.y; dy < 32; dy += 8) {
+    const int c = c0 + dy, p = p0 + threadIdx.x;
+    tile[dy][threadIdx.x] = (c < C && p < hw) ? feat_to_float<T>(src[(size_t)c * hw + p]) : 0.f;
+  }
+  __syncthreads();
+  for (int dy = threadIdx.y; dy < 32; dy += 8) {
+    const int p = p0 + dy, c = c0 + threadIdx.x;
+    if (c < C && p < hw) dst[(size_t)p * C + c] = tile[threadIdx.x][dy];
+  }
+}
+
+template <typename T>
+__global__ void widen_kernel(const T* __restrict__ src, float* __restrict__ dst, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = feat_to_float<T>(src[i]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -659,6 +688,34 @@ int mv_chw_to_hwc(const float* src_chw, float* dst_hwc, int C, int hw, int preno
   } else {
     dim3 grid((hw + 31) / 32, (C + 31) / 32);
     chw_to_hwc_kernel<<<grid, dim3(32, 8), 0, st>>>(src_chw, dst_hwc, C, hw, norm);
+  }
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+int mv_feat_to_hwc_f32(const void* src, int dtype, int channel_last, int C, int hw, float* dst_hwc, mv_stream_t stream) {
+  MV_REQUIRE(src && dst_hwc, MV_E_ARG, "mv_feat_to_hwc_f32: null pointer");
+  MV_REQUIRE(C > 0 && hw > 0, MV_E_ARG, "mv_feat_to_hwc_f32: C and hw must be positive");
+  MV_REQUIRE(dtype == MV_FEAT_F32 || dtype == MV_FEAT_BF16 || dtype == MV_FEAT_F16, MV_E_ARG,
+             "mv_feat_to_hwc_f32: unknown feature dtype %d", dtype);
+  cudaStream_t st = mv_cuda_stream(stream);
+  if (dtype == MV_FEAT_F32) {
+    if (channel_last) {
+      MV_CUDA(cudaMemcpyAsync(dst_hwc, src, (size_t)C * hw * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      return MV_OK;
+    }
+    return mv_chw_to_hwc(static_cast<const float*>(src), dst_hwc, C, hw, 0, nullptr, stream);
+  }
+  const size_t total = (size_t)C * hw;
+  if (channel_last) {
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (dtype == MV_FEAT_BF16) widen_kernel<<<blocks, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(src), dst_hwc, total);
+    else widen_kernel<<<blocks, 256, 0, st>>>(static_cast<const __half*>(src), dst_hwc, total);
+  } else {
+    dim3 grid((hw + 31) / 32, (C + 31) / 32);
+    if (dtype == MV_FEAT_BF16)
+      chw_to_hwc_widen_kernel<<<grid, dim3(32, 8), 0, st>>>(static_cast<const __nv_bfloat16*>(src), dst_hwc, C, hw);
+    else chw_to_hwc_widen_kernel<<<grid, dim3(32, 8), 0, st>>>(static_cast<const __half*>(src), dst_hwc, C, hw);
   }
   MV_LAUNCH_CHECK();
   return MV_OK;

@@ -171,7 +171,7 @@ class GraphedPairMatcher:
     """
 
     def __init__(self, kind, feat_shape, grid_shape, num_corr, K=None, device=None, ratio_test=True, with_outputs=False,
-                 feat_layout="chw"):
+                 feat_layout="chw", feat_dtype=torch.float32):
         """feat_layout: memory layout of the static feature buffers -- "chw" (the reference's contiguous
         (C, h, w)) or "hwc" (channel-last views, the layout ViT tokens / channels_last CNN outputs already have:
         loading such features is a flat copy and the transpose kernel is skipped)."""
@@ -180,6 +180,7 @@ class GraphedPairMatcher:
         if feat_layout not in ("chw", "hwc"):
             raise ValueError(feat_layout)
         self.feat_layout = feat_layout
+        self.feat_dtype = feat_dtype  # torch.bfloat16 / float16: 16-bit static buffers, widened on the device
         C_._check_C(feat_shape[0])
         self.kind, self.num_corr = kind, int(num_corr)
         self.ratio_test, self.with_outputs = bool(ratio_test), bool(with_outputs)
@@ -188,11 +189,11 @@ class GraphedPairMatcher:
         self.dev = device or C_._device()
         if feat_layout == "hwc":
             C, h, w = feat_shape
-            self.f0 = torch.zeros((h, w, C), dtype=torch.float32, device=self.dev).permute(2, 0, 1)
-            self.f1 = torch.zeros((h, w, C), dtype=torch.float32, device=self.dev).permute(2, 0, 1)
+            self.f0 = torch.zeros((h, w, C), dtype=feat_dtype, device=self.dev).permute(2, 0, 1)
+            self.f1 = torch.zeros((h, w, C), dtype=feat_dtype, device=self.dev).permute(2, 0, 1)
         else:
-            self.f0 = torch.zeros(feat_shape, dtype=torch.float32, device=self.dev)
-            self.f1 = torch.zeros(feat_shape, dtype=torch.float32, device=self.dev)
+            self.f0 = torch.zeros(feat_shape, dtype=feat_dtype, device=self.dev)
+            self.f1 = torch.zeros(feat_shape, dtype=feat_dtype, device=self.dev)
         self.g0 = torch.zeros(grid_shape, dtype=torch.float32, device=self.dev)
         self.g1 = torch.zeros(grid_shape, dtype=torch.float32, device=self.dev)
         if kind == "depth":
@@ -274,7 +275,8 @@ class GraphedPairMatcher:
     @property
     def launches_per_replay(self):
         # per image: (backproject) + compact + coords + chw_to_hwc + kernel 1; per pair: kernel 2 (2) + ratio + top-k
-        per_side = (5 if self.kind == "depth" else 4) - (1 if self.feat_layout == "hwc" else 0)
+        zero_copy = self.feat_layout == "hwc" and self.feat_dtype == torch.float32
+        per_side = (5 if self.kind == "depth" else 4) - (1 if zero_copy else 0)
         return 2 * per_side + 4 + (1 if self.with_outputs else 0)
 
 
@@ -289,14 +291,15 @@ class PairPipeline:
         pipe.join()
     """
 
-    def __init__(self, kind, feat_shape, grid_shape, num_corr, K=None, device=None, lanes=2, feat_layout="chw"):
+    def __init__(self, kind, feat_shape, grid_shape, num_corr, K=None, device=None, lanes=2, feat_layout="chw",
+                 feat_dtype=torch.float32):
         self.dev = device or C_._device()
         self.lanes = []
         for _ in range(max(1, int(lanes))):
             st = torch.cuda.Stream(device=self.dev)
             with torch.cuda.stream(st):
                 gm = GraphedPairMatcher(kind, feat_shape, grid_shape, num_corr, K=K, device=self.dev,
-                                        feat_layout=feat_layout).capture()
+                                        feat_layout=feat_layout, feat_dtype=feat_dtype).capture()
             self.lanes.append((st, gm))
         torch.cuda.synchronize(self.dev)
         self.turn = 0

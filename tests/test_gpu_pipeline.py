@@ -310,3 +310,38 @@ def test_channel_last_features_take_the_zero_copy_path(mv, syn):
         gm.run(acc, p["Rt"], p["intrinsics"])
         accs.append(acc.hits.cpu())
     assert torch.equal(accs[0], accs[1]) and int(accs[0][0]) == 200
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_16bit_feature_maps_equal_their_fp32_widening(mv, syn, dt):
+    """autocast backbones hand over bf16 / fp16 maps: they are uploaded as they are (half the bytes) and widened on
+    the device, which is exact -- the outputs must be bit-identical to the call with feat.float(), in both memory
+    layouts, through the eager helper, the cached-graph helper and the 16-bit static buffers of the graph matcher."""
+    C_, ev = mv.correspondence, mv.evaluation
+    p = syn.navi_pair(13, C=256, h=12, w=12, H=48, W=48, radius=18.0)
+    f0, f1 = p["feat_0"].to(dt), p["feat_1"].to(dt)
+    cl = lambda t: t.permute(1, 2, 0).contiguous().permute(2, 0, 1)
+    for graphs in (0, 1):
+        C_.set_match_precision(helper_graphs=graphs)
+        try:
+            want = C_.estimate_correspondence_xyz(f0.float(), f1.float(), p["xyz_grid_0"], p["xyz_grid_1"], 200)
+            for a, b in ((f0, f1), (cl(f0), cl(f1))):
+                got = C_.estimate_correspondence_xyz(a, b, p["xyz_grid_0"], p["xyz_grid_1"], 200)
+                for x, y in zip(want, got):
+                    assert torch.equal(x, y)
+        finally:
+            C_.set_match_precision(helper_graphs=1)
+    d = syn.scannet_pair(14, C=64, h=6, w=8, H=24, W=32)
+    g0, g1 = d["feat_0"].to(dt).cuda(), d["feat_1"].to(dt).cuda()
+    want = C_.estimate_correspondence_depth(g0.float(), g1.float(), d["depth_0"].cuda(), d["depth_1"].cuda(), d["K"], 100)
+    got = C_.estimate_correspondence_depth(g0, g1, d["depth_0"].cuda(), d["depth_1"].cuda(), d["K"], 100)
+    for x, y in zip(want, got):
+        assert torch.equal(x, y)
+    accs = []
+    for fdt, a, b in ((torch.float32, f0.float(), f1.float()), (dt, f0, f1)):
+        acc = ev.RecallAccumulator([0.01, 0.02], [5, 25], device=torch.device("cuda"))
+        gm = ev.GraphedPairMatcher("xyz", tuple(f0.shape), tuple(p["xyz_grid_0"].shape), 200, feat_dtype=fdt).capture()
+        gm.load(a.cuda(), b.cuda(), p["xyz_grid_0"].cuda(), p["xyz_grid_1"].cuda())
+        gm.run(acc, p["Rt"], p["intrinsics"])
+        accs.append(acc.hits.cpu())
+    assert torch.equal(accs[0], accs[1]) and int(accs[0][0]) == 200
