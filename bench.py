@@ -144,7 +144,7 @@ def cpu_pairs_per_s(syn, workload, budget_s=12.0, max_pairs=6):
     return done / t_total, done, torch.get_num_threads()
 
 
-SPAIR_BATCH = 512  # pairs per step (one launch); 1.2 MB of features per pair -> 617 MB per step, far beyond L2
+SPAIR_BATCH = 1184  # pairs per step (one launch) = 4 waves of 2 CTAs x 148 SMs; 1.2 MB of features per pair -> 1.4 GB per step
 
 
 def run_spair(args, rank, local_rank, world):
@@ -222,7 +222,7 @@ def run_spair(args, rank, local_rank, world):
             "data": "synthetic",
             "config": {"workload": "SPair-shaped pairs: (2, 768, 14, 14) features, 20 key points, fused batched matching "
                                    "(BASELINE.json configs[0])", "pairs_per_step": B,
-                       "l2": "inputs larger than L2: 617 MB of features per step", "features": "seeded maps of the backbone's output shape"},
+                       "l2": "inputs larger than L2: 1.4 GB of features per step", "features": "seeded maps of the backbone's output shape"},
             "clocks": clocks,
             "e2e": {"value": e2e, "unit": "pairs/s", "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host.values()),
                     "d2h_bytes_per_step": sum(o.numel() * o.element_size() for o in out), "steps": args.steps,
