@@ -33,7 +33,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-PAIRS_PER_STEP = 8
+PAIRS_PER_STEP = 32
 POOL = 16          # distinct pairs cycled through; their working set (~190 MB / pair) exceeds the 126 MB L2
 NUM_CORR = 1000
 THR3 = [0.01, 0.02, 0.05]
