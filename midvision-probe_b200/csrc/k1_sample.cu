@@ -654,7 +654,9 @@ int launch_k1(const K1Params& p, cudaStream_t st) {
   K1W_CASE(768, 6, 1, 4, 128, 3)    // ViT-B
   K1W_CASE(1024, 4, 2, 4, 256, 2)   // ViT-L
   K1W_CASE(2048, 4, 4, 4, 256, 2)   // ResNet-50 layer4
+  K1W_CASE(1536, 6, 2, 2, 256, 2)   // ViT-S 4-block concat
   K1W_CASE(3072, 24, 1, 1, 192, 2)  // ViT-B 4-block concat
+  K1W_CASE(4096, 8, 4, 2, 256, 2)   // ViT-L 4-block concat
 #undef K1W_CASE
   return launch_k1_inst<MODE, 0, 1, 1, K1W_OUT_ANY, 256, 2>(p, st);
 }

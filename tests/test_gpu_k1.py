@@ -47,7 +47,9 @@ def test_compact_valid_is_bit_exact(mv, n, stride, p_valid):
     assert torch.equal(idx[: want.numel()].cpu(), want)
 
 
-@pytest.mark.parametrize("shape", [dict(C=64, h=6, w=8, H=24, W=32), dict(C=2048, h=15, w=20, H=120, W=160)])
+@pytest.mark.parametrize("shape", [dict(C=64, h=6, w=8, H=24, W=32), dict(C=2048, h=15, w=20, H=120, W=160),
+                                   dict(C=768, h=6, w=8, H=48, W=64), dict(C=1024, h=6, w=8, H=48, W=64),
+                                   dict(C=1536, h=6, w=8, H=24, W=32), dict(C=4096, h=6, w=8, H=48, W=64)])
 def test_depth_side_matches_oracle(C_, mv, syn, shape):
     p = syn.scannet_pair(3, coherent=False, **shape)
     K = p["K"]
@@ -68,7 +70,9 @@ def test_depth_side_matches_oracle(C_, mv, syn, shape):
 
 
 @pytest.mark.parametrize("shape", [dict(C=64, h=8, w=8, H=32, W=32, radius=12.0), dict(C=3072, h=28, w=28, H=112, W=112, radius=40.0),
-                                   dict(C=768, h=7, w=9, H=30, W=41, radius=14.0)])
+                                   dict(C=768, h=7, w=9, H=30, W=41, radius=14.0), dict(C=1024, h=9, w=9, H=36, W=36, radius=14.0),
+                                   dict(C=1536, h=8, w=8, H=32, W=32, radius=12.0), dict(C=4096, h=8, w=8, H=16, W=16, radius=7.0),
+                                   dict(C=2048, h=8, w=8, H=64, W=64, radius=30.0)])
 def test_xyz_side_matches_oracle(C_, syn, shape):
     p = syn.navi_pair(5, coherent=False, **shape)
     xyz_o, f_o, uv_o, keep_o = restated.xyz_side(p["feat_0"], p["xyz_grid_0"])
