@@ -73,8 +73,10 @@ def main():
                         grid=np32(ref.get_grid(3, 5)), uv=np32(uv))
 
     p = syn.spair_pair(7, **SPAIR_SMALL)
-    es, en, isame, inn, heat = restated.spair_compute_errors(p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"], p["image_size"], return_pred=True)
-    np.savez_compressed(os.path.join(OUT, "spair_small.npz"), source="restated (reference script not importable: hydra + CUDA)",
+    # the reference's own compute_errors (evaluate_spair_correspondence.py:45-103), hydra / omegaconf stubbed and
+    # .cuda() mapped to the identity (oracle/reference_loader.py)
+    es, en, isame, inn, heat = reference_loader.spair_compute_errors_reference(p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"], p["image_size"])
+    np.savez_compressed(os.path.join(OUT, "spair_small.npz"), source="reference",
                         index=7, error_same=np32(es), error_nn=np32(en), index_same=np32(isame), index_nn=np32(inn),
                         pred=np32(restated.argmax_2d(heat)))
     for f in sorted(os.listdir(OUT)):

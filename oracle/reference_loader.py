@@ -27,3 +27,50 @@ def load():
     corr = importlib.import_module("evals.utils.correspondence")
     tr = importlib.import_module("evals.utils.transformations")
     return corr, tr
+
+
+def load_spair():
+    """-> the reference's own `compute_errors` / `evaluate_dataset` (evaluate_spair_correspondence.py:45-123),
+    unmodified.  The script imports hydra / omegaconf (not installed here) only for its `main`; both are
+    replaced by empty stand-ins.  `compute_errors` moves tensors with `.cuda()`, which has no meaning in the
+    GPU-less build container: use `spair_compute_errors_reference`, which maps `.cuda()` to the identity
+    for the duration of the call."""
+    if not available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    import types
+
+    if "hydra" not in sys.modules:
+        hydra = types.ModuleType("hydra")
+        hydra.main = lambda *a, **k: (lambda fn: fn)
+        hydra_utils = types.ModuleType("hydra.utils")
+        hydra_utils.instantiate = lambda *a, **k: None
+        hydra.utils = hydra_utils
+        sys.modules["hydra"], sys.modules["hydra.utils"] = hydra, hydra_utils
+    if "omegaconf" not in sys.modules:
+        oc = types.ModuleType("omegaconf")
+        oc.DictConfig, oc.OmegaConf = dict, type("OmegaConf", (), {})
+        sys.modules["omegaconf"] = oc
+    from . import faiss_shim
+
+    faiss_shim.install()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    return importlib.import_module("evaluate_spair_correspondence")
+
+
+def spair_compute_errors_reference(feats, kps_i, kps_j, thresh_scale, image_size):
+    """run the reference's compute_errors on given backbone features: the `model` is a stand-in that returns
+    `feats`, the images / masks are blanks of the right size (masks are only used with mask_feats=True)."""
+    import numpy as np
+    import torch
+
+    mod = load_spair()
+    img = torch.zeros(3, image_size, image_size)
+    mask = np.ones((image_size, image_size), dtype=float)
+    instance = (img, mask, kps_i.clone(), img, mask, kps_j.clone(), thresh_scale, None)
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        return mod.compute_errors(lambda images: feats.clone(), instance, return_heatmaps=True)
+    finally:
+        torch.Tensor.cuda = real_cuda

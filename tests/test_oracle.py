@@ -89,6 +89,22 @@ def test_restated_equals_reference_on_fresh_inputs(syn):
     torch.testing.assert_close(ref_tr.transform_points_Rt(pts, Rt), restated.transform_points_Rt(pts, Rt), rtol=0, atol=0)
 
 
+@pytest.mark.skipif(not reference_loader.available(), reason="reference tree not on this machine")
+@pytest.mark.parametrize("kw", [dict(C=768, h=14, w=14, K=20, image_size=224), dict(C=64, h=50, w=50, K=30, image_size=800),
+                                dict(C=40, h=5, w=7, K=3, image_size=64)])
+def test_spair_restated_equals_the_reference_script(syn, kw):
+    """the reference's own compute_errors (evaluate_spair_correspondence.py:45-103; hydra / omegaconf stubbed,
+    .cuda() mapped to the identity, the model replaced by its output) against the restatement: identical."""
+    for i in range(3):
+        p = syn.spair_pair(30 + i, **kw)
+        a = reference_loader.spair_compute_errors_reference(p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"], p["image_size"])
+        b = restated.spair_compute_errors(p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"], p["image_size"], return_pred=True)
+        for x, y in zip(a, b):
+            assert x.shape == y.shape
+            torch.testing.assert_close(x.float(), y.float(), rtol=0, atol=1e-6)
+        assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+
+
 def test_mutual_oracle_is_self_consistent():
     gen = torch.Generator().manual_seed(1)
     X = torch.randn(50, 16, generator=gen)
