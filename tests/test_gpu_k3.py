@@ -290,3 +290,32 @@ def test_spair_batch_equals_per_pair_path_and_edge_cases(mv, syn):
     assert e[0].shape == (5, 0)
     with pytest.raises(ValueError):
         sp.compute_errors_batch(feats[0], ki, kj, ts, 224)
+
+
+def test_spair_paths_vs_reference_golden(mv, syn, golden):
+    """both SPair paths against tests/golden/spair_small.npz, the output of the reference's own compute_errors."""
+    from oracle.make_golden import SPAIR_SMALL
+
+    g = golden("spair_small")
+    p = syn.spair_pair(int(g["index"]), **SPAIR_SMALL)
+    want_same, want_nn = torch.from_numpy(g["error_same"]), torch.from_numpy(g["error_nn"])
+    want_isame, want_inn = torch.from_numpy(g["index_same"]).long(), torch.from_numpy(g["index_nn"]).long()
+    es, en, inn, pred = mv.spair.compute_errors_batch(p["feats"][None], p["kps_i"][None], p["kps_j"][None], [p["thresh_scale"]],
+                                                      p["image_size"])
+    es, en, inn = es[0].cpu(), en[0].cpu(), inn[0].cpu().long()
+    keep = (es >= 0).nonzero().squeeze(1)
+    assert torch.equal(keep, want_isame)
+    torch.testing.assert_close(es[keep], want_same, rtol=0, atol=1e-5)
+    torch.testing.assert_close(en[keep], want_nn, rtol=0, atol=1e-5)
+    assert torch.equal(inn[keep], want_inn)
+    w = p["feats"].shape[-1]
+    pr = pred[0].cpu().long()
+    assert torch.equal(torch.stack((pr % w, pr // w), dim=1), torch.from_numpy(g["pred"]).long())
+    mv.correspondence.set_match_precision(dtype="tf32")
+    try:
+        a = mv.spair.compute_errors_from_features(p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"], p["image_size"])
+    finally:
+        mv.correspondence.set_match_precision(dtype="bf16")
+    assert torch.equal(a[2], want_isame)
+    same = a[3] == want_inn
+    assert same.float().mean() >= 0.9   # tf32 ranking: only near-ties of the heat map may differ
