@@ -74,3 +74,31 @@ def spair_compute_errors_reference(feats, kps_i, kps_j, thresh_scale, image_size
         return mod.compute_errors(lambda images: feats.clone(), instance, return_heatmaps=True)
     finally:
         torch.Tensor.cuda = real_cuda
+
+
+def spair_evaluate_dataset_reference(pairs, thresh=0.10):
+    """the reference's evaluate_dataset (evaluate_spair_correspondence.py:106-123) over a list of synthetic pairs
+    (dicts with feats, kps_i, kps_j, thresh_scale, image_size): -> (recall, confusion)."""
+    import numpy as np
+    import torch
+
+    mod = load_spair()
+    calls = {"i": 0}
+
+    class Data:
+        def __len__(self):
+            return len(pairs)
+
+        def __getitem__(self, i):
+            p = pairs[i]
+            calls["i"] = i
+            img = torch.zeros(3, p["image_size"], p["image_size"])
+            mask = np.ones((p["image_size"], p["image_size"]), dtype=float)
+            return (img, mask, p["kps_i"].clone(), img, mask, p["kps_j"].clone(), p["thresh_scale"], None)
+
+    real_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        return mod.evaluate_dataset(lambda images: pairs[calls["i"]]["feats"].clone(), Data(), thresh)
+    finally:
+        torch.Tensor.cuda = real_cuda

@@ -105,6 +105,24 @@ def test_spair_restated_equals_the_reference_script(syn, kw):
         assert torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
 
 
+@pytest.mark.skipif(not reference_loader.available(), reason="reference tree not on this machine")
+def test_spair_dataset_recall_and_confusion_equal_the_reference(syn):
+    """evaluate_dataset of the reference script (recall + confusion matrix over a list of pairs) against the same
+    quantities assembled from the restatement, the way the GPU tests assemble their expectation."""
+    pairs = [syn.spair_pair(i) for i in range(6)]
+    rec, conf = reference_loader.spair_evaluate_dataset_reference(pairs, 0.10)
+    errs, src, tgt = [], [], []
+    for p in pairs:
+        es, en, isame, inn = restated.spair_compute_errors(p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"], p["image_size"])
+        errs.append(es); src.append(isame); tgt.append(inn)
+    errs, src, tgt = torch.cat(errs), torch.cat(src), torch.cat(tgt)
+    want = torch.zeros_like(conf)
+    for a, b in zip(src.tolist(), tgt.tolist()):
+        want[a, b] += 1
+    assert torch.equal(conf, want)
+    assert abs(rec - 100.0 * (errs < 0.10).float().mean().item()) < 1e-4
+
+
 def test_mutual_oracle_is_self_consistent():
     gen = torch.Generator().manual_seed(1)
     X = torch.randn(50, 16, generator=gen)
