@@ -13,6 +13,12 @@ void mv_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int mv_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) dev = 0;
+  return dev % MV_MAX_DEVICES;
+}
+
 int mv_sm_count() {
   static int cached[64] = {0};
   int dev = 0;

@@ -40,6 +40,8 @@ void mv_set_error(const char* fmt, ...);
 static inline cudaStream_t mv_cuda_stream(mv_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int mv_sm_count();  // cached multiprocessor count of the current device
+int mv_device_slot();  // index of the current device in [0, 64) for per-device caches (function attributes are per device)
+constexpr int MV_MAX_DEVICES = 64;
 
 // ---- device helpers ---------------------------------------------------------------------
 #define MV_MASKED_F (-3.0e38f)

@@ -616,7 +616,9 @@ int launch_k1_inst(const K1Params& p, cudaStream_t st) {
   if (grid > p.n_max) grid = p.n_max;
   if (grid < 1) grid = 1;
   auto kern = k1_rows_kernel<MODE, NITW, W, G, OUTS, THREADS, MINB>;
-  static size_t opted_in = 44 << 10;  // per instantiation: the attribute belongs to the device function
+  static size_t opted[MV_MAX_DEVICES];  // per instantiation and device: the attribute belongs to the device function
+  size_t& opted_in = opted[mv_device_slot()];
+  if (opted_in < (44u << 10)) opted_in = 44 << 10;
   if (smem > opted_in) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {

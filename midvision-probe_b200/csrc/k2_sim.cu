@@ -459,7 +459,8 @@ int pick_mc(int cluster) { return cluster <= 1 ? 1 : (cluster >= 4 ? 4 : 2); }
 // boundaries strand SMs for cluster sizes that do not divide a GPC), or the grid runs in two waves
 template <bool TF32, int MC, bool PAIR = false>
 int k2_max_clusters() {
-  static int cached = 0;
+  static int cache[MV_MAX_DEVICES];
+  int& cached = cache[mv_device_slot()];
   if (cached) return cached;
   auto kern = k2_sim_top2_kernel<TF32, MC, PAIR>;
   int n = mv_sm_count() / MC;
@@ -497,7 +498,8 @@ template <bool TF32, int MC, bool PAIR = false>
 int launch_k2(const CUtensorMap& tmA, const CUtensorMap& tmB, const K2Params& p, int grid, cudaStream_t st) {
   auto kern = k2_sim_top2_kernel<TF32, MC, PAIR>;
   constexpr int K2_SMEM_BYTES = k2_smem_bytes<PAIR>();
-  static bool attr_done = false;
+  static bool done[MV_MAX_DEVICES];
+  bool& attr_done = done[mv_device_slot()];
   if (!attr_done) {
     MV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, K2_SMEM_BYTES));
     attr_done = true;

@@ -225,7 +225,9 @@ template <int KT>
 int launch_spair_batch(const SpairBatchParams& p, cudaStream_t st) {
   const size_t smem = (size_t)p.C * KT * sizeof(float);
   auto kern = spair_batch_kernel<KT>;
-  static size_t opted_in = 24 << 10;  // static + dynamic shared memory above 48 KB needs the opt-in
+  static size_t opted[MV_MAX_DEVICES];  // per device; static + dynamic shared memory above 48 KB needs the opt-in
+  size_t& opted_in = opted[mv_device_slot()];
+  if (opted_in < (24u << 10)) opted_in = 24 << 10;
   if (smem > opted_in) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {

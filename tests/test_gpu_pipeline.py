@@ -345,3 +345,22 @@ def test_16bit_feature_maps_equal_their_fp32_widening(mv, syn, dt):
         gm.run(acc, p["Rt"], p["intrinsics"])
         accs.append(acc.hits.cpu())
     assert torch.equal(accs[0], accs[1]) and int(accs[0][0]) == 200
+
+
+def test_second_device_in_the_same_process(mv, syn):
+    """function attributes (large shared-memory opt-ins, cluster occupancy) are cached per device: a process that
+    uses cuda:0 and then cuda:1 must get the same results on both."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    C_ = mv.correspondence
+    p = syn.navi_pair(15, C=3072, h=12, w=12, H=48, W=48, radius=18.0)
+    outs = []
+    for d in (0, 1):
+        with torch.cuda.device(d):
+            outs.append([t.cpu() for t in C_.estimate_correspondence_xyz(p["feat_0"].cuda(d), p["feat_1"].cuda(d), p["xyz_grid_0"].cuda(d),
+                                                                        p["xyz_grid_1"].cuda(d), 300)])
+            s = syn.spair_pair(3)
+            e = mv.spair.compute_errors_batch(s["feats"][None].cuda(d), s["kps_i"][None], s["kps_j"][None], [s["thresh_scale"]], 224)
+            outs[-1].append(e[3].cpu())
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
