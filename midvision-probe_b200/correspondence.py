@@ -249,21 +249,25 @@ def _rows_from_features(F, normalize, dev):
 # reference interface: nearest neighbours
 # ------------------------------------------------------------------------------------------------
 def faiss_knn(query, target, k):
-    """L2 k-NN, k <= 2: (squared L2 distances ascending, int64 indices).  correspondence.py:14-23.
+    """L2 k-NN: (squared L2 distances ascending, int64 indices).  correspondence.py:14-23.
+    k <= 2 (every call site) runs on kernel 2; larger k takes the exact blocked search of _exact_knn_blocks.
 
     Neighbours are ranked at tf32 precision (kernel 2), their distances recomputed in fp32.
     The search runs on kernel 2 through the identity ||q-t||^2 = ||q||^2 + ||t||^2 - 2 q.t : the rows are
     extended by (1, -||t||^2/2) split into tf32-exact pieces so that the inner-product order is the L2
     order; the returned distances are recomputed in fp32 for the winners.
     """
-    if k not in (1, 2):
-        raise NotImplementedError("the B200 path keeps the two nearest neighbours per query (k <= 2)")
     dev = _device()
     in_dev = query.device
     q = _f32(query, dev)
     t = _f32(target, dev)
     n, C = q.shape
     m = t.shape[0]
+    if k > 2:
+        d, idx = _exact_knn_blocks(q, t, int(k))
+        return d.to(in_dev), idx.to(in_dev)
+    if k < 1:
+        raise ValueError("k must be positive")
     # extra columns: q' = [q, 1, 1, 1, 0..], t' = [t, h0, h1, h2, 0..] with h0+h1+h2 = -||t||^2/2, each piece
     # holding <= 10 mantissa bits so the tf32 tensor-core product does not round it
     half = -0.5 * (t * t).sum(dim=1)
@@ -297,18 +301,51 @@ def faiss_knn(query, target, k):
     return d.to(in_dev), idx.to(in_dev)
 
 
+def _exact_knn_blocks(q, t, k):
+    """k > 2 neighbours (no call site in the reference asks for them): exact fp32 squared-L2 top-k on the device in
+    row blocks, ||q||^2 - 2 q.t + ||t||^2 like faiss's flat index.  Not the fused kernel -- kernel 2's epilogue
+    keeps two candidates per row -- but it keeps the interface complete without a CPU path."""
+    k = min(k, t.shape[0])
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        tn = (t * t).sum(dim=1)
+        ds, ids = [], []
+        for r0 in range(0, q.shape[0], 4096):
+            qb = q[r0:r0 + 4096]
+            d2 = (qb * qb).sum(dim=1, keepdim=True) - 2.0 * (qb @ t.t()) + tn[None, :]
+            d, i = torch.topk(d2, k, dim=1, largest=False, sorted=True)
+            ds.append(d)
+            ids.append(i)
+        if not ds:
+            return q.new_zeros((0, k)), torch.zeros((0, k), dtype=torch.int64, device=q.device)
+        return torch.cat(ds), torch.cat(ids)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
 def knn_points(X_f, Y_f, K=1, metric="euclidean"):
-    """(dists (N, K), idx (N, K) int64), K <= 2.  correspondence.py:26-60.
+    """(dists (N, K), idx (N, K) int64).  correspondence.py:26-60.
 
     cosine: rows are L2-normalised, neighbours come from kernel 2 and the distances 1 - cos are
     recomputed in fp32 by kernel 3, exactly the reference's order of operations (:47-58).
     euclidean: exact L2 neighbours through faiss_knn, distances = ||x - y||_2 (:55-56).
+    K > 2 (no call site in the reference) takes the exact blocked search of _exact_knn_blocks.
     """
     assert metric in ["cosine", "euclidean"]
-    if K not in (1, 2):
-        raise NotImplementedError("the B200 path keeps the two nearest neighbours per query (K <= 2)")
     dev = _device()
     in_dev = X_f.device
+    if K > 2:
+        X, Y = _f32(X_f, dev), _f32(Y_f, dev)
+        if metric == "cosine":
+            X, Y = torch.nn.functional.normalize(X, dim=-1), torch.nn.functional.normalize(Y, dim=-1)
+        _, idx = _exact_knn_blocks(X, Y, int(K))
+        gathered = Y[idx]
+        if metric == "euclidean":
+            d = (gathered - X[:, None, :]).norm(p=2, dim=2)
+        else:
+            d = 1 - torch.nn.functional.cosine_similarity(gathered, X[:, None, :], dim=-1)
+        return d.to(in_dev), idx.to(in_dev)
     if metric == "euclidean":
         _, idx = faiss_knn(X_f, Y_f, K)
         X = _f32(X_f, dev)

@@ -114,6 +114,23 @@ def test_faiss_knn_and_euclidean(mv):
     assert torch.equal(ie[clear, 0], oi[clear, 0])
 
 
+def test_more_than_two_neighbours(mv):
+    """K > 2 (no call site in the reference): exact blocked search on the device, same interface."""
+    gen = torch.Generator().manual_seed(33)
+    X = torch.randn(500, 48, generator=gen)
+    Y = torch.randn(700, 48, generator=gen)
+    d, i = mv.correspondence.faiss_knn(X, Y, 5)
+    od, oi = restated.exact_l2_knn(X, Y, 5)
+    assert i.dtype == torch.int64 and i.shape == (500, 5)
+    assert (i == oi).float().mean() > 0.999
+    torch.testing.assert_close(d, od, rtol=1e-4, atol=1e-3)
+    for metric in ("cosine", "euclidean"):
+        dk, ik = mv.correspondence.knn_points(X, Y, 4, metric)
+        odk, oik = restated.knn_points(X, Y, 4, metric)
+        assert (ik == oik).float().mean() > 0.999
+        torch.testing.assert_close(dk, odk, rtol=1e-4, atol=1e-5)
+
+
 def test_ratio_test_euclidean_metric(mv):
     """metric="euclidean" of get_correspondences_ratio_test (correspondence.py:63-102; no call site in the
     reference, kept for interface parity) against the oracle's literal restatement."""

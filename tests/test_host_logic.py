@@ -98,14 +98,16 @@ def test_pure_helpers_match_oracle(mv, golden):
     assert len(auc) == 2 and 0 < auc[0] < 1 and auc[1] > auc[0]
 
 
-def test_cosine_only_and_k_limits(mv):
+def test_argument_errors_mirror_the_reference(mv):
     C_ = mv.correspondence
-    with pytest.raises(AssertionError):
+    with pytest.raises(AssertionError):  # the reference's `assert metric in [...]` (correspondence.py:45)
         C_.knn_points(torch.zeros(2, 8), torch.zeros(2, 8), 1, "manhattan")
-    with pytest.raises(NotImplementedError):
-        C_.knn_points(torch.zeros(2, 8), torch.zeros(2, 8), 3, "cosine")
+    with pytest.raises(AssertionError):
+        C_.get_correspondences_ratio_test(torch.zeros(2, 8), torch.zeros(2, 8), 1, metric="manhattan")
     with pytest.raises(ValueError):
         C_.set_match_precision(dtype="fp8")
+    with pytest.raises(ValueError):
+        C_.set_match_precision(rows="fp8")
 
 
 # ---- kernel 2's tile schedule, restated: every tile owned exactly once, parts consecutive -----------------
