@@ -48,7 +48,27 @@ def only_load2(p):
     torch.cuda.current_stream().synchronize()
 
 
+_streams = [torch.cuda.Stream() for _ in range(4)]
+
+
+def only_load4(p):
+    cur = torch.cuda.current_stream()
+    C = p["feat_0"].shape[0]
+    jobs = [(gm.f0[:C // 2], p["feat_0"][:C // 2]), (gm.f0[C // 2:], p["feat_0"][C // 2:]),
+            (gm.f1[:C // 2], p["feat_1"][:C // 2]), (gm.f1[C // 2:], p["feat_1"][C // 2:])]
+    for st, (dst, src) in zip(_streams, jobs):
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            dst.copy_(src, non_blocking=True)
+    gm.g0.copy_(p["xyz_grid_0"], non_blocking=True)
+    gm.g1.copy_(p["xyz_grid_1"], non_blocking=True)
+    for st in _streams:
+        cur.wait_stream(st)
+    cur.synchronize()
+
+
 print(f"H2D of one pair (19.6 MB pinned) + sync : {timed(only_load):7.1f} us")
+print(f"the same on four streams                : {timed(only_load4):7.1f} us")
 print(f"the same on two streams                 : {timed(only_load2):7.1f} us")
 print(f"graph replay + sync                     : {timed(only_replay):7.1f} us")
 print(f"H2D + replay + sync                     : {timed(load_replay):7.1f} us")
