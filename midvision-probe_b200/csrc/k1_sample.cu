@@ -311,8 +311,8 @@ __device__ __forceinline__ void cubic_coeffs(float t, float c[4]) {
 //            (G x C / W values per warp); the sum of squares is 5 shuffles per point and warp plus one
 //            named barrier per group among the W warps; then scale + row stores, contiguous per warp.
 // History (profiles/): one CTA per point with taps in registers and a block-wide reduction issued ~37
-// instructions per element (2.6 TB/s); one warp per point over the window issued ~10 but was bound by the
-// LSU pipe (96 LDS.128 + 48 STG per point and warp); the group form cuts the LDS count by G.
+// instructions per element (2.6 TB/s); one warp per point over the window issues ~10 (W = G = 1, still the
+// configuration for C = 3072); the group form cuts the LDS count by G, worth 4 % at C = 2048 (see launch_k1).
 constexpr int K1W_PMAX = 32;  // points per sub-run: one warp inspects them with a ballot
 // which row outputs exist: bf16 + fp32, fp32 only, bf16 + bf16 residual, or ANY (checked at run time)
 constexpr int K1W_OUT_BOTH = 0, K1W_OUT_F32 = 1, K1W_OUT_ANY = 2, K1W_OUT_SPLIT = 3;
