@@ -98,6 +98,24 @@ def test_pure_helpers_match_oracle(mv, golden):
     assert len(auc) == 2 and 0 < auc[0] < 1 and auc[1] > auc[0]
 
 
+def test_feature_layout_and_dtype_detection(mv):
+    """which feature tensors take the zero-copy / 16-bit hand-off paths is decided from strides and dtype alone."""
+    C_ = mv.correspondence
+    chw = torch.zeros(8, 3, 5)
+    hwc_view = torch.zeros(3, 5, 8).permute(2, 0, 1)          # what a (B, tokens, C) ViT output looks like as (C, h, w)
+    assert not C_._is_channel_last(chw) and C_._is_channel_last(hwc_view)
+    assert C_._is_channel_last(hwc_view.to(torch.bfloat16)) and C_._is_channel_last(hwc_view.half())
+    assert not C_._is_channel_last(hwc_view.double())          # fp64 goes through the fp32 conversion
+    assert not C_._is_channel_last(torch.zeros(8, 1, 1))       # degenerate strides: ambiguous, take the copy path
+    assert not C_._is_channel_last(torch.zeros(3, 5, 16)[:, :, ::2].permute(2, 0, 1))  # strided channels
+    assert C_._row_format("split") == (True, False, True) and C_._row_format("f32") == (True, True, False)
+    C_.set_match_precision(dtype="tf32")
+    try:
+        assert C_._row_format("split") == (False, True, False)  # the tf32 path always keeps fp32 rows
+    finally:
+        C_.set_match_precision(dtype="bf16")
+
+
 def test_argument_errors_mirror_the_reference(mv):
     C_ = mv.correspondence
     with pytest.raises(AssertionError):  # the reference's `assert metric in [...]` (correspondence.py:45)
