@@ -17,6 +17,7 @@ ap.add_argument("--kind", default="navi")
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--nosync", action="store_true")
 ap.add_argument("--rows", default=None, choices=["split", "f32"])
+ap.add_argument("--radius", type=float, default=40.0, help="navi: radius of the live disc in the 112 x 112 grid")
 a = ap.parse_args()
 mv = importlib.import_module("midvision-probe_b200")
 syn = importlib.import_module("midvision-probe_b200.synthetic")
@@ -26,7 +27,7 @@ if a.rows:
 dev = torch.device("cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 if a.kind == "navi":
-    p = syn.navi_pair(0)
+    p = syn.navi_pair(0, radius=a.radius)
     f, g = p["feat_0"].cuda(), p["xyz_grid_0"].cuda()
     run = lambda: C_.prepare_xyz_side(f, g, dev, sync=not a.nosync)
 else:
