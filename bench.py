@@ -508,6 +508,8 @@ def main():
                 "frac": achieved / tc_sustained if achieved else None, "traffic": traffic,
                 "traffic_note": "dram read+write bytes per launch from the committed ncu --set full capture of this shape (profiles/k2_traffic.json)",
                 "peak_kind": f"{peak_kind} sustained bf16",
+                "peak_note": "the sustained figure is cuBLAS bf16 back to back for 4 s, i.e. at power-capped clocks; a run of a few "
+                             f"hundred ms keeps higher clocks, so frac can exceed 1 (burst figure: {tc_peak} TFLOP/s)",
                 "kernel": "k2_sim_top2_kernel (event pair around mv_k2_sim_top2: memset + GEMM/top-2 kernel + row merge)",
                 "launches_timed": len(k2_ms), "avg_ms": k2_avg_ms, "flop_per_launch": k2_avg_flop,
                 "k2_share_of_step": sum(k2_ms) / ms_total if ms_total else None,
