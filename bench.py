@@ -463,6 +463,28 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * e2e_steps * PAIRS_PER_STEP / float(t.item())
+    # the same synchronous helper with DEVICE-resident tensors (a caller that keeps the backbone output on the GPU,
+    # SURVEY 8f.1): no upload, results stay on the device, one host sync per call for the match count
+    def call_dev(p):
+        if args.workload == "navi":
+            return C_.estimate_correspondence_xyz(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], NUM_CORR)
+        return C_.estimate_correspondence_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], p["K"].clone(), NUM_CORR)
+
+    for j in range(4):
+        call_dev(pool_dev[j % POOL])
+    barrier()
+    t0 = time.perf_counter()
+    n_dev_calls = e2e_steps * PAIRS_PER_STEP
+    for j in range(n_dev_calls):
+        out_dev = call_dev(pool_dev[j % POOL])
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    helper_dev = {"value": world * n_dev_calls / float(t.item()), "unit": "pairs/s",
+                  "api": "the same helper called with device-resident tensors (no H2D; results returned on the device)"}
+
     # the same host-resident pairs through the pair pipeline (the evaluation loop's API: submit / join, integer hit
     # counts read back once at the end): the upload of one pair overlaps the kernels of the previous ones
     e2e_pipe = None
@@ -527,6 +549,7 @@ def main():
                     "steps": e2e_steps, "api": "correspondence.estimate_correspondence_xyz(host tensors)" if args.workload == "navi"
                     else "correspondence.estimate_correspondence_depth(host tensors)"},
             "e2e_pipeline": e2e_pipe,
+            "helper_device_tensors": helper_dev,
             "gpu_launches": launches,
             "roofline": roof,
             "recall": {"scored": summary["scored"], "recall_3d": summary["recall_3d"], "recall_2d": summary["recall_2d"],

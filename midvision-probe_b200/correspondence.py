@@ -676,9 +676,10 @@ def _host_mat(M):
 
 
 def _graphed_helper(kind, feat_0, feat_1, grid_0, grid_1, num_corr, ratio_test, K=None):
-    """Host-tensor fast path of the two dense helpers: the whole pair (kernels 1-3 + the gathers of the return
-    tuple) is one cached CUDA graph; a call is 4 uploads into static buffers, one replay and ONE packed
-    device -> host copy (results + the three live counts), i.e. a single host sync."""
+    """Fast path of the two dense helpers: the whole pair (kernels 1-3 + the gathers of the return tuple) is one
+    cached CUDA graph; a call is 4 copies into static buffers (uploads for host tensors), one replay and ONE
+    packed read-back (results + the three live counts), i.e. a single host sync.  Results are returned on the
+    device of the first feature argument, like the reference."""
     dev = _device()
     layout = "hwc" if (_is_channel_last(feat_0) and _is_channel_last(feat_1)) else "chw"
     fdt = feat_0.dtype if (feat_0.dtype == feat_1.dtype and feat_0.dtype in _FEAT_DTYPES) else torch.float32
@@ -694,12 +695,18 @@ def _graphed_helper(kind, feat_0, feat_1, grid_0, grid_1, num_corr, ratio_test, 
         gm = ev.GraphedPairMatcher(kind, tuple(feat_0.shape), tuple(grid_0.shape), num_corr, K=K, device=dev,
                                    ratio_test=ratio_test, with_outputs=True, feat_layout=layout, feat_dtype=fdt).capture()
         _HELPER_GRAPHS[key] = gm
-    gm.load(feat_0, feat_1, grid_0, grid_1, two_streams=True)
+    on_host = feat_0.device.type == "cpu"
+    gm.load(feat_0, feat_1, grid_0, grid_1, two_streams=on_host)
     gm.graph.replay()
     L.LAUNCHES["count"] += gm.launches_per_replay
-    gm.host_packed.copy_(gm.packed, non_blocking=True)
-    torch.cuda.current_stream(dev).synchronize()
-    res = gm.host_packed.clone()  # the pinned buffer is overwritten by the next call
+    if on_host:
+        gm.host_packed.copy_(gm.packed, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        res = gm.host_packed.clone()  # the pinned buffer is overwritten by the next call
+    else:  # device-resident caller (e.g. features straight from the backbone): results stay on its device
+        res = gm.packed.clone()       # the static buffer is overwritten by the next replay
+        if res.device != feat_0.device:
+            res = res.to(feat_0.device)
     km = gm.k_max
     blocks = 11 if kind == "xyz" else 7
     n0, n1, k = (int(v) for v in res[blocks * km:blocks * km + 3].tolist())
@@ -715,7 +722,7 @@ def estimate_correspondence_depth(feat_0, feat_1, depth_0, depth_1, K, num_corr=
     """(corr_xyz0 (k, 3), corr_xyz1 (k, 3), corr_dist (k,)).  correspondence.py:218-232."""
     dev = _device()
     in_dev = feat_0.device
-    if _CFG["helper_graphs"] and in_dev.type == "cpu":
+    if _CFG["helper_graphs"]:
         return _graphed_helper("depth", feat_0, feat_1, depth_0, depth_1, num_corr, True, K=K)
     Kc = K.detach().float().cpu()
     Kh, Kinv = _host_mat(Kc), _host_mat(Kc.inverse())
@@ -742,7 +749,7 @@ def estimate_correspondence_xyz(feat_0, feat_1, xyz_grid_0, xyz_grid_1, num_corr
     """(c_xyz0, c_xyz1, c_dist, c_uv0, c_uv1).  correspondence.py:235-263."""
     dev = _device()
     in_dev = feat_0.device
-    if _CFG["helper_graphs"] and in_dev.type == "cpu":
+    if _CFG["helper_graphs"]:
         return _graphed_helper("xyz", feat_0, feat_1, xyz_grid_0, xyz_grid_1, num_corr, ratio_test)
     _check_C(feat_0.shape[0])
     g0, g1 = _f32(xyz_grid_0, dev), _f32(xyz_grid_1, dev)
