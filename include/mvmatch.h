@@ -93,7 +93,9 @@ int mv_compact_valid(const float* z, int z_stride, int n, int32_t* valid_idx, in
  *   xyz_all (H*W, 3) = Kinv @ (depth * pixel-centre grid)            [always written]
  * and for the live points listed in valid_idx (after mv_compact_valid on xyz_all[:,2]):
  *   xyz (n, 3) compacted, coords (n, 2) = (ix, iy) in feature-map pixels.
- * Two entry points because the compaction sits between them.  K, Kinv: host, row-major 3x3. */
+ * Two entry points because the compaction sits between them.  K, Kinv: row-major 3x3, either HOST pointers (the
+ * matrix is passed to the kernel by value) or DEVICE pointers (the kernel reads them: the intrinsics can then
+ * change between replays of a captured CUDA graph -- ScanNet's differ per scene). */
 int mv_geom_backproject(const float* depth, int H, int W, const float* Kinv_host, float* xyz_all, mv_stream_t stream);
 int mv_geom_project_coords(const float* xyz_all, const int32_t* valid_idx, const int32_t* n_dev, int n_max,
                            const float* K_host, int H, int W, int h, int w, float* xyz, float* coords,

@@ -683,8 +683,9 @@ def _graphed_helper(kind, feat_0, feat_1, grid_0, grid_1, num_corr, ratio_test, 
     dev = _device()
     layout = "hwc" if (_is_channel_last(feat_0) and _is_channel_last(feat_1)) else "chw"
     fdt = feat_0.dtype if (feat_0.dtype == feat_1.dtype and feat_0.dtype in _FEAT_DTYPES) else torch.float32
+    # the intrinsics are NOT part of the key: they live in device memory and are refreshed per call (gm.load)
     key = (kind, tuple(feat_0.shape), tuple(grid_0.shape), int(num_corr), bool(ratio_test), _CFG["dtype"], _CFG["cluster"], _CFG["rows"], fdt,
-           None if K is None else tuple(K.detach().float().cpu().reshape(-1).tolist()), dev.index, layout)
+           dev.index, layout)
     gm = _HELPER_GRAPHS.get(key)
     if gm is None:
         import importlib
@@ -696,7 +697,7 @@ def _graphed_helper(kind, feat_0, feat_1, grid_0, grid_1, num_corr, ratio_test, 
                                    ratio_test=ratio_test, with_outputs=True, feat_layout=layout, feat_dtype=fdt).capture()
         _HELPER_GRAPHS[key] = gm
     on_host = feat_0.device.type == "cpu"
-    gm.load(feat_0, feat_1, grid_0, grid_1, two_streams=on_host)
+    gm.load(feat_0, feat_1, grid_0, grid_1, two_streams=on_host, K=K)
     gm.graph.replay()
     L.LAUNCHES["count"] += gm.launches_per_replay
     if on_host:

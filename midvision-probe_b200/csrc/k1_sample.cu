@@ -182,10 +182,21 @@ struct Mat3 {
 };
 
 // correspondence.py:132-161: points = depth * (x+.5, y+.5, 1); xyz = Kinv @ points
-__global__ void backproject_kernel(const float* __restrict__ depth, int H, int W, Mat3 Ki,
-                                   float* __restrict__ xyz_all) {
+// A 3x3 matrix argument is either passed by value (host pointer at the ABI) or read from device memory (device
+// pointer at the ABI: the matrix can then change between replays of a captured CUDA graph).
+__device__ __forceinline__ Mat3 pick_mat3(const Mat3& by_value, const float* __restrict__ dev) {
+  if (!dev) return by_value;
+  Mat3 m;
+#pragma unroll
+  for (int i = 0; i < 9; ++i) m.m[i] = __ldg(dev + i);
+  return m;
+}
+
+__global__ void backproject_kernel(const float* __restrict__ depth, int H, int W, Mat3 Ki_val,
+                                   const float* __restrict__ Ki_dev, float* __restrict__ xyz_all) {
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= H * W) return;
+  const Mat3 Ki = pick_mat3(Ki_val, Ki_dev);
   int y = p / W, x = p - y * W;
   float d = __ldg(depth + p);
   float px = __fmul_rn(d, (float)x + 0.5f), py = __fmul_rn(d, (float)y + 0.5f), pz = d;  // depth * grid
@@ -200,11 +211,13 @@ __global__ void backproject_kernel(const float* __restrict__ depth, int H, int W
 
 // correspondence.py:164-170 + ATen CPU grid_sampler (align_corners=False): ix = (g+1)*(size/2) - 0.5
 __global__ void project_coords_kernel(const float* __restrict__ xyz_all, const int32_t* __restrict__ valid_idx,
-                                      const int32_t* __restrict__ n_dev, int n_max, Mat3 K, int H, int W, int h,
-                                      int w, float* __restrict__ xyz, float* __restrict__ coords) {
+                                      const int32_t* __restrict__ n_dev, int n_max, Mat3 K_val,
+                                      const float* __restrict__ K_dev, int H, int W, int h, int w,
+                                      float* __restrict__ xyz, float* __restrict__ coords) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int n = n_dev ? min(*n_dev, n_max) : n_max;
   if (i >= n) return;
+  const Mat3 K = pick_mat3(K_val, K_dev);
   int p = valid_idx ? valid_idx[i] : i;
   float X = xyz_all[(size_t)p * 3 + 0], Y = xyz_all[(size_t)p * 3 + 1], Z = xyz_all[(size_t)p * 3 + 2];
   xyz[(size_t)i * 3 + 0] = X;
@@ -669,6 +682,18 @@ Mat3 load_mat3(const float* host) {
   return m;
 }
 
+// host pointer -> by value; device pointer -> the kernel reads it (returns the device pointer, else nullptr)
+const float* split_mat3_arg(const float* p, Mat3* by_value) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) == cudaSuccess && (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged)) {
+    *by_value = Mat3{};
+    return p;
+  }
+  (void)cudaGetLastError();  // unregistered host memory reports an error on old drivers
+  *by_value = load_mat3(p);
+  return nullptr;
+}
+
 }  // namespace
 
 extern "C" {
@@ -739,8 +764,9 @@ int mv_geom_backproject(const float* depth, int H, int W, const float* Kinv_host
   MV_REQUIRE(depth && Kinv_host && xyz_all, MV_E_ARG, "mv_geom_backproject: null pointer");
   MV_REQUIRE(H > 0 && W > 0, MV_E_ARG, "mv_geom_backproject: H and W must be positive");
   int n = H * W;
-  backproject_kernel<<<(n + 255) / 256, 256, 0, mv_cuda_stream(stream)>>>(depth, H, W, load_mat3(Kinv_host),
-                                                                         xyz_all);
+  Mat3 Ki;
+  const float* Ki_dev = split_mat3_arg(Kinv_host, &Ki);
+  backproject_kernel<<<(n + 255) / 256, 256, 0, mv_cuda_stream(stream)>>>(depth, H, W, Ki, Ki_dev, xyz_all);
   MV_LAUNCH_CHECK();
   return MV_OK;
 }
@@ -751,8 +777,10 @@ int mv_geom_project_coords(const float* xyz_all, const int32_t* valid_idx, const
   MV_REQUIRE(xyz_all && K_host && xyz && coords, MV_E_ARG, "mv_geom_project_coords: null pointer");
   MV_REQUIRE(n_max >= 0 && H > 0 && W > 0 && h > 0 && w > 0, MV_E_ARG, "mv_geom_project_coords: bad sizes");
   if (n_max == 0) return MV_OK;
+  Mat3 Km;
+  const float* K_dev = split_mat3_arg(K_host, &Km);
   project_coords_kernel<<<(n_max + 255) / 256, 256, 0, mv_cuda_stream(stream)>>>(
-      xyz_all, valid_idx, n_dev, n_max, load_mat3(K_host), H, W, h, w, xyz, coords);
+      xyz_all, valid_idx, n_dev, n_max, Km, K_dev, H, W, h, w, xyz, coords);
   MV_LAUNCH_CHECK();
   return MV_OK;
 }

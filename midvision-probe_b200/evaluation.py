@@ -197,8 +197,13 @@ class GraphedPairMatcher:
         self.g0 = torch.zeros(grid_shape, dtype=torch.float32, device=self.dev)
         self.g1 = torch.zeros(grid_shape, dtype=torch.float32, device=self.dev)
         if kind == "depth":
-            Kc = K.detach().float().cpu()
-            self.Kc, self.Kh, self.Kinv = Kc, C_._host_mat(Kc), C_._host_mat(Kc.inverse())
+            # the intrinsics live in device memory ([K | K^-1], 18 floats) so that they can change between replays of
+            # the captured graph (ScanNet's differ per scene); load(..., K=...) refreshes them
+            self.Kdev = torch.zeros(18, dtype=torch.float32, device=self.dev)
+            self.Kpin = torch.zeros((8, 18), dtype=torch.float32).pin_memory()  # ring of staging rows: no sync on a change
+            self.Kturn = 0
+            self.Kc = None
+            self.set_intrinsics(K)
         self.graph = None
         self.out = None
 
@@ -207,8 +212,9 @@ class GraphedPairMatcher:
             s0, s1 = _both_sides(lambda: C_.prepare_xyz_side(self.f0, self.g0, self.dev, sync=False),
                                  lambda: C_.prepare_xyz_side(self.f1, self.g1, self.dev, sync=False), self.dev)
         else:
-            s0, s1 = _both_sides(lambda: C_.prepare_depth_side(self.f0, self.g0, self.Kh, self.Kinv, self.dev, sync=False),
-                                 lambda: C_.prepare_depth_side(self.f1, self.g1, self.Kh, self.Kinv, self.dev, sync=False), self.dev)
+            Kd, Kinvd = L.ptr(self.Kdev), c_void_p(self.Kdev.data_ptr() + 36)
+            s0, s1 = _both_sides(lambda: C_.prepare_depth_side(self.f0, self.g0, Kd, Kinvd, self.dev, sync=False),
+                                 lambda: C_.prepare_depth_side(self.f1, self.g1, Kd, Kinvd, self.dev, sync=False), self.dev)
         r = C_._match_sides(s0, s1, s0.n, s1.n, self.num_corr, self.ratio_test, n_dev=s0.n_dev, m_dev=s1.n_dev)
         if self.with_outputs:
             # the helper's return tuple + the live counts in one buffer of column blocks (mv_pack_matches):
@@ -239,10 +245,25 @@ class GraphedPairMatcher:
             self.host_packed = torch.empty(self.packed.shape, dtype=torch.float32, pin_memory=True)
         return self
 
-    def load(self, feat_0, feat_1, grid_0, grid_1, two_streams=False):
+    def set_intrinsics(self, K):
+        """(depth kind) K (3, 3) for the following replays; a no-op when it is the matrix already loaded."""
+        Kc = K.detach().float().cpu().reshape(3, 3)
+        if self.Kc is not None and torch.equal(Kc, self.Kc):
+            return
+        self.Kc = Kc.clone()
+        row = self.Kpin[self.Kturn % 8]  # a row is reused only after 8 further changes: its copy has long completed
+        self.Kturn += 1
+        row[:9] = Kc.reshape(-1)
+        row[9:] = Kc.inverse().reshape(-1)
+        self.Kdev.copy_(row, non_blocking=True)
+
+    def load(self, feat_0, feat_1, grid_0, grid_1, two_streams=False, K=None):
         """stage one pair's inputs (any device; pinned host memory makes the copies asynchronous).
+        K: (depth kind) the pair's intrinsics, if they differ from the ones the matcher was built with.
         two_streams: issue image 1's copies on a second stream -- two concurrent host -> device transfers use the
         PCIe link better than one (measured: 463 -> ~390 us for the 19.6 MB of a NAVI-shaped pair)."""
+        if K is not None and self.kind == "depth":
+            self.set_intrinsics(K)
         if not two_streams:
             self.f0.copy_(feat_0, non_blocking=True)
             self.f1.copy_(feat_1, non_blocking=True)
@@ -309,7 +330,7 @@ class PairPipeline:
         self.turn += 1
         st.wait_stream(torch.cuda.current_stream(self.dev))  # inputs produced on the caller's stream
         with torch.cuda.stream(st):
-            gm.load(feat_0, feat_1, grid_0, grid_1)
+            gm.load(feat_0, feat_1, grid_0, grid_1, K=K if gm.kind == "depth" else None)
             return gm.run(acc, Rt, K)
 
     def join(self):

@@ -381,3 +381,35 @@ def test_second_device_in_the_same_process(mv, syn):
             outs[-1].append(e[3].cpu())
     for x, y in zip(*outs):
         assert torch.equal(x, y)
+
+
+def test_intrinsics_change_between_replays_of_one_graph(mv, syn):
+    """ScanNet's intrinsics differ per scene: the cached graph keeps K / K^-1 in device memory, so calls with
+    different K re-use ONE captured graph and still equal the eager launches with that K."""
+    C_ = mv.correspondence
+    p = syn.scannet_pair(16, C=64, h=6, w=8, H=24, W=32)
+    Ks = [p["K"].clone(), p["K"].clone() * torch.tensor([[1.05], [0.97], [1.0]]), p["K"].clone()]
+    Ks[1][0, 2] += 1.5
+    n_before = len(C_._HELPER_GRAPHS)
+    outs_g = [C_.estimate_correspondence_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], K.clone(), 100) for K in Ks]
+    assert len(C_._HELPER_GRAPHS) <= n_before + 1                      # one graph for all three K
+    C_.set_match_precision(helper_graphs=0)
+    try:
+        outs_e = [C_.estimate_correspondence_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], K.clone(), 100) for K in Ks]
+    finally:
+        C_.set_match_precision(helper_graphs=1)
+    for a, b in zip(outs_g, outs_e):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    assert not torch.equal(outs_g[0][0], outs_g[1][0]) and torch.equal(outs_g[0][0], outs_g[2][0])
+    # the pipeline takes per-pair intrinsics too
+    ev = mv.evaluation
+    acc_a = ev.RecallAccumulator([0.05], [25], device=torch.device("cuda"))
+    acc_b = ev.RecallAccumulator([0.05], [25], device=torch.device("cuda"))
+    pipe = ev.PairPipeline("depth", tuple(p["feat_0"].shape), tuple(p["depth_0"].shape), 100, K=Ks[0], lanes=2)
+    for K in Ks:
+        pipe.submit(p["feat_0"].cuda(), p["feat_1"].cuda(), p["depth_0"].cuda(), p["depth_1"].cuda(), acc_a, p["Rt"], K)
+        ev.match_and_score_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], K, p["Rt"], 100, acc_b, sync=True)
+    pipe.join()
+    torch.cuda.synchronize()
+    assert torch.equal(acc_a.hits.cpu(), acc_b.hits.cpu())
