@@ -134,6 +134,9 @@ __global__ void __launch_bounds__(RATIO_THREADS, 6) k3_ratio_mutual_kernel(ROWS 
 // ------------------------------------------------------------------------------------------
 // top-k of the weights (single CTA, 1024 threads): radix select the k-th key, stable pick among the
 // ties, bitonic sort of the k winners by (weight desc, row asc)
+// 20 us for 5 k weights / k = 1000.  Measured and rejected: caching the keys in shared memory (20.2 us, the five
+// passes are not load-bound) and __match_any_sync-aggregated histogram atomics (36.8 us: the match instruction
+// costs more than the same-address shared atomics it saves).
 // ------------------------------------------------------------------------------------------
 constexpr int TOPK_THREADS = 1024;
 
@@ -501,7 +504,8 @@ int mv_k3_topk_matches(const float* weight, const int32_t* row_idx, const int32_
   int kpad = 2;
   while (kpad < kmax) kpad <<= 1;
   const size_t smem = (size_t)(kpad > 2 * TOPK_THREADS ? kpad : 2 * TOPK_THREADS) * sizeof(unsigned long long);
-  static size_t smem_set = 0;
+  static size_t smem_set_dev[MV_MAX_DEVICES];  // the attribute is per device
+  size_t& smem_set = smem_set_dev[mv_device_slot()];
   if (smem > 48 * 1024 && smem > smem_set) {
     MV_CUDA(cudaFuncSetAttribute(k3_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     smem_set = smem;
