@@ -48,6 +48,11 @@ typedef void* mv_stream_t; /* cudaStream_t */
 /* operand types of kernel 2 */
 #define MV_DTYPE_BF16 0 /* tcgen05.mma kind::f16, bf16 inputs, fp32 accumulate  */
 #define MV_DTYPE_TF32 1 /* tcgen05.mma kind::tf32, fp32 inputs, fp32 accumulate */
+#define MV_DTYPE_F16 2  /* tcgen05.mma kind::f16, fp16 inputs (11-bit mantissa at the bf16 rate), fp32 accumulate */
+
+/* role of a row set in a match: queries are the rows of S, targets its columns (f16c rows, see mv_k1_sample_f16c) */
+#define MV_ROLE_QUERY 0
+#define MV_ROLE_TARGET 1
 
 /* `cluster` argument of kernel 2: 0 / 1 = every SM on its own; 2 / 4 = clusters of that many CTAs with the B tile
  * TMA-multicast; MV_CLUSTER_PAIR = CTA pairs (tcgen05 cta_group::2): one 256 x 256 MMA tile per two SMs */
@@ -124,6 +129,27 @@ int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, cons
                            const int32_t* n_dev, int n_max, int normalize, uint16_t* out_bf16, uint16_t* out_bf16_lo,
                            float* out_f32, int32_t* taps, mv_stream_t stream);
 
+/* "f16c" rows: kernel 2's fp16 operand with the precision of a tf32 product at the bf16 rate, for feature sets whose
+ * rows are nearly collinear (CNN features: all-positive, mean cosine ~0.9 -- there a bf16 product ranks the
+ * wrong neighbour on most rows).  For a target row b and any fixed centre mu (we use the mean direction of the target's
+ * source map), a . b = a . (b - mu) + a . mu, so
+ *     target row  = [ fp16(b - mu) (C) | 1, 1, 2^-11, 0, 0, 0, 0, 0 ]
+ *     query  row  = [ fp16(a)      (C) | p0, p1, p2, 0, 0, 0, 0, 0 ]     p0 + p1 + p2 * 2^-11 = r = a . mu  (fp32)
+ * have the inner product a . b with the rounding error of the target scaled by |b - mu| instead of |b|; the ranking
+ * along a row AND along a column is that of a . b for every mu.  Row pitch C + 8 halfs; kernel 2 is called with
+ * C + 8 columns and MV_DTYPE_F16.  out_f16_lo (optional, (n, C) halfs): fp16((y - float(out_f16)) * 2^11) with
+ * y = row - center, so that y = hi + lo * 2^-11 to 2^-22 relative (consumed by mv_k3_ratio_mutual_f16c).
+ * role: MV_ROLE_QUERY uses dotvec (= the target's centre; NULL -> r = 0), MV_ROLE_TARGET uses center.  Both may be
+ * given.  row_dot (optional, n floats): r.  Other arguments as mv_k1_sample_normalize. */
+int mv_k1_sample_f16c(int mode, const float* src, int C, int h, int w, const float* coords, const int32_t* n_dev, int n_max,
+                      int normalize, int role, const float* center, const float* dotvec, uint16_t* out_f16, uint16_t* out_f16_lo,
+                      float* out_f32, float* row_dot, int32_t* taps, mv_stream_t stream);
+
+/* mu (C floats) = mean over every `step`-th row p < n of rows[p] / max(||rows[p]||, 1e-12); rows (n, C) fp32 (a channel-last
+ * feature map or a set of feature rows).  inv_scratch: ceil(n_max / step) floats.  Deterministic. */
+int mv_rows_center(const float* rows, int C, int n_max, const int32_t* n_dev, int step, float* inv_scratch, float* mu,
+                   mv_stream_t stream);
+
 /* ---- kernel 2: similarity GEMM with fused row top-2 / column arg-max (tensor-core bound) -- */
 /* S = A @ B^T (n x m, never written).  Replaces faiss GpuIndexFlatL2.search(k<=2)
  * (correspondence.py:14-23) for L2-normalised rows, where the L2 order equals the cosine order
@@ -131,7 +157,7 @@ int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, cons
  *   row_val/row_idx (n_max, 2): the two largest S[i, :] and their columns, best first, ties to the
  *                               lower column; missing entries = MV_SIM_MASKED / -1.
  *   col_best (m_max) optional : packed arg-max over rows of S[:, j]; decode with mv_k2_unpack_col.
- * A, B: bf16 (MV_DTYPE_BF16) or fp32 (MV_DTYPE_TF32), 16-byte aligned, C % 8 == 0 (bf16) / C % 4 == 0.
+ * A, B: bf16 (MV_DTYPE_BF16), fp16 (MV_DTYPE_F16) or fp32 (MV_DTYPE_TF32), 16-byte aligned, C % 8 == 0 (16-bit) / C % 4 == 0.
  * cluster: 0 or 1 = one CTA per SM on its own; 2 or 4 = thread-block clusters of that many CTAs working on
  * consecutive row blocks with the B tile loaded once and TMA-multicast to all of them; MV_CLUSTER_PAIR = the two
  * CTAs of a cluster issue ONE 256-row MMA (cta_group::2), each holding half of the B tile.
@@ -155,6 +181,14 @@ int mv_k3_ratio_mutual(const float* A32, const float* B32, int C, const int32_t*
 int mv_k3_ratio_mutual_split(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* B_hi, const uint16_t* B_lo, int C,
                              const int32_t* n_dev, int n_max, int32_t* row_idx, const unsigned long long* col_best,
                              int ratio_test, float* dists, float* weight, uint8_t* mutual, mv_stream_t stream);
+
+/* The same on f16c rows (mv_k1_sample_f16c): A_hi (n, C + 8) / A_lo (n, C) query rows, B_hi / B_lo target rows,
+ * center_B (C floats or NULL) the centre the target rows are relative to; every element is rebuilt as
+ * float(hi) + float(lo) * 2^-11 (+ center_B) before the identical fp32 arithmetic. */
+int mv_k3_ratio_mutual_f16c(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* B_hi, const uint16_t* B_lo, int C,
+                            const float* center_B, const int32_t* n_dev, int n_max, int32_t* row_idx,
+                            const unsigned long long* col_best, int ratio_test, float* dists, float* weight, uint8_t* mutual,
+                            mv_stream_t stream);
 
 /* get_topk_matches (correspondence.py:125-129): the k = min(num_corr, n) largest weights, sorted
  * descending (ties: lower row first).  sel_* have num_corr entries; k_dev receives k.

@@ -26,11 +26,14 @@ PROTOTYPES = {
     "mv_geom_grid_coords": (c_int, [P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P, P]),
     "mv_geom_keypoint_coords": (c_int, [P, c_int, c_int, c_float, c_int, c_int, P, P]),
     "mv_k1_sample_normalize": (c_int, [c_int, P, c_int, c_int, c_int, P, P, c_int, c_int, P, P, P, P, P]),
+    "mv_k1_sample_f16c": (c_int, [c_int, P, c_int, c_int, c_int, P, P, c_int, c_int, c_int, P, P, P, P, P, P, P, P]),
+    "mv_rows_center": (c_int, [P, c_int, c_int, P, c_int, P, P, P]),
     "mv_k2_workspace_bytes": (c_size_t, [c_int, c_int]),
     "mv_k2_sim_top2": (c_int, [P, P, c_int, c_int, c_int, P, P, c_int, c_int, P, P, P, P, c_size_t, P]),
     "mv_k2_unpack_col": (c_int, [P, c_int, P, P, P]),
     "mv_k3_ratio_mutual": (c_int, [P, P, c_int, P, c_int, P, P, c_int, P, P, P, P]),
     "mv_k3_ratio_mutual_split": (c_int, [P, P, P, P, c_int, P, c_int, P, P, c_int, P, P, P, P]),
+    "mv_k3_ratio_mutual_f16c": (c_int, [P, P, P, P, c_int, P, P, c_int, P, P, c_int, P, P, P, P]),
     "mv_k3_topk_matches": (c_int, [P, P, P, c_int, c_int, P, P, P, P, P]),
     "mv_k3_score": (c_int, [P, P, P, c_int, P, P, P, P, P, P, c_int, P, c_int, P, P, P, P, P, P]),
     "mv_gather_rows": (c_int, [P, c_int, P, P, c_int, P, P]),
@@ -47,6 +50,8 @@ MV_SAMPLE_BICUBIC_CLAMP = 1
 MV_SAMPLE_ROWS = 2
 MV_DTYPE_BF16 = 0
 MV_DTYPE_TF32 = 1
+MV_DTYPE_F16 = 2
+MV_ROLE_QUERY, MV_ROLE_TARGET = 0, 1
 MV_FEAT_F32, MV_FEAT_BF16, MV_FEAT_F16 = 0, 1, 2
 MV_SIM_MASKED = -3.0e38
 MV_MAX_THRESHOLDS = 16
@@ -56,8 +61,8 @@ _lib = None
 # kernels launched per entry point (for bench.py's gpu_launches claim); memsets are not counted
 KERNELS_PER_CALL = {
     "mv_chw_to_hwc": 1, "mv_feat_to_hwc_f32": 1, "mv_compact_valid": 1, "mv_geom_backproject": 1, "mv_geom_project_coords": 1,
-    "mv_geom_grid_coords": 1, "mv_geom_keypoint_coords": 1, "mv_k1_sample_normalize": 1, "mv_k2_sim_top2": 2,
-    "mv_k2_unpack_col": 1, "mv_k3_ratio_mutual": 1, "mv_k3_ratio_mutual_split": 1, "mv_k3_topk_matches": 1, "mv_k3_score": 1, "mv_gather_rows": 1,
+    "mv_geom_grid_coords": 1, "mv_geom_keypoint_coords": 1, "mv_k1_sample_normalize": 1, "mv_k1_sample_f16c": 1, "mv_rows_center": 2, "mv_k2_sim_top2": 2,
+    "mv_k2_unpack_col": 1, "mv_k3_ratio_mutual": 1, "mv_k3_ratio_mutual_split": 1, "mv_k3_ratio_mutual_f16c": 1, "mv_k3_topk_matches": 1, "mv_k3_score": 1, "mv_gather_rows": 1,
     "mv_pack_matches": 1, "mv_argmax_rows": 1, "mv_k3_spair_errors": 1, "mv_spair_match_batch": 1,
 }
 LAUNCHES = {"count": 0}

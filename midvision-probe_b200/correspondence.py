@@ -28,9 +28,16 @@ __all__ = [
     "set_match_precision", "match_rows", "prepare_depth_side", "prepare_xyz_side", "MatchResult",
 ]
 
-# operand type of kernel 2: "bf16" (tcgen05 kind::f16) or "tf32" (kind::tf32); cluster = B-tile multicast width
+# operand type of kernel 2:
+#   "f16"  (default) tcgen05 kind::f16 on fp16 "f16c" rows: target rows stored relative to a centre, the query rows carry
+#          their dot product with that centre in three extra columns (include/mvmatch.h, mv_k1_sample_f16c).  Same tensor
+#          rate as bf16 with the ranking precision of fp32 on real backbone features (CNN maps are nearly collinear:
+#          a plain bf16 product ranks the wrong neighbour there)
+#   "bf16" tcgen05 kind::f16 on plain bf16 rows     "tf32" kind::tf32 on fp32 rows (half the rate)
+# cluster = B-tile multicast width
+DEFAULT_DTYPE = "f16"
 _CFG = {
-    "dtype": os.environ.get("MVMATCH_DTYPE", "bf16"),
+    "dtype": os.environ.get("MVMATCH_DTYPE", DEFAULT_DTYPE),
     "cluster": int(os.environ.get("MVMATCH_CLUSTER", "-1")),  # -1 = let the library choose (MV_CLUSTER_AUTO)
     # host-tensor calls of the two dense helpers replay a CUDA graph cached per input shape (0 = launch eagerly)
     "helper_graphs": int(os.environ.get("MVMATCH_HELPER_GRAPHS", "1")),
@@ -47,7 +54,7 @@ _PROFILE = {}
 
 
 def set_match_precision(dtype=None, cluster=None, helper_graphs=None, rows=None):
-    """Choose kernel 2's operand type ("bf16" | "tf32"), its cluster width (1, 2 or 4), whether the dense
+    """Choose kernel 2's operand type ("f16" | "bf16" | "tf32"), its cluster width (1, 2 or 4), whether the dense
     helpers replay cached CUDA graphs for host-tensor calls, and the row format between kernels 1 and 3
     ("split" | "f32", see _CFG)."""
     if rows is not None:
@@ -57,8 +64,8 @@ def set_match_precision(dtype=None, cluster=None, helper_graphs=None, rows=None)
     if helper_graphs is not None:
         _CFG["helper_graphs"] = int(bool(helper_graphs))
     if dtype is not None:
-        if dtype not in ("bf16", "tf32"):
-            raise ValueError("dtype must be 'bf16' or 'tf32'")
+        if dtype not in ("f16", "bf16", "tf32"):
+            raise ValueError("dtype must be 'f16', 'bf16' or 'tf32'")
         _CFG["dtype"] = dtype
     if cluster is not None:
         if cluster not in (-1, 1, 2, 4, 20):
@@ -134,22 +141,40 @@ def _check_C(C):
         raise ValueError(f"feature dimension {C} must be a multiple of 8 for the tensor-core path")
 
 
-def _sample(mode, src, C, h, w, coords, n_dev, n_max, normalize, want_bf16, want_f32, taps=None, want_lo=False):
+def _sample(mode, src, C, h, w, coords, n_dev, n_max, normalize, want_bf16, want_f32, taps=None, want_lo=False,
+            role=L.MV_ROLE_QUERY, center=None, dotvec=None):
     """kernel 1.  src: (h*w, C) channel-last (or (n, C) rows for MV_SAMPLE_ROWS).
-    Returns (bf16 rows, fp32 rows, bf16 residual rows); the ones not asked for are None."""
+    Returns (16-bit rows, fp32 rows, 16-bit residual rows); the ones not asked for are None.
+    The 16-bit rows are bf16 (n, C) for the "bf16" operand type and fp16 "f16c" rows (n, C + 8) for "f16":
+    role / center / dotvec are the f16c parameters of mv_k1_sample_f16c."""
     dev = src.device
-    o16 = _empty((max(n_max, 1), C), torch.bfloat16, dev) if (want_bf16 or want_lo) else None
-    olo = _empty((max(n_max, 1), C), torch.bfloat16, dev) if want_lo else None
+    f16 = _CFG["dtype"] == "f16" and (want_bf16 or want_lo)
+    t16 = torch.float16 if f16 else torch.bfloat16
+    o16 = _empty((max(n_max, 1), C + 8 if f16 else C), t16, dev) if (want_bf16 or want_lo) else None
+    olo = _empty((max(n_max, 1), C), t16, dev) if want_lo else None
     o32 = _empty((max(n_max, 1), C), torch.float32, dev) if want_f32 else None
-    if n_max > 0:
+    if n_max > 0 and f16:
+        L.call("mv_k1_sample_f16c", mode, L.ptr(src), C, h, w, L.ptr(coords), L.ptr(n_dev), n_max, int(normalize), role,
+               L.ptr(center), L.ptr(dotvec), L.ptr(o16), L.ptr(olo), L.ptr(o32), None, L.ptr(taps), _stream())
+    elif n_max > 0:
         L.call("mv_k1_sample_normalize", mode, L.ptr(src), C, h, w, L.ptr(coords), L.ptr(n_dev), n_max, int(normalize),
                L.ptr(o16), L.ptr(olo), L.ptr(o32), L.ptr(taps), _stream())
     return o16, o32, olo
 
 
+def _center(rows, n, n_dev=None, step=1):
+    """(C,) fp32 centre of the L2-normalised rows (mean direction of every step-th row): mv_rows_center."""
+    C = rows.shape[1]
+    mu = _empty((C,), torch.float32, rows.device)
+    scratch = _empty(((n + step - 1) // step,), torch.float32, rows.device)
+    L.call("mv_rows_center", L.ptr(rows), C, n, L.ptr(n_dev), step, L.ptr(scratch), L.ptr(mu), _stream())
+    return mu
+
+
 def _row_format(rows=None):
-    """(want_bf16, want_f32, want_lo) of kernel 1 for the configured kernel-2 operand type and row format."""
-    if _CFG["dtype"] != "bf16":
+    """(want 16-bit rows, want fp32 rows, want 16-bit residual rows) of kernel 1 for the configured kernel-2 operand
+    type and row format."""
+    if _CFG["dtype"] == "tf32":
         return False, True, False
     if (rows or _CFG["rows"]) == "split":
         return True, False, True
@@ -163,22 +188,24 @@ class MatchResult:
 
 
 def match_rows(A16, A32, B16, B32, n, m, num_corr, ratio_test=True, n_dev=None, m_dev=None, want_topk=True, run_k3=True,
-               A_lo=None, B_lo=None):
+               A_lo=None, B_lo=None, center_B=None):
     """kernel 2 + kernel 3 on prepared rows.
 
-    A16/B16: (n, C)/(m, C) bf16 rows (None when the tf32 path is selected), A32/B32: fp32 rows -- or None
-    when the split form is used: A_lo/B_lo are then the bf16 residual planes of A16/B16.
+    A16/B16: (n, C)/(m, C) bf16 rows or (n, C + 8)/(m, C + 8) fp16 f16c rows (query / target role; None when the
+    tf32 path is selected), A32/B32: fp32 rows -- or None when the split form is used: A_lo/B_lo are then the 16-bit
+    residual planes of A16/B16.  center_B: the centre f16c target rows are relative to (None: not centred).
     Mirrors get_correspondences_ratio_test (correspondence.py:63-102, bidirectional=False):
     2-NN -> fp32 cosine distances -> ratio weights -> top-num_corr, plus the mutual-NN flag.
     n, m are the live counts when n_dev/m_dev are None, otherwise upper bounds.
     """
     ref = A32 if A32 is not None else A16
     dev = ref.device
-    C = ref.shape[1]
     tf32 = _CFG["dtype"] == "tf32"
+    f16 = _CFG["dtype"] == "f16"
+    C = ref.shape[1] - (8 if (f16 and A32 is None) else 0)
     split = A32 is None or B32 is None
     if split and (tf32 or A_lo is None or B_lo is None or A16 is None or B16 is None):
-        raise ValueError("split rows need the bf16 path and both residual planes")
+        raise ValueError("split rows need a 16-bit operand type and both residual planes")
     st = _stream()
     res = MatchResult()
     row_val = _empty((n, 2), torch.float32, dev)
@@ -189,23 +216,27 @@ def match_rows(A16, A32, B16, B32, n, m, num_corr, ratio_test=True, n_dev=None, 
     ws = _empty((ws_bytes,), torch.uint8, dev)
     A = A32 if tf32 else A16
     B = B32 if tf32 else B16
+    Ck = A.shape[1]  # C + 8 for f16c rows
     prof = _PROFILE.get("k2_events")
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    L.call("mv_k2_sim_top2", L.ptr(A), L.ptr(B), n, m, C, L.ptr(n_dev), L.ptr(m_dev),
-           L.MV_DTYPE_TF32 if tf32 else L.MV_DTYPE_BF16, _CFG["cluster"], L.ptr(row_val), L.ptr(row_idx),
-           L.ptr(col_best), L.ptr(ws), c_size_t(ws_bytes), st)
+    L.call("mv_k2_sim_top2", L.ptr(A), L.ptr(B), n, m, Ck, L.ptr(n_dev), L.ptr(m_dev),
+           L.MV_DTYPE_TF32 if tf32 else (L.MV_DTYPE_F16 if f16 else L.MV_DTYPE_BF16), _CFG["cluster"], L.ptr(row_val),
+           L.ptr(row_idx), L.ptr(col_best), L.ptr(ws), c_size_t(ws_bytes), st)
     if prof is not None:
         ev1.record()
-        prof.append((ev0, ev1, (n, m, C, n_dev, m_dev)))
+        prof.append((ev0, ev1, (n, m, Ck, n_dev, m_dev)))
     res.row_idx, res.col_best = row_idx, col_best
     if not run_k3:  # raw kernel-2 neighbours (inner-product order), no cosine re-ranking
         return res
     dists = _empty((n, 2), torch.float32, dev)
     weight = _empty((n,), torch.float32, dev)
     mutual = _empty((n,), torch.uint8, dev)
-    if split:
+    if split and f16:
+        L.call("mv_k3_ratio_mutual_f16c", L.ptr(A16), L.ptr(A_lo), L.ptr(B16), L.ptr(B_lo), C, L.ptr(center_B), L.ptr(n_dev), n,
+               L.ptr(row_idx), L.ptr(col_best), int(ratio_test), L.ptr(dists), L.ptr(weight), L.ptr(mutual), st)
+    elif split:
         L.call("mv_k3_ratio_mutual_split", L.ptr(A16), L.ptr(A_lo), L.ptr(B16), L.ptr(B_lo), C, L.ptr(n_dev), n,
                L.ptr(row_idx), L.ptr(col_best), int(ratio_test), L.ptr(dists), L.ptr(weight), L.ptr(mutual), st)
     else:
@@ -234,15 +265,27 @@ def _gather(src, idx, k, k_dev=None):
     return out
 
 
-def _rows_from_features(F, normalize, dev):
-    """(N, C) features -> (bf16 rows or None, fp32 rows), optionally L2-normalised (correspondence.py:47-48)."""
+def _rows_from_features(F, normalize, dev, role=L.MV_ROLE_QUERY, center=None, dotvec=None):
+    """(N, C) features -> (16-bit rows or None, fp32 rows), optionally L2-normalised (correspondence.py:47-48)."""
     F = _f32(F, dev)
     n, C = F.shape
     _check_C(C)
-    want16 = _CFG["dtype"] == "bf16"
+    want16 = _CFG["dtype"] != "tf32"
     if not normalize and not want16:
         return None, F
-    return _sample(L.MV_SAMPLE_ROWS, F, C, 0, 0, None, None, n, normalize, want16, True)[:2]
+    return _sample(L.MV_SAMPLE_ROWS, F, C, 0, 0, None, None, n, normalize, want16, True, role=role, center=center,
+                   dotvec=dotvec)[:2]
+
+
+def _rows_pair(X_f, Y_f, dev):
+    """query rows of X_f and target rows of Y_f for one cosine match: ((A16, A32), (B16, B32), centre of the targets)."""
+    mu = None
+    if _CFG["dtype"] == "f16" and Y_f.shape[0] > 0:
+        Y = _f32(Y_f, dev)
+        mu = _center(Y, Y.shape[0], step=max(1, Y.shape[0] // 1024))  # any vector near the mean direction will do
+        Y_f = Y
+    return (_rows_from_features(X_f, True, dev, L.MV_ROLE_QUERY, dotvec=mu),
+            _rows_from_features(Y_f, True, dev, L.MV_ROLE_TARGET, center=mu), mu)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -252,7 +295,10 @@ def faiss_knn(query, target, k):
     """L2 k-NN: (squared L2 distances ascending, int64 indices).  correspondence.py:14-23.
     k <= 2 (every call site) runs on kernel 2; larger k takes the exact blocked search of _exact_knn_blocks.
 
-    Neighbours are ranked at tf32 precision (kernel 2), their distances recomputed in fp32.
+    Neighbours are PROPOSED at tf32 precision (kernel 2's two best per row); the fp32 distances of the two decide
+    their order.  Ranking tolerance: a neighbour whose squared distance is within ~1e-3 relative of the second
+    candidate's can be missed (the north-star gap rule); missing neighbours (target smaller than k) come back as
+    (-1, inf) like faiss.
     The search runs on kernel 2 through the identity ||q-t||^2 = ||q||^2 + ||t||^2 - 2 q.t : the rows are
     extended by (1, -||t||^2/2) split into tf32-exact pieces so that the inner-product order is the L2
     order; the returned distances are recomputed in fp32 for the winners.
@@ -281,9 +327,11 @@ def faiss_knn(query, target, k):
     Cp = ((C + 3 + 7) // 8) * 8
     qe = torch.zeros((n, Cp), dtype=torch.float32, device=dev)
     te = torch.zeros((m, Cp), dtype=torch.float32, device=dev)
+    # targets relative to their mean: q.(t - mu) differs from q.t by a per-query constant, so the order along a row is
+    # unchanged while the tf32 rounding error shrinks with |t - mu| (the same idea as the f16c rows)
     qe[:, :C] = q
     qe[:, C:C + 3] = 1.0
-    te[:, :C] = t
+    te[:, :C] = t - t.mean(dim=0, keepdim=True) if m > 1 else t
     for i, p in enumerate(pieces):
         te[:, C + i] = p
     saved = dict(_CFG)
@@ -292,13 +340,16 @@ def faiss_knn(query, target, k):
         r = match_rows(None, qe, None, te, n, m, 0, want_topk=False, run_k3=False)
     finally:
         _CFG.update(saved)
-    idx = r.row_idx[:, :k].long()
-    d = ((q[:, None, :] - t[idx]) ** 2).sum(dim=-1)
-    if k == 2:  # ascending, like faiss
-        swap = d[:, 1] < d[:, 0]
-        d = torch.where(swap[:, None], d.flip(1), d)
-        idx = torch.where(swap[:, None], idx.flip(1), idx)
-    return d.to(in_dev), idx.to(in_dev)
+    # both candidates always: the tf32 product only PROPOSES them, their fp32 distances decide the order (so k = 1
+    # also returns the better of the two); a missing neighbour (m < k) is faiss's (-1, inf), never a wrapped index
+    idx = r.row_idx.long()
+    have = idx >= 0
+    d = ((q[:, None, :] - t[idx.clamp(min=0)]) ** 2).sum(dim=-1)
+    d = torch.where(have, d, torch.full_like(d, float("inf")))
+    swap = d[:, 1] < d[:, 0]
+    d = torch.where(swap[:, None], d.flip(1), d)
+    idx = torch.where(swap[:, None], idx.flip(1), idx)
+    return d[:, :k].contiguous().to(in_dev), idx[:, :k].contiguous().to(in_dev)
 
 
 def _exact_knn_blocks(q, t, k):
@@ -352,9 +403,10 @@ def knn_points(X_f, Y_f, K=1, metric="euclidean"):
         Y = _f32(Y_f, dev)
         d = (Y[idx.to(dev)] - X[:, None, :]).norm(p=2, dim=2)
         return d.to(in_dev), idx
-    A16, A32 = _rows_from_features(X_f, True, dev)
-    B16, B32 = _rows_from_features(Y_f, True, dev)
-    r = match_rows(A16, A32, B16, B32, A32.shape[0], B32.shape[0], 0, want_topk=False)
+    if X_f.shape[0] == 0 or Y_f.shape[0] < K:
+        raise ValueError(f"knn_points: {X_f.shape[0]} queries against {Y_f.shape[0]} targets for K={K}")
+    (A16, A32), (B16, B32), mu = _rows_pair(X_f, Y_f, dev)
+    r = match_rows(A16, A32, B16, B32, X_f.shape[0], Y_f.shape[0], 0, want_topk=False, center_B=mu)
     return r.dists[:, :K].to(in_dev), r.row_idx[:, :K].long().to(in_dev)
 
 
@@ -369,15 +421,17 @@ def get_correspondences_ratio_test(P1_F, P2_F, num_corres, metric="cosine", bidi
         return _ratio_test_euclidean(P1_F, P2_F, num_corres, bidirectional, ratio_test)
     dev = _device()
     in_dev = P1_F.device
-    A16, A32 = _rows_from_features(P1_F, True, dev)
-    B16, B32 = _rows_from_features(P2_F, True, dev)
-    n, m = A32.shape[0], B32.shape[0]
+    n, m = P1_F.shape[0], P2_F.shape[0]
+    if n == 0 or m < 2:  # the reference's K=2 search has nothing to return (the dense helpers raise the same way)
+        raise ValueError(f"get_correspondences_ratio_test: too few points to match ({n} vs {m})")
+    (A16, A32), (B16, B32), mu = _rows_pair(P1_F, P2_F, dev)
     if not bidirectional:
-        r = match_rows(A16, A32, B16, B32, n, m, num_corres, ratio_test)
+        r = match_rows(A16, A32, B16, B32, n, m, num_corres, ratio_test, center_B=mu)
         k = r.k
         return (r.sel_src[:k].long().to(in_dev), r.sel_dst[:k].long().to(in_dev), r.sel_weight[:k].to(in_dev))
-    r12 = match_rows(A16, A32, B16, B32, n, m, num_corres // 2, ratio_test)
-    r21 = match_rows(B16, B32, A16, A32, m, n, num_corres // 2, ratio_test)
+    r12 = match_rows(A16, A32, B16, B32, n, m, num_corres // 2, ratio_test, center_B=mu)
+    (B16, B32), (A16, A32), mu = _rows_pair(P2_F, P1_F, dev)  # the reverse direction swaps the query / target roles
+    r21 = match_rows(B16, B32, A16, A32, m, n, num_corres // 2, ratio_test, center_B=mu)
     idx1 = torch.cat((r12.sel_src[:r12.k], r21.sel_dst[:r21.k])).long()
     idx2 = torch.cat((r12.sel_dst[:r12.k], r21.sel_src[:r21.k])).long()
     w = torch.cat((r12.sel_weight[:r12.k], r21.sel_weight[:r21.k]))
@@ -510,12 +564,23 @@ def compute_binned_performance(y, x, x_bins):
 class _Side:
     """One image of a pair after kernel 1: compacted geometry + feature rows."""
 
-    __slots__ = ("n", "n_dev", "xyz", "uv", "rows16", "rows32", "rows_lo", "valid_idx", "taps")
+    __slots__ = ("n", "n_dev", "xyz", "uv", "rows16", "rows32", "rows_lo", "valid_idx", "taps", "center")
 
 
 def _match_sides(s0, s1, n0, n1, num_corr, ratio_test=True, n_dev=None, m_dev=None):
+    """s0 = query side, s1 = target side (prepared with the matching f16c roles, see _pair_maps)."""
     return match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, n0, n1, num_corr, ratio_test, n_dev=n_dev, m_dev=m_dev,
-                      A_lo=s0.rows_lo, B_lo=s1.rows_lo)
+                      A_lo=s0.rows_lo, B_lo=s1.rows_lo, center_B=s1.center)
+
+
+def _pair_maps(feat_0, feat_1, dev):
+    """channel-last fp32 maps of both images + the f16c centre of the target image (None for the other operand types):
+    -> (fm0, fm1, kw0, kw1) where fm = (src, C, h, w) and kw are the role keywords of kernel 1 for each side."""
+    fm0, fm1 = _feature_map(feat_0, dev), _feature_map(feat_1, dev)
+    if _CFG["dtype"] != "f16":
+        return fm0, fm1, {}, {}
+    mu = _center(fm1[0], fm1[0].shape[0])
+    return fm0, fm1, {"role": L.MV_ROLE_QUERY, "dotvec": mu}, {"role": L.MV_ROLE_TARGET, "center": mu}
 
 
 def _stage_depth(depth_dev, Kinv):
@@ -531,12 +596,12 @@ def _stage_depth(depth_dev, Kinv):
     return xyz_all, valid_idx, n_dev
 
 
-def _finish_depth(f, d, K, staged, n, synced, want_taps=False, rows=None):
+def _finish_depth(f, d, K, staged, n, synced, want_taps=False, rows=None, role=L.MV_ROLE_QUERY, center=None, dotvec=None):
     """projection to feature-map coordinates + kernel 1 for the n (live or upper-bound) points of one image.
-    f: the (C, h, w) feature map in either layout (see _feature_map)."""
+    f: the (C, h, w) feature map in either layout (see _feature_map), or the tuple _feature_map returned for it."""
     xyz_all, valid_idx, n_dev = staged
     dev = d.device
-    src, C, h, w = _feature_map(f, dev)
+    src, C, h, w = f if isinstance(f, tuple) else _feature_map(f, dev)
     H, W = d.shape[-2:]
     s = _Side()
     s.n_dev, s.valid_idx, s.n = n_dev, valid_idx, n
@@ -550,21 +615,22 @@ def _finish_depth(f, d, K, staged, n, synced, want_taps=False, rows=None):
     s.uv = None
     w16, w32, wlo = _row_format(rows)
     s.rows16, s.rows32, s.rows_lo = _sample(L.MV_SAMPLE_BILINEAR_ZEROS, src, C, h, w, coords, nd, n, True, w16, w32,
-                                            s.taps, wlo)
+                                            s.taps, wlo, role=role, center=center, dotvec=dotvec)
+    s.center = center
     return s
 
 
-def prepare_depth_side(feat, depth, K, Kinv, dev, sync=True, want_taps=False, rows=None):
+def prepare_depth_side(feat, depth, K, Kinv, dev, sync=True, want_taps=False, rows=None, **role_kw):
     """ScanNet-style preparation of one image.  correspondence.py:219-225, :147-176, :47-48.
 
     back-project depth -> keep z > 0 (row-major) -> project with K -> bilinear grid_sample coordinates
     (align_corners=False) -> kernel 1 (sample + L2 normalise).  sync=False keeps n on the device.
     """
     d = _f32(depth, dev)
-    _check_C(feat.shape[0])
+    _check_C(feat[1] if isinstance(feat, tuple) else feat.shape[0])
     staged = _stage_depth(d, Kinv)
     n = int(staged[2].item()) if sync else d.shape[-2] * d.shape[-1]
-    return _finish_depth(feat, d, K, staged, n, sync, want_taps, rows)
+    return _finish_depth(feat, d, K, staged, n, sync, want_taps, rows, **role_kw)
 
 
 def _stage_xyz(g):
@@ -576,10 +642,10 @@ def _stage_xyz(g):
     return valid_idx, n_dev
 
 
-def _finish_xyz(f, g, staged, n, synced, want_taps=False, rows=None):
+def _finish_xyz(f, g, staged, n, synced, want_taps=False, rows=None, role=L.MV_ROLE_QUERY, center=None, dotvec=None):
     valid_idx, n_dev = staged
     dev = g.device
-    src, C, h, w = _feature_map(f, dev)
+    src, C, h, w = f if isinstance(f, tuple) else _feature_map(f, dev)
     _, H, W = g.shape
     s = _Side()
     s.n_dev, s.valid_idx, s.n = n_dev, valid_idx, n
@@ -593,21 +659,22 @@ def _finish_xyz(f, g, staged, n, synced, want_taps=False, rows=None):
     s.taps = _empty((max(n, 1), 2), torch.int32, dev) if want_taps else None
     w16, w32, wlo = _row_format(rows)
     s.rows16, s.rows32, s.rows_lo = _sample(L.MV_SAMPLE_BICUBIC_CLAMP, src, C, h, w, coords, nd, n, True, w16, w32,
-                                            s.taps, wlo)
+                                            s.taps, wlo, role=role, center=center, dotvec=dotvec)
+    s.center = center
     return s
 
 
-def prepare_xyz_side(feat, xyz_grid, dev, sync=True, want_taps=False, rows=None):
+def prepare_xyz_side(feat, xyz_grid, dev, sync=True, want_taps=False, rows=None, **role_kw):
     """NAVI-style preparation of one image.  correspondence.py:240-252, :47-48.
 
     bicubic upsample of feat to the xyz grid's size evaluated only at the pixels with xyz_grid[2] > 0
     (row-major), + their xyz and pixel-centre uv, + kernel 1's L2 normalisation.
     """
     g = _f32(xyz_grid, dev)
-    _check_C(feat.shape[0])
+    _check_C(feat[1] if isinstance(feat, tuple) else feat.shape[0])
     staged = _stage_xyz(g)
     n = int(staged[1].item()) if sync else g.shape[-2] * g.shape[-1]
-    return _finish_xyz(feat, g, staged, n, sync, want_taps, rows)
+    return _finish_xyz(feat, g, staged, n, sync, want_taps, rows, **role_kw)
 
 
 _SIDE_STREAMS = {}
@@ -737,10 +804,13 @@ def estimate_correspondence_depth(feat_0, feat_1, depth_0, depth_1, K, num_corr=
         raise RuntimeError(f"too few valid points to match ({n0} vs {n1})")
     f0 = _upload_feat(feat_0, dev)
     f1, side = _on_side_stream(lambda: _upload_feat(feat_1, dev), dev)
-    s0 = _finish_depth(f0, d0, Kh, a0, n0, True)
+    _join_side(side, dev, f1)  # the target's map is needed first: its centre goes into the query's rows (f16c)
+    fm0, fm1, kw0, kw1 = _pair_maps(f0, f1, dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    s0 = _finish_depth(fm0, d0, Kh, a0, n0, True, **kw0)
     with torch.cuda.stream(side):
-        s1 = _finish_depth(f1, d1, Kh, a1, n1, True)
-    _join_side(side, dev, f1, s1)
+        s1 = _finish_depth(fm1, d1, Kh, a1, n1, True, **kw1)
+    _join_side(side, dev, s1)
     r = _match_sides(s0, s1, n0, n1, num_corr)
     k = r.k
     return _return_packed([_gather(s0.xyz, r.sel_src, k), _gather(s1.xyz, r.sel_dst, k), r.sel_weight[:k]], in_dev)
@@ -760,10 +830,13 @@ def estimate_correspondence_xyz(feat_0, feat_1, xyz_grid_0, xyz_grid_1, num_corr
         raise RuntimeError(f"too few valid points to match ({n0} vs {n1})")
     f0 = _upload_feat(feat_0, dev)
     f1, side = _on_side_stream(lambda: _upload_feat(feat_1, dev), dev)
-    s0 = _finish_xyz(f0, g0, a0, n0, True)
+    _join_side(side, dev, f1)  # the target's map is needed first: its centre goes into the query's rows (f16c)
+    fm0, fm1, kw0, kw1 = _pair_maps(f0, f1, dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    s0 = _finish_xyz(fm0, g0, a0, n0, True, **kw0)
     with torch.cuda.stream(side):
-        s1 = _finish_xyz(f1, g1, a1, n1, True)
-    _join_side(side, dev, f1, s1)
+        s1 = _finish_xyz(fm1, g1, a1, n1, True, **kw1)
+    _join_side(side, dev, s1)
     r = _match_sides(s0, s1, n0, n1, num_corr, ratio_test)
     k = r.k
     return _return_packed([_gather(s0.xyz, r.sel_src, k), _gather(s1.xyz, r.sel_dst, k), r.sel_weight[:k],

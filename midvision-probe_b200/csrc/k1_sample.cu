@@ -284,11 +284,19 @@ struct K1Params {
   const float* coords;
   const int32_t* n_dev;
   int n_max, C, h, w, normalize;
-  __nv_bfloat16* out_bf16;
-  __nv_bfloat16* out_lo;  // bf16(row - float(bf16(row))): with out_bf16 a 16-bit-mantissa copy of the fp32 row in 4 bytes
+  __nv_bfloat16* out_bf16;  // 16-bit rows: bf16 (fmt16 == 0, pitch C) or fp16 (fmt16 == 1, pitch C + 8: "f16c" rows)
+  __nv_bfloat16* out_lo;  // 16-bit residual of the 16-bit rounding: with out_bf16 a copy of the fp32 row in 4 bytes
   float* out_f32;
   int32_t* taps;
+  // ---- f16c rows (fmt16 == 1): kernel 2's fp16 operand = [fp16(row - center) | 8 augmentation columns]
+  int fmt16;            // 0 = bf16, 1 = fp16 + augmentation columns
+  int role;             // MV_ROLE_QUERY: aug = 3 fp16 pieces of r = row . dotvec;  MV_ROLE_TARGET: aug = (1, 1, 2^-11)
+  const float* center;  // (C) or NULL: subtracted from the normalised row before the 16-bit split
+  const float* dotvec;  // (C) or NULL
+  float* row_dot;       // (n) or NULL: r in fp32
 };
+
+constexpr float K1_LO_SCALE = 2048.f;  // the fp16 residual is stored * 2^11 so that it stays a normal number
 
 __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 __device__ __forceinline__ void fma4(float4& a, float w, const float4& v) {
@@ -336,6 +344,7 @@ struct K1WShared {
   int off[K1W_PMAX][4];  // float offsets of the point's four columns / taps in the window
   int g_start[K1W_PMAX], g_cnt[K1W_PMAX];
   float part[2][4][4][4];  // [parity][team][point of the group][warp of the team]: partial sums of squares
+  float partd[2][4][4][4]; // the same for row . dotvec
   float cy[4];
   int npts, ncols, xbase, y0, ngroups;
 };
@@ -372,6 +381,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
   const bool normalize = p.normalize != 0;
   int parity = 0;  // of this team's group counter: double-buffers sh.part
 
+  const bool f16c = p.fmt16 != 0;
+  const size_t pitch16 = f16c ? (size_t)C + 8 : (size_t)C;
+  const bool hasdot = p.dotvec != nullptr;
   auto put = [&](int pt, int c, float4 o, float inv) {
     o.x *= inv;  // inv == 1 when not normalising: exact
     o.y *= inv;
@@ -379,8 +391,30 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
     o.w *= inv;
     if (has32) __stcs(reinterpret_cast<float4*>(p.out_f32 + (size_t)pt * C + c), o);
     if (has16) {
-      __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+      if (p.center) {  // rows relative to the centre: the 16-bit rounding error scales with |row - center|
+        const float4 m = ld4(p.center + c);
+        o.x -= m.x;
+        o.y -= m.y;
+        o.z -= m.z;
+        o.w -= m.w;
+      }
       uint2 pk;
+      if (f16c) {
+        const __half2 lo = __floats2half2_rn(o.x, o.y), hi = __floats2half2_rn(o.z, o.w);
+        pk.x = *reinterpret_cast<const uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out_bf16) + (size_t)pt * pitch16 + c) = pk;
+        if (haslo) {  // residual * 2^11 (exact scaling): value = hi + lo * 2^-11 carries 22 mantissa bits
+          const float2 l = __half22float2(lo), h = __half22float2(hi);
+          const __half2 rl = __floats2half2_rn((o.x - l.x) * K1_LO_SCALE, (o.y - l.y) * K1_LO_SCALE);
+          const __half2 rh = __floats2half2_rn((o.z - h.x) * K1_LO_SCALE, (o.w - h.y) * K1_LO_SCALE);
+          pk.x = *reinterpret_cast<const uint32_t*>(&rl);
+          pk.y = *reinterpret_cast<const uint32_t*>(&rh);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__half*>(p.out_lo) + (size_t)pt * C + c) = pk;
+        }
+        return;
+      }
+      __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
       pk.x = *reinterpret_cast<uint32_t*>(&lo);
       pk.y = *reinterpret_cast<uint32_t*>(&hi);
       *reinterpret_cast<uint2*>(p.out_bf16 + (size_t)pt * C + c) = pk;
@@ -393,54 +427,102 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
       }
     }
   };
-  // x * (1 / max(||x||, eps)) from the per-warp partial sums of squares of the cnt rows of a group
-  auto inverse_norms = [&](float (&ss)[G], float (&inv)[G]) {
+  // the 8 augmentation columns of an f16c row (and the fp32 r), written by one lane per row
+  auto put_aug = [&](int pt, float r) {
+    if (p.row_dot) p.row_dot[pt] = r;
+    if (!f16c || !has16) return;
+    __half a[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = __float2half_rn(0.f);
+    if (p.role == MV_ROLE_TARGET) {
+      a[0] = __float2half_rn(1.f);
+      a[1] = __float2half_rn(1.f);
+      a[2] = __float2half_rn(1.f / K1_LO_SCALE);
+    } else {
+      a[0] = __float2half_rn(r);
+      const float r1 = r - __half2float(a[0]);
+      a[1] = __float2half_rn(r1);
+      a[2] = __float2half_rn((r1 - __half2float(a[1])) * K1_LO_SCALE);
+    }
+    *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out_bf16) + (size_t)pt * pitch16 + C) = *reinterpret_cast<const uint4*>(a);
+  };
+  // x * (1 / max(||x||, eps)) from the per-warp partial sums of squares of the cnt rows of a group; dd (raw row .
+  // dotvec) is reduced the same way and comes back as r = (normalised row) . dotvec
+  auto inverse_norms = [&](float (&ss)[G], float (&inv)[G], float (&dd)[G]) {
 #pragma unroll
     for (int j = 0; j < G; ++j) inv[j] = 1.f;
-    if (!normalize) return;
+    if (!normalize && !hasdot) return;
 #pragma unroll
     for (int j = 0; j < G; ++j) ss[j] = warp_sum(ss[j]);
+    if (hasdot) {
+#pragma unroll
+      for (int j = 0; j < G; ++j) dd[j] = warp_sum(dd[j]);
+    }
     if (W > 1) {
       if (lane == 0) {
 #pragma unroll
-        for (int j = 0; j < G; ++j) sh.part[parity][team][j][wsub] = ss[j];
+        for (int j = 0; j < G; ++j) {
+          sh.part[parity][team][j][wsub] = ss[j];
+          sh.partd[parity][team][j][wsub] = dd[j];
+        }
       }
       sm100::named_bar_sync(1 + team, W * 32);
 #pragma unroll
       for (int j = 0; j < G; ++j) {
-        float t = 0.f;
+        float t = 0.f, u = 0.f;
 #pragma unroll
-        for (int q = 0; q < W; ++q) t += sh.part[parity][team][j][q];  // fixed order: every warp gets the same bits
+        for (int q = 0; q < W; ++q) {  // fixed order: every warp gets the same bits
+          t += sh.part[parity][team][j][q];
+          u += sh.partd[parity][team][j][q];
+        }
         ss[j] = t;
+        dd[j] = u;
       }
       parity ^= 1;  // the next group's partials go to the other buffer; its barrier orders the re-use of this one
     }
+    if (normalize) {
 #pragma unroll
-    for (int j = 0; j < G; ++j) inv[j] = __frcp_rn(fmaxf(sqrtf(ss[j]), K1_NORM_EPS));
+      for (int j = 0; j < G; ++j) inv[j] = __frcp_rn(fmaxf(sqrtf(ss[j]), K1_NORM_EPS));
+    }
+#pragma unroll
+    for (int j = 0; j < G; ++j) dd[j] *= inv[j];
   };
+  auto dotacc = [&](const float4& v, const float4& d, float acc) {
+    acc = fmaf(v.x, d.x, acc);
+    acc = fmaf(v.y, d.y, acc);
+    acc = fmaf(v.z, d.z, acc);
+    return fmaf(v.w, d.w, acc);
+  };
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
   if (MODE == MV_SAMPLE_ROWS) {  // rows as they are, no window: a team per row
     for (int pt = pt_beg + team; pt < pt_end; pt += NTEAM) {
       const float* row = p.src + (size_t)pt * C;
-      float ss[G], inv[G];
+      float ss[G], inv[G], dd[G];
 #pragma unroll
-      for (int j = 0; j < G; ++j) ss[j] = 0.f;
+      for (int j = 0; j < G; ++j) ss[j] = dd[j] = 0.f;
       if (NITW > 0) {
         float4 acc[NITW > 0 ? NITW : 1];
 #pragma unroll
         for (int it = 0; it < NITW; ++it) {
           acc[it] = ld4(row + cbase + (it * 32 + lane) * 4);
           ss[0] = dot4(acc[it], ss[0]);
+          if (hasdot) dd[0] = dotacc(acc[it], ld4(p.dotvec + cbase + (it * 32 + lane) * 4), dd[0]);
         }
-        inverse_norms(ss, inv);
+        inverse_norms(ss, inv, dd);
 #pragma unroll
         for (int it = 0; it < NITW; ++it) put(pt, cbase + (it * 32 + lane) * 4, acc[it], inv[0]);
       } else {
-        if (normalize)
-          for (int c = lane * 4; c < C; c += 128) ss[0] = dot4(ld4(row + c), ss[0]);
-        inverse_norms(ss, inv);
+        if (normalize || hasdot)
+          for (int c = lane * 4; c < C; c += 128) {
+            const float4 v = ld4(row + c);
+            ss[0] = dot4(v, ss[0]);
+            if (hasdot) dd[0] = dotacc(v, ld4(p.dotvec + c), dd[0]);
+          }
+        inverse_norms(ss, inv, dd);
         for (int c = lane * 4; c < C; c += 128) put(pt, c, ld4(row + c), inv[0]);
       }
+      if (lane == 0 && wsub == 0) put_aug(pt, dd[0]);
     }
     return;
   }
@@ -579,41 +661,83 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
         fma4(o, wt[j][3], d);
         return o;
       };
-      float ss[G], inv[G];
+      float ss[G], inv[G], dd[G];
 #pragma unroll
-      for (int j = 0; j < G; ++j) ss[j] = 0.f;
+      for (int j = 0; j < G; ++j) ss[j] = dd[j] = 0.f;
       if (NITW > 0) {
         float4 acc[G][NITW > 0 ? NITW : 1];
 #pragma unroll
         for (int it = 0; it < NITW; ++it) {
           const int c = (it * 32 + lane) * 4;
           const float4 a = lds4(q0 + c), b = lds4(q1 + c), cc = lds4(q2 + c), d = lds4(q3 + c);
+          const float4 dv = hasdot ? ld4(p.dotvec + cbase + c) : zero4;
 #pragma unroll
           for (int j = 0; j < G; ++j) {
             acc[j][it] = blend(j, a, b, cc, d);
             ss[j] = dot4(acc[j][it], ss[j]);
+            if (hasdot) dd[j] = dotacc(acc[j][it], dv, dd[j]);
           }
         }
-        inverse_norms(ss, inv);
+        inverse_norms(ss, inv, dd);
 #pragma unroll
         for (int j = 0; j < G; ++j) {
           if (j < cnt) {
 #pragma unroll
             for (int it = 0; it < NITW; ++it) put(cur + t0 + j, cbase + (it * 32 + lane) * 4, acc[j][it], inv[j]);
+            if (lane == 0 && wsub == 0) put_aug(cur + t0 + j, dd[j]);
           }
         }
       } else {  // W == G == 1
-        if (normalize)
-          for (int c = lane * 4; c < C; c += 128)
-            ss[0] = dot4(blend(0, lds4(q0 + c), lds4(q1 + c), lds4(q2 + c), lds4(q3 + c)), ss[0]);
-        inverse_norms(ss, inv);
+        if (normalize || hasdot)
+          for (int c = lane * 4; c < C; c += 128) {
+            const float4 v = blend(0, lds4(q0 + c), lds4(q1 + c), lds4(q2 + c), lds4(q3 + c));
+            ss[0] = dot4(v, ss[0]);
+            if (hasdot) dd[0] = dotacc(v, ld4(p.dotvec + c), dd[0]);
+          }
+        inverse_norms(ss, inv, dd);
         for (int c = lane * 4; c < C; c += 128)
           put(cur + t0, c, blend(0, lds4(q0 + c), lds4(q1 + c), lds4(q2 + c), lds4(q3 + c)), inv[0]);
+        if (lane == 0) put_aug(cur + t0, dd[0]);
       }
     }
     __syncthreads();  // the window and the per-point scalars are rewritten by the next sub-run
     cur += npts;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// centre of a set of rows: mu = mean_p rows[p] / max(||rows[p]||, eps) over every `step`-th row.  Any vector near the
+// mean DIRECTION of the normalised rows works as the centre of f16c rows (the ranking is exact for every choice; the
+// fp16 rounding error of kernel 2's operands scales with |row - mu|).
+// ------------------------------------------------------------------------------------------
+__global__ void center_invnorm_kernel(const float* __restrict__ rows, int C, int n_max, const int32_t* __restrict__ n_dev,
+                                      int step, float* __restrict__ inv) {
+  const int n = n_dev ? min(*n_dev, n_max) : n_max;
+  const int cnt = (n + step - 1) / step;
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (q >= cnt) return;
+  const float* r = rows + (size_t)q * step * C;
+  float ss = 0.f;
+  for (int c = lane * 4; c < C; c += 128) ss = dot4(ld4(r + c), ss);
+  ss = warp_sum(ss);
+  if (lane == 0) inv[q] = 1.f / fmaxf(sqrtf(ss), K1_NORM_EPS);
+}
+
+__global__ void center_mean_kernel(const float* __restrict__ rows, int C, int n_max, const int32_t* __restrict__ n_dev,
+                                   int step, const float* __restrict__ inv, float* __restrict__ mu) {
+  const int n = n_dev ? min(*n_dev, n_max) : n_max;
+  const int cnt = (n + step - 1) / step;
+  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (c >= C) return;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+  int q = 0;
+  for (; q + 1 < cnt; q += 2) {  // two independent chains; fixed order: the centre is deterministic
+    fma4(a0, __ldg(inv + q), ld4(rows + (size_t)q * step * C + c));
+    fma4(a1, __ldg(inv + q + 1), ld4(rows + (size_t)(q + 1) * step * C + c));
+  }
+  if (q < cnt) fma4(a0, __ldg(inv + q), ld4(rows + (size_t)q * step * C + c));
+  const float s = cnt > 0 ? 1.f / (float)cnt : 0.f;
+  *reinterpret_cast<float4*>(mu + c) = make_float4((a0.x + a1.x) * s, (a0.y + a1.y) * s, (a0.z + a1.z) * s, (a0.w + a1.w) * s);
 }
 
 template <int MODE, int NITW, int W, int G, int OUTS, int THREADS, int MINB>
@@ -808,23 +932,40 @@ int mv_geom_keypoint_coords(const float* kps, int kp_stride, int n, float image_
   return MV_OK;
 }
 
-int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, const float* coords,
-                           const int32_t* n_dev, int n_max, int normalize, uint16_t* out_bf16, uint16_t* out_bf16_lo, float* out_f32,
-                           int32_t* taps, mv_stream_t stream) {
-  MV_REQUIRE(src && (out_bf16 || out_f32), MV_E_ARG, "mv_k1_sample_normalize: null src or no output");
+int mv_rows_center(const float* rows, int C, int n_max, const int32_t* n_dev, int step, float* inv_scratch, float* mu,
+                   mv_stream_t stream) {
+  MV_REQUIRE(rows && inv_scratch && mu, MV_E_ARG, "mv_rows_center: null pointer");
+  MV_REQUIRE(C > 0 && C % 4 == 0 && n_max > 0 && step > 0, MV_E_ARG, "mv_rows_center: C %% 4 == 0, n_max > 0 and step > 0 required");
+  MV_REQUIRE(((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(mu)) & 15) == 0, MV_E_ALIGN,
+             "mv_rows_center: rows and mu must be 16-byte aligned");
+  cudaStream_t st = mv_cuda_stream(stream);
+  const int cnt = (n_max + step - 1) / step;
+  center_invnorm_kernel<<<(cnt + 7) / 8, 256, 0, st>>>(rows, C, n_max, n_dev, step, inv_scratch);
+  MV_LAUNCH_CHECK();
+  center_mean_kernel<<<(C / 4 + 63) / 64, 64, 0, st>>>(rows, C, n_max, n_dev, step, inv_scratch, mu);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+static int k1_entry(const char* who, int mode, const float* src, int C, int h, int w, const float* coords, const int32_t* n_dev,
+                    int n_max, int normalize, int fmt16, int role, const float* center, const float* dotvec, uint16_t* out16,
+                    uint16_t* out16_lo, float* out_f32, float* row_dot, int32_t* taps, mv_stream_t stream) {
+  MV_REQUIRE(src && (out16 || out_f32), MV_E_ARG, "%s: null src or no output", who);
   MV_REQUIRE(mode == MV_SAMPLE_BILINEAR_ZEROS || mode == MV_SAMPLE_BICUBIC_CLAMP || mode == MV_SAMPLE_ROWS,
-             MV_E_ARG, "mv_k1_sample_normalize: unknown mode %d", mode);
+             MV_E_ARG, "%s: unknown mode %d", who, mode);
   MV_REQUIRE(mode == MV_SAMPLE_ROWS || (coords && h > 0 && w > 0), MV_E_ARG,
-             "mv_k1_sample_normalize: sampling modes need coords and a map size");
-  MV_REQUIRE(C > 0 && C % 8 == 0 && C <= 8192, MV_E_RANGE, "mv_k1_sample_normalize: C=%d must be a multiple of 8, <= 8192", C);
-  MV_REQUIRE(n_max >= 0, MV_E_ARG, "mv_k1_sample_normalize: negative n_max");
-  MV_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0, MV_E_ALIGN, "mv_k1_sample_normalize: src must be 16-byte aligned");
-  MV_REQUIRE(!out_f32 || (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0, MV_E_ALIGN,
-             "mv_k1_sample_normalize: out_f32 must be 16-byte aligned");
-  MV_REQUIRE(!out_bf16 || (reinterpret_cast<uintptr_t>(out_bf16) & 7) == 0, MV_E_ALIGN,
-             "mv_k1_sample_normalize: out_bf16 must be 8-byte aligned");
-  MV_REQUIRE(!out_bf16_lo || (out_bf16 && (reinterpret_cast<uintptr_t>(out_bf16_lo) & 7) == 0), MV_E_ARG,
-             "mv_k1_sample_normalize: out_bf16_lo needs out_bf16 and 8-byte alignment");
+             "%s: sampling modes need coords and a map size", who);
+  MV_REQUIRE(C > 0 && C % 8 == 0 && C <= 8192, MV_E_RANGE, "%s: C=%d must be a multiple of 8, <= 8192", who, C);
+  MV_REQUIRE(n_max >= 0, MV_E_ARG, "%s: negative n_max", who);
+  MV_REQUIRE(role == MV_ROLE_QUERY || role == MV_ROLE_TARGET, MV_E_ARG, "%s: unknown role %d", who, role);
+  MV_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0, MV_E_ALIGN, "%s: src must be 16-byte aligned", who);
+  MV_REQUIRE(!out_f32 || (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0, MV_E_ALIGN, "%s: out_f32 must be 16-byte aligned", who);
+  MV_REQUIRE(!out16 || (reinterpret_cast<uintptr_t>(out16) & (fmt16 ? 15 : 7)) == 0, MV_E_ALIGN,
+             "%s: the 16-bit rows must be %d-byte aligned", who, fmt16 ? 16 : 8);
+  MV_REQUIRE(!out16_lo || (out16 && (reinterpret_cast<uintptr_t>(out16_lo) & 7) == 0), MV_E_ARG,
+             "%s: the residual plane needs the 16-bit rows and 8-byte alignment", who);
+  MV_REQUIRE((!center || (reinterpret_cast<uintptr_t>(center) & 15) == 0) && (!dotvec || (reinterpret_cast<uintptr_t>(dotvec) & 15) == 0),
+             MV_E_ALIGN, "%s: center / dotvec must be 16-byte aligned", who);
   if (n_max == 0) return MV_OK;
 
   K1Params p;
@@ -836,15 +977,35 @@ int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, cons
   p.h = h;
   p.w = w;
   p.normalize = normalize;
-  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-  p.out_lo = reinterpret_cast<__nv_bfloat16*>(out_bf16_lo);
+  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out16);
+  p.out_lo = reinterpret_cast<__nv_bfloat16*>(out16_lo);
   p.out_f32 = out_f32;
   p.taps = taps;
+  p.fmt16 = fmt16;
+  p.role = role;
+  p.center = center;
+  p.dotvec = dotvec;
+  p.row_dot = row_dot;
 
   cudaStream_t st = mv_cuda_stream(stream);
   if (mode == MV_SAMPLE_BILINEAR_ZEROS) return launch_k1<MV_SAMPLE_BILINEAR_ZEROS>(p, st);
   if (mode == MV_SAMPLE_BICUBIC_CLAMP) return launch_k1<MV_SAMPLE_BICUBIC_CLAMP>(p, st);
   return launch_k1<MV_SAMPLE_ROWS>(p, st);
+}
+
+int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, const float* coords,
+                           const int32_t* n_dev, int n_max, int normalize, uint16_t* out_bf16, uint16_t* out_bf16_lo, float* out_f32,
+                           int32_t* taps, mv_stream_t stream) {
+  return k1_entry("mv_k1_sample_normalize", mode, src, C, h, w, coords, n_dev, n_max, normalize, 0, MV_ROLE_QUERY, nullptr, nullptr,
+                  out_bf16, out_bf16_lo, out_f32, nullptr, taps, stream);
+}
+
+int mv_k1_sample_f16c(int mode, const float* src, int C, int h, int w, const float* coords, const int32_t* n_dev, int n_max,
+                      int normalize, int role, const float* center, const float* dotvec, uint16_t* out_f16, uint16_t* out_f16_lo,
+                      float* out_f32, float* row_dot, int32_t* taps, mv_stream_t stream) {
+  MV_REQUIRE(out_f16, MV_E_ARG, "mv_k1_sample_f16c: out_f16 is required");
+  return k1_entry("mv_k1_sample_f16c", mode, src, C, h, w, coords, n_dev, n_max, normalize, 1, role, center, dotvec, out_f16,
+                  out_f16_lo, out_f32, row_dot, taps, stream);
 }
 
 }  // extern "C"

@@ -72,6 +72,8 @@ struct K2Params {
   const int32_t* n_dev;
   const int32_t* m_dev;
   int n_max, m_max, kblocks;
+  int tail_steps;   // MMA K-steps that carry data in the LAST k-block (1..4): K extents need not fill the 128-byte row
+  uint32_t ab_fmt;  // tcgen05 instruction-descriptor operand format: 0 = fp16, 1 = bf16 (kind::f16), 2 = tf32
   int clusters;     // clusters in the grid
   float4* partial;  // (clusters + n_sb_max) slots of MC * 128 rows x 2 column halves of {max1, idx1, max2, idx2}; slot = cluster + sb
   unsigned long long* col_best;
@@ -210,7 +212,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
     // ===================================== MMA issuer =======================================
     // The whole warp walks the (warp-uniform) loop; one elected lane issues.  Everything the issuing thread
     // executes per k-block is a barrier wait, two integer multiply-adds and ONE asm block.
-    constexpr uint32_t idesc = umma_idesc(TF32 ? 2 : 1, PAIR ? 2 * BM : BM, BN);
+    const uint32_t idesc = umma_idesc((int)p.ab_fmt, PAIR ? 2 * BM : BM, BN);
+    const int kb_last = p.kblocks - 1;
+    const uint32_t tail_steps = (uint32_t)p.tail_steps;
     const uint64_t desc0 = umma_desc_sw128(smem_base);  // stage 0, A tile; later tiles add (bytes >> 4) to the low word
     const bool leader = elect_one() && (!PAIR || rank == 0);  // PAIR: only the rank-0 CTA issues
     int stage = 0;
@@ -227,7 +231,10 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
         if (leader) {
           const uint64_t da = desc0 + (uint64_t)((uint32_t)stage * (STAGE_BYTES >> 4));
           const uint64_t db = da + (uint64_t)(A_STAGE_BYTES >> 4);
-          if (PAIR) umma_kblock_pair<TF32>(d_tmem, da, db, idesc, (uint32_t)(kb != 0), smem_u32(&bars->empty[stage]));
+          if (kb == kb_last && tail_steps < 4u) {  // partial last k-block (e.g. the 8 augmentation columns of f16c rows)
+            umma_kblock_tail<TF32, PAIR ? 2 : (MC == 1 ? 0 : 1)>(d_tmem, da, db, idesc, (uint32_t)(kb != 0), smem_u32(&bars->empty[stage]),
+                                                               (uint16_t)((1u << MC) - 1), tail_steps);
+          } else if (PAIR) umma_kblock_pair<TF32>(d_tmem, da, db, idesc, (uint32_t)(kb != 0), smem_u32(&bars->empty[stage]));
           else if (MC == 1) umma_kblock<TF32>(d_tmem, da, db, idesc, (uint32_t)(kb != 0), smem_u32(&bars->empty[stage]));
           else umma_kblock_mc<TF32>(d_tmem, da, db, idesc, (uint32_t)(kb != 0), smem_u32(&bars->empty[stage]),
                                     (uint16_t)((1u << MC) - 1));
@@ -433,7 +440,8 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 // (rows, C) row-major operand -> tensor map with a (box_rows x 128 bytes) 128B-swizzled box
-int make_operand_map(CUtensorMap* tm, const void* base, int rows, int C, bool tf32, int box_rows) {
+int make_operand_map(CUtensorMap* tm, const void* base, int rows, int C, int dtype, int box_rows) {
+  const bool tf32 = dtype == MV_DTYPE_TF32;
   EncodeTiledFn enc = get_encode_tiled();
   MV_REQUIRE(enc, MV_E_DRIVER, "mv_k2_sim_top2: cuTensorMapEncodeTiled is not available from this driver");
   const int esz = tf32 ? 4 : 2;
@@ -441,7 +449,9 @@ int make_operand_map(CUtensorMap* tm, const void* base, int rows, int C, bool tf
   cuuint64_t gstride[1] = {(cuuint64_t)C * esz};
   cuuint32_t box[2] = {(cuuint32_t)(ROW_BYTES / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+  const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                      : (dtype == MV_DTYPE_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  CUresult r = enc(tm, dt, 2,
                    const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   MV_REQUIRE(r == CUDA_SUCCESS, MV_E_DRIVER, "mv_k2_sim_top2: cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);
@@ -539,7 +549,7 @@ int mv_k2_sim_top2(const void* A, const void* B, int n_max, int m_max, int C, co
                    const int32_t* m_dev, int dtype, int cluster, float* row_val, int32_t* row_idx,
                    unsigned long long* col_best, void* workspace, size_t workspace_bytes, mv_stream_t stream) {
   MV_REQUIRE(A && B && row_val && row_idx && col_best && workspace, MV_E_ARG, "mv_k2_sim_top2: null pointer");
-  MV_REQUIRE(dtype == MV_DTYPE_BF16 || dtype == MV_DTYPE_TF32, MV_E_ARG, "mv_k2_sim_top2: unknown dtype %d", dtype);
+  MV_REQUIRE(dtype == MV_DTYPE_BF16 || dtype == MV_DTYPE_TF32 || dtype == MV_DTYPE_F16, MV_E_ARG, "mv_k2_sim_top2: unknown dtype %d", dtype);
   MV_REQUIRE(n_max > 0 && m_max > 0 && C > 0, MV_E_ARG, "mv_k2_sim_top2: sizes must be positive");
   MV_REQUIRE(n_max <= (1 << 20) && m_max <= (1 << 20), MV_E_RANGE, "mv_k2_sim_top2: at most 2^20 rows per side");
   const bool tf32 = dtype == MV_DTYPE_TF32;
@@ -574,13 +584,16 @@ int mv_k2_sim_top2(const void* A, const void* B, int n_max, int m_max, int C, co
   p.m_max = m_max;
   const int ke = tf32 ? 32 : 64;
   p.kblocks = (C + ke - 1) / ke;
+  const int kstep = ke / 4;  // K elements per MMA: 16 (16-bit operands) / 8 (tf32)
+  p.tail_steps = (C - (p.kblocks - 1) * ke + kstep - 1) / kstep;
+  p.ab_fmt = tf32 ? 2u : (dtype == MV_DTYPE_F16 ? 0u : 1u);
   p.partial = reinterpret_cast<float4*>(workspace);
   p.col_best = col_best;
 
   CUtensorMap tmA, tmB;
-  int rc = make_operand_map(&tmA, A, n_max, C, tf32, BM);
+  int rc = make_operand_map(&tmA, A, n_max, C, dtype, BM);
   if (rc) return rc;
-  rc = make_operand_map(&tmB, B, m_max, C, tf32, BN / mc);
+  rc = make_operand_map(&tmB, B, m_max, C, dtype, BN / mc);
   if (rc) return rc;
 
   cudaStream_t st = mv_cuda_stream(stream);

@@ -16,6 +16,7 @@
 //   evals/utils/transformations.py:27-36   transform_points_Rt
 //   evaluate_navi_correspondence.py:186-212, render_scannet_correspondence.py:211-217, :253-264  errors, recall
 //   evaluate_spair_correspondence.py:83-98, :121  SPair errors and PCK
+#include <cuda_fp16.h>
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -42,6 +43,27 @@ struct RowsSplit {
   const __nv_bfloat16* B_hi;
   const __nv_bfloat16* B_lo;
 };
+
+// f16c rows (mv_k1_sample_f16c): hi (pitch C + 8) + lo * 2^-11 (pitch C), target rows relative to a centre
+struct RowsF16c {
+  const __half* A_hi;
+  const __half* A_lo;
+  const __half* B_hi;
+  const __half* B_lo;
+  const float* center_B;  // may be null
+};
+
+__device__ __forceinline__ void f16c8(const __half* hi, const __half* lo, int c8, float (&out)[8]) {
+  const uint4 h = __ldg(reinterpret_cast<const uint4*>(hi) + c8), l = __ldg(reinterpret_cast<const uint4*>(lo) + c8);
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&hw[k]));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&lw[k]));
+    out[2 * k] = fmaf(b.x, 1.f / 2048.f, a.x);  // exact: 11 + 11 mantissa bits
+    out[2 * k + 1] = fmaf(b.y, 1.f / 2048.f, a.y);
+  }
+}
 
 __device__ __forceinline__ void acc5(float v, float a, float b, float& xx, float& aa, float& bb, float& xa, float& xb) {
   xx = fmaf(v, v, xx);
@@ -88,6 +110,31 @@ __global__ void __launch_bounds__(RATIO_THREADS, 6) k3_ratio_mutual_kernel(ROWS 
       bb = fmaf(b.x, b.x, bb); bb = fmaf(b.y, b.y, bb); bb = fmaf(b.z, b.z, bb); bb = fmaf(b.w, b.w, bb);
       xa = fmaf(v.x, a.x, xa); xa = fmaf(v.y, a.y, xa); xa = fmaf(v.z, a.z, xa); xa = fmaf(v.w, a.w, xa);
       xb = fmaf(v.x, b.x, xb); xb = fmaf(v.y, b.y, xb); xb = fmaf(v.z, b.z, xb); xb = fmaf(v.w, b.w, xb);
+    }
+  } else if constexpr (sizeof(ROWS) == sizeof(RowsF16c)) {
+    const size_t P = (size_t)C + 8;
+    const size_t ox = (size_t)i * C, o0 = (size_t)max(j0, 0) * C, o1 = (size_t)max(j1, 0) * C;
+    const __half* xh = rows.A_hi + (size_t)i * P;
+    const __half* ah = rows.B_hi + (size_t)max(j0, 0) * P;
+    const __half* bh = rows.B_hi + (size_t)max(j1, 0) * P;
+#pragma unroll 2
+    for (int c8 = lane; c8 < (C >> 3); c8 += 32) {
+      float v[8], a[8], b[8];
+      f16c8(xh, rows.A_lo + ox, c8, v);
+      f16c8(ah, rows.B_lo + o0, c8, a);
+      f16c8(bh, rows.B_lo + o1, c8, b);
+      if (rows.center_B) {
+        const float4 m0 = __ldg(reinterpret_cast<const float4*>(rows.center_B) + 2 * c8);
+        const float4 m1 = __ldg(reinterpret_cast<const float4*>(rows.center_B) + 2 * c8 + 1);
+        const float mu[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          a[k] += mu[k];
+          b[k] += mu[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc5(v[k], a[k], b[k], xx, aa, bb, xa, xb);
     }
   } else {
     const size_t ox = (size_t)i * C, o0 = (size_t)max(j0, 0) * C, o1 = (size_t)max(j1, 0) * C;
@@ -485,6 +532,25 @@ int mv_k3_ratio_mutual_split(const uint16_t* A_hi, const uint16_t* A_lo, const u
   RowsSplit rows{reinterpret_cast<const __nv_bfloat16*>(A_hi), reinterpret_cast<const __nv_bfloat16*>(A_lo),
                  reinterpret_cast<const __nv_bfloat16*>(B_hi), reinterpret_cast<const __nv_bfloat16*>(B_lo)};
   k3_ratio_mutual_kernel<RowsSplit><<<(n_max + rows_per_cta - 1) / rows_per_cta, 32 * rows_per_cta, 0, mv_cuda_stream(stream)>>>(
+      rows, C, n_dev, n_max, row_idx, col_best, ratio_test, dists, weight, mutual);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+int mv_k3_ratio_mutual_f16c(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* B_hi, const uint16_t* B_lo, int C,
+                            const float* center_B, const int32_t* n_dev, int n_max, int32_t* row_idx,
+                            const unsigned long long* col_best, int ratio_test, float* dists, float* weight, uint8_t* mutual,
+                            mv_stream_t stream) {
+  MV_REQUIRE(A_hi && A_lo && B_hi && B_lo && row_idx, MV_E_ARG, "mv_k3_ratio_mutual_f16c: null pointer");
+  MV_REQUIRE(C > 0 && C % 8 == 0, MV_E_ALIGN, "mv_k3_ratio_mutual_f16c: C=%d must be a positive multiple of 8", C);
+  MV_REQUIRE((((uintptr_t)A_hi | (uintptr_t)A_lo | (uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)center_B) & 15) == 0, MV_E_ALIGN,
+             "mv_k3_ratio_mutual_f16c: the row planes and the centre must be 16-byte aligned");
+  MV_REQUIRE(n_max >= 0, MV_E_ARG, "mv_k3_ratio_mutual_f16c: negative n_max");
+  if (n_max == 0) return MV_OK;
+  const int rows_per_cta = RATIO_THREADS / 32;
+  RowsF16c rows{reinterpret_cast<const __half*>(A_hi), reinterpret_cast<const __half*>(A_lo), reinterpret_cast<const __half*>(B_hi),
+                reinterpret_cast<const __half*>(B_lo), center_B};
+  k3_ratio_mutual_kernel<RowsF16c><<<(n_max + rows_per_cta - 1) / rows_per_cta, 32 * rows_per_cta, 0, mv_cuda_stream(stream)>>>(
       rows, C, n_dev, n_max, row_idx, col_best, ratio_test, dists, weight, mutual);
   MV_LAUNCH_CHECK();
   return MV_OK;

@@ -108,7 +108,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   return ((uint64_t)hi << 32) | lo;
 }
 
-// instruction descriptor: D fp32, A/B K-major, M x N tile.  fmt: 1 = bf16 (kind::f16), 2 = tf32 (kind::tf32)
+// instruction descriptor: D fp32, A/B K-major, M x N tile.  fmt: 0 = fp16, 1 = bf16 (both kind::f16), 2 = tf32 (kind::tf32)
 __host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) |
          ((uint32_t)(M >> 4) << 24);
@@ -270,6 +270,39 @@ __device__ __forceinline__ void umma_kblock_pair(uint32_t d_tmem, uint64_t a_des
         "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first), "r"(empty_bar), "h"((uint16_t)3)
         : "memory");
   }
+}
+
+// Last k-block of an operand whose K extent is not a multiple of the 128-byte row: only `steps` (1..3) of the four
+// MMAs carry data (the rest of the TMA box is zero fill), so only those are issued.  FORM: 0 = one CTA, 1 = commit
+// multicast to `mask`, 2 = CTA pair.
+template <bool TF32, int FORM>
+__device__ __forceinline__ void umma_kblock_tail(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                 uint32_t accumulate_first, uint32_t empty_bar, uint16_t mask, uint32_t steps) {
+#define MV_TAIL_BODY(GROUP, KIND, COMMIT)                                                                            \
+  asm volatile(                                                                                                      \
+      "{\n\t.reg .pred p, pt, q1, q2;\n\t.reg .b64 da, db;\n\t"                                                      \
+      "setp.ne.b32 p, %4, 0;\n\tsetp.eq.b32 pt, 0, 0;\n\tsetp.gt.u32 q1, %7, 1;\n\tsetp.gt.u32 q2, %7, 2;\n\t"          \
+      "tcgen05.mma.cta_group::" GROUP ".kind::" KIND " [%0], %1, %2, %3, p;\n\t"                                      \
+      "add.u64 da, %1, 2;\n\tadd.u64 db, %2, 2;\n\t"                                                                \
+      "@q1 tcgen05.mma.cta_group::" GROUP ".kind::" KIND " [%0], da, db, %3, pt;\n\t"                                 \
+      "add.u64 da, %1, 4;\n\tadd.u64 db, %2, 4;\n\t"                                                                \
+      "@q2 tcgen05.mma.cta_group::" GROUP ".kind::" KIND " [%0], da, db, %3, pt;\n\t" COMMIT "\n\t}" ::"r"(d_tmem),   \
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate_first), "r"(empty_bar), "h"(mask), "r"(steps)               \
+      : "memory")
+#define MV_COMMIT_ONE "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%5];"
+#define MV_COMMIT_MC "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%5], %6;"
+#define MV_COMMIT_PAIR "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%5], %6;"
+  if (FORM == 0) {
+    if (TF32) MV_TAIL_BODY("1", "tf32", MV_COMMIT_ONE); else MV_TAIL_BODY("1", "f16", MV_COMMIT_ONE);
+  } else if (FORM == 1) {
+    if (TF32) MV_TAIL_BODY("1", "tf32", MV_COMMIT_MC); else MV_TAIL_BODY("1", "f16", MV_COMMIT_MC);
+  } else {
+    if (TF32) MV_TAIL_BODY("2", "tf32", MV_COMMIT_PAIR); else MV_TAIL_BODY("2", "f16", MV_COMMIT_PAIR);
+  }
+#undef MV_TAIL_BODY
+#undef MV_COMMIT_ONE
+#undef MV_COMMIT_MC
+#undef MV_COMMIT_PAIR
 }
 
 __device__ __forceinline__ bool elect_one() {

@@ -139,8 +139,9 @@ def match_and_score_depth(feat_0, feat_1, depth_0, depth_1, K, Rt, num_corr, acc
     dev = C_._device()
     Kc = K.detach().float().cpu()
     Kh, Kinv = C_._host_mat(Kc), C_._host_mat(Kc.inverse())
-    s0, s1 = _both_sides(lambda: C_.prepare_depth_side(feat_0, depth_0, Kh, Kinv, dev, sync=sync),
-                         lambda: C_.prepare_depth_side(feat_1, depth_1, Kh, Kinv, dev, sync=sync), dev)
+    fm0, fm1, kw0, kw1 = C_._pair_maps(feat_0, feat_1, dev)
+    s0, s1 = _both_sides(lambda: C_.prepare_depth_side(fm0, depth_0, Kh, Kinv, dev, sync=sync, **kw0),
+                         lambda: C_.prepare_depth_side(fm1, depth_1, Kh, Kinv, dev, sync=sync, **kw1), dev)
     r = C_._match_sides(s0, s1, s0.n, s1.n, num_corr, n_dev=None if sync else s0.n_dev, m_dev=None if sync else s1.n_dev)
     acc.score(r, s0.xyz, s1.xyz, Rt, Kc)
     return r
@@ -150,8 +151,9 @@ def match_and_score_xyz(feat_0, feat_1, xyz_grid_0, xyz_grid_1, intrinsics, Rt, 
     """NAVI-shaped pair: estimate_correspondence_xyz (correspondence.py:235-263) + the caller's error /
     recall block (evaluate_navi_correspondence.py:186-212)."""
     dev = C_._device()
-    s0, s1 = _both_sides(lambda: C_.prepare_xyz_side(feat_0, xyz_grid_0, dev, sync=sync),
-                         lambda: C_.prepare_xyz_side(feat_1, xyz_grid_1, dev, sync=sync), dev)
+    fm0, fm1, kw0, kw1 = C_._pair_maps(feat_0, feat_1, dev)
+    s0, s1 = _both_sides(lambda: C_.prepare_xyz_side(fm0, xyz_grid_0, dev, sync=sync, **kw0),
+                         lambda: C_.prepare_xyz_side(fm1, xyz_grid_1, dev, sync=sync, **kw1), dev)
     r = C_._match_sides(s0, s1, s0.n, s1.n, num_corr, n_dev=None if sync else s0.n_dev, m_dev=None if sync else s1.n_dev)
     acc.score(r, s0.xyz, s1.xyz, Rt, intrinsics)
     return r
@@ -208,13 +210,14 @@ class GraphedPairMatcher:
         self.out = None
 
     def _body(self):
+        fm0, fm1, kw0, kw1 = C_._pair_maps(self.f0, self.f1, self.dev)
         if self.kind == "xyz":
-            s0, s1 = _both_sides(lambda: C_.prepare_xyz_side(self.f0, self.g0, self.dev, sync=False),
-                                 lambda: C_.prepare_xyz_side(self.f1, self.g1, self.dev, sync=False), self.dev)
+            s0, s1 = _both_sides(lambda: C_.prepare_xyz_side(fm0, self.g0, self.dev, sync=False, **kw0),
+                                 lambda: C_.prepare_xyz_side(fm1, self.g1, self.dev, sync=False, **kw1), self.dev)
         else:
             Kd, Kinvd = L.ptr(self.Kdev), c_void_p(self.Kdev.data_ptr() + 36)
-            s0, s1 = _both_sides(lambda: C_.prepare_depth_side(self.f0, self.g0, Kd, Kinvd, self.dev, sync=False),
-                                 lambda: C_.prepare_depth_side(self.f1, self.g1, Kd, Kinvd, self.dev, sync=False), self.dev)
+            s0, s1 = _both_sides(lambda: C_.prepare_depth_side(fm0, self.g0, Kd, Kinvd, self.dev, sync=False, **kw0),
+                                 lambda: C_.prepare_depth_side(fm1, self.g1, Kd, Kinvd, self.dev, sync=False, **kw1), self.dev)
         r = C_._match_sides(s0, s1, s0.n, s1.n, self.num_corr, self.ratio_test, n_dev=s0.n_dev, m_dev=s1.n_dev)
         if self.with_outputs:
             # the helper's return tuple + the live counts in one buffer of column blocks (mv_pack_matches):
@@ -295,10 +298,10 @@ class GraphedPairMatcher:
 
     @property
     def launches_per_replay(self):
-        # per image: (backproject) + compact + coords + chw_to_hwc + kernel 1; per pair: kernel 2 (2) + ratio + top-k
+        # per image: (backproject) + compact + coords + chw_to_hwc + kernel 1; per pair: (centre: 2) + kernel 2 (2) + ratio + top-k
         zero_copy = self.feat_layout == "hwc" and self.feat_dtype == torch.float32
         per_side = (5 if self.kind == "depth" else 4) - (1 if zero_copy else 0)
-        return 2 * per_side + 4 + (1 if self.with_outputs else 0)
+        return 2 * per_side + 4 + (2 if C_._CFG["dtype"] == "f16" else 0) + (1 if self.with_outputs else 0)
 
 
 class PairPipeline:

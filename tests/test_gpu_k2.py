@@ -11,6 +11,8 @@ pytestmark = pytest.mark.gpu
 def round_operand(x, dtype):
     if dtype == "bf16":
         return x.to(torch.bfloat16).float()
+    if dtype == "f16":
+        return x.to(torch.float16).float()
     # tf32-exact: keep 10 explicit mantissa bits so the tensor core neither rounds nor truncates
     bits = x.contiguous().view(torch.int32)
     return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
@@ -22,8 +24,9 @@ def run_k2(mv, A, B, dtype, cluster, n_live=None, m_live=None):
     n, C = A.shape
     m = B.shape[0]
     dev = torch.device("cuda")
-    Ad = A.cuda().to(torch.bfloat16).contiguous() if dtype == "bf16" else A.cuda().contiguous()
-    Bd = B.cuda().to(torch.bfloat16).contiguous() if dtype == "bf16" else B.cuda().contiguous()
+    t16 = {"bf16": torch.bfloat16, "f16": torch.float16}.get(dtype)
+    Ad = A.cuda().to(t16).contiguous() if t16 else A.cuda().contiguous()
+    Bd = B.cuda().to(t16).contiguous() if t16 else B.cuda().contiguous()
     row_val = torch.full((n, 2), 7.0, device=dev)
     row_idx = torch.full((n, 2), -9, dtype=torch.int32, device=dev)
     col_best = torch.empty(m, dtype=torch.int64, device=dev)
@@ -32,7 +35,7 @@ def run_k2(mv, A, B, dtype, cluster, n_live=None, m_live=None):
     nd = torch.tensor([n_live], dtype=torch.int32, device=dev) if n_live is not None else None
     md = torch.tensor([m_live], dtype=torch.int32, device=dev) if m_live is not None else None
     L.call("mv_k2_sim_top2", L.ptr(Ad), L.ptr(Bd), n, m, C, L.ptr(nd), L.ptr(md),
-           L.MV_DTYPE_BF16 if dtype == "bf16" else L.MV_DTYPE_TF32, cluster, L.ptr(row_val), L.ptr(row_idx),
+           {"bf16": L.MV_DTYPE_BF16, "f16": L.MV_DTYPE_F16, "tf32": L.MV_DTYPE_TF32}[dtype], cluster, L.ptr(row_val), L.ptr(row_idx),
            L.ptr(col_best), L.ptr(ws), c_size_t(ws_bytes), C_._stream())
     col_val = torch.empty(m, device=dev)
     col_idx = torch.empty(m, dtype=torch.int32, device=dev)
@@ -79,20 +82,21 @@ def check(mv, n, m, C, dtype, cluster, seed=0, n_live=None, m_live=None, scale=1
     return float(clear1.float().mean())
 
 
+# K extents that end inside a 128-byte row exercise the partial last k-block (C + 8 of the f16c rows: 776, 2056, 3080)
 SHAPES = [
     (1, 1, 8), (1, 2, 8), (5, 3, 16), (128, 256, 64), (129, 257, 64), (300, 280, 64), (127, 255, 72),
-    (700, 1500, 128), (1000, 777, 768), (2048, 2048, 256), (196, 20, 768), (20, 196, 768),
+    (700, 1500, 128), (1000, 777, 768), (2048, 2048, 256), (196, 20, 768), (20, 196, 768), (260, 300, 776), (150, 520, 104),
 ]
 
 
 @pytest.mark.parametrize("n,m,C", SHAPES)
-@pytest.mark.parametrize("dtype", ["bf16", "tf32"])
+@pytest.mark.parametrize("dtype", ["bf16", "tf32", "f16"])
 def test_k2_single_cta_schedule(mv, n, m, C, dtype):
     check(mv, n, m, C, dtype, cluster=0)
 
 
-@pytest.mark.parametrize("n,m,C", [(1, 2, 8), (129, 257, 64), (700, 1500, 128), (1000, 777, 768), (2048, 2048, 256)])
-@pytest.mark.parametrize("dtype", ["bf16", "tf32"])
+@pytest.mark.parametrize("n,m,C", [(1, 2, 8), (129, 257, 64), (700, 1500, 128), (1000, 777, 768), (2048, 2048, 256), (600, 700, 2056)])
+@pytest.mark.parametrize("dtype", ["bf16", "tf32", "f16"])
 @pytest.mark.parametrize("cluster", [2, 4, 20])  # 20 = MV_CLUSTER_PAIR: cta_group::2, one 256 x 256 MMA per two SMs
 def test_k2_multicast_clusters(mv, n, m, C, dtype, cluster):
     check(mv, n, m, C, dtype, cluster=cluster)
@@ -124,7 +128,7 @@ def test_k2_repeatable(mv):
     assert all(torch.equal(x, y) for x, y in zip(a, b))
 
 
-@pytest.mark.parametrize("dtype,cluster", [("bf16", 0), ("bf16", 2), ("tf32", 0), ("bf16", 20), ("tf32", 20)])
+@pytest.mark.parametrize("dtype,cluster", [("bf16", 0), ("bf16", 2), ("tf32", 0), ("bf16", 20), ("tf32", 20), ("f16", -1)])
 def test_k2_full_size_properties(mv, syn, dtype, cluster):
     """19200 x 19200 x 768 (BASELINE.json stress config): too big for an element-wise CPU check, so
     size-independent properties: B = A => every row's arg-max is itself, mutual everywhere; and a sampled

@@ -7,6 +7,8 @@ import torch.nn.functional as F
 
 from oracle import restated
 
+DEFAULT_DTYPE = "f16"  # correspondence.DEFAULT_DTYPE: what the finally blocks restore
+
 pytestmark = pytest.mark.gpu
 
 
@@ -149,7 +151,7 @@ def test_spair_errors(mv, syn, idx, shape):
         es, en, isame, inn, pred = mv.spair.compute_errors_from_features(
             p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"], p["image_size"], hits=hits, return_heatmap_argmax=True)
     finally:
-        mv.correspondence.set_match_precision(dtype="bf16")
+        mv.correspondence.set_match_precision(dtype=DEFAULT_DTYPE)
     oes, oen, oisame, oinn, heat = restated.spair_compute_errors(p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"],
                                                                  p["image_size"], return_pred=True)
     # arg-max identical wherever the oracle's top-2 heat-map gap exceeds 1e-3 (north-star tolerance)
@@ -173,7 +175,7 @@ def test_spair_confusion_and_dataset_recall(mv, syn):
     try:
         recall, conf = mv.spair.evaluate_pairs(pairs, pck_thresh=0.10)
     finally:
-        mv.correspondence.set_match_precision(dtype="bf16")
+        mv.correspondence.set_match_precision(dtype=DEFAULT_DTYPE)
     errs, src, tgt = [], [], []
     for p in pairs:
         es, en, isame, inn = restated.spair_compute_errors(p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"], p["image_size"])
@@ -280,7 +282,7 @@ def test_spair_batch_equals_per_pair_path_and_edge_cases(mv, syn):
             assert torch.equal(a[2], keep)
         r1, c1 = sp.evaluate_pairs(pairs, kp_max=30)
     finally:
-        mv.correspondence.set_match_precision(dtype="bf16")
+        mv.correspondence.set_match_precision(dtype=DEFAULT_DTYPE)
     r2, c2 = sp.evaluate_batches([dict(feats=feats, kps_i=ki, kps_j=kj, thresh_scale=ts, image_size=224)], kp_max=30)
     assert int(c1.sum()) == int(c2.sum()) and (c1 - c2).abs().sum() <= 4 and abs(r1 - r2) <= 100.0 * 2 / max(int(c1.sum()), 1) + 1e-6
     # degenerate sizes
@@ -315,7 +317,7 @@ def test_spair_paths_vs_reference_golden(mv, syn, golden):
     try:
         a = mv.spair.compute_errors_from_features(p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"], p["image_size"])
     finally:
-        mv.correspondence.set_match_precision(dtype="bf16")
+        mv.correspondence.set_match_precision(dtype=DEFAULT_DTYPE)
     assert torch.equal(a[2], want_isame)
     same = a[3] == want_inn
     assert same.float().mean() >= 0.9   # tf32 ranking: only near-ties of the heat map may differ

@@ -10,6 +10,8 @@ import torch.nn.functional as F
 
 from oracle import restated
 
+DEFAULT_DTYPE = "f16"  # correspondence.DEFAULT_DTYPE: what the finally blocks restore
+
 pytestmark = pytest.mark.gpu
 
 SCANNET_SMALL = dict(C=64, h=6, w=8, H=24, W=32)
@@ -29,7 +31,7 @@ def set_equal_modulo_ties(w_got, w_ref, tol):
     assert (w_got - w_ref).abs().max() <= tol, float((w_got - w_ref).abs().max())
 
 
-@pytest.mark.parametrize("dtype", ["tf32", "bf16"])
+@pytest.mark.parametrize("dtype", ["f16", "tf32", "bf16"])
 @pytest.mark.parametrize("tag,coherent", [("coh", True), ("rnd", False)])
 def test_depth_helper_vs_reference_golden(mv, syn, golden, dtype, tag, coherent):
     g = golden(f"scannet_small_{tag}")
@@ -38,21 +40,22 @@ def test_depth_helper_vs_reference_golden(mv, syn, golden, dtype, tag, coherent)
     try:
         x0, x1, w = mv.correspondence.estimate_correspondence_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], p["K"].clone(), 100)
     finally:
-        mv.correspondence.set_match_precision(dtype="bf16")
+        mv.correspondence.set_match_precision(dtype=DEFAULT_DTYPE)
     assert x0.device.type == "cpu" and x0.shape == (100, 3) and w.shape == (100,)
     assert (w[1:] <= w[:-1]).all()
-    tol = 2e-3 if dtype == "tf32" else 2e-2
+    tol = 2e-2 if dtype == "bf16" else 2e-3  # the default (f16c) is held to the tf32 tolerance
     set_equal_modulo_ties(w, t(g["corr_dist"]), tol)
     # every returned match whose weight is clear of the k-th weight by tol must be in the reference's set
     ref0 = {tuple(np.round(r, 5)) for r in g["corr_xyz0"]}
     clear = w > (w[-1] + tol)
     got0 = [tuple(np.round(r, 5)) for r in x0[clear].numpy()]
-    assert sum(r in ref0 for r in got0) >= 0.97 * len(got0)
+    assert sum(r in ref0 for r in got0) >= (0.97 if dtype == "bf16" else 0.99) * len(got0)
     e3, _ = restated.pair_errors(x0, x1, p["Rt"], p["K"])
     for th in THR3:
         r_got = 100.0 * (e3 < th).float().mean().item()
         r_ref = 100.0 * float((g["err3d"] < th).mean())
-        assert abs(r_got - r_ref) <= 2.0  # k = 100 matches: one match = 1 pp; the 0.1 pp gate is tested at full size
+        # k = 100 matches: one match = 1 pp; the 0.1 pp gate is tested at full size
+        assert abs(r_got - r_ref) <= (2.0 if dtype == "bf16" else 1.0) + 1e-4
 
 
 @pytest.mark.parametrize("tag,coherent", [("coh", True), ("rnd", False)])
@@ -64,7 +67,7 @@ def test_xyz_helper_vs_reference_golden(mv, syn, golden, tag, coherent):
         out = mv.correspondence.estimate_correspondence_xyz(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], 100)
         nr = mv.correspondence.estimate_correspondence_xyz(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], 100, ratio_test=False)
     finally:
-        mv.correspondence.set_match_precision(dtype="bf16")
+        mv.correspondence.set_match_precision(dtype=DEFAULT_DTYPE)
     assert [tuple(o.shape) for o in out] == [(100, 3), (100, 3), (100,), (100, 2), (100, 2)]
     set_equal_modulo_ties(out[2], t(g["c_dist"]), 2e-3)
     set_equal_modulo_ties(nr[2], t(g["nr_dist"]), 1e-5)
@@ -84,7 +87,7 @@ def test_rows_helper_vs_reference_golden(mv, golden):
         i1, i2, w = C_.get_correspondences_ratio_test(X, Y, 50)
         b1, b2, bw = C_.get_correspondences_ratio_test(X, Y, 50, bidirectional=True)
     finally:
-        C_.set_match_precision(dtype="bf16")
+        C_.set_match_precision(dtype=DEFAULT_DTYPE)
     o = restated.similarity_top2_and_mutual(X, Y)
     clear = o["row_gap"] > 1e-3
     assert i.dtype == torch.int64 and torch.equal(i[clear, 0], t(g["idx"])[clear, 0])
@@ -171,7 +174,7 @@ def full_size_case(mv, kind, dtype, syn):
             ref = restated.estimate_correspondence_xyz(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], 1000)
         d, i = C_.knn_points(f0, f1, 2, "cosine")
     finally:
-        C_.set_match_precision(dtype="bf16")
+        C_.set_match_precision(dtype=DEFAULT_DTYPE)
     o = restated.similarity_top2_and_mutual(f0, f1)
     clear = o["row_gap"] > 1e-3
     frac = float(clear.float().mean())
@@ -190,18 +193,18 @@ def full_size_case(mv, kind, dtype, syn):
     return frac, rec
 
 
-@pytest.mark.parametrize("dtype", ["bf16", "tf32"])
+@pytest.mark.parametrize("dtype", ["f16", "bf16", "tf32"])
 def test_scannet_full_size_parity(mv, syn, dtype):
     frac, rec = full_size_case(mv, "scannet", dtype, syn)
     print(f"scannet-shaped {dtype}: rows compared (gap > 1e-3) = {100 * frac:.1f}%, recall@thr (got, ref) = {rec}")
-    assert frac > 0.05
+    assert frac > 0.55  # DESIGN.md publishes 59 % for the Gaussian ScanNet-shaped pair
 
 
-@pytest.mark.parametrize("dtype", ["bf16", "tf32"])
+@pytest.mark.parametrize("dtype", ["f16", "bf16", "tf32"])
 def test_navi_full_size_parity(mv, syn, dtype):
     frac, rec = full_size_case(mv, "navi", dtype, syn)
     print(f"navi-shaped {dtype}: rows compared (gap > 1e-3) = {100 * frac:.1f}%, recall@thr (got, ref) = {rec}")
-    assert frac > 0.05
+    assert frac > 0.70  # DESIGN.md publishes 73 % for the Gaussian NAVI-shaped pair
 
 
 def test_fused_scoring_equals_helper_plus_oracle_errors(mv, syn):

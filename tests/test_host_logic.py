@@ -14,6 +14,8 @@ import torch.multiprocessing as mp
 from conftest import ROOT
 from oracle import restated
 
+DEFAULT_DTYPE = "f16"  # correspondence.DEFAULT_DTYPE: what the finally blocks restore
+
 THR3 = [0.01, 0.02, 0.05]
 THR2 = [5, 25, 50]
 
@@ -113,7 +115,7 @@ def test_feature_layout_and_dtype_detection(mv):
     try:
         assert C_._row_format("split") == (False, True, False)  # the tf32 path always keeps fp32 rows
     finally:
-        C_.set_match_precision(dtype="bf16")
+        C_.set_match_precision(dtype=DEFAULT_DTYPE)
 
 
 def test_argument_errors_mirror_the_reference(mv):
