@@ -136,14 +136,15 @@ int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, cons
  *     target row  = [ fp16(b - mu) (C) | 1, 1, 2^-11, 0, 0, 0, 0, 0 ]
  *     query  row  = [ fp16(a)      (C) | p0, p1, p2, 0, 0, 0, 0, 0 ]     p0 + p1 + p2 * 2^-11 = r = a . mu  (fp32)
  * have the inner product a . b with the rounding error of the target scaled by |b - mu| instead of |b|; the ranking
- * along a row AND along a column is that of a . b for every mu.  Row pitch C + 8 halfs; kernel 2 is called with
- * C + 8 columns and MV_DTYPE_F16.  out_f16_lo (optional, (n, C) halfs): fp16((y - float(out_f16)) * 2^11) with
+ * along a row AND along a column is that of a . b for every mu.  Row pitch `pitch` >= C + 8 halfs (a multiple of 64 keeps
+ * kernel 2's 128-byte TMA rows aligned: an unaligned pitch costs ~20 % of kernel 2); kernel 2 is called through
+ * mv_k2_sim_top2_ld with C + 8 columns, that pitch and MV_DTYPE_F16 (columns beyond C + 8 are never read).  out_f16_lo (optional, (n, C) halfs): fp16((y - float(out_f16)) * 2^11) with
  * y = row - center, so that y = hi + lo * 2^-11 to 2^-22 relative (consumed by mv_k3_ratio_mutual_f16c).
  * role: MV_ROLE_QUERY uses dotvec (= the target's centre; NULL -> r = 0), MV_ROLE_TARGET uses center.  Both may be
  * given.  row_dot (optional, n floats): r.  Other arguments as mv_k1_sample_normalize. */
 int mv_k1_sample_f16c(int mode, const float* src, int C, int h, int w, const float* coords, const int32_t* n_dev, int n_max,
-                      int normalize, int role, const float* center, const float* dotvec, uint16_t* out_f16, uint16_t* out_f16_lo,
-                      float* out_f32, float* row_dot, int32_t* taps, mv_stream_t stream);
+                      int normalize, int role, const float* center, const float* dotvec, uint16_t* out_f16, int pitch,
+                      uint16_t* out_f16_lo, float* out_f32, float* row_dot, int32_t* taps, mv_stream_t stream);
 
 /* mu (C floats) = mean over every `step`-th row p < n of rows[p] / max(||rows[p]||, 1e-12); rows (n, C) fp32 (a channel-last
  * feature map or a set of feature rows).  inv_scratch: ceil(n_max / step) floats.  Deterministic. */
@@ -166,6 +167,11 @@ size_t mv_k2_workspace_bytes(int n_max, int m_max);
 int mv_k2_sim_top2(const void* A, const void* B, int n_max, int m_max, int C, const int32_t* n_dev,
                    const int32_t* m_dev, int dtype, int cluster, float* row_val, int32_t* row_idx,
                    unsigned long long* col_best, void* workspace, size_t workspace_bytes, mv_stream_t stream);
+/* the same with explicit row pitches lda / ldb (elements, >= C, a multiple of 16 bytes): only the first C columns of a row
+ * are read (f16c rows: C = channels + 8, pitch rounded up to 128 bytes) */
+int mv_k2_sim_top2_ld(const void* A, int lda, const void* B, int ldb, int n_max, int m_max, int C, const int32_t* n_dev,
+                      const int32_t* m_dev, int dtype, int cluster, float* row_val, int32_t* row_idx,
+                      unsigned long long* col_best, void* workspace, size_t workspace_bytes, mv_stream_t stream);
 int mv_k2_unpack_col(const unsigned long long* col_best, int m, float* col_val, int32_t* col_idx, mv_stream_t stream);
 
 /* ---- kernel 3: fp32 distance recompute, ratio test, mutual check, selection, scoring ---- */
@@ -182,10 +188,10 @@ int mv_k3_ratio_mutual_split(const uint16_t* A_hi, const uint16_t* A_lo, const u
                              const int32_t* n_dev, int n_max, int32_t* row_idx, const unsigned long long* col_best,
                              int ratio_test, float* dists, float* weight, uint8_t* mutual, mv_stream_t stream);
 
-/* The same on f16c rows (mv_k1_sample_f16c): A_hi (n, C + 8) / A_lo (n, C) query rows, B_hi / B_lo target rows,
+/* The same on f16c rows (mv_k1_sample_f16c): A_hi (n, pitch) / A_lo (n, C) query rows, B_hi / B_lo target rows,
  * center_B (C floats or NULL) the centre the target rows are relative to; every element is rebuilt as
  * float(hi) + float(lo) * 2^-11 (+ center_B) before the identical fp32 arithmetic. */
-int mv_k3_ratio_mutual_f16c(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* B_hi, const uint16_t* B_lo, int C,
+int mv_k3_ratio_mutual_f16c(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* B_hi, const uint16_t* B_lo, int C, int pitch,
                             const float* center_B, const int32_t* n_dev, int n_max, int32_t* row_idx,
                             const unsigned long long* col_best, int ratio_test, float* dists, float* weight, uint8_t* mutual,
                             mv_stream_t stream);

@@ -145,17 +145,17 @@ def _sample(mode, src, C, h, w, coords, n_dev, n_max, normalize, want_bf16, want
             role=L.MV_ROLE_QUERY, center=None, dotvec=None):
     """kernel 1.  src: (h*w, C) channel-last (or (n, C) rows for MV_SAMPLE_ROWS).
     Returns (16-bit rows, fp32 rows, 16-bit residual rows); the ones not asked for are None.
-    The 16-bit rows are bf16 (n, C) for the "bf16" operand type and fp16 "f16c" rows (n, C + 8) for "f16":
+    The 16-bit rows are bf16 (n, C) for the "bf16" operand type and fp16 "f16c" rows (n, f16c_pitch(C)) for "f16":
     role / center / dotvec are the f16c parameters of mv_k1_sample_f16c."""
     dev = src.device
     f16 = _CFG["dtype"] == "f16" and (want_bf16 or want_lo)
     t16 = torch.float16 if f16 else torch.bfloat16
-    o16 = _empty((max(n_max, 1), C + 8 if f16 else C), t16, dev) if (want_bf16 or want_lo) else None
+    o16 = _empty((max(n_max, 1), L.f16c_pitch(C) if f16 else C), t16, dev) if (want_bf16 or want_lo) else None
     olo = _empty((max(n_max, 1), C), t16, dev) if want_lo else None
     o32 = _empty((max(n_max, 1), C), torch.float32, dev) if want_f32 else None
     if n_max > 0 and f16:
         L.call("mv_k1_sample_f16c", mode, L.ptr(src), C, h, w, L.ptr(coords), L.ptr(n_dev), n_max, int(normalize), role,
-               L.ptr(center), L.ptr(dotvec), L.ptr(o16), L.ptr(olo), L.ptr(o32), None, L.ptr(taps), _stream())
+               L.ptr(center), L.ptr(dotvec), L.ptr(o16), o16.shape[1], L.ptr(olo), L.ptr(o32), None, L.ptr(taps), _stream())
     elif n_max > 0:
         L.call("mv_k1_sample_normalize", mode, L.ptr(src), C, h, w, L.ptr(coords), L.ptr(n_dev), n_max, int(normalize),
                L.ptr(o16), L.ptr(olo), L.ptr(o32), L.ptr(taps), _stream())
@@ -188,10 +188,10 @@ class MatchResult:
 
 
 def match_rows(A16, A32, B16, B32, n, m, num_corr, ratio_test=True, n_dev=None, m_dev=None, want_topk=True, run_k3=True,
-               A_lo=None, B_lo=None, center_B=None):
+               A_lo=None, B_lo=None, center_B=None, C=None):
     """kernel 2 + kernel 3 on prepared rows.
 
-    A16/B16: (n, C)/(m, C) bf16 rows or (n, C + 8)/(m, C + 8) fp16 f16c rows (query / target role; None when the
+    A16/B16: (n, C)/(m, C) bf16 rows or (n, pitch)/(m, pitch) fp16 f16c rows (query / target role; None when the
     tf32 path is selected), A32/B32: fp32 rows -- or None when the split form is used: A_lo/B_lo are then the 16-bit
     residual planes of A16/B16.  center_B: the centre f16c target rows are relative to (None: not centred).
     Mirrors get_correspondences_ratio_test (correspondence.py:63-102, bidirectional=False):
@@ -202,7 +202,7 @@ def match_rows(A16, A32, B16, B32, n, m, num_corr, ratio_test=True, n_dev=None, 
     dev = ref.device
     tf32 = _CFG["dtype"] == "tf32"
     f16 = _CFG["dtype"] == "f16"
-    C = ref.shape[1] - (8 if (f16 and A32 is None) else 0)
+    C = ref.shape[1] if A32 is not None else (C if C is not None else ref.shape[1])
     split = A32 is None or B32 is None
     if split and (tf32 or A_lo is None or B_lo is None or A16 is None or B16 is None):
         raise ValueError("split rows need a 16-bit operand type and both residual planes")
@@ -216,12 +216,15 @@ def match_rows(A16, A32, B16, B32, n, m, num_corr, ratio_test=True, n_dev=None, 
     ws = _empty((ws_bytes,), torch.uint8, dev)
     A = A32 if tf32 else A16
     B = B32 if tf32 else B16
-    Ck = A.shape[1]  # C + 8 for f16c rows
+    if split:
+        C = A_lo.shape[1]
+    ld = A.shape[1]
+    Ck = C + 8 if (f16 and not tf32) else C  # f16c rows: the 8 augmentation columns take part in the product
     prof = _PROFILE.get("k2_events")
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    L.call("mv_k2_sim_top2", L.ptr(A), L.ptr(B), n, m, Ck, L.ptr(n_dev), L.ptr(m_dev),
+    L.call("mv_k2_sim_top2_ld", L.ptr(A), ld, L.ptr(B), B.shape[1], n, m, Ck, L.ptr(n_dev), L.ptr(m_dev),
            L.MV_DTYPE_TF32 if tf32 else (L.MV_DTYPE_F16 if f16 else L.MV_DTYPE_BF16), _CFG["cluster"], L.ptr(row_val),
            L.ptr(row_idx), L.ptr(col_best), L.ptr(ws), c_size_t(ws_bytes), st)
     if prof is not None:
@@ -234,7 +237,7 @@ def match_rows(A16, A32, B16, B32, n, m, num_corr, ratio_test=True, n_dev=None, 
     weight = _empty((n,), torch.float32, dev)
     mutual = _empty((n,), torch.uint8, dev)
     if split and f16:
-        L.call("mv_k3_ratio_mutual_f16c", L.ptr(A16), L.ptr(A_lo), L.ptr(B16), L.ptr(B_lo), C, L.ptr(center_B), L.ptr(n_dev), n,
+        L.call("mv_k3_ratio_mutual_f16c", L.ptr(A16), L.ptr(A_lo), L.ptr(B16), L.ptr(B_lo), C, ld, L.ptr(center_B), L.ptr(n_dev), n,
                L.ptr(row_idx), L.ptr(col_best), int(ratio_test), L.ptr(dists), L.ptr(weight), L.ptr(mutual), st)
     elif split:
         L.call("mv_k3_ratio_mutual_split", L.ptr(A16), L.ptr(A_lo), L.ptr(B16), L.ptr(B_lo), C, L.ptr(n_dev), n,

@@ -290,6 +290,7 @@ struct K1Params {
   int32_t* taps;
   // ---- f16c rows (fmt16 == 1): kernel 2's fp16 operand = [fp16(row - center) | 8 augmentation columns]
   int fmt16;            // 0 = bf16, 1 = fp16 + augmentation columns
+  int pitch16;          // row pitch of the fp16 rows in elements (>= C + 8; a multiple of 64 keeps kernel 2's TMA rows 128-byte aligned)
   int role;             // MV_ROLE_QUERY: aug = 3 fp16 pieces of r = row . dotvec;  MV_ROLE_TARGET: aug = (1, 1, 2^-11)
   const float* center;  // (C) or NULL: subtracted from the normalised row before the 16-bit split
   const float* dotvec;  // (C) or NULL
@@ -382,7 +383,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
   int parity = 0;  // of this team's group counter: double-buffers sh.part
 
   const bool f16c = p.fmt16 != 0;
-  const size_t pitch16 = f16c ? (size_t)C + 8 : (size_t)C;
+  const size_t pitch16 = f16c ? (size_t)p.pitch16 : (size_t)C;
   const bool hasdot = p.dotvec != nullptr;
   auto put = [&](int pt, int c, float4 o, float inv) {
     o.x *= inv;  // inv == 1 when not normalising: exact
@@ -723,21 +724,35 @@ __global__ void center_invnorm_kernel(const float* __restrict__ rows, int C, int
   if (lane == 0) inv[q] = 1.f / fmaxf(sqrtf(ss), K1_NORM_EPS);
 }
 
-__global__ void center_mean_kernel(const float* __restrict__ rows, int C, int n_max, const int32_t* __restrict__ n_dev,
-                                   int step, const float* __restrict__ inv, float* __restrict__ mu) {
+// block = 32 channel quads x 16 row groups: group g sums rows q = g, g + 16, ... (independent loads, 4 in flight), the 16
+// partial sums are added in a fixed order -> deterministic
+__global__ void __launch_bounds__(512) center_mean_kernel(const float* __restrict__ rows, int C, int n_max,
+                                                          const int32_t* __restrict__ n_dev, int step,
+                                                          const float* __restrict__ inv, float* __restrict__ mu) {
+  __shared__ float4 part[16][32];
   const int n = n_dev ? min(*n_dev, n_max) : n_max;
   const int cnt = (n + step - 1) / step;
-  const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (c >= C) return;
-  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
-  int q = 0;
-  for (; q + 1 < cnt; q += 2) {  // two independent chains; fixed order: the centre is deterministic
-    fma4(a0, __ldg(inv + q), ld4(rows + (size_t)q * step * C + c));
-    fma4(a1, __ldg(inv + q + 1), ld4(rows + (size_t)(q + 1) * step * C + c));
+  const int cq = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + cq) * 4;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < C) {
+#pragma unroll 4
+    for (int q = g; q < cnt; q += 16) fma4(a, __ldg(inv + q), ld4(rows + (size_t)q * step * C + c));
   }
-  if (q < cnt) fma4(a0, __ldg(inv + q), ld4(rows + (size_t)q * step * C + c));
-  const float s = cnt > 0 ? 1.f / (float)cnt : 0.f;
-  *reinterpret_cast<float4*>(mu + c) = make_float4((a0.x + a1.x) * s, (a0.y + a1.y) * s, (a0.z + a1.z) * s, (a0.w + a1.w) * s);
+  part[g][cq] = a;
+  __syncthreads();
+  if (g == 0 && c < C) {
+    float4 t = part[0][cq];
+#pragma unroll
+    for (int k = 1; k < 16; ++k) {
+      t.x += part[k][cq].x;
+      t.y += part[k][cq].y;
+      t.z += part[k][cq].z;
+      t.w += part[k][cq].w;
+    }
+    const float s = cnt > 0 ? 1.f / (float)cnt : 0.f;
+    *reinterpret_cast<float4*>(mu + c) = make_float4(t.x * s, t.y * s, t.z * s, t.w * s);
+  }
 }
 
 template <int MODE, int NITW, int W, int G, int OUTS, int THREADS, int MINB>
@@ -942,13 +957,13 @@ int mv_rows_center(const float* rows, int C, int n_max, const int32_t* n_dev, in
   const int cnt = (n_max + step - 1) / step;
   center_invnorm_kernel<<<(cnt + 7) / 8, 256, 0, st>>>(rows, C, n_max, n_dev, step, inv_scratch);
   MV_LAUNCH_CHECK();
-  center_mean_kernel<<<(C / 4 + 63) / 64, 64, 0, st>>>(rows, C, n_max, n_dev, step, inv_scratch, mu);
+  center_mean_kernel<<<(C / 4 + 31) / 32, 512, 0, st>>>(rows, C, n_max, n_dev, step, inv_scratch, mu);
   MV_LAUNCH_CHECK();
   return MV_OK;
 }
 
 static int k1_entry(const char* who, int mode, const float* src, int C, int h, int w, const float* coords, const int32_t* n_dev,
-                    int n_max, int normalize, int fmt16, int role, const float* center, const float* dotvec, uint16_t* out16,
+                    int n_max, int normalize, int fmt16, int pitch16, int role, const float* center, const float* dotvec, uint16_t* out16,
                     uint16_t* out16_lo, float* out_f32, float* row_dot, int32_t* taps, mv_stream_t stream) {
   MV_REQUIRE(src && (out16 || out_f32), MV_E_ARG, "%s: null src or no output", who);
   MV_REQUIRE(mode == MV_SAMPLE_BILINEAR_ZEROS || mode == MV_SAMPLE_BICUBIC_CLAMP || mode == MV_SAMPLE_ROWS,
@@ -958,6 +973,7 @@ static int k1_entry(const char* who, int mode, const float* src, int C, int h, i
   MV_REQUIRE(C > 0 && C % 8 == 0 && C <= 8192, MV_E_RANGE, "%s: C=%d must be a multiple of 8, <= 8192", who, C);
   MV_REQUIRE(n_max >= 0, MV_E_ARG, "%s: negative n_max", who);
   MV_REQUIRE(role == MV_ROLE_QUERY || role == MV_ROLE_TARGET, MV_E_ARG, "%s: unknown role %d", who, role);
+  MV_REQUIRE(!fmt16 || (pitch16 >= C + 8 && pitch16 % 8 == 0), MV_E_ALIGN, "%s: pitch %d must be >= C + 8 and a multiple of 8", who, pitch16);
   MV_REQUIRE((reinterpret_cast<uintptr_t>(src) & 15) == 0, MV_E_ALIGN, "%s: src must be 16-byte aligned", who);
   MV_REQUIRE(!out_f32 || (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0, MV_E_ALIGN, "%s: out_f32 must be 16-byte aligned", who);
   MV_REQUIRE(!out16 || (reinterpret_cast<uintptr_t>(out16) & (fmt16 ? 15 : 7)) == 0, MV_E_ALIGN,
@@ -982,6 +998,7 @@ static int k1_entry(const char* who, int mode, const float* src, int C, int h, i
   p.out_f32 = out_f32;
   p.taps = taps;
   p.fmt16 = fmt16;
+  p.pitch16 = pitch16;
   p.role = role;
   p.center = center;
   p.dotvec = dotvec;
@@ -996,15 +1013,15 @@ static int k1_entry(const char* who, int mode, const float* src, int C, int h, i
 int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, const float* coords,
                            const int32_t* n_dev, int n_max, int normalize, uint16_t* out_bf16, uint16_t* out_bf16_lo, float* out_f32,
                            int32_t* taps, mv_stream_t stream) {
-  return k1_entry("mv_k1_sample_normalize", mode, src, C, h, w, coords, n_dev, n_max, normalize, 0, MV_ROLE_QUERY, nullptr, nullptr,
+  return k1_entry("mv_k1_sample_normalize", mode, src, C, h, w, coords, n_dev, n_max, normalize, 0, C, MV_ROLE_QUERY, nullptr, nullptr,
                   out_bf16, out_bf16_lo, out_f32, nullptr, taps, stream);
 }
 
 int mv_k1_sample_f16c(int mode, const float* src, int C, int h, int w, const float* coords, const int32_t* n_dev, int n_max,
-                      int normalize, int role, const float* center, const float* dotvec, uint16_t* out_f16, uint16_t* out_f16_lo,
+                      int normalize, int role, const float* center, const float* dotvec, uint16_t* out_f16, int pitch, uint16_t* out_f16_lo,
                       float* out_f32, float* row_dot, int32_t* taps, mv_stream_t stream) {
   MV_REQUIRE(out_f16, MV_E_ARG, "mv_k1_sample_f16c: out_f16 is required");
-  return k1_entry("mv_k1_sample_f16c", mode, src, C, h, w, coords, n_dev, n_max, normalize, 1, role, center, dotvec, out_f16,
+  return k1_entry("mv_k1_sample_f16c", mode, src, C, h, w, coords, n_dev, n_max, normalize, 1, pitch, role, center, dotvec, out_f16,
                   out_f16_lo, out_f32, row_dot, taps, stream);
 }
 

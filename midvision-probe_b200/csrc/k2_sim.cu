@@ -440,13 +440,13 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 // (rows, C) row-major operand -> tensor map with a (box_rows x 128 bytes) 128B-swizzled box
-int make_operand_map(CUtensorMap* tm, const void* base, int rows, int C, int dtype, int box_rows) {
+int make_operand_map(CUtensorMap* tm, const void* base, int rows, int C, int ld, int dtype, int box_rows) {
   const bool tf32 = dtype == MV_DTYPE_TF32;
   EncodeTiledFn enc = get_encode_tiled();
   MV_REQUIRE(enc, MV_E_DRIVER, "mv_k2_sim_top2: cuTensorMapEncodeTiled is not available from this driver");
   const int esz = tf32 ? 4 : 2;
   cuuint64_t gdim[2] = {(cuuint64_t)C, (cuuint64_t)rows};
-  cuuint64_t gstride[1] = {(cuuint64_t)C * esz};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * esz};  // row pitch; columns >= C are out of bounds = zero fill
   cuuint32_t box[2] = {(cuuint32_t)(ROW_BYTES / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
@@ -548,7 +548,16 @@ size_t mv_k2_workspace_bytes(int n_max, int m_max) {
 int mv_k2_sim_top2(const void* A, const void* B, int n_max, int m_max, int C, const int32_t* n_dev,
                    const int32_t* m_dev, int dtype, int cluster, float* row_val, int32_t* row_idx,
                    unsigned long long* col_best, void* workspace, size_t workspace_bytes, mv_stream_t stream) {
+  return mv_k2_sim_top2_ld(A, C, B, C, n_max, m_max, C, n_dev, m_dev, dtype, cluster, row_val, row_idx, col_best, workspace,
+                           workspace_bytes, stream);
+}
+
+int mv_k2_sim_top2_ld(const void* A, int lda, const void* B, int ldb, int n_max, int m_max, int C, const int32_t* n_dev,
+                      const int32_t* m_dev, int dtype, int cluster, float* row_val, int32_t* row_idx,
+                      unsigned long long* col_best, void* workspace, size_t workspace_bytes, mv_stream_t stream) {
   MV_REQUIRE(A && B && row_val && row_idx && col_best && workspace, MV_E_ARG, "mv_k2_sim_top2: null pointer");
+  MV_REQUIRE(lda >= C && ldb >= C && (lda * (dtype == MV_DTYPE_TF32 ? 4 : 2)) % 16 == 0 && (ldb * (dtype == MV_DTYPE_TF32 ? 4 : 2)) % 16 == 0,
+             MV_E_ALIGN, "mv_k2_sim_top2: row pitches (%d, %d) must be >= C and a multiple of 16 bytes", lda, ldb);
   MV_REQUIRE(dtype == MV_DTYPE_BF16 || dtype == MV_DTYPE_TF32 || dtype == MV_DTYPE_F16, MV_E_ARG, "mv_k2_sim_top2: unknown dtype %d", dtype);
   MV_REQUIRE(n_max > 0 && m_max > 0 && C > 0, MV_E_ARG, "mv_k2_sim_top2: sizes must be positive");
   MV_REQUIRE(n_max <= (1 << 20) && m_max <= (1 << 20), MV_E_RANGE, "mv_k2_sim_top2: at most 2^20 rows per side");
@@ -591,9 +600,9 @@ int mv_k2_sim_top2(const void* A, const void* B, int n_max, int m_max, int C, co
   p.col_best = col_best;
 
   CUtensorMap tmA, tmB;
-  int rc = make_operand_map(&tmA, A, n_max, C, dtype, BM);
+  int rc = make_operand_map(&tmA, A, n_max, C, lda, dtype, BM);
   if (rc) return rc;
-  rc = make_operand_map(&tmB, B, m_max, C, dtype, BN / mc);
+  rc = make_operand_map(&tmB, B, m_max, C, ldb, dtype, BN / mc);
   if (rc) return rc;
 
   cudaStream_t st = mv_cuda_stream(stream);

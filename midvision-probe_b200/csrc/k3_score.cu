@@ -51,6 +51,7 @@ struct RowsF16c {
   const __half* B_hi;
   const __half* B_lo;
   const float* center_B;  // may be null
+  int pitch;              // row pitch of the hi planes (>= C + 8)
 };
 
 __device__ __forceinline__ void f16c8(const __half* hi, const __half* lo, int c8, float (&out)[8]) {
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(RATIO_THREADS, 6) k3_ratio_mutual_kernel(ROWS 
       xb = fmaf(v.x, b.x, xb); xb = fmaf(v.y, b.y, xb); xb = fmaf(v.z, b.z, xb); xb = fmaf(v.w, b.w, xb);
     }
   } else if constexpr (sizeof(ROWS) == sizeof(RowsF16c)) {
-    const size_t P = (size_t)C + 8;
+    const size_t P = (size_t)rows.pitch;
     const size_t ox = (size_t)i * C, o0 = (size_t)max(j0, 0) * C, o1 = (size_t)max(j1, 0) * C;
     const __half* xh = rows.A_hi + (size_t)i * P;
     const __half* ah = rows.B_hi + (size_t)max(j0, 0) * P;
@@ -537,7 +538,7 @@ int mv_k3_ratio_mutual_split(const uint16_t* A_hi, const uint16_t* A_lo, const u
   return MV_OK;
 }
 
-int mv_k3_ratio_mutual_f16c(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* B_hi, const uint16_t* B_lo, int C,
+int mv_k3_ratio_mutual_f16c(const uint16_t* A_hi, const uint16_t* A_lo, const uint16_t* B_hi, const uint16_t* B_lo, int C, int pitch,
                             const float* center_B, const int32_t* n_dev, int n_max, int32_t* row_idx,
                             const unsigned long long* col_best, int ratio_test, float* dists, float* weight, uint8_t* mutual,
                             mv_stream_t stream) {
@@ -545,11 +546,11 @@ int mv_k3_ratio_mutual_f16c(const uint16_t* A_hi, const uint16_t* A_lo, const ui
   MV_REQUIRE(C > 0 && C % 8 == 0, MV_E_ALIGN, "mv_k3_ratio_mutual_f16c: C=%d must be a positive multiple of 8", C);
   MV_REQUIRE((((uintptr_t)A_hi | (uintptr_t)A_lo | (uintptr_t)B_hi | (uintptr_t)B_lo | (uintptr_t)center_B) & 15) == 0, MV_E_ALIGN,
              "mv_k3_ratio_mutual_f16c: the row planes and the centre must be 16-byte aligned");
-  MV_REQUIRE(n_max >= 0, MV_E_ARG, "mv_k3_ratio_mutual_f16c: negative n_max");
+  MV_REQUIRE(n_max >= 0 && pitch >= C + 8 && pitch % 8 == 0, MV_E_ARG, "mv_k3_ratio_mutual_f16c: negative n_max or bad pitch %d", pitch);
   if (n_max == 0) return MV_OK;
   const int rows_per_cta = RATIO_THREADS / 32;
   RowsF16c rows{reinterpret_cast<const __half*>(A_hi), reinterpret_cast<const __half*>(A_lo), reinterpret_cast<const __half*>(B_hi),
-                reinterpret_cast<const __half*>(B_lo), center_B};
+                reinterpret_cast<const __half*>(B_lo), center_B, pitch};
   k3_ratio_mutual_kernel<RowsF16c><<<(n_max + rows_per_cta - 1) / rows_per_cta, 32 * rows_per_cta, 0, mv_cuda_stream(stream)>>>(
       rows, C, n_dev, n_max, row_idx, col_best, ratio_test, dists, weight, mutual);
   MV_LAUNCH_CHECK();

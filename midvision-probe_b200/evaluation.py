@@ -14,7 +14,72 @@ from . import _lib as L
 from . import correspondence as C_
 
 __all__ = ["RecallAccumulator", "shard_pairs", "match_and_score_depth", "match_and_score_xyz", "GraphedPairMatcher",
-           "PairPipeline"]
+           "PairPipeline", "bind_rank_to_gpu"]
+
+
+def _cpulist(text):
+    out = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        out.extend(range(int(a), int(b or a) + 1))
+    return out
+
+
+def bind_rank_to_gpu(local_rank, local_world=1):
+    """Pin this process (one per GPU) to a share of the cores of its GPU's NUMA node, BEFORE it allocates pinned
+    staging memory, so that the host side of its H2D copies (page-locked buffers, the memcpy into them, the launch
+    thread) lives next to the PCIe root of its own GPU instead of on node 0 with every other rank.
+
+    The node comes from /sys/bus/pci/devices/<bus id>/numa_node, its cores from /sys/devices/system/node/nodeK/cpulist;
+    ranks that share a node split its cores evenly.  Memory follows by first touch (and set_mempolicy when libnuma's
+    syscall is reachable).  Returns a description dict; never raises (a box without the sysfs files is left unbound)."""
+    import ctypes
+    import os
+
+    info = {"bound": False}
+    try:
+        import torch.cuda as tc
+
+        ngpu = tc.device_count()
+        nodes = []
+        for g in range(ngpu):
+            bus = tc.get_device_properties(g).pci_bus_id if hasattr(tc.get_device_properties(g), "pci_bus_id") else None
+            dom = getattr(tc.get_device_properties(g), "pci_domain_id", 0)
+            dev_id = getattr(tc.get_device_properties(g), "pci_device_id", 0)
+            path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node" if bus is not None else None
+            node = -1
+            if path and os.path.exists(path):
+                node = int(open(path).read().strip())
+            nodes.append(node)
+        node = nodes[local_rank] if local_rank < len(nodes) else -1
+        if node < 0:
+            all_nodes = sorted(int(d[4:]) for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit())
+            if len(all_nodes) <= 1:
+                info["reason"] = "single NUMA node"
+                return info
+            node = all_nodes[local_rank * len(all_nodes) // max(local_world, 1) % len(all_nodes)]
+        cpus = _cpulist(open(f"/sys/devices/system/node/node{node}/cpulist").read())
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0))) or cpus
+        peers = [r for r in range(min(local_world, max(len(nodes), 1))) if (nodes[r] if r < len(nodes) else -1) == nodes[local_rank]] if nodes else [local_rank]
+        if local_rank not in peers:
+            peers = [local_rank]
+        share = max(1, len(allowed) // len(peers))
+        k = peers.index(local_rank)
+        mine = allowed[k * share:(k + 1) * share] or allowed
+        os.sched_setaffinity(0, mine)
+        info.update({"bound": True, "numa_node": node, "cpus": f"{mine[0]}-{mine[-1]}", "n_cpus": len(mine), "ranks_on_node": len(peers)})
+        try:  # prefer this node for every later allocation (MPOL_PREFERRED = 1); best effort
+            libc = ctypes.CDLL(None, use_errno=True)
+            mask = ctypes.c_ulong(1 << node)
+            rc = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))  # __NR_set_mempolicy on x86-64
+            info["mempolicy"] = "preferred" if rc == 0 else f"errno {ctypes.get_errno()}"
+        except Exception as e:  # noqa: BLE001
+            info["mempolicy"] = f"unavailable ({type(e).__name__})"
+    except Exception as e:  # noqa: BLE001 -- binding is an optimisation, never a failure
+        info["reason"] = f"{type(e).__name__}: {e}"
+    return info
 
 
 def shard_pairs(num_pairs, rank, world):

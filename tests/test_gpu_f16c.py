@@ -26,11 +26,11 @@ def f16c_rows(mv, X, role, center=None, dotvec=None, normalize=True, lo=True):
     L, C_ = mv._lib, mv.correspondence
     Xd = X.cuda().contiguous()
     n, C = Xd.shape
-    hi = torch.full((n, C + 8), 9.0, dtype=torch.float16, device="cuda")
+    hi = torch.full((n, L.f16c_pitch(C)), 9.0, dtype=torch.float16, device="cuda")
     lo_t = torch.empty((n, C), dtype=torch.float16, device="cuda") if lo else None
     rdot = torch.empty(n, device="cuda")
     L.call("mv_k1_sample_f16c", L.MV_SAMPLE_ROWS, L.ptr(Xd), C, 0, 0, None, None, n, int(normalize), role, L.ptr(center),
-           L.ptr(dotvec), L.ptr(hi), L.ptr(lo_t), None, L.ptr(rdot), None, C_._stream())
+           L.ptr(dotvec), L.ptr(hi), hi.shape[1], L.ptr(lo_t), None, L.ptr(rdot), None, C_._stream())
     torch.cuda.synchronize()
     return hi, lo_t, rdot
 
@@ -55,13 +55,14 @@ def test_f16c_row_planes_bit_exact(mv, C):
     assert (got != y.half().float()).float().mean() < 2e-3
     rebuilt = got + lo.float() / 2048.0
     assert ((rebuilt - y).abs() <= y.abs() * 2.0 ** -21 + 1e-9).all()
-    aug = hi[:, C:].float().cpu()
+    aug = hi[:, C:C + 8].float().cpu()
     assert torch.equal(aug, torch.tensor([1.0, 1.0, 2.0 ** -11, 0, 0, 0, 0, 0]).expand(300, 8))
+    assert (hi[:, C + 8:] == 9.0).all()  # the padding up to the 128-byte pitch is never written (and never read by kernel 2)
     # query role: plain fp16 rows, aug = three pieces of r = x . mu
     hq, lq, r = f16c_rows(mv, X, L.MV_ROLE_QUERY, dotvec=mu)
     want_r = (Xn * mu[None]).sum(1)
     torch.testing.assert_close(r, want_r, rtol=0, atol=2e-6)
-    a = hq[:, C:].float()
+    a = hq[:, C:C + 8].float()
     torch.testing.assert_close(a[:, 0] + a[:, 1] + a[:, 2] / 2048.0, r, rtol=0, atol=1e-7)
     assert (a[:, 3:] == 0).all()
     assert ((hq[:, :C].float() - Xn).abs() <= Xn.abs() * 2.0 ** -11 * 1.01 + 1e-7).all()
@@ -81,7 +82,7 @@ def test_f16c_product_is_the_uncentred_product(mv, C, cluster):
     col_best = torch.empty(m, dtype=torch.int64, device="cuda")
     wsb = L.load().mv_k2_workspace_bytes(n, m)
     ws = torch.empty(wsb, dtype=torch.uint8, device="cuda")
-    L.call("mv_k2_sim_top2", L.ptr(A), L.ptr(B), n, m, C + 8, None, None, L.MV_DTYPE_F16, cluster, L.ptr(row_val), L.ptr(row_idx),
+    L.call("mv_k2_sim_top2_ld", L.ptr(A), A.shape[1], L.ptr(B), B.shape[1], n, m, C + 8, None, None, L.MV_DTYPE_F16, cluster, L.ptr(row_val), L.ptr(row_idx),
            L.ptr(col_best), L.ptr(ws), c_size_t(wsb), C_._stream())
     col_val = torch.empty(m, device="cuda")
     col_idx = torch.empty(m, dtype=torch.int32, device="cuda")

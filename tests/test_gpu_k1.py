@@ -64,8 +64,8 @@ def test_depth_side_matches_oracle(C_, mv, syn, shape):
     assert torch.equal(s.taps[:n].cpu().long(), torch.floor(coords).long())        # upsample tap origins: bit-exact
     ref = F.normalize(f_o, dim=-1)
     torch.testing.assert_close(s.rows32[:n].cpu(), ref, rtol=0, atol=ATOL)
-    if s.rows16 is not None:
-        got16 = s.rows16[:n].float().cpu()
+    if s.rows16 is not None:  # the 16-bit operand rows (fp16 + 8 augmentation columns by default, query role: not centred)
+        got16 = s.rows16[:n, :shape["C"]].float().cpu()
         assert (got16 - s.rows32[:n].cpu()).abs().max() <= 2 ** -8 * s.rows32[:n].abs().max().item() + 1e-8
 
 
@@ -139,8 +139,12 @@ def test_split_rows_rebuild_the_fp32_rows(C_, syn, C):
     the fp32 row bit for bit, and hi + lo rebuilds it to 2^-16 relative (the stated tolerance of the format)."""
     p = syn.navi_pair(7, coherent=False, C=C, h=10, w=10, H=40, W=40, radius=15.0)
     dev = torch.device("cuda")
-    a = C_.prepare_xyz_side(p["feat_0"], p["xyz_grid_0"], dev, rows="f32")
-    b = C_.prepare_xyz_side(p["feat_0"], p["xyz_grid_0"], dev, rows="split")
+    C_.set_match_precision(dtype="bf16")
+    try:
+        a = C_.prepare_xyz_side(p["feat_0"], p["xyz_grid_0"], dev, rows="f32")
+        b = C_.prepare_xyz_side(p["feat_0"], p["xyz_grid_0"], dev, rows="split")
+    finally:
+        C_.set_match_precision(dtype=C_.DEFAULT_DTYPE)
     n = a.n
     assert b.rows32 is None and b.rows_lo is not None
     assert torch.equal(a.rows16[:n], b.rows16[:n])
@@ -148,3 +152,12 @@ def test_split_rows_rebuild_the_fp32_rows(C_, syn, C):
     rebuilt = b.rows16[:n].float() + b.rows_lo[:n].float()
     err = (rebuilt - a.rows32[:n]).abs()
     assert bool((err <= 2.0 ** -16 * a.rows32[:n].abs() + 1e-30).all())
+    # the default format: fp16 hi (C + 8 columns, 128-byte pitch) + fp16 residual scaled by 2^11 -> 2^-21 relative
+    a = C_.prepare_xyz_side(p["feat_0"], p["xyz_grid_0"], dev, rows="f32")
+    b = C_.prepare_xyz_side(p["feat_0"], p["xyz_grid_0"], dev, rows="split")
+    assert b.rows16.dtype == torch.float16 and b.rows16.shape[1] == (C + 8 + 63) // 64 * 64 and b.rows32 is None
+    assert torch.equal(a.rows16[:n, :C + 8], b.rows16[:n, :C + 8])
+    assert torch.equal(a.rows32[:n].to(torch.float16), b.rows16[:n, :C])
+    rebuilt = b.rows16[:n, :C].float() + b.rows_lo[:n].float() / 2048.0
+    err = (rebuilt - a.rows32[:n]).abs()
+    assert bool((err <= 2.0 ** -21 * a.rows32[:n].abs() + 1e-9).all())
