@@ -751,6 +751,8 @@ def _graphed_helper(kind, feat_0, feat_1, grid_0, grid_1, num_corr, ratio_test, 
     packed read-back (results + the three live counts), i.e. a single host sync.  Results are returned on the
     device of the first feature argument, like the reference."""
     dev = _device()
+    if tuple(feat_1.shape) != tuple(feat_0.shape) or tuple(grid_1.shape) != tuple(grid_0.shape):
+        return None  # two differently sized images (the reference accepts them): the eager path handles any shapes
     layout = "hwc" if (_is_channel_last(feat_0) and _is_channel_last(feat_1)) else "chw"
     fdt = feat_0.dtype if (feat_0.dtype == feat_1.dtype and feat_0.dtype in _FEAT_DTYPES) else torch.float32
     # the intrinsics are NOT part of the key: they live in device memory and are refreshed per call (gm.load)
@@ -794,7 +796,9 @@ def estimate_correspondence_depth(feat_0, feat_1, depth_0, depth_1, K, num_corr=
     dev = _device()
     in_dev = feat_0.device
     if _CFG["helper_graphs"]:
-        return _graphed_helper("depth", feat_0, feat_1, depth_0, depth_1, num_corr, True, K=K)
+        out = _graphed_helper("depth", feat_0, feat_1, depth_0, depth_1, num_corr, True, K=K)
+        if out is not None:
+            return out
     Kc = K.detach().float().cpu()
     Kh, Kinv = _host_mat(Kc), _host_mat(Kc.inverse())
     _check_C(feat_0.shape[0])
@@ -824,7 +828,9 @@ def estimate_correspondence_xyz(feat_0, feat_1, xyz_grid_0, xyz_grid_1, num_corr
     dev = _device()
     in_dev = feat_0.device
     if _CFG["helper_graphs"]:
-        return _graphed_helper("xyz", feat_0, feat_1, xyz_grid_0, xyz_grid_1, num_corr, ratio_test)
+        out = _graphed_helper("xyz", feat_0, feat_1, xyz_grid_0, xyz_grid_1, num_corr, ratio_test)
+        if out is not None:
+            return out
     _check_C(feat_0.shape[0])
     g0, g1 = _f32(xyz_grid_0, dev), _f32(xyz_grid_1, dev)
     a0, a1 = _stage_xyz(g0), _stage_xyz(g1)

@@ -268,6 +268,7 @@ class GraphedPairMatcher:
             # the captured graph (ScanNet's differ per scene); load(..., K=...) refreshes them
             self.Kdev = torch.zeros(18, dtype=torch.float32, device=self.dev)
             self.Kpin = torch.zeros((8, 18), dtype=torch.float32).pin_memory()  # ring of staging rows: no sync on a change
+            self.Kevents = [None] * 8  # per row: recorded after the row's H2D copy; the row is rewritten only once it fired
             self.Kturn = 0
             self.Kc = None
             self.set_intrinsics(K)
@@ -319,11 +320,20 @@ class GraphedPairMatcher:
         if self.Kc is not None and torch.equal(Kc, self.Kc):
             return
         self.Kc = Kc.clone()
-        row = self.Kpin[self.Kturn % 8]  # a row is reused only after 8 further changes: its copy has long completed
+        slot = self.Kturn % 8
         self.Kturn += 1
+        row = self.Kpin[slot]
+        # the host may run many pairs ahead of the GPU (PairPipeline.submit never syncs): a queued copy from this row
+        # could still be pending 8 changes later, so wait for ITS event before overwriting the staging memory
+        ev = self.Kevents[slot]
+        if ev is not None:
+            ev.synchronize()
         row[:9] = Kc.reshape(-1)
         row[9:] = Kc.inverse().reshape(-1)
         self.Kdev.copy_(row, non_blocking=True)
+        if ev is None:
+            ev = self.Kevents[slot] = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
 
     def load(self, feat_0, feat_1, grid_0, grid_1, two_streams=False, K=None):
         """stage one pair's inputs (any device; pinned host memory makes the copies asynchronous).
@@ -358,7 +368,11 @@ class GraphedPairMatcher:
         L.LAUNCHES["count"] += self.launches_per_replay
         s0, s1, r = self.out
         if acc is not None:
-            acc.score(r, s0.xyz, s1.xyz, Rt, K if K is not None else self.Kc)
+            if K is None:
+                if self.kind != "depth":
+                    raise ValueError("run(acc=...) of an 'xyz' matcher needs the pair's intrinsics K (there is no matcher-wide K)")
+                K = self.Kc
+            acc.score(r, s0.xyz, s1.xyz, Rt, K)
         return r
 
     @property

@@ -206,3 +206,64 @@ def spair_compute_errors(feats, kps_i, kps_j, thresh_scale, image_size, return_p
     if return_pred:
         return error_same, error_nn, index_same, index_nn, heat
     return error_same, error_nn, index_same, index_nn
+
+
+# ---- the two reference entry points without a caller ---------------------------------------------------
+def correspondences_ratio_test_bidirectional(P1_F, P2_F, num_corres, ratio_test=True):
+    """get_correspondences_ratio_test with bidirectional=True, evals/utils/correspondence.py:79-98, with the
+    concatenations along dim 0 (the reference's `dim=1` on these 1-D tensors raises; dim 0 is what the surrounding code
+    -- half the budget per direction, then one list of matches -- evidently means)."""
+    d1, i1 = knn_points(P1_F, P2_F, 2, "cosine")
+    d2, i2 = knn_points(P2_F, P1_F, 2, "cosine")
+    w1 = ratio_weights(d1) if ratio_test else d1[:, 0]
+    w2 = ratio_weights(d2) if ratio_test else d2[:, 0]
+    m12_idx1, m12_idx2, m12_dist = topk_matches(w1, i1[:, 0], num_corres // 2)   # :89-91
+    m21_idx2, m21_idx1, m21_dist = topk_matches(w2, i2[:, 0], num_corres // 2)   # :92-94
+    return torch.cat((m12_idx1, m21_idx1)), torch.cat((m12_idx2, m21_idx2)), torch.cat((m12_dist, m21_dist))
+
+
+def error_auc(errors, thresholds):
+    """evals/utils/correspondence.py:199-215 (numpy; no caller in the reference)."""
+    import numpy as np
+
+    errors = [0] + sorted(list(errors))
+    recall = list(np.linspace(0, 1, len(errors)))
+    trapz = getattr(np, "trapezoid", None) or np.trapz
+    aucs = []
+    for thr in thresholds:
+        last_index = np.searchsorted(errors, thr)
+        y = recall[:last_index] + [recall[last_index - 1]]
+        x = errors[:last_index] + [thr]
+        aucs.append(trapz(y, x) / thr)
+    return aucs
+
+
+# ---- a caller, restated: the NAVI evaluation loop -------------------------------------------------------
+def navi_error_block(corr, tr, feats_0, feats_1, xyz_grid_0, xyz_grid_1, Rt_gt, intrinsics, num_corr, scale_factor=0.25):
+    """evaluate_navi_correspondence.py:174-221 with the functions taken from the modules `corr` (an
+    evals.utils.correspondence) and `tr` (an evals.utils.transformations): the per-pair helper call, the 3-D / 2-D
+    errors, the six recalls and the angle-binned recall@2cm.  Pinned against the reference's own text by
+    tests/test_oracle.py (oracle/reference_loader.navi_error_block_reference executes those lines)."""
+    import math
+
+    err_3d, err_2d = [], []
+    for i in range(len(feats_0)):                                                     # :177
+        c_xyz0, c_xyz1, c_dist, c_uv0, c_uv1 = corr.estimate_correspondence_xyz(      # :178-180
+            feats_0[i], feats_1[i], xyz_grid_0[i], xyz_grid_1[i], num_corr)
+        c_uv0, c_uv1 = c_uv0 / scale_factor, c_uv1 / scale_factor                     # :182-183
+        c_xyz0in1 = tr.transform_points_Rt(c_xyz0, Rt_gt[i].float())                  # :185
+        c_err3d = (c_xyz0in1 - c_xyz1).norm(p=2, dim=1)                               # :186
+        uv1 = corr.project_3dto2d(c_xyz1, intrinsics[i])                              # :188
+        uv0 = corr.project_3dto2d(c_xyz0in1, intrinsics[i])                           # :189
+        c_err2d = (uv0 - uv1).norm(p=2, dim=1)                                        # :190
+        err_3d.append(c_err3d.detach().cpu())
+        err_2d.append(c_err2d.detach().cpu())
+    err_3d = torch.stack(err_3d, dim=0).float()                                       # :195-196
+    err_2d = torch.stack(err_2d, dim=0).float()
+    rec3 = [100 * (err_3d < th).float().mean() for th in (0.01, 0.02, 0.05)]          # :199-204
+    rec2 = [100 * (err_2d < th).float().mean() for th in (5, 25, 50)]                 # :206-211
+    rel_ang = tr.so3_rotation_angle(Rt_gt[:, :3, :3]) * 180.0 / math.pi              # :214-215
+    rec_2cm = (err_3d < 0.02).float().mean(dim=1)                                     # :218
+    bin_rec = corr.compute_binned_performance(rec_2cm, rel_ang, [0, 30, 60, 90, 120]) # :219
+    return {"err_3d": err_3d, "err_2d": err_2d, "recall_3d": torch.stack(rec3), "recall_2d": torch.stack(rec2),
+            "bin_rec": torch.stack([torch.as_tensor(b) for b in bin_rec])}

@@ -416,3 +416,50 @@ def test_intrinsics_change_between_replays_of_one_graph(mv, syn):
     pipe.join()
     torch.cuda.synchronize()
     assert torch.equal(acc_a.hits.cpu(), acc_b.hits.cpu())
+
+
+def test_many_intrinsics_changes_queued_behind_a_long_kernel(mv, syn):
+    """the matcher stages [K | K^-1] in a ring of 8 pinned rows; with the host running far ahead of the GPU (a long
+    kernel in front, 20 K changes queued behind it on ONE lane) a staging row must not be rewritten before the copy
+    that reads it has run -- every pair has to be scored with ITS intrinsics."""
+    ev = mv.evaluation
+    p = syn.scannet_pair(17, C=64, h=6, w=8, H=24, W=32)
+    dev = torch.device("cuda")
+    T3, T2 = [0.004, 0.006, 0.008, 0.012, 0.02], [1.5, 3.0]  # around the 3-D distance of neighbouring pixels: sensitive to K
+    Ks = []
+    for i in range(20):
+        K = p["K"].clone()
+        K[0, 0] *= 1.0 + 0.03 * i
+        K[1, 1] *= 1.0 - 0.02 * i
+        K[1, 2] += 0.3 * i
+        Ks.append(K)
+    want = []
+    for K in Ks:
+        acc = ev.RecallAccumulator(T3, T2, device=dev)
+        ev.match_and_score_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], K, p["Rt"], 100, acc, sync=True)
+        want.append(acc.hits.cpu())
+    assert len({tuple(w.tolist()) for w in want}) > 3, want  # the intrinsics matter for the counts
+    pipe = ev.PairPipeline("depth", tuple(p["feat_0"].shape), tuple(p["depth_0"].shape), 100, K=Ks[0], lanes=1)
+    f0, f1, d0, d1 = (p[k].cuda() for k in ("feat_0", "feat_1", "depth_0", "depth_1"))
+    accs = [ev.RecallAccumulator(T3, T2, device=dev) for _ in Ks]
+    st, _ = pipe.lanes[0]
+    with torch.cuda.stream(st):
+        torch.cuda._sleep(int(2e8))  # ~0.1 s of GPU time in front of everything that follows on the lane
+    for K, acc in zip(Ks, accs):
+        pipe.submit(f0, f1, d0, d1, acc, p["Rt"], K)
+    pipe.join()
+    torch.cuda.synchronize()
+    for a, w in zip(accs, want):
+        assert torch.equal(a.hits.cpu(), w)
+
+
+def test_differently_sized_images_take_the_eager_path(mv, syn):
+    """the reference accepts two images of different sizes; the cached-graph fast path is keyed on image 0's shapes, so
+    such a call must fall back to the eager launches instead of copying image 1 into image 0's buffers."""
+    C_ = mv.correspondence
+    a = syn.navi_pair(21, C=64, h=8, w=8, H=32, W=32, radius=12.0)
+    b = syn.navi_pair(22, C=64, h=6, w=6, H=24, W=24, radius=9.0)
+    got = C_.estimate_correspondence_xyz(a["feat_0"], b["feat_1"], a["xyz_grid_0"], b["xyz_grid_1"], 50)
+    ref = restated.estimate_correspondence_xyz(a["feat_0"], b["feat_1"], a["xyz_grid_0"], b["xyz_grid_1"], 50)
+    assert [tuple(t.shape) for t in got] == [tuple(t.shape) for t in ref]
+    torch.testing.assert_close(got[2], ref[2], rtol=0, atol=2e-3)

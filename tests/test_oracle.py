@@ -10,6 +10,8 @@ from oracle import reference_loader, restated
 SCANNET_SMALL = dict(C=64, h=6, w=8, H=24, W=32)
 NAVI_SMALL = dict(C=64, h=8, w=8, H=32, W=32, radius=12.0)
 SPAIR_SMALL = dict(C=64, h=14, w=14, K=20, image_size=224)
+# error_auc([0.3, 4.0, 1.2, 9.5, 0.05, 2.2, 7.7, 3.1], [1, 5, 10]) of the reference (evals/utils/correspondence.py:199-215)
+ERROR_AUC_GOLDEN = [0.22499999999999998, 0.5287499999999999, 0.70875]
 
 
 def t(a):
@@ -143,3 +145,53 @@ def test_transformations_mirror_equals_reference(mv, syn):
     assert torch.equal(tr.so3_relative_angle(Rt[:3, :3, :3], Rt[3:, :3, :3]), ref_tr.so3_relative_angle(Rt[:3, :3, :3], Rt[3:, :3, :3]))
     with pytest.raises(ValueError):
         tr.so3_rotation_angle(torch.eye(3)[None] * 5)
+
+
+def _navi_batch(syn, n=4, **kw):
+    ps = [syn.navi_pair(40 + i, coherent=(i % 2 == 0), **kw) for i in range(n)]
+    g = torch.Generator().manual_seed(77)
+    Rt = torch.stack([syn.random_rt(g, max_deg=110.0) for _ in ps])  # angles spread over the four bins
+    stack = lambda k: torch.stack([p[k] for p in ps])
+    return stack("feat_0"), stack("feat_1"), stack("xyz_grid_0"), stack("xyz_grid_1"), Rt, stack("intrinsics")
+
+
+@pytest.mark.skipif(not reference_loader.available(), reason="reference tree not on this machine")
+def test_navi_caller_block_restated_equals_the_reference_text(syn):
+    """the reference's own evaluation loop (evaluate_navi_correspondence.py:174-221, executed from its file) against
+    restated.navi_error_block fed the reference's modules: errors, the six recalls and the angle-binned recall."""
+    corr, tr = reference_loader.load()
+    args = _navi_batch(syn, C=32, h=6, w=6, H=24, W=24, radius=9.0)
+    ref = reference_loader.navi_error_block_reference(*args, num_corr=40)
+    got = restated.navi_error_block(corr, tr, *args, num_corr=40)
+    assert torch.equal(ref["err_3d"], got["err_3d"]) and torch.equal(ref["err_2d"], got["err_2d"])
+    want = [float(r) for r in ref["results"]]  # the script formats every number as f"{x:5.02f}"
+    have = [float(f"{float(x):5.02f}") for x in list(got["recall_3d"]) + list(got["recall_2d"])]
+    have += [float(f"{float(b) * 100:5.02f}") for b in got["bin_rec"]]
+    assert len(want) == len(have) == 10
+    for w, h in zip(want, have):
+        assert (w != w and h != h) or w == h  # empty angle bins are nan in both
+
+
+@pytest.mark.skipif(not reference_loader.available(), reason="reference tree not on this machine")
+def test_bidirectional_and_error_auc_restatements(mv):
+    """the two reference entry points without a caller.  bidirectional=True: the reference's branch raises at its
+    torch.cat(dim=1); its executable parts -- the two directed calls with half the budget each -- are what the
+    restatement concatenates.  error_auc: restatement and product mirror against the reference's numpy."""
+    corr, _ = reference_loader.load()
+    gen = torch.Generator().manual_seed(12)
+    X = torch.randn(120, 24, generator=gen)
+    Y = X[torch.randperm(120, generator=gen)][:100] + 0.4 * torch.randn(100, 24, generator=gen)
+    with pytest.raises((IndexError, RuntimeError)):
+        corr.get_correspondences_ratio_test(X, Y, 30, bidirectional=True)
+    a1, a2, aw = corr.get_correspondences_ratio_test(X, Y, 15)
+    b2, b1, bw = corr.get_correspondences_ratio_test(Y, X, 15)
+    r1, r2, rw = restated.correspondences_ratio_test_bidirectional(X, Y, 30)
+    assert torch.equal(r1, torch.cat((a1, b1))) and torch.equal(r2, torch.cat((a2, b2)))
+    torch.testing.assert_close(rw, torch.cat((aw, bw)), rtol=0, atol=2e-6)
+    errs = [0.3, 4.0, 1.2, 9.5, 0.05, 2.2, 7.7, 3.1]
+    thr = [1, 5, 10]
+    want = corr.error_auc(errs, thr)
+    np.testing.assert_allclose(restated.error_auc(errs, thr), want, rtol=0, atol=0)
+    np.testing.assert_allclose(mv.correspondence.error_auc(errs, thr), want, rtol=0, atol=0)
+    np.testing.assert_allclose(want, ERROR_AUC_GOLDEN, rtol=0, atol=1e-12)  # the constant test_host_logic checks on the GPU box
+
