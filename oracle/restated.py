@@ -267,3 +267,16 @@ def navi_error_block(corr, tr, feats_0, feats_1, xyz_grid_0, xyz_grid_1, Rt_gt, 
     bin_rec = corr.compute_binned_performance(rec_2cm, rel_ang, [0, 30, 60, 90, 120]) # :219
     return {"err_3d": err_3d, "err_2d": err_2d, "recall_3d": torch.stack(rec3), "recall_2d": torch.stack(rec2),
             "bin_rec": torch.stack([torch.as_tensor(b) for b in bin_rec])}
+
+
+def compute_binned_performance(y, x, x_bins):
+    """evals/utils/correspondence.py:266-277."""
+    return [y[(x >= x_bins[i]) * (x < x_bins[i + 1])].mean() for i in range(len(x_bins) - 1)]
+
+
+def so3_rotation_angle(R, eps=1e-4):
+    """evals/utils/transformations.py:47-63: rotation angle (radians) of a batch of 3x3 rotations from the trace."""
+    tr = R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2]
+    if ((tr < -1.0 - eps) + (tr > 3.0 + eps)).any():
+        raise ValueError("A matrix has trace outside valid range [-1-eps,3+eps].")
+    return torch.acos(((tr - 1.0) * 0.5).clamp(min=-1, max=1))
