@@ -146,6 +146,20 @@ int mv_k1_sample_f16c(int mode, const float* src, int C, int h, int w, const flo
                       int normalize, int role, const float* center, const float* dotvec, uint16_t* out_f16, int pitch,
                       uint16_t* out_f16_lo, float* out_f32, float* row_dot, int32_t* taps, mv_stream_t stream);
 
+/* The NAVI-style side as ONE tiled kernel (csrc/k1_grid.cu): bicubic upsampling (A = -0.75, align_corners=False, border
+ * clamp) of the (h*w, C) map by the integer factors W / w (4 or 8) and H / h (1..8) onto the live pixels of the (H, W)
+ * grid, L2-normalise, f16c rows -- the same values as mv_geom_grid_coords + mv_k1_sample_f16c(MV_SAMPLE_BICUBIC_CLAMP)
+ * (identical arithmetic per element; the sum of squares is accumulated in another order: <= 1 ulp of the norm).
+ * 2-D tiles (the fy output rows of a source-row step share 5 source rows, the pixels of a quad 5 columns) with the
+ * channels split over a thread-block cluster whose CTAs exchange their partial sums of squares through distributed
+ * shared memory: 3x less L2 traffic than the point-run kernel at C = 3072.
+ * rank (H*W int32): row index of every live pixel, -1 elsewhere (mv_rank_of_valid).  Row r = rank[y*W + x] of
+ * out_f16 / out_f16_lo is written for every live pixel.  mv_k1_grid_supported says whether a shape is covered. */
+int mv_k1_grid_supported(int C, int h, int w, int H, int W);
+int mv_rank_of_valid(const int32_t* valid_idx, const int32_t* n_dev, int n_max, int32_t* rank, int n_pixels, mv_stream_t stream);
+int mv_k1_grid_f16c(const float* src, int C, int h, int w, int H, int W, const int32_t* rank, int role, const float* center,
+                    const float* dotvec, uint16_t* out_f16, int pitch, uint16_t* out_f16_lo, mv_stream_t stream);
+
 /* mu (C floats) = mean over every `step`-th row p < n of rows[p] / max(||rows[p]||, 1e-12); rows (n, C) fp32 (a channel-last
  * feature map or a set of feature rows).  inv_scratch: ceil(n_max / step) floats.  Deterministic. */
 int mv_rows_center(const float* rows, int C, int n_max, const int32_t* n_dev, int step, float* inv_scratch, float* mu,

@@ -44,6 +44,9 @@ _CFG = {
     # how kernel 1 hands the fp32 rows to kernel 3 on the bf16 path: "split" = bf16 hi + bf16 residual planes
     # (4 bytes / element, hi doubles as kernel 2's operand), "f32" = bf16 + fp32 rows (6 bytes / element)
     "rows": os.environ.get("MVMATCH_ROWS", "split"),
+    # the NAVI-style side through the tiled cluster kernel (csrc/k1_grid.cu) where its shape is covered; 0 = always the
+    # point-run kernel (same-box A/B)
+    "k1_grid": int(os.environ.get("MVMATCH_K1_GRID", "1")),
 }
 _HELPER_GRAPHS = {}  # (kind, shapes, num_corr, ratio_test, dtype, cluster, K bytes) -> evaluation.GraphedPairMatcher
 _HELPER_GRAPHS_MAX = 8
@@ -53,10 +56,12 @@ _HELPER_GRAPHS_MAX = 8
 _PROFILE = {}
 
 
-def set_match_precision(dtype=None, cluster=None, helper_graphs=None, rows=None):
+def set_match_precision(dtype=None, cluster=None, helper_graphs=None, rows=None, k1_grid=None):
     """Choose kernel 2's operand type ("f16" | "bf16" | "tf32"), its cluster width (1, 2 or 4), whether the dense
     helpers replay cached CUDA graphs for host-tensor calls, and the row format between kernels 1 and 3
     ("split" | "f32", see _CFG)."""
+    if k1_grid is not None:
+        _CFG["k1_grid"] = int(bool(k1_grid))
     if rows is not None:
         if rows not in ("split", "f32"):
             raise ValueError("rows must be 'split' or 'f32'")
@@ -661,9 +666,20 @@ def _finish_xyz(f, g, staged, n, synced, want_taps=False, rows=None, role=L.MV_R
                L.ptr(coords), _stream())
     s.taps = _empty((max(n, 1), 2), torch.int32, dev) if want_taps else None
     w16, w32, wlo = _row_format(rows)
+    s.center = center
+    if (_CFG["k1_grid"] and _CFG["dtype"] == "f16" and w16 and wlo and not w32 and not want_taps and n > 0
+            and L.load().mv_k1_grid_supported(C, h, w, H, W)):
+        # f16c split rows of an integer-factor upsample: the tiled cluster kernel (a third of the L2 traffic)
+        rank = _empty((H * W,), torch.int32, dev)
+        L.call("mv_rank_of_valid", L.ptr(valid_idx), L.ptr(nd), n, L.ptr(rank), H * W, _stream())
+        s.rows16 = _empty((n, L.f16c_pitch(C)), torch.float16, dev)
+        s.rows_lo = _empty((n, C), torch.float16, dev)
+        s.rows32 = None
+        L.call("mv_k1_grid_f16c", L.ptr(src), C, h, w, H, W, L.ptr(rank), role, L.ptr(center), L.ptr(dotvec), L.ptr(s.rows16),
+               s.rows16.shape[1], L.ptr(s.rows_lo), _stream())
+        return s
     s.rows16, s.rows32, s.rows_lo = _sample(L.MV_SAMPLE_BICUBIC_CLAMP, src, C, h, w, coords, nd, n, True, w16, w32,
                                             s.taps, wlo, role=role, center=center, dotvec=dotvec)
-    s.center = center
     return s
 
 
@@ -756,7 +772,7 @@ def _graphed_helper(kind, feat_0, feat_1, grid_0, grid_1, num_corr, ratio_test, 
     layout = "hwc" if (_is_channel_last(feat_0) and _is_channel_last(feat_1)) else "chw"
     fdt = feat_0.dtype if (feat_0.dtype == feat_1.dtype and feat_0.dtype in _FEAT_DTYPES) else torch.float32
     # the intrinsics are NOT part of the key: they live in device memory and are refreshed per call (gm.load)
-    key = (kind, tuple(feat_0.shape), tuple(grid_0.shape), int(num_corr), bool(ratio_test), _CFG["dtype"], _CFG["cluster"], _CFG["rows"], fdt,
+    key = (kind, tuple(feat_0.shape), tuple(grid_0.shape), int(num_corr), bool(ratio_test), _CFG["dtype"], _CFG["cluster"], _CFG["rows"], _CFG["k1_grid"], fdt,
            dev.index, layout)
     gm = _HELPER_GRAPHS.get(key)
     if gm is None:

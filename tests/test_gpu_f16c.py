@@ -54,7 +54,7 @@ def test_f16c_row_planes_bit_exact(mv, C):
     assert ((got - y).abs() <= 0.5 * ulp * 1.01 + 2e-8).all()  # + a few fp32 ulps of the normalised row (summation order)
     assert (got != y.half().float()).float().mean() < 2e-3
     rebuilt = got + lo.float() / 2048.0
-    assert ((rebuilt - y).abs() <= y.abs() * 2.0 ** -21 + 1e-9).all()
+    assert ((rebuilt - y).abs() <= y.abs() * 2.0 ** -21 + 2e-8).all()
     aug = hi[:, C:C + 8].float().cpu()
     assert torch.equal(aug, torch.tensor([1.0, 1.0, 2.0 ** -11, 0, 0, 0, 0, 0]).expand(300, 8))
     assert (hi[:, C + 8:] == 9.0).all()  # the padding up to the 128-byte pitch is never written (and never read by kernel 2)

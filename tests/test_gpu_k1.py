@@ -153,11 +153,64 @@ def test_split_rows_rebuild_the_fp32_rows(C_, syn, C):
     err = (rebuilt - a.rows32[:n]).abs()
     assert bool((err <= 2.0 ** -16 * a.rows32[:n].abs() + 1e-30).all())
     # the default format: fp16 hi (C + 8 columns, 128-byte pitch) + fp16 residual scaled by 2^11 -> 2^-21 relative
-    a = C_.prepare_xyz_side(p["feat_0"], p["xyz_grid_0"], dev, rows="f32")
-    b = C_.prepare_xyz_side(p["feat_0"], p["xyz_grid_0"], dev, rows="split")
+    # (both through the point-run kernel: the tiled grid kernel sums the squares in another order, tested separately)
+    C_.set_match_precision(k1_grid=0)
+    try:
+        a = C_.prepare_xyz_side(p["feat_0"], p["xyz_grid_0"], dev, rows="f32")
+        b = C_.prepare_xyz_side(p["feat_0"], p["xyz_grid_0"], dev, rows="split")
+    finally:
+        C_.set_match_precision(k1_grid=1)
     assert b.rows16.dtype == torch.float16 and b.rows16.shape[1] == (C + 8 + 63) // 64 * 64 and b.rows32 is None
     assert torch.equal(a.rows16[:n, :C + 8], b.rows16[:n, :C + 8])
     assert torch.equal(a.rows32[:n].to(torch.float16), b.rows16[:n, :C])
     rebuilt = b.rows16[:n, :C].float() + b.rows_lo[:n].float() / 2048.0
     err = (rebuilt - a.rows32[:n]).abs()
     assert bool((err <= 2.0 ** -21 * a.rows32[:n].abs() + 1e-9).all())
+
+
+@pytest.mark.parametrize("shape", [dict(C=3072, h=28, w=28, H=112, W=112, radius=40.0), dict(C=768, h=14, w=14, H=56, W=56, radius=22.0),
+                                   dict(C=1536, h=8, w=8, H=32, W=32, radius=13.0), dict(C=1024, h=6, w=6, H=48, W=48, radius=20.0),
+                                   dict(C=2048, h=8, w=8, H=32, W=32, radius=15.0), dict(C=4096, h=4, w=4, H=16, W=16, radius=7.0),
+                                   dict(C=768, h=8, w=8, H=16, W=32, radius=9.0), dict(C=384, h=5, w=7, H=5, W=28, radius=20.0)])
+@pytest.mark.parametrize("role", ["query", "target"])
+def test_grid_kernel_equals_point_run_kernel_and_oracle(C_, mv, syn, shape, role):
+    """the tiled cluster kernel (csrc/k1_grid.cu: 2-D tiles, channels split over a thread-block cluster, partial sums of
+    squares exchanged through distributed shared memory) against the point-run kernel on the same inputs and against the
+    oracle: same arithmetic per element, only the order of the sum of squares differs."""
+    L = mv._lib
+    C, H, W = shape["C"], shape["H"], shape["W"]
+    assert L.load().mv_k1_grid_supported(C, shape["h"], shape["w"], H, W) == 1
+    p = syn.navi_pair(9, coherent=False, **shape)
+    dev = torch.device("cuda")
+    fm = C_._feature_map(p["feat_0"], dev)
+    mu = C_._center(fm[0], fm[0].shape[0])
+    kw = {"role": L.MV_ROLE_QUERY, "dotvec": mu} if role == "query" else {"role": L.MV_ROLE_TARGET, "center": mu}
+    outs = {}
+    for grid in (0, 1):
+        C_.set_match_precision(k1_grid=grid)
+        try:
+            s = C_.prepare_xyz_side(fm, p["xyz_grid_0"], dev, **kw)
+        finally:
+            C_.set_match_precision(k1_grid=1)
+        torch.cuda.synchronize()
+        outs[grid] = s
+    a, b = outs[0], outs[1]
+    n = a.n
+    assert b.n == n and n > 50 and b.rows16.shape == a.rows16.shape
+    ha, hb = a.rows16[:n, :C].float(), b.rows16[:n, :C].float()
+    ulp = (ha.abs().clamp(min=2.0 ** -14) * 2.0 ** -10)
+    assert ((ha - hb).abs() <= ulp).all()                       # at most one fp16 step, on the few elements that sit at a rounding boundary
+    assert (ha != hb).float().mean() < 0.01
+    ra, rb = ha + a.rows_lo[:n].float() / 2048.0, hb + b.rows_lo[:n].float() / 2048.0
+    full = ra + (mu[None] if role == "target" else 0.0)
+    assert ((ra - rb).abs() <= 4e-7 * full.abs() + 1e-9).all()   # the rebuilt fp32 rows: a few ulps of the row (norm summation order)
+    auga, augb = a.rows16[:n, C:C + 8].float(), b.rows16[:n, C:C + 8].float()
+    if role == "target":
+        assert torch.equal(auga, augb)
+    else:
+        ra_, rb_ = auga[:, 0] + auga[:, 1] + auga[:, 2] / 2048.0, augb[:, 0] + augb[:, 1] + augb[:, 2] / 2048.0
+        torch.testing.assert_close(ra_, rb_, rtol=0, atol=2e-6)
+    _, f_o, _, _ = restated.xyz_side(p["feat_0"], p["xyz_grid_0"])
+    want = F.normalize(f_o, dim=-1)
+    rebuilt = rb + (mu[None] if role == "target" else 0.0)
+    torch.testing.assert_close(rebuilt.cpu(), want, rtol=0, atol=ATOL)

