@@ -489,13 +489,14 @@ def k1_record(ctx):
         p = ctx.pair(kind, 0)
         f = p["feat_0"].to(dev)
         calls = []
-        orig = C_._sample
+        orig_call = L.call
 
-        def spy(*a, **kw):
-            calls.append((a, kw))
-            return orig(*a, **kw)
+        def spy(name, *a):
+            if name in ("mv_k1_sample_f16c", "mv_k1_sample_normalize", "mv_k1_grid_f16c"):
+                calls.append((name, a))
+            return orig_call(name, *a)
 
-        C_._sample = spy
+        L.call = spy
         try:
             fm0, fm1, kw0, kw1 = C_._pair_maps(f, p["feat_1"].to(dev), dev)
             if kind == "navi":
@@ -504,22 +505,22 @@ def k1_record(ctx):
                 Kh, Kinv = C_._host_mat(p["K"]), C_._host_mat(p["K"].inverse())
                 s = C_.prepare_depth_side(fm0, p["depth_0"].to(dev), Kh, Kinv, dev, sync=True, **kw0)
         finally:
-            C_._sample = orig
-        (mode, src, C, h, w, coords, n_dev, n, normalize, w16, w32), kw = calls[0][0][:11], calls[0][1]
-        f16 = C_._CFG["dtype"] == "f16"
+            L.call = orig_call
+        name, a = calls[0]
+        n, C, h, w = s.n, fm0[1], fm0[2], fm0[3]
+        f16 = name != "mv_k1_sample_normalize"
         t16 = torch.float16 if f16 else torch.bfloat16
         pitch = L.f16c_pitch(C) if f16 else C
         sets = [(torch.empty((n, pitch), dtype=t16, device=dev), torch.empty((n, C), dtype=t16, device=dev)) for _ in range(6)]
+        # positions of the (stream, 16-bit rows, residual rows) arguments of the recorded call
+        slots = {"mv_k1_sample_f16c": (-1, 12, 14), "mv_k1_sample_normalize": (-1, 9, 10), "mv_k1_grid_f16c": (-1, 10, 12)}[name]
         st = torch.cuda.Stream()
         with torch.cuda.stream(st):
             def launch(i):
                 hi, lo = sets[i % 6]
-                if f16:
-                    L.call("mv_k1_sample_f16c", mode, L.ptr(src), C, h, w, L.ptr(coords), None, n, 1, kw.get("role", 0), L.ptr(kw.get("center")),
-                           L.ptr(kw.get("dotvec")), L.ptr(hi), pitch, L.ptr(lo), None, None, None, c_void_p(st.cuda_stream))
-                else:
-                    L.call("mv_k1_sample_normalize", mode, L.ptr(src), C, h, w, L.ptr(coords), None, n, 1, L.ptr(hi), L.ptr(lo), None, None,
-                           c_void_p(st.cuda_stream))
+                b = list(a)
+                b[slots[0]], b[slots[1]], b[slots[2]] = c_void_p(st.cuda_stream), L.ptr(hi), L.ptr(lo)
+                L.call(name, *b)
             launch(0)
             st.synchronize()
             g = torch.cuda.CUDAGraph()
@@ -540,7 +541,7 @@ def k1_record(ctx):
         surveyed = C * h * w * 4 + n * C * 2
         moved = C * h * w * 4 + n * ((C + 8 if f16 else C) + C) * 2
         out[f"{kind}_side"] = {
-            "points": n, "C": C, "mode": "bicubic 4x (28x28 -> live pixels of 112x112)" if kind == "navi" else "bilinear (15x20 -> 120x160 depth pixels)",
+            "points": n, "C": C, "entry_point": name, "mode": "bicubic 4x (28x28 -> live pixels of 112x112)" if kind == "navi" else "bilinear (15x20 -> 120x160 depth pixels)",
             "avg_us": us, "bytes_surveyed": surveyed, "bytes_moved": moved,
             "GB/s_surveyed": surveyed / us / 1e3, "GB/s_moved": moved / us / 1e3, "peak": hbm_peak, "peak_kind": f"{peak_kind} copy bandwidth (read + write)",
             "frac_surveyed": surveyed / us / 1e3 / hbm_peak, "frac_moved": moved / us / 1e3 / hbm_peak,
@@ -754,6 +755,7 @@ def main():
     ap.add_argument("--feat-dtype", default="f32", choices=["f32", "bf16"],
                     help="dtype of the feature tensors handed to the path: f32 = the reference's convention (BASELINE config); "
                          "bf16 = an autocast backbone's output, uploaded as 16-bit and widened on the device (supplementary)")
+    ap.add_argument("--k1-only", action="store_true", help="print only the kernel-1 record (CUDA-event timing of kernel 1 alone) and exit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stress", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
@@ -770,6 +772,9 @@ def main():
     ctx.init_device()
     ctx.mv.correspondence.set_match_precision(dtype=args.dtype, cluster=args.cluster)
     _, tc_peak, _, _ = peaks()
+    if args.k1_only:
+        print(json.dumps({"k1": k1_record(ctx), "k1_grid": ctx.mv.correspondence._CFG["k1_grid"]}), flush=True)
+        return
     head = "navi" if args.workload == "all" else args.workload
     if head == "spair":
         line = run_spair(ctx, args.steps, args.warmup)

@@ -70,6 +70,15 @@ const char* mv_last_error(void);
 /* sm count, compute capability and L2 size of `device` (host out-params, any may be NULL) */
 int mv_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int* l2_bytes);
 
+/* ---- host -> device upload of pageable memory -------------------------------------------- */
+/* The reference's callers hold plain CPU tensors (.detach().cpu(), evaluate_navi_correspondence.py:149-150): pageable
+ * memory, which a plain cudaMemcpyAsync stages on the calling thread at a fifth of the PCIe rate.  mv_h2d_staged copies
+ * `bytes` from src_host to dst_device through a pinned ring filled by a small pool of worker threads (MVMATCH_STAGE_THREADS,
+ * default 4), one plain cudaMemcpyAsync per 1 MiB chunk on `stream`.  Returns when every chunk has been issued: src_host
+ * may be modified afterwards, the transfers complete in stream order.  One upload at a time per process. */
+int mv_h2d_staged(void* dst_device, const void* src_host, size_t bytes, mv_stream_t stream);
+int mv_h2d_staged_threads(void);
+
 /* ---- layout helpers ------------------------------------------------------------------ */
 /* (C, hw) channel-major fp32 map -> (hw, C) channel-last.  prenorm != 0 additionally divides
  * every pixel's C-vector by max(||.||_2, 1e-12)  (SPair: F.normalize(feats, p=2, dim=1),

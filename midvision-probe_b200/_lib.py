@@ -18,6 +18,8 @@ PROTOTYPES = {
     "mv_version": (c_int, []),
     "mv_last_error": (c_char_p, []),
     "mv_device_info": (c_int, [c_int, P, P, P, P]),
+    "mv_h2d_staged": (c_int, [P, P, c_size_t, P]),
+    "mv_h2d_staged_threads": (c_int, []),
     "mv_chw_to_hwc": (c_int, [P, P, c_int, c_int, c_int, P, P]),
     "mv_feat_to_hwc_f32": (c_int, [P, c_int, c_int, c_int, c_int, P, P]),
     "mv_compact_valid": (c_int, [P, c_int, c_int, P, P, P]),

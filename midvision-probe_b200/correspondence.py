@@ -44,9 +44,10 @@ _CFG = {
     # how kernel 1 hands the fp32 rows to kernel 3 on the bf16 path: "split" = bf16 hi + bf16 residual planes
     # (4 bytes / element, hi doubles as kernel 2's operand), "f32" = bf16 + fp32 rows (6 bytes / element)
     "rows": os.environ.get("MVMATCH_ROWS", "split"),
-    # the NAVI-style side through the tiled cluster kernel (csrc/k1_grid.cu) where its shape is covered; 0 = always the
-    # point-run kernel (same-box A/B)
-    "k1_grid": int(os.environ.get("MVMATCH_K1_GRID", "1")),
+    # 1 = the NAVI-style side through the tiled cluster kernel (csrc/k1_grid.cu) where its shape is covered.  Measured on
+    # B200 (bench.py --k1-only, same box): 56.2 us against 32.3 us of the point-run kernel for a NAVI-shaped side -- a third
+    # of the L2 traffic, but 16 warps per SM behind a cluster barrier per round are latency-bound -- so it is OFF by default
+    "k1_grid": int(os.environ.get("MVMATCH_K1_GRID", "0")),
 }
 _HELPER_GRAPHS = {}  # (kind, shapes, num_corr, ratio_test, dtype, cluster, K bytes) -> evaluation.GraphedPairMatcher
 _HELPER_GRAPHS_MAX = 8

@@ -224,6 +224,30 @@ def match_and_score_xyz(feat_0, feat_1, xyz_grid_0, xyz_grid_1, intrinsics, Rt, 
     return r
 
 
+STAGE_MIN_BYTES = 1 << 18  # below this a plain copy_ is as fast
+
+
+def copy_in(dst, src, stream=None):
+    """dst.copy_(src) for a device tensor dst; a large PAGEABLE host tensor of the same dtype and memory order goes through
+    the library's threaded pinned staging ring (mv_h2d_staged) instead of the driver's single-threaded staging."""
+    if (src.device.type == "cpu" and not src.is_pinned() and src.dtype == dst.dtype and src.numel() == dst.numel()
+            and src.numel() * src.element_size() >= STAGE_MIN_BYTES and src.stride() == dst.stride()
+            and _dense(src) and _dense(dst)):
+        st = stream if stream is not None else torch.cuda.current_stream(dst.device)
+        L.call("mv_h2d_staged", c_void_p(dst.data_ptr()), c_void_p(src.data_ptr()), src.numel() * src.element_size(),
+               c_void_p(st.cuda_stream))
+        return
+    dst.copy_(src, non_blocking=True)
+
+
+def _dense(t):
+    """True when the tensor's elements occupy one contiguous block (any permutation of a contiguous layout)."""
+    if t.is_contiguous():
+        return True
+    order = sorted(range(t.dim()), key=lambda d: -t.stride(d))
+    return t.permute(order).is_contiguous()
+
+
 class GraphedPairMatcher:
     """The per-pair device pipeline (kernel 1 for both images, kernel 2, kernel 3 ratio / mutual / top-k)
     captured ONCE into a CUDA graph and replayed per pair: the ~25 launches of a pair cost one graph launch,
@@ -342,11 +366,12 @@ class GraphedPairMatcher:
         PCIe link better than one (measured: 463 -> ~390 us for the 19.6 MB of a NAVI-shaped pair)."""
         if K is not None and self.kind == "depth":
             self.set_intrinsics(K)
-        if not two_streams:
-            self.f0.copy_(feat_0, non_blocking=True)
-            self.f1.copy_(feat_1, non_blocking=True)
-            self.g0.copy_(grid_0, non_blocking=True)
-            self.g1.copy_(grid_1, non_blocking=True)
+        pageable = feat_0.device.type == "cpu" and not feat_0.is_pinned()
+        if not two_streams or pageable:  # pageable sources: the staging threads already keep the link busy on one stream
+            copy_in(self.f0, feat_0)
+            copy_in(self.f1, feat_1)
+            copy_in(self.g0, grid_0)
+            copy_in(self.g1, grid_1)
             return
         cur = torch.cuda.current_stream(self.dev)
         if getattr(self, "_copy_stream", None) is None:
