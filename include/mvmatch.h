@@ -74,7 +74,7 @@ int mv_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, int*
 /* The reference's callers hold plain CPU tensors (.detach().cpu(), evaluate_navi_correspondence.py:149-150): pageable
  * memory, which a plain cudaMemcpyAsync stages on the calling thread at a fifth of the PCIe rate.  mv_h2d_staged copies
  * `bytes` from src_host to dst_device through a pinned ring filled by a small pool of worker threads (MVMATCH_STAGE_THREADS,
- * default 4), one plain cudaMemcpyAsync per 1 MiB chunk on `stream`.  Returns when every chunk has been issued: src_host
+ * default: half of the cores, at most 8), one plain cudaMemcpyAsync per 1 MiB chunk on `stream`.  Returns when every chunk has been issued: src_host
  * may be modified afterwards, the transfers complete in stream order.  One upload at a time per process. */
 int mv_h2d_staged(void* dst_device, const void* src_host, size_t bytes, mv_stream_t stream);
 int mv_h2d_staged_threads(void);
@@ -195,6 +195,13 @@ int mv_k2_sim_top2(const void* A, const void* B, int n_max, int m_max, int C, co
 int mv_k2_sim_top2_ld(const void* A, int lda, const void* B, int ldb, int n_max, int m_max, int C, const int32_t* n_dev,
                       const int32_t* m_dev, int dtype, int cluster, float* row_val, int32_t* row_idx,
                       unsigned long long* col_best, void* workspace, size_t workspace_bytes, mv_stream_t stream);
+/* The same GEMM with the similarity matrix WRITTEN OUT as well: S_out (n_max, ld_s) fp32, S[i][j] = A[i] . B[j] (rows / columns
+ * beyond the live counts are left untouched).  For consumers that need the matrix itself -- MaskCut's normalised affinity
+ * feats^T @ feats (evals/models/maskcut_processor.py:77-78) -- instead of its row top-2 / column arg-max, which are still
+ * produced (the epilogue is the same kernel; S_out == NULL is exactly mv_k2_sim_top2_ld). */
+int mv_k2_affinity(const void* A, int lda, const void* B, int ldb, int n_max, int m_max, int C, const int32_t* n_dev,
+                   const int32_t* m_dev, int dtype, int cluster, float* S_out, int ld_s, float* row_val, int32_t* row_idx,
+                   unsigned long long* col_best, void* workspace, size_t workspace_bytes, mv_stream_t stream);
 int mv_k2_unpack_col(const unsigned long long* col_best, int m, float* col_val, int32_t* col_idx, mv_stream_t stream);
 
 /* ---- kernel 3: fp32 distance recompute, ratio test, mutual check, selection, scoring ---- */
@@ -218,6 +225,16 @@ int mv_k3_ratio_mutual_f16c(const uint16_t* A_hi, const uint16_t* A_lo, const ui
                             const float* center_B, const int32_t* n_dev, int n_max, int32_t* row_idx,
                             const unsigned long long* col_best, int ratio_test, float* dists, float* weight, uint8_t* mutual,
                             mv_stream_t stream);
+
+/* MaskCut's thresholded affinity (evals/models/maskcut_processor.py:103-106): A[i][j] = S[i][j] > tau ? 1 : eps, written as
+ * fp32, and count[i] = #{j : S[i][j] > tau} (so that d_i = count + (m - count) * eps is exact in any precision).  S (n, ld_s). */
+int mv_affinity_threshold(const float* S, int n, int m, int ld_s, float tau, float eps, float* A_out, int32_t* count, mv_stream_t stream);
+
+/* 2AFC perceptual evaluation (evaluate_model_percepture.py:46-48, :118-122): per sample i the cosine similarities
+ * sim_l = cos(ref_i, left_i), sim_r = cos(ref_i, right_i) with torch.nn.functional.cosine_similarity's arithmetic
+ * (x . y / (max(|x|, 1e-8) * max(|y|, 1e-8))) and pred_i = sim_l > sim_r ? 0 : 1.  Rows (n, C) fp32, C % 4 == 0. */
+int mv_cosine_2afc(const float* ref, const float* left, const float* right, int n, int C, float* sim_left, float* sim_right,
+                   int32_t* pred, mv_stream_t stream);
 
 /* get_topk_matches (correspondence.py:125-129): the k = min(num_corr, n) largest weights, sorted
  * descending (ties: lower row first).  sel_* have num_corr entries; k_dev receives k.

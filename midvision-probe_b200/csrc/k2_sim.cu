@@ -77,6 +77,8 @@ struct K2Params {
   int clusters;     // clusters in the grid
   float4* partial;  // (clusters + n_sb_max) slots of MC * 128 rows x 2 column halves of {max1, idx1, max2, idx2}; slot = cluster + sb
   unsigned long long* col_best;
+  float* S_out;     // optional (n_max, ld_s) fp32: the similarity tile is also written out (affinity consumers, mv_k2_affinity)
+  int ld_s;
 };
 
 __host__ __device__ inline K2Sched make_sched(int n, int m, int mc, int clusters) {
@@ -292,6 +294,17 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
         if (edge) {
 #pragma unroll
           for (int q = 0; q < 32; ++q) v[q] = (row_ok && cb + q < m) ? v[q] : -CUDART_INF_F;
+        }
+        if (p.S_out != nullptr && row_ok) {  // similarity-only consumers (MaskCut's affinity): the tile goes to memory as well
+          float* dst = p.S_out + (size_t)(row0 + e) * p.ld_s + cb;
+          if (cb + 32 <= m) {
+#pragma unroll
+            for (int q = 0; q < 32; q += 4) *reinterpret_cast<float4*>(dst + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              if (cb + q < m) dst[q] = v[q];
+          }
         }
         // ---- rows: this thread's row against its running top-2.  Only groups of 8 columns whose maximum
         // beats the current second best are scanned (rare after the first tiles of a row block).
@@ -555,6 +568,15 @@ int mv_k2_sim_top2(const void* A, const void* B, int n_max, int m_max, int C, co
 int mv_k2_sim_top2_ld(const void* A, int lda, const void* B, int ldb, int n_max, int m_max, int C, const int32_t* n_dev,
                       const int32_t* m_dev, int dtype, int cluster, float* row_val, int32_t* row_idx,
                       unsigned long long* col_best, void* workspace, size_t workspace_bytes, mv_stream_t stream) {
+  return mv_k2_affinity(A, lda, B, ldb, n_max, m_max, C, n_dev, m_dev, dtype, cluster, nullptr, 0, row_val, row_idx, col_best, workspace,
+                        workspace_bytes, stream);
+}
+
+int mv_k2_affinity(const void* A, int lda, const void* B, int ldb, int n_max, int m_max, int C, const int32_t* n_dev,
+                   const int32_t* m_dev, int dtype, int cluster, float* S_out, int ld_s, float* row_val, int32_t* row_idx,
+                   unsigned long long* col_best, void* workspace, size_t workspace_bytes, mv_stream_t stream) {
+  MV_REQUIRE(!S_out || (ld_s >= m_max && ld_s % 4 == 0 && ((uintptr_t)S_out & 15) == 0), MV_E_ALIGN,
+             "mv_k2_affinity: S_out must be 16-byte aligned with a row pitch >= m_max that is a multiple of 4 floats");
   MV_REQUIRE(A && B && row_val && row_idx && col_best && workspace, MV_E_ARG, "mv_k2_sim_top2: null pointer");
   MV_REQUIRE(lda >= C && ldb >= C && (lda * (dtype == MV_DTYPE_TF32 ? 4 : 2)) % 16 == 0 && (ldb * (dtype == MV_DTYPE_TF32 ? 4 : 2)) % 16 == 0,
              MV_E_ALIGN, "mv_k2_sim_top2: row pitches (%d, %d) must be >= C and a multiple of 16 bytes", lda, ldb);
@@ -598,6 +620,8 @@ int mv_k2_sim_top2_ld(const void* A, int lda, const void* B, int ldb, int n_max,
   p.ab_fmt = tf32 ? 2u : (dtype == MV_DTYPE_F16 ? 0u : 1u);
   p.partial = reinterpret_cast<float4*>(workspace);
   p.col_best = col_best;
+  p.S_out = S_out;
+  p.ld_s = ld_s;
 
   CUtensorMap tmA, tmB;
   int rc = make_operand_map(&tmA, A, n_max, C, lda, dtype, BM);

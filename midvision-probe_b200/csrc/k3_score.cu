@@ -180,6 +180,51 @@ __global__ void __launch_bounds__(RATIO_THREADS, 6) k3_ratio_mutual_kernel(ROWS 
 }
 
 // ------------------------------------------------------------------------------------------
+// adjacent similarity consumers
+// ------------------------------------------------------------------------------------------
+// MaskCut: A = S > tau ? 1 : eps and the per-row counts (maskcut_processor.py:103-106); one warp per row
+__global__ void affinity_threshold_kernel(const float* __restrict__ S, int n, int m, int ld_s, float tau, float eps,
+                                          float* __restrict__ A_out, int32_t* __restrict__ count) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= n) return;
+  int c = 0;
+  for (int j = lane; j < m; j += 32) {
+    const bool on = S[(size_t)i * ld_s + j] > tau;
+    c += on ? 1 : 0;
+    if (A_out) A_out[(size_t)i * m + j] = on ? 1.f : eps;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0 && count) count[i] = c;
+}
+
+// 2AFC: cos(ref, left), cos(ref, right) per sample (F.cosine_similarity, eps 1e-8) and the prediction; one warp per sample
+__global__ void cosine_2afc_kernel(const float* __restrict__ ref, const float* __restrict__ left, const float* __restrict__ right,
+                                   int n, int C, float* __restrict__ sim_left, float* __restrict__ sim_right,
+                                   int32_t* __restrict__ pred) {
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= n) return;
+  const float4* x = reinterpret_cast<const float4*>(ref + (size_t)i * C);
+  const float4* a = reinterpret_cast<const float4*>(left + (size_t)i * C);
+  const float4* b = reinterpret_cast<const float4*>(right + (size_t)i * C);
+  float xx = 0.f, aa = 0.f, bb = 0.f, xa = 0.f, xb = 0.f;
+  for (int c = lane; c < (C >> 2); c += 32) {
+    const float4 v = __ldg(x + c), p = __ldg(a + c), q = __ldg(b + c);
+    acc5(v.x, p.x, q.x, xx, aa, bb, xa, xb);
+    acc5(v.y, p.y, q.y, xx, aa, bb, xa, xb);
+    acc5(v.z, p.z, q.z, xx, aa, bb, xa, xb);
+    acc5(v.w, p.w, q.w, xx, aa, bb, xa, xb);
+  }
+  xx = warp_sum(xx); aa = warp_sum(aa); bb = warp_sum(bb); xa = warp_sum(xa); xb = warp_sum(xb);
+  if (lane != 0) return;
+  const float nx = fmaxf(sqrtf(xx), COS_EPS);
+  const float sl = xa / (nx * fmaxf(sqrtf(aa), COS_EPS)), sr = xb / (nx * fmaxf(sqrtf(bb), COS_EPS));
+  if (sim_left) sim_left[i] = sl;
+  if (sim_right) sim_right[i] = sr;
+  if (pred) pred[i] = sl > sr ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------------------------
 // top-k of the weights (single CTA, 1024 threads): radix select the k-th key, stable pick among the
 // ties, bitonic sort of the k winners by (weight desc, row asc)
 // 20 us for 5 k weights / k = 1000.  Measured and rejected: caching the keys in shared memory (20.2 us, the five
@@ -553,6 +598,26 @@ int mv_k3_ratio_mutual_f16c(const uint16_t* A_hi, const uint16_t* A_lo, const ui
                 reinterpret_cast<const __half*>(B_lo), center_B, pitch};
   k3_ratio_mutual_kernel<RowsF16c><<<(n_max + rows_per_cta - 1) / rows_per_cta, 32 * rows_per_cta, 0, mv_cuda_stream(stream)>>>(
       rows, C, n_dev, n_max, row_idx, col_best, ratio_test, dists, weight, mutual);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+int mv_affinity_threshold(const float* S, int n, int m, int ld_s, float tau, float eps, float* A_out, int32_t* count, mv_stream_t stream) {
+  MV_REQUIRE(S && (A_out || count), MV_E_ARG, "mv_affinity_threshold: null pointer");
+  MV_REQUIRE(n >= 0 && m >= 0 && ld_s >= m, MV_E_ARG, "mv_affinity_threshold: bad sizes");
+  if (n == 0) return MV_OK;
+  affinity_threshold_kernel<<<(n + 7) / 8, 256, 0, mv_cuda_stream(stream)>>>(S, n, m, ld_s, tau, eps, A_out, count);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+int mv_cosine_2afc(const float* ref, const float* left, const float* right, int n, int C, float* sim_left, float* sim_right,
+                   int32_t* pred, mv_stream_t stream) {
+  MV_REQUIRE(ref && left && right && (sim_left || sim_right || pred), MV_E_ARG, "mv_cosine_2afc: null pointer");
+  MV_REQUIRE(n >= 0 && C > 0 && C % 4 == 0, MV_E_ALIGN, "mv_cosine_2afc: C=%d must be a positive multiple of 4", C);
+  MV_REQUIRE((((uintptr_t)ref | (uintptr_t)left | (uintptr_t)right) & 15) == 0, MV_E_ALIGN, "mv_cosine_2afc: rows must be 16-byte aligned");
+  if (n == 0) return MV_OK;
+  cosine_2afc_kernel<<<(n + 7) / 8, 256, 0, mv_cuda_stream(stream)>>>(ref, left, right, n, C, sim_left, sim_right, pred);
   MV_LAUNCH_CHECK();
   return MV_OK;
 }

@@ -224,7 +224,7 @@ def match_and_score_xyz(feat_0, feat_1, xyz_grid_0, xyz_grid_1, intrinsics, Rt, 
     return r
 
 
-STAGE_MIN_BYTES = 1 << 18  # below this a plain copy_ is as fast
+STAGE_MIN_BYTES = 1 << 15  # below this a plain copy_ is as fast; above, the driver's own pageable path also serialises with the stream
 
 
 def copy_in(dst, src, stream=None):

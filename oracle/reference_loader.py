@@ -137,3 +137,43 @@ def navi_error_block_reference(feats_0, feats_1, xyz_grid_0, xyz_grid_1, Rt_gt, 
     exec(compile(block, path, "exec"), ns)  # noqa: S102 -- the reference's own text, test infrastructure only
     return {"err_3d": ns["err_3d"], "err_2d": ns["err_2d"], "results": ns["results"], "bin_rec": ns["bin_rec"],
             "rec_2cm": ns["rec_2cm"], "rel_ang": ns["rel_ang"]}
+
+
+def _exec_lines(path, first_marker, last_marker, ns):
+    """exec the lines of a reference file from the one containing first_marker to the one containing last_marker."""
+    import textwrap
+
+    lines = open(os.path.join(REFERENCE_ROOT, path)).read().splitlines()
+    beg = next(i for i, l in enumerate(lines) if first_marker in l)
+    end = next(i for i, l in enumerate(lines) if last_marker in l and i >= beg)
+    exec(compile(textwrap.dedent("\n".join(lines[beg:end + 1])), path, "exec"), ns)  # noqa: S102 -- the reference's own text
+    return ns
+
+
+def maskcut_affinity_reference(feats, tau, eps=1e-5):
+    """the reference's own affinity lines (evals/models/maskcut_processor.py:77-78 and :103-106), executed from its file
+    (the module itself needs pydensecrf / sklearn / wandb to import): -> (A_raw, A_thresholded, d_i)."""
+    import numpy as np
+    import torch.nn.functional as F
+
+    ns = {"feats": feats, "F": F, "np": np}
+    _exec_lines("evals/models/maskcut_processor.py", "feats = F.normalize(feats, p=2, dim=0)", "A = (feats.transpose(0, 1) @ feats).cpu().numpy()", ns)
+    raw = ns["A"].copy()
+    ns.update({"tau": tau, "eps": eps})
+    _exec_lines("evals/models/maskcut_processor.py", "A = A > tau", "d_i = np.sum(A, axis=1)", ns)
+    return raw, ns["A"], ns["d_i"]
+
+
+def twoafc_reference(ref, left, right):
+    """cosine_similarity_batch of evaluate_model_percepture.py:46-48 and the prediction line :120-122, from the file."""
+    import torch
+    import torch.nn.functional as F
+
+    ns = {"F": F, "torch": torch}
+    _exec_lines("evaluate_model_percepture.py", "def cosine_similarity_batch(tensor1, tensor2):", "return F.cosine_similarity(tensor1, tensor2, dim=-1)", ns)
+    ns.update({"features_ref": ref, "features_left": left, "features_right": right})
+    ns["similarity_left"] = ns["cosine_similarity_batch"](ref, left)
+    ns["similarity_right"] = ns["cosine_similarity_batch"](ref, right)
+    _exec_lines("evaluate_model_percepture.py", "predictions = torch.where(similarity_left > similarity_right, 0, 1)",
+                "predictions = torch.where(similarity_left > similarity_right, 0, 1)", ns)
+    return ns["similarity_left"], ns["similarity_right"], ns["predictions"]

@@ -280,3 +280,23 @@ def so3_rotation_angle(R, eps=1e-4):
     if ((tr < -1.0 - eps) + (tr > 3.0 + eps)).any():
         raise ValueError("A matrix has trace outside valid range [-1-eps,3+eps].")
     return torch.acos(((tr - 1.0) * 0.5).clamp(min=-1, max=1))
+
+
+# ---- the adjacent similarity consumers ---------------------------------------------------
+def maskcut_affinity(feats, tau=None, eps=1e-5):
+    """evals/models/maskcut_processor.py:77-78 (normalised affinity of the columns of feats (C, N)) and, for a given
+    tau, :103-106 (A = A > tau; zeros -> eps; d_i = row sums).  The k-means choice of tau (:80-96) is not restated."""
+    f = F.normalize(feats.float(), p=2, dim=0)
+    A = f.transpose(0, 1) @ f
+    if tau is None:
+        return A
+    B = (A > tau).double()
+    B = torch.where(B == 0, torch.full_like(B, eps), B)
+    return A, B, B.sum(dim=1)
+
+
+def twoafc(features_ref, features_left, features_right):
+    """evaluate_model_percepture.py:46-48, :118-122."""
+    sl = F.cosine_similarity(features_ref, features_left, dim=-1)
+    sr = F.cosine_similarity(features_ref, features_right, dim=-1)
+    return sl, sr, torch.where(sl > sr, 0, 1)

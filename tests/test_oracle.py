@@ -195,3 +195,21 @@ def test_bidirectional_and_error_auc_restatements(mv):
     np.testing.assert_allclose(mv.correspondence.error_auc(errs, thr), want, rtol=0, atol=0)
     np.testing.assert_allclose(want, ERROR_AUC_GOLDEN, rtol=0, atol=1e-12)  # the constant test_host_logic checks on the GPU box
 
+
+
+@pytest.mark.skipif(not reference_loader.available(), reason="reference tree not on this machine")
+def test_adjacent_consumers_restated_equal_the_reference_text():
+    """MaskCut's affinity lines and the 2AFC cosine lines, executed from the reference's files, against the restatements."""
+    g = torch.Generator().manual_seed(3)
+    feats = torch.rand(96, 1, generator=g) + 0.5 * torch.randn(96, 50, generator=g)
+    raw, thr, d = reference_loader.maskcut_affinity_reference(feats, tau=0.6)
+    A, B, dB = restated.maskcut_affinity(feats, tau=0.6)
+    np.testing.assert_allclose(A.numpy(), raw, rtol=0, atol=0)
+    np.testing.assert_allclose(B.numpy(), thr, rtol=0, atol=0)
+    np.testing.assert_allclose(dB.numpy(), d, rtol=0, atol=1e-12)
+    ref = torch.randn(20, 64, generator=g)
+    left, right = ref + torch.randn(20, 64, generator=g), ref + torch.randn(20, 64, generator=g)
+    a = reference_loader.twoafc_reference(ref, left, right)
+    b = restated.twoafc(ref, left, right)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
