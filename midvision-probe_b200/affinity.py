@@ -23,9 +23,9 @@ def cosine_affinity(feats, return_neighbours=False):
     """(N, N) fp32 cosine affinity of the N columns of feats (C, N) -- the `A` of get_affinity_matrix before its
     `.cpu().numpy()` (maskcut_processor.py:77-78) -- on the device of `feats`.
 
-    The product runs on kernel 2 (tcgen05) with the operand type of set_match_precision; with the default f16c rows its
-    entries are within ~2e-5 of the fp32 product (a plain 16-bit product is off by 1e-4..1e-3 on the nearly collinear
-    token features MaskCut sees), "tf32" gives ~1e-4.  return_neighbours: also the per-row top-2 (values, indices) that
+    The product runs on kernel 2 (tcgen05) with the operand type of set_match_precision.  Stated tolerance against the
+    fp32 product: 1e-4 with the default f16c rows (measured <= 6e-5; the closer to collinear the token features are, the
+    smaller -- a plain bf16 product is off by up to 1e-3), 1.5e-3 with "tf32" (the tensor core truncates fp32 operands).  return_neighbours: also the per-row top-2 (values, indices) that
     the same launch produces."""
     dev = C_._device()
     in_dev = feats.device

@@ -48,9 +48,12 @@ _CFG = {
     # B200 (bench.py --k1-only, same box): 56.2 us against 32.3 us of the point-run kernel for a NAVI-shaped side -- a third
     # of the L2 traffic, but 16 warps per SM behind a cluster barrier per round are latency-bound -- so it is OFF by default
     "k1_grid": int(os.environ.get("MVMATCH_K1_GRID", "0")),
+    # host-tensor calls of the dense helpers: two graphs (target side / the rest) so that the second image's upload overlaps
+    # the first one's kernels (evaluation.GraphedPairMatcher.load_and_replay_split); 0 = one graph after both uploads
+    "helper_split": int(os.environ.get("MVMATCH_HELPER_SPLIT", "1")),
 }
 _HELPER_GRAPHS = {}  # (kind, shapes, num_corr, ratio_test, dtype, cluster, K bytes) -> evaluation.GraphedPairMatcher
-_HELPER_GRAPHS_MAX = 8
+_HELPER_GRAPHS_MAX = 12
 
 
 # bench.py sets _PROFILE["k2_events"] = [] to collect (start, end, flop) CUDA-event records of kernel 2
@@ -772,8 +775,9 @@ def _graphed_helper(kind, feat_0, feat_1, grid_0, grid_1, num_corr, ratio_test, 
         return None  # two differently sized images (the reference accepts them): the eager path handles any shapes
     layout = "hwc" if (_is_channel_last(feat_0) and _is_channel_last(feat_1)) else "chw"
     fdt = feat_0.dtype if (feat_0.dtype == feat_1.dtype and feat_0.dtype in _FEAT_DTYPES) else torch.float32
+    on_host = feat_0.device.type == "cpu"
     # the intrinsics are NOT part of the key: they live in device memory and are refreshed per call (gm.load)
-    key = (kind, tuple(feat_0.shape), tuple(grid_0.shape), int(num_corr), bool(ratio_test), _CFG["dtype"], _CFG["cluster"], _CFG["rows"], _CFG["k1_grid"], fdt,
+    key = (on_host, kind, tuple(feat_0.shape), tuple(grid_0.shape), int(num_corr), bool(ratio_test), _CFG["dtype"], _CFG["cluster"], _CFG["rows"], _CFG["k1_grid"], fdt,
            dev.index, layout)
     gm = _HELPER_GRAPHS.get(key)
     if gm is None:
@@ -783,12 +787,15 @@ def _graphed_helper(kind, feat_0, feat_1, grid_0, grid_1, num_corr, ratio_test, 
         if len(_HELPER_GRAPHS) >= _HELPER_GRAPHS_MAX:
             _HELPER_GRAPHS.pop(next(iter(_HELPER_GRAPHS)))
         gm = ev.GraphedPairMatcher(kind, tuple(feat_0.shape), tuple(grid_0.shape), num_corr, K=K, device=dev,
-                                   ratio_test=ratio_test, with_outputs=True, feat_layout=layout, feat_dtype=fdt).capture()
+                                   ratio_test=ratio_test, with_outputs=True, feat_layout=layout, feat_dtype=fdt,
+                                   split=on_host and bool(_CFG["helper_split"])).capture()
         _HELPER_GRAPHS[key] = gm
-    on_host = feat_0.device.type == "cpu"
-    gm.load(feat_0, feat_1, grid_0, grid_1, two_streams=on_host, K=K)
-    gm.graph.replay()
-    L.LAUNCHES["count"] += gm.launches_per_replay
+    if gm.split:  # host caller: image 1 uploads first and its side runs while image 0 uploads
+        gm.load_and_replay_split(feat_0, feat_1, grid_0, grid_1, K=K)
+    else:
+        gm.load(feat_0, feat_1, grid_0, grid_1, two_streams=on_host, K=K)
+        gm.graph.replay()
+        L.LAUNCHES["count"] += gm.launches_per_replay
     if on_host:
         gm.host_packed.copy_(gm.packed, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()

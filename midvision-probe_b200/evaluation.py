@@ -262,7 +262,7 @@ class GraphedPairMatcher:
     """
 
     def __init__(self, kind, feat_shape, grid_shape, num_corr, K=None, device=None, ratio_test=True, with_outputs=False,
-                 feat_layout="chw", feat_dtype=torch.float32):
+                 feat_layout="chw", feat_dtype=torch.float32, split=False):
         """feat_layout: memory layout of the static feature buffers -- "chw" (the reference's contiguous
         (C, h, w)) or "hwc" (channel-last views, the layout ViT tokens / channels_last CNN outputs already have:
         loading such features is a flat copy and the transpose kernel is skipped)."""
@@ -270,6 +270,10 @@ class GraphedPairMatcher:
             raise ValueError(kind)
         if feat_layout not in ("chw", "hwc"):
             raise ValueError(feat_layout)
+        # split: TWO graphs -- the target image's side (its map, the f16c centre, kernel 1) and everything else -- so that a
+        # host caller's upload of image 0 overlaps the target side's kernels (load_and_replay_split)
+        self.split = bool(split)
+        self.graph_target = None
         self.feat_layout = feat_layout
         self.feat_dtype = feat_dtype  # torch.bfloat16 / float16: 16-bit static buffers, widened on the device
         C_._check_C(feat_shape[0])
@@ -299,6 +303,27 @@ class GraphedPairMatcher:
         self.graph = None
         self.out = None
 
+    def _prepare(self, fm, g, kw):
+        if self.kind == "xyz":
+            return C_.prepare_xyz_side(fm, g, self.dev, sync=False, **kw)
+        Kd, Kinvd = L.ptr(self.Kdev), c_void_p(self.Kdev.data_ptr() + 36)
+        return C_.prepare_depth_side(fm, g, Kd, Kinvd, self.dev, sync=False, **kw)
+
+    def _body_target(self):
+        """graph 1 of the split form: everything that needs only the TARGET image (image 1)."""
+        fm1 = C_._feature_map(self.f1, self.dev)
+        f16 = C_._CFG["dtype"] == "f16"
+        self._mu = C_._center(fm1[0], fm1[0].shape[0]) if f16 else None
+        kw1 = {"role": L.MV_ROLE_TARGET, "center": self._mu} if f16 else {}
+        self._s1 = self._prepare(fm1, self.g1, kw1)
+
+    def _body_query(self):
+        """graph 2 of the split form: the query image's side, kernels 2 and 3, the packed outputs."""
+        fm0 = C_._feature_map(self.f0, self.dev)
+        kw0 = {"role": L.MV_ROLE_QUERY, "dotvec": self._mu} if self._mu is not None else {}
+        s0, s1 = self._prepare(fm0, self.g0, kw0), self._s1
+        return self._match_and_pack(s0, s1)
+
     def _body(self):
         fm0, fm1, kw0, kw1 = C_._pair_maps(self.f0, self.f1, self.dev)
         if self.kind == "xyz":
@@ -308,6 +333,9 @@ class GraphedPairMatcher:
             Kd, Kinvd = L.ptr(self.Kdev), c_void_p(self.Kdev.data_ptr() + 36)
             s0, s1 = _both_sides(lambda: C_.prepare_depth_side(fm0, self.g0, Kd, Kinvd, self.dev, sync=False, **kw0),
                                  lambda: C_.prepare_depth_side(fm1, self.g1, Kd, Kinvd, self.dev, sync=False, **kw1), self.dev)
+        return self._match_and_pack(s0, s1)
+
+    def _match_and_pack(self, s0, s1):
         r = C_._match_sides(s0, s1, s0.n, s1.n, self.num_corr, self.ratio_test, n_dev=s0.n_dev, m_dev=s1.n_dev)
         if self.with_outputs:
             # the helper's return tuple + the live counts in one buffer of column blocks (mv_pack_matches):
@@ -331,9 +359,18 @@ class GraphedPairMatcher:
             self._body()
         cur.wait_stream(side)
         torch.cuda.synchronize(self.dev)
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = self._body()
+        if self.split:
+            pool = torch.cuda.graph_pool_handle()  # the second graph consumes tensors the first one produces
+            self.graph_target = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_target, pool=pool):
+                self._body_target()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, pool=pool):
+                self.out = self._body_query()
+        else:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.out = self._body()
         if self.with_outputs:
             self.host_packed = torch.empty(self.packed.shape, dtype=torch.float32, pin_memory=True)
         return self
@@ -385,10 +422,38 @@ class GraphedPairMatcher:
         self.g0.copy_(grid_0, non_blocking=True)
         cur.wait_stream(side)
 
+    def load_and_replay_split(self, feat_0, feat_1, grid_0, grid_1, K=None):
+        """(split form, host tensors) upload the TARGET image first, replay its graph while the query image uploads, then
+        replay the rest: the target side's ~60 us of kernels disappear behind the second half of the upload.  The copies go
+        through one copy stream in order (image 1, then image 0), so image 1 owns the link until it is complete."""
+        if K is not None and self.kind == "depth":
+            self.set_intrinsics(K)
+        cur = torch.cuda.current_stream(self.dev)
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+            self._ev1, self._ev0 = torch.cuda.Event(), torch.cuda.Event()
+        cp = self._copy_stream
+        cp.wait_stream(cur)  # the static buffers may still be read by the previous replay
+        with torch.cuda.stream(cp):
+            copy_in(self.f1, feat_1, cp)
+            copy_in(self.g1, grid_1, cp)
+            self._ev1.record(cp)
+        cur.wait_event(self._ev1)
+        self.graph_target.replay()
+        with torch.cuda.stream(cp):
+            copy_in(self.f0, feat_0, cp)
+            copy_in(self.g0, grid_0, cp)
+            self._ev0.record(cp)
+        cur.wait_event(self._ev0)
+        self.graph.replay()
+        L.LAUNCHES["count"] += self.launches_per_replay
+
     def run(self, acc=None, Rt=None, K=None):
         """replay the captured pipeline on the staged inputs; optionally score into `acc`."""
         if self.graph is None:
             self.capture()
+        if self.graph_target is not None:
+            self.graph_target.replay()
         self.graph.replay()
         L.LAUNCHES["count"] += self.launches_per_replay
         s0, s1, r = self.out
