@@ -513,7 +513,7 @@ def k1_record(ctx):
         pitch = L.f16c_pitch(C) if f16 else C
         sets = [(torch.empty((n, pitch), dtype=t16, device=dev), torch.empty((n, C), dtype=t16, device=dev)) for _ in range(6)]
         # positions of the (stream, 16-bit rows, residual rows) arguments of the recorded call
-        slots = {"mv_k1_sample_f16c": (-1, 12, 14), "mv_k1_sample_normalize": (-1, 9, 10), "mv_k1_grid_f16c": (-1, 10, 12)}[name]
+        slots = {"mv_k1_sample_f16c": (-1, 13, 15), "mv_k1_sample_normalize": (-1, 9, 10), "mv_k1_grid_f16c": (-1, 10, 12)}[name]
         st = torch.cuda.Stream()
         with torch.cuda.stream(st):
             def launch(i):

@@ -150,10 +150,16 @@ int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, cons
  * mv_k2_sim_top2_ld with C + 8 columns, that pitch and MV_DTYPE_F16 (columns beyond C + 8 are never read).  out_f16_lo (optional, (n, C) halfs): fp16((y - float(out_f16)) * 2^11) with
  * y = row - center, so that y = hi + lo * 2^-11 to 2^-22 relative (consumed by mv_k3_ratio_mutual_f16c).
  * role: MV_ROLE_QUERY uses dotvec (= the target's centre; NULL -> r = 0), MV_ROLE_TARGET uses center.  Both may be
- * given.  row_dot (optional, n floats): r.  Other arguments as mv_k1_sample_normalize. */
+ * given.  pixdot (optional; h*w floats, n for MV_SAMPLE_ROWS): src[p] . dotvec of every source row (mv_rows_dot); when
+ * given, r is the row's own 4- / 16-tap blend of these scalars (times 1/norm) instead of a C-long dot product per row --
+ * the same number up to the order of the fp32 sums -- and dotvec is not read.  row_dot (optional, n floats): r.  Other
+ * arguments as mv_k1_sample_normalize. */
 int mv_k1_sample_f16c(int mode, const float* src, int C, int h, int w, const float* coords, const int32_t* n_dev, int n_max,
-                      int normalize, int role, const float* center, const float* dotvec, uint16_t* out_f16, int pitch,
-                      uint16_t* out_f16_lo, float* out_f32, float* row_dot, int32_t* taps, mv_stream_t stream);
+                      int normalize, int role, const float* center, const float* dotvec, const float* pixdot, uint16_t* out_f16,
+                      int pitch, uint16_t* out_f16_lo, float* out_f32, float* row_dot, int32_t* taps, mv_stream_t stream);
+
+/* out[p] = rows[p] . vec for the n rows of rows (n, C) fp32 (C % 4 == 0): the per-source-pixel dots of the pixdot form. */
+int mv_rows_dot(const float* rows, int C, int n, const float* vec, float* out, mv_stream_t stream);
 
 /* The NAVI-style side as ONE tiled kernel (csrc/k1_grid.cu): bicubic upsampling (A = -0.75, align_corners=False, border
  * clamp) of the (h*w, C) map by the integer factors W / w (4 or 8) and H / h (1..8) onto the live pixels of the (H, W)

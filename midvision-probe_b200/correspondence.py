@@ -151,7 +151,7 @@ def _check_C(C):
 
 
 def _sample(mode, src, C, h, w, coords, n_dev, n_max, normalize, want_bf16, want_f32, taps=None, want_lo=False,
-            role=L.MV_ROLE_QUERY, center=None, dotvec=None):
+            role=L.MV_ROLE_QUERY, center=None, dotvec=None, pixdot=None):
     """kernel 1.  src: (h*w, C) channel-last (or (n, C) rows for MV_SAMPLE_ROWS).
     Returns (16-bit rows, fp32 rows, 16-bit residual rows); the ones not asked for are None.
     The 16-bit rows are bf16 (n, C) for the "bf16" operand type and fp16 "f16c" rows (n, f16c_pitch(C)) for "f16":
@@ -164,7 +164,8 @@ def _sample(mode, src, C, h, w, coords, n_dev, n_max, normalize, want_bf16, want
     o32 = _empty((max(n_max, 1), C), torch.float32, dev) if want_f32 else None
     if n_max > 0 and f16:
         L.call("mv_k1_sample_f16c", mode, L.ptr(src), C, h, w, L.ptr(coords), L.ptr(n_dev), n_max, int(normalize), role,
-               L.ptr(center), L.ptr(dotvec), L.ptr(o16), o16.shape[1], L.ptr(olo), L.ptr(o32), None, L.ptr(taps), _stream())
+               L.ptr(center), L.ptr(dotvec), L.ptr(pixdot), L.ptr(o16), o16.shape[1], L.ptr(olo), L.ptr(o32), None, L.ptr(taps),
+               _stream())
     elif n_max > 0:
         L.call("mv_k1_sample_normalize", mode, L.ptr(src), C, h, w, L.ptr(coords), L.ptr(n_dev), n_max, int(normalize),
                L.ptr(o16), L.ptr(olo), L.ptr(o32), L.ptr(taps), _stream())
@@ -592,7 +593,14 @@ def _pair_maps(feat_0, feat_1, dev):
     if _CFG["dtype"] != "f16":
         return fm0, fm1, {}, {}
     mu = _center(fm1[0], fm1[0].shape[0])
-    return fm0, fm1, {"role": L.MV_ROLE_QUERY, "dotvec": mu}, {"role": L.MV_ROLE_TARGET, "center": mu}
+    return fm0, fm1, {"role": L.MV_ROLE_QUERY, "dotvec": mu, "pixdot": _rows_dot(fm0[0], mu)}, {"role": L.MV_ROLE_TARGET, "center": mu}
+
+
+def _rows_dot(rows, vec):
+    """(n,) fp32: rows[p] . vec (mv_rows_dot) -- the per-source-pixel dots kernel 1 blends into a query row's r."""
+    out = _empty((rows.shape[0],), torch.float32, rows.device)
+    L.call("mv_rows_dot", L.ptr(rows), rows.shape[1], rows.shape[0], L.ptr(vec), L.ptr(out), _stream())
+    return out
 
 
 def _stage_depth(depth_dev, Kinv):
@@ -608,7 +616,8 @@ def _stage_depth(depth_dev, Kinv):
     return xyz_all, valid_idx, n_dev
 
 
-def _finish_depth(f, d, K, staged, n, synced, want_taps=False, rows=None, role=L.MV_ROLE_QUERY, center=None, dotvec=None):
+def _finish_depth(f, d, K, staged, n, synced, want_taps=False, rows=None, role=L.MV_ROLE_QUERY, center=None, dotvec=None,
+                  pixdot=None):
     """projection to feature-map coordinates + kernel 1 for the n (live or upper-bound) points of one image.
     f: the (C, h, w) feature map in either layout (see _feature_map), or the tuple _feature_map returned for it."""
     xyz_all, valid_idx, n_dev = staged
@@ -627,7 +636,7 @@ def _finish_depth(f, d, K, staged, n, synced, want_taps=False, rows=None, role=L
     s.uv = None
     w16, w32, wlo = _row_format(rows)
     s.rows16, s.rows32, s.rows_lo = _sample(L.MV_SAMPLE_BILINEAR_ZEROS, src, C, h, w, coords, nd, n, True, w16, w32,
-                                            s.taps, wlo, role=role, center=center, dotvec=dotvec)
+                                            s.taps, wlo, role=role, center=center, dotvec=dotvec, pixdot=pixdot)
     s.center = center
     return s
 
@@ -654,7 +663,8 @@ def _stage_xyz(g):
     return valid_idx, n_dev
 
 
-def _finish_xyz(f, g, staged, n, synced, want_taps=False, rows=None, role=L.MV_ROLE_QUERY, center=None, dotvec=None):
+def _finish_xyz(f, g, staged, n, synced, want_taps=False, rows=None, role=L.MV_ROLE_QUERY, center=None, dotvec=None,
+                pixdot=None):
     valid_idx, n_dev = staged
     dev = g.device
     src, C, h, w = f if isinstance(f, tuple) else _feature_map(f, dev)
@@ -683,7 +693,7 @@ def _finish_xyz(f, g, staged, n, synced, want_taps=False, rows=None, role=L.MV_R
                s.rows16.shape[1], L.ptr(s.rows_lo), _stream())
         return s
     s.rows16, s.rows32, s.rows_lo = _sample(L.MV_SAMPLE_BICUBIC_CLAMP, src, C, h, w, coords, nd, n, True, w16, w32,
-                                            s.taps, wlo, role=role, center=center, dotvec=dotvec)
+                                            s.taps, wlo, role=role, center=center, dotvec=dotvec, pixdot=pixdot)
     return s
 
 
@@ -776,8 +786,11 @@ def _graphed_helper(kind, feat_0, feat_1, grid_0, grid_1, num_corr, ratio_test, 
     layout = "hwc" if (_is_channel_last(feat_0) and _is_channel_last(feat_1)) else "chw"
     fdt = feat_0.dtype if (feat_0.dtype == feat_1.dtype and feat_0.dtype in _FEAT_DTYPES) else torch.float32
     on_host = feat_0.device.type == "cpu"
+    # two graphs (upload of image 0 behind image 1's kernels) pay off for pinned sources (1369 -> 1536 pairs/s, NAVI-shaped);
+    # pageable ones are staged by host threads, which the interleaved replay only delays (578 -> 458)
+    split = on_host and bool(_CFG["helper_split"]) and feat_0.is_pinned() and feat_1.is_pinned()
     # the intrinsics are NOT part of the key: they live in device memory and are refreshed per call (gm.load)
-    key = (on_host, kind, tuple(feat_0.shape), tuple(grid_0.shape), int(num_corr), bool(ratio_test), _CFG["dtype"], _CFG["cluster"], _CFG["rows"], _CFG["k1_grid"], fdt,
+    key = (on_host, split, kind, tuple(feat_0.shape), tuple(grid_0.shape), int(num_corr), bool(ratio_test), _CFG["dtype"], _CFG["cluster"], _CFG["rows"], _CFG["k1_grid"], fdt,
            dev.index, layout)
     gm = _HELPER_GRAPHS.get(key)
     if gm is None:
@@ -788,7 +801,7 @@ def _graphed_helper(kind, feat_0, feat_1, grid_0, grid_1, num_corr, ratio_test, 
             _HELPER_GRAPHS.pop(next(iter(_HELPER_GRAPHS)))
         gm = ev.GraphedPairMatcher(kind, tuple(feat_0.shape), tuple(grid_0.shape), num_corr, K=K, device=dev,
                                    ratio_test=ratio_test, with_outputs=True, feat_layout=layout, feat_dtype=fdt,
-                                   split=on_host and bool(_CFG["helper_split"])).capture()
+                                   split=split).capture()
         _HELPER_GRAPHS[key] = gm
     if gm.split:  # host caller: image 1 uploads first and its side runs while image 0 uploads
         gm.load_and_replay_split(feat_0, feat_1, grid_0, grid_1, K=K)

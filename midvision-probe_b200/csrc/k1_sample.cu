@@ -294,6 +294,8 @@ struct K1Params {
   int role;             // MV_ROLE_QUERY: aug = 3 fp16 pieces of r = row . dotvec;  MV_ROLE_TARGET: aug = (1, 1, 2^-11)
   const float* center;  // (C) or NULL: subtracted from the normalised row before the 16-bit split
   const float* dotvec;  // (C) or NULL
+  const float* pixdot;  // (h*w; n for MV_SAMPLE_ROWS) or NULL: src[p] . dotvec per source row, precomputed (mv_rows_dot).  The
+                        // row's dot product is then the same blend of 4 / 16 of these scalars instead of C multiply-adds
   float* row_dot;       // (n) or NULL: r in fp32
 };
 
@@ -346,6 +348,7 @@ struct K1WShared {
   int g_start[K1W_PMAX], g_cnt[K1W_PMAX];
   float part[2][4][4][4];  // [parity][team][point of the group][warp of the team]: partial sums of squares
   float partd[2][4][4][4]; // the same for row . dotvec
+  float rd[K1W_PMAX];      // per point: (unnormalised row) . dotvec from the pixel dots (pixdot form)
   float cy[4];
   int npts, ncols, xbase, y0, ngroups;
 };
@@ -384,7 +387,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
 
   const bool f16c = p.fmt16 != 0;
   const size_t pitch16 = f16c ? (size_t)p.pitch16 : (size_t)C;
-  const bool hasdot = p.dotvec != nullptr;
+  const bool haspd = p.pixdot != nullptr;                    // the dot product comes from per-pixel dots: nothing in the hot loop
+  const bool hasdot = p.dotvec != nullptr && !haspd;
   auto put = [&](int pt, int c, float4 o, float inv) {
     o.x *= inv;  // inv == 1 when not normalising: exact
     o.y *= inv;
@@ -523,7 +527,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
         inverse_norms(ss, inv, dd);
         for (int c = lane * 4; c < C; c += 128) put(pt, c, ld4(row + c), inv[0]);
       }
-      if (lane == 0 && wsub == 0) put_aug(pt, dd[0]);
+      if (lane == 0 && wsub == 0) put_aug(pt, haspd ? __ldg(p.pixdot + pt) * inv[0] : dd[0]);
     }
     return;
   }
@@ -589,6 +593,32 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
           sh.off[lane][2] = (ncols + dx) * C;
           sh.off[lane][3] = (ncols + dx + 1) * C;
         }
+      }
+      if (haspd && lane < npts) {
+        // (unnormalised row) . dotvec = the row's own blend applied to the per-pixel dots
+        float r = 0.f;
+        if (CUBIC) {
+          float cx[4], cyl[4];
+          cubic_coeffs(xy.x - fx, cx);
+          cubic_coeffs(xy.y - fy, cyl);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int xx = min(max(x0 - 1 + i, 0), p.w - 1);
+            float yb = 0.f;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) yb = fmaf(cyl[j], __ldg(p.pixdot + min(max(y0 - 1 + j, 0), p.h - 1) * p.w + xx), yb);
+            r = fmaf(cx[i], yb, r);
+          }
+        } else {
+          const float ww = xy.x - fx, we = 1.f - ww, wn = xy.y - fy, ws = 1.f - wn;
+          const float wt4[4] = {ws * we, ws * ww, wn * we, wn * ww};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int xx = x0 + (k & 1), yy = y0 + (k >> 1);
+            if (xx >= 0 && xx < p.w && yy >= 0 && yy < p.h) r = fmaf(wt4[k], __ldg(p.pixdot + yy * p.w + xx), r);
+          }
+        }
+        sh.rd[lane] = r;
       }
       if (lane == 0) {
         sh.npts = npts;
@@ -685,7 +715,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
           if (j < cnt) {
 #pragma unroll
             for (int it = 0; it < NITW; ++it) put(cur + t0 + j, cbase + (it * 32 + lane) * 4, acc[j][it], inv[j]);
-            if (lane == 0 && wsub == 0) put_aug(cur + t0 + j, dd[j]);
+            if (lane == 0 && wsub == 0) put_aug(cur + t0 + j, haspd ? sh.rd[t0 + j] * inv[j] : dd[j]);
           }
         }
       } else {  // W == G == 1
@@ -698,7 +728,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
         inverse_norms(ss, inv, dd);
         for (int c = lane * 4; c < C; c += 128)
           put(cur + t0, c, blend(0, lds4(q0 + c), lds4(q1 + c), lds4(q2 + c), lds4(q3 + c)), inv[0]);
-        if (lane == 0) put_aug(cur + t0, dd[0]);
+        if (lane == 0) put_aug(cur + t0, haspd ? sh.rd[t0] * inv[0] : dd[0]);
       }
     }
     __syncthreads();  // the window and the per-point scalars are rewritten by the next sub-run
@@ -722,6 +752,23 @@ __global__ void center_invnorm_kernel(const float* __restrict__ rows, int C, int
   for (int c = lane * 4; c < C; c += 128) ss = dot4(ld4(r + c), ss);
   ss = warp_sum(ss);
   if (lane == 0) inv[q] = 1.f / fmaxf(sqrtf(ss), K1_NORM_EPS);
+}
+
+// out[p] = rows[p] . vec (one warp per row): the per-pixel dots of the pixdot form
+__global__ void rows_dot_kernel(const float* __restrict__ rows, int C, int n, const float* __restrict__ vec, float* __restrict__ out) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (q >= n) return;
+  const float* r = rows + (size_t)q * C;
+  float acc = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = ld4(r + c), d = ld4(vec + c);
+    acc = fmaf(v.x, d.x, acc);
+    acc = fmaf(v.y, d.y, acc);
+    acc = fmaf(v.z, d.z, acc);
+    acc = fmaf(v.w, d.w, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[q] = acc;
 }
 
 // block = 32 channel quads x 16 row groups: group g sums rows q = g, g + 16, ... (independent loads, 4 in flight), the 16
@@ -962,8 +1009,20 @@ int mv_rows_center(const float* rows, int C, int n_max, const int32_t* n_dev, in
   return MV_OK;
 }
 
+int mv_rows_dot(const float* rows, int C, int n, const float* vec, float* out, mv_stream_t stream) {
+  MV_REQUIRE(rows && vec && out, MV_E_ARG, "mv_rows_dot: null pointer");
+  MV_REQUIRE(C > 0 && C % 4 == 0 && n >= 0, MV_E_ARG, "mv_rows_dot: C %% 4 == 0 and n >= 0 required");
+  MV_REQUIRE(((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(vec)) & 15) == 0, MV_E_ALIGN,
+             "mv_rows_dot: rows and vec must be 16-byte aligned");
+  if (n == 0) return MV_OK;
+  rows_dot_kernel<<<(n + 7) / 8, 256, 0, mv_cuda_stream(stream)>>>(rows, C, n, vec, out);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
 static int k1_entry(const char* who, int mode, const float* src, int C, int h, int w, const float* coords, const int32_t* n_dev,
-                    int n_max, int normalize, int fmt16, int pitch16, int role, const float* center, const float* dotvec, uint16_t* out16,
+                    int n_max, int normalize, int fmt16, int pitch16, int role, const float* center, const float* dotvec,
+                    const float* pixdot, uint16_t* out16,
                     uint16_t* out16_lo, float* out_f32, float* row_dot, int32_t* taps, mv_stream_t stream) {
   MV_REQUIRE(src && (out16 || out_f32), MV_E_ARG, "%s: null src or no output", who);
   MV_REQUIRE(mode == MV_SAMPLE_BILINEAR_ZEROS || mode == MV_SAMPLE_BICUBIC_CLAMP || mode == MV_SAMPLE_ROWS,
@@ -1002,6 +1061,7 @@ static int k1_entry(const char* who, int mode, const float* src, int C, int h, i
   p.role = role;
   p.center = center;
   p.dotvec = dotvec;
+  p.pixdot = pixdot;
   p.row_dot = row_dot;
 
   cudaStream_t st = mv_cuda_stream(stream);
@@ -1013,15 +1073,15 @@ static int k1_entry(const char* who, int mode, const float* src, int C, int h, i
 int mv_k1_sample_normalize(int mode, const float* src, int C, int h, int w, const float* coords,
                            const int32_t* n_dev, int n_max, int normalize, uint16_t* out_bf16, uint16_t* out_bf16_lo, float* out_f32,
                            int32_t* taps, mv_stream_t stream) {
-  return k1_entry("mv_k1_sample_normalize", mode, src, C, h, w, coords, n_dev, n_max, normalize, 0, C, MV_ROLE_QUERY, nullptr, nullptr,
+  return k1_entry("mv_k1_sample_normalize", mode, src, C, h, w, coords, n_dev, n_max, normalize, 0, C, MV_ROLE_QUERY, nullptr, nullptr, nullptr,
                   out_bf16, out_bf16_lo, out_f32, nullptr, taps, stream);
 }
 
 int mv_k1_sample_f16c(int mode, const float* src, int C, int h, int w, const float* coords, const int32_t* n_dev, int n_max,
-                      int normalize, int role, const float* center, const float* dotvec, uint16_t* out_f16, int pitch, uint16_t* out_f16_lo,
-                      float* out_f32, float* row_dot, int32_t* taps, mv_stream_t stream) {
+                      int normalize, int role, const float* center, const float* dotvec, const float* pixdot, uint16_t* out_f16, int pitch,
+                      uint16_t* out_f16_lo, float* out_f32, float* row_dot, int32_t* taps, mv_stream_t stream) {
   MV_REQUIRE(out_f16, MV_E_ARG, "mv_k1_sample_f16c: out_f16 is required");
-  return k1_entry("mv_k1_sample_f16c", mode, src, C, h, w, coords, n_dev, n_max, normalize, 1, pitch, role, center, dotvec, out_f16,
+  return k1_entry("mv_k1_sample_f16c", mode, src, C, h, w, coords, n_dev, n_max, normalize, 1, pitch, role, center, dotvec, pixdot, out_f16,
                   out_f16_lo, out_f32, row_dot, taps, stream);
 }
 

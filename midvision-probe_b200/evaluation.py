@@ -320,7 +320,7 @@ class GraphedPairMatcher:
     def _body_query(self):
         """graph 2 of the split form: the query image's side, kernels 2 and 3, the packed outputs."""
         fm0 = C_._feature_map(self.f0, self.dev)
-        kw0 = {"role": L.MV_ROLE_QUERY, "dotvec": self._mu} if self._mu is not None else {}
+        kw0 = {"role": L.MV_ROLE_QUERY, "dotvec": self._mu, "pixdot": C_._rows_dot(fm0[0], self._mu)} if self._mu is not None else {}
         s0, s1 = self._prepare(fm0, self.g0, kw0), self._s1
         return self._match_and_pack(s0, s1)
 
@@ -467,10 +467,10 @@ class GraphedPairMatcher:
 
     @property
     def launches_per_replay(self):
-        # per image: (backproject) + compact + coords + chw_to_hwc + kernel 1; per pair: (centre: 2) + kernel 2 (2) + ratio + top-k
+        # per image: (backproject) + compact + coords + chw_to_hwc + kernel 1; per pair: (centre: 2, pixel dots: 1) + kernel 2 (2) + ratio + top-k
         zero_copy = self.feat_layout == "hwc" and self.feat_dtype == torch.float32
         per_side = (5 if self.kind == "depth" else 4) - (1 if zero_copy else 0)
-        return 2 * per_side + 4 + (2 if C_._CFG["dtype"] == "f16" else 0) + (1 if self.with_outputs else 0)
+        return 2 * per_side + 4 + (3 if C_._CFG["dtype"] == "f16" else 0) + (1 if self.with_outputs else 0)
 
 
 class PairPipeline:

@@ -30,7 +30,7 @@ def f16c_rows(mv, X, role, center=None, dotvec=None, normalize=True, lo=True):
     lo_t = torch.empty((n, C), dtype=torch.float16, device="cuda") if lo else None
     rdot = torch.empty(n, device="cuda")
     L.call("mv_k1_sample_f16c", L.MV_SAMPLE_ROWS, L.ptr(Xd), C, 0, 0, None, None, n, int(normalize), role, L.ptr(center),
-           L.ptr(dotvec), L.ptr(hi), hi.shape[1], L.ptr(lo_t), None, L.ptr(rdot), None, C_._stream())
+           L.ptr(dotvec), None, L.ptr(hi), hi.shape[1], L.ptr(lo_t), None, L.ptr(rdot), None, C_._stream())
     torch.cuda.synchronize()
     return hi, lo_t, rdot
 
@@ -123,3 +123,29 @@ def test_f16c_beats_plain_16bit_products_on_collinear_rows(mv):
     # documents the failure mode the default avoids: bf16 proposes a wrong pair of candidates on some of these rows even
     # after kernel 3's fp32 re-rank of the two (measured 0.983; 0.87 for its raw arg-max in a CPU simulation of the roundings)
     assert agree["bf16"] < 0.995
+
+
+@pytest.mark.parametrize("kind", ["navi", "scannet"])
+def test_pixel_dot_form_of_the_query_rows(mv, syn, kind):
+    """the query rows' r = row . mu from the per-source-pixel dots (the row's own 4- / 16-tap blend of src[p] . mu, times
+    1 / norm: nothing in kernel 1's hot loop) against the C-long dot product per row: the same number up to fp32 summation
+    order, everything else bit-identical."""
+    C_, L = mv.correspondence, mv._lib
+    dev = torch.device("cuda")
+    if kind == "navi":
+        p = syn.navi_pair(3, coherent=False, C=768, h=14, w=14, H=56, W=56, radius=22.0)
+        prep = lambda fm, kw: C_.prepare_xyz_side(fm, p["xyz_grid_0"], dev, **kw)
+    else:
+        p = syn.scannet_pair(3, coherent=False, C=2048, h=15, w=20, H=60, W=80)
+        Kh, Kinv = C_._host_mat(p["K"]), C_._host_mat(p["K"].inverse())
+        prep = lambda fm, kw: C_.prepare_depth_side(fm, p["depth_0"], Kh, Kinv, dev, **kw)
+    fm0, fm1, kw0, _ = C_._pair_maps(p["feat_0"], p["feat_1"], dev)
+    assert kw0["pixdot"] is not None
+    a = prep(fm0, kw0)                                                  # pixel-dot form (the default)
+    b = prep(fm0, {"role": kw0["role"], "dotvec": kw0["dotvec"]})       # dot product inside the row loop
+    n, C = a.n, fm0[1]
+    assert torch.equal(a.rows16[:n, :C], b.rows16[:n, :C]) and torch.equal(a.rows_lo[:n], b.rows_lo[:n])
+    ra = a.rows16[:n, C:C + 3].float()
+    rb = b.rows16[:n, C:C + 3].float()
+    ra, rb = ra[:, 0] + ra[:, 1] + ra[:, 2] / 2048.0, rb[:, 0] + rb[:, 1] + rb[:, 2] / 2048.0
+    assert (ra - rb).abs().max() <= 2e-6 and ra.abs().max() > 0.01
