@@ -18,6 +18,8 @@
 
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 
@@ -806,7 +808,7 @@ template <int MODE, int NITW, int W, int G, int OUTS, int THREADS, int MINB>
 int launch_k1_inst(const K1Params& p, cudaStream_t st) {
   const int C = p.C;
   // window bytes per CTA: MINB CTAs per SM share 227 KB (minus ~3 KB static and 1 KB reserved each)
-  const int budget = (MINB >= 3 ? 72 : 108) << 10;
+  const int budget = (MINB >= 3 ? 72 : (MINB == 2 ? 108 : 216)) << 10;
   int nslots = budget / (C * 4);
   if (nslots < 4) nslots = 4;    // C <= 8192: 4 slots = 128 KB, one CTA per SM
   if (nslots > 40) nslots = 40;  // more than any 32-point sub-run can use
@@ -852,6 +854,11 @@ int launch_k1(const K1Params& p, cudaStream_t st) {
   // 39.6 us with teams of 4 warps x 4 points vs 41.4 us point-at-a-time; C = 3072 (4x bicubic, ~12-17 points per
   // CTA) 31.5 us with teams -- the 72 KB window of a 3-CTA/SM layout splits the short runs -- vs 27.4 us with one
   // warp per point and the whole row (96 registers) in a 108 KB window, so that shape keeps the latter.
+  // C = 3072, one CTA per SM with a 216 KB window (MVMATCH_K1_WIDE=1): longer runs per window -> 30 % less L2 traffic
+  static const bool wide = getenv("MVMATCH_K1_WIDE") && atoi(getenv("MVMATCH_K1_WIDE")) != 0;
+  if (wide) {
+    K1W_CASE(3072, 24, 1, 1, 384, 1)
+  }
   K1W_CASE(768, 6, 1, 4, 128, 3)    // ViT-B
   K1W_CASE(1024, 4, 2, 4, 256, 2)   // ViT-L
   K1W_CASE(2048, 4, 4, 4, 256, 2)   // ResNet-50 layer4

@@ -17,6 +17,8 @@
 //   evaluate_navi_correspondence.py:186-212, render_scannet_correspondence.py:211-217, :253-264  errors, recall
 //   evaluate_spair_correspondence.py:83-98, :121  SPair errors and PCK
 #include <cuda_fp16.h>
+
+#include <cstdlib>
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -84,73 +86,99 @@ __device__ __forceinline__ void split8(const __nv_bfloat16* hi, const __nv_bfloa
   }
 }
 
-// 128 threads = 4 queries per CTA: small CTAs keep the tail of the single wave short.  ncu (ratio_probe.py, NAVI
-// size): 123.5 MB of DRAM reads in 25.7 us (fp32 rows) / 32.5 us (split rows: twice the instructions for the
-// same bytes); both are latency-bound (long-scoreboard stalls), in the pipeline the two formats are within 2 %.
+// A TEAM of W warps per query (W = 1, 2 or 4 by C): each warp owns a contiguous 1/W of the channels, so the serial chain
+// of a row is C / (8 * 32 * W) chunk loads deep instead of C / 256 -- the kernel is bound by the DRAM latency of the row
+// reads (ncu round 2: 74 % of the samples on long-scoreboard stalls, 81 MB read in 27.6 us = 2.9 TB/s with one warp per
+// row at C = 3072).  The five partial sums meet in shared memory and are added in a fixed order.
 constexpr int RATIO_THREADS = 128;
-template <typename ROWS>
+template <typename ROWS, int W>
 __global__ void __launch_bounds__(RATIO_THREADS, 6) k3_ratio_mutual_kernel(ROWS rows, int C, const int32_t* __restrict__ n_dev, int n_max,
                                                               int32_t* __restrict__ row_idx,
                                                               const unsigned long long* __restrict__ col_best,
                                                               int ratio_test, float* __restrict__ dists,
                                                               float* __restrict__ weight, uint8_t* __restrict__ mutual) {
+  constexpr int TEAMS = RATIO_THREADS / 32 / W;
+  __shared__ float part[TEAMS][W][5];
   const int n = n_dev ? min(*n_dev, n_max) : n_max;
-  const int lane = threadIdx.x & 31;
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= n) return;
-  int j0 = row_idx[2 * (size_t)i], j1 = row_idx[2 * (size_t)i + 1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int team = wid / W, wsub = wid % W;
+  const int i = blockIdx.x * TEAMS + team;
+  const bool live = i < n;
+  int j0 = -1, j1 = -1;
   float xx = 0.f, aa = 0.f, bb = 0.f, xa = 0.f, xb = 0.f;
-  if constexpr (sizeof(ROWS) == sizeof(RowsF32)) {
-    const float4* x = reinterpret_cast<const float4*>(rows.A + (size_t)i * C);
-    const float4* y0 = reinterpret_cast<const float4*>(rows.B + (size_t)max(j0, 0) * C);
-    const float4* y1 = reinterpret_cast<const float4*>(rows.B + (size_t)max(j1, 0) * C);
-    for (int c = lane; c < (C >> 2); c += 32) {
-      const float4 v = __ldg(x + c), a = __ldg(y0 + c), b = __ldg(y1 + c);
-      xx = fmaf(v.x, v.x, xx); xx = fmaf(v.y, v.y, xx); xx = fmaf(v.z, v.z, xx); xx = fmaf(v.w, v.w, xx);
-      aa = fmaf(a.x, a.x, aa); aa = fmaf(a.y, a.y, aa); aa = fmaf(a.z, a.z, aa); aa = fmaf(a.w, a.w, aa);
-      bb = fmaf(b.x, b.x, bb); bb = fmaf(b.y, b.y, bb); bb = fmaf(b.z, b.z, bb); bb = fmaf(b.w, b.w, bb);
-      xa = fmaf(v.x, a.x, xa); xa = fmaf(v.y, a.y, xa); xa = fmaf(v.z, a.z, xa); xa = fmaf(v.w, a.w, xa);
-      xb = fmaf(v.x, b.x, xb); xb = fmaf(v.y, b.y, xb); xb = fmaf(v.z, b.z, xb); xb = fmaf(v.w, b.w, xb);
-    }
-  } else if constexpr (sizeof(ROWS) == sizeof(RowsF16c)) {
-    const size_t P = (size_t)rows.pitch;
-    const size_t ox = (size_t)i * C, o0 = (size_t)max(j0, 0) * C, o1 = (size_t)max(j1, 0) * C;
-    const __half* xh = rows.A_hi + (size_t)i * P;
-    const __half* ah = rows.B_hi + (size_t)max(j0, 0) * P;
-    const __half* bh = rows.B_hi + (size_t)max(j1, 0) * P;
-#pragma unroll 2
-    for (int c8 = lane; c8 < (C >> 3); c8 += 32) {
-      float v[8], a[8], b[8];
-      f16c8(xh, rows.A_lo + ox, c8, v);
-      f16c8(ah, rows.B_lo + o0, c8, a);
-      f16c8(bh, rows.B_lo + o1, c8, b);
-      if (rows.center_B) {
-        const float4 m0 = __ldg(reinterpret_cast<const float4*>(rows.center_B) + 2 * c8);
-        const float4 m1 = __ldg(reinterpret_cast<const float4*>(rows.center_B) + 2 * c8 + 1);
-        const float mu[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          a[k] += mu[k];
-          b[k] += mu[k];
-        }
+  if (live) {
+    j0 = row_idx[2 * (size_t)i];
+    j1 = row_idx[2 * (size_t)i + 1];
+    if constexpr (sizeof(ROWS) == sizeof(RowsF32)) {
+      const float4* x = reinterpret_cast<const float4*>(rows.A + (size_t)i * C);
+      const float4* y0 = reinterpret_cast<const float4*>(rows.B + (size_t)max(j0, 0) * C);
+      const float4* y1 = reinterpret_cast<const float4*>(rows.B + (size_t)max(j1, 0) * C);
+      const int q = ((C >> 2) + W - 1) / W, beg = wsub * q, end = min(beg + q, C >> 2);
+      for (int c = beg + lane; c < end; c += 32) {
+        const float4 v = __ldg(x + c), a = __ldg(y0 + c), b = __ldg(y1 + c);
+        xx = fmaf(v.x, v.x, xx); xx = fmaf(v.y, v.y, xx); xx = fmaf(v.z, v.z, xx); xx = fmaf(v.w, v.w, xx);
+        aa = fmaf(a.x, a.x, aa); aa = fmaf(a.y, a.y, aa); aa = fmaf(a.z, a.z, aa); aa = fmaf(a.w, a.w, aa);
+        bb = fmaf(b.x, b.x, bb); bb = fmaf(b.y, b.y, bb); bb = fmaf(b.z, b.z, bb); bb = fmaf(b.w, b.w, bb);
+        xa = fmaf(v.x, a.x, xa); xa = fmaf(v.y, a.y, xa); xa = fmaf(v.z, a.z, xa); xa = fmaf(v.w, a.w, xa);
+        xb = fmaf(v.x, b.x, xb); xb = fmaf(v.y, b.y, xb); xb = fmaf(v.z, b.z, xb); xb = fmaf(v.w, b.w, xb);
       }
+    } else if constexpr (sizeof(ROWS) == sizeof(RowsF16c)) {
+      const size_t P = (size_t)rows.pitch;
+      const size_t ox = (size_t)i * C, o0 = (size_t)max(j0, 0) * C, o1 = (size_t)max(j1, 0) * C;
+      const __half* xh = rows.A_hi + (size_t)i * P;
+      const __half* ah = rows.B_hi + (size_t)max(j0, 0) * P;
+      const __half* bh = rows.B_hi + (size_t)max(j1, 0) * P;
+      const int q = ((C >> 3) + W - 1) / W, beg = wsub * q, end = min(beg + q, C >> 3);
+#pragma unroll 3
+      for (int c8 = beg + lane; c8 < end; c8 += 32) {
+        float v[8], a[8], b[8];
+        f16c8(xh, rows.A_lo + ox, c8, v);
+        f16c8(ah, rows.B_lo + o0, c8, a);
+        f16c8(bh, rows.B_lo + o1, c8, b);
+        if (rows.center_B) {
+          const float4 m0 = __ldg(reinterpret_cast<const float4*>(rows.center_B) + 2 * c8);
+          const float4 m1 = __ldg(reinterpret_cast<const float4*>(rows.center_B) + 2 * c8 + 1);
+          const float mu[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc5(v[k], a[k], b[k], xx, aa, bb, xa, xb);
-    }
-  } else {
-    const size_t ox = (size_t)i * C, o0 = (size_t)max(j0, 0) * C, o1 = (size_t)max(j1, 0) * C;
+          for (int k = 0; k < 8; ++k) {
+            a[k] += mu[k];
+            b[k] += mu[k];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc5(v[k], a[k], b[k], xx, aa, bb, xa, xb);
+      }
+    } else {
+      const size_t ox = (size_t)i * C, o0 = (size_t)max(j0, 0) * C, o1 = (size_t)max(j1, 0) * C;
+      const int q = ((C >> 3) + W - 1) / W, beg = wsub * q, end = min(beg + q, C >> 3);
 #pragma unroll 2
-    for (int c8 = lane; c8 < (C >> 3); c8 += 32) {
-      float v[8], a[8], b[8];
-      split8(rows.A_hi + ox, rows.A_lo + ox, c8, v);
-      split8(rows.B_hi + o0, rows.B_lo + o0, c8, a);
-      split8(rows.B_hi + o1, rows.B_lo + o1, c8, b);
+      for (int c8 = beg + lane; c8 < end; c8 += 32) {
+        float v[8], a[8], b[8];
+        split8(rows.A_hi + ox, rows.A_lo + ox, c8, v);
+        split8(rows.B_hi + o0, rows.B_lo + o0, c8, a);
+        split8(rows.B_hi + o1, rows.B_lo + o1, c8, b);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc5(v[k], a[k], b[k], xx, aa, bb, xa, xb);
+        for (int k = 0; k < 8; ++k) acc5(v[k], a[k], b[k], xx, aa, bb, xa, xb);
+      }
+    }
+    xx = warp_sum(xx); aa = warp_sum(aa); bb = warp_sum(bb); xa = warp_sum(xa); xb = warp_sum(xb);
+  }
+  if (W > 1) {
+    if (lane == 0) {
+      float* q = part[team][wsub];
+      q[0] = xx; q[1] = aa; q[2] = bb; q[3] = xa; q[4] = xb;
+    }
+    __syncthreads();
+    if (wsub == 0 && lane == 0) {
+      xx = aa = bb = xa = xb = 0.f;
+#pragma unroll
+      for (int w = 0; w < W; ++w) {  // fixed order
+        const float* q = part[team][w];
+        xx += q[0]; aa += q[1]; bb += q[2]; xa += q[3]; xb += q[4];
+      }
     }
   }
-  xx = warp_sum(xx); aa = warp_sum(aa); bb = warp_sum(bb); xa = warp_sum(xa); xb = warp_sum(xb);
-  if (lane != 0) return;
+  if (!live || lane != 0 || wsub != 0) return;
   const float nx = fmaxf(sqrtf(xx), COS_EPS);
   float d0 = j0 >= 0 ? 1.f - xa / (nx * fmaxf(sqrtf(aa), COS_EPS)) : MISSING_DIST;
   float d1 = j1 >= 0 ? 1.f - xb / (nx * fmaxf(sqrtf(bb), COS_EPS)) : MISSING_DIST;
@@ -177,6 +205,19 @@ __global__ void __launch_bounds__(RATIO_THREADS, 6) k3_ratio_mutual_kernel(ROWS 
     }
     mutual[i] = f;
   }
+}
+
+// W warps per query by the row length: deeper rows get more warps (shorter dependent-load chains)
+template <typename ROWS>
+void launch_ratio(const ROWS& rows, int C, const int32_t* n_dev, int n_max, int32_t* row_idx, const unsigned long long* col_best,
+                  int ratio_test, float* dists, float* weight, uint8_t* mutual, cudaStream_t st) {
+  static const int forced = getenv("MVMATCH_RATIO_W") ? atoi(getenv("MVMATCH_RATIO_W")) : 0;
+  const int W = forced ? forced : (C >= 2048 ? 4 : (C >= 1024 ? 2 : 1));
+  const int teams = RATIO_THREADS / 32 / W;
+  const unsigned grid = (unsigned)((n_max + teams - 1) / teams);
+  if (W == 4) k3_ratio_mutual_kernel<ROWS, 4><<<grid, RATIO_THREADS, 0, st>>>(rows, C, n_dev, n_max, row_idx, col_best, ratio_test, dists, weight, mutual);
+  else if (W == 2) k3_ratio_mutual_kernel<ROWS, 2><<<grid, RATIO_THREADS, 0, st>>>(rows, C, n_dev, n_max, row_idx, col_best, ratio_test, dists, weight, mutual);
+  else k3_ratio_mutual_kernel<ROWS, 1><<<grid, RATIO_THREADS, 0, st>>>(rows, C, n_dev, n_max, row_idx, col_best, ratio_test, dists, weight, mutual);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -557,10 +598,8 @@ int mv_k3_ratio_mutual(const float* A32, const float* B32, int C, const int32_t*
              "mv_k3_ratio_mutual: A32 and B32 must be 16-byte aligned");
   MV_REQUIRE(n_max >= 0, MV_E_ARG, "mv_k3_ratio_mutual: negative n_max");
   if (n_max == 0) return MV_OK;
-  const int rows_per_cta = RATIO_THREADS / 32;
   RowsF32 rows{A32, B32};
-  k3_ratio_mutual_kernel<RowsF32><<<(n_max + rows_per_cta - 1) / rows_per_cta, 32 * rows_per_cta, 0, mv_cuda_stream(stream)>>>(
-      rows, C, n_dev, n_max, row_idx, col_best, ratio_test, dists, weight, mutual);
+  launch_ratio(rows, C, n_dev, n_max, row_idx, col_best, ratio_test, dists, weight, mutual, mv_cuda_stream(stream));
   MV_LAUNCH_CHECK();
   return MV_OK;
 }
@@ -574,11 +613,9 @@ int mv_k3_ratio_mutual_split(const uint16_t* A_hi, const uint16_t* A_lo, const u
              "mv_k3_ratio_mutual_split: the row planes must be 16-byte aligned");
   MV_REQUIRE(n_max >= 0, MV_E_ARG, "mv_k3_ratio_mutual_split: negative n_max");
   if (n_max == 0) return MV_OK;
-  const int rows_per_cta = RATIO_THREADS / 32;
   RowsSplit rows{reinterpret_cast<const __nv_bfloat16*>(A_hi), reinterpret_cast<const __nv_bfloat16*>(A_lo),
                  reinterpret_cast<const __nv_bfloat16*>(B_hi), reinterpret_cast<const __nv_bfloat16*>(B_lo)};
-  k3_ratio_mutual_kernel<RowsSplit><<<(n_max + rows_per_cta - 1) / rows_per_cta, 32 * rows_per_cta, 0, mv_cuda_stream(stream)>>>(
-      rows, C, n_dev, n_max, row_idx, col_best, ratio_test, dists, weight, mutual);
+  launch_ratio(rows, C, n_dev, n_max, row_idx, col_best, ratio_test, dists, weight, mutual, mv_cuda_stream(stream));
   MV_LAUNCH_CHECK();
   return MV_OK;
 }
@@ -593,11 +630,9 @@ int mv_k3_ratio_mutual_f16c(const uint16_t* A_hi, const uint16_t* A_lo, const ui
              "mv_k3_ratio_mutual_f16c: the row planes and the centre must be 16-byte aligned");
   MV_REQUIRE(n_max >= 0 && pitch >= C + 8 && pitch % 8 == 0, MV_E_ARG, "mv_k3_ratio_mutual_f16c: negative n_max or bad pitch %d", pitch);
   if (n_max == 0) return MV_OK;
-  const int rows_per_cta = RATIO_THREADS / 32;
   RowsF16c rows{reinterpret_cast<const __half*>(A_hi), reinterpret_cast<const __half*>(A_lo), reinterpret_cast<const __half*>(B_hi),
                 reinterpret_cast<const __half*>(B_lo), center_B, pitch};
-  k3_ratio_mutual_kernel<RowsF16c><<<(n_max + rows_per_cta - 1) / rows_per_cta, 32 * rows_per_cta, 0, mv_cuda_stream(stream)>>>(
-      rows, C, n_dev, n_max, row_idx, col_best, ratio_test, dists, weight, mutual);
+  launch_ratio(rows, C, n_dev, n_max, row_idx, col_best, ratio_test, dists, weight, mutual, mv_cuda_stream(stream));
   MV_LAUNCH_CHECK();
   return MV_OK;
 }
