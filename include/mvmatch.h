@@ -158,6 +158,14 @@ int mv_k1_sample_f16c(int mode, const float* src, int C, int h, int w, const flo
                       int normalize, int role, const float* center, const float* dotvec, const float* pixdot, uint16_t* out_f16,
                       int pitch, uint16_t* out_f16_lo, float* out_f32, float* row_dot, int32_t* taps, mv_stream_t stream);
 
+/* The same centring for the tf32 operand type ("tf32c" rows): out_op (n, pitch) fp32 = [tf32_round(row - center) (C) | 8
+ * augmentation columns: three tf32-exact pieces of r (query) or (1, 1, 1) (target)], rounded to nearest tf32 here so
+ * that the tensor core's truncation of fp32 operands is exact; pitch >= C + 8 (a multiple of 32 keeps the TMA rows
+ * 128-byte aligned); kernel 2 takes C + 8 columns with MV_DTYPE_TF32.  out_f32 (n, C): the exact fp32 rows kernel 3 reads. */
+int mv_k1_sample_tf32c(int mode, const float* src, int C, int h, int w, const float* coords, const int32_t* n_dev, int n_max,
+                       int normalize, int role, const float* center, const float* dotvec, const float* pixdot, float* out_op, int pitch,
+                       float* out_f32, int32_t* taps, mv_stream_t stream);
+
 /* out[p] = rows[p] . vec for the n rows of rows (n, C) fp32 (C % 4 == 0): the per-source-pixel dots of the pixdot form. */
 int mv_rows_dot(const float* rows, int C, int n, const float* vec, float* out, mv_stream_t stream);
 

@@ -30,6 +30,7 @@ PROTOTYPES = {
     "mv_k1_sample_normalize": (c_int, [c_int, P, c_int, c_int, c_int, P, P, c_int, c_int, P, P, P, P, P]),
     "mv_k1_sample_f16c": (c_int, [c_int, P, c_int, c_int, c_int, P, P, c_int, c_int, c_int, P, P, P, P, c_int, P, P, P, P, P]),
     "mv_rows_dot": (c_int, [P, c_int, c_int, P, P, P]),
+    "mv_k1_sample_tf32c": (c_int, [c_int, P, c_int, c_int, c_int, P, P, c_int, c_int, c_int, P, P, P, P, c_int, P, P, P]),
     "mv_rows_center": (c_int, [P, c_int, c_int, P, c_int, P, P, P]),
     "mv_k1_grid_supported": (c_int, [c_int, c_int, c_int, c_int, c_int]),
     "mv_rank_of_valid": (c_int, [P, P, c_int, P, c_int, P]),
@@ -71,7 +72,7 @@ _lib = None
 # kernels launched per entry point (for bench.py's gpu_launches claim); memsets are not counted
 KERNELS_PER_CALL = {
     "mv_chw_to_hwc": 1, "mv_feat_to_hwc_f32": 1, "mv_compact_valid": 1, "mv_geom_backproject": 1, "mv_geom_project_coords": 1,
-    "mv_geom_grid_coords": 1, "mv_geom_keypoint_coords": 1, "mv_k1_sample_normalize": 1, "mv_k1_sample_f16c": 1, "mv_rows_center": 2, "mv_rows_dot": 1, "mv_rank_of_valid": 1, "mv_k1_grid_f16c": 1, "mv_k2_sim_top2": 2, "mv_k2_sim_top2_ld": 2, "mv_k2_affinity": 2, "mv_affinity_threshold": 1, "mv_cosine_2afc": 1,
+    "mv_geom_grid_coords": 1, "mv_geom_keypoint_coords": 1, "mv_k1_sample_normalize": 1, "mv_k1_sample_f16c": 1, "mv_k1_sample_tf32c": 1, "mv_rows_center": 2, "mv_rows_dot": 1, "mv_rank_of_valid": 1, "mv_k1_grid_f16c": 1, "mv_k2_sim_top2": 2, "mv_k2_sim_top2_ld": 2, "mv_k2_affinity": 2, "mv_affinity_threshold": 1, "mv_cosine_2afc": 1,
     "mv_k2_unpack_col": 1, "mv_k3_ratio_mutual": 1, "mv_k3_ratio_mutual_split": 1, "mv_k3_ratio_mutual_f16c": 1, "mv_k3_topk_matches": 1, "mv_k3_score": 1, "mv_gather_rows": 1,
     "mv_pack_matches": 1, "mv_argmax_rows": 1, "mv_k3_spair_errors": 1, "mv_spair_match_batch": 1,
 }
@@ -105,6 +106,11 @@ def load(build_if_missing=True):
 def f16c_pitch(C):
     """row pitch (elements) of f16c rows of C channels: C + 8 augmentation columns rounded up to a 128-byte multiple."""
     return (C + 8 + 63) // 64 * 64
+
+
+def tf32c_pitch(C):
+    """row pitch (elements) of tf32c operand rows: C + 8 augmentation columns rounded up to a 128-byte multiple."""
+    return (C + 8 + 31) // 32 * 32
 
 
 def call(name, *args):

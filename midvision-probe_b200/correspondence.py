@@ -157,6 +157,15 @@ def _sample(mode, src, C, h, w, coords, n_dev, n_max, normalize, want_bf16, want
     The 16-bit rows are bf16 (n, C) for the "bf16" operand type and fp16 "f16c" rows (n, f16c_pitch(C)) for "f16":
     role / center / dotvec are the f16c parameters of mv_k1_sample_f16c."""
     dev = src.device
+    if _CFG["dtype"] == "tf32" and want_f32 and (center is not None or dotvec is not None or pixdot is not None):
+        # tf32c: exact fp32 rows for kernel 3 + a centred, tf32-rounded operand plane with the augmentation columns for
+        # kernel 2 (returned in the operand-rows slot)
+        o32 = _empty((max(n_max, 1), C), torch.float32, dev)
+        oop = _empty((max(n_max, 1), L.tf32c_pitch(C)), torch.float32, dev)
+        if n_max > 0:
+            L.call("mv_k1_sample_tf32c", mode, L.ptr(src), C, h, w, L.ptr(coords), L.ptr(n_dev), n_max, int(normalize), role,
+                   L.ptr(center), L.ptr(dotvec), L.ptr(pixdot), L.ptr(oop), oop.shape[1], L.ptr(o32), L.ptr(taps), _stream())
+        return oop, o32, None
     f16 = _CFG["dtype"] == "f16" and (want_bf16 or want_lo)
     t16 = torch.float16 if f16 else torch.bfloat16
     o16 = _empty((max(n_max, 1), L.f16c_pitch(C) if f16 else C), t16, dev) if (want_bf16 or want_lo) else None
@@ -224,12 +233,13 @@ def match_rows(A16, A32, B16, B32, n, m, num_corr, ratio_test=True, n_dev=None, 
     lib = L.load()
     ws_bytes = lib.mv_k2_workspace_bytes(n, m)
     ws = _empty((ws_bytes,), torch.uint8, dev)
-    A = A32 if tf32 else A16
-    B = B32 if tf32 else B16
+    tf32c = tf32 and A16 is not None and B16 is not None  # centred tf32 operand planes ride in the operand-rows slot
+    A = A16 if (not tf32 or tf32c) else A32
+    B = B16 if (not tf32 or tf32c) else B32
     if split:
         C = A_lo.shape[1]
     ld = A.shape[1]
-    Ck = C + 8 if (f16 and not tf32) else C  # f16c rows: the 8 augmentation columns take part in the product
+    Ck = C + 8 if (f16 or tf32c) else C  # f16c / tf32c rows: the 8 augmentation columns take part in the product
     prof = _PROFILE.get("k2_events")
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -293,7 +303,7 @@ def _rows_from_features(F, normalize, dev, role=L.MV_ROLE_QUERY, center=None, do
 def _rows_pair(X_f, Y_f, dev):
     """query rows of X_f and target rows of Y_f for one cosine match: ((A16, A32), (B16, B32), centre of the targets)."""
     mu = None
-    if _CFG["dtype"] == "f16" and Y_f.shape[0] > 0:
+    if _CFG["dtype"] != "bf16" and Y_f.shape[0] > 0:
         Y = _f32(Y_f, dev)
         mu = _center(Y, Y.shape[0], step=max(1, Y.shape[0] // 1024))  # any vector near the mean direction will do
         Y_f = Y
@@ -590,7 +600,7 @@ def _pair_maps(feat_0, feat_1, dev):
     """channel-last fp32 maps of both images + the f16c centre of the target image (None for the other operand types):
     -> (fm0, fm1, kw0, kw1) where fm = (src, C, h, w) and kw are the role keywords of kernel 1 for each side."""
     fm0, fm1 = _feature_map(feat_0, dev), _feature_map(feat_1, dev)
-    if _CFG["dtype"] != "f16":
+    if _CFG["dtype"] == "bf16":
         return fm0, fm1, {}, {}
     mu = _center(fm1[0], fm1[0].shape[0])
     return fm0, fm1, {"role": L.MV_ROLE_QUERY, "dotvec": mu, "pixdot": _rows_dot(fm0[0], mu)}, {"role": L.MV_ROLE_TARGET, "center": mu}

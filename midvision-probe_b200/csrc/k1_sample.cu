@@ -299,6 +299,9 @@ struct K1Params {
   const float* pixdot;  // (h*w; n for MV_SAMPLE_ROWS) or NULL: src[p] . dotvec per source row, precomputed (mv_rows_dot).  The
                         // row's dot product is then the same blend of 4 / 16 of these scalars instead of C multiply-adds
   float* row_dot;       // (n) or NULL: r in fp32
+  // ---- tf32c rows: kernel 2's fp32 (tf32) operand = [tf32_round(row - center) | 8 augmentation columns], pitch pitch_op32
+  float* out_op32;
+  int pitch_op32;
 };
 
 constexpr float K1_LO_SCALE = 2048.f;  // the fp16 residual is stored * 2^11 so that it stays a normal number
@@ -355,6 +358,8 @@ struct K1WShared {
   int npts, ncols, xbase, y0, ngroups;
 };
 
+// round to nearest tf32 (10 explicit mantissa bits), ties away from zero: the value the tensor core then reads exactly
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
 __device__ __forceinline__ float4 lds4(const float* q) { return *reinterpret_cast<const float4*>(q); }
 __device__ __forceinline__ float dot4(const float4& v, float ss) {
   ss = fmaf(v.x, v.x, ss);
@@ -397,6 +402,21 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
     o.z *= inv;
     o.w *= inv;
     if (has32) __stcs(reinterpret_cast<float4*>(p.out_f32 + (size_t)pt * C + c), o);
+    if (p.out_op32) {  // tf32 operand rows: centred, rounded to nearest tf32 here (the tensor core would truncate)
+      float4 y = o;
+      if (p.center) {
+        const float4 m = ld4(p.center + c);
+        y.x -= m.x;
+        y.y -= m.y;
+        y.z -= m.z;
+        y.w -= m.w;
+      }
+      y.x = tf32_rn(y.x);
+      y.y = tf32_rn(y.y);
+      y.z = tf32_rn(y.z);
+      y.w = tf32_rn(y.w);
+      *reinterpret_cast<float4*>(p.out_op32 + (size_t)pt * p.pitch_op32 + c) = y;
+    }
     if (has16) {
       if (p.center) {  // rows relative to the centre: the 16-bit rounding error scales with |row - center|
         const float4 m = ld4(p.center + c);
@@ -437,6 +457,19 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
   // the 8 augmentation columns of an f16c row (and the fp32 r), written by one lane per row
   auto put_aug = [&](int pt, float r) {
     if (p.row_dot) p.row_dot[pt] = r;
+    if (p.out_op32) {  // three tf32-exact pieces of r against (1, 1, 1) of the target rows
+      float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+      if (p.role == MV_ROLE_TARGET) {
+        a0.x = a0.y = a0.z = 1.f;
+      } else {
+        a0.x = tf32_rn(r);
+        a0.y = tf32_rn(r - a0.x);
+        a0.z = tf32_rn(r - a0.x - a0.y);
+      }
+      float* q = p.out_op32 + (size_t)pt * p.pitch_op32 + C;
+      *reinterpret_cast<float4*>(q) = a0;
+      *reinterpret_cast<float4*>(q + 4) = a1;
+    }
     if (!f16c || !has16) return;
     __half a[8];
 #pragma unroll
@@ -1030,8 +1063,11 @@ int mv_rows_dot(const float* rows, int C, int n, const float* vec, float* out, m
 static int k1_entry(const char* who, int mode, const float* src, int C, int h, int w, const float* coords, const int32_t* n_dev,
                     int n_max, int normalize, int fmt16, int pitch16, int role, const float* center, const float* dotvec,
                     const float* pixdot, uint16_t* out16,
-                    uint16_t* out16_lo, float* out_f32, float* row_dot, int32_t* taps, mv_stream_t stream) {
+                    uint16_t* out16_lo, float* out_f32, float* row_dot, int32_t* taps, mv_stream_t stream, float* out_op32 = nullptr,
+                    int pitch_op32 = 0) {
   MV_REQUIRE(src && (out16 || out_f32), MV_E_ARG, "%s: null src or no output", who);
+  MV_REQUIRE(!out_op32 || (pitch_op32 >= C + 8 && pitch_op32 % 4 == 0 && (reinterpret_cast<uintptr_t>(out_op32) & 15) == 0), MV_E_ALIGN,
+             "%s: the tf32 operand rows need a 16-byte aligned base and a pitch >= C + 8 that is a multiple of 4", who);
   MV_REQUIRE(mode == MV_SAMPLE_BILINEAR_ZEROS || mode == MV_SAMPLE_BICUBIC_CLAMP || mode == MV_SAMPLE_ROWS,
              MV_E_ARG, "%s: unknown mode %d", who, mode);
   MV_REQUIRE(mode == MV_SAMPLE_ROWS || (coords && h > 0 && w > 0), MV_E_ARG,
@@ -1070,6 +1106,8 @@ static int k1_entry(const char* who, int mode, const float* src, int C, int h, i
   p.dotvec = dotvec;
   p.pixdot = pixdot;
   p.row_dot = row_dot;
+  p.out_op32 = out_op32;
+  p.pitch_op32 = pitch_op32;
 
   cudaStream_t st = mv_cuda_stream(stream);
   if (mode == MV_SAMPLE_BILINEAR_ZEROS) return launch_k1<MV_SAMPLE_BILINEAR_ZEROS>(p, st);
@@ -1090,6 +1128,14 @@ int mv_k1_sample_f16c(int mode, const float* src, int C, int h, int w, const flo
   MV_REQUIRE(out_f16, MV_E_ARG, "mv_k1_sample_f16c: out_f16 is required");
   return k1_entry("mv_k1_sample_f16c", mode, src, C, h, w, coords, n_dev, n_max, normalize, 1, pitch, role, center, dotvec, pixdot, out_f16,
                   out_f16_lo, out_f32, row_dot, taps, stream);
+}
+
+int mv_k1_sample_tf32c(int mode, const float* src, int C, int h, int w, const float* coords, const int32_t* n_dev, int n_max,
+                       int normalize, int role, const float* center, const float* dotvec, const float* pixdot, float* out_op, int pitch,
+                       float* out_f32, int32_t* taps, mv_stream_t stream) {
+  MV_REQUIRE(out_op && out_f32, MV_E_ARG, "mv_k1_sample_tf32c: out_op and out_f32 are required");
+  return k1_entry("mv_k1_sample_tf32c", mode, src, C, h, w, coords, n_dev, n_max, normalize, 0, C, role, center, dotvec, pixdot, nullptr,
+                  nullptr, out_f32, nullptr, taps, stream, out_op, pitch);
 }
 
 }  // extern "C"

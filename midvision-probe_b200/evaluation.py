@@ -312,7 +312,7 @@ class GraphedPairMatcher:
     def _body_target(self):
         """graph 1 of the split form: everything that needs only the TARGET image (image 1)."""
         fm1 = C_._feature_map(self.f1, self.dev)
-        f16 = C_._CFG["dtype"] == "f16"
+        f16 = C_._CFG["dtype"] != "bf16"  # f16c and tf32c rows are centred on the target
         self._mu = C_._center(fm1[0], fm1[0].shape[0]) if f16 else None
         kw1 = {"role": L.MV_ROLE_TARGET, "center": self._mu} if f16 else {}
         self._s1 = self._prepare(fm1, self.g1, kw1)
@@ -470,7 +470,7 @@ class GraphedPairMatcher:
         # per image: (backproject) + compact + coords + chw_to_hwc + kernel 1; per pair: (centre: 2, pixel dots: 1) + kernel 2 (2) + ratio + top-k
         zero_copy = self.feat_layout == "hwc" and self.feat_dtype == torch.float32
         per_side = (5 if self.kind == "depth" else 4) - (1 if zero_copy else 0)
-        return 2 * per_side + 4 + (3 if C_._CFG["dtype"] == "f16" else 0) + (1 if self.with_outputs else 0)
+        return 2 * per_side + 4 + (3 if C_._CFG["dtype"] != "bf16" else 0) + (1 if self.with_outputs else 0)
 
 
 class PairPipeline:

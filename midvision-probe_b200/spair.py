@@ -43,12 +43,12 @@ def compute_errors_from_features(feats, kps_i, kps_j, thresh_scale, image_size, 
     coords = torch.empty((K, 2), dtype=torch.float32, device=dev)
     L.call("mv_geom_keypoint_coords", L.ptr(ki), ki.shape[1], K, c_float(float(image_size)), h, w, L.ptr(coords), st)
     # f16c operands: image j's pixels are the targets (stored relative to their centre), the key-point rows the queries
-    mu = C_._center(rows_j32, h * w) if C_._CFG["dtype"] == "f16" else None
+    mu = C_._center(rows_j32, h * w) if C_._CFG["dtype"] != "bf16" else None
     a16, a32, _ = C_._sample(L.MV_SAMPLE_BILINEAR_ZEROS, src_i, C, h, w, coords, None, K, False, want16, True,
                              role=L.MV_ROLE_QUERY, dotvec=mu)
     b16 = None
-    if want16:
-        b16 = C_._sample(L.MV_SAMPLE_ROWS, rows_j32, C, 0, 0, None, None, h * w, False, True, False,
+    if want16 or mu is not None:  # the kernel-2 operand rows of image j (bf16 / f16c / tf32c)
+        b16 = C_._sample(L.MV_SAMPLE_ROWS, rows_j32, C, 0, 0, None, None, h * w, False, want16, not want16,
                          role=L.MV_ROLE_TARGET, center=mu)[0]
     r = C_.match_rows(a16, a32, b16, rows_j32, K, h * w, 0, want_topk=False, center_B=mu)
     pred = r.row_idx[:, 0].contiguous()
