@@ -356,6 +356,7 @@ struct K1WShared {
   float rd[K1W_PMAX];      // per point: (unnormalised row) . dotvec from the pixel dots (pixdot form)
   float cy[4];
   int npts, ncols, xbase, y0, ngroups;
+  int cur0;  // first point of the sub-run
 };
 
 // round to nearest tf32 (10 explicit mantissa bits), ties away from zero: the value the tensor core then reads exactly
@@ -370,16 +371,25 @@ __device__ __forceinline__ float dot4(const float4& v, float ss) {
 
 // NITW > 0: C == 128 * NITW * W exactly; a warp holds G rows of C / W channels (G * NITW float4 per lane).
 // NITW == 0: any C (multiple of 4), W = G = 1: two passes over the window (sum of squares, then values).
-template <int MODE, int NITW, int W, int G, int OUTS, int THREADS, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int nslots, uint32_t c4_magic) {
+// PW > 0: WARP-SPECIALISED form -- the first PW warps are PRODUCERS (phases S and A of sub-run i + 1 into the second
+// window) while the THREADS / 32 CONSUMER warps run phase B of sub-run i; two windows, full / empty mbarriers.  The window
+// fill is bound by L2 -> SM bandwidth (128 MB of reads for a NAVI-shaped side) and the row writes by HBM: with one phase
+// after the other (PW == 0) a side costs the sum, here the larger of the two.
+template <int MODE, int NITW, int W, int G, int OUTS, int THREADS, int MINB, int PW = 0>
+__global__ void __launch_bounds__(THREADS + 32 * PW, MINB) k1_rows_kernel(K1Params p, int nslots, uint32_t c4_magic) {
   static_assert(W == 1 || W == 2 || W == 4, "team size");
   static_assert(G >= 1 && G <= 4 && (THREADS / 32) % W == 0 && (W == 1 || THREADS / 32 / W <= 4), "team layout");
+  static_assert(PW == 0 || MODE != MV_SAMPLE_ROWS, "the row-copy mode has no window to produce");
   extern __shared__ float4 k1w_dyn[];
-  float* win = reinterpret_cast<float*>(k1w_dyn);
-  __shared__ K1WShared<W> sh;
+  constexpr int NBUF = PW > 0 ? 2 : 1;
+  __shared__ K1WShared<W> shb[NBUF];
+  __shared__ unsigned long long ws_full[2], ws_empty[2];
+  K1WShared<W>& sh0 = shb[0];  // the consumers' partial-sum exchange lives in buffer 0's struct
   const int n = p.n_dev ? min(*p.n_dev, p.n_max) : p.n_max;
   const int C = (NITW > 0) ? NITW * W * 128 : p.C, C4 = C >> 2;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  float* winb[2] = {reinterpret_cast<float*>(k1w_dyn), reinterpret_cast<float*>(k1w_dyn) + (size_t)(PW > 0 ? nslots : 0) * C};
+  const int tid = threadIdx.x, lane = tid & 31, wid_all = tid >> 5;
+  const int wid = wid_all - PW;  // consumer warp index (negative for a producer warp)
   constexpr int NWARP = THREADS / 32, NTEAM = NWARP / W;
   const int team = wid / W, wsub = wid % W;
   const int cbase = wsub * (C / W);  // this warp's channel slice
@@ -502,8 +512,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
       if (lane == 0) {
 #pragma unroll
         for (int j = 0; j < G; ++j) {
-          sh.part[parity][team][j][wsub] = ss[j];
-          sh.partd[parity][team][j][wsub] = dd[j];
+          sh0.part[parity][team][j][wsub] = ss[j];
+          sh0.partd[parity][team][j][wsub] = dd[j];
         }
       }
       sm100::named_bar_sync(1 + team, W * 32);
@@ -512,8 +522,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
         float t = 0.f, u = 0.f;
 #pragma unroll
         for (int q = 0; q < W; ++q) {  // fixed order: every warp gets the same bits
-          t += sh.part[parity][team][j][q];
-          u += sh.partd[parity][team][j][q];
+          t += sh0.part[parity][team][j][q];
+          u += sh0.partd[parity][team][j][q];
         }
         ss[j] = t;
         dd[j] = u;
@@ -571,10 +581,9 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
   const int max_cols = CUBIC ? nslots : (nslots >> 1);
   const int max_dx = max_cols - (CUBIC ? 4 : 2);  // tap origins x0 .. x0 + max_dx share one window
 
-  int cur = pt_beg;
-  while (cur < pt_end) {  // uniform across the CTA
-    // ---- phase S ----
-    if (wid == 0) {
+  // ---- phase S (one warp): the sub-run that starts at point `cur`
+  auto phase_S = [&](K1WShared<W>& sh, int cur) {
+    {
       const int pt = cur + lane;
       const bool live = pt < pt_end;
       float2 xy = make_float2(0.f, 0.f);
@@ -656,6 +665,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
         sh.rd[lane] = r;
       }
       if (lane == 0) {
+        sh.cur0 = cur;
         sh.npts = npts;
         sh.ncols = ncols;
         sh.xbase = CUBIC ? x0 - 1 : x0;
@@ -664,10 +674,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
         if (CUBIC) cubic_coeffs(xy.y - fy, sh.cy);
       }
     }
-    __syncthreads();
-    const int npts = sh.npts, ncols = sh.ncols, xbase = sh.xbase, y0 = sh.y0, ngroups = sh.ngroups;
+  };
 
-    // ---- phase A: one flat loop over (window slot, 4 channels), several items = many loads in flight per thread ----
+  // ---- phase A (threads t of nt): one flat loop over (window slot, 4 channels), several items = many loads in flight per thread
+  auto phase_A = [&](const K1WShared<W>& sh, float* win, int t, int nt) {
+    const int ncols = sh.ncols, xbase = sh.xbase, y0 = sh.y0;
     if (CUBIC) {
       const float cy0 = sh.cy[0], cy1 = sh.cy[1], cy2 = sh.cy[2], cy3 = sh.cy[3];
       const size_t rs = (size_t)p.w * C;
@@ -677,7 +688,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
       const float* r3 = p.src + (size_t)min(max(y0 + 2, 0), p.h - 1) * rs;
       const int items = ncols * C4;
 #pragma unroll 4  // 16 loads in flight per thread; 32 measured slower (28.7 vs 27.5 us NAVI side, same box)
-      for (int idx = tid; idx < items; idx += THREADS) {
+      for (int idx = t; idx < items; idx += nt) {
         const int s = (int)__umulhi((uint32_t)idx, c4_magic);  // idx / C4
         const int c = (idx - s * C4) * 4;
         const int xo = min(max(xbase + s, 0), p.w - 1) * C + c;
@@ -692,7 +703,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
     } else {
       const int items = 2 * ncols * C4;
 #pragma unroll 8
-      for (int idx = tid; idx < items; idx += THREADS) {
+      for (int idx = t; idx < items; idx += nt) {
         const int slot = (int)__umulhi((uint32_t)idx, c4_magic);  // r * ncols + s
         const int c = (idx - slot * C4) * 4;
         const int r = slot >= ncols ? 1 : 0;
@@ -703,9 +714,11 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
         *reinterpret_cast<float4*>(win + idx * 4) = v;
       }
     }
-    __syncthreads();
+  };
 
-    // ---- phase B ----
+  // ---- phase B (the consumer warps, in teams)
+  auto phase_B = [&](K1WShared<W>& sh, const float* win) {
+    const int cur = sh.cur0, ngroups = sh.ngroups;
     for (int g = team; g < ngroups; g += NTEAM) {
       const int t0 = sh.g_start[g], cnt = sh.g_cnt[g];
       const float* q0 = win + sh.off[t0][0] + cbase;
@@ -766,10 +779,61 @@ __global__ void __launch_bounds__(THREADS, MINB) k1_rows_kernel(K1Params p, int 
         if (lane == 0) put_aug(cur + t0, haspd ? sh.rd[t0] * inv[0] : dd[0]);
       }
     }
-    __syncthreads();  // the window and the per-point scalars are rewritten by the next sub-run
-    cur += npts;
+  };
+
+  if (PW == 0) {  // one phase after the other, the whole CTA in each
+    int cur = pt_beg;
+    while (cur < pt_end) {  // uniform across the CTA
+      if (wid == 0) phase_S(shb[0], cur);
+      __syncthreads();
+      phase_A(shb[0], winb[0], tid, THREADS);
+      __syncthreads();
+      phase_B(shb[0], winb[0]);
+      __syncthreads();  // the window and the per-point scalars are rewritten by the next sub-run
+      cur += shb[0].npts;
+    }
+    return;
+  }
+
+  // ---- warp-specialised driver
+  using namespace sm100;
+  if (tid == 0) {
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&ws_full[b]), PW);      // one arrival per producer warp
+      mbar_init(smem_u32(&ws_empty[b]), NWARP);  // one per consumer warp
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (wid_all < PW) {
+    int cur = pt_beg;
+    for (uint32_t it = 0;; ++it) {
+      const int b = (int)(it & 1u);
+      if (it >= 2) mbar_wait(smem_u32(&ws_empty[b]), ((it >> 1) - 1u) & 1u);  // the consumers released this buffer
+      if (wid_all == 0) {
+        if (cur < pt_end) phase_S(shb[b], cur);
+        else if (lane == 0) shb[b].npts = 0;  // end marker
+      }
+      named_bar_sync(15, PW * 32);  // producers only
+      const int npts = shb[b].npts;
+      if (npts > 0) phase_A(shb[b], winb[b], tid, PW * 32);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ws_full[b]));
+      if (npts == 0) break;
+      cur += npts;
+    }
+  } else {
+    for (uint32_t it = 0;; ++it) {
+      const int b = (int)(it & 1u);
+      mbar_wait(smem_u32(&ws_full[b]), (it >> 1) & 1u);
+      if (shb[b].npts == 0) break;
+      phase_B(shb[b], winb[b]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ws_empty[b]));
+    }
   }
 }
+
 
 // ------------------------------------------------------------------------------------------
 // centre of a set of rows: mu = mean_p rows[p] / max(||rows[p]||, eps) over every `step`-th row.  Any vector near the
@@ -837,19 +901,20 @@ __global__ void __launch_bounds__(512) center_mean_kernel(const float* __restric
   }
 }
 
-template <int MODE, int NITW, int W, int G, int OUTS, int THREADS, int MINB>
+template <int MODE, int NITW, int W, int G, int OUTS, int THREADS, int MINB, int PW = 0>
 int launch_k1_inst(const K1Params& p, cudaStream_t st) {
   const int C = p.C;
-  // window bytes per CTA: MINB CTAs per SM share 227 KB (minus ~3 KB static and 1 KB reserved each)
-  const int budget = (MINB >= 3 ? 72 : (MINB == 2 ? 108 : 216)) << 10;
+  // window bytes per CTA: MINB CTAs per SM share 227 KB (minus ~3 KB static and 1 KB reserved each); the warp-specialised
+  // form holds two windows of 108 KB
+  const int budget = (PW > 0 ? 108 : (MINB >= 3 ? 72 : (MINB == 2 ? 108 : 216))) << 10;
   int nslots = budget / (C * 4);
   if (nslots < 4) nslots = 4;    // C <= 8192: 4 slots = 128 KB, one CTA per SM
   if (nslots > 40) nslots = 40;  // more than any 32-point sub-run can use
-  const size_t smem = (MODE == MV_SAMPLE_ROWS) ? 0 : (size_t)nslots * C * 4;
+  const size_t smem = (MODE == MV_SAMPLE_ROWS) ? 0 : (size_t)(PW > 0 ? 2 : 1) * nslots * C * 4;
   int grid = mv_sm_count() * MINB;
   if (grid > p.n_max) grid = p.n_max;
   if (grid < 1) grid = 1;
-  auto kern = k1_rows_kernel<MODE, NITW, W, G, OUTS, THREADS, MINB>;
+  auto kern = k1_rows_kernel<MODE, NITW, W, G, OUTS, THREADS, MINB, PW>;
   static size_t opted[MV_MAX_DEVICES];  // per instantiation and device: the attribute belongs to the device function
   size_t& opted_in = opted[mv_device_slot()];
   if (opted_in < (44u << 10)) opted_in = 44 << 10;
@@ -864,7 +929,7 @@ int launch_k1_inst(const K1Params& p, cudaStream_t st) {
   }
   const uint32_t C4 = (uint32_t)p.C / 4;
   const uint32_t magic = (uint32_t)((0x100000000ull + C4 - 1) / C4);  // idx / C4 == umulhi(idx, magic) for idx * C4 < 2^32
-  kern<<<grid, THREADS, smem, st>>>(p, nslots, magic);
+  kern<<<grid, THREADS + 32 * PW, smem, st>>>(p, nslots, magic);
   MV_LAUNCH_CHECK();
   return MV_OK;
 }
@@ -887,10 +952,20 @@ int launch_k1(const K1Params& p, cudaStream_t st) {
   // 39.6 us with teams of 4 warps x 4 points vs 41.4 us point-at-a-time; C = 3072 (4x bicubic, ~12-17 points per
   // CTA) 31.5 us with teams -- the 72 KB window of a 3-CTA/SM layout splits the short runs -- vs 27.4 us with one
   // warp per point and the whole row (96 registers) in a 108 KB window, so that shape keeps the latter.
-  // C = 3072, one CTA per SM with a 216 KB window (MVMATCH_K1_WIDE=1): longer runs per window -> 30 % less L2 traffic
+  // C = 3072, one CTA per SM with a 216 KB window (MVMATCH_K1_WIDE=1): 30 % less L2 traffic, measured SLOWER (33.7 vs 31.6 us)
   static const bool wide = getenv("MVMATCH_K1_WIDE") && atoi(getenv("MVMATCH_K1_WIDE")) != 0;
   if (wide) {
     K1W_CASE(3072, 24, 1, 1, 384, 1)
+  }
+  // warp-specialised form (MVMATCH_K1_WS, sampling modes only): 4 producer warps + 8 consumer warps, one CTA per SM
+  static const bool ws = !getenv("MVMATCH_K1_WS") || atoi(getenv("MVMATCH_K1_WS")) != 0;
+  if (ws && MODE != MV_SAMPLE_ROWS && outs == K1W_OUT_SPLIT) {
+#define K1WS_CASE(CC, NITW, W, GG)                                                                                   \
+  if (C == CC) return launch_k1_inst<(MODE == MV_SAMPLE_ROWS ? MV_SAMPLE_BILINEAR_ZEROS : MODE), NITW, W, GG, K1W_OUT_SPLIT, 256, 1, 4>(p, st);
+    K1WS_CASE(3072, 24, 1, 1)
+    K1WS_CASE(2048, 4, 4, 4)
+    K1WS_CASE(768, 6, 1, 4)
+#undef K1WS_CASE
   }
   K1W_CASE(768, 6, 1, 4, 128, 3)    // ViT-B
   K1W_CASE(1024, 4, 2, 4, 256, 2)   // ViT-L

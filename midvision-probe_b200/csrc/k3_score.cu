@@ -212,7 +212,9 @@ template <typename ROWS>
 void launch_ratio(const ROWS& rows, int C, const int32_t* n_dev, int n_max, int32_t* row_idx, const unsigned long long* col_best,
                   int ratio_test, float* dists, float* weight, uint8_t* mutual, cudaStream_t st) {
   static const int forced = getenv("MVMATCH_RATIO_W") ? atoi(getenv("MVMATCH_RATIO_W")) : 0;
-  const int W = forced ? forced : (C >= 2048 ? 4 : (C >= 1024 ? 2 : 1));
+  // measured in the 4-lane pipeline (bench.py, same box): NAVI-shaped 4153 pairs/s with teams of 4 vs 4353 with one warp per query,
+  // ScanNet-shaped 917 vs 917 -- the other lanes already hide this kernel's load latency -- so one warp per query stays the default
+  const int W = forced ? forced : 1;
   const int teams = RATIO_THREADS / 32 / W;
   const unsigned grid = (unsigned)((n_max + teams - 1) / teams);
   if (W == 4) k3_ratio_mutual_kernel<ROWS, 4><<<grid, RATIO_THREADS, 0, st>>>(rows, C, n_dev, n_max, row_idx, col_best, ratio_test, dists, weight, mutual);
