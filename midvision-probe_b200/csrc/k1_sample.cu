@@ -957,8 +957,11 @@ int launch_k1(const K1Params& p, cudaStream_t st) {
   if (wide) {
     K1W_CASE(3072, 24, 1, 1, 384, 1)
   }
-  // warp-specialised form (MVMATCH_K1_WS, sampling modes only): 4 producer warps + 8 consumer warps, one CTA per SM
-  static const bool ws = !getenv("MVMATCH_K1_WS") || atoi(getenv("MVMATCH_K1_WS")) != 0;
+  // warp-specialised form (MVMATCH_K1_WS=1, sampling modes only): 4 producer warps + 8 consumer warps, one CTA per SM.
+  // Measured on B200 (bench.py --k1-only, same box): NAVI-shaped side 40.7 us vs 35.1 us, ScanNet-shaped side 80.0 vs 53.8 us:
+  // at 159-168 registers per thread one CTA per SM leaves 8 consumer warps where the two classic CTAs have 12-16, and 128
+  // producer threads keep a third of the window-fill loads in flight -- the overlap does not pay for either.  OFF by default.
+  static const bool ws = getenv("MVMATCH_K1_WS") && atoi(getenv("MVMATCH_K1_WS")) != 0;
   if (ws && MODE != MV_SAMPLE_ROWS && outs == K1W_OUT_SPLIT) {
 #define K1WS_CASE(CC, NITW, W, GG)                                                                                   \
   if (C == CC) return launch_k1_inst<(MODE == MV_SAMPLE_ROWS ? MV_SAMPLE_BILINEAR_ZEROS : MODE), NITW, W, GG, K1W_OUT_SPLIT, 256, 1, 4>(p, st);
