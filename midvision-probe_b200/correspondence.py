@@ -602,8 +602,13 @@ def _pair_maps(feat_0, feat_1, dev):
     fm0, fm1 = _feature_map(feat_0, dev), _feature_map(feat_1, dev)
     if _CFG["dtype"] == "bf16":
         return fm0, fm1, {}, {}
-    mu = _center(fm1[0], fm1[0].shape[0])
+    mu = _center(fm1[0], fm1[0].shape[0], step=_center_step(fm1[0].shape[0]))
     return fm0, fm1, {"role": L.MV_ROLE_QUERY, "dotvec": mu, "pixdot": _rows_dot(fm0[0], mu)}, {"role": L.MV_ROLE_TARGET, "center": mu}
+
+
+def _center_step(n_rows):
+    """the centre only has to lie near the mean direction (the ranking is exact for every centre): ~256 pixels are plenty"""
+    return max(1, n_rows // 256)
 
 
 def _rows_dot(rows, vec):

@@ -840,34 +840,46 @@ __global__ void __launch_bounds__(THREADS + 32 * PW, MINB) k1_rows_kernel(K1Para
 // mean DIRECTION of the normalised rows works as the centre of f16c rows (the ranking is exact for every choice; the
 // fp16 rounding error of kernel 2's operands scales with |row - mu|).
 // ------------------------------------------------------------------------------------------
-__global__ void center_invnorm_kernel(const float* __restrict__ rows, int C, int n_max, const int32_t* __restrict__ n_dev,
-                                      int step, float* __restrict__ inv) {
+// one CTA of 4 warps per row: the row's channels are split over the warps (short dependent-load chains; these small kernels sit
+// on the critical path of a synchronous helper call), partial sums added in a fixed order
+__device__ __forceinline__ float block4_sum(float v, float* sm4) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) sm4[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return (sm4[0] + sm4[1]) + (sm4[2] + sm4[3]);
+}
+
+__global__ void __launch_bounds__(128) center_invnorm_kernel(const float* __restrict__ rows, int C, int n_max,
+                                                             const int32_t* __restrict__ n_dev, int step, float* __restrict__ inv) {
+  __shared__ float sm4[4];
   const int n = n_dev ? min(*n_dev, n_max) : n_max;
   const int cnt = (n + step - 1) / step;
-  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int q = blockIdx.x;
   if (q >= cnt) return;
   const float* r = rows + (size_t)q * step * C;
   float ss = 0.f;
-  for (int c = lane * 4; c < C; c += 128) ss = dot4(ld4(r + c), ss);
-  ss = warp_sum(ss);
-  if (lane == 0) inv[q] = 1.f / fmaxf(sqrtf(ss), K1_NORM_EPS);
+  for (int c = threadIdx.x * 4; c < C; c += 512) ss = dot4(ld4(r + c), ss);
+  ss = block4_sum(ss, sm4);
+  if (threadIdx.x == 0) inv[q] = 1.f / fmaxf(sqrtf(ss), K1_NORM_EPS);
 }
 
-// out[p] = rows[p] . vec (one warp per row): the per-pixel dots of the pixdot form
-__global__ void rows_dot_kernel(const float* __restrict__ rows, int C, int n, const float* __restrict__ vec, float* __restrict__ out) {
-  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+// out[p] = rows[p] . vec (one CTA of 4 warps per row): the per-pixel dots of the pixdot form
+__global__ void __launch_bounds__(128) rows_dot_kernel(const float* __restrict__ rows, int C, int n, const float* __restrict__ vec,
+                                                       float* __restrict__ out) {
+  __shared__ float sm4[4];
+  const int q = blockIdx.x;
   if (q >= n) return;
   const float* r = rows + (size_t)q * C;
   float acc = 0.f;
-  for (int c = lane * 4; c < C; c += 128) {
+  for (int c = threadIdx.x * 4; c < C; c += 512) {
     const float4 v = ld4(r + c), d = ld4(vec + c);
     acc = fmaf(v.x, d.x, acc);
     acc = fmaf(v.y, d.y, acc);
     acc = fmaf(v.z, d.z, acc);
     acc = fmaf(v.w, d.w, acc);
   }
-  acc = warp_sum(acc);
-  if (lane == 0) out[q] = acc;
+  acc = block4_sum(acc, sm4);
+  if (threadIdx.x == 0) out[q] = acc;
 }
 
 // block = 32 channel quads x 16 row groups: group g sums rows q = g, g + 16, ... (independent loads, 4 in flight), the 16
@@ -1120,7 +1132,7 @@ int mv_rows_center(const float* rows, int C, int n_max, const int32_t* n_dev, in
              "mv_rows_center: rows and mu must be 16-byte aligned");
   cudaStream_t st = mv_cuda_stream(stream);
   const int cnt = (n_max + step - 1) / step;
-  center_invnorm_kernel<<<(cnt + 7) / 8, 256, 0, st>>>(rows, C, n_max, n_dev, step, inv_scratch);
+  center_invnorm_kernel<<<cnt, 128, 0, st>>>(rows, C, n_max, n_dev, step, inv_scratch);
   MV_LAUNCH_CHECK();
   center_mean_kernel<<<(C / 4 + 31) / 32, 512, 0, st>>>(rows, C, n_max, n_dev, step, inv_scratch, mu);
   MV_LAUNCH_CHECK();
@@ -1133,7 +1145,7 @@ int mv_rows_dot(const float* rows, int C, int n, const float* vec, float* out, m
   MV_REQUIRE(((reinterpret_cast<uintptr_t>(rows) | reinterpret_cast<uintptr_t>(vec)) & 15) == 0, MV_E_ALIGN,
              "mv_rows_dot: rows and vec must be 16-byte aligned");
   if (n == 0) return MV_OK;
-  rows_dot_kernel<<<(n + 7) / 8, 256, 0, mv_cuda_stream(stream)>>>(rows, C, n, vec, out);
+  rows_dot_kernel<<<n, 128, 0, mv_cuda_stream(stream)>>>(rows, C, n, vec, out);
   MV_LAUNCH_CHECK();
   return MV_OK;
 }

@@ -313,7 +313,7 @@ class GraphedPairMatcher:
         """graph 1 of the split form: everything that needs only the TARGET image (image 1)."""
         fm1 = C_._feature_map(self.f1, self.dev)
         f16 = C_._CFG["dtype"] != "bf16"  # f16c and tf32c rows are centred on the target
-        self._mu = C_._center(fm1[0], fm1[0].shape[0]) if f16 else None
+        self._mu = C_._center(fm1[0], fm1[0].shape[0], step=C_._center_step(fm1[0].shape[0])) if f16 else None
         kw1 = {"role": L.MV_ROLE_TARGET, "center": self._mu} if f16 else {}
         self._s1 = self._prepare(fm1, self.g1, kw1)
 
