@@ -359,17 +359,20 @@ class GraphedPairMatcher:
             self._body()
         cur.wait_stream(side)
         torch.cuda.synchronize(self.dev)
+        # torch.cuda.graph's default capture stream is created once per process on whatever device was current then: a
+        # matcher on another device must bring its own, or its allocations fall outside the capture's pool
+        cap = torch.cuda.Stream(device=self.dev)
         if self.split:
             pool = torch.cuda.graph_pool_handle()  # the second graph consumes tensors the first one produces
             self.graph_target = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph_target, pool=pool):
+            with torch.cuda.graph(self.graph_target, pool=pool, stream=cap):
                 self._body_target()
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph, pool=pool):
+            with torch.cuda.graph(self.graph, pool=pool, stream=cap):
                 self.out = self._body_query()
         else:
             self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, stream=cap):
                 self.out = self._body()
         if self.with_outputs:
             self.host_packed = torch.empty(self.packed.shape, dtype=torch.float32, pin_memory=True)
