@@ -216,6 +216,13 @@ int mv_k2_sim_top2_ld(const void* A, int lda, const void* B, int ldb, int n_max,
 int mv_k2_affinity(const void* A, int lda, const void* B, int ldb, int n_max, int m_max, int C, const int32_t* n_dev,
                    const int32_t* m_dev, int dtype, int cluster, float* S_out, int ld_s, float* row_val, int32_t* row_idx,
                    unsigned long long* col_best, void* workspace, size_t workspace_bytes, mv_stream_t stream);
+/* Timing of the GEMM kernel ALONE (for a roofline figure that is not diluted by the col_best memset and the row merge of
+ * the same call): after mv_k2_profile_begin(capacity) the next `capacity` calls of mv_k2_sim_top2* / mv_k2_affinity on this
+ * host thread record a CUDA event pair right around the launch of the tcgen05 kernel; mv_k2_profile_read waits for them
+ * and returns how many durations (milliseconds, call order) it wrote to ms_out (host).  begin(0) switches it off.  Not
+ * capturable into a CUDA graph. */
+int mv_k2_profile_begin(int capacity);
+int mv_k2_profile_read(float* ms_out, int max_n);
 int mv_k2_unpack_col(const unsigned long long* col_best, int m, float* col_val, int32_t* col_idx, mv_stream_t stream);
 
 /* ---- kernel 3: fp32 distance recompute, ratio test, mutual check, selection, scoring ---- */

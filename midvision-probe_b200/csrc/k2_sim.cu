@@ -26,6 +26,8 @@
 // every SM gets the same number of tiles (+-1); a row block that is split between CTAs leaves partial
 // top-2 records in the workspace which k2_merge_rows_kernel folds (ties: lower column).
 #include <cuda.h>
+
+#include <vector>
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -543,9 +545,39 @@ int launch_k2(const CUtensorMap& tmA, const CUtensorMap& tmB, const K2Params& p,
   return MV_OK;
 }
 
+// ---- optional timing of the GEMM kernel alone (bench.py's roofline): events recorded right around the launch of
+// k2_sim_top2_kernel, so that the figure is the kernel's own duration and not memset + kernel + row merge
+struct K2Profile {
+  std::vector<cudaEvent_t> ev;  // 2 per recorded launch
+  int capacity = 0, count = 0;
+};
+thread_local K2Profile g_k2_prof;
+
 }  // namespace
 
 extern "C" {
+
+int mv_k2_profile_begin(int capacity) {
+  MV_REQUIRE(capacity >= 0 && capacity <= (1 << 16), MV_E_RANGE, "mv_k2_profile_begin: capacity out of range");
+  K2Profile& pr = g_k2_prof;
+  for (cudaEvent_t e : pr.ev) cudaEventDestroy(e);
+  pr.ev.clear();
+  pr.count = 0;
+  pr.capacity = capacity;
+  pr.ev.resize((size_t)2 * capacity);
+  for (auto& e : pr.ev) MV_CUDA(cudaEventCreate(&e));
+  return MV_OK;
+}
+
+int mv_k2_profile_read(float* ms_out, int max_n) {
+  K2Profile& pr = g_k2_prof;
+  const int n = pr.count < max_n ? pr.count : max_n;
+  for (int i = 0; i < n; ++i) {
+    MV_CUDA(cudaEventSynchronize(pr.ev[2 * i + 1]));
+    MV_CUDA(cudaEventElapsedTime(ms_out + i, pr.ev[2 * i], pr.ev[2 * i + 1]));
+  }
+  return n;
+}
 
 size_t mv_k2_workspace_bytes(int n_max, int m_max) {
   (void)m_max;
@@ -631,6 +663,9 @@ int mv_k2_affinity(const void* A, int lda, const void* B, int ldb, int n_max, in
 
   cudaStream_t st = mv_cuda_stream(stream);
   MV_CUDA(cudaMemsetAsync(col_best, 0, (size_t)m_max * sizeof(unsigned long long), st));
+  K2Profile& pr = g_k2_prof;
+  const bool timed = pr.count < pr.capacity;
+  if (timed) MV_CUDA(cudaEventRecord(pr.ev[2 * pr.count], st));
   if (pair) {
     rc = tf32 ? launch_k2<true, 2, true>(tmA, tmB, p, grid, st) : launch_k2<false, 2, true>(tmA, tmB, p, grid, st);
   } else if (tf32) {
@@ -643,6 +678,10 @@ int mv_k2_affinity(const void* A, int lda, const void* B, int ldb, int n_max, in
     else rc = launch_k2<false, 4>(tmA, tmB, p, grid, st);
   }
   if (rc) return rc;
+  if (timed) {
+    MV_CUDA(cudaEventRecord(pr.ev[2 * pr.count + 1], st));
+    ++pr.count;
+  }
   const int mt = 256;
   if (mc == 1) k2_merge_rows_kernel<1><<<(n_max + mt - 1) / mt, mt, 0, st>>>(p.clusters, p.partial, n_dev, n_max, m_dev, m_max, row_val, row_idx);
   else if (mc == 2) k2_merge_rows_kernel<2><<<(n_max + mt - 1) / mt, mt, 0, st>>>(p.clusters, p.partial, n_dev, n_max, m_dev, m_max, row_val, row_idx);
