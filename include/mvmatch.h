@@ -221,6 +221,12 @@ int mv_k2_affinity(const void* A, int lda, const void* B, int ldb, int n_max, in
  * host thread record a CUDA event pair right around the launch of the tcgen05 kernel; mv_k2_profile_read waits for them
  * and returns how many durations (milliseconds, call order) it wrote to ms_out (host).  begin(0) switches it off.  Not
  * capturable into a CUDA graph. */
+/* Schedule switch of kernel 2: 1 lets the persistent schedule cut tiles along K when a cluster would otherwise get a
+ * small non-integer number of tiles ("stream-K": equal k-block counts per SM, head fragments handed over through the
+ * workspace).  Default 0 (MVMATCH_K2_STREAMK=1 in the environment starts with 1): measured slower on B200, see
+ * csrc/k2_sim.cu.  Returns the previous setting; on < 0 only queries.  Takes effect for launches issued afterwards (a
+ * captured CUDA graph keeps the setting it was captured with). */
+int mv_k2_set_streamk(int on);
 int mv_k2_profile_begin(int capacity);
 int mv_k2_profile_read(float* ms_out, int max_n);
 int mv_k2_unpack_col(const unsigned long long* col_best, int m, float* col_val, int32_t* col_idx, mv_stream_t stream);

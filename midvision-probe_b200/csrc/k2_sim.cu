@@ -27,6 +27,8 @@
 // top-2 records in the workspace which k2_merge_rows_kernel folds (ties: lower column).
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <vector>
 #include <math_constants.h>
 
@@ -62,13 +64,26 @@ constexpr int COL_SMEM_BYTES = 2 * 4 * BN * 8;  // [2 buffers][4 warps][256 colu
 template <bool PAIR> constexpr int k2_smem_bytes() { return 1024 /*align slack*/ + Ring<PAIR>::BYTES + COL_SMEM_BYTES + 256 /*barriers*/; }
 
 struct K2Sched {
-  // tiles are numbered t = sb * n_ct + ct; cluster c owns [c*T/G, (c+1)*T/G).  Built on the device from the
-  // LIVE row counts, so a problem whose counts only exist in device memory is balanced like any other.
+  // tiles are numbered t = sb * n_ct + ct and cut into tk work UNITS each; cluster c owns the units
+  // [c*W/G, (c+1)*W/G).  Built on the device from the LIVE row counts, so a problem whose counts only exist in
+  // device memory is balanced like any other.
+  //   tk == 1       : a unit is a tile (every SM gets the same number of tiles +-1)
+  //   tk == kblocks : "stream-K": a unit is one k-block of a tile, so every SM gets the same number of k-blocks
+  //                   +-1.  A cluster whose range starts inside a tile computes that tile's LAST k-blocks first
+  //                   (its head fragment), stores the raw accumulators to the workspace and raises a flag; the
+  //                   cluster that holds the tile's k-block 0 OWNS the tile: it runs the fused epilogue on its
+  //                   own accumulators + that fragment.  Chosen when a cluster has few tiles (the NAVI shape:
+  //                   5.4 tiles per SM would otherwise cost the time of 6).
   unsigned long long T;  // n_sb * n_ct
-  int G;                 // clusters that own tiles: min(clusters in the grid, T)
+  unsigned long long W;  // T * tk
+  int G;                 // clusters that own work: min(clusters in the grid, T)
   int n_ct;              // column tiles
   int n_sb;              // super row blocks (MC * 128 rows)
+  int tk;                // units per tile
 };
+constexpr int SK_MIN_KBLOCKS = 8;         // stream-K only when a tile has enough k-blocks to be worth cutting
+constexpr int SK_MAX_TILES_PER_CLUSTER = 16;  // ... and few enough tiles per cluster for the tail to matter
+constexpr int FRAG_BYTES = BM * BN * 4;   // raw accumulators of one CTA's 128 x 256 tile
 
 struct K2Params {
   const int32_t* n_dev;
@@ -77,13 +92,16 @@ struct K2Params {
   int tail_steps;   // MMA K-steps that carry data in the LAST k-block (1..4): K extents need not fill the 128-byte row
   uint32_t ab_fmt;  // tcgen05 instruction-descriptor operand format: 0 = fp16, 1 = bf16 (kind::f16), 2 = tf32
   int clusters;     // clusters in the grid
+  int streamk;      // 1 = the schedule may cut tiles along K (see K2Sched)
+  float4* frag;     // gridDim.x slots of FRAG_BYTES: head-fragment accumulators, slot = contributing CTA
+  uint32_t* flags;  // gridDim.x flags, zeroed before the launch: 1 = the CTA's head fragment is in memory
   float4* partial;  // (clusters + n_sb_max) slots of MC * 128 rows x 2 column halves of {max1, idx1, max2, idx2}; slot = cluster + sb
   unsigned long long* col_best;
   float* S_out;     // optional (n_max, ld_s) fp32: the similarity tile is also written out (affinity consumers, mv_k2_affinity)
   int ld_s;
 };
 
-__host__ __device__ inline K2Sched make_sched(int n, int m, int mc, int clusters) {
+__host__ __device__ inline K2Sched make_sched(int n, int m, int mc, int clusters, int kblocks, int streamk) {
   K2Sched s;
   s.n_sb = (n + 128 * mc - 1) / (128 * mc);
   s.n_ct = (m + 256 - 1) / 256;
@@ -92,15 +110,23 @@ __host__ __device__ inline K2Sched make_sched(int n, int m, int mc, int clusters
   s.G = clusters;
   if ((unsigned long long)s.G > s.T) s.G = (int)s.T;
   if (s.G < 1) s.G = 1;
+  // T >= G makes every range at least one tile's worth of units long: a tile is shared by at most two clusters and
+  // every cluster holds the k-block 0 of at least one tile
+  const bool sk = streamk && kblocks >= SK_MIN_KBLOCKS && s.T % (unsigned long long)s.G != 0 &&
+                  s.T < (unsigned long long)SK_MAX_TILES_PER_CLUSTER * (unsigned long long)s.G;
+  s.tk = sk ? kblocks : 1;
+  s.W = s.T * (unsigned long long)s.tk;
   return s;
 }
 
+// first unit of cluster c
 __host__ __device__ inline unsigned long long sched_begin(const K2Sched& s, int c) {
-  return (unsigned long long)c * s.T / (unsigned long long)s.G;
+  return (unsigned long long)c * s.W / (unsigned long long)s.G;
 }
-// cluster that owns tile t
+// cluster that owns tile t (the one whose range holds the tile's first unit)
 __host__ __device__ inline int sched_owner(const K2Sched& s, unsigned long long t) {
-  return (int)(((t + 1) * (unsigned long long)s.G + s.T - 1) / s.T) - 1;
+  const unsigned long long u = t * (unsigned long long)s.tk;
+  return (int)(((u + 1) * (unsigned long long)s.G + s.W - 1) / s.W) - 1;
 }
 
 __device__ __forceinline__ bool better(float x, int j, float y, int k) {
@@ -138,19 +164,51 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
   const int m = p.m_dev ? min(*p.m_dev, p.m_max) : p.m_max;
 
   // clusters beyond sch.G (fewer tiles than clusters) own nothing
-  const K2Sched sch = make_sched(n, m, MC, p.clusters);
+  const K2Sched sch = make_sched(n, m, MC, p.clusters, p.kblocks, p.streamk);
   const bool has_work = cluster_id < sch.G && sch.T > 0;
-  const unsigned long long t_beg = has_work ? sched_begin(sch, cluster_id) : 0ull;
-  const unsigned long long t_end = has_work ? sched_begin(sch, cluster_id + 1) : 0ull;
+  const unsigned long long u_beg = has_work ? sched_begin(sch, cluster_id) : 0ull;
+  const unsigned long long u_end = has_work ? sched_begin(sch, cluster_id + 1) : 0ull;
+  const unsigned tk = (unsigned)sch.tk;
+  // stream-K pieces of this cluster's range (all zero when tk == 1): the head fragment = k-blocks [head_k0, kblocks) of
+  // tile head_tile, computed FIRST and handed to the previous cluster; the owned tiles [t_beg, t_end); the last owned
+  // tile only up to k-block tail_k (the next cluster's head fragment supplies the rest), computed LAST
+  const int head_k0 = (int)(u_beg % tk);
+  const unsigned long long head_tile = u_beg / tk;
+  const int tail_k = (int)(u_end % tk);
+  const unsigned long long t_beg = (u_beg + tk - 1) / tk;
+  const unsigned long long t_end = (u_end + tk - 1) / tk;
   // The range is walked starting at its first row-block boundary and wrapping around, so that every CTA sweeps
   // the column tiles in phase (all at column ~s mod n_ct at step s): the B tiles in flight are then the same
   // few for the whole chip and the L2 working set is the active A blocks + a narrow window of B, instead of
   // all of B (which overflows the 126 MB L2 once (n + m) * C * 2 bytes does).
   const unsigned long long t_len = t_end - t_beg;
   unsigned long long t_rot = (t_beg + (unsigned)sch.n_ct - 1) / (unsigned)sch.n_ct * (unsigned)sch.n_ct;
-  if (t_rot >= t_end) t_rot = t_beg;
+  if (t_rot >= t_end || tk > 1) t_rot = t_beg;  // stream-K keeps the order: the tail tile has to come last
   const unsigned long long t_head = t_end - t_rot;  // steps [0, t_head) map to [t_rot, t_end), the rest to [t_beg, t_rot)
 #define MV_K2_TILE_AT(step) ((step) < t_head ? t_rot + (step) : t_beg + ((step) - t_head))
+  // work items of this cluster, in execution order: [head fragment] + owned tiles
+  const unsigned long long n_items = t_len + (head_k0 ? 1u : 0u);
+  struct Item {
+    unsigned long long t;
+    int kb0, kb1;
+    int kind;  // 0 = whole tile, 1 = head fragment (store the accumulators), 2 = tail tile (add the next cluster's fragment)
+  };
+  auto item_at = [&](unsigned long long s) -> Item {
+    Item it;
+    if (head_k0) {
+      if (s == 0) {
+        it.t = head_tile; it.kb0 = head_k0; it.kb1 = p.kblocks; it.kind = 1;
+        return it;
+      }
+      s -= 1;
+    }
+    it.t = MV_K2_TILE_AT(s);
+    const bool last = tail_k != 0 && s + 1 == t_len;
+    it.kb0 = 0;
+    it.kb1 = last ? tail_k : p.kblocks;
+    it.kind = last ? 2 : 0;
+    return it;
+  };
   constexpr int KE = TF32 ? 32 : 64;  // K elements per 128-byte row
 
   if (threadIdx.x == 0) {
@@ -182,11 +240,12 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (unsigned long long step = 0; step < t_len; ++step) {
-        const unsigned long long t = MV_K2_TILE_AT(step);
+      for (unsigned long long step = 0; step < n_items; ++step) {
+        const Item it = item_at(step);
+        const unsigned long long t = it.t;
         const int sb = (int)(t / (unsigned)sch.n_ct), ct = (int)(t - (unsigned long long)sb * sch.n_ct);
         const int row0 = (sb * MC + rank) * BM, col0 = ct * BN;
-        for (int kb = 0; kb < p.kblocks; ++kb) {
+        for (int kb = it.kb0; kb < it.kb1; ++kb) {
           mbar_wait(smem_u32(&bars->empty[stage]), phase ^ 1u);
           const uint32_t full = smem_u32(&bars->full[stage]);
           const uint32_t sa = smem_base + stage * STAGE_BYTES, sbm = sa + A_STAGE_BYTES;
@@ -225,22 +284,24 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (unsigned long long step = 0; (!PAIR || rank == 0) && step < t_len; ++step) {
+    for (unsigned long long step = 0; (!PAIR || rank == 0) && step < n_items; ++step) {
+      const Item it = item_at(step);
+      const int kb_first = it.kb0;
       mbar_wait(smem_u32(&bars->tmem_empty[acc]), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)acc * BN;
-      for (int kb = 0; kb < p.kblocks; ++kb) {
+      for (int kb = it.kb0; kb < it.kb1; ++kb) {
         mbar_wait(smem_u32(&bars->full[stage]), phase);
         tc_fence_after();
         if (leader) {
           const uint64_t da = desc0 + (uint64_t)((uint32_t)stage * (STAGE_BYTES >> 4));
           const uint64_t db = da + (uint64_t)(A_STAGE_BYTES >> 4);
           if (kb == kb_last && tail_steps < 4u) {  // partial last k-block (e.g. the 8 augmentation columns of f16c rows)
-            umma_kblock_tail<TF32, PAIR ? 2 : (MC == 1 ? 0 : 1)>(d_tmem, da, db, idesc, (uint32_t)(kb != 0), smem_u32(&bars->empty[stage]),
+            umma_kblock_tail<TF32, PAIR ? 2 : (MC == 1 ? 0 : 1)>(d_tmem, da, db, idesc, (uint32_t)(kb != kb_first), smem_u32(&bars->empty[stage]),
                                                                (uint16_t)((1u << MC) - 1), tail_steps);
-          } else if (PAIR) umma_kblock_pair<TF32>(d_tmem, da, db, idesc, (uint32_t)(kb != 0), smem_u32(&bars->empty[stage]));
-          else if (MC == 1) umma_kblock<TF32>(d_tmem, da, db, idesc, (uint32_t)(kb != 0), smem_u32(&bars->empty[stage]));
-          else umma_kblock_mc<TF32>(d_tmem, da, db, idesc, (uint32_t)(kb != 0), smem_u32(&bars->empty[stage]),
+          } else if (PAIR) umma_kblock_pair<TF32>(d_tmem, da, db, idesc, (uint32_t)(kb != kb_first), smem_u32(&bars->empty[stage]));
+          else if (MC == 1) umma_kblock<TF32>(d_tmem, da, db, idesc, (uint32_t)(kb != kb_first), smem_u32(&bars->empty[stage]));
+          else umma_kblock_mc<TF32>(d_tmem, da, db, idesc, (uint32_t)(kb != kb_first), smem_u32(&bars->empty[stage]),
                                     (uint16_t)((1u << MC) - 1));
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -270,9 +331,38 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
           make_float4(m1, __int_as_float(i1), m2, __int_as_float(i2));
     };
 
-    for (unsigned long long step = 0; step < t_len; ++step) {
-      const unsigned long long t = MV_K2_TILE_AT(step);
+    // fragment slots: [chunk of 32 columns][4 columns][row] float4, so that the 128 rows of a column group are contiguous
+    float4* const frag_mine = p.frag + (size_t)blockIdx.x * (FRAG_BYTES / 16) + e;
+    const float4* const frag_next = p.frag + (size_t)(blockIdx.x + MC) * (FRAG_BYTES / 16) + e;  // same rank, next cluster
+    for (unsigned long long step = 0; step < n_items; ++step) {
+      const Item it = item_at(step);
+      const unsigned long long t = it.t;
       const int sb = (int)(t / (unsigned)sch.n_ct), ct = (int)(t - (unsigned long long)sb * sch.n_ct);
+      if (it.kind == 1) {
+        // ---- head fragment: raw accumulators to the workspace, then the flag the owning cluster waits for
+        mbar_wait(smem_u32(&bars->tmem_full[acc]), acc_phase);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (uint32_t)acc * BN + ((uint32_t)(ew * 32) << 16);
+#pragma unroll 1
+        for (int ch = half * 4; ch < half * 4 + 4; ++ch) {
+          float v[32];
+          tmem_ld_32x32(taddr + ch * 32, v);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) __stcg(frag_mine + (size_t)(ch * 8 + q) * BM, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(map_to_cta(smem_u32(&bars->tmem_empty[acc]), 0));
+          else mbar_arrive(smem_u32(&bars->tmem_empty[acc]));
+        }
+        __threadfence();
+        named_bar_sync(3, 256);  // all eight epilogue warps have stored and fenced
+        if (threadIdx.x == EPI_WARP0 * 32) st_release_gpu(p.flags + blockIdx.x, 1u);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+        continue;
+      }
       if (sb != cur_sb) {
         if (cur_sb >= 0) flush(cur_sb);
         m1 = m2 = -CUDART_INF_F;
@@ -287,11 +377,26 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
       mbar_wait(smem_u32(&bars->tmem_full[acc]), acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)acc * BN + ((uint32_t)(ew * 32) << 16);
+      const bool add_frag = it.kind == 2;
+      if (add_frag) {  // the rest of this tile's K range: the next cluster computed it first thing
+        if (lane == 0) flag_wait(p.flags + blockIdx.x + MC);
+        __syncwarp();
+      }
 
 #pragma unroll 1
       for (int ch = half * 4; ch < half * 4 + 4; ++ch) {
         float v[32];
         tmem_ld_32x32(taddr + ch * 32, v);
+        if (add_frag) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 f = __ldcg(frag_next + (size_t)(ch * 8 + q) * BM);
+            v[4 * q] += f.x;
+            v[4 * q + 1] += f.y;
+            v[4 * q + 2] += f.z;
+            v[4 * q + 3] += f.w;
+          }
+        }
         const int cb = col0 + ch * 32;
         if (edge) {
 #pragma unroll
@@ -390,7 +495,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
 
 // fold the partial top-2 records of every row; write (n_max, 2) value / index pairs
 template <int MC>
-__global__ void k2_merge_rows_kernel(int clusters, const float4* __restrict__ partial, const int32_t* __restrict__ n_dev,
+__global__ void k2_merge_rows_kernel(int clusters, int kblocks, int streamk, const float4* __restrict__ partial, const int32_t* __restrict__ n_dev,
                                      int n_max, const int32_t* __restrict__ m_dev, int m_max, float* __restrict__ row_val,
                                      int32_t* __restrict__ row_idx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -400,7 +505,7 @@ __global__ void k2_merge_rows_kernel(int clusters, const float4* __restrict__ pa
   float m1 = -CUDART_INF_F, m2 = -CUDART_INF_F;
   int i1 = -1, i2 = -1;
   if (i < n && m > 0) {
-    const K2Sched s = make_sched(n, m, MC, clusters);
+    const K2Sched s = make_sched(n, m, MC, clusters, kblocks, streamk);
     const int sb = i / (BM * MC);
     const int c_first = sched_owner(s, (unsigned long long)sb * s.n_ct);
     const int c_last = sched_owner(s, (unsigned long long)(sb + 1) * s.n_ct - 1);
@@ -475,7 +580,26 @@ int make_operand_map(CUtensorMap* tm, const void* base, int rows, int C, int ld,
 
 size_t k2_partial_bytes(int n_max, int mc, int clusters) {
   const int n_sb_max = (n_max + BM * mc - 1) / (BM * mc);
-  return (size_t)(clusters + n_sb_max) * (BM * mc) * 2 * sizeof(float4);
+  return ((size_t)(clusters + n_sb_max) * (BM * mc) * 2 * sizeof(float4) + 255) / 256 * 256;
+}
+// stream-K area behind the partial records: one flag and one accumulator-fragment slot per CTA of the grid
+constexpr size_t SK_FLAG_BYTES = 1024;  // >= 4 * 148, keeps the fragments 256-byte aligned
+size_t k2_streamk_bytes(int ctas) { return SK_FLAG_BYTES + (size_t)ctas * FRAG_BYTES; }
+
+// The K-cut schedule is OFF by default: measured on B200 at the NAVI shape (tools/k2_streamk_ab.py, same process,
+// kernel timed alone) 117.6 us against 111.6 us of the tile-granular schedule back to back, 125 against 122 us for
+// isolated launches.  Equalising the k-blocks per SM buys nothing because the kernel is not limited per SM: it pulls
+// 1.29 GB of operand tiles out of L2 per launch (11.6 TB/s, the chip's ~6300 B/clk L2 slice throughput) and runs at the
+// power-capped sustained rate of the chip, so the SMs that finish a tile early simply leave more L2 bandwidth to the
+// others; the K-cut only adds 38 MB of fragment traffic and one extra epilogue per SM.  MVMATCH_K2_STREAMK=1 or
+// mv_k2_set_streamk(1) switches it on (tests/test_gpu_k2.py runs it).
+int g_k2_streamk = -1;
+int k2_streamk_enabled() {
+  if (g_k2_streamk < 0) {
+    const char* e = getenv("MVMATCH_K2_STREAMK");
+    g_k2_streamk = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_k2_streamk;
 }
 
 int pick_mc(int cluster) { return cluster <= 1 ? 1 : (cluster >= 4 ? 4 : 2); }
@@ -557,6 +681,12 @@ thread_local K2Profile g_k2_prof;
 
 extern "C" {
 
+int mv_k2_set_streamk(int on) {
+  const int prev = k2_streamk_enabled();
+  if (on >= 0) g_k2_streamk = on ? 1 : 0;
+  return prev;
+}
+
 int mv_k2_profile_begin(int capacity) {
   MV_REQUIRE(capacity >= 0 && capacity <= (1 << 16), MV_E_RANGE, "mv_k2_profile_begin: capacity out of range");
   K2Profile& pr = g_k2_prof;
@@ -581,13 +711,13 @@ int mv_k2_profile_read(float* ms_out, int max_n) {
 
 size_t mv_k2_workspace_bytes(int n_max, int m_max) {
   (void)m_max;
-  if (n_max <= 0) return 256;
+  if (n_max <= 0) return 256 + k2_streamk_bytes(mv_sm_count());
   size_t worst = 0;
   for (int mc = 1; mc <= 4; mc *= 2) {
     const size_t b = k2_partial_bytes(n_max, mc, mv_sm_count() / mc);
     if (b > worst) worst = b;
   }
-  return worst + 256;
+  return worst + 256 + k2_streamk_bytes(mv_sm_count());
 }
 
 int mv_k2_sim_top2(const void* A, const void* B, int n_max, int m_max, int C, const int32_t* n_dev,
@@ -638,7 +768,8 @@ int mv_k2_affinity(const void* A, int lda, const void* B, int ldb, int n_max, in
   const int grid = k2_grid(mc, tf32, pair);
   K2Params p;
   p.clusters = grid / mc;
-  const size_t need = k2_partial_bytes(n_max, mc, p.clusters);
+  const size_t part_bytes = k2_partial_bytes(n_max, mc, p.clusters);
+  const size_t need = part_bytes + k2_streamk_bytes(grid);
   MV_REQUIRE(workspace_bytes >= need, MV_E_WORKSPACE, "mv_k2_sim_top2: workspace has %zu bytes, %zu needed",
              workspace_bytes, need);
   p.n_dev = n_dev;
@@ -651,6 +782,9 @@ int mv_k2_affinity(const void* A, int lda, const void* B, int ldb, int n_max, in
   p.tail_steps = (C - (p.kblocks - 1) * ke + kstep - 1) / kstep;
   p.ab_fmt = tf32 ? 2u : (dtype == MV_DTYPE_F16 ? 0u : 1u);
   p.partial = reinterpret_cast<float4*>(workspace);
+  p.flags = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + part_bytes);
+  p.frag = reinterpret_cast<float4*>(reinterpret_cast<uint8_t*>(workspace) + part_bytes + SK_FLAG_BYTES);
+  p.streamk = k2_streamk_enabled();
   p.col_best = col_best;
   p.S_out = S_out;
   p.ld_s = ld_s;
@@ -663,6 +797,7 @@ int mv_k2_affinity(const void* A, int lda, const void* B, int ldb, int n_max, in
 
   cudaStream_t st = mv_cuda_stream(stream);
   MV_CUDA(cudaMemsetAsync(col_best, 0, (size_t)m_max * sizeof(unsigned long long), st));
+  if (p.streamk) MV_CUDA(cudaMemsetAsync(p.flags, 0, SK_FLAG_BYTES, st));
   K2Profile& pr = g_k2_prof;
   const bool timed = pr.count < pr.capacity;
   if (timed) MV_CUDA(cudaEventRecord(pr.ev[2 * pr.count], st));
@@ -683,9 +818,9 @@ int mv_k2_affinity(const void* A, int lda, const void* B, int ldb, int n_max, in
     ++pr.count;
   }
   const int mt = 256;
-  if (mc == 1) k2_merge_rows_kernel<1><<<(n_max + mt - 1) / mt, mt, 0, st>>>(p.clusters, p.partial, n_dev, n_max, m_dev, m_max, row_val, row_idx);
-  else if (mc == 2) k2_merge_rows_kernel<2><<<(n_max + mt - 1) / mt, mt, 0, st>>>(p.clusters, p.partial, n_dev, n_max, m_dev, m_max, row_val, row_idx);
-  else k2_merge_rows_kernel<4><<<(n_max + mt - 1) / mt, mt, 0, st>>>(p.clusters, p.partial, n_dev, n_max, m_dev, m_max, row_val, row_idx);
+  if (mc == 1) k2_merge_rows_kernel<1><<<(n_max + mt - 1) / mt, mt, 0, st>>>(p.clusters, p.kblocks, p.streamk, p.partial, n_dev, n_max, m_dev, m_max, row_val, row_idx);
+  else if (mc == 2) k2_merge_rows_kernel<2><<<(n_max + mt - 1) / mt, mt, 0, st>>>(p.clusters, p.kblocks, p.streamk, p.partial, n_dev, n_max, m_dev, m_max, row_val, row_idx);
+  else k2_merge_rows_kernel<4><<<(n_max + mt - 1) / mt, mt, 0, st>>>(p.clusters, p.kblocks, p.streamk, p.partial, n_dev, n_max, m_dev, m_max, row_val, row_idx);
   MV_LAUNCH_CHECK();
   return MV_OK;
 }

@@ -352,4 +352,28 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
+// ---- flags in global memory between CTAs of one grid (stream-K hand-over) ----------------------
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// spin until *p != 0.  The writer is a CTA of the same persistent grid that raises the flag as its first piece of work.
+__device__ __forceinline__ void flag_wait(const uint32_t* p) {
+#if MV_WATCHDOG
+  for (uint32_t spin = 0; ld_acquire_gpu(p) == 0u; ++spin) {
+    if (spin > (1u << 24)) {  // seconds
+      printf("mvmatch: stream-K flag watchdog: block %d thread %d\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+    __nanosleep(64);
+  }
+#else
+  while (ld_acquire_gpu(p) == 0u) __nanosleep(64);
+#endif
+}
+
 }  // namespace sm100

@@ -128,6 +128,47 @@ def test_k2_repeatable(mv):
     assert all(torch.equal(x, y) for x, y in zip(a, b))
 
 
+@pytest.fixture
+def streamk(mv):
+    """the K-cut schedule is off by default (measured slower, csrc/k2_sim.cu): switch it on for the test"""
+    lib = mv._lib.load()
+    prev = lib.mv_k2_set_streamk(1)
+    yield
+    lib.mv_k2_set_streamk(prev)
+
+
+# shapes whose tile count is a small non-multiple of the SM / cluster count and whose K extent has >= 8 k-blocks: the
+# schedule cuts tiles along K there (stream-K: head fragments through the workspace, owner adds them in its epilogue)
+STREAMK_SHAPES = [(5024, 5024, 520), (3000, 4100, 1032), (2500, 2300, 776)]
+
+
+@pytest.mark.parametrize("n,m,C", STREAMK_SHAPES)
+@pytest.mark.parametrize("dtype,cluster", [("f16", 0), ("bf16", 2), ("f16", 4), ("f16", 20), ("tf32", 20), ("tf32", 0), ("bf16", -1)])
+def test_k2_streamk_schedule(mv, streamk, n, m, C, dtype, cluster):
+    frac = check(mv, n, m, C, dtype, cluster)
+    assert frac > 0.9
+
+
+@pytest.mark.parametrize("cluster", [0, 20])
+def test_k2_streamk_device_counts_and_repeatability(mv, streamk, cluster):
+    check(mv, 5200, 5100, 776, "f16", cluster, n_live=5024, m_live=5011)
+    g = torch.Generator().manual_seed(11)
+    A = torch.randn(5024, 776, generator=g)
+    B = torch.randn(4999, 776, generator=g)
+    a = run_k2(mv, A, B, "f16", cluster)
+    b = run_k2(mv, A, B, "f16", cluster)
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+
+
+def test_k2_streamk_is_exercised(mv):
+    """the schedule really is the K-cut one for these shapes (library-side decision, restated here)."""
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    for n, m, C in STREAMK_SHAPES:
+        tiles = ((n + 127) // 128) * ((m + 255) // 256)
+        kblocks = (C + 63) // 64
+        assert kblocks >= 8 and tiles >= sms and tiles % sms != 0 and tiles < 16 * sms
+
+
 @pytest.mark.parametrize("dtype,cluster", [("bf16", 0), ("bf16", 2), ("tf32", 0), ("bf16", 20), ("tf32", 20), ("f16", -1)])
 def test_k2_full_size_properties(mv, syn, dtype, cluster):
     """19200 x 19200 x 768 (BASELINE.json stress config): too big for an element-wise CPU check, so
