@@ -299,7 +299,8 @@ def run_dense(ctx, workload, steps, warmup, fixed_pairs=0, light=False):
     C_._PROFILE["k2_events"] = []
     k2_steps = max(1, min(steps, 10))
     lib = L.load()
-    lib.mv_k2_profile_begin(k2_steps * PAIRS_PER_STEP)  # event pairs right around the tcgen05 kernel inside the library
+    k2_cap = 2 * k2_steps * PAIRS_PER_STEP  # room for the Gram launch of the low-rank proposal next to the main product
+    lib.mv_k2_profile_begin(k2_cap)  # event pairs right around the tcgen05 kernel inside the library
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     for s in range(k2_steps):
@@ -311,11 +312,18 @@ def run_dense(ctx, workload, steps, warmup, fixed_pairs=0, light=False):
     k2_ev = C_._PROFILE.pop("k2_events")
     import ctypes
 
-    kbuf = (ctypes.c_float * (k2_steps * PAIRS_PER_STEP))()
-    n_k = lib.mv_k2_profile_read(kbuf, k2_steps * PAIRS_PER_STEP)
+    kbuf = (ctypes.c_float * k2_cap)()
+    dbuf = (ctypes.c_int * (3 * k2_cap))()
+    n_k = lib.mv_k2_profile_read(kbuf, k2_cap)
+    lib.mv_k2_profile_dims(dbuf, k2_cap)
     lib.mv_k2_profile_begin(0)
-    k2_kernel_ms = [kbuf[i] for i in range(max(n_k, 0))]
+    # the main product's launches are the ones with the (n_max, C) of the calls match_rows made; with the low-rank proposal
+    # the same kernel also computes the small Gram matrix of the source pixels (mv_k2_affinity): reported separately
+    main_dims = {(n_, c_) for _, _, (n_, m_, c_, nd, md) in k2_ev}
+    k2_kernel_ms = [kbuf[i] for i in range(max(n_k, 0)) if (dbuf[3 * i], dbuf[3 * i + 2]) in main_dims]
+    gram = [(kbuf[i], dbuf[3 * i], dbuf[3 * i + 1], dbuf[3 * i + 2]) for i in range(max(n_k, 0)) if (dbuf[3 * i], dbuf[3 * i + 2]) not in main_dims]
     k2_call_ms = [a.elapsed_time(b) for a, b, _ in k2_ev]
+    k2_kernel_ms = k2_kernel_ms[:len(k2_call_ms)]
     k2_ms = k2_kernel_ms if len(k2_kernel_ms) == len(k2_call_ms) and k2_kernel_ms else k2_call_ms
     k2_flops = [2.0 * (int(nd.item()) if nd is not None else n_) * (int(md.item()) if md is not None else m_) * c_
                 for _, _, (n_, m_, c_, nd, md) in k2_ev]
@@ -343,8 +351,9 @@ def run_dense(ctx, workload, steps, warmup, fixed_pairs=0, light=False):
         achieved = k2_avg_flop / (k2_avg_ms * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "k2_traffic.json")
+        lowrank_used = bool(k2_ev) and k2_ev[0][2][2] < pool_dev[0]["feat_0"].shape[0]
         if os.path.exists(tpath) and args.dtype != "tf32":
-            traffic = json.load(open(tpath)).get(workload, {}).get("dram_bytes")
+            traffic = json.load(open(tpath)).get(workload + ("_lowrank" if lowrank_used else ""), {}).get("dram_bytes")
         # burst figure unless the timed pass is seconds long (the sustained cuBLAS figure is a 4 s back-to-back run)
         long_pass = ms_total > 2000.0
         peak = tc_sustained if long_pass else tc_peak
@@ -362,6 +371,18 @@ def run_dense(ctx, workload, steps, warmup, fixed_pairs=0, light=False):
             "timed_in": "second, eagerly launched pass over the same steps (events cannot be recorded inside the captured graph)",
             "eager_pass_ms_per_step": ms_eager / k2_steps,
             "whole_step_tensor_frac": (k2_avg_flop * pairs_total / world / (ms_total * 1e-3) / 1e12) / tc_peak}
+        Ck_main = k2_ev[0][2][2]
+        C_feat = pool_dev[0]["feat_0"].shape[0]
+        if Ck_main < C_feat:  # the low-rank proposal: kernel 2 multiplies over the target's source pixels, not the channels
+            rec["roofline"]["lowrank"] = {
+                "k2_columns": Ck_main, "channels": C_feat,
+                "note": "kernel 2 ranks the same cosine similarities as a product over the target image's h*w source pixels (+8 "
+                        "augmentation columns) instead of the C channels (csrc/lr_gram.cu); achieved / frac above count the FLOPs "
+                        "ISSUED (2 n m k2_columns); at this K the kernel is bound by its epilogue (row top-2 + column arg-max of "
+                        "every 128 x 256 tile), not by the tensor pipe",
+                "dense_equivalent_tflops": achieved * (C_feat + 8) / Ck_main,
+                "gram_launch": ({"avg_ms": sum(g[0] for g in gram) / len(gram), "rows": gram[0][1], "K": gram[0][3], "launches": len(gram)}
+                                if gram else None)}
     if fixed_pairs and light:
         del gm
         return rec

@@ -188,6 +188,32 @@ int mv_k1_grid_f16c(const float* src, int C, int h, int w, int H, int W, const i
 int mv_rows_center(const float* rows, int C, int n_max, const int32_t* n_dev, int step, float* inv_scratch, float* mu,
                    mv_stream_t stream);
 
+/* ---- kernel 2's operands in the basis of the source pixels ("low-rank proposal", csrc/lr_gram.cu) ----
+ * The dense helpers interpolate every row linearly from an (h*w, C) source map (correspondence.py:164-176 bilinear
+ * grid_sample; :240-241 bicubic interpolate), so the cosine similarity of two interpolated, normalised rows
+ * (correspondence.py:47-48 + :14-23) is a product over the h*w SOURCE PIXELS of the target image instead of the C
+ * channels:  cos(x_i, y_j) = sum_t A[i,t] B[j,t],  A[i,t] = (x_i/|x_i|) . (src1[t]/|src1[t]|),  B[j,t] = W1[j,t] |src1[t]| / |y_j|.
+ * The N x M product still runs on kernel 2 (mv_k2_sim_top2_ld, MV_DTYPE_F16, hwp + 8 columns); these entry points build
+ * its operands.  hwp = h*w rounded up to a multiple of 8 (<= MV_LR_MAX_SOURCE_PIXELS).
+ *   mv_lr_unit_rows    U (hw, C) fp16 = src / |src| per source pixel, snorm (hw) = |src|; src (hw, C) fp32 channel-last.
+ *                      The caller stacks both images' U (image k at row offset off_k, pad rows zero) and obtains the
+ *                      stacked cosine Gram matrix G (fp32, pitch ld_g) from mv_k2_affinity(U, U).
+ *   mv_lr_build_query  A_f16 (n, pitch): [fp16(A[i,:] - c_i) (hw) | 0 (to hwp) | c_i, c_i, 0 x 6], c_i = fp16(max_t A[i,t])
+ *                      (centring a row on its own maximum keeps the fp16 rounding error of the columns that compete for
+ *                      the row's top-2 at ~1e-6, also on nearly collinear CNN features).
+ *   mv_lr_build_target B_f16 (m, pitch): [fp16(B[j,:]) scattered into zeros | two fp16 pieces of beta_j = sum_t B[j,t], 0 x 6]
+ * so that the product of an A row and a B row over hwp + 8 columns is cos(x_i, y_j) up to the fp16 rounding of A - c and B.
+ * coords (n, 2): the continuous source coordinates kernel 1 samples at (mv_geom_project_coords / mv_geom_grid_coords);
+ * mode: MV_SAMPLE_BILINEAR_ZEROS or MV_SAMPLE_BICUBIC_CLAMP (the taps of kernel 1); snorm, off_own: this image's |src| and
+ * its offset in G; off_tgt: the target image's offset in G.  The product only PROPOSES a row's two candidates: kernel 3
+ * recomputes their fp32 distances from the exact rows. */
+#define MV_LR_MAX_SOURCE_PIXELS 1024
+int mv_lr_unit_rows(const float* src_hwc, int C, int hw, void* U_f16, float* snorm, mv_stream_t stream);
+int mv_lr_build_query(int mode, const float* coords, const int32_t* n_dev, int n_max, int h, int w, const float* snorm,
+                      const float* G, int ld_g, int off_own, int off_tgt, void* A_f16, int pitch, int hwp, mv_stream_t stream);
+int mv_lr_build_target(int mode, const float* coords, const int32_t* n_dev, int n_max, int h, int w, const float* snorm,
+                       const float* G, int ld_g, int off_own, void* B_f16, int pitch, int hwp, mv_stream_t stream);
+
 /* ---- kernel 2: similarity GEMM with fused row top-2 / column arg-max (tensor-core bound) -- */
 /* S = A @ B^T (n x m, never written).  Replaces faiss GpuIndexFlatL2.search(k<=2)
  * (correspondence.py:14-23) for L2-normalised rows, where the L2 order equals the cosine order
@@ -229,6 +255,9 @@ int mv_k2_affinity(const void* A, int lda, const void* B, int ldb, int n_max, in
 int mv_k2_set_streamk(int on);
 int mv_k2_profile_begin(int capacity);
 int mv_k2_profile_read(float* ms_out, int max_n);
+/* (n_max, m_max, C) of the recorded launches, three ints each, call order: tells the launches of one call site from another's
+ * (the Gram launch of the low-rank proposal and the main product go through the same kernel). */
+int mv_k2_profile_dims(int* nmc_out, int max_n);
 int mv_k2_unpack_col(const unsigned long long* col_best, int m, float* col_val, int32_t* col_idx, mv_stream_t stream);
 
 /* ---- kernel 3: fp32 distance recompute, ratio test, mutual check, selection, scoring ---- */

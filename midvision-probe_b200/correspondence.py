@@ -51,6 +51,10 @@ _CFG = {
     # host-tensor calls of the dense helpers: two graphs (target side / the rest) so that the second image's upload overlaps
     # the first one's kernels (evaluation.GraphedPairMatcher.load_and_replay_split); 0 = one graph after both uploads
     "helper_split": int(os.environ.get("MVMATCH_HELPER_SPLIT", "1")),
+    # kernel 2's product over the SOURCE PIXELS of the target image instead of the channels (csrc/lr_gram.cu, "low-rank
+    # proposal"): "auto" = where it pays (dense helpers, fp16 operands, h*w + 8 <= C / 5 and a large similarity matrix: the
+    # ScanNet-shaped pairs, 312 instead of 2056 columns), "1" = wherever it applies, "0" = never
+    "lowrank": os.environ.get("MVMATCH_LOWRANK", "auto"),
 }
 _HELPER_GRAPHS = {}  # (kind, shapes, num_corr, ratio_test, dtype, cluster, K bytes) -> evaluation.GraphedPairMatcher
 _HELPER_GRAPHS_MAX = 12
@@ -60,12 +64,16 @@ _HELPER_GRAPHS_MAX = 12
 _PROFILE = {}
 
 
-def set_match_precision(dtype=None, cluster=None, helper_graphs=None, rows=None, k1_grid=None):
+def set_match_precision(dtype=None, cluster=None, helper_graphs=None, rows=None, k1_grid=None, lowrank=None):
     """Choose kernel 2's operand type ("f16" | "bf16" | "tf32"), its cluster width (1, 2 or 4), whether the dense
     helpers replay cached CUDA graphs for host-tensor calls, and the row format between kernels 1 and 3
     ("split" | "f32", see _CFG)."""
     if k1_grid is not None:
         _CFG["k1_grid"] = int(bool(k1_grid))
+    if lowrank is not None:
+        if str(lowrank) not in ("auto", "0", "1"):
+            raise ValueError("lowrank must be 'auto', 0 or 1")
+        _CFG["lowrank"] = str(lowrank)
     if rows is not None:
         if rows not in ("split", "f32"):
             raise ValueError("rows must be 'split' or 'f32'")
@@ -207,7 +215,7 @@ class MatchResult:
 
 
 def match_rows(A16, A32, B16, B32, n, m, num_corr, ratio_test=True, n_dev=None, m_dev=None, want_topk=True, run_k3=True,
-               A_lo=None, B_lo=None, center_B=None, C=None):
+               A_lo=None, B_lo=None, center_B=None, C=None, proposal=None):
     """kernel 2 + kernel 3 on prepared rows.
 
     A16/B16: (n, C)/(m, C) bf16 rows or (n, pitch)/(m, pitch) fp16 f16c rows (query / target role; None when the
@@ -216,6 +224,8 @@ def match_rows(A16, A32, B16, B32, n, m, num_corr, ratio_test=True, n_dev=None, 
     Mirrors get_correspondences_ratio_test (correspondence.py:63-102, bidirectional=False):
     2-NN -> fp32 cosine distances -> ratio weights -> top-num_corr, plus the mutual-NN flag.
     n, m are the live counts when n_dev/m_dev are None, otherwise upper bounds.
+    proposal: (A_op, B_op, K) fp16 operand rows of _lowrank_operands -- kernel 2 then ranks their product over K columns
+    (the same cosine similarities in the basis of the source pixels) while kernel 3 still reads the exact rows.
     """
     ref = A32 if A32 is not None else A16
     dev = ref.device
@@ -240,12 +250,16 @@ def match_rows(A16, A32, B16, B32, n, m, num_corr, ratio_test=True, n_dev=None, 
         C = A_lo.shape[1]
     ld = A.shape[1]
     Ck = C + 8 if (f16 or tf32c) else C  # f16c / tf32c rows: the 8 augmentation columns take part in the product
+    k2_A, k2_B, k2_dtype = A, B, L.MV_DTYPE_TF32 if tf32 else (L.MV_DTYPE_F16 if f16 else L.MV_DTYPE_BF16)
+    if proposal is not None:
+        k2_A, k2_B, Ck = proposal
+        k2_dtype = L.MV_DTYPE_F16
     prof = _PROFILE.get("k2_events")
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    L.call("mv_k2_sim_top2_ld", L.ptr(A), ld, L.ptr(B), B.shape[1], n, m, Ck, L.ptr(n_dev), L.ptr(m_dev),
-           L.MV_DTYPE_TF32 if tf32 else (L.MV_DTYPE_F16 if f16 else L.MV_DTYPE_BF16), _CFG["cluster"], L.ptr(row_val),
+    L.call("mv_k2_sim_top2_ld", L.ptr(k2_A), k2_A.shape[1], L.ptr(k2_B), k2_B.shape[1], n, m, Ck, L.ptr(n_dev), L.ptr(m_dev),
+           k2_dtype, _CFG["cluster"], L.ptr(row_val),
            L.ptr(row_idx), L.ptr(col_best), L.ptr(ws), c_size_t(ws_bytes), st)
     if prof is not None:
         ev1.record()
@@ -587,13 +601,67 @@ def compute_binned_performance(y, x, x_bins):
 class _Side:
     """One image of a pair after kernel 1: compacted geometry + feature rows."""
 
-    __slots__ = ("n", "n_dev", "xyz", "uv", "rows16", "rows32", "rows_lo", "valid_idx", "taps", "center")
+    __slots__ = ("n", "n_dev", "xyz", "uv", "rows16", "rows32", "rows_lo", "valid_idx", "taps", "center",
+                 "coords", "mode", "src", "fshape")  # the last four: what the low-rank proposal builds its operands from
+
+
+def lowrank_applies(C, h, w, n_max, m_max, mode=L.MV_SAMPLE_BILINEAR_ZEROS):
+    """whether the dense helpers run kernel 2 over the target's source pixels (h*w + 8 columns) instead of the channels."""
+    cfg = _CFG["lowrank"]
+    hwp = (h * w + 7) // 8 * 8
+    if cfg == "0" or _CFG["dtype"] != "f16" or hwp > L.MV_LR_MAX_SOURCE_PIXELS or h * w < 2:
+        return False
+    if mode not in (L.MV_SAMPLE_BILINEAR_ZEROS, L.MV_SAMPLE_BICUBIC_CLAMP):
+        return False
+    if cfg == "1":
+        return True
+    # measured on B200: ScanNet-shaped (300 source pixels, C = 2048, 18231^2) 0.83 -> ~0.35 ms for kernel 2; NAVI-shaped (784
+    # source pixels, C = 3072, 5024^2) would trade 113 us of kernel 2 for a 60 us product + a 45 us Gram launch + the builders
+    return (hwp + 8) * 5 <= C and n_max * m_max >= (1 << 24)
+
+
+def _lowrank_operands(s0, s1, n, m, n_dev, m_dev):
+    """fp16 operands of kernel 2 in the basis of the target image's source pixels (csrc/lr_gram.cu):
+    unit source rows of both images -> their stacked cosine Gram matrix (kernel 2 with the similarity written out) ->
+    query rows A' (n, P) and target rows B (m, P); returns (A', B, h*w padded + 8)."""
+    C, h, w = s0.fshape
+    dev = s0.src.device
+    st = _stream()
+    hw = h * w
+    hwp = (hw + 7) // 8 * 8
+    P = L.f16c_pitch(hwp)
+    U = _empty((2 * hwp, C), torch.float16, dev)
+    if hwp > hw:  # pad rows: zero Gram rows / columns
+        U[hw:hwp].zero_()
+        U[hwp + hw:].zero_()
+    snorm = _empty((2 * hwp,), torch.float32, dev)
+    L.call("mv_lr_unit_rows", L.ptr(s0.src), C, hw, L.ptr(U), L.ptr(snorm), st)
+    L.call("mv_lr_unit_rows", L.ptr(s1.src), C, hw, c_void_p(U.data_ptr() + hwp * C * 2), c_void_p(snorm.data_ptr() + hwp * 4), st)
+    G = _empty((2 * hwp, 2 * hwp), torch.float32, dev)
+    rv = _empty((2 * hwp, 2), torch.float32, dev)
+    ri = _empty((2 * hwp, 2), torch.int32, dev)
+    cb = _empty((2 * hwp,), torch.int64, dev)
+    wsb = L.load().mv_k2_workspace_bytes(2 * hwp, 2 * hwp)
+    ws = _empty((wsb,), torch.uint8, dev)
+    L.call("mv_k2_affinity", L.ptr(U), C, L.ptr(U), C, 2 * hwp, 2 * hwp, C, None, None, L.MV_DTYPE_F16, _CFG["cluster"], L.ptr(G),
+           2 * hwp, L.ptr(rv), L.ptr(ri), L.ptr(cb), L.ptr(ws), c_size_t(wsb), st)
+    A_op = _empty((max(n, 1), P), torch.float16, dev)
+    B_op = _empty((max(m, 1), P), torch.float16, dev)
+    L.call("mv_lr_build_target", s1.mode, L.ptr(s1.coords), L.ptr(m_dev), m, h, w, c_void_p(snorm.data_ptr() + hwp * 4), L.ptr(G),
+           2 * hwp, hwp, L.ptr(B_op), P, hwp, st)
+    L.call("mv_lr_build_query", s0.mode, L.ptr(s0.coords), L.ptr(n_dev), n, h, w, L.ptr(snorm), L.ptr(G), 2 * hwp, 0, hwp,
+           L.ptr(A_op), P, hwp, st)
+    return A_op, B_op, hwp + 8
 
 
 def _match_sides(s0, s1, n0, n1, num_corr, ratio_test=True, n_dev=None, m_dev=None):
     """s0 = query side, s1 = target side (prepared with the matching f16c roles, see _pair_maps)."""
+    proposal = None
+    if (s0.src is not None and s1.src is not None and s0.fshape == s1.fshape and s0.mode == s1.mode and n0 > 0 and n1 > 0
+            and s0.rows_lo is not None and lowrank_applies(*s0.fshape, n0, n1, s0.mode)):
+        proposal = _lowrank_operands(s0, s1, n0, n1, n_dev, m_dev)
     return match_rows(s0.rows16, s0.rows32, s1.rows16, s1.rows32, n0, n1, num_corr, ratio_test, n_dev=n_dev, m_dev=m_dev,
-                      A_lo=s0.rows_lo, B_lo=s1.rows_lo, center_B=s1.center)
+                      A_lo=s0.rows_lo, B_lo=s1.rows_lo, center_B=s1.center, proposal=proposal)
 
 
 def _pair_maps(feat_0, feat_1, dev):
@@ -649,6 +717,7 @@ def _finish_depth(f, d, K, staged, n, synced, want_taps=False, rows=None, role=L
                L.ptr(coords), _stream())
     s.taps = _empty((max(n, 1), 2), torch.int32, dev) if want_taps else None
     s.uv = None
+    s.coords, s.mode, s.src, s.fshape = coords, L.MV_SAMPLE_BILINEAR_ZEROS, src, (C, h, w)
     w16, w32, wlo = _row_format(rows)
     s.rows16, s.rows32, s.rows_lo = _sample(L.MV_SAMPLE_BILINEAR_ZEROS, src, C, h, w, coords, nd, n, True, w16, w32,
                                             s.taps, wlo, role=role, center=center, dotvec=dotvec, pixdot=pixdot)
@@ -694,6 +763,7 @@ def _finish_xyz(f, g, staged, n, synced, want_taps=False, rows=None, role=L.MV_R
         L.call("mv_geom_grid_coords", L.ptr(g), L.ptr(valid_idx), L.ptr(nd), n, H, W, h, w, L.ptr(s.xyz), L.ptr(s.uv),
                L.ptr(coords), _stream())
     s.taps = _empty((max(n, 1), 2), torch.int32, dev) if want_taps else None
+    s.coords, s.mode, s.src, s.fshape = coords, L.MV_SAMPLE_BICUBIC_CLAMP, src, (C, h, w)
     w16, w32, wlo = _row_format(rows)
     s.center = center
     if (_CFG["k1_grid"] and _CFG["dtype"] == "f16" and w16 and wlo and not w32 and not want_taps and n > 0
@@ -805,7 +875,7 @@ def _graphed_helper(kind, feat_0, feat_1, grid_0, grid_1, num_corr, ratio_test, 
     # pageable ones are staged by host threads, which the interleaved replay only delays (578 -> 458)
     split = on_host and bool(_CFG["helper_split"]) and feat_0.is_pinned() and feat_1.is_pinned()
     # the intrinsics are NOT part of the key: they live in device memory and are refreshed per call (gm.load)
-    key = (on_host, split, kind, tuple(feat_0.shape), tuple(grid_0.shape), int(num_corr), bool(ratio_test), _CFG["dtype"], _CFG["cluster"], _CFG["rows"], _CFG["k1_grid"], fdt,
+    key = (on_host, split, kind, tuple(feat_0.shape), tuple(grid_0.shape), int(num_corr), bool(ratio_test), _CFG["dtype"], _CFG["cluster"], _CFG["rows"], _CFG["k1_grid"], _CFG["lowrank"], fdt,
            dev.index, layout)
     gm = _HELPER_GRAPHS.get(key)
     if gm is None:

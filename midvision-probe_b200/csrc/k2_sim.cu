@@ -673,6 +673,7 @@ int launch_k2(const CUtensorMap& tmA, const CUtensorMap& tmB, const K2Params& p,
 // k2_sim_top2_kernel, so that the figure is the kernel's own duration and not memset + kernel + row merge
 struct K2Profile {
   std::vector<cudaEvent_t> ev;  // 2 per recorded launch
+  std::vector<int> dims;        // (n_max, m_max, C) per recorded launch
   int capacity = 0, count = 0;
 };
 thread_local K2Profile g_k2_prof;
@@ -695,8 +696,16 @@ int mv_k2_profile_begin(int capacity) {
   pr.count = 0;
   pr.capacity = capacity;
   pr.ev.resize((size_t)2 * capacity);
+  pr.dims.assign((size_t)3 * capacity, 0);
   for (auto& e : pr.ev) MV_CUDA(cudaEventCreate(&e));
   return MV_OK;
+}
+
+int mv_k2_profile_dims(int* nmc_out, int max_n) {
+  K2Profile& pr = g_k2_prof;
+  const int n = pr.count < max_n ? pr.count : max_n;
+  for (int i = 0; i < 3 * n; ++i) nmc_out[i] = pr.dims[i];
+  return n;
 }
 
 int mv_k2_profile_read(float* ms_out, int max_n) {
@@ -815,6 +824,9 @@ int mv_k2_affinity(const void* A, int lda, const void* B, int ldb, int n_max, in
   if (rc) return rc;
   if (timed) {
     MV_CUDA(cudaEventRecord(pr.ev[2 * pr.count + 1], st));
+    pr.dims[3 * pr.count] = n_max;
+    pr.dims[3 * pr.count + 1] = m_max;
+    pr.dims[3 * pr.count + 2] = C;
     ++pr.count;
   }
   const int mt = 256;

@@ -336,6 +336,8 @@ class GraphedPairMatcher:
         return self._match_and_pack(s0, s1)
 
     def _match_and_pack(self, s0, s1):
+        self.lowrank_used = (s0.rows_lo is not None and s0.fshape == s1.fshape
+                             and C_.lowrank_applies(*s0.fshape, s0.n, s1.n, s0.mode))
         r = C_._match_sides(s0, s1, s0.n, s1.n, self.num_corr, self.ratio_test, n_dev=s0.n_dev, m_dev=s1.n_dev)
         if self.with_outputs:
             # the helper's return tuple + the live counts in one buffer of column blocks (mv_pack_matches):
@@ -473,7 +475,8 @@ class GraphedPairMatcher:
         # per image: (backproject) + compact + coords + chw_to_hwc + kernel 1; per pair: (centre: 2, pixel dots: 1) + kernel 2 (2) + ratio + top-k
         zero_copy = self.feat_layout == "hwc" and self.feat_dtype == torch.float32
         per_side = (5 if self.kind == "depth" else 4) - (1 if zero_copy else 0)
-        return 2 * per_side + 4 + (3 if C_._CFG["dtype"] != "bf16" else 0) + (1 if self.with_outputs else 0)
+        lowrank = 6 if getattr(self, "lowrank_used", False) else 0  # 2 unit-row launches, the Gram launch + its row merge, 2 builders
+        return 2 * per_side + 4 + (3 if C_._CFG["dtype"] != "bf16" else 0) + (1 if self.with_outputs else 0) + lowrank
 
 
 class PairPipeline:

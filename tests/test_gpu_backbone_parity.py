@@ -119,6 +119,32 @@ def test_navi_vit_features(mv, bb, models, dtype):
     assert min(r["common"]) >= 995, r
 
 
+def test_navi_vit_features_lowrank_forced(mv, bb, models):
+    """the low-rank proposal (kernel 2 over the 784 source pixels of the target, bicubic taps) is not the default at the
+    NAVI shape (no faster there), but it has to hold the same gates when switched on."""
+    mv.correspondence.set_match_precision(lowrank=1)
+    try:
+        r = run_kind(mv, bb, models, "navi", "f16")
+    finally:
+        mv.correspondence.set_match_precision(lowrank="auto")
+    print(f"NAVI-shaped, ViT features, low-rank proposal forced: {r}")
+    assert r["agg_pp"] <= 0.1 + 1e-6 and r["worst_pair_pp"] <= 0.2 + 1e-6, r
+    assert min(r["common"]) >= 995, r
+
+
+def test_scannet_resnet_features_dense_product(mv, bb, models):
+    """the ScanNet-shaped pairs with the low-rank proposal switched OFF (kernel 2 over the 2056 f16c columns, round 2's
+    first form): the same gates."""
+    mv.correspondence.set_match_precision(lowrank=0)
+    try:
+        r = run_kind(mv, bb, models, "scannet", "f16")
+    finally:
+        mv.correspondence.set_match_precision(lowrank="auto")
+    print(f"ScanNet-shaped, ResNet features, dense f16c product: {r}")
+    assert r["agg_pp"] <= 0.1 + 1e-6 and r["worst_pair_pp"] <= 0.2 + 1e-6, r
+    assert min(r["common"]) >= 990, r
+
+
 @pytest.mark.parametrize("dtype", ["f16", "tf32"])
 def test_scannet_resnet_features(mv, bb, models, dtype):
     """the centred operand forms (f16c, the default, and tf32c) on all-positive, nearly collinear CNN features."""

@@ -1,0 +1,133 @@
+"""The low-rank proposal operands of kernel 2 (csrc/lr_gram.cu): the product of the fp16 operand rows over the target
+image's SOURCE PIXELS must reproduce the cosine similarity of the reference's interpolated, normalised rows
+(correspondence.py:164-176 / :240-241 + :47-48), most precisely where a row's best columns are; and the dense helpers must
+return the reference's matches when kernel 2 ranks that product instead of the C-channel one."""
+import importlib
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import restated
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def lowrank_on(mv):
+    C_ = mv.correspondence
+    C_.set_match_precision(lowrank=1)
+    yield
+    C_.set_match_precision(lowrank="auto")
+
+
+def sides(mv, kind, p):
+    C_ = mv.correspondence
+    L = mv._lib
+    dev = torch.device("cuda")
+    if kind == "depth":
+        Kc = p["K"].float()
+        Kh, Kinv = C_._host_mat(Kc), C_._host_mat(Kc.inverse())
+        s0 = C_.prepare_depth_side(p["feat_0"].cuda(), p["depth_0"], Kh, Kinv, dev)
+        s1 = C_.prepare_depth_side(p["feat_1"].cuda(), p["depth_1"], Kh, Kinv, dev)
+        f0 = restated.depth_side(p["feat_0"], p["depth_0"], p["K"])[1]
+        f1 = restated.depth_side(p["feat_1"], p["depth_1"], p["K"])[1]
+    else:
+        s0 = C_.prepare_xyz_side(p["feat_0"].cuda(), p["xyz_grid_0"], dev)
+        s1 = C_.prepare_xyz_side(p["feat_1"].cuda(), p["xyz_grid_1"], dev)
+        f0 = restated.xyz_side(p["feat_0"], p["xyz_grid_0"])[1]
+        f1 = restated.xyz_side(p["feat_1"], p["xyz_grid_1"])[1]
+    return s0, s1, f0, f1
+
+
+@pytest.mark.parametrize("kind,shape", [("depth", dict(C=256, h=15, w=20, H=60, W=80)), ("depth", dict(C=64, h=7, w=9, H=40, W=52)),
+                                        ("xyz", dict(C=256, h=14, w=14, H=56, W=56, radius=22.0)),
+                                        ("xyz", dict(C=128, h=9, w=11, H=36, W=44, radius=15.0))])
+def test_operand_product_equals_the_cosine_similarity(mv, syn, kind, shape):
+    C_ = mv.correspondence
+    p = syn.scannet_pair(3, **shape) if kind == "depth" else syn.navi_pair(3, **shape)
+    s0, s1, f0, f1 = sides(mv, kind, p)
+    n, m = f0.shape[0], f1.shape[0]
+    assert (s0.n, s1.n) == (n, m)
+    A, B, K = C_._lowrank_operands(s0, s1, n, m, None, None)
+    torch.cuda.synchronize()
+    h, w = shape["h"], shape["w"]
+    hw = h * w
+    hwp = (hw + 7) // 8 * 8
+    assert K == hwp + 8
+    A, B = A[:, :K].float().cpu().double(), B[:, :K].float().cpu().double()
+    S = A @ B.t()
+    a, b = F.normalize(f0, dim=-1).double(), F.normalize(f1, dim=-1).double()
+    S_ref = a @ b.t()
+    err = (S - S_ref).abs()
+    # fp16 operands: 2^-11 relative on entries of magnitude <= 1, a handful of terms per product
+    assert err.max() < 2e-3, float(err.max())
+    # ... and far better where it matters: at every row's two best columns (the row is centred on its maximum)
+    top = torch.topk(S_ref, 2, dim=1).indices
+    assert err.gather(1, top).max() < 2e-4, float(err.gather(1, top).max())
+    # structure: a target row has at most 4 (bilinear) / 16 (bicubic) non-zeros among the source-pixel columns, zeros in the
+    # padding, and two augmentation columns that add up to the row sum; a query row's augmentation columns repeat its centre
+    nnz = (B[:, :hwp] != 0).sum(1)
+    assert int(nnz.max()) <= (4 if kind == "depth" else 16)
+    assert (B[:, hw:hwp] == 0).all() and (A[:, hw:hwp] == 0).all()
+    assert ((B[:, hwp] + B[:, hwp + 1]) - B[:, :hw].sum(1)).abs().max() < 2e-3
+    assert torch.equal(A[:, hwp], A[:, hwp + 1]) and (A[:, hwp + 2:] == 0).all() and (B[:, hwp + 2:] == 0).all()
+    assert (A[:, :hw].max(1).values.abs() < 1e-3).all()  # centred on the row maximum
+
+
+@pytest.mark.parametrize("kind", ["depth", "xyz"])
+def test_helpers_with_the_lowrank_proposal_match_the_oracle(mv, syn, lowrank_on, kind):
+    """small pairs through the public helpers with the low-rank proposal forced on: the reference's matches"""
+    C_ = mv.correspondence
+    for seed in range(3):
+        if kind == "depth":
+            p = syn.scannet_pair(seed, C=256, h=15, w=20, H=60, W=80)
+            got = C_.estimate_correspondence_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], p["K"].clone(), 500)
+            ref = restated.estimate_correspondence_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], p["K"].clone(), 500)
+        else:
+            p = syn.navi_pair(seed, C=256, h=14, w=14, H=56, W=56, radius=22.0)
+            got = C_.estimate_correspondence_xyz(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], 500)
+            ref = restated.estimate_correspondence_xyz(p["feat_0"], p["feat_1"], p["xyz_grid_0"], p["xyz_grid_1"], 500)
+        gset = {tuple(a.tolist()) + tuple(b.tolist()) for a, b in zip(got[0].cpu(), got[1].cpu())}
+        rset = {tuple(a.tolist()) + tuple(b.tolist()) for a, b in zip(ref[0], ref[1])}
+        assert len(gset & rset) >= 495, (kind, seed, len(gset & rset))
+        # the ratio weights of the selected matches: equal, except where a row's SECOND candidate is a near-tie of the
+        # third (the weight then moves by that gap; the match itself is the same)
+        diff = (torch.sort(got[2].cpu()).values - torch.sort(ref[2]).values).abs()
+        assert int((diff > 2e-5).sum()) <= 5 and float(diff.max()) < 5e-3, (kind, seed, float(diff.max()))
+
+
+def test_lowrank_is_the_default_where_it_pays(mv):
+    C_ = mv.correspondence
+    assert C_._CFG["lowrank"] == "auto"
+    assert C_.lowrank_applies(2048, 15, 20, 19200, 19200)            # ScanNet-shaped: 312 columns instead of 2056
+    assert not C_.lowrank_applies(3072, 28, 28, 12544, 12544)        # NAVI-shaped: the dense product stays
+    assert not C_.lowrank_applies(768, 14, 14, 196, 20)              # small problems
+
+
+def test_full_size_scannet_pair_same_result_with_and_without(mv, syn):
+    """ScanNet-shaped Gaussian pair at full size: the default (low-rank proposal) and the C-channel product give the same
+    selected matches (up to ties: >= 995 of 1000) and the helper's neighbour indices agree wherever the reference gap is clear."""
+    C_ = mv.correspondence
+    p = syn.scannet_pair(5)
+    out = {}
+    for lr in ("auto", 0):
+        C_.set_match_precision(lowrank=lr)
+        try:
+            out[lr] = C_.estimate_correspondence_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], p["K"].clone(), 1000)
+        finally:
+            C_.set_match_precision(lowrank="auto")
+    a = {tuple(x.tolist()) + tuple(y.tolist()) for x, y in zip(out["auto"][0].cpu(), out["auto"][1].cpu())}
+    b = {tuple(x.tolist()) + tuple(y.tolist()) for x, y in zip(out[0][0].cpu(), out[0][1].cpu())}
+    assert len(a & b) >= 995, len(a & b)
+    # north-star rule on the proposal itself: the nearest neighbour of every row whose reference fp32 top-2 gap exceeds 1e-3
+    s0, s1, f0, f1 = sides(mv, "depth", p)
+    assert C_.lowrank_applies(*s0.fshape, s0.n, s1.n, s0.mode)
+    r = C_._match_sides(s0, s1, s0.n, s1.n, 1000)
+    o = restated.similarity_top2_and_mutual(f0, f1)
+    clear = o["row_gap"] > 1e-3
+    assert float(clear.float().mean()) > 0.5
+    assert torch.equal(r.row_idx[:, 0].cpu().long()[clear], o["row_idx"][clear, 0])
+    cclear = o["col_gap"] > 1e-3  # and the mutual flag wherever both the row's and its column's decision are clear
+    both = clear & cclear[o["row_idx"][:, 0]]
+    assert torch.equal(r.mutual.cpu().bool()[both], o["mutual"][both])
