@@ -198,21 +198,40 @@ int mv_rows_center(const float* rows, int C, int n_max, const int32_t* n_dev, in
  *   mv_lr_unit_rows    U (hw, C) fp16 = src / |src| per source pixel, snorm (hw) = |src|; src (hw, C) fp32 channel-last.
  *                      The caller stacks both images' U (image k at row offset off_k, pad rows zero) and obtains the
  *                      stacked cosine Gram matrix G (fp32, pitch ld_g) from mv_k2_affinity(U, U).
+ *   mv_lr_gram_exact   the other source of G: the Gram matrix of the RAW source rows of both images stacked (image 1 at row /
+ *                      column offset hwp), (2 hwp, ld_g) fp32, computed on the CUDA cores with blocked fp32 accumulation
+ *                      (16 slices of C / 16 channels per entry, fixed-order tree: ~1 ulp, deterministic; C % 64 == 0), plus
+ *                      snorm / rsnorm (2 hwp): |src[p]| and its reciprocal from the diagonal.  Exact enough for kernel 3
+ *                      (mv_k3_ratio_mutual_lr); the tensor-core Gram is not (tcgen05 accumulates with truncation).
  *   mv_lr_build_query  A_f16 (n, pitch): [fp16(A[i,:] - c_i) (hw) | 0 (to hwp) | c_i, c_i, 0 x 6], c_i = fp16(max_t A[i,t])
  *                      (centring a row on its own maximum keeps the fp16 rounding error of the columns that compete for
  *                      the row's top-2 at ~1e-6, also on nearly collinear CNN features).
  *   mv_lr_build_target B_f16 (m, pitch): [fp16(B[j,:]) scattered into zeros | two fp16 pieces of beta_j = sum_t B[j,t], 0 x 6]
  * so that the product of an A row and a B row over hwp + 8 columns is cos(x_i, y_j) up to the fp16 rounding of A - c and B.
  * coords (n, 2): the continuous source coordinates kernel 1 samples at (mv_geom_project_coords / mv_geom_grid_coords);
- * mode: MV_SAMPLE_BILINEAR_ZEROS or MV_SAMPLE_BICUBIC_CLAMP (the taps of kernel 1); snorm, off_own: this image's |src| and
- * its offset in G; off_tgt: the target image's offset in G.  The product only PROPOSES a row's two candidates: kernel 3
- * recomputes their fp32 distances from the exact rows. */
+ * mode: MV_SAMPLE_BILINEAR_ZEROS or MV_SAMPLE_BICUBIC_CLAMP (the taps of kernel 1); off_own / off_tgt: this image's and the
+ * target image's offset in G.  Scales, by the kind of G:   cosine Gram of unit rows: tapscale = this image's snorm, query
+ * colscale = NULL;   raw Gram: tapscale = NULL, query colscale = the target's rsnorm.  The target's snorm argument is the
+ * target image's |src| in both cases.  inv_norm_out (optional, n floats): 1 / max(|x_i|, 1e-12) of every point.
+ *   mv_k3_ratio_mutual_lr  kernel 3's ratio / mutual step on the raw Gram: the fp32 cosine distances of every query's two
+ *                      candidates (row_idx from kernel 2) as 1 - (sum_{a,b} W0[i,a] W1[j,b] G[off_q + s_a, off_t + t_b]) inv_q[i] inv_t[j]
+ *                      -- 16 (bilinear) / 256 (bicubic) Gram entries per candidate instead of three C-long rows -- then exactly
+ *                      mv_k3_ratio_mutual's outputs (correspondence.py:53-58, :72-77, :105-121).  With it the interpolated
+ *                      rows are never materialised: kernel 1 does not run. */
 #define MV_LR_MAX_SOURCE_PIXELS 1024
 int mv_lr_unit_rows(const float* src_hwc, int C, int hw, void* U_f16, float* snorm, mv_stream_t stream);
-int mv_lr_build_query(int mode, const float* coords, const int32_t* n_dev, int n_max, int h, int w, const float* snorm,
-                      const float* G, int ld_g, int off_own, int off_tgt, void* A_f16, int pitch, int hwp, mv_stream_t stream);
-int mv_lr_build_target(int mode, const float* coords, const int32_t* n_dev, int n_max, int h, int w, const float* snorm,
-                       const float* G, int ld_g, int off_own, void* B_f16, int pitch, int hwp, mv_stream_t stream);
+int mv_lr_gram_exact(const float* src0_hwc, const float* src1_hwc, int C, int hw, int hwp, float* G, int ld_g, float* snorm,
+                     float* rsnorm, mv_stream_t stream);
+int mv_lr_build_query(int mode, const float* coords, const int32_t* n_dev, int n_max, int h, int w, const float* tapscale,
+                      const float* colscale, const float* G, int ld_g, int off_own, int off_tgt, void* A_f16, int pitch, int hwp,
+                      float* inv_norm_out, mv_stream_t stream);
+int mv_lr_build_target(int mode, const float* coords, const int32_t* n_dev, int n_max, int h, int w, const float* tapscale,
+                       const float* snorm, const float* G, int ld_g, int off_own, void* B_f16, int pitch, int hwp,
+                       float* inv_norm_out, mv_stream_t stream);
+int mv_k3_ratio_mutual_lr(int mode, const float* coords_q, const float* coords_t, const float* inv_q, const float* inv_t,
+                          const float* G, int ld_g, int off_q, int off_t, int h, int w, const int32_t* n_dev, int n_max,
+                          int32_t* row_idx, const unsigned long long* col_best, int ratio_test, float* dists, float* weight,
+                          uint8_t* mutual, mv_stream_t stream);
 
 /* ---- kernel 2: similarity GEMM with fused row top-2 / column arg-max (tensor-core bound) -- */
 /* S = A @ B^T (n x m, never written).  Replaces faiss GpuIndexFlatL2.search(k<=2)

@@ -55,6 +55,10 @@ _CFG = {
     # proposal"): "auto" = where it pays (dense helpers, fp16 operands, h*w + 8 <= C / 5 and a large similarity matrix: the
     # ScanNet-shaped pairs, 312 instead of 2056 columns), "1" = wherever it applies, "0" = never
     "lowrank": os.environ.get("MVMATCH_LOWRANK", "auto"),
+    # with the low-rank proposal: 1 = kernel 3's two distances per query also come from the (exact, CUDA-core fp32) Gram matrix
+    # of the source pixels (mv_lr_gram_exact + mv_k3_ratio_mutual_lr) and the interpolated rows are never materialised
+    # (no kernel 1); 0 = kernel 1 writes the row planes and kernel 3 reads them, as for the dense product
+    "lowrank_k3": os.environ.get("MVMATCH_LOWRANK_K3", "1"),
 }
 _HELPER_GRAPHS = {}  # (kind, shapes, num_corr, ratio_test, dtype, cluster, K bytes) -> evaluation.GraphedPairMatcher
 _HELPER_GRAPHS_MAX = 12
@@ -64,7 +68,7 @@ _HELPER_GRAPHS_MAX = 12
 _PROFILE = {}
 
 
-def set_match_precision(dtype=None, cluster=None, helper_graphs=None, rows=None, k1_grid=None, lowrank=None):
+def set_match_precision(dtype=None, cluster=None, helper_graphs=None, rows=None, k1_grid=None, lowrank=None, lowrank_k3=None):
     """Choose kernel 2's operand type ("f16" | "bf16" | "tf32"), its cluster width (1, 2 or 4), whether the dense
     helpers replay cached CUDA graphs for host-tensor calls, and the row format between kernels 1 and 3
     ("split" | "f32", see _CFG)."""
@@ -74,6 +78,8 @@ def set_match_precision(dtype=None, cluster=None, helper_graphs=None, rows=None,
         if str(lowrank) not in ("auto", "0", "1"):
             raise ValueError("lowrank must be 'auto', 0 or 1")
         _CFG["lowrank"] = str(lowrank)
+    if lowrank_k3 is not None:
+        _CFG["lowrank_k3"] = "1" if int(lowrank_k3) else "0"
     if rows is not None:
         if rows not in ("split", "f32"):
             raise ValueError("rows must be 'split' or 'f32'")
@@ -620,16 +626,37 @@ def lowrank_applies(C, h, w, n_max, m_max, mode=L.MV_SAMPLE_BILINEAR_ZEROS):
     return (hwp + 8) * 5 <= C and n_max * m_max >= (1 << 24)
 
 
-def _lowrank_operands(s0, s1, n, m, n_dev, m_dev):
+def lowrank_exact_applies(C, h, w, n_max, m_max, mode=L.MV_SAMPLE_BILINEAR_ZEROS):
+    """whether a dense helper runs WITHOUT kernel 1: low-rank proposal + kernel 3 on the exact Gram matrix of the source pixels."""
+    return _CFG["lowrank_k3"] == "1" and C % 64 == 0 and _CFG["rows"] == "split" and lowrank_applies(C, h, w, n_max, m_max, mode)
+
+
+def _lowrank_operands(s0, s1, n, m, n_dev, m_dev, exact=False):
     """fp16 operands of kernel 2 in the basis of the target image's source pixels (csrc/lr_gram.cu):
     unit source rows of both images -> their stacked cosine Gram matrix (kernel 2 with the similarity written out) ->
-    query rows A' (n, P) and target rows B (m, P); returns (A', B, h*w padded + 8)."""
+    query rows A' (n, P) and target rows B (m, P); returns (A', B, h*w padded + 8).
+    exact=True: the Gram matrix of the RAW rows in fp32 from the CUDA cores instead (mv_lr_gram_exact); a fourth value is
+    returned with what mv_k3_ratio_mutual_lr needs (G, its pitch, the points' inverse norms)."""
     C, h, w = s0.fshape
     dev = s0.src.device
     st = _stream()
     hw = h * w
     hwp = (hw + 7) // 8 * 8
     P = L.f16c_pitch(hwp)
+    if exact:
+        G = _empty((2 * hwp, 2 * hwp), torch.float32, dev)
+        snorm = _empty((2 * hwp,), torch.float32, dev)
+        rsnorm = _empty((2 * hwp,), torch.float32, dev)
+        L.call("mv_lr_gram_exact", L.ptr(s0.src), L.ptr(s1.src), C, hw, hwp, L.ptr(G), 2 * hwp, L.ptr(snorm), L.ptr(rsnorm), st)
+        A_op = _empty((max(n, 1), P), torch.float16, dev)
+        B_op = _empty((max(m, 1), P), torch.float16, dev)
+        inv0 = _empty((max(n, 1),), torch.float32, dev)
+        inv1 = _empty((max(m, 1),), torch.float32, dev)
+        L.call("mv_lr_build_target", s1.mode, L.ptr(s1.coords), L.ptr(m_dev), m, h, w, None, c_void_p(snorm.data_ptr() + hwp * 4),
+               L.ptr(G), 2 * hwp, hwp, L.ptr(B_op), P, hwp, L.ptr(inv1), st)
+        L.call("mv_lr_build_query", s0.mode, L.ptr(s0.coords), L.ptr(n_dev), n, h, w, None, c_void_p(rsnorm.data_ptr() + hwp * 4),
+               L.ptr(G), 2 * hwp, 0, hwp, L.ptr(A_op), P, hwp, L.ptr(inv0), st)
+        return A_op, B_op, hwp + 8, {"G": G, "ld": 2 * hwp, "off_t": hwp, "inv0": inv0, "inv1": inv1, "keep": (snorm, rsnorm)}
     U = _empty((2 * hwp, C), torch.float16, dev)
     if hwp > hw:  # pad rows: zero Gram rows / columns
         U[hw:hwp].zero_()
@@ -647,16 +674,62 @@ def _lowrank_operands(s0, s1, n, m, n_dev, m_dev):
            2 * hwp, L.ptr(rv), L.ptr(ri), L.ptr(cb), L.ptr(ws), c_size_t(wsb), st)
     A_op = _empty((max(n, 1), P), torch.float16, dev)
     B_op = _empty((max(m, 1), P), torch.float16, dev)
-    L.call("mv_lr_build_target", s1.mode, L.ptr(s1.coords), L.ptr(m_dev), m, h, w, c_void_p(snorm.data_ptr() + hwp * 4), L.ptr(G),
-           2 * hwp, hwp, L.ptr(B_op), P, hwp, st)
-    L.call("mv_lr_build_query", s0.mode, L.ptr(s0.coords), L.ptr(n_dev), n, h, w, L.ptr(snorm), L.ptr(G), 2 * hwp, 0, hwp,
-           L.ptr(A_op), P, hwp, st)
+    sn1 = c_void_p(snorm.data_ptr() + hwp * 4)
+    L.call("mv_lr_build_target", s1.mode, L.ptr(s1.coords), L.ptr(m_dev), m, h, w, sn1, sn1, L.ptr(G),
+           2 * hwp, hwp, L.ptr(B_op), P, hwp, None, st)
+    L.call("mv_lr_build_query", s0.mode, L.ptr(s0.coords), L.ptr(n_dev), n, h, w, L.ptr(snorm), None, L.ptr(G), 2 * hwp, 0, hwp,
+           L.ptr(A_op), P, hwp, None, st)
     return A_op, B_op, hwp + 8
+
+
+def _match_lowrank_exact(s0, s1, n, m, num_corr, ratio_test=True, n_dev=None, m_dev=None, want_topk=True):
+    """one directional match WITHOUT interpolated rows: kernel 2 on the low-rank operands, kernel 3's distances from the exact
+    Gram matrix of the source pixels (mv_k3_ratio_mutual_lr), then the usual top-k.  Same MatchResult as match_rows."""
+    dev = s0.src.device
+    st = _stream()
+    A_op, B_op, Ck, x = _lowrank_operands(s0, s1, n, m, n_dev, m_dev, exact=True)
+    C, h, w = s0.fshape
+    res = MatchResult()
+    row_val = _empty((n, 2), torch.float32, dev)
+    row_idx = _empty((n, 2), torch.int32, dev)
+    col_best = _empty((m,), torch.int64, dev)
+    ws_bytes = L.load().mv_k2_workspace_bytes(n, m)
+    ws = _empty((ws_bytes,), torch.uint8, dev)
+    prof = _PROFILE.get("k2_events")
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    L.call("mv_k2_sim_top2_ld", L.ptr(A_op), A_op.shape[1], L.ptr(B_op), B_op.shape[1], n, m, Ck, L.ptr(n_dev), L.ptr(m_dev),
+           L.MV_DTYPE_F16, _CFG["cluster"], L.ptr(row_val), L.ptr(row_idx), L.ptr(col_best), L.ptr(ws), c_size_t(ws_bytes), st)
+    if prof is not None:
+        ev1.record()
+        prof.append((ev0, ev1, (n, m, Ck, n_dev, m_dev)))
+    dists = _empty((n, 2), torch.float32, dev)
+    weight = _empty((n,), torch.float32, dev)
+    mutual = _empty((n,), torch.uint8, dev)
+    L.call("mv_k3_ratio_mutual_lr", s0.mode, L.ptr(s0.coords), L.ptr(s1.coords), L.ptr(x["inv0"]), L.ptr(x["inv1"]), L.ptr(x["G"]),
+           x["ld"], 0, x["off_t"], h, w, L.ptr(n_dev), n, L.ptr(row_idx), L.ptr(col_best), int(ratio_test), L.ptr(dists),
+           L.ptr(weight), L.ptr(mutual), st)
+    res.row_idx, res.dists, res.weight, res.mutual, res.col_best = row_idx, dists, weight, mutual, col_best
+    if want_topk:
+        k = min(int(num_corr), n)
+        res.k = k
+        res.sel_src = _empty((max(k, 1),), torch.int32, dev)
+        res.sel_dst = _empty((max(k, 1),), torch.int32, dev)
+        res.sel_weight = _empty((max(k, 1),), torch.float32, dev)
+        res.k_dev = _empty((1,), torch.int32, dev)
+        L.call("mv_k3_topk_matches", L.ptr(weight), L.ptr(row_idx), L.ptr(n_dev), n, k, L.ptr(res.sel_src),
+               L.ptr(res.sel_dst), L.ptr(res.sel_weight), L.ptr(res.k_dev), st)
+    return res
 
 
 def _match_sides(s0, s1, n0, n1, num_corr, ratio_test=True, n_dev=None, m_dev=None):
     """s0 = query side, s1 = target side (prepared with the matching f16c roles, see _pair_maps)."""
     proposal = None
+    if s0.rows16 is None and s0.rows32 is None:  # prepared without rows (want_rows=False): the exact low-rank route
+        if not (s0.fshape == s1.fshape and s0.mode == s1.mode and s1.rows16 is None and s1.rows32 is None):
+            raise ValueError("sides prepared without rows need equal feature shapes and sampling modes")
+        return _match_lowrank_exact(s0, s1, n0, n1, num_corr, ratio_test, n_dev=n_dev, m_dev=m_dev)
     if (s0.src is not None and s1.src is not None and s0.fshape == s1.fshape and s0.mode == s1.mode and n0 > 0 and n1 > 0
             and s0.rows_lo is not None and lowrank_applies(*s0.fshape, n0, n1, s0.mode)):
         proposal = _lowrank_operands(s0, s1, n0, n1, n_dev, m_dev)
@@ -664,10 +737,15 @@ def _match_sides(s0, s1, n0, n1, num_corr, ratio_test=True, n_dev=None, m_dev=No
                       A_lo=s0.rows_lo, B_lo=s1.rows_lo, center_B=s1.center, proposal=proposal)
 
 
-def _pair_maps(feat_0, feat_1, dev):
+def _pair_maps(feat_0, feat_1, dev, grid_pixels=0, mode=None):
     """channel-last fp32 maps of both images + the f16c centre of the target image (None for the other operand types):
-    -> (fm0, fm1, kw0, kw1) where fm = (src, C, h, w) and kw are the role keywords of kernel 1 for each side."""
+    -> (fm0, fm1, kw0, kw1) where fm = (src, C, h, w) and kw are the role keywords of kernel 1 for each side.
+    grid_pixels / mode: upper bound of the point count per image and the sampling mode -- where the exact low-rank route
+    applies (lowrank_exact_applies) the sides are prepared WITHOUT rows (kw = want_rows False: no kernel 1, no centre)."""
     fm0, fm1 = _feature_map(feat_0, dev), _feature_map(feat_1, dev)
+    if (mode is not None and fm0[1:] == fm1[1:]
+            and lowrank_exact_applies(fm0[1], fm0[2], fm0[3], grid_pixels, grid_pixels, mode)):
+        return fm0, fm1, {"want_rows": False}, {"want_rows": False}
     if _CFG["dtype"] == "bf16":
         return fm0, fm1, {}, {}
     mu = _center(fm1[0], fm1[0].shape[0], step=_center_step(fm1[0].shape[0]))
@@ -700,7 +778,7 @@ def _stage_depth(depth_dev, Kinv):
 
 
 def _finish_depth(f, d, K, staged, n, synced, want_taps=False, rows=None, role=L.MV_ROLE_QUERY, center=None, dotvec=None,
-                  pixdot=None):
+                  pixdot=None, want_rows=True):
     """projection to feature-map coordinates + kernel 1 for the n (live or upper-bound) points of one image.
     f: the (C, h, w) feature map in either layout (see _feature_map), or the tuple _feature_map returned for it."""
     xyz_all, valid_idx, n_dev = staged
@@ -718,6 +796,10 @@ def _finish_depth(f, d, K, staged, n, synced, want_taps=False, rows=None, role=L
     s.taps = _empty((max(n, 1), 2), torch.int32, dev) if want_taps else None
     s.uv = None
     s.coords, s.mode, s.src, s.fshape = coords, L.MV_SAMPLE_BILINEAR_ZEROS, src, (C, h, w)
+    s.center = None
+    if not want_rows:  # the exact low-rank route: no interpolated rows at all
+        s.rows16 = s.rows32 = s.rows_lo = None
+        return s
     w16, w32, wlo = _row_format(rows)
     s.rows16, s.rows32, s.rows_lo = _sample(L.MV_SAMPLE_BILINEAR_ZEROS, src, C, h, w, coords, nd, n, True, w16, w32,
                                             s.taps, wlo, role=role, center=center, dotvec=dotvec, pixdot=pixdot)
@@ -748,7 +830,7 @@ def _stage_xyz(g):
 
 
 def _finish_xyz(f, g, staged, n, synced, want_taps=False, rows=None, role=L.MV_ROLE_QUERY, center=None, dotvec=None,
-                pixdot=None):
+                pixdot=None, want_rows=True):
     valid_idx, n_dev = staged
     dev = g.device
     src, C, h, w = f if isinstance(f, tuple) else _feature_map(f, dev)
@@ -764,6 +846,10 @@ def _finish_xyz(f, g, staged, n, synced, want_taps=False, rows=None, role=L.MV_R
                L.ptr(coords), _stream())
     s.taps = _empty((max(n, 1), 2), torch.int32, dev) if want_taps else None
     s.coords, s.mode, s.src, s.fshape = coords, L.MV_SAMPLE_BICUBIC_CLAMP, src, (C, h, w)
+    s.center = None
+    if not want_rows:  # the exact low-rank route: no interpolated rows at all
+        s.rows16 = s.rows32 = s.rows_lo = None
+        return s
     w16, w32, wlo = _row_format(rows)
     s.center = center
     if (_CFG["k1_grid"] and _CFG["dtype"] == "f16" and w16 and wlo and not w32 and not want_taps and n > 0
@@ -875,7 +961,7 @@ def _graphed_helper(kind, feat_0, feat_1, grid_0, grid_1, num_corr, ratio_test, 
     # pageable ones are staged by host threads, which the interleaved replay only delays (578 -> 458)
     split = on_host and bool(_CFG["helper_split"]) and feat_0.is_pinned() and feat_1.is_pinned()
     # the intrinsics are NOT part of the key: they live in device memory and are refreshed per call (gm.load)
-    key = (on_host, split, kind, tuple(feat_0.shape), tuple(grid_0.shape), int(num_corr), bool(ratio_test), _CFG["dtype"], _CFG["cluster"], _CFG["rows"], _CFG["k1_grid"], _CFG["lowrank"], fdt,
+    key = (on_host, split, kind, tuple(feat_0.shape), tuple(grid_0.shape), int(num_corr), bool(ratio_test), _CFG["dtype"], _CFG["cluster"], _CFG["rows"], _CFG["k1_grid"], _CFG["lowrank"], _CFG["lowrank_k3"], fdt,
            dev.index, layout)
     gm = _HELPER_GRAPHS.get(key)
     if gm is None:
@@ -934,7 +1020,7 @@ def estimate_correspondence_depth(feat_0, feat_1, depth_0, depth_1, K, num_corr=
     f0 = _upload_feat(feat_0, dev)
     f1, side = _on_side_stream(lambda: _upload_feat(feat_1, dev), dev)
     _join_side(side, dev, f1)  # the target's map is needed first: its centre goes into the query's rows (f16c)
-    fm0, fm1, kw0, kw1 = _pair_maps(f0, f1, dev)
+    fm0, fm1, kw0, kw1 = _pair_maps(f0, f1, dev, max(n0, n1), L.MV_SAMPLE_BILINEAR_ZEROS)
     side.wait_stream(torch.cuda.current_stream(dev))
     s0 = _finish_depth(fm0, d0, Kh, a0, n0, True, **kw0)
     with torch.cuda.stream(side):
@@ -962,7 +1048,7 @@ def estimate_correspondence_xyz(feat_0, feat_1, xyz_grid_0, xyz_grid_1, num_corr
     f0 = _upload_feat(feat_0, dev)
     f1, side = _on_side_stream(lambda: _upload_feat(feat_1, dev), dev)
     _join_side(side, dev, f1)  # the target's map is needed first: its centre goes into the query's rows (f16c)
-    fm0, fm1, kw0, kw1 = _pair_maps(f0, f1, dev)
+    fm0, fm1, kw0, kw1 = _pair_maps(f0, f1, dev, max(n0, n1), L.MV_SAMPLE_BICUBIC_CLAMP)
     side.wait_stream(torch.cuda.current_stream(dev))
     s0 = _finish_xyz(fm0, g0, a0, n0, True, **kw0)
     with torch.cuda.stream(side):

@@ -415,6 +415,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
         }
         // ---- rows: this thread's row against its running top-2.  Only groups of 8 columns whose maximum
         // beats the current second best are scanned (rare after the first tiles of a row block).
+#ifdef MV_K2_EXP_NO_ROWS
+        if (v[ch] > m2) { m2 = v[ch]; i2 = cb; }
+#else
         float g[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -437,7 +440,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
             }
           }
         }
+#endif
         // ---- columns: max over the warp's 32 rows and which row holds it
+#ifndef MV_K2_EXP_NO_COLS
 #pragma unroll
         for (int q = 0; q < 32; q += 2) {
           const float x0 = warp_max_f32(v[q]), x1 = warp_max_f32(v[q + 1]);
@@ -446,6 +451,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
           if (lane == 0)
             *reinterpret_cast<uint4*>(colw + ch * 32 + q) = make_uint4(__float_as_uint(x0), b0, __float_as_uint(x1), b1);
         }
+#endif
       }
       // accumulator drained: hand the TMEM buffer back to the MMA warp
       tc_fence_before();

@@ -17,8 +17,16 @@
 // makes A' smallest exactly where the competitive columns have their taps: the rounding error of the candidates that
 // decide a row's top-2 is ~1e-6 even on nearly collinear CNN features (tools/gram_sim.py: 996-1000 of 1000 matches in
 // common with the reference on ResNet-50 features, 1000 of 1000 on ViT features).
-// The product only PROPOSES the two candidates of a row; kernel 3 recomputes their fp32 distances from the exact rows
-// as before.
+// The product only PROPOSES the two candidates of a row; kernel 3 recomputes their fp32 distances.
+//
+// The exact route (mv_lr_gram_exact + mv_k3_ratio_mutual_lr): with the Gram matrix of the RAW source rows in fp32 (CUDA
+// cores, blocked accumulation: 16 slices of C / 16 channels per entry, fixed-order tree -- ~1 ulp, like kernel 3's own dot
+// products) the fp32 distances of the two candidates are
+//     1 - (sum_{a,b} W0[i,a] W1[j,b] G01[s_a,t_b]) / (|x_i| |y_j|),   |x_i|^2 = sum_{a,a'} W0[i,a] W0[i,a'] G00[s_a,s_a']
+// i.e. 16 (bilinear) / 256 (bicubic) terms per candidate instead of three C-long rows: the interpolated rows are never
+// materialised (no kernel 1, no row planes) -- SURVEY.md 8(f).2 taken to its end for the shapes where h*w << C.
+// (The tensor-core Gram cannot serve here: tcgen05 accumulates with truncation, measured -2.4e-6 .. -6.9e-6 of bias over
+// K = 2048-3072, tools/gram_probe.py.)  The builders then read the same raw Gram (tap scale 1, column scale 1 / |src1[t]|).
 #include <cuda_fp16.h>
 
 #include "common.cuh"
@@ -123,11 +131,15 @@ struct LrParams {
   const float* coords;     // (n, 2) continuous source coordinates (x, y) of every point: what kernel 1 samples at
   const int32_t* n_dev;
   int n_max, h, w, hw, hwp;
-  const float* snorm;      // (hw) |src[p]| of THIS image
-  const float* G;          // stacked cosine Gram of the unit source rows of both images, fp32, row pitch ld
+  const float* tapscale;   // (hw) or NULL (= 1): factor of a tap's blend weight in the basis G is written in -- |src[p]| of THIS
+                           // image for the cosine Gram of unit rows, NULL for the Gram of the raw rows
+  const float* colscale;   // query rows: (hw) or NULL (= 1) factor of column t -- 1 / |src1[t]| for the raw Gram.
+                           // target rows: (hw) |src1[p]|, the factor of the values written (B[j,t] = w |src1[t]| / |y_j|)
+  const float* G;          // stacked Gram matrix of the source rows of both images, fp32, row pitch ld
   int ld, off_own, off_tgt;  // row / column offset of this image's and of the target image's source pixels in G
   __half* out;             // (n, pitch) fp16 operand rows
   int pitch;
+  float* inv_out;          // (n) or NULL: 1 / max(|x_i|, eps) of every point (for mv_k3_ratio_mutual_lr)
 };
 
 // ---- target rows: fp16(B) scattered into a zero row + the two fp16 pieces of beta.  One warp per point.
@@ -142,9 +154,10 @@ __global__ void __launch_bounds__(256) lr_build_target_kernel(LrParams p) {
   int idx;
   float wt;
   lane_tap<MODE>(xy.x, xy.y, p.h, p.w, lane, idx, wt);
-  const float V = idx >= 0 ? wt * __ldg(p.snorm + idx) : 0.f;
+  const float V = idx >= 0 ? (p.tapscale ? wt * __ldg(p.tapscale + idx) : wt) : 0.f;
   const float inv = inv_norm_from_gram<T>(idx, V, p.G, p.ld, p.off_own, lane);
-  const float Vn = V * inv;
+  if (p.inv_out && lane == 0) p.inv_out[j] = inv;
+  const float Vn = idx >= 0 ? wt * __ldg(p.colscale + idx) * inv : 0.f;  // w |src1[t]| / |y_j|
   __half* row = p.out + (size_t)j * p.pitch;
   for (int c = lane * 8; c < p.pitch; c += 256) *reinterpret_cast<uint4*>(row + c) = make_uint4(0u, 0u, 0u, 0u);
   __syncwarp();
@@ -183,8 +196,9 @@ __global__ void __launch_bounds__(256) lr_build_query_kernel(LrParams p) {
   int idx;
   float wt;
   lane_tap<MODE>(xy.x, xy.y, p.h, p.w, lane, idx, wt);
-  const float V = idx >= 0 ? wt * __ldg(p.snorm + idx) : 0.f;
+  const float V = idx >= 0 ? (p.tapscale ? wt * __ldg(p.tapscale + idx) : wt) : 0.f;
   const float inv = inv_norm_from_gram<T>(idx, V, p.G, p.ld, p.off_own, lane);
+  if (p.inv_out && lane == 0) p.inv_out[i] = inv;
   const float Vn = V * inv;
   float2 acc[KT];
 #pragma unroll
@@ -202,6 +216,17 @@ __global__ void __launch_bounds__(256) lr_build_query_kernel(LrParams p) {
         const float2 v = __ldg(g + c2);
         acc[k].x = fmaf(va, v.x, acc[k].x);
         acc[k].y = fmaf(va, v.y, acc[k].y);
+      }
+    }
+  }
+  if (p.colscale) {
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      const int c2 = lane + 32 * k;
+      if (2 * c2 < p.hwp) {
+        const float2 cs = __ldg(reinterpret_cast<const float2*>(p.colscale) + c2);
+        acc[k].x *= cs.x;
+        acc[k].y *= cs.y;
       }
     }
   }
@@ -235,6 +260,181 @@ __global__ void __launch_bounds__(256) lr_build_query_kernel(LrParams p) {
   }
 }
 
+// ---- exact fp32 Gram of the raw source rows of both images stacked (image 1 at row / column offset hwp) ----------
+// One CTA per 32 x 32 tile of the upper block triangle (mirrored on the way out), 16 warps: warp w accumulates the
+// channels [w C/16, (w+1) C/16) of all 1024 entries (lane = 4 rows x 8 columns), the 16 partial sums meet in shared memory
+// and are added in a fixed tree.  Every entry is 16 chains of C/16 fused multiply-adds + 4 tree levels: ~1 ulp.
+constexpr int GX_TILE = 32, GX_WARPS = 16, GX_THREADS = GX_WARPS * 32;
+constexpr int GX_SMEM_BYTES = GX_WARPS * GX_TILE * GX_TILE * 4;  // 64 KB
+
+__global__ void __launch_bounds__(GX_THREADS, 1) lr_gram_exact_kernel(const float* __restrict__ src0, const float* __restrict__ src1,
+                                                                      int C, int hw, int hwp, float* __restrict__ G, int ld, int nt) {
+  extern __shared__ float gx_red[];  // [warp][row][col]
+  // tile pair (ti <= tj) of the upper block triangle from the linear block index
+  int ti = 0, rem = blockIdx.x;
+  while (rem >= nt - ti) {
+    rem -= nt - ti;
+    ++ti;
+  }
+  const int tj = ti + rem;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int ly = lane >> 2, lx = lane & 3;
+  auto row_ptr = [&](int r) -> const float* {  // stacked row r -> its C floats, or NULL for a pad row
+    if (r < hw) return src0 + (size_t)r * C;
+    if (r >= hwp && r < hwp + hw) return src1 + (size_t)(r - hwp) * C;
+    return nullptr;
+  };
+  const int slice = C / GX_WARPS, k_beg = wid * slice;
+  const float* ap[4];
+  const float* bp[8];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) ap[r] = row_ptr(ti * GX_TILE + 4 * ly + r);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) bp[c] = row_ptr(tj * GX_TILE + 8 * lx + c);
+  float acc[4][8];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+  for (int k = k_beg; k < k_beg + slice; k += 4) {
+    float4 a[4], b[8];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) a[r] = ap[r] ? __ldg(reinterpret_cast<const float4*>(ap[r] + k)) : z4;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) b[c] = bp[c] ? __ldg(reinterpret_cast<const float4*>(bp[c] + k)) : z4;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        acc[r][c] = fmaf(a[r].x, b[c].x, acc[r][c]);
+        acc[r][c] = fmaf(a[r].y, b[c].y, acc[r][c]);
+        acc[r][c] = fmaf(a[r].z, b[c].z, acc[r][c]);
+        acc[r][c] = fmaf(a[r].w, b[c].w, acc[r][c]);
+      }
+  }
+  float* mine = gx_red + (size_t)wid * GX_TILE * GX_TILE;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    float4* q = reinterpret_cast<float4*>(mine + (4 * ly + r) * GX_TILE + 8 * lx);
+    q[0] = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+    q[1] = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+  }
+  __syncthreads();
+  const int rows = 2 * hwp;
+  for (int o = threadIdx.x; o < GX_TILE * GX_TILE; o += GX_THREADS) {
+    float v[GX_WARPS];
+#pragma unroll
+    for (int q = 0; q < GX_WARPS; ++q) v[q] = gx_red[(size_t)q * GX_TILE * GX_TILE + o];
+#pragma unroll
+    for (int st = 1; st < GX_WARPS; st <<= 1)  // fixed tree: (0+1), (2+3), ... then pairs of pairs
+#pragma unroll
+      for (int q = 0; q < GX_WARPS; q += 2 * st) v[q] += v[q + st];
+    const int gi = ti * GX_TILE + o / GX_TILE, gj = tj * GX_TILE + o % GX_TILE;
+    if (gi < rows && gj < rows) {
+      G[(size_t)gi * ld + gj] = v[0];
+      G[(size_t)gj * ld + gi] = v[0];
+    }
+  }
+}
+
+// |src[p]| and 1 / |src[p]| of every stacked source row from the diagonal of the raw Gram (0 for pad / zero rows)
+__global__ void lr_diag_norms_kernel(const float* __restrict__ G, int ld, int rows, float* __restrict__ snorm, float* __restrict__ rsnorm) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float nrm = sqrtf(fmaxf(G[(size_t)r * ld + r], 0.f));
+  snorm[r] = nrm;
+  rsnorm[r] = nrm > 0.f ? 1.f / nrm : 0.f;
+}
+
+// ---- kernel 3 on the Gram matrix: the fp32 cosine distances of a query's two candidates from 16 / 256 entries of G01,
+// then exactly kernel 3's tail (k3_score.cu): fp32 order wins, ratio weight with both clamps, mutual flag.  One warp per query.
+constexpr float LR_RATIO_CLAMP = 1e-9f;   // calculate_ratio_test clamps (correspondence.py:105-121)
+constexpr float LR_MISSING_DIST = 2.0f;   // a candidate that does not exist (m < 2), as in k3_score.cu
+
+struct LrK3Params {
+  const float* coords_q;
+  const float* coords_t;
+  const float* inv_q;  // 1 / max(|x_i|, eps) from the builders
+  const float* inv_t;
+  const float* G;
+  int ld, off_q, off_t, h, w;
+  const int32_t* n_dev;
+  int n_max;
+  int32_t* row_idx;
+  const unsigned long long* col_best;
+  int ratio_test;
+  float* dists;
+  float* weight;
+  uint8_t* mutual;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) lr_k3_ratio_mutual_kernel(LrK3Params p) {
+  constexpr int T = MODE == MV_SAMPLE_BICUBIC_CLAMP ? 16 : 4;
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int n = p.n_dev ? min(*p.n_dev, p.n_max) : p.n_max;
+  if (i >= n) return;
+  const float2 xy = __ldg(reinterpret_cast<const float2*>(p.coords_q) + i);
+  int iq;
+  float wq;
+  lane_tap<MODE>(xy.x, xy.y, p.h, p.w, lane, iq, wq);
+  const float inv_i = __ldg(p.inv_q + i);
+  int js[2] = {p.row_idx[2 * (size_t)i], p.row_idx[2 * (size_t)i + 1]};
+  float d[2];
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    const int j = js[c];
+    if (j < 0) {  // warp-uniform
+      d[c] = LR_MISSING_DIST;
+      continue;
+    }
+    const float2 uv = __ldg(reinterpret_cast<const float2*>(p.coords_t) + j);
+    int it;
+    float wt;
+    lane_tap<MODE>(uv.x, uv.y, p.h, p.w, lane, it, wt);
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < (T * T + 31) / 32; ++k) {
+      const int q = lane + 32 * k;
+      const int a = (q / T) % T, b = q % T;
+      const float wa = __shfl_sync(0xffffffffu, wq, a), wb = __shfl_sync(0xffffffffu, wt, b);
+      const int ia = __shfl_sync(0xffffffffu, iq, a), ib = __shfl_sync(0xffffffffu, it, b);
+      if (q < T * T && ia >= 0 && ib >= 0) acc = fmaf(wa * wb, __ldg(p.G + (size_t)(p.off_q + ia) * p.ld + p.off_t + ib), acc);
+    }
+    acc = warp_sum(acc);
+    d[c] = 1.f - (acc * inv_i) * __ldg(p.inv_t + j);
+  }
+  if (lane != 0) return;
+  float d0 = d[0], d1 = d[1];
+  int j0 = js[0], j1 = js[1];
+  if (j1 >= 0 && (d1 < d0 || (d1 == d0 && j1 < j0))) {  // fp32 order wins over the tensor-core order
+    const float td = d0; d0 = d1; d1 = td;
+    const int tj = j0; j0 = j1; j1 = tj;
+    p.row_idx[2 * (size_t)i] = j0;
+    p.row_idx[2 * (size_t)i + 1] = j1;
+  }
+  if (p.dists) {
+    p.dists[2 * (size_t)i] = d0;
+    p.dists[2 * (size_t)i + 1] = d1;
+  }
+  if (p.weight) {
+    float wv = d0;
+    if (p.ratio_test) wv = 1.f - __fdiv_rn(fmaxf(d0, LR_RATIO_CLAMP), fmaxf(fmaxf(d1, LR_RATIO_CLAMP), LR_RATIO_CLAMP));
+    p.weight[i] = wv;
+  }
+  if (p.mutual) {
+    uint8_t f = 0;
+    if (p.col_best && j0 >= 0) {
+      const unsigned long long pk = p.col_best[j0];
+      f = (pk != 0ull && (0xffffffffu - (uint32_t)(pk & 0xffffffffull)) == (uint32_t)i) ? 1 : 0;
+    }
+    p.mutual[i] = f;
+  }
+}
+
 template <int MODE>
 int launch_query(const LrParams& p, cudaStream_t st) {
   const int grid = (p.n_max + 7) / 8;
@@ -247,10 +447,10 @@ int launch_query(const LrParams& p, cudaStream_t st) {
   return MV_OK;
 }
 
-int check_params(const char* who, int mode, const float* coords, int n_max, int h, int w, const float* snorm, const float* G,
+int check_params(const char* who, int mode, const float* coords, int n_max, int h, int w, const float* G,
                  int ld_g, int off_own, int off_tgt, const void* out, int pitch, int hwp) {
   MV_REQUIRE(mode == MV_SAMPLE_BILINEAR_ZEROS || mode == MV_SAMPLE_BICUBIC_CLAMP, MV_E_ARG, "%s: mode must be bilinear-zeros or bicubic-clamp", who);
-  MV_REQUIRE(coords && snorm && G && out, MV_E_ARG, "%s: null pointer", who);
+  MV_REQUIRE(coords && G && out, MV_E_ARG, "%s: null pointer", who);
   MV_REQUIRE(n_max > 0 && h > 0 && w > 0, MV_E_ARG, "%s: sizes must be positive", who);
   MV_REQUIRE(hwp >= h * w && hwp % 8 == 0 && hwp <= MV_LR_MAX_SOURCE_PIXELS, MV_E_RANGE,
              "%s: hwp=%d must be a multiple of 8 in [h*w, %d]", who, hwp, MV_LR_MAX_SOURCE_PIXELS);
@@ -275,23 +475,67 @@ int mv_lr_unit_rows(const float* src_hwc, int C, int hw, void* U_f16, float* sno
   return MV_OK;
 }
 
-int mv_lr_build_query(int mode, const float* coords, const int32_t* n_dev, int n_max, int h, int w, const float* snorm,
-                      const float* G, int ld_g, int off_own, int off_tgt, void* A_f16, int pitch, int hwp, mv_stream_t stream) {
-  int rc = check_params("mv_lr_build_query", mode, coords, n_max, h, w, snorm, G, ld_g, off_own, off_tgt, A_f16, pitch, hwp);
+int mv_lr_build_query(int mode, const float* coords, const int32_t* n_dev, int n_max, int h, int w, const float* tapscale,
+                      const float* colscale, const float* G, int ld_g, int off_own, int off_tgt, void* A_f16, int pitch, int hwp,
+                      float* inv_norm_out, mv_stream_t stream) {
+  int rc = check_params("mv_lr_build_query", mode, coords, n_max, h, w, G, ld_g, off_own, off_tgt, A_f16, pitch, hwp);
   if (rc) return rc;
-  LrParams p{coords, n_dev, n_max, h, w, h * w, hwp, snorm, G, ld_g, off_own, off_tgt, reinterpret_cast<__half*>(A_f16), pitch};
+  MV_REQUIRE(!colscale || ((uintptr_t)colscale & 7) == 0, MV_E_ALIGN, "mv_lr_build_query: colscale must be 8-byte aligned");
+  LrParams p{coords, n_dev, n_max, h, w, h * w, hwp, tapscale, colscale, G, ld_g, off_own, off_tgt, reinterpret_cast<__half*>(A_f16),
+             pitch, inv_norm_out};
   return mode == MV_SAMPLE_BICUBIC_CLAMP ? launch_query<MV_SAMPLE_BICUBIC_CLAMP>(p, mv_cuda_stream(stream))
                                          : launch_query<MV_SAMPLE_BILINEAR_ZEROS>(p, mv_cuda_stream(stream));
 }
 
-int mv_lr_build_target(int mode, const float* coords, const int32_t* n_dev, int n_max, int h, int w, const float* snorm,
-                       const float* G, int ld_g, int off_own, void* B_f16, int pitch, int hwp, mv_stream_t stream) {
-  int rc = check_params("mv_lr_build_target", mode, coords, n_max, h, w, snorm, G, ld_g, off_own, off_own, B_f16, pitch, hwp);
+int mv_lr_build_target(int mode, const float* coords, const int32_t* n_dev, int n_max, int h, int w, const float* tapscale,
+                       const float* snorm, const float* G, int ld_g, int off_own, void* B_f16, int pitch, int hwp,
+                       float* inv_norm_out, mv_stream_t stream) {
+  int rc = check_params("mv_lr_build_target", mode, coords, n_max, h, w, G, ld_g, off_own, off_own, B_f16, pitch, hwp);
   if (rc) return rc;
-  LrParams p{coords, n_dev, n_max, h, w, h * w, hwp, snorm, G, ld_g, off_own, off_own, reinterpret_cast<__half*>(B_f16), pitch};
+  MV_REQUIRE(snorm, MV_E_ARG, "mv_lr_build_target: null snorm");
+  LrParams p{coords, n_dev, n_max, h, w, h * w, hwp, tapscale, snorm, G, ld_g, off_own, off_own, reinterpret_cast<__half*>(B_f16),
+             pitch, inv_norm_out};
   const int grid = (n_max + 7) / 8;
   if (mode == MV_SAMPLE_BICUBIC_CLAMP) lr_build_target_kernel<MV_SAMPLE_BICUBIC_CLAMP><<<grid, 256, 0, mv_cuda_stream(stream)>>>(p);
   else lr_build_target_kernel<MV_SAMPLE_BILINEAR_ZEROS><<<grid, 256, 0, mv_cuda_stream(stream)>>>(p);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+int mv_lr_gram_exact(const float* src0_hwc, const float* src1_hwc, int C, int hw, int hwp, float* G, int ld_g, float* snorm,
+                     float* rsnorm, mv_stream_t stream) {
+  MV_REQUIRE(src0_hwc && src1_hwc && G && snorm && rsnorm, MV_E_ARG, "mv_lr_gram_exact: null pointer");
+  MV_REQUIRE(C > 0 && C % 64 == 0, MV_E_ALIGN, "mv_lr_gram_exact: C=%d must be a positive multiple of 64", C);
+  MV_REQUIRE(hw > 0 && hwp >= hw && hwp % 8 == 0 && hwp <= MV_LR_MAX_SOURCE_PIXELS && ld_g >= 2 * hwp, MV_E_RANGE,
+             "mv_lr_gram_exact: need hw <= hwp <= %d, hwp a multiple of 8, ld_g >= 2 hwp", MV_LR_MAX_SOURCE_PIXELS);
+  MV_REQUIRE((((uintptr_t)src0_hwc | (uintptr_t)src1_hwc) & 15) == 0, MV_E_ALIGN, "mv_lr_gram_exact: maps must be 16-byte aligned");
+  static bool done[MV_MAX_DEVICES];
+  bool& attr_done = done[mv_device_slot()];
+  if (!attr_done) {
+    MV_CUDA(cudaFuncSetAttribute(lr_gram_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GX_SMEM_BYTES));
+    attr_done = true;
+  }
+  const int nt = (2 * hwp + GX_TILE - 1) / GX_TILE;
+  cudaStream_t st = mv_cuda_stream(stream);
+  lr_gram_exact_kernel<<<nt * (nt + 1) / 2, GX_THREADS, GX_SMEM_BYTES, st>>>(src0_hwc, src1_hwc, C, hw, hwp, G, ld_g, nt);
+  MV_LAUNCH_CHECK();
+  lr_diag_norms_kernel<<<(2 * hwp + 255) / 256, 256, 0, st>>>(G, ld_g, 2 * hwp, snorm, rsnorm);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
+int mv_k3_ratio_mutual_lr(int mode, const float* coords_q, const float* coords_t, const float* inv_q, const float* inv_t,
+                          const float* G, int ld_g, int off_q, int off_t, int h, int w, const int32_t* n_dev, int n_max,
+                          int32_t* row_idx, const unsigned long long* col_best, int ratio_test, float* dists, float* weight,
+                          uint8_t* mutual, mv_stream_t stream) {
+  MV_REQUIRE(mode == MV_SAMPLE_BILINEAR_ZEROS || mode == MV_SAMPLE_BICUBIC_CLAMP, MV_E_ARG, "mv_k3_ratio_mutual_lr: bad mode");
+  MV_REQUIRE(coords_q && coords_t && inv_q && inv_t && G && row_idx, MV_E_ARG, "mv_k3_ratio_mutual_lr: null pointer");
+  MV_REQUIRE(n_max >= 0 && h > 0 && w > 0 && ld_g > 0 && off_q >= 0 && off_t >= 0, MV_E_ARG, "mv_k3_ratio_mutual_lr: bad sizes");
+  if (n_max == 0) return MV_OK;
+  LrK3Params p{coords_q, coords_t, inv_q, inv_t, G, ld_g, off_q, off_t, h, w, n_dev, n_max, row_idx, col_best, ratio_test, dists, weight, mutual};
+  const int grid = (n_max + 7) / 8;
+  if (mode == MV_SAMPLE_BICUBIC_CLAMP) lr_k3_ratio_mutual_kernel<MV_SAMPLE_BICUBIC_CLAMP><<<grid, 256, 0, mv_cuda_stream(stream)>>>(p);
+  else lr_k3_ratio_mutual_kernel<MV_SAMPLE_BILINEAR_ZEROS><<<grid, 256, 0, mv_cuda_stream(stream)>>>(p);
   MV_LAUNCH_CHECK();
   return MV_OK;
 }

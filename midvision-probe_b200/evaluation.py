@@ -204,7 +204,7 @@ def match_and_score_depth(feat_0, feat_1, depth_0, depth_1, K, Rt, num_corr, acc
     dev = C_._device()
     Kc = K.detach().float().cpu()
     Kh, Kinv = C_._host_mat(Kc), C_._host_mat(Kc.inverse())
-    fm0, fm1, kw0, kw1 = C_._pair_maps(feat_0, feat_1, dev)
+    fm0, fm1, kw0, kw1 = C_._pair_maps(feat_0, feat_1, dev, depth_0.shape[-2] * depth_0.shape[-1], L.MV_SAMPLE_BILINEAR_ZEROS)
     s0, s1 = _both_sides(lambda: C_.prepare_depth_side(fm0, depth_0, Kh, Kinv, dev, sync=sync, **kw0),
                          lambda: C_.prepare_depth_side(fm1, depth_1, Kh, Kinv, dev, sync=sync, **kw1), dev)
     r = C_._match_sides(s0, s1, s0.n, s1.n, num_corr, n_dev=None if sync else s0.n_dev, m_dev=None if sync else s1.n_dev)
@@ -216,7 +216,7 @@ def match_and_score_xyz(feat_0, feat_1, xyz_grid_0, xyz_grid_1, intrinsics, Rt, 
     """NAVI-shaped pair: estimate_correspondence_xyz (correspondence.py:235-263) + the caller's error /
     recall block (evaluate_navi_correspondence.py:186-212)."""
     dev = C_._device()
-    fm0, fm1, kw0, kw1 = C_._pair_maps(feat_0, feat_1, dev)
+    fm0, fm1, kw0, kw1 = C_._pair_maps(feat_0, feat_1, dev, xyz_grid_0.shape[-2] * xyz_grid_0.shape[-1], L.MV_SAMPLE_BICUBIC_CLAMP)
     s0, s1 = _both_sides(lambda: C_.prepare_xyz_side(fm0, xyz_grid_0, dev, sync=sync, **kw0),
                          lambda: C_.prepare_xyz_side(fm1, xyz_grid_1, dev, sync=sync, **kw1), dev)
     r = C_._match_sides(s0, s1, s0.n, s1.n, num_corr, n_dev=None if sync else s0.n_dev, m_dev=None if sync else s1.n_dev)
@@ -309,9 +309,20 @@ class GraphedPairMatcher:
         Kd, Kinvd = L.ptr(self.Kdev), c_void_p(self.Kdev.data_ptr() + 36)
         return C_.prepare_depth_side(fm, g, Kd, Kinvd, self.dev, sync=False, **kw)
 
+    def _exact(self):
+        """the exact low-rank route (no kernel 1) for this matcher's shapes?"""
+        C, h, w = self.f0.shape
+        gp = self.g0.shape[-2] * self.g0.shape[-1]
+        mode = L.MV_SAMPLE_BICUBIC_CLAMP if self.kind == "xyz" else L.MV_SAMPLE_BILINEAR_ZEROS
+        return C_.lowrank_exact_applies(C, h, w, gp, gp, mode)
+
     def _body_target(self):
         """graph 1 of the split form: everything that needs only the TARGET image (image 1)."""
         fm1 = C_._feature_map(self.f1, self.dev)
+        if self._exact():
+            self._mu = None
+            self._s1 = self._prepare(fm1, self.g1, {"want_rows": False})
+            return
         f16 = C_._CFG["dtype"] != "bf16"  # f16c and tf32c rows are centred on the target
         self._mu = C_._center(fm1[0], fm1[0].shape[0], step=C_._center_step(fm1[0].shape[0])) if f16 else None
         kw1 = {"role": L.MV_ROLE_TARGET, "center": self._mu} if f16 else {}
@@ -321,11 +332,15 @@ class GraphedPairMatcher:
         """graph 2 of the split form: the query image's side, kernels 2 and 3, the packed outputs."""
         fm0 = C_._feature_map(self.f0, self.dev)
         kw0 = {"role": L.MV_ROLE_QUERY, "dotvec": self._mu, "pixdot": C_._rows_dot(fm0[0], self._mu)} if self._mu is not None else {}
+        if self._exact():
+            kw0 = {"want_rows": False}
         s0, s1 = self._prepare(fm0, self.g0, kw0), self._s1
         return self._match_and_pack(s0, s1)
 
     def _body(self):
-        fm0, fm1, kw0, kw1 = C_._pair_maps(self.f0, self.f1, self.dev)
+        gp = self.g0.shape[-2] * self.g0.shape[-1]
+        fm0, fm1, kw0, kw1 = C_._pair_maps(self.f0, self.f1, self.dev, gp,
+                                           L.MV_SAMPLE_BICUBIC_CLAMP if self.kind == "xyz" else L.MV_SAMPLE_BILINEAR_ZEROS)
         if self.kind == "xyz":
             s0, s1 = _both_sides(lambda: C_.prepare_xyz_side(fm0, self.g0, self.dev, sync=False, **kw0),
                                  lambda: C_.prepare_xyz_side(fm1, self.g1, self.dev, sync=False, **kw1), self.dev)
@@ -336,7 +351,8 @@ class GraphedPairMatcher:
         return self._match_and_pack(s0, s1)
 
     def _match_and_pack(self, s0, s1):
-        self.lowrank_used = (s0.rows_lo is not None and s0.fshape == s1.fshape
+        self.lowrank_exact = s0.rows16 is None and s0.rows32 is None
+        self.lowrank_used = (not self.lowrank_exact and s0.rows_lo is not None and s0.fshape == s1.fshape
                              and C_.lowrank_applies(*s0.fshape, s0.n, s1.n, s0.mode))
         r = C_._match_sides(s0, s1, s0.n, s1.n, self.num_corr, self.ratio_test, n_dev=s0.n_dev, m_dev=s1.n_dev)
         if self.with_outputs:
@@ -475,6 +491,9 @@ class GraphedPairMatcher:
         # per image: (backproject) + compact + coords + chw_to_hwc + kernel 1; per pair: (centre: 2, pixel dots: 1) + kernel 2 (2) + ratio + top-k
         zero_copy = self.feat_layout == "hwc" and self.feat_dtype == torch.float32
         per_side = (5 if self.kind == "depth" else 4) - (1 if zero_copy else 0)
+        if getattr(self, "lowrank_exact", False):
+            # per image everything but kernel 1; per pair: exact Gram (2), 2 builders, kernel 2 (2), kernel 3 on the Gram, top-k
+            return 2 * (per_side - 1) + 8 + (1 if self.with_outputs else 0)
         lowrank = 6 if getattr(self, "lowrank_used", False) else 0  # 2 unit-row launches, the Gram launch + its row merge, 2 builders
         return 2 * per_side + 4 + (3 if C_._CFG["dtype"] != "bf16" else 0) + (1 if self.with_outputs else 0) + lowrank
 

@@ -145,6 +145,18 @@ def test_scannet_resnet_features_dense_product(mv, bb, models):
     assert min(r["common"]) >= 990, r
 
 
+def test_scannet_resnet_features_lowrank_with_row_planes(mv, bb, models):
+    """the low-rank proposal with kernel 3 on kernel 1's row planes (lowrank_k3=0) instead of the exact Gram matrix"""
+    mv.correspondence.set_match_precision(lowrank_k3=0)
+    try:
+        r = run_kind(mv, bb, models, "scannet", "f16")
+    finally:
+        mv.correspondence.set_match_precision(lowrank_k3=1)
+    print(f"ScanNet-shaped, ResNet features, low-rank proposal + row planes: {r}")
+    assert r["agg_pp"] <= 0.1 + 1e-6 and r["worst_pair_pp"] <= 0.2 + 1e-6, r
+    assert min(r["common"]) >= 990, r
+
+
 @pytest.mark.parametrize("dtype", ["f16", "tf32"])
 def test_scannet_resnet_features(mv, bb, models, dtype):
     """the centred operand forms (f16c, the default, and tf32c) on all-positive, nearly collinear CNN features."""

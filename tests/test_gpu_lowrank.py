@@ -43,13 +43,15 @@ def sides(mv, kind, p):
 @pytest.mark.parametrize("kind,shape", [("depth", dict(C=256, h=15, w=20, H=60, W=80)), ("depth", dict(C=64, h=7, w=9, H=40, W=52)),
                                         ("xyz", dict(C=256, h=14, w=14, H=56, W=56, radius=22.0)),
                                         ("xyz", dict(C=128, h=9, w=11, H=36, W=44, radius=15.0))])
-def test_operand_product_equals_the_cosine_similarity(mv, syn, kind, shape):
+@pytest.mark.parametrize("exact", [False, True])
+def test_operand_product_equals_the_cosine_similarity(mv, syn, kind, shape, exact):
+    """exact=False: cosine Gram of fp16 unit rows from kernel 2; exact=True: fp32 Gram of the raw rows from the CUDA cores"""
     C_ = mv.correspondence
     p = syn.scannet_pair(3, **shape) if kind == "depth" else syn.navi_pair(3, **shape)
     s0, s1, f0, f1 = sides(mv, kind, p)
     n, m = f0.shape[0], f1.shape[0]
     assert (s0.n, s1.n) == (n, m)
-    A, B, K = C_._lowrank_operands(s0, s1, n, m, None, None)
+    A, B, K = C_._lowrank_operands(s0, s1, n, m, None, None, exact=exact)[:3]
     torch.cuda.synchronize()
     h, w = shape["h"], shape["w"]
     hw = h * w
@@ -97,12 +99,71 @@ def test_helpers_with_the_lowrank_proposal_match_the_oracle(mv, syn, lowrank_on,
         assert int((diff > 2e-5).sum()) <= 5 and float(diff.max()) < 5e-3, (kind, seed, float(diff.max()))
 
 
+@pytest.mark.parametrize("C,h,w", [(2048, 15, 20), (256, 9, 7), (3072, 12, 12)])
+def test_exact_gram_is_fp32_exact(mv, C, h, w):
+    """mv_lr_gram_exact against an fp64 product: every entry to ~1 ulp (blocked fp32 accumulation), symmetric, pad rows zero,
+    snorm / rsnorm from the diagonal; bit-repeatable."""
+    from ctypes import c_void_p
+    L, C_ = mv._lib, mv.correspondence
+    g = torch.Generator().manual_seed(C + h)
+    hw = h * w
+    hwp = (hw + 7) // 8 * 8
+    # all-positive, nearly collinear rows (the CNN regime) and signed rows
+    s0 = (torch.rand(hw, C, generator=g) + 0.5).cuda()
+    s1 = torch.randn(hw, C, generator=g).cuda()
+    outs = []
+    for _ in range(2):
+        G = torch.full((2 * hwp, 2 * hwp), 7.0, device="cuda")
+        sn = torch.empty(2 * hwp, device="cuda")
+        rs = torch.empty(2 * hwp, device="cuda")
+        L.call("mv_lr_gram_exact", L.ptr(s0), L.ptr(s1), C, hw, hwp, L.ptr(G), 2 * hwp, L.ptr(sn), L.ptr(rs), C_._stream())
+        torch.cuda.synchronize()
+        outs.append(G)
+    assert torch.equal(outs[0], outs[1])
+    G = outs[0]
+    R = torch.zeros(2 * hwp, C, dtype=torch.float64, device="cuda")
+    R[:hw] = s0.double()
+    R[hwp:hwp + hw] = s1.double()
+    ref = R @ R.t()
+    scale = (R.norm(dim=1)[:, None] * R.norm(dim=1)[None, :]).clamp_min(1e-30)
+    rel = ((G.double() - ref).abs() / scale)
+    assert float(rel.max()) < 2.5e-7, float(rel.max())   # relative to |a||b|: a few ulp of a cosine
+    assert torch.equal(G, G.t())
+    assert (G[hw:hwp] == 0).all() and (G[hwp + hw:] == 0).all()
+    torch.testing.assert_close(sn.double(), R.norm(dim=1), rtol=3e-7, atol=0)
+    assert (rs[hw:hwp] == 0).all()
+
+
+@pytest.mark.parametrize("kind", ["depth", "xyz"])
+def test_k3_on_the_gram_matrix_equals_the_oracle_distances(mv, syn, kind):
+    """mv_k3_ratio_mutual_lr: the fp32 cosine distances of the two candidates from the Gram matrix against the reference's own
+    1 - cosine_similarity of the gathered rows (correspondence.py:53-58): <= 1e-6, same neighbours, same weights."""
+    C_ = mv.correspondence
+    shape = dict(C=256, h=15, w=20, H=60, W=80) if kind == "depth" else dict(C=256, h=14, w=14, H=56, W=56, radius=22.0)
+    p = syn.scannet_pair(4, **shape) if kind == "depth" else syn.navi_pair(4, **shape)
+    s0, s1, f0, f1 = sides(mv, kind, p)
+    s0.rows16 = s0.rows32 = s0.rows_lo = s1.rows16 = s1.rows32 = s1.rows_lo = None   # as prepared with want_rows=False
+    r = C_._match_sides(s0, s1, s0.n, s1.n, 500)
+    torch.cuda.synchronize()
+    d_ref, i_ref = restated.knn_points(f0, f1, 2, "cosine")
+    o = restated.similarity_top2_and_mutual(f0, f1)
+    clear = o["row_gap"] > 1e-3
+    idx = r.row_idx.cpu().long()
+    assert torch.equal(idx[clear, 0], i_ref[clear, 0])
+    same = (idx == i_ref).all(1)
+    assert float(same.float().mean()) > 0.9
+    assert float((r.dists.cpu()[same] - d_ref[same]).abs().max()) <= 1e-6
+    w_ref = restated.ratio_weights(d_ref)
+    assert float((r.weight.cpu()[same] - w_ref[same]).abs().max()) <= 2e-5
+
+
 def test_lowrank_is_the_default_where_it_pays(mv):
     C_ = mv.correspondence
     assert C_._CFG["lowrank"] == "auto"
     assert C_.lowrank_applies(2048, 15, 20, 19200, 19200)            # ScanNet-shaped: 312 columns instead of 2056
     assert not C_.lowrank_applies(3072, 28, 28, 12544, 12544)        # NAVI-shaped: the dense product stays
     assert not C_.lowrank_applies(768, 14, 14, 196, 20)              # small problems
+    assert C_.lowrank_exact_applies(2048, 15, 20, 19200, 19200)      # ... and there without kernel 1 (kernel 3 on the exact Gram)
 
 
 def test_full_size_scannet_pair_same_result_with_and_without(mv, syn):
@@ -111,15 +172,15 @@ def test_full_size_scannet_pair_same_result_with_and_without(mv, syn):
     C_ = mv.correspondence
     p = syn.scannet_pair(5)
     out = {}
-    for lr in ("auto", 0):
-        C_.set_match_precision(lowrank=lr)
+    for name, lr, k3 in (("exact", "auto", 1), ("rows", "auto", 0), ("dense", 0, 1)):
+        C_.set_match_precision(lowrank=lr, lowrank_k3=k3)
         try:
-            out[lr] = C_.estimate_correspondence_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], p["K"].clone(), 1000)
+            out[name] = C_.estimate_correspondence_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], p["K"].clone(), 1000)
         finally:
-            C_.set_match_precision(lowrank="auto")
-    a = {tuple(x.tolist()) + tuple(y.tolist()) for x, y in zip(out["auto"][0].cpu(), out["auto"][1].cpu())}
-    b = {tuple(x.tolist()) + tuple(y.tolist()) for x, y in zip(out[0][0].cpu(), out[0][1].cpu())}
-    assert len(a & b) >= 995, len(a & b)
+            C_.set_match_precision(lowrank="auto", lowrank_k3=1)
+    sets = {k: {tuple(x.tolist()) + tuple(y.tolist()) for x, y in zip(v[0].cpu(), v[1].cpu())} for k, v in out.items()}
+    assert len(sets["exact"] & sets["dense"]) >= 995, len(sets["exact"] & sets["dense"])
+    assert len(sets["rows"] & sets["dense"]) >= 995, len(sets["rows"] & sets["dense"])
     # north-star rule on the proposal itself: the nearest neighbour of every row whose reference fp32 top-2 gap exceeds 1e-3
     s0, s1, f0, f1 = sides(mv, "depth", p)
     assert C_.lowrank_applies(*s0.fshape, s0.n, s1.n, s0.mode)
