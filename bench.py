@@ -769,6 +769,28 @@ def stress(ctx, tc_peak):
     return out
 
 
+def h2d_link_probe(ctx, bytes_per_pair):
+    """The ceiling of the end-to-end arm on THIS box at THIS N: all ranks copy one pair's worth of pinned host memory to their
+    GPU at the same time, back to back; pairs/s ceiling = aggregate bandwidth / bytes per pair.  (On the 8-GPU boxes of this
+    pool pairs of GPUs share a PCIe uplink: 54.9 GB/s alone, 29.8 GB/s each at N = 8 -- profiles/r2_h2d_scale.txt.)"""
+    n = int(bytes_per_pair) // 4
+    src = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(4)]
+    dst = torch.empty(n, dtype=torch.float32, device=ctx.dev)
+    for s_ in src:
+        dst.copy_(s_, non_blocking=True)
+    torch.cuda.synchronize()
+    ctx.barrier()
+    reps = 64
+    t0 = time.perf_counter()
+    for i in range(reps):
+        dst.copy_(src[i % 4], non_blocking=True)
+    torch.cuda.synchronize()
+    dt = ctx.max_over_ranks(time.perf_counter() - t0)
+    agg = ctx.world * reps * n * 4 / dt / 1e9
+    return {"aggregate_GBps": agg, "per_gpu_GBps": agg / ctx.world, "pairs_per_s_ceiling": agg * 1e9 / (n * 4),
+            "note": "all ranks copying from pinned host memory at once: what the PCIe topology of this box gives N GPUs"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -815,6 +837,8 @@ def main():
         if ctx.world == 1 and ctx.rank == 0 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_pairs_per_s(ctx, head)
     line["host_binding"] = ctx.binding
+    if head != "spair" and "e2e" in line:
+        line["e2e"]["h2d_link"] = h2d_link_probe(ctx, line["e2e"]["h2d_bytes_per_step"] / line["config"]["pairs_per_step"])
     if args.workload == "all":
         sub_steps = max(3, args.steps // 4)
         line["workloads"] = {"scannet": run_dense(ctx, "scannet", sub_steps, 3, light=True), "spair": run_spair(ctx, max(5, args.steps // 2), 3)}
