@@ -199,10 +199,14 @@ int mv_rows_center(const float* rows, int C, int n_max, const int32_t* n_dev, in
  *                      The caller stacks both images' U (image k at row offset off_k, pad rows zero) and obtains the
  *                      stacked cosine Gram matrix G (fp32, pitch ld_g) from mv_k2_affinity(U, U).
  *   mv_lr_gram_exact   the other source of G: the Gram matrix of the RAW source rows of both images stacked (image 1 at row /
- *                      column offset hwp), (2 hwp, ld_g) fp32, computed on the CUDA cores with blocked fp32 accumulation
- *                      (16 slices of C / 16 channels per entry, fixed-order tree: ~1 ulp, deterministic; C % 64 == 0), plus
- *                      snorm / rsnorm (2 hwp): |src[p]| and its reciprocal from the diagonal.  Exact enough for kernel 3
- *                      (mv_k3_ratio_mutual_lr); the tensor-core Gram is not (tcgen05 accumulates with truncation).
+ *                      column offset off1, a multiple of 32 >= hw), (2 off1, ld_g) fp32, computed on the CUDA cores with blocked
+ *                      fp32 accumulation (16 slices of C / 16 channels per entry, fixed-order tree: ~1 ulp, deterministic;
+ *                      C % 64 == 0), plus snorm / rsnorm (2 off1): |src[p]| and its reciprocal from the diagonal.  Written: the
+ *                      whole cross block (image 0 x image 1, both orientations) and, of the two same-image blocks, the entries
+ *                      whose indices are at most `reach` apart (at least those: whole 32 x 32 tiles of the band) -- pass the largest
+ *                      index distance between two taps of one point ((T - 1) (w + 1) for T x T taps); the rest of G is left
+ *                      untouched.  Exact enough for kernel 3 (mv_k3_ratio_mutual_lr); the tensor-core Gram is not (tcgen05
+ *                      accumulates with truncation).
  *   mv_lr_build_query  A_f16 (n, pitch): [fp16(A[i,:] - c_i) (hw) | 0 (to hwp) | c_i, c_i, 0 x 6], c_i = fp16(max_t A[i,t])
  *                      (centring a row on its own maximum keeps the fp16 rounding error of the columns that compete for
  *                      the row's top-2 at ~1e-6, also on nearly collinear CNN features).
@@ -220,8 +224,8 @@ int mv_rows_center(const float* rows, int C, int n_max, const int32_t* n_dev, in
  *                      rows are never materialised: kernel 1 does not run. */
 #define MV_LR_MAX_SOURCE_PIXELS 1024
 int mv_lr_unit_rows(const float* src_hwc, int C, int hw, void* U_f16, float* snorm, mv_stream_t stream);
-int mv_lr_gram_exact(const float* src0_hwc, const float* src1_hwc, int C, int hw, int hwp, float* G, int ld_g, float* snorm,
-                     float* rsnorm, mv_stream_t stream);
+int mv_lr_gram_exact(const float* src0_hwc, const float* src1_hwc, int C, int hw, int off1, int reach, float* G, int ld_g,
+                     float* snorm, float* rsnorm, mv_stream_t stream);
 int mv_lr_build_query(int mode, const float* coords, const int32_t* n_dev, int n_max, int h, int w, const float* tapscale,
                       const float* colscale, const float* G, int ld_g, int off_own, int off_tgt, void* A_f16, int pitch, int hwp,
                       float* inv_norm_out, mv_stream_t stream);

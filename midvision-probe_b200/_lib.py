@@ -36,7 +36,7 @@ PROTOTYPES = {
     "mv_rank_of_valid": (c_int, [P, P, c_int, P, c_int, P]),
     "mv_k1_grid_f16c": (c_int, [P, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P, P, c_int, P, P]),
     "mv_lr_unit_rows": (c_int, [P, c_int, c_int, P, P, P]),
-    "mv_lr_gram_exact": (c_int, [P, P, c_int, c_int, c_int, P, c_int, P, P, P]),
+    "mv_lr_gram_exact": (c_int, [P, P, c_int, c_int, c_int, c_int, P, c_int, P, P, P]),
     "mv_lr_build_query": (c_int, [c_int, P, P, c_int, c_int, c_int, P, P, P, c_int, c_int, c_int, P, c_int, c_int, P, P]),
     "mv_lr_build_target": (c_int, [c_int, P, P, c_int, c_int, c_int, P, P, P, c_int, c_int, P, c_int, c_int, P, P]),
     "mv_k3_ratio_mutual_lr": (c_int, [c_int, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, P, c_int, P, P, c_int, P, P, P, P]),

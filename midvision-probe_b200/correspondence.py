@@ -644,19 +644,22 @@ def _lowrank_operands(s0, s1, n, m, n_dev, m_dev, exact=False):
     hwp = (hw + 7) // 8 * 8
     P = L.f16c_pitch(hwp)
     if exact:
-        G = _empty((2 * hwp, 2 * hwp), torch.float32, dev)
-        snorm = _empty((2 * hwp,), torch.float32, dev)
-        rsnorm = _empty((2 * hwp,), torch.float32, dev)
-        L.call("mv_lr_gram_exact", L.ptr(s0.src), L.ptr(s1.src), C, hw, hwp, L.ptr(G), 2 * hwp, L.ptr(snorm), L.ptr(rsnorm), st)
+        off1 = (hw + 31) // 32 * 32  # image 1's offset in the stacked Gram matrix: whole 32 x 32 tiles per image
+        taps = 4 if s0.mode == L.MV_SAMPLE_BICUBIC_CLAMP else 2
+        reach = (taps - 1) * (w + 1)  # largest index distance between two taps of one point
+        G = _empty((2 * off1, 2 * off1), torch.float32, dev)
+        snorm = _empty((2 * off1,), torch.float32, dev)
+        rsnorm = _empty((2 * off1,), torch.float32, dev)
+        L.call("mv_lr_gram_exact", L.ptr(s0.src), L.ptr(s1.src), C, hw, off1, reach, L.ptr(G), 2 * off1, L.ptr(snorm), L.ptr(rsnorm), st)
         A_op = _empty((max(n, 1), P), torch.float16, dev)
         B_op = _empty((max(m, 1), P), torch.float16, dev)
         inv0 = _empty((max(n, 1),), torch.float32, dev)
         inv1 = _empty((max(m, 1),), torch.float32, dev)
-        L.call("mv_lr_build_target", s1.mode, L.ptr(s1.coords), L.ptr(m_dev), m, h, w, None, c_void_p(snorm.data_ptr() + hwp * 4),
-               L.ptr(G), 2 * hwp, hwp, L.ptr(B_op), P, hwp, L.ptr(inv1), st)
-        L.call("mv_lr_build_query", s0.mode, L.ptr(s0.coords), L.ptr(n_dev), n, h, w, None, c_void_p(rsnorm.data_ptr() + hwp * 4),
-               L.ptr(G), 2 * hwp, 0, hwp, L.ptr(A_op), P, hwp, L.ptr(inv0), st)
-        return A_op, B_op, hwp + 8, {"G": G, "ld": 2 * hwp, "off_t": hwp, "inv0": inv0, "inv1": inv1, "keep": (snorm, rsnorm)}
+        L.call("mv_lr_build_target", s1.mode, L.ptr(s1.coords), L.ptr(m_dev), m, h, w, None, c_void_p(snorm.data_ptr() + off1 * 4),
+               L.ptr(G), 2 * off1, off1, L.ptr(B_op), P, hwp, L.ptr(inv1), st)
+        L.call("mv_lr_build_query", s0.mode, L.ptr(s0.coords), L.ptr(n_dev), n, h, w, None, c_void_p(rsnorm.data_ptr() + off1 * 4),
+               L.ptr(G), 2 * off1, 0, off1, L.ptr(A_op), P, hwp, L.ptr(inv0), st)
+        return A_op, B_op, hwp + 8, {"G": G, "ld": 2 * off1, "off_t": off1, "inv0": inv0, "inv1": inv1, "keep": (snorm, rsnorm)}
     U = _empty((2 * hwp, C), torch.float16, dev)
     if hwp > hw:  # pad rows: zero Gram rows / columns
         U[hw:hwp].zero_()

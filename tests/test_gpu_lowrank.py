@@ -99,39 +99,46 @@ def test_helpers_with_the_lowrank_proposal_match_the_oracle(mv, syn, lowrank_on,
         assert int((diff > 2e-5).sum()) <= 5 and float(diff.max()) < 5e-3, (kind, seed, float(diff.max()))
 
 
-@pytest.mark.parametrize("C,h,w", [(2048, 15, 20), (256, 9, 7), (3072, 12, 12)])
-def test_exact_gram_is_fp32_exact(mv, C, h, w):
-    """mv_lr_gram_exact against an fp64 product: every entry to ~1 ulp (blocked fp32 accumulation), symmetric, pad rows zero,
-    snorm / rsnorm from the diagonal; bit-repeatable."""
-    from ctypes import c_void_p
+@pytest.mark.parametrize("C,h,w,taps", [(2048, 15, 20, 2), (256, 9, 7, 4), (3072, 12, 12, 4), (320, 28, 28, 2)])
+def test_exact_gram_is_fp32_exact(mv, C, h, w, taps):
+    """mv_lr_gram_exact against an fp64 product: every entry it promises (the whole cross block, the same-image entries whose
+    indices are at most `reach` apart) to ~1 ulp (blocked fp32 accumulation), symmetric, pad rows zero, snorm / rsnorm from
+    the diagonal; bit-repeatable."""
     L, C_ = mv._lib, mv.correspondence
     g = torch.Generator().manual_seed(C + h)
     hw = h * w
-    hwp = (hw + 7) // 8 * 8
+    off1 = (hw + 31) // 32 * 32
+    reach = (taps - 1) * (w + 1)
     # all-positive, nearly collinear rows (the CNN regime) and signed rows
     s0 = (torch.rand(hw, C, generator=g) + 0.5).cuda()
     s1 = torch.randn(hw, C, generator=g).cuda()
     outs = []
     for _ in range(2):
-        G = torch.full((2 * hwp, 2 * hwp), 7.0, device="cuda")
-        sn = torch.empty(2 * hwp, device="cuda")
-        rs = torch.empty(2 * hwp, device="cuda")
-        L.call("mv_lr_gram_exact", L.ptr(s0), L.ptr(s1), C, hw, hwp, L.ptr(G), 2 * hwp, L.ptr(sn), L.ptr(rs), C_._stream())
+        G = torch.full((2 * off1, 2 * off1), 7.0, device="cuda")
+        sn = torch.empty(2 * off1, device="cuda")
+        rs = torch.empty(2 * off1, device="cuda")
+        L.call("mv_lr_gram_exact", L.ptr(s0), L.ptr(s1), C, hw, off1, reach, L.ptr(G), 2 * off1, L.ptr(sn), L.ptr(rs), C_._stream())
         torch.cuda.synchronize()
         outs.append(G)
     assert torch.equal(outs[0], outs[1])
     G = outs[0]
-    R = torch.zeros(2 * hwp, C, dtype=torch.float64, device="cuda")
+    R = torch.zeros(2 * off1, C, dtype=torch.float64, device="cuda")
     R[:hw] = s0.double()
-    R[hwp:hwp + hw] = s1.double()
+    R[off1:off1 + hw] = s1.double()
     ref = R @ R.t()
     scale = (R.norm(dim=1)[:, None] * R.norm(dim=1)[None, :]).clamp_min(1e-30)
-    rel = ((G.double() - ref).abs() / scale)
+    idx = torch.arange(2 * off1, device="cuda")
+    same_img = (idx[:, None] < off1) == (idx[None, :] < off1)
+    promised = ~same_img | ((idx[:, None] - idx[None, :]).abs() <= reach)
+    rel = ((G.double() - ref).abs() / scale)[promised]
     assert float(rel.max()) < 2.5e-7, float(rel.max())   # relative to |a||b|: a few ulp of a cosine
-    assert torch.equal(G, G.t())
-    assert (G[hw:hwp] == 0).all() and (G[hwp + hw:] == 0).all()
+    assert torch.equal(torch.where(promised, G, 0), torch.where(promised, G.t(), 0))
+    pad = torch.ones(2 * off1, dtype=torch.bool, device="cuda")
+    pad[:hw] = False
+    pad[off1:off1 + hw] = False
+    assert (G[pad][:, ~pad][promised[pad][:, ~pad]] == 0).all()
     torch.testing.assert_close(sn.double(), R.norm(dim=1), rtol=3e-7, atol=0)
-    assert (rs[hw:hwp] == 0).all()
+    assert (rs[pad] == 0).all()
 
 
 @pytest.mark.parametrize("kind", ["depth", "xyz"])
