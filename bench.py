@@ -774,19 +774,20 @@ def h2d_link_probe(ctx, bytes_per_pair):
     GPU at the same time, back to back; pairs/s ceiling = aggregate bandwidth / bytes per pair.  (On the 8-GPU boxes of this
     pool pairs of GPUs share a PCIe uplink: 54.9 GB/s alone, 29.8 GB/s each at N = 8 -- profiles/r2_h2d_scale.txt.)"""
     n = int(bytes_per_pair) // 4
-    src = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(4)]
+    src = [torch.zeros(n, dtype=torch.float32).pin_memory() for _ in range(4)]
     dst = torch.empty(n, dtype=torch.float32, device=ctx.dev)
     for s_ in src:
         dst.copy_(s_, non_blocking=True)
     torch.cuda.synchronize()
-    ctx.barrier()
-    reps = 64
-    t0 = time.perf_counter()
-    for i in range(reps):
-        dst.copy_(src[i % 4], non_blocking=True)
-    torch.cuda.synchronize()
-    dt = ctx.max_over_ranks(time.perf_counter() - t0)
-    agg = ctx.world * reps * n * 4 / dt / 1e9
+    reps, best = 32, float("inf")
+    for _ in range(5):  # best of five rounds: the figure is a ceiling, a descheduled host thread must not lower it
+        ctx.barrier()
+        t0 = time.perf_counter()
+        for i in range(reps):
+            dst.copy_(src[i % 4], non_blocking=True)
+        torch.cuda.synchronize()
+        best = min(best, ctx.max_over_ranks(time.perf_counter() - t0))
+    agg = ctx.world * reps * n * 4 / best / 1e9
     return {"aggregate_GBps": agg, "per_gpu_GBps": agg / ctx.world, "pairs_per_s_ceiling": agg * 1e9 / (n * 4),
             "note": "all ranks copying from pinned host memory at once: what the PCIe topology of this box gives N GPUs"}
 
