@@ -447,7 +447,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
         // warp can improve, ~20 % of them -- is SLOWER: 0.418 vs 0.340 ms at 18231^2 x 312, 0.477 vs 0.411 ms at
         // 19200^2 x 768.  The unconditional loop below is software-pipelined by the compiler (32 independent CREDUX in
         // flight); behind a branch every taken group pays the CREDUX -> FSETP -> VOTE latency chain, plus one more barrier
-        // per tile.  Without any column work the K = 312 launch takes 0.267 ms: the rows + TMEM reads are the larger part.)
+        // per tile.  Without any column work the K = 312 launch takes 0.267 ms: the rows + TMEM reads are the larger part.
+        // Also measured and rejected: the TMEM read of chunk c + 1 in flight while chunk c is processed (two register
+        // buffers, 168 registers): 0.375 vs 0.340 ms at K = 312, 0.432 vs 0.411 ms at 19200^2 x 768.)
 #ifndef MV_K2_EXP_NO_COLS
 #pragma unroll
         for (int q = 0; q < 32; q += 2) {
