@@ -17,8 +17,10 @@
 // backbone's (B, 2, C, h, w) output, the heat map lives in registers and nothing but K integers per pair is
 // written, so the path is bounded by HBM, not by launches.
 #include <math_constants.h>
+#include <stdlib.h>
 
 #include "common.cuh"
+#include "sm100_ptx.cuh"
 #include "spair_score.cuh"
 
 namespace {
@@ -221,8 +223,266 @@ __global__ void __launch_bounds__(SPB_THREADS) spair_batch_kernel(SpairBatchPara
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// the streaming form (the default where it applies: h*w <= 256, C % 8 == 0, 16-byte aligned maps)
+// ------------------------------------------------------------------------------------------
+// A pair's two maps are ONE contiguous 2 * C * h*w * 4 byte block, read three times in channel order: image i for the
+// pixel norms, image i again (from L2) for the key-point features q, image j for the heat map.  A producer warp streams
+// that sequence through a ring of shared-memory stages with 1-D bulk copies (cp.async.bulk, 8 channels = 6.3 KB per
+// stage for a 14 x 14 map, completion on an mbarrier) and runs up to STAGES chunks -- across the passes and across pairs --
+// ahead of the 8 consumer warps, which only ever read shared memory.  In the first form every consumer thread issued its
+// own 4-byte global loads, 16 in flight, and sat on their DRAM latency (ncu: 45 % of the samples on long-scoreboard
+// stalls at 2.2 TB/s); here the bytes in flight do not depend on registers or occupancy.  The arithmetic (order of every
+// sum) is that of the first form, so the results are bit-identical.
+constexpr int SPS_CONS = 256;               // consumer threads: thread = pixel in the norm / heat passes
+constexpr int SPS_THREADS = SPS_CONS + 32;  // + one producer warp
+constexpr int SPS_CC = 8;                   // channels per stage
+constexpr int SPS_STAGES = 4;
+
+template <int KT>
+__global__ void __launch_bounds__(SPS_THREADS, 2) spair_stream_kernel(SpairBatchParams p) {
+  using namespace sm100;
+  extern __shared__ __align__(16) float4 sps_dyn[];
+  __shared__ SpairScoreShared score;
+  __shared__ int s_pred[64];
+  __shared__ float s_wt[64][4];
+  __shared__ int s_tap[64][4];
+  __shared__ float s_bv[SPS_CONS / 32][KT];
+  __shared__ int s_bi[SPS_CONS / 32][KT];
+  __shared__ __align__(8) unsigned long long full[SPS_STAGES], empty[SPS_STAGES];
+  const int C = p.C, hw = p.h * p.w, K = p.K;
+  const int chunk_floats = SPS_CC * hw;
+  const uint32_t chunk_bytes = (uint32_t)chunk_floats * 4u;
+  float* ring = reinterpret_cast<float*>(sps_dyn);                  // [STAGES][CC * hw]
+  float* q = ring + (size_t)SPS_STAGES * chunk_floats;              // [C][KT]
+  float* pix_ss = q + (size_t)C * KT;                               // [hw]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nchunk = C / SPS_CC;
+  const int nkt = (K + KT - 1) / KT;  // key-point tiles: passes Q and H repeat per tile
+
+  if (tid == 0) {
+    for (int s = 0; s < SPS_STAGES; ++s) {
+      mbar_init(smem_u32(&full[s]), 1);
+      mbar_init(smem_u32(&empty[s]), SPS_CONS / 32);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (wid == SPS_CONS / 32) {
+    // ===================================== producer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+        const float* fi = p.feats + (size_t)b * 2 * C * hw;
+        const float* fj = fi + (size_t)C * hw;
+        for (int pass = 0; pass < 1 + 2 * nkt; ++pass) {
+          const float* base = (pass == 0 || (pass & 1)) ? fi : fj;  // N, then (Q, H) per key-point tile
+          for (int ck = 0; ck < nchunk; ++ck) {
+            mbar_wait(smem_u32(&empty[stage]), phase ^ 1u);
+            mbar_arrive_expect_tx(smem_u32(&full[stage]), chunk_bytes);
+            bulk_load_1d(smem_u32(ring + (size_t)stage * chunk_floats), base + (size_t)ck * chunk_floats, chunk_bytes,
+                         smem_u32(&full[stage]));
+            if (++stage == SPS_STAGES) { stage = 0; phase ^= 1u; }
+          }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===================================== consumers =====================================
+  int stage = 0;
+  uint32_t phase = 0;
+  auto cons_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(SPS_CONS) : "memory"); };
+  auto release = [&] {  // this warp is done with the current stage
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&empty[stage]));
+    if (++stage == SPS_STAGES) { stage = 0; phase ^= 1u; }
+  };
+  const int nwarp = SPS_CONS / 32;
+  const int px = tid;
+  const bool has_px = px < hw;
+
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    const float* ki = p.kps_i + (size_t)b * K * p.stride;
+    const float* kj = p.kps_j + (size_t)b * K * p.stride;
+    // ---- key-point taps: kp / size * 2 - 1 -> ((g + 1) / 2) * (size - 1)  (align_corners=True) ----
+    if (tid < K) {
+      const float kx = __fdiv_rn(ki[(size_t)tid * p.stride + 0], p.image_size);
+      const float ky = __fdiv_rn(ki[(size_t)tid * p.stride + 1], p.image_size);
+      const float gx = __fsub_rn(__fmul_rn(kx, 2.f), 1.f), gy = __fsub_rn(__fmul_rn(ky, 2.f), 1.f);
+      const float ix = __fmul_rn(__fdiv_rn(__fadd_rn(gx, 1.f), 2.f), (float)(p.w - 1));
+      const float iy = __fmul_rn(__fdiv_rn(__fadd_rn(gy, 1.f), 2.f), (float)(p.h - 1));
+      const float fx = floorf(ix), fy = floorf(iy);
+      const int x0 = (int)fx, y0 = (int)fy;
+      const float ww = ix - fx, we = 1.f - ww, wn = iy - fy, ws = 1.f - wn;
+      const float wt[4] = {ws * we, ws * ww, wn * we, wn * ww};  // nw, ne, sw, se
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int xx = x0 + (t & 1), yy = y0 + (t >> 1);
+        const bool in = xx >= 0 && xx < p.w && yy >= 0 && yy < p.h;
+        s_wt[tid][t] = in ? wt[t] : 0.f;
+        s_tap[tid][t] = min(max(yy, 0), p.h - 1) * p.w + min(max(xx, 0), p.w - 1);
+      }
+    }
+    // ---- pass N: ||f_i[px]||^2 of every pixel, channels in ascending order ----
+    {
+      float ss = 0.f;
+      for (int ck = 0; ck < nchunk; ++ck) {
+        mbar_wait(smem_u32(&full[stage]), phase);
+        const float* st = ring + (size_t)stage * chunk_floats + px;
+        if (has_px) {
+#pragma unroll
+          for (int c = 0; c < SPS_CC; ++c) {
+            const float v = st[c * hw];
+            ss = fmaf(v, v, ss);
+          }
+        }
+        release();
+      }
+      if (has_px) pix_ss[px] = ss;
+    }
+    cons_sync();
+    if (tid < 4 * K) {  // fold 1 / max(||f_i[tap]||, eps) into the blend weight
+      const int k = tid >> 2, t = tid & 3;
+      s_wt[k][t] = __fdiv_rn(s_wt[k][t], fmaxf(sqrtf(pix_ss[s_tap[k][t]]), SPB_NORM_EPS));
+    }
+    cons_sync();
+
+    for (int k0 = 0; k0 < K; k0 += KT) {
+      const int kt = min(KT, K - k0);
+      // ---- pass Q: q[c][k] = sum_t wt * f_i[c][tap] / max(||f_i[tap]||, eps): the grid_sample of the normalised map ----
+      for (int ck = 0; ck < nchunk; ++ck) {
+        mbar_wait(smem_u32(&full[stage]), phase);
+        const float* st = ring + (size_t)stage * chunk_floats;
+        for (int idx = tid; idx < SPS_CC * KT; idx += SPS_CONS) {
+          const int c = idx / KT, k = idx - c * KT;
+          const int kk = k0 + min(k, kt - 1);
+          const float* src = st + c * hw;
+          float acc = src[s_tap[kk][0]] * s_wt[kk][0];
+          acc = fmaf(src[s_tap[kk][1]], s_wt[kk][1], acc);
+          acc = fmaf(src[s_tap[kk][2]], s_wt[kk][2], acc);
+          acc = fmaf(src[s_tap[kk][3]], s_wt[kk][3], acc);
+          q[(size_t)(ck * SPS_CC + c) * KT + k] = (k < kt) ? acc : 0.f;
+        }
+        release();
+      }
+      cons_sync();
+      // ---- pass H: heat[k][px] = (sum_c q[c][k] * f_j[c][px]) / max(||f_j[px]||, eps), norm accumulated alongside ----
+      float acc[KT];
+#pragma unroll
+      for (int k = 0; k < KT; ++k) acc[k] = 0.f;
+      float ss = 0.f;
+      for (int ck = 0; ck < nchunk; ++ck) {
+        mbar_wait(smem_u32(&full[stage]), phase);
+        const float* st = ring + (size_t)stage * chunk_floats + px;
+        if (has_px) {
+#pragma unroll
+          for (int c = 0; c < SPS_CC; ++c) {
+            const float v = st[c * hw];
+            ss = fmaf(v, v, ss);
+            const float4* qc = reinterpret_cast<const float4*>(q + (size_t)(ck * SPS_CC + c) * KT);
+#pragma unroll
+            for (int k4 = 0; k4 < KT / 4; ++k4) {
+              const float4 qq = qc[k4];  // same address in every lane: broadcast
+              acc[4 * k4 + 0] = fmaf(qq.x, v, acc[4 * k4 + 0]);
+              acc[4 * k4 + 1] = fmaf(qq.y, v, acc[4 * k4 + 1]);
+              acc[4 * k4 + 2] = fmaf(qq.z, v, acc[4 * k4 + 2]);
+              acc[4 * k4 + 3] = fmaf(qq.w, v, acc[4 * k4 + 3]);
+            }
+          }
+        }
+        release();
+      }
+      const float nrm = fmaxf(sqrtf(ss), SPB_NORM_EPS);
+#pragma unroll
+      for (int k = 0; k < KT; ++k) {
+        float v = has_px ? __fdiv_rn(acc[k], nrm) : -CUDART_INF_F;
+        int i = has_px ? px : 0x7fffffff;
+        if (!(v > -CUDART_INF_F)) {  // NaN / -inf never win (the first form's `hv > bestv` test against -inf)
+          v = -CUDART_INF_F;
+          i = 0x7fffffff;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+          if (ov > v || (ov == v && oi < i)) {
+            v = ov;
+            i = oi;
+          }
+        }
+        if (lane == 0) {
+          s_bv[wid][k] = v;
+          s_bi[wid][k] = i;
+        }
+      }
+      cons_sync();
+      if (tid < kt) {
+        float v = s_bv[0][tid];
+        int i = s_bi[0][tid];
+        for (int wq = 1; wq < nwarp; ++wq) {
+          const float ov = s_bv[wq][tid];
+          const int oi = s_bi[wq][tid];
+          if (ov > v || (ov == v && oi < i)) {
+            v = ov;
+            i = oi;
+          }
+        }
+        i = (i == 0x7fffffff) ? 0 : i;  // an all-NaN heat map: torch.argmax would return a NaN position; we return 0
+        s_pred[k0 + tid] = i;
+        if (p.pred) p.pred[(size_t)b * K + k0 + tid] = i;
+      }
+      cons_sync();  // q, s_bv are rewritten by the next tile
+    }
+
+    spair_score_block<SPS_CONS>(score, s_pred, K, p.w, ki, kj, p.stride, p.image_size, __ldg(p.thresh_scale + b), p.pck, nullptr,
+                                p.error_same ? p.error_same + (size_t)b * K : nullptr,
+                                p.error_nn ? p.error_nn + (size_t)b * K : nullptr,
+                                p.index_nn ? p.index_nn + (size_t)b * K : nullptr, p.hits, p.confusion, p.conf_dim);
+  }
+}
+
+// the streaming form needs one pixel per consumer thread and 16-byte-granular stages
+bool spair_stream_ok(const SpairBatchParams& p) {
+  static const int off = getenv("MVMATCH_SPAIR_STREAM") && getenv("MVMATCH_SPAIR_STREAM")[0] == '0';
+  const int hw = p.h * p.w;
+  return !off && hw <= SPS_CONS && p.C % SPS_CC == 0 && (hw * SPS_CC) % 4 == 0 && ((uintptr_t)p.feats & 15) == 0 &&
+         ((size_t)p.C * hw) % 4 == 0;
+}
+
+template <int KT>
+int launch_spair_stream(const SpairBatchParams& p, cudaStream_t st) {
+  const int hw = p.h * p.w;
+  const size_t smem = ((size_t)SPS_STAGES * SPS_CC * hw + (size_t)p.C * KT + (size_t)((hw + 3) / 4 * 4)) * sizeof(float);
+  auto kern = spair_stream_kernel<KT>;
+  static size_t opted[MV_MAX_DEVICES];
+  size_t& opted_in = opted[mv_device_slot()];
+  if (smem > opted_in) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      mv_set_error("mv_spair_match_batch: cannot opt in to %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+      return (int)e;
+    }
+    opted_in = smem;
+  }
+  int per_sm = (int)((227u << 10) / (smem + (21u << 10)));  // static shared memory of the kernel is ~20 KB
+  if (per_sm < 1) per_sm = 1;
+  if (per_sm > 2) per_sm = 2;
+  int grid = mv_sm_count() * per_sm;
+  if (grid > p.B) grid = p.B;
+  kern<<<grid, SPS_THREADS, smem, st>>>(p);
+  MV_LAUNCH_CHECK();
+  return MV_OK;
+}
+
 template <int KT>
 int launch_spair_batch(const SpairBatchParams& p, cudaStream_t st) {
+  if (spair_stream_ok(p) && ((size_t)SPS_STAGES * SPS_CC * p.h * p.w + (size_t)p.C * KT + p.h * p.w + 4) * sizeof(float) <= (200u << 10))
+    return launch_spair_stream<KT>(p, st);
   const size_t smem = (size_t)p.C * KT * sizeof(float);
   auto kern = spair_batch_kernel<KT>;
   static size_t opted[MV_MAX_DEVICES];  // per device; static + dynamic shared memory above 48 KB needs the opt-in

@@ -13,6 +13,14 @@ struct SpairScoreShared {
 };
 
 // One CTA, any block size; K <= 64.  pred_flat may point to shared or global memory.  Ends with a barrier.
+// NT == 0: every thread of the CTA takes part (__syncthreads); NT > 0: the first NT threads only, synchronised with named
+// barrier 1 (the streaming SPair kernel keeps a producer warp out of it).
+template <int NT = 0>
+__device__ __forceinline__ void spair_score_sync() {
+  if (NT == 0) __syncthreads();
+  else asm volatile("bar.sync 1, %0;" ::"r"(NT) : "memory");
+}
+template <int NT = 0>
 __device__ __forceinline__ void spair_score_block(SpairScoreShared& sh, const int32_t* pred_flat, int K, int w,
                                                   const float* __restrict__ kps_i, const float* __restrict__ kps_j,
                                                   int stride, float image_size, float thresh_scale, float pck,
@@ -20,8 +28,9 @@ __device__ __forceinline__ void spair_score_block(SpairScoreShared& sh, const in
                                                   float* __restrict__ error_nn, int32_t* __restrict__ index_nn,
                                                   unsigned long long* __restrict__ hits,
                                                   unsigned long long* __restrict__ confusion, int conf_dim) {
+  const int nthreads = NT == 0 ? (int)blockDim.x : NT;
   if (threadIdx.x < 2) sh.cnt[threadIdx.x] = 0;
-  for (int t = threadIdx.x; t < K * K; t += blockDim.x) {
+  for (int t = threadIdx.x; t < K * K; t += nthreads) {
     const int k = t / K, l = t - k * K;
     const int flat = pred_flat[k];
     // argmax_2d -> (col, row); both divided by feats.shape[-1]  (spair:83)
@@ -34,8 +43,8 @@ __device__ __forceinline__ void spair_score_block(SpairScoreShared& sh, const in
     sh.err[k][l] = e;
     if (errors) errors[t] = e;
   }
-  __syncthreads();
-  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+  spair_score_sync<NT>();
+  for (int k = threadIdx.x; k < K; k += nthreads) {
     const bool in_both = (kps_i[(size_t)k * stride + 2] * kps_j[(size_t)k * stride + 2]) == 1.f;
     float es = -1.f, en = -1.f;
     int in = -1;
@@ -53,7 +62,7 @@ __device__ __forceinline__ void spair_score_block(SpairScoreShared& sh, const in
     if (error_nn) error_nn[k] = en;
     if (index_nn) index_nn[k] = in;
   }
-  __syncthreads();
+  spair_score_sync<NT>();
   if (hits && threadIdx.x < 2 && sh.cnt[threadIdx.x]) atomicAdd(&hits[threadIdx.x], (unsigned long long)sh.cnt[threadIdx.x]);
-  __syncthreads();
+  spair_score_sync<NT>();
 }
