@@ -240,7 +240,22 @@ constexpr int SPS_THREADS = SPS_CONS + 32;  // + one producer warp
 constexpr int SPS_CC = 8;                   // channels per stage
 constexpr int SPS_STAGES = 4;
 
-template <int KT>
+// m16n8k8 tf32 tensor-core step (legacy warp-level MMA: the heat map of a pair is 196 x 20 x 768, far below a tcgen05 tile)
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// x = hi + lo with hi exactly representable in tf32 (the tensor core drops the low 13 mantissa bits of its operands);
+// hi*hi + hi*lo + lo*hi carries ~21 mantissa bits ("3xTF32")
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
+// MMA: the heat-map pass on the tensor cores -- pixels on M (16 per tile, 2 tiles per warp), key points on N (8 per tile),
+// one 8-channel stage = one K step, 3xTF32 -- instead of 21 FFMA + 6 LDS per channel and pixel.
+template <int KT, bool MMA>
 __global__ void __launch_bounds__(SPS_THREADS, 2) spair_stream_kernel(SpairBatchParams p) {
   using namespace sm100;
   extern __shared__ __align__(16) float4 sps_dyn[];
@@ -372,6 +387,96 @@ __global__ void __launch_bounds__(SPS_THREADS, 2) spair_stream_kernel(SpairBatch
       }
       cons_sync();
       // ---- pass H: heat[k][px] = (sum_c q[c][k] * f_j[c][px]) / max(||f_j[px]||, eps), norm accumulated alongside ----
+      if constexpr (MMA) {
+        static_assert(SPS_CC == 8, "one stage = one m16n8k8 K step");
+        constexpr int NT8 = (KT + 7) / 8;
+        const int g = lane >> 2, t = lane & 3;
+        float d[2][NT8][4];
+        float ssr[2][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          ssr[i][0] = ssr[i][1] = 0.f;
+#pragma unroll
+          for (int j = 0; j < NT8; ++j) d[i][j][0] = d[i][j][1] = d[i][j][2] = d[i][j][3] = 0.f;
+        }
+        const int ntile = (hw + 15) >> 4;  // this warp owns tiles wid and wid + 8
+        for (int ck = 0; ck < nchunk; ++ck) {
+          mbar_wait(smem_u32(&full[stage]), phase);
+          const float* st = ring + (size_t)stage * chunk_floats;
+          uint32_t bh[NT8][2], bl[NT8][2];
+#pragma unroll
+          for (int j = 0; j < NT8; ++j) {
+            const int kcol = 8 * j + g;
+            const float b0 = kcol < KT ? q[(size_t)(ck * SPS_CC + t) * KT + kcol] : 0.f;
+            const float b1 = kcol < KT ? q[(size_t)(ck * SPS_CC + t + 4) * KT + kcol] : 0.f;
+            split_tf32(b0, bh[j][0], bl[j][0]);
+            split_tf32(b1, bh[j][1], bl[j][1]);
+          }
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            const int mt = wid + 8 * i;
+            if (mt < ntile) {  // warp-uniform
+              const int p0 = mt * 16 + g;
+              const float a0 = st[t * hw + p0], a1 = st[t * hw + p0 + 8];            // rows beyond h*w read the following
+              const float a2 = st[(t + 4) * hw + p0], a3 = st[(t + 4) * hw + p0 + 8];  // floats of the ring: masked below
+              ssr[i][0] = fmaf(a0, a0, ssr[i][0]);
+              ssr[i][0] = fmaf(a2, a2, ssr[i][0]);
+              ssr[i][1] = fmaf(a1, a1, ssr[i][1]);
+              ssr[i][1] = fmaf(a3, a3, ssr[i][1]);
+              uint32_t ah[4], al[4];
+              split_tf32(a0, ah[0], al[0]);
+              split_tf32(a1, ah[1], al[1]);
+              split_tf32(a2, ah[2], al[2]);
+              split_tf32(a3, ah[3], al[3]);
+#pragma unroll
+              for (int j = 0; j < NT8; ++j) {
+                mma_tf32(d[i][j], al, bh[j][0], bh[j][1]);
+                mma_tf32(d[i][j], ah, bl[j][0], bl[j][1]);
+                mma_tf32(d[i][j], ah, bh[j][0], bh[j][1]);
+              }
+            }
+          }
+          release();
+        }
+        // per key point this lane owns (columns 2t, 2t + 1 of every N tile): best of its rows, then across the 8 row groups
+#pragma unroll
+        for (int j = 0; j < NT8; ++j) {
+#pragma unroll
+          for (int e2 = 0; e2 < 2; ++e2) {
+            float v = -CUDART_INF_F;
+            int bi = 0x7fffffff;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+#pragma unroll
+              for (int r = 0; r < 2; ++r) {
+                const int pxl = (wid + 8 * i) * 16 + g + 8 * r;
+                float ss = ssr[i][r];
+                ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+                ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+                const float hv = __fdiv_rn(d[i][j][2 * r + e2], fmaxf(sqrtf(ss), SPB_NORM_EPS));
+                if (wid + 8 * i < ntile && pxl < hw && (hv > v || (hv == v && pxl < bi))) {
+                  v = hv;
+                  bi = pxl;
+                }
+              }
+            }
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+              const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+              const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+              if (ov > v || (ov == v && oi < bi)) {
+                v = ov;
+                bi = oi;
+              }
+            }
+            const int kcol = 8 * j + 2 * t + e2;
+            if (g == 0 && kcol < KT) {
+              s_bv[wid][kcol] = v;
+              s_bi[wid][kcol] = bi;
+            }
+          }
+        }
+      } else {
       float acc[KT];
 #pragma unroll
       for (int k = 0; k < KT; ++k) acc[k] = 0.f;
@@ -420,6 +525,7 @@ __global__ void __launch_bounds__(SPS_THREADS, 2) spair_stream_kernel(SpairBatch
           s_bi[wid][k] = i;
         }
       }
+      }
       cons_sync();
       if (tid < kt) {
         float v = s_bv[0][tid];
@@ -458,9 +564,11 @@ template <int KT>
 int launch_spair_stream(const SpairBatchParams& p, cudaStream_t st) {
   const int hw = p.h * p.w;
   const size_t smem = ((size_t)SPS_STAGES * SPS_CC * hw + (size_t)p.C * KT + (size_t)((hw + 3) / 4 * 4)) * sizeof(float);
-  auto kern = spair_stream_kernel<KT>;
-  static size_t opted[MV_MAX_DEVICES];
-  size_t& opted_in = opted[mv_device_slot()];
+  // MVMATCH_SPAIR_MMA=0: the heat-map pass on the CUDA cores (bit-identical to the first form)
+  static const bool mma = !(getenv("MVMATCH_SPAIR_MMA") && getenv("MVMATCH_SPAIR_MMA")[0] == '0');
+  auto kern = mma ? spair_stream_kernel<KT, true> : spair_stream_kernel<KT, false>;
+  static size_t opted[MV_MAX_DEVICES][2];
+  size_t& opted_in = opted[mv_device_slot()][mma ? 1 : 0];
   if (smem > opted_in) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
