@@ -238,7 +238,12 @@ __global__ void __launch_bounds__(SPB_THREADS) spair_batch_kernel(SpairBatchPara
 constexpr int SPS_CONS = 256;               // consumer threads: thread = pixel in the norm / heat passes
 constexpr int SPS_THREADS = SPS_CONS + 32;  // + one producer warp
 constexpr int SPS_CC = 8;                   // channels per stage
-constexpr int SPS_STAGES = 4;
+// ring depth.  Measured (same box): 4 stages x 2 CTAs per SM 2.56 M pairs/s; 12 or 20 stages with ONE CTA per SM (the ring then
+// takes the shared memory of the second CTA) 1.75 M -- the kernel is bound by its 16 consumer warps per SM, not by bytes in flight
+#ifndef SPS_STAGES_N
+#define SPS_STAGES_N 4
+#endif
+constexpr int SPS_STAGES = SPS_STAGES_N;
 
 // m16n8k8 tf32 tensor-core step (legacy warp-level MMA: the heat map of a pair is 196 x 20 x 768, far below a tcgen05 tile)
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -256,7 +261,7 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 // MMA: the heat-map pass on the tensor cores -- pixels on M (16 per tile, 2 tiles per warp), key points on N (8 per tile),
 // one 8-channel stage = one K step, 3xTF32 -- instead of 21 FFMA + 6 LDS per channel and pixel.
 template <int KT, bool MMA>
-__global__ void __launch_bounds__(SPS_THREADS, 2) spair_stream_kernel(SpairBatchParams p) {
+__global__ void __launch_bounds__(SPS_THREADS, SPS_STAGES_N > 5 ? 1 : 2) spair_stream_kernel(SpairBatchParams p) {
   using namespace sm100;
   extern __shared__ __align__(16) float4 sps_dyn[];
   __shared__ SpairScoreShared score;
