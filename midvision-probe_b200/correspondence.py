@@ -962,7 +962,8 @@ def _graphed_helper(kind, feat_0, feat_1, grid_0, grid_1, num_corr, ratio_test, 
     on_host = feat_0.device.type == "cpu"
     # two graphs (upload of image 0 behind image 1's kernels) pay off for pinned sources (1369 -> 1536 pairs/s, NAVI-shaped);
     # pageable ones are staged by host threads, which the interleaved replay only delays (578 -> 458)
-    split = on_host and bool(_CFG["helper_split"]) and feat_0.is_pinned() and feat_1.is_pinned()
+    split = on_host and bool(_CFG["helper_split"]) and ((feat_0.is_pinned() and feat_1.is_pinned()) or
+                                                      os.environ.get("MVMATCH_HELPER_SPLIT_PAGEABLE", "0") == "1")
     # the intrinsics are NOT part of the key: they live in device memory and are refreshed per call (gm.load)
     key = (on_host, split, kind, tuple(feat_0.shape), tuple(grid_0.shape), int(num_corr), bool(ratio_test), _CFG["dtype"], _CFG["cluster"], _CFG["rows"], _CFG["k1_grid"], _CFG["lowrank"], _CFG["lowrank_k3"], fdt,
            dev.index, layout)

@@ -8,10 +8,14 @@
 // i mod SLOTS of a pinned ring and issues the chunk's own cudaMemcpyAsync on the caller's stream, so the host-side
 // memcpy of several chunks and the DMA of earlier ones run at the same time.  A slot is reused once the event recorded
 // after its DMA has fired.  The call returns when every chunk has been ISSUED (the source may then be modified);
-// the stream completes the transfers.  No batched-memcpy API is involved: one plain cudaMemcpyAsync per chunk.
+// the stream completes the transfers.  No batched-memcpy API is involved: plain cudaMemcpyAsync calls, one per run of
+// adjacent staged chunks.
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstring>
+#include <deque>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -21,21 +25,32 @@
 namespace {
 
 constexpr size_t STAGE_CHUNK = 1u << 18;  // 256 KiB: ~5 us of PCIe time, ~30 us of one core's memcpy; a 9.6 MB map = 37 chunks
-constexpr int STAGE_SLOTS = 32;
+constexpr int STAGE_SLOTS = 64;           // 16 MiB pinned ring
 constexpr int STAGE_MAX_THREADS = 16;
+constexpr int STAGE_MAX_BATCH = 8;        // ready chunks that are adjacent in the ring go out as ONE cudaMemcpyAsync (<= 2 MiB)
+constexpr int STAGE_EVENTS = 64;
+
+inline void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#else
+  std::this_thread::yield();
+#endif
+}
 
 struct Job {
   const char* src = nullptr;
-  char* dst = nullptr;
   size_t bytes = 0;
-  cudaStream_t stream = nullptr;
-  int device = 0;
-  std::atomic<size_t> next{0};   // next chunk index to claim
   size_t chunks = 0;
-  std::atomic<size_t> done{0};
-  std::atomic<int> error{0};
+  unsigned long long base = 0;            // ring position (global chunk id) of chunk 0
+  std::atomic<size_t> next{0};            // next chunk index to claim
+  std::atomic<unsigned char>* ready = nullptr;  // per chunk: staged into its ring slot
 };
 
+// Round 2: the workers ONLY copy into the ring; every CUDA call (one cudaMemcpyAsync per run of adjacent ready chunks, one event
+// per run, event queries that free ring slots) comes from the calling thread.  With eight threads each issuing their own
+// chunk's cudaMemcpyAsync + cudaEventRecord + cudaEventSynchronize the driver calls serialised on the context lock and a 9.6 MB
+// map uploaded at 14 GB/s (64 MB: 25 GB/s); the ring position now runs on across calls, so consecutive tensors need no reset.
 class Stager {
  public:
   static Stager& get() {
@@ -53,11 +68,12 @@ class Stager {
     if (rc) return rc;
     Job job;
     job.src = static_cast<const char*>(src);
-    job.dst = static_cast<char*>(dst);
     job.bytes = bytes;
-    job.stream = stream;
-    job.device = dev;
     job.chunks = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
+    job.base = next_id_;
+    std::unique_ptr<std::atomic<unsigned char>[]> ready(new std::atomic<unsigned char>[job.chunks]);
+    for (size_t i = 0; i < job.chunks; ++i) ready[i].store(0, std::memory_order_relaxed);
+    job.ready = ready.get();
     {
       std::lock_guard<std::mutex> lk(m_);
       job_ = &job;
@@ -65,21 +81,53 @@ class Stager {
       gen_atomic_.store(generation_, std::memory_order_release);
     }
     cv_.notify_all();
-    work(job);  // the calling thread stages chunks too
+
+    // ---- the issuer: DMAs go out in chunk order as soon as their chunks are staged
+    char* d = static_cast<char*>(dst);
+    int err = 0;
+    size_t i = 0;
+    while (i < job.chunks) {
+      poll_drained();
+      if (!job.ready[i].load(std::memory_order_acquire)) {
+        if (workers_.empty()) stage_one(job);  // single-threaded configuration: the caller stages too
+        else cpu_relax();
+        continue;
+      }
+      size_t j = i + 1;
+      while (j < job.chunks && j - i < (size_t)STAGE_MAX_BATCH && ((job.base + j) % STAGE_SLOTS) != 0 &&
+             job.ready[j].load(std::memory_order_acquire))
+        ++j;
+      const size_t off = i * STAGE_CHUNK;
+      const size_t len = (j * STAGE_CHUNK <= bytes ? j * STAGE_CHUNK : bytes) - off;
+      const char* pin = ring_ + (size_t)((job.base + i) % STAGE_SLOTS) * STAGE_CHUNK;
+      e = cudaMemcpyAsync(d + off, pin, len, cudaMemcpyHostToDevice, stream);
+      if (e == cudaSuccess) {
+        if (pending_.size() >= (size_t)STAGE_EVENTS) {  // every event is in flight: wait for the oldest
+          cudaEventSynchronize(events_[pending_.front().ev]);
+          poll_drained();
+        }
+        const int ev = ev_next_++ % STAGE_EVENTS;
+        e = cudaEventRecord(events_[ev], stream);
+        pending_.push_back({ev, job.base + j});
+      }
+      if (e != cudaSuccess && !err) err = (int)e;
+      i = j;
+    }
+    next_id_ = job.base + job.chunks;
     {
       std::unique_lock<std::mutex> lk(m_);
-      done_cv_.wait(lk, [&] { return job.done.load() == job.chunks && active_ == 0; });
+      done_cv_.wait(lk, [&] { return active_ == 0; });  // no worker still looks at this job
       job_ = nullptr;
     }
-    return job.error.load();
+    return err;
   }
 
   int threads() const { return (int)workers_.size() + 1; }
 
  private:
   Stager() {
-    // measured on the B200 box (16 cores, tools/h2d_staged_probe.py, 64 MB): 1 thread 8 GB/s, 2: 18, 4: 36, 8: 42, 16: 28
-    // (torch's pageable copy: 14 GB/s, pinned: 55 GB/s) -> half of the cores, at most 8
+    // measured on the B200 box (16 cores, tools/h2d_staged_probe.py): the copy threads saturate around 8 (torch's pageable
+    // copy: 12-20 GB/s, pinned: 55 GB/s) -> half of the cores, at most 8, one of them the issuing caller
     const int hw = (int)std::thread::hardware_concurrency();
     int n = hw > 0 ? (hw / 2 < 8 ? hw / 2 : 8) : 4;
     if (const char* env = getenv("MVMATCH_STAGE_THREADS")) n = atoi(env);
@@ -102,24 +150,55 @@ class Stager {
   int ensure(int dev) {
     if (ring_ && ring_dev_ == dev) return 0;
     if (ring_) {  // another device became current: the events belong to the old one
+      for (auto& pb : pending_) cudaEventSynchronize(events_[pb.ev]);
+      pending_.clear();
+      drained_.store(next_id_, std::memory_order_release);
       cudaFreeHost(ring_);
       ring_ = nullptr;
       for (auto& ev : events_) cudaEventDestroy(ev);
       events_.clear();
     }
-    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&ring_), STAGE_SLOTS * STAGE_CHUNK, cudaHostAllocDefault);
+    cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&ring_), (size_t)STAGE_SLOTS * STAGE_CHUNK, cudaHostAllocDefault);
     if (e != cudaSuccess) {
       ring_ = nullptr;
       return (int)e;
     }
-    events_.resize(STAGE_SLOTS);
+    events_.resize(STAGE_EVENTS);
     for (auto& ev : events_) {
       e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
       if (e != cudaSuccess) return (int)e;
     }
-    used_.assign(STAGE_SLOTS, false);
     ring_dev_ = dev;
     return 0;
+  }
+
+  // DMAs whose event has fired free their ring slots: every chunk id below drained_ may be overwritten
+  void poll_drained() {
+    while (!pending_.empty()) {
+      if (cudaEventQuery(events_[pending_.front().ev]) != cudaSuccess) {
+        (void)cudaGetLastError();  // cudaErrorNotReady is not an error: do not leave it for the next launch check
+        break;
+      }
+      drained_.store(pending_.front().end_id, std::memory_order_release);
+      pending_.pop_front();
+    }
+  }
+
+  // claim one chunk and copy it into its ring slot (strictly after the DMA of the chunk that used the slot before)
+  bool stage_one(Job& job) {
+    const size_t i = job.next.fetch_add(1);
+    if (i >= job.chunks) return false;
+    const unsigned long long g = job.base + i;
+    while (g >= drained_.load(std::memory_order_acquire) + STAGE_SLOTS) {
+      if (workers_.empty()) poll_drained();  // single-threaded: nobody else polls
+      else cpu_relax();
+      if (stop_flag_.load(std::memory_order_relaxed)) return false;
+    }
+    const size_t off = i * STAGE_CHUNK;
+    const size_t len = (off + STAGE_CHUNK <= job.bytes) ? STAGE_CHUNK : job.bytes - off;
+    std::memcpy(ring_ + (size_t)(g % STAGE_SLOTS) * STAGE_CHUNK, job.src + off, len);
+    job.ready[i].store(1, std::memory_order_release);
+    return true;
   }
 
   void loop() {
@@ -127,10 +206,13 @@ class Stager {
     for (;;) {
       Job* job = nullptr;
       {
-        // uploads come in bursts (four tensors per image pair): spin briefly before going to sleep, a condition-variable
-        // wake-up costs more than staging a chunk
-        for (int spin = 0; spin < 20000; ++spin) {
-            if (stop_flag_.load(std::memory_order_relaxed) || gen_atomic_.load(std::memory_order_acquire) != seen) break;
+        // uploads come in bursts (four tensors per image pair, a pair every millisecond): spin for ~300 us before going to
+        // sleep, a condition-variable wake-up costs more than staging several chunks
+        const auto t0 = std::chrono::steady_clock::now();
+        for (int spin = 0;; ++spin) {
+          if (stop_flag_.load(std::memory_order_relaxed) || gen_atomic_.load(std::memory_order_acquire) != seen) break;
+          cpu_relax();
+          if ((spin & 1023) == 1023 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(300)) break;
         }
         std::unique_lock<std::mutex> lk(m_);
         cv_.wait(lk, [&] { return stop_ || (job_ && generation_ != seen); });
@@ -139,8 +221,8 @@ class Stager {
         job = job_;
         ++active_;
       }
-      cudaSetDevice(job->device);
-      work(*job);
+      while (stage_one(*job)) {
+      }
       {
         std::lock_guard<std::mutex> lk(m_);
         --active_;
@@ -149,45 +231,13 @@ class Stager {
     }
   }
 
-  // claim chunks until none is left: chunk i uses slot i mod SLOTS, strictly after the DMA of chunk i - SLOTS
-  void work(Job& job) {
-    for (;;) {
-      const size_t i = job.next.fetch_add(1);
-      if (i >= job.chunks) break;
-      const int slot = (int)(i % STAGE_SLOTS);
-      const size_t off = i * STAGE_CHUNK;
-      const size_t len = (off + STAGE_CHUNK <= job.bytes) ? STAGE_CHUNK : job.bytes - off;
-      char* pin = ring_ + (size_t)slot * STAGE_CHUNK;
-      cudaError_t e = cudaSuccess;
-      {
-        // slot ownership: chunk i may touch the slot only after chunk i - SLOTS has recorded its event
-        std::unique_lock<std::mutex> lk(slot_m_);
-        slot_cv_.wait(lk, [&] { return slot_turn_[slot] == i / STAGE_SLOTS; });
-      }
-      if (used_[slot]) e = cudaEventSynchronize(events_[slot]);  // its previous DMA has drained
-      if (e == cudaSuccess) {
-        std::memcpy(pin, job.src + off, len);
-        e = cudaMemcpyAsync(job.dst + off, pin, len, cudaMemcpyHostToDevice, job.stream);
-      }
-      if (e == cudaSuccess) e = cudaEventRecord(events_[slot], job.stream);
-      used_[slot] = true;
-      {
-        std::lock_guard<std::mutex> lk(slot_m_);
-        slot_turn_[slot] = i / STAGE_SLOTS + 1;
-      }
-      slot_cv_.notify_all();
-      if (e != cudaSuccess) job.error.store((int)e);
-      if (job.done.fetch_add(1) + 1 == job.chunks) {
-        // last chunk of the call: reset the slot turns for the next call
-        std::lock_guard<std::mutex> lk(slot_m_);
-        for (auto& t : slot_turn_) t = 0;
-      }
-    }
-    done_cv_.notify_all();
-  }
+  struct PendingBatch {
+    int ev;
+    unsigned long long end_id;  // chunk ids below this are drained once the event has fired
+  };
 
-  std::mutex call_mutex_, m_, slot_m_;
-  std::condition_variable cv_, done_cv_, slot_cv_;
+  std::mutex call_mutex_, m_;
+  std::condition_variable cv_, done_cv_;
   std::vector<std::thread> workers_;
   Job* job_ = nullptr;
   unsigned long long generation_ = 0;
@@ -198,8 +248,10 @@ class Stager {
   char* ring_ = nullptr;
   int ring_dev_ = -1;
   std::vector<cudaEvent_t> events_;
-  std::vector<char> used_;
-  size_t slot_turn_[STAGE_SLOTS] = {};
+  std::deque<PendingBatch> pending_;       // issued DMA runs, oldest first (caller thread only)
+  unsigned long long next_id_ = 0;         // ring position of the next call's chunk 0 (caller thread only)
+  unsigned int ev_next_ = 0;
+  std::atomic<unsigned long long> drained_{0};
 };
 
 }  // namespace

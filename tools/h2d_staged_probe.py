@@ -11,7 +11,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 mv = importlib.import_module("midvision-probe_b200")
 L = mv._lib
-nbytes = 64 << 20
+nbytes = int(sys.argv[1]) if len(sys.argv) > 1 else 64 << 20
 src = torch.randn(nbytes // 4)
 pin = src.clone().pin_memory()
 dst = torch.empty(nbytes // 4, device="cuda")
