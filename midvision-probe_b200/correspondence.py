@@ -960,10 +960,9 @@ def _graphed_helper(kind, feat_0, feat_1, grid_0, grid_1, num_corr, ratio_test, 
     layout = "hwc" if (_is_channel_last(feat_0) and _is_channel_last(feat_1)) else "chw"
     fdt = feat_0.dtype if (feat_0.dtype == feat_1.dtype and feat_0.dtype in _FEAT_DTYPES) else torch.float32
     on_host = feat_0.device.type == "cpu"
-    # two graphs (upload of image 0 behind image 1's kernels) pay off for pinned sources (1369 -> 1536 pairs/s, NAVI-shaped);
-    # pageable ones are staged by host threads, which the interleaved replay only delays (578 -> 458)
-    split = on_host and bool(_CFG["helper_split"]) and ((feat_0.is_pinned() and feat_1.is_pinned()) or
-                                                      os.environ.get("MVMATCH_HELPER_SPLIT_PAGEABLE", "0") == "1")
+    # two graphs (upload of image 0 behind image 1's kernels): 1369 -> 1536 pairs/s NAVI-shaped from pinned sources; pageable
+    # sources (staged by host threads, every CUDA call on this thread since round 2) gain 2 % (811 -> 829)
+    split = on_host and bool(_CFG["helper_split"])
     # the intrinsics are NOT part of the key: they live in device memory and are refreshed per call (gm.load)
     key = (on_host, split, kind, tuple(feat_0.shape), tuple(grid_0.shape), int(num_corr), bool(ratio_test), _CFG["dtype"], _CFG["cluster"], _CFG["rows"], _CFG["k1_grid"], _CFG["lowrank"], _CFG["lowrank_k3"], fdt,
            dev.index, layout)
