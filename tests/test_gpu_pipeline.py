@@ -608,3 +608,30 @@ def test_two_gpu_nccl_counts(tmp_path, mv, syn):
     mp.spawn(_nccl_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert torch.equal(torch.load(os.path.join(tmp_path, f"nccl_r{r}.pt")), single.hits.cpu())
+
+
+def test_staged_upload_of_pageable_memory_is_exact(mv):
+    """mv_h2d_staged (threaded pinned ring, csrc/stage.cu): odd sizes, transfers larger than the 16 MiB ring, many calls back
+    to back on one stream (the ring position runs on across calls) and behind a long kernel -- the device copy must equal the
+    pageable source bit for bit, also when the source is overwritten right after the call returns (every chunk is staged by then)."""
+    from ctypes import c_void_p
+
+    L = mv._lib
+    st = torch.cuda.current_stream()
+    g = torch.Generator().manual_seed(3)
+    sizes = [1, 7, 4096, (1 << 18) - 3, (1 << 18) + 5, 9633792, (1 << 24) + 12345, 40_000_001, 150_528, 9633792, 150_528]
+    busy = torch.randn(4096, 4096, device="cuda")
+    dsts, refs = [], []
+    for rep in range(2):
+        for _ in range(3):
+            busy = busy @ busy * 1e-3  # keep the stream busy so that ring slots have to wait for their DMAs
+        for nb in sizes:
+            src = torch.randint(0, 256, (nb,), dtype=torch.uint8, generator=g)
+            dst = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+            L.call("mv_h2d_staged", c_void_p(dst.data_ptr()), c_void_p(src.data_ptr()), nb, c_void_p(st.cuda_stream))
+            refs.append(src.clone())
+            src.zero_()  # the call has returned: the source may be modified
+            dsts.append(dst)
+    torch.cuda.synchronize()
+    for d, r in zip(dsts, refs):
+        assert torch.equal(d.cpu(), r)
