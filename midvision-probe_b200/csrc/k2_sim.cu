@@ -449,7 +449,11 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
         // flight); behind a branch every taken group pays the CREDUX -> FSETP -> VOTE latency chain, plus one more barrier
         // per tile.  Without any column work the K = 312 launch takes 0.267 ms: the rows + TMEM reads are the larger part.
         // Also measured and rejected: the TMEM read of chunk c + 1 in flight while chunk c is processed (two register
-        // buffers, 168 registers): 0.375 vs 0.340 ms at K = 312, 0.432 vs 0.411 ms at 19200^2 x 768.)
+        // buffers, 168 registers): 0.375 vs 0.340 ms at K = 312, 0.432 vs 0.411 ms at 19200^2 x 768.  And: keeping the A
+        // tiles of a row block resident in shared memory for its whole column sweep at K <= 384 (the ring then carries B
+        // tiles only, a third less L2 -> shared-memory traffic): 0.337 vs 0.339 ms at K = 312 -- no change, and K = 256 takes
+        // 0.354 ms: at small K the tile time (~4.7 us per 128 x 256 tile) does not depend on K or on the operand traffic at
+        // all, it is the epilogue's own instruction stream (TMEM reads alone: 128 KB per tile at 64 B/clk = 2048 of ~9000 clk).)
 #ifndef MV_K2_EXP_NO_COLS
 #pragma unroll
         for (int q = 0; q < 32; q += 2) {
