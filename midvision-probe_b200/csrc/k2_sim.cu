@@ -58,7 +58,10 @@ template <bool PAIR> struct Ring {
   static constexpr int STAGES = PAIR ? MV_K2_PAIR_STAGES : 4;
   static constexpr int BYTES = STAGES * STAGE_BYTES;
 };
-constexpr int K2_THREADS = 384;   // 4 control warps + 8 epilogue warps
+constexpr int K2_THREADS = 640;   // 4 control warps + 16 epilogue warps
+constexpr int EPI_PARTS = 4;      // epilogue warps per TMEM lane quarter: each owns 256 / EPI_PARTS columns of the tile
+constexpr int EPI_CW = 16;        // columns per TMEM read (chunk)
+constexpr int PART_COLS = BN / EPI_PARTS, PART_CHUNKS = PART_COLS / EPI_CW;
 constexpr int EPI_WARP0 = 4;
 constexpr int COL_SMEM_BYTES = 2 * 4 * BN * 8;  // [2 buffers][4 warps][256 columns] (max bits, ballot)
 template <bool PAIR> constexpr int k2_smem_bytes() { return 1024 /*align slack*/ + Ring<PAIR>::BYTES + COL_SMEM_BYTES + 256 /*barriers*/; }
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(smem_u32(&bars->tmem_full[a]), 1);
-      mbar_init(smem_u32(&bars->tmem_empty[a]), PAIR ? 16 : 8);  // PAIR: the epilogue warps of BOTH CTAs (rank 0's barrier)
+      mbar_init(smem_u32(&bars->tmem_empty[a]), PAIR ? 8 * EPI_PARTS : 4 * EPI_PARTS);  // PAIR: the epilogue warps of BOTH CTAs (rank 0's barrier)
     }
     mbar_fence_init();
   }
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
     // two warps per TMEM lane quarter (one per SM sub-partition pair), each owning half of the tile's columns:
     // with a single epilogue warp per scheduler the dependent-issue latencies of the reduce chain are exposed
     const int ew = warp & 3;           // TMEM lane quarter this warp may read
-    const int half = (warp - EPI_WARP0) >> 2;  // columns [128 * half, 128 * half + 128) of the tile
+    const int half = (warp - EPI_WARP0) >> 2;  // "part": columns [PART_COLS * half, PART_COLS * half + PART_COLS) of the tile
     const int e = ew * 32 + lane;      // row inside the tile; also column-combine slot
     float m1 = -CUDART_INF_F, m2 = -CUDART_INF_F;
     int i1 = -1, i2 = -1;
@@ -327,7 +330,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
     uint32_t acc_phase = 0;
 
     auto flush = [&](int sb) {
-      p.partial[((size_t)(cluster_id + sb) * (BM * MC) + rank * BM + e) * 2 + half] =
+      p.partial[((size_t)(cluster_id + sb) * (BM * MC) + rank * BM + e) * EPI_PARTS + half] =
           make_float4(m1, __int_as_float(i1), m2, __int_as_float(i2));
     };
 
@@ -344,11 +347,12 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
         tc_fence_after();
         const uint32_t taddr = tmem_base + (uint32_t)acc * BN + ((uint32_t)(ew * 32) << 16);
 #pragma unroll 1
-        for (int ch = half * 4; ch < half * 4 + 4; ++ch) {
-          float v[32];
-          tmem_ld_32x32(taddr + ch * 32, v);
+        for (int ch = half * PART_CHUNKS; ch < (half + 1) * PART_CHUNKS; ++ch) {
+          float v[EPI_CW];
+          tmem_ld_32x16(taddr + ch * EPI_CW, v);
 #pragma unroll
-          for (int q = 0; q < 8; ++q) __stcg(frag_mine + (size_t)(ch * 8 + q) * BM, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
+          for (int q = 0; q < EPI_CW / 4; ++q)
+            __stcg(frag_mine + (size_t)(ch * (EPI_CW / 4) + q) * BM, make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]));
         }
         tc_fence_before();
         __syncwarp();
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
           else mbar_arrive(smem_u32(&bars->tmem_empty[acc]));
         }
         __threadfence();
-        named_bar_sync(3, 256);  // all eight epilogue warps have stored and fenced
+        named_bar_sync(5, 128 * EPI_PARTS);  // all epilogue warps have stored and fenced
         if (threadIdx.x == EPI_WARP0 * 32) st_release_gpu(p.flags + blockIdx.x, 1u);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
@@ -384,32 +388,32 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
       }
 
 #pragma unroll 1
-      for (int ch = half * 4; ch < half * 4 + 4; ++ch) {
-        float v[32];
-        tmem_ld_32x32(taddr + ch * 32, v);
+      for (int ch = half * PART_CHUNKS; ch < (half + 1) * PART_CHUNKS; ++ch) {
+        float v[EPI_CW];
+        tmem_ld_32x16(taddr + ch * EPI_CW, v);
         if (add_frag) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 f = __ldcg(frag_next + (size_t)(ch * 8 + q) * BM);
+          for (int q = 0; q < EPI_CW / 4; ++q) {
+            const float4 f = __ldcg(frag_next + (size_t)(ch * (EPI_CW / 4) + q) * BM);
             v[4 * q] += f.x;
             v[4 * q + 1] += f.y;
             v[4 * q + 2] += f.z;
             v[4 * q + 3] += f.w;
           }
         }
-        const int cb = col0 + ch * 32;
+        const int cb = col0 + ch * EPI_CW;
         if (edge) {
 #pragma unroll
-          for (int q = 0; q < 32; ++q) v[q] = (row_ok && cb + q < m) ? v[q] : -CUDART_INF_F;
+          for (int q = 0; q < EPI_CW; ++q) v[q] = (row_ok && cb + q < m) ? v[q] : -CUDART_INF_F;
         }
         if (p.S_out != nullptr && row_ok) {  // similarity-only consumers (MaskCut's affinity): the tile goes to memory as well
           float* dst = p.S_out + (size_t)(row0 + e) * p.ld_s + cb;
-          if (cb + 32 <= m) {
+          if (cb + EPI_CW <= m) {
 #pragma unroll
-            for (int q = 0; q < 32; q += 4) *reinterpret_cast<float4*>(dst + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+            for (int q = 0; q < EPI_CW; q += 4) *reinterpret_cast<float4*>(dst + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
           } else {
 #pragma unroll
-            for (int q = 0; q < 32; ++q)
+            for (int q = 0; q < EPI_CW; ++q)
               if (cb + q < m) dst[q] = v[q];
           }
         }
@@ -418,16 +422,16 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
 #ifdef MV_K2_EXP_NO_ROWS
         if (v[ch] > m2) { m2 = v[ch]; i2 = cb; }
 #else
-        float g[4];
+        float g[EPI_CW / 8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < EPI_CW / 8; ++u) {
           const float a = fmaxf(fmaxf(v[8 * u], v[8 * u + 1]), fmaxf(v[8 * u + 2], v[8 * u + 3]));
           const float b = fmaxf(fmaxf(v[8 * u + 4], v[8 * u + 5]), fmaxf(v[8 * u + 6], v[8 * u + 7]));
           g[u] = fmaxf(a, b);
         }
-        if (fmaxf(fmaxf(g[0], g[1]), fmaxf(g[2], g[3])) > m2) {
+        if (fmaxf(g[0], g[1]) > m2) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) {
+          for (int u = 0; u < EPI_CW / 8; ++u) {
             if (g[u] > m2) {
 #pragma unroll
               for (int q = 8 * u; q < 8 * u + 8; ++q) {
@@ -456,12 +460,12 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
         // all, it is the epilogue's own instruction stream (TMEM reads alone: 128 KB per tile at 64 B/clk = 2048 of ~9000 clk).)
 #ifndef MV_K2_EXP_NO_COLS
 #pragma unroll
-        for (int q = 0; q < 32; q += 2) {
+        for (int q = 0; q < EPI_CW; q += 2) {
           const float x0 = warp_max_f32(v[q]), x1 = warp_max_f32(v[q + 1]);
           const uint32_t b0 = __ballot_sync(0xffffffffu, v[q] == x0);
           const uint32_t b1 = __ballot_sync(0xffffffffu, v[q + 1] == x1);
           if (lane == 0)
-            *reinterpret_cast<uint4*>(colw + ch * 32 + q) = make_uint4(__float_as_uint(x0), b0, __float_as_uint(x1), b1);
+            *reinterpret_cast<uint4*>(colw + ch * EPI_CW + q) = make_uint4(__float_as_uint(x0), b0, __float_as_uint(x1), b1);
         }
 #endif
       }
@@ -473,11 +477,11 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
         else mbar_arrive(smem_u32(&bars->tmem_empty[acc]));
       }
 
-      // combine the 4 warps' column results of this half; thread e owns column e + 128 * half
+      // combine the 4 warps' column results of this part; thread e < PART_COLS owns column e + PART_COLS * half
       named_bar_sync(1 + half, 128);
       const uint2* colr = col_smem + (size_t)acc * (4 * BN);
-      {
-        const int c = e + half * 128;
+      if (e < PART_COLS) {
+        const int c = e + half * PART_COLS;
         float best = -CUDART_INF_F;
         int brow = 0;
 #pragma unroll
@@ -528,12 +532,19 @@ __global__ void k2_merge_rows_kernel(int clusters, int kblocks, int streamk, con
     const int c_first = sched_owner(s, (unsigned long long)sb * s.n_ct);
     const int c_last = sched_owner(s, (unsigned long long)(sb + 1) * s.n_ct - 1);
     for (int c = c_first; c <= c_last; ++c) {
-      const float4* rec = partial + ((size_t)(c + sb) * (BM * MC) + (i - sb * BM * MC)) * 2;
-      const float4 r = rec[0], r2 = rec[1];  // the two column halves of every tile
-      const float xs[4] = {r.x, r.z, r2.x, r2.z};
-      const int js[4] = {__float_as_int(r.y), __float_as_int(r.w), __float_as_int(r2.y), __float_as_int(r2.w)};
+      const float4* rec = partial + ((size_t)(c + sb) * (BM * MC) + (i - sb * BM * MC)) * EPI_PARTS;
+      float xs[2 * EPI_PARTS];
+      int js[2 * EPI_PARTS];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int q = 0; q < EPI_PARTS; ++q) {  // the column parts of every tile, in column order
+        const float4 r = rec[q];
+        xs[2 * q] = r.x;
+        xs[2 * q + 1] = r.z;
+        js[2 * q] = __float_as_int(r.y);
+        js[2 * q + 1] = __float_as_int(r.w);
+      }
+#pragma unroll
+      for (int u = 0; u < 2 * EPI_PARTS; ++u) {
         if (js[u] < 0) continue;
         if (better(xs[u], js[u], m1, i1)) { m2 = m1; i2 = i1; m1 = xs[u]; i1 = js[u]; }
         else if (better(xs[u], js[u], m2, i2)) { m2 = xs[u]; i2 = js[u]; }
@@ -598,7 +609,7 @@ int make_operand_map(CUtensorMap* tm, const void* base, int rows, int C, int ld,
 
 size_t k2_partial_bytes(int n_max, int mc, int clusters) {
   const int n_sb_max = (n_max + BM * mc - 1) / (BM * mc);
-  return ((size_t)(clusters + n_sb_max) * (BM * mc) * 2 * sizeof(float4) + 255) / 256 * 256;
+  return ((size_t)(clusters + n_sb_max) * (BM * mc) * EPI_PARTS * sizeof(float4) + 255) / 256 * 256;
 }
 // stream-K area behind the partial records: one flag and one accumulator-fragment slot per CTA of the grid
 constexpr size_t SK_FLAG_BYTES = 1024;  // >= 4 * 148, keeps the fragments 256-byte aligned
