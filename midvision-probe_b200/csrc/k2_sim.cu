@@ -5,7 +5,7 @@
 //   evals/utils/correspondence.py:14-23   faiss.GpuIndexFlatL2(res, C).add(target).search(query, k<=2)
 //   evaluate_spair_correspondence.py:82-83 einsum("k f, f h w -> k h w") + argmax_2d   (row arg-max)
 //
-// Structure (one persistent CTA per SM, 12 warps, warp-specialised):
+// Structure (one persistent CTA per SM, 20 warps, warp-specialised):
 //   warp 0      TMA producer : A tile 128 x 128B and B tile 256 x 128B per k-block into a 4-stage
 //                              128B-swizzled shared-memory ring; with MC > 1 the B tile is loaded in MC
 //                              slices, each multicast to the MC CTAs of the cluster (they work on MC
@@ -13,8 +13,10 @@
 //   warp 1      MMA issuer   : one thread, tcgen05.mma M=128 N=256 K=16 (bf16) / K=8 (tf32), fp32
 //                              accumulators in TMEM, two accumulator buffers (2 x 256 = all 512 columns)
 //   warp 2      TMEM allocator
-//   warps 4..11 epilogue     : two warps per TMEM lane quarter, each owning half of the tile's columns;
-//                              tcgen05.ld 32 rows x 32 columns per warp; thread = one row of S.
+//   warps 4..19 epilogue     : four warps per TMEM lane quarter, each owning a quarter of the tile's columns;
+//                              tcgen05.ld 32 rows x 16 columns per warp; thread = one row of S.  (Round 2: 16 warps
+//                              instead of 8 -- the epilogue was latency-bound at IPC 1.2 per SM; 19200^2 x 768 went
+//                              from 0.411 to 0.384 ms, the 312-column low-rank product from 0.328 to 0.277 ms.)
 //                              rows   : running (max1, idx1, max2, idx2) in registers across the column
 //                                       tiles of a row block; a chunk is only scanned when its maximum
 //                                       beats the current second best
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1)
     }
   } else if (warp >= EPI_WARP0) {
     // ===================================== epilogue =========================================
-    // two warps per TMEM lane quarter (one per SM sub-partition pair), each owning half of the tile's columns:
+    // four warps per TMEM lane quarter, each owning a quarter of the tile's columns:
     // with a single epilogue warp per scheduler the dependent-issue latencies of the reduce chain are exposed
     const int ew = warp & 3;           // TMEM lane quarter this warp may read
     const int half = (warp - EPI_WARP0) >> 2;  // "part": columns [PART_COLS * half, PART_COLS * half + PART_COLS) of the tile
