@@ -814,7 +814,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stress", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
-    ap.add_argument("--lanes", type=int, default=4, help="pairs in flight on separate streams (CUDA-graph arm)")
+    ap.add_argument("--lanes", type=int, default=6, help="pairs in flight on separate streams (CUDA-graph arm)")
     ap.add_argument("--feat-layout", default="chw", choices=["chw", "hwc"],
                     help="memory layout of the (C, h, w) feature tensors handed to the path: chw = contiguous, as the "
                          "reference's tokens_to_output returns them; hwc = channel-last views (ViT token order), no transpose kernel")
