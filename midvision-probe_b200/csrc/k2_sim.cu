@@ -619,10 +619,10 @@ size_t k2_streamk_bytes(int ctas) { return SK_FLAG_BYTES + (size_t)ctas * FRAG_B
 
 // The K-cut schedule is OFF by default: measured on B200 at the NAVI shape (tools/k2_streamk_ab.py, same process,
 // kernel timed alone) 117.6 us against 111.6 us of the tile-granular schedule back to back, 125 against 122 us for
-// isolated launches.  Equalising the k-blocks per SM buys nothing because the kernel is not limited per SM: it pulls
-// 1.29 GB of operand tiles out of L2 per launch (11.6 TB/s, the chip's ~6300 B/clk L2 slice throughput) and runs at the
-// power-capped sustained rate of the chip, so the SMs that finish a tile early simply leave more L2 bandwidth to the
-// others; the K-cut only adds 38 MB of fragment traffic and one extra epilogue per SM.  MVMATCH_K2_STREAMK=1 or
+// isolated launches.  Equalising the k-blocks per SM buys nothing because the kernel is not limited per SM: it runs at the
+// power-capped sustained rate of the chip (sw_power_cap in every run; frac_sustained 1.0 in the bench line), so the SMs that
+// finish early lower the power draw and the others clock higher; the K-cut only adds 38 MB of fragment traffic and one
+// extra epilogue per SM.  MVMATCH_K2_STREAMK=1 or
 // mv_k2_set_streamk(1) switches it on (tests/test_gpu_k2.py runs it).
 int g_k2_streamk = -1;
 int k2_streamk_enabled() {
