@@ -199,3 +199,49 @@ def test_full_size_scannet_pair_same_result_with_and_without(mv, syn):
     cclear = o["col_gap"] > 1e-3  # and the mutual flag wherever both the row's and its column's decision are clear
     both = clear & cclear[o["row_idx"][:, 0]]
     assert torch.equal(r.mutual.cpu().bool()[both], o["mutual"][both])
+
+
+@pytest.mark.parametrize("kind", ["xyz", "depth"])
+@pytest.mark.parametrize("split", [False, True])
+def test_lowrank_graph_replay_equals_eager(mv, syn, lowrank_on, kind, split):
+    """the exact low-rank route inside the captured CUDA graphs (one graph, and the split target / query pair of graphs the
+    synchronous helper replays; device-resident live counts) gives the integer counts and the selected matches of the eager
+    launches with host-known counts, pair after pair."""
+    ev = mv.evaluation
+    thr3, thr2 = [0.01, 0.02, 0.05], [5.0, 25.0, 50.0]
+    if kind == "xyz":
+        pairs = [syn.navi_pair(i, C=256, h=14, w=14, H=56, W=56, radius=20.0) for i in range(3)]
+        gk = ("xyz_grid_0", "xyz_grid_1", "intrinsics")
+    else:
+        pairs = [syn.scannet_pair(i, C=256, h=15, w=21, H=60, W=84) for i in range(3)]  # 315 source pixels: not a multiple of 8
+        gk = ("depth_0", "depth_1", "K")
+    gm = ev.GraphedPairMatcher(kind, tuple(pairs[0]["feat_0"].shape), tuple(pairs[0][gk[0]].shape), 300, K=pairs[0].get("K"),
+                               split=split).capture()
+    assert gm.lowrank_exact
+    for p in pairs + pairs[:1]:
+        a = ev.RecallAccumulator(thr3, thr2, device="cuda")
+        b = ev.RecallAccumulator(thr3, thr2, device="cuda")
+        gm.load(p["feat_0"], p["feat_1"], p[gk[0]], p[gk[1]])
+        rg = gm.run(a, p["Rt"], p[gk[2]])
+        if kind == "xyz":
+            re_ = ev.match_and_score_xyz(p["feat_0"], p["feat_1"], p[gk[0]], p[gk[1]], p[gk[2]], p["Rt"], 300, b, sync=True)
+        else:
+            re_ = ev.match_and_score_depth(p["feat_0"], p["feat_1"], p[gk[0]], p[gk[1]], p[gk[2]], p["Rt"], 300, b, sync=True)
+        assert a.hits.cpu().tolist() == b.hits.cpu().tolist()
+        k = re_.k
+        assert int(rg.k_dev.item()) == k
+        assert torch.equal(rg.sel_src[:k], re_.sel_src[:k]) and torch.equal(rg.sel_weight[:k], re_.sel_weight[:k])
+
+
+def test_lowrank_with_few_live_points_and_border_taps(mv, syn, lowrank_on):
+    """mostly empty depth maps (a few hundred live points, many of them at the image border where bilinear taps fall outside
+    the map and are dropped) through the low-rank route: the reference's matches."""
+    C_ = mv.correspondence
+    for seed in range(2):
+        p = syn.scannet_pair(10 + seed, C=128, h=8, w=10, H=48, W=60, zero_frac=0.9)
+        got = C_.estimate_correspondence_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], p["K"].clone(), 100)
+        ref = restated.estimate_correspondence_depth(p["feat_0"], p["feat_1"], p["depth_0"], p["depth_1"], p["K"].clone(), 100)
+        gset = {tuple(a.tolist()) + tuple(b.tolist()) for a, b in zip(got[0].cpu(), got[1].cpu())}
+        rset = {tuple(a.tolist()) + tuple(b.tolist()) for a, b in zip(ref[0], ref[1])}
+        assert got[0].shape == ref[0].shape
+        assert len(gset & rset) >= int(0.97 * len(rset)), (seed, len(gset & rset), len(rset))
