@@ -422,6 +422,16 @@ def run_dense(ctx, workload, steps, warmup, fixed_pairs=0, light=False):
         del gm
         return rec
 
+    # the same helper fed 16-bit feature maps from pinned memory -- what a backbone under bf16 autocast hands over (the helper
+    # uploads them as they are and widens them exactly on the device: tests/test_gpu_pipeline.py::test_16bit_feature_maps_*):
+    # half the PCIe bytes of the fp32 arm.  Informational: the headline e2e above is the fp32 hand-over of the reference.
+    if args.feat_dtype == "f32":
+        pool_16 = [{k: (pin(v.to(torch.bfloat16)) if (torch.is_tensor(v) and k in ("feat_0", "feat_1")) else (pin(v) if torch.is_tensor(v) else v))
+                    for k, v in p.items()} for p in pool_host]
+        v16, _ = time_helper(pool_16, max(PAIRS_PER_STEP, n_calls // 2))
+        rec["e2e_bf16_features"] = {"value": v16, "unit": "pairs/s", "host_memory": "pinned, bf16 feature maps (autocast backbone)",
+                                    "h2d_bytes_per_step": h2d - PAIRS_PER_STEP * sum(pool_host[0][k].numel() * 2 for k in ("feat_0", "feat_1"))}
+
     # the same synchronous helper with DEVICE-resident tensors (a caller that keeps the backbone output on the GPU,
     # SURVEY 8f.1): no upload, results stay on the device, one host sync per call for the match count
     hd_value, _ = time_helper(pool_dev, n_calls, n_warm=4)
