@@ -235,7 +235,15 @@ __global__ void __launch_bounds__(SPB_THREADS) spair_batch_kernel(SpairBatchPara
 // own 4-byte global loads, 16 in flight, and sat on their DRAM latency (ncu: 45 % of the samples on long-scoreboard
 // stalls at 2.2 TB/s); here the bytes in flight do not depend on registers or occupancy.  The arithmetic (order of every
 // sum) is that of the first form, so the results are bit-identical.
-constexpr int SPS_CONS = 256;               // consumer threads: thread = pixel in the norm / heat passes
+// consumer threads per CTA.  Measured: 512 (16 consumer warps per CTA, one pixel tile per warp in the tensor-core pass, 54
+// registers, still two CTAs per SM) runs 2.16 M pairs/s against 2.56 M for 256 -- the per-stage waits / releases grow with the warp
+// count while the light passes (norms, key-point vectors) do not get shorter
+#ifndef SPS_CONS_N
+#define SPS_CONS_N 256
+#endif
+constexpr int SPS_CONS = SPS_CONS_N;        // consumer threads: thread = pixel in the norm / heat passes
+constexpr int SPS_WARPS = SPS_CONS / 32;
+constexpr int SPS_MT = (16 + SPS_WARPS - 1) / SPS_WARPS;  // m16 pixel tiles per warp in the tensor-core pass (h*w <= 256: 16 tiles)
 constexpr int SPS_THREADS = SPS_CONS + 32;  // + one producer warp
 constexpr int SPS_CC = 8;                   // channels per stage
 // ring depth.  Measured (same box): 4 stages x 2 CTAs per SM 2.56 M pairs/s; 12 or 20 stages with ONE CTA per SM (the ring then
@@ -262,6 +270,7 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 // one 8-channel stage = one K step, 3xTF32 -- instead of 21 FFMA + 6 LDS per channel and pixel.
 template <int KT, bool MMA>
 __global__ void __launch_bounds__(SPS_THREADS, SPS_STAGES_N > 5 ? 1 : 2) spair_stream_kernel(SpairBatchParams p) {
+  static_assert(SPS_MT == 1 || SPS_MT == 2, "tile loop");
   using namespace sm100;
   extern __shared__ __align__(16) float4 sps_dyn[];
   __shared__ SpairScoreShared score;
@@ -396,15 +405,15 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_STAGES_N > 5 ? 1 : 2) spair_s
         static_assert(SPS_CC == 8, "one stage = one m16n8k8 K step");
         constexpr int NT8 = (KT + 7) / 8;
         const int g = lane >> 2, t = lane & 3;
-        float d[2][NT8][4];
-        float ssr[2][2];
+        float d[SPS_MT][NT8][4];
+        float ssr[SPS_MT][2];
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < SPS_MT; ++i) {
           ssr[i][0] = ssr[i][1] = 0.f;
 #pragma unroll
           for (int j = 0; j < NT8; ++j) d[i][j][0] = d[i][j][1] = d[i][j][2] = d[i][j][3] = 0.f;
         }
-        const int ntile = (hw + 15) >> 4;  // this warp owns tiles wid and wid + 8
+        const int ntile = (hw + 15) >> 4;  // this warp owns tiles wid (and wid + SPS_WARPS)
         for (int ck = 0; ck < nchunk; ++ck) {
           mbar_wait(smem_u32(&full[stage]), phase);
           const float* st = ring + (size_t)stage * chunk_floats;
@@ -418,8 +427,8 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_STAGES_N > 5 ? 1 : 2) spair_s
             split_tf32(b1, bh[j][1], bl[j][1]);
           }
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const int mt = wid + 8 * i;
+          for (int i = 0; i < SPS_MT; ++i) {
+            const int mt = wid + SPS_WARPS * i;
             if (mt < ntile) {  // warp-uniform
               const int p0 = mt * 16 + g;
               const float a0 = st[t * hw + p0], a1 = st[t * hw + p0 + 8];            // rows beyond h*w read the following
@@ -451,15 +460,15 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_STAGES_N > 5 ? 1 : 2) spair_s
             float v = -CUDART_INF_F;
             int bi = 0x7fffffff;
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < SPS_MT; ++i) {
 #pragma unroll
               for (int r = 0; r < 2; ++r) {
-                const int pxl = (wid + 8 * i) * 16 + g + 8 * r;
+                const int pxl = (wid + SPS_WARPS * i) * 16 + g + 8 * r;
                 float ss = ssr[i][r];
                 ss += __shfl_xor_sync(0xffffffffu, ss, 1);
                 ss += __shfl_xor_sync(0xffffffffu, ss, 2);
                 const float hv = __fdiv_rn(d[i][j][2 * r + e2], fmaxf(sqrtf(ss), SPB_NORM_EPS));
-                if (wid + 8 * i < ntile && pxl < hw && (hv > v || (hv == v && pxl < bi))) {
+                if (wid + SPS_WARPS * i < ntile && pxl < hw && (hv > v || (hv == v && pxl < bi))) {
                   v = hv;
                   bi = pxl;
                 }
@@ -561,7 +570,7 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_STAGES_N > 5 ? 1 : 2) spair_s
 bool spair_stream_ok(const SpairBatchParams& p) {
   static const int off = getenv("MVMATCH_SPAIR_STREAM") && getenv("MVMATCH_SPAIR_STREAM")[0] == '0';
   const int hw = p.h * p.w;
-  return !off && hw <= SPS_CONS && p.C % SPS_CC == 0 && (hw * SPS_CC) % 4 == 0 && ((uintptr_t)p.feats & 15) == 0 &&
+  return !off && hw <= 256 && p.C % SPS_CC == 0 && (hw * SPS_CC) % 4 == 0 && ((uintptr_t)p.feats & 15) == 0 &&
          ((size_t)p.C * hw) % 4 == 0;
 }
 
