@@ -60,6 +60,15 @@ __device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint
                "l"((uint64_t)src), "r"(bytes), "r"(bar)
                : "memory");
 }
+// the same with an L2 eviction priority (the fixed policy encodings that createpolicy.fractional.L2::evict_* produces at fraction 1.0)
+constexpr uint64_t L2_EVICT_NORMAL = 0x1000000000000000ull;
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
+constexpr uint64_t L2_EVICT_LAST = 0x14F0000000000000ull;
+__device__ __forceinline__ void bulk_load_1d_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"((uint64_t)src), "r"(bytes), "r"(bar), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tmap) : "memory");
 }

@@ -43,6 +43,7 @@ struct SpairBatchParams {
   unsigned long long* hits;
   unsigned long long* confusion;
   int conf_dim;
+  int stages, cc, rs;  // streaming form: ring depth, channels per half slot, row stride in floats (set by the launcher)
 };
 
 // dynamic shared memory: q[C][KT], the key-point features of the current tile
@@ -227,31 +228,52 @@ __global__ void __launch_bounds__(SPB_THREADS) spair_batch_kernel(SpairBatchPara
 // ------------------------------------------------------------------------------------------
 // the streaming form (the default where it applies: h*w <= 256, C % 8 == 0, 16-byte aligned maps)
 // ------------------------------------------------------------------------------------------
-// A pair's two maps are ONE contiguous 2 * C * h*w * 4 byte block, read three times in channel order: image i for the
-// pixel norms, image i again (from L2) for the key-point features q, image j for the heat map.  A producer warp streams
-// that sequence through a ring of shared-memory stages with 1-D bulk copies (cp.async.bulk, 8 channels = 6.3 KB per
-// stage for a 14 x 14 map, completion on an mbarrier) and runs up to STAGES chunks -- across the passes and across pairs --
-// ahead of the 8 consumer warps, which only ever read shared memory.  In the first form every consumer thread issued its
-// own 4-byte global loads, 16 in flight, and sat on their DRAM latency (ncu: 45 % of the samples on long-scoreboard
-// stalls at 2.2 TB/s); here the bytes in flight do not depend on registers or occupancy.  The arithmetic (order of every
-// sum) is that of the first form, so the results are bit-identical.
-// consumer threads per CTA.  Measured: 512 (16 consumer warps per CTA, one pixel tile per warp in the tensor-core pass, 54
-// registers, still two CTAs per SM) runs 2.16 M pairs/s against 2.56 M for 256 -- the per-stage waits / releases grow with the warp
-// count while the light passes (norms, key-point vectors) do not get shorter
+// A pair's two maps are ONE contiguous 2 * C * h*w * 4 byte block.  A producer warp streams it through a ring of
+// shared-memory slots with 1-D bulk copies (cp.async.bulk, completion on an mbarrier) and runs up to `stages` slots -- across
+// the passes and across pairs -- ahead of the 8 consumer warps, which only ever read shared memory:
+//   pass N    slots of 2*cc channels of image i: ||f_i[px]||^2 of every pixel (the key points' taps need their norms first)
+//   pass QH   slots of cc channels of image i AND the same cc channels of image j: the consumers blend the key-point vectors
+//             q of these channels from the i half (step Q), then add the channels' share of the heat map from the j half
+//             (step H).  q therefore lives for one slot only (two small buffers) instead of C x KT floats (61 KB at C = 768,
+//             which used to cap the ring at 25-37 KB per CTA): the ring takes the shared memory, 75 KB per CTA in flight.
+// Image i is read twice, 0.6 MB apart per CTA, 178 MB apart over the chip's 296 CTAs -- more than the 126 MB L2, and a cyclic
+// walk through a smaller LRU-like cache hits nothing (ncu before: L2 hit rate 0.4 %, 1.8 MB of DRAM reads per pair against
+// 1.2 MB algorithmic).  SPS_QREV: pass QH walks the channels from the last chunk to the first, so that its first i reads are
+// the most recently cached ones; SPS_HINTS: pass N loads with L2 evict_last, everything that is read for the last time with
+// evict_first (ncu after: 1.33 MB per pair).
+// Rows (one channel = h*w floats) land `rs` floats apart: rs = h*w rounded up to 8 mod 32 when h*w % 4 == 0 (one bulk copy
+// per row), so that the tensor-core pass reads its A fragments with conflict-free 16-byte loads -- lane (g, t) of warp w owns
+// pixels 32 w + 4 g .. + 3 of channels t and t + 4: two LDS.128 per K step where the pixel-per-row mapping took eight LDS.32
+// with two-way bank conflicts; rs = h*w (one copy per half slot, 4-byte loads) otherwise.
+//
+// Measured history (SPair-shaped, 2048 pairs, one B200): round 1 per-thread global loads 1.81 M pairs/s; ring of 4 x 8
+// channels + tensor-core heat map 2.60 M; 2 x 16 channels 2.79 M; score matrix out of static shared memory, 3 x 16 channels
+// 3.17 M, 2 x 24 channels 3.35-3.42 M (63 % of the HBM copy peak); 16 consumer warps per CTA: slower (2.16 M at the 4 x 8 ring).
 #ifndef SPS_CONS_N
 #define SPS_CONS_N 256
 #endif
-constexpr int SPS_CONS = SPS_CONS_N;        // consumer threads: thread = pixel in the norm / heat passes
-constexpr int SPS_WARPS = SPS_CONS / 32;
-constexpr int SPS_MT = (16 + SPS_WARPS - 1) / SPS_WARPS;  // m16 pixel tiles per warp in the tensor-core pass (h*w <= 256: 16 tiles)
+constexpr int SPS_CONS = SPS_CONS_N;        // consumer threads: thread = pixel in pass N
+constexpr int SPS_WARPS = SPS_CONS / 32;    // each owns 32 pixels (two m16 tiles) in the tensor-core pass
 constexpr int SPS_THREADS = SPS_CONS + 32;  // + one producer warp
-constexpr int SPS_CC = 8;                   // channels per stage
-// ring depth.  Measured (same box): 4 stages x 2 CTAs per SM 2.56 M pairs/s; 12 or 20 stages with ONE CTA per SM (the ring then
-// takes the shared memory of the second CTA) 1.75 M -- the kernel is bound by its 16 consumer warps per SM, not by bytes in flight
-#ifndef SPS_STAGES_N
-#define SPS_STAGES_N 4
+static_assert(SPS_CONS == 256, "32 pixels per consumer warp, h*w <= 256");
+constexpr int SPS_MAX_STAGES = 8;
+#ifndef SPS_CC_N
+#define SPS_CC_N 24
 #endif
-constexpr int SPS_STAGES = SPS_STAGES_N;
+constexpr int SPS_CC = SPS_CC_N;  // channels per half slot (a multiple of 8: the tensor-core pass takes 8 per K step)
+static_assert(SPS_CC % 8 == 0 && SPS_CC >= 8, "whole K steps");
+#ifndef SPS_CTAS
+#define SPS_CTAS 2  // CTAs per SM the kernel is built for (registers) and the launcher plans for (shared memory)
+#endif
+#ifndef SPS_NULL
+#define SPS_NULL 0  // diagnostic build: 1 = consumers only wait and release (the memory side alone), 2 = no step H, 3 = no step Q
+#endif
+#ifndef SPS_QREV
+#define SPS_QREV 1
+#endif
+#ifndef SPS_HINTS
+#define SPS_HINTS 1
+#endif
 
 // m16n8k8 tf32 tensor-core step (legacy warp-level MMA: the heat map of a pair is 196 x 20 x 768, far below a tcgen05 tile)
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
@@ -261,61 +283,100 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 }
 // x = hi + lo with hi exactly representable in tf32 (the tensor core drops the low 13 mantissa bits of its operands);
 // hi*hi + hi*lo + lo*hi carries ~21 mantissa bits ("3xTF32")
+// (the AND sits in an asm block: seen by the compiler, it is dropped for the MMA operand -- the tensor core ignores those bits --
+// and kept for the subtraction, and the raw values are then MOVed into the operand's register quad: three instructions per
+// value instead of two)
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = __float_as_uint(x) & 0xffffe000u;
+  asm("and.b32 %0, %1, 0xffffe000;" : "=r"(hi) : "r"(__float_as_uint(x)));
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
-// MMA: the heat-map pass on the tensor cores -- pixels on M (16 per tile, 2 tiles per warp), key points on N (8 per tile),
-// one 8-channel stage = one K step, 3xTF32 -- instead of 21 FFMA + 6 LDS per channel and pixel.
+// where q[c][k] of a chunk sits in its buffer.  Tensor-core pass: per K step (8 channels) and N tile j (8 key points) the
+// B fragment of lane (g, t) -- channels t and t + 4 of key point 8 j + g, each already split into its tf32 halves -- is one
+// float4 {hi(t), hi(t + 4), lo(t), lo(t + 4)} (the register pairs the MMA takes, no moves), lanes in order: a conflict-free
+// LDS.128, and the split is done once per value by step Q instead of once per warp by step H.  Columns beyond KT stay zero
+// from the start of the kernel.
 template <int KT, bool MMA>
-__global__ void __launch_bounds__(SPS_THREADS, SPS_STAGES_N > 5 ? 1 : 2) spair_stream_kernel(SpairBatchParams p) {
-  static_assert(SPS_MT == 1 || SPS_MT == 2, "tile loop");
+__device__ __forceinline__ int sps_q_off(int c, int k) {
+  if (!MMA) return c * KT + k;
+  constexpr int NT8 = (KT + 7) / 8;
+  const int c8 = c & 7;
+  return (((c >> 3) * NT8 + (k >> 3)) * 32 + ((k & 7) << 2) + (c8 & 3)) * 4 + (c8 >> 2);
+}
+template <int KT, bool MMA>
+constexpr int sps_q_floats(int cc) {  // one q buffer
+  return MMA ? (cc / 8) * ((KT + 7) / 8) * 128 : cc * KT;
+}
+
+// MMA: the heat-map step on the tensor cores -- pixels on M (16 per tile, 2 tiles per warp), key points on N (8 per tile),
+// 8 channels per K step, 3xTF32 -- instead of 21 FFMA + 6 LDS per channel and pixel.
+template <int KT, bool MMA>
+__global__ void __launch_bounds__(SPS_THREADS, SPS_CTAS) spair_stream_kernel(SpairBatchParams p) {
   using namespace sm100;
   extern __shared__ __align__(16) float4 sps_dyn[];
-  __shared__ SpairScoreShared score;
   __shared__ int s_pred[64];
   __shared__ float s_wt[64][4];
   __shared__ int s_tap[64][4];
-  __shared__ float s_bv[SPS_CONS / 32][KT];
-  __shared__ int s_bi[SPS_CONS / 32][KT];
-  __shared__ __align__(8) unsigned long long full[SPS_STAGES], empty[SPS_STAGES];
-  const int C = p.C, hw = p.h * p.w, K = p.K;
-  const int chunk_floats = SPS_CC * hw;
-  const uint32_t chunk_bytes = (uint32_t)chunk_floats * 4u;
-  float* ring = reinterpret_cast<float*>(sps_dyn);                  // [STAGES][CC * hw]
-  float* q = ring + (size_t)SPS_STAGES * chunk_floats;              // [C][KT]
-  float* pix_ss = q + (size_t)C * KT;                               // [hw]
+  __shared__ float s_bv[SPS_WARPS][KT];
+  __shared__ int s_bi[SPS_WARPS][KT];
+  __shared__ __align__(8) unsigned long long full[SPS_MAX_STAGES], empty[SPS_MAX_STAGES];
+  constexpr bool REV = SPS_QREV && MMA;  // the CUDA-core form keeps the channel order (and the bits) of the first form
+  const int C = p.C, hw = p.h * p.w, K = p.K, rs = hw;
+  constexpr int cc = SPS_CC;
+  const int nstage = p.stages;
+  const int slot_floats = 2 * cc * rs;
+  float* ring = reinterpret_cast<float*>(sps_dyn);                  // [stages][2 * cc rows][rs]
+  float* qbuf = ring + (size_t)nstage * slot_floats;                // [2][cc][KT]
+  float* pix_ss = qbuf + 2 * sps_q_floats<KT, MMA>(cc);             // [hw]
+  float* score_mem = pix_ss + ((hw + 3) & ~3);                      // [K][K + 1] errors, 2 counters
+  const SpairScoreView score{score_mem, K + 1, reinterpret_cast<unsigned int*>(score_mem + K * (K + 1))};
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int nchunk = C / SPS_CC;
-  const int nkt = (K + KT - 1) / KT;  // key-point tiles: passes Q and H repeat per tile
+  const int nchunk = (C + cc - 1) / cc;
+  const int nkt = (K + KT - 1) / KT;  // key-point tiles: pass QH repeats per tile
+  const bool vec2 = (hw & 1) == 0;  // rows 8-byte aligned: step H reads its A fragments with LDS.64
 
   if (tid == 0) {
-    for (int s = 0; s < SPS_STAGES; ++s) {
+    for (int s = 0; s < nstage; ++s) {
       mbar_init(smem_u32(&full[s]), 1);
-      mbar_init(smem_u32(&empty[s]), SPS_CONS / 32);
+      mbar_init(smem_u32(&empty[s]), SPS_WARPS);
     }
     mbar_fence_init();
   }
   __syncthreads();
 
-  if (wid == SPS_CONS / 32) {
-    // ===================================== producer =====================================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-        const float* fi = p.feats + (size_t)b * 2 * C * hw;
-        const float* fj = fi + (size_t)C * hw;
-        for (int pass = 0; pass < 1 + 2 * nkt; ++pass) {
-          const float* base = (pass == 0 || (pass & 1)) ? fi : fj;  // N, then (Q, H) per key-point tile
-          for (int ck = 0; ck < nchunk; ++ck) {
-            mbar_wait(smem_u32(&empty[stage]), phase ^ 1u);
-            mbar_arrive_expect_tx(smem_u32(&full[stage]), chunk_bytes);
-            bulk_load_1d(smem_u32(ring + (size_t)stage * chunk_floats), base + (size_t)ck * chunk_floats, chunk_bytes,
-                         smem_u32(&full[stage]));
-            if (++stage == SPS_STAGES) { stage = 0; phase ^= 1u; }
-          }
+  if (wid == SPS_WARPS) {
+    // ===================================== producer warp =====================================
+    int stage = 0;
+    uint32_t phase = 0;
+    // L2 eviction priorities (SPS_HINTS): 1 = what is read again keeps (evict_last), what is read for the last time streams
+    // (evict_first); 2 = only the streaming half, the rest at the normal priority
+    const uint64_t pol_keep = SPS_HINTS == 1 ? L2_EVICT_LAST : L2_EVICT_NORMAL;
+    const uint64_t pol_stream = SPS_HINTS ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+    // rows [c0, c0 + rows) of one map into a slot at float offset `at`
+    auto rows_in = [&](const float* map, int c0, int rows, int at, uint64_t pol) {
+      bulk_load_1d_hint(smem_u32(ring + (size_t)stage * slot_floats + at), map + (size_t)c0 * hw, (uint32_t)(rows * hw) * 4u,
+                        smem_u32(&full[stage]), pol);
+    };
+    if (lane != 0) return;
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+      const float* fi = p.feats + (size_t)b * 2 * C * hw;
+      const float* fj = fi + (size_t)C * hw;
+      for (int c0 = 0; c0 < C; c0 += 2 * cc) {  // pass N
+        const int rows = min(2 * cc, C - c0);
+        mbar_wait(smem_u32(&empty[stage]), phase ^ 1u);
+        mbar_arrive_expect_tx(smem_u32(&full[stage]), (uint32_t)(rows * hw) * 4u);
+        rows_in(fi, c0, rows, 0, pol_keep);
+        if (++stage == nstage) { stage = 0; phase ^= 1u; }
+      }
+      for (int kt = 0; kt < nkt; ++kt) {  // pass QH per key-point tile
+        const uint64_t pol_i = kt + 1 < nkt ? pol_keep : pol_stream, pol_j = pol_i;
+        for (int cq = 0; cq < nchunk; ++cq) {
+          const int c0 = (REV ? nchunk - 1 - cq : cq) * cc, rows = min(cc, C - c0);
+          mbar_wait(smem_u32(&empty[stage]), phase ^ 1u);
+          mbar_arrive_expect_tx(smem_u32(&full[stage]), (uint32_t)(2 * rows * hw) * 4u);
+          rows_in(fi, c0, rows, 0, pol_i);
+          rows_in(fj, c0, rows, cc * rs, pol_j);
+          if (++stage == nstage) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -326,14 +387,15 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_STAGES_N > 5 ? 1 : 2) spair_s
   int stage = 0;
   uint32_t phase = 0;
   auto cons_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(SPS_CONS) : "memory"); };
-  auto release = [&] {  // this warp is done with the current stage
+  auto release = [&] {  // this warp is done with the current slot
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&empty[stage]));
-    if (++stage == SPS_STAGES) { stage = 0; phase ^= 1u; }
+    if (++stage == nstage) { stage = 0; phase ^= 1u; }
   };
-  const int nwarp = SPS_CONS / 32;
   const int px = tid;
   const bool has_px = px < hw;
+  for (int i = tid; i < 2 * sps_q_floats<KT, MMA>(cc); i += SPS_CONS) qbuf[i] = 0.f;
+  cons_sync();
 
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
     const float* ki = p.kps_i + (size_t)b * K * p.stride;
@@ -360,14 +422,17 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_STAGES_N > 5 ? 1 : 2) spair_s
     // ---- pass N: ||f_i[px]||^2 of every pixel, channels in ascending order ----
     {
       float ss = 0.f;
-      for (int ck = 0; ck < nchunk; ++ck) {
+      for (int c0 = 0; c0 < C; c0 += 2 * cc) {
+        const int rows = min(2 * cc, C - c0);
         mbar_wait(smem_u32(&full[stage]), phase);
-        const float* st = ring + (size_t)stage * chunk_floats + px;
-        if (has_px) {
+        const float* st = ring + (size_t)stage * slot_floats + px;
+        if (has_px && SPS_NULL != 1) {
+          for (int c = 0; c < rows; c += 8) {
 #pragma unroll
-          for (int c = 0; c < SPS_CC; ++c) {
-            const float v = st[c * hw];
-            ss = fmaf(v, v, ss);
+            for (int u = 0; u < 8; ++u) {
+              const float v = st[(c + u) * rs];
+              ss = fmaf(v, v, ss);
+            }
           }
         }
         release();
@@ -383,76 +448,142 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_STAGES_N > 5 ? 1 : 2) spair_s
 
     for (int k0 = 0; k0 < K; k0 += KT) {
       const int kt = min(KT, K - k0);
-      // ---- pass Q: q[c][k] = sum_t wt * f_i[c][tap] / max(||f_i[tap]||, eps): the grid_sample of the normalised map ----
-      for (int ck = 0; ck < nchunk; ++ck) {
-        mbar_wait(smem_u32(&full[stage]), phase);
-        const float* st = ring + (size_t)stage * chunk_floats;
-        for (int idx = tid; idx < SPS_CC * KT; idx += SPS_CONS) {
-          const int c = idx / KT, k = idx - c * KT;
-          const int kk = k0 + min(k, kt - 1);
-          const float* src = st + c * hw;
-          float acc = src[s_tap[kk][0]] * s_wt[kk][0];
-          acc = fmaf(src[s_tap[kk][1]], s_wt[kk][1], acc);
-          acc = fmaf(src[s_tap[kk][2]], s_wt[kk][2], acc);
-          acc = fmaf(src[s_tap[kk][3]], s_wt[kk][3], acc);
-          q[(size_t)(ck * SPS_CC + c) * KT + k] = (k < kt) ? acc : 0.f;
-        }
-        release();
-      }
-      cons_sync();
-      // ---- pass H: heat[k][px] = (sum_c q[c][k] * f_j[c][px]) / max(||f_j[px]||, eps), norm accumulated alongside ----
+      // accumulators of step H.  Tensor-core form: d[i][j][2 r + e] = heat of pixel 32 wid + 16 i + 2 g + r (tile i, fragment
+      // row g + 8 r) and key point 8 j + 2 t + e; ssr[i][r] = this lane's share (channels t, t + 4) of that pixel's norm
+      constexpr int NT8 = (KT + 7) / 8;
+      const int g = lane >> 2, t = lane & 3;
+      float d[2][MMA ? NT8 : 1][4];
+      float ssr[2][2];
+      float acc[MMA ? 1 : KT];
+      float ssp = 0.f;
       if constexpr (MMA) {
-        static_assert(SPS_CC == 8, "one stage = one m16n8k8 K step");
-        constexpr int NT8 = (KT + 7) / 8;
-        const int g = lane >> 2, t = lane & 3;
-        float d[SPS_MT][NT8][4];
-        float ssr[SPS_MT][2];
 #pragma unroll
-        for (int i = 0; i < SPS_MT; ++i) {
+        for (int i = 0; i < 2; ++i) {
           ssr[i][0] = ssr[i][1] = 0.f;
 #pragma unroll
           for (int j = 0; j < NT8; ++j) d[i][j][0] = d[i][j][1] = d[i][j][2] = d[i][j][3] = 0.f;
         }
-        const int ntile = (hw + 15) >> 4;  // this warp owns tiles wid (and wid + SPS_WARPS)
-        for (int ck = 0; ck < nchunk; ++ck) {
-          mbar_wait(smem_u32(&full[stage]), phase);
-          const float* st = ring + (size_t)stage * chunk_floats;
-          uint32_t bh[NT8][2], bl[NT8][2];
+      } else {
 #pragma unroll
-          for (int j = 0; j < NT8; ++j) {
-            const int kcol = 8 * j + g;
-            const float b0 = kcol < KT ? q[(size_t)(ck * SPS_CC + t) * KT + kcol] : 0.f;
-            const float b1 = kcol < KT ? q[(size_t)(ck * SPS_CC + t + 4) * KT + kcol] : 0.f;
-            split_tf32(b0, bh[j][0], bl[j][0]);
-            split_tf32(b1, bh[j][1], bl[j][1]);
+        for (int k = 0; k < KT; ++k) acc[k] = 0.f;
+      }
+      const bool warp_live = 32 * wid < hw;  // warp-uniform: this warp's 32 pixels hold at least one of the map
+
+      for (int cq = 0; cq < nchunk; ++cq) {
+        const int c0 = (REV ? nchunk - 1 - cq : cq) * cc, rows = min(cc, C - c0);
+        float* qb = qbuf + (cq & 1) * sps_q_floats<KT, MMA>(cc);
+        mbar_wait(smem_u32(&full[stage]), phase);
+        const float* sti = ring + (size_t)stage * slot_floats;
+        const float* stj = sti + cc * rs;
+        // ---- step Q: q[c][k] = sum_t wt * f_i[c][tap] / max(||f_i[tap]||, eps): the grid_sample of the normalised map ----
+        for (int idx = tid; idx < rows * KT && SPS_NULL != 1 && SPS_NULL != 3; idx += SPS_CONS) {
+          const int c = idx / KT, k = idx - c * KT;
+          const int kk = k0 + min(k, kt - 1);
+          const float* src = sti + c * rs;
+          float a = src[s_tap[kk][0]] * s_wt[kk][0];
+          a = fmaf(src[s_tap[kk][1]], s_wt[kk][1], a);
+          a = fmaf(src[s_tap[kk][2]], s_wt[kk][2], a);
+          a = fmaf(src[s_tap[kk][3]], s_wt[kk][3], a);
+          a = (k < kt) ? a : 0.f;
+          if constexpr (MMA) {
+            uint32_t hi, lo;
+            split_tf32(a, hi, lo);
+            float* qd = qb + sps_q_off<KT, MMA>(c, k);
+            qd[0] = __uint_as_float(hi);
+            qd[2] = __uint_as_float(lo);
+          } else {
+            qb[sps_q_off<KT, MMA>(c, k)] = a;
           }
-#pragma unroll
-          for (int i = 0; i < SPS_MT; ++i) {
-            const int mt = wid + SPS_WARPS * i;
-            if (mt < ntile) {  // warp-uniform
-              const int p0 = mt * 16 + g;
-              const float a0 = st[t * hw + p0], a1 = st[t * hw + p0 + 8];            // rows beyond h*w read the following
-              const float a2 = st[(t + 4) * hw + p0], a3 = st[(t + 4) * hw + p0 + 8];  // floats of the ring: masked below
-              ssr[i][0] = fmaf(a0, a0, ssr[i][0]);
-              ssr[i][0] = fmaf(a2, a2, ssr[i][0]);
-              ssr[i][1] = fmaf(a1, a1, ssr[i][1]);
-              ssr[i][1] = fmaf(a3, a3, ssr[i][1]);
-              uint32_t ah[4], al[4];
-              split_tf32(a0, ah[0], al[0]);
-              split_tf32(a1, ah[1], al[1]);
-              split_tf32(a2, ah[2], al[2]);
-              split_tf32(a3, ah[3], al[3]);
+        }
+        cons_sync();  // q of this chunk complete; the other buffer is free again once every warp has passed this point
+        // ---- step H: heat[k][px] += sum_c q[c][k] * f_j[c][px], the pixel's norm accumulated alongside ----
+        if constexpr (MMA) {
+          if (warp_live && SPS_NULL != 1 && SPS_NULL != 2) {
+            const float* aj = stj + 32 * wid + 2 * g;
+            const float4* bq = reinterpret_cast<const float4*>(qb) + lane;
+            auto kstep = [&](int ks) {  // channels ks .. ks + 7 of the chunk
+              uint32_t bh[NT8][2], bl[NT8][2];
 #pragma unroll
               for (int j = 0; j < NT8; ++j) {
-                mma_tf32(d[i][j], al, bh[j][0], bh[j][1]);
-                mma_tf32(d[i][j], ah, bl[j][0], bl[j][1]);
-                mma_tf32(d[i][j], ah, bh[j][0], bh[j][1]);
+                const float4 b4 = bq[((ks >> 3) * NT8 + j) * 32];
+                bh[j][0] = __float_as_uint(b4.x);
+                bh[j][1] = __float_as_uint(b4.y);
+                bl[j][0] = __float_as_uint(b4.z);
+                bl[j][1] = __float_as_uint(b4.w);
+              }
+              // A fragments: pixels 16 i + 2 g, + 1 (fragment rows g, g + 8 of tile i) of channels t and t + 4, each pair one
+              // LDS.64 straight into its half of the operand's register quad (the tensor core ignores the low mantissa bits, so
+              // the loaded values ARE the hi operand).  Pixels beyond h*w read whatever follows in the slot (finite or not:
+              // their rows are never looked at).
+              const float* r0 = aj + (ks + t) * rs;
+              const float* r1 = r0 + 4 * rs;
+              float av[2][4];
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                if (vec2) {
+                  const float2 x0 = *reinterpret_cast<const float2*>(r0 + 16 * i), x1 = *reinterpret_cast<const float2*>(r1 + 16 * i);
+                  av[i][0] = x0.x, av[i][1] = x0.y, av[i][2] = x1.x, av[i][3] = x1.y;
+                } else {
+                  av[i][0] = r0[16 * i], av[i][1] = r0[16 * i + 1], av[i][2] = r1[16 * i], av[i][3] = r1[16 * i + 1];
+                }
+              }
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                ssr[i][0] = fmaf(av[i][0], av[i][0], ssr[i][0]);
+                ssr[i][0] = fmaf(av[i][2], av[i][2], ssr[i][0]);
+                ssr[i][1] = fmaf(av[i][1], av[i][1], ssr[i][1]);
+                ssr[i][1] = fmaf(av[i][3], av[i][3], ssr[i][1]);
+                uint32_t ah[4], al[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split_tf32(av[i][e], ah[e], al[e]);
+#pragma unroll
+                for (int j = 0; j < NT8; ++j) {
+                  if (SPS_NULL != 4 && SPS_NULL != 5) mma_tf32(d[i][j], al, bh[j][0], bh[j][1]);
+                  if (SPS_NULL != 4 && SPS_NULL != 5) mma_tf32(d[i][j], ah, bl[j][0], bl[j][1]);
+                  if (SPS_NULL != 5) mma_tf32(d[i][j], ah, bh[j][0], bh[j][1]);
+                }
+              }
+            };
+            if (rows == cc) {
+#pragma unroll
+              for (int ks = 0; ks < cc; ks += 8) kstep(ks);
+            } else {
+              for (int ks = 0; ks < rows; ks += 8) kstep(ks);
+            }
+          }
+        } else {
+          if (has_px) {
+            const float* sj = stj + px;
+            for (int c = 0; c < rows; ++c) {
+              const float v = sj[c * rs];
+              ssp = fmaf(v, v, ssp);
+              const float4* qc = reinterpret_cast<const float4*>(qb + c * KT);
+#pragma unroll
+              for (int k4 = 0; k4 < KT / 4; ++k4) {
+                const float4 qq = qc[k4];  // same address in every lane: broadcast
+                acc[4 * k4 + 0] = fmaf(qq.x, v, acc[4 * k4 + 0]);
+                acc[4 * k4 + 1] = fmaf(qq.y, v, acc[4 * k4 + 1]);
+                acc[4 * k4 + 2] = fmaf(qq.z, v, acc[4 * k4 + 2]);
+                acc[4 * k4 + 3] = fmaf(qq.w, v, acc[4 * k4 + 3]);
               }
             }
           }
-          release();
         }
-        // per key point this lane owns (columns 2t, 2t + 1 of every N tile): best of its rows, then across the 8 row groups
+        release();
+      }
+
+      // ---- heat / max(||f_j[px]||, eps), arg-max per key point (first pixel among equals) ----
+      if constexpr (MMA) {
+        // per key point this lane owns (columns 2t, 2t + 1 of every N tile): best of its 4 pixels, then across the 8 row groups
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            float ss = ssr[i][r];
+            ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+            ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+            ssr[i][r] = fmaxf(sqrtf(ss), SPB_NORM_EPS);
+          }
 #pragma unroll
         for (int j = 0; j < NT8; ++j) {
 #pragma unroll
@@ -460,15 +591,12 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_STAGES_N > 5 ? 1 : 2) spair_s
             float v = -CUDART_INF_F;
             int bi = 0x7fffffff;
 #pragma unroll
-            for (int i = 0; i < SPS_MT; ++i) {
+            for (int i = 0; i < 2; ++i) {
 #pragma unroll
               for (int r = 0; r < 2; ++r) {
-                const int pxl = (wid + SPS_WARPS * i) * 16 + g + 8 * r;
-                float ss = ssr[i][r];
-                ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-                ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-                const float hv = __fdiv_rn(d[i][j][2 * r + e2], fmaxf(sqrtf(ss), SPB_NORM_EPS));
-                if (wid + SPS_WARPS * i < ntile && pxl < hw && (hv > v || (hv == v && pxl < bi))) {
+                const int pxl = 32 * wid + 16 * i + 2 * g + r;  // ascending in (i, r): `>` keeps the first among equals
+                const float hv = __fdiv_rn(d[i][j][2 * r + e2], ssr[i][r]);
+                if (warp_live && pxl < hw && hv > v) {
                   v = hv;
                   bi = pxl;
                 }
@@ -491,60 +619,35 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_STAGES_N > 5 ? 1 : 2) spair_s
           }
         }
       } else {
-      float acc[KT];
+        const float nrm = fmaxf(sqrtf(ssp), SPB_NORM_EPS);
 #pragma unroll
-      for (int k = 0; k < KT; ++k) acc[k] = 0.f;
-      float ss = 0.f;
-      for (int ck = 0; ck < nchunk; ++ck) {
-        mbar_wait(smem_u32(&full[stage]), phase);
-        const float* st = ring + (size_t)stage * chunk_floats + px;
-        if (has_px) {
+        for (int k = 0; k < KT; ++k) {
+          float v = has_px ? __fdiv_rn(acc[k], nrm) : -CUDART_INF_F;
+          int i = has_px ? px : 0x7fffffff;
+          if (!(v > -CUDART_INF_F)) {  // NaN / -inf never win (the first form's `hv > bestv` test against -inf)
+            v = -CUDART_INF_F;
+            i = 0x7fffffff;
+          }
 #pragma unroll
-          for (int c = 0; c < SPS_CC; ++c) {
-            const float v = st[c * hw];
-            ss = fmaf(v, v, ss);
-            const float4* qc = reinterpret_cast<const float4*>(q + (size_t)(ck * SPS_CC + c) * KT);
-#pragma unroll
-            for (int k4 = 0; k4 < KT / 4; ++k4) {
-              const float4 qq = qc[k4];  // same address in every lane: broadcast
-              acc[4 * k4 + 0] = fmaf(qq.x, v, acc[4 * k4 + 0]);
-              acc[4 * k4 + 1] = fmaf(qq.y, v, acc[4 * k4 + 1]);
-              acc[4 * k4 + 2] = fmaf(qq.z, v, acc[4 * k4 + 2]);
-              acc[4 * k4 + 3] = fmaf(qq.w, v, acc[4 * k4 + 3]);
+          for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+            if (ov > v || (ov == v && oi < i)) {
+              v = ov;
+              i = oi;
             }
           }
-        }
-        release();
-      }
-      const float nrm = fmaxf(sqrtf(ss), SPB_NORM_EPS);
-#pragma unroll
-      for (int k = 0; k < KT; ++k) {
-        float v = has_px ? __fdiv_rn(acc[k], nrm) : -CUDART_INF_F;
-        int i = has_px ? px : 0x7fffffff;
-        if (!(v > -CUDART_INF_F)) {  // NaN / -inf never win (the first form's `hv > bestv` test against -inf)
-          v = -CUDART_INF_F;
-          i = 0x7fffffff;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float ov = __shfl_xor_sync(0xffffffffu, v, o);
-          const int oi = __shfl_xor_sync(0xffffffffu, i, o);
-          if (ov > v || (ov == v && oi < i)) {
-            v = ov;
-            i = oi;
+          if (lane == 0) {
+            s_bv[wid][k] = v;
+            s_bi[wid][k] = i;
           }
         }
-        if (lane == 0) {
-          s_bv[wid][k] = v;
-          s_bi[wid][k] = i;
-        }
-      }
       }
       cons_sync();
       if (tid < kt) {
         float v = s_bv[0][tid];
         int i = s_bi[0][tid];
-        for (int wq = 1; wq < nwarp; ++wq) {
+        for (int wq = 1; wq < SPS_WARPS; ++wq) {
           const float ov = s_bv[wq][tid];
           const int oi = s_bi[wq][tid];
           if (ov > v || (ov == v && oi < i)) {
@@ -556,7 +659,7 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_STAGES_N > 5 ? 1 : 2) spair_s
         s_pred[k0 + tid] = i;
         if (p.pred) p.pred[(size_t)b * K + k0 + tid] = i;
       }
-      cons_sync();  // q, s_bv are rewritten by the next tile
+      cons_sync();  // s_bv is rewritten by the next tile
     }
 
     spair_score_block<SPS_CONS>(score, s_pred, K, p.w, ki, kj, p.stride, p.image_size, __ldg(p.thresh_scale + b), p.pck, nullptr,
@@ -566,45 +669,69 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_STAGES_N > 5 ? 1 : 2) spair_s
   }
 }
 
-// the streaming form needs one pixel per consumer thread and 16-byte-granular stages
-bool spair_stream_ok(const SpairBatchParams& p) {
-  static const int off = getenv("MVMATCH_SPAIR_STREAM") && getenv("MVMATCH_SPAIR_STREAM")[0] == '0';
+// shared-memory plan of the streaming form
+struct SpsPlan {
+  int cc, rs, stages;
+  size_t smem;
+  bool ok;
+};
+SpsPlan sps_plan(const SpairBatchParams& p, int KT) {
+  SpsPlan pl{};
   const int hw = p.h * p.w;
-  return !off && hw <= 256 && p.C % SPS_CC == 0 && (hw * SPS_CC) % 4 == 0 && ((uintptr_t)p.feats & 15) == 0 &&
-         ((size_t)p.C * hw) % 4 == 0;
+  static const int off = getenv("MVMATCH_SPAIR_STREAM") && getenv("MVMATCH_SPAIR_STREAM")[0] == '0';
+  if (off || hw > 256 || p.C % 8 != 0 || ((uintptr_t)p.feats & 15) != 0) return pl;
+  static const int env_stages = getenv("MVMATCH_SPAIR_STAGES") ? atoi(getenv("MVMATCH_SPAIR_STAGES")) : 0;
+  static const bool mma = !(getenv("MVMATCH_SPAIR_MMA") && getenv("MVMATCH_SPAIR_MMA")[0] == '0');
+  const int cc = SPS_CC, rs = hw;
+  const size_t qf = mma ? (size_t)(cc / 8) * ((KT + 7) / 8) * 128 : (size_t)cc * KT;
+  const size_t fixed = (2 * qf + (size_t)((hw + 3) & ~3) + (size_t)((p.K * (p.K + 1) + 2 + 3) & ~3)) * sizeof(float);
+  const size_t slot = (size_t)2 * cc * rs * sizeof(float);
+  // SPS_CTAS CTAs per SM: 227 KB less 1 KB reserved and ~4 KB of static shared memory per CTA
+  const size_t budget = ((227u << 10) / SPS_CTAS) - (5u << 10);
+  int stages = env_stages > 0 ? env_stages : (fixed + 2 * slot <= budget ? (int)((budget - fixed) / slot) : 2);
+  if (stages < 2) stages = 2;
+  if (stages > SPS_MAX_STAGES) stages = SPS_MAX_STAGES;
+  pl.cc = cc;
+  pl.rs = rs;
+  pl.stages = stages;
+  pl.smem = fixed + stages * slot;
+  pl.ok = pl.smem <= (200u << 10);
+  return pl;
 }
 
 template <int KT>
-int launch_spair_stream(const SpairBatchParams& p, cudaStream_t st) {
-  const int hw = p.h * p.w;
-  const size_t smem = ((size_t)SPS_STAGES * SPS_CC * hw + (size_t)p.C * KT + (size_t)((hw + 3) / 4 * 4)) * sizeof(float);
-  // MVMATCH_SPAIR_MMA=0: the heat-map pass on the CUDA cores (bit-identical to the first form)
+int launch_spair_stream(const SpairBatchParams& p, const SpsPlan& pl, cudaStream_t st) {
+  // MVMATCH_SPAIR_MMA=0: the heat-map step on the CUDA cores (the arithmetic of the first form)
   static const bool mma = !(getenv("MVMATCH_SPAIR_MMA") && getenv("MVMATCH_SPAIR_MMA")[0] == '0');
   auto kern = mma ? spair_stream_kernel<KT, true> : spair_stream_kernel<KT, false>;
   static size_t opted[MV_MAX_DEVICES][2];
   size_t& opted_in = opted[mv_device_slot()][mma ? 1 : 0];
-  if (smem > opted_in) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (pl.smem > opted_in) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) {
-      mv_set_error("mv_spair_match_batch: cannot opt in to %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+      mv_set_error("mv_spair_match_batch: cannot opt in to %zu bytes of shared memory: %s", pl.smem, cudaGetErrorString(e));
       return (int)e;
     }
-    opted_in = smem;
+    opted_in = pl.smem;
   }
-  int per_sm = (int)((227u << 10) / (smem + (21u << 10)));  // static shared memory of the kernel is ~20 KB
+  int per_sm = (int)((227u << 10) / (pl.smem + (5u << 10)));  // static shared memory of the kernel is ~4 KB
   if (per_sm < 1) per_sm = 1;
-  if (per_sm > 2) per_sm = 2;
+  if (per_sm > SPS_CTAS) per_sm = SPS_CTAS;
   int grid = mv_sm_count() * per_sm;
   if (grid > p.B) grid = p.B;
-  kern<<<grid, SPS_THREADS, smem, st>>>(p);
+  SpairBatchParams ps = p;
+  ps.stages = pl.stages;
+  ps.cc = pl.cc;
+  ps.rs = pl.rs;
+  kern<<<grid, SPS_THREADS, pl.smem, st>>>(ps);
   MV_LAUNCH_CHECK();
   return MV_OK;
 }
 
 template <int KT>
 int launch_spair_batch(const SpairBatchParams& p, cudaStream_t st) {
-  if (spair_stream_ok(p) && ((size_t)SPS_STAGES * SPS_CC * p.h * p.w + (size_t)p.C * KT + p.h * p.w + 4) * sizeof(float) <= (200u << 10))
-    return launch_spair_stream<KT>(p, st);
+  const SpsPlan pl = sps_plan(p, KT);
+  if (pl.ok) return launch_spair_stream<KT>(p, pl, st);
   const size_t smem = (size_t)p.C * KT * sizeof(float);
   auto kern = spair_batch_kernel<KT>;
   static size_t opted[MV_MAX_DEVICES];  // per device; static + dynamic shared memory above 48 KB needs the opt-in
@@ -667,6 +794,7 @@ int mv_spair_match_batch(const float* feats, int B, int C, int h, int w, const f
   p.hits = hits;
   p.confusion = confusion;
   p.conf_dim = conf_dim;
+  p.stages = p.cc = p.rs = 0;
   cudaStream_t st = mv_cuda_stream(stream);
   // key-point tile = accumulators per thread; the tile's features (C * KT floats) must fit shared memory
   const size_t budget = 160u << 10;

@@ -20,8 +20,15 @@ __device__ __forceinline__ void spair_score_sync() {
   if (NT == 0) __syncthreads();
   else asm volatile("bar.sync 1, %0;" ::"r"(NT) : "memory");
 }
+// the error matrix as a view: err[k * pitch + l] (pitch > K, odd pitches are conflict-free), cnt[2]
+struct SpairScoreView {
+  float* err;
+  int pitch;
+  unsigned int* cnt;
+  __device__ __forceinline__ float& at(int k, int l) const { return err[k * pitch + l]; }
+};
 template <int NT = 0>
-__device__ __forceinline__ void spair_score_block(SpairScoreShared& sh, const int32_t* pred_flat, int K, int w,
+__device__ __forceinline__ void spair_score_block(SpairScoreView sh, const int32_t* pred_flat, int K, int w,
                                                   const float* __restrict__ kps_i, const float* __restrict__ kps_j,
                                                   int stride, float image_size, float thresh_scale, float pck,
                                                   float* __restrict__ errors, float* __restrict__ error_same,
@@ -40,7 +47,7 @@ __device__ __forceinline__ void spair_score_block(SpairScoreShared& sh, const in
     float e = __fdiv_rn(sqrtf(fmaf(dy, dy, dx * dx)), thresh_scale);
     const bool valid = (kps_i[(size_t)k * stride + 2] * kps_j[(size_t)l * stride + 2]) == 1.f;
     if (!valid) e = 1e3f;
-    sh.err[k][l] = e;
+    sh.at(k, l) = e;
     if (errors) errors[t] = e;
   }
   spair_score_sync<NT>();
@@ -49,11 +56,11 @@ __device__ __forceinline__ void spair_score_block(SpairScoreShared& sh, const in
     float es = -1.f, en = -1.f;
     int in = -1;
     if (in_both) {
-      es = sh.err[k][k];
-      en = sh.err[k][0];
+      es = sh.at(k, k);
+      en = sh.at(k, 0);
       in = 0;
       for (int l = 1; l < K; ++l)
-        if (sh.err[k][l] < en) { en = sh.err[k][l]; in = l; }
+        if (sh.at(k, l) < en) { en = sh.at(k, l); in = l; }
       atomicAdd(&sh.cnt[0], 1u);
       if (es < pck) atomicAdd(&sh.cnt[1], 1u);
       if (confusion) atomicAdd(&confusion[(size_t)k * conf_dim + in], 1ull);
@@ -65,4 +72,16 @@ __device__ __forceinline__ void spair_score_block(SpairScoreShared& sh, const in
   spair_score_sync<NT>();
   if (hits && threadIdx.x < 2 && sh.cnt[threadIdx.x]) atomicAdd(&hits[threadIdx.x], (unsigned long long)sh.cnt[threadIdx.x]);
   spair_score_sync<NT>();
+}
+
+template <int NT = 0>
+__device__ __forceinline__ void spair_score_block(SpairScoreShared& sh, const int32_t* pred_flat, int K, int w,
+                                                  const float* __restrict__ kps_i, const float* __restrict__ kps_j,
+                                                  int stride, float image_size, float thresh_scale, float pck,
+                                                  float* __restrict__ errors, float* __restrict__ error_same,
+                                                  float* __restrict__ error_nn, int32_t* __restrict__ index_nn,
+                                                  unsigned long long* __restrict__ hits,
+                                                  unsigned long long* __restrict__ confusion, int conf_dim) {
+  spair_score_block<NT>(SpairScoreView{&sh.err[0][0], 65, sh.cnt}, pred_flat, K, w, kps_i, kps_j, stride, image_size,
+                        thresh_scale, pck, errors, error_same, error_nn, index_nn, hits, confusion, conf_dim);
 }
