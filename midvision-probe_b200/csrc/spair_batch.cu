@@ -468,6 +468,7 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_CTAS) spair_stream_kernel(Spa
         for (int k = 0; k < KT; ++k) acc[k] = 0.f;
       }
       const bool warp_live = 32 * wid < hw;  // warp-uniform: this warp's 32 pixels hold at least one of the map
+      const bool tile1_live = 32 * wid + 16 < hw;
 
       for (int cq = 0; cq < nchunk; ++cq) {
         const int c0 = (REV ? nchunk - 1 - cq : cq) * cc, rows = min(cc, C - c0);
@@ -520,6 +521,7 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_CTAS) spair_stream_kernel(Spa
               float av[2][4];
 #pragma unroll
               for (int i = 0; i < 2; ++i) {
+                if (i == 1 && !tile1_live) break;  // warp-uniform: the warp's second 16 pixels lie beyond the map
                 if (vec2) {
                   const float2 x0 = *reinterpret_cast<const float2*>(r0 + 16 * i), x1 = *reinterpret_cast<const float2*>(r1 + 16 * i);
                   av[i][0] = x0.x, av[i][1] = x0.y, av[i][2] = x1.x, av[i][3] = x1.y;
@@ -529,6 +531,7 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_CTAS) spair_stream_kernel(Spa
               }
 #pragma unroll
               for (int i = 0; i < 2; ++i) {
+                if (i == 1 && !tile1_live) break;
                 ssr[i][0] = fmaf(av[i][0], av[i][0], ssr[i][0]);
                 ssr[i][0] = fmaf(av[i][2], av[i][2], ssr[i][0]);
                 ssr[i][1] = fmaf(av[i][1], av[i][1], ssr[i][1]);
