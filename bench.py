@@ -597,6 +597,7 @@ def k1_record(ctx):
 # --------------------------------------------------------------------------------------------------------------
 # SPair (configs[0])
 # --------------------------------------------------------------------------------------------------------------
+SPAIR_DRAM_BYTES_PER_PAIR = 1.44e6  # ncu --set full of one SPAIR_BATCH launch (dram__bytes_read.sum + dram__bytes_write.sum) / pairs
 SPAIR_BATCH = 1184  # pairs per step (one launch) = 4 waves of 2 CTAs x 148 SMs; 1.2 MB of features per pair -> 1.4 GB per step
 
 
@@ -660,8 +661,11 @@ def run_spair(ctx, steps, warmup):
                 "api": "spair.compute_errors_batch(host tensors)"},
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": byts / (per_launch_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": byts / (per_launch_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "peak_kind": f"{peak_kind} copy bandwidth",
-                     "kernel": "spair_batch_kernel (one launch per step; algorithmic bytes = the (B, 2, C, h, w) features, read once)",
+                     "frac": byts / (per_launch_ms * 1e-3) / 1e9 / hbm_peak, "traffic": SPAIR_DRAM_BYTES_PER_PAIR * B if B == SPAIR_BATCH else None,
+                     "peak_kind": f"{peak_kind} copy bandwidth",
+                     "kernel": "spair_stream_kernel (one launch per step; algorithmic bytes = the (B, 2, C, h, w) features, read once; "
+                               "traffic = dram__bytes_read + write of one launch under ncu, profiles/r2_spair_stream_final.txt: image i is "
+                               "read twice and its second read hits L2 only in part)",
                      "avg_ms": per_launch_ms, "bytes_per_launch": byts},
         "recall": {"keypoints_in_both": h[0], "pck_0.10": 100.0 * h[1] / max(h[0], 1)},
     }

@@ -217,7 +217,10 @@ def test_angle_binned_recall(mv, syn):
 
 
 @pytest.mark.parametrize("shape,B", [(dict(C=768, h=14, w=14, K=20, image_size=224), 7), (dict(C=64, h=50, w=50, K=30, image_size=800), 3),
-                                     (dict(C=40, h=5, w=7, K=3, image_size=64), 4), (dict(C=3072, h=14, w=14, K=9, image_size=224), 2)])
+                                     (dict(C=40, h=5, w=7, K=3, image_size=64), 4), (dict(C=3072, h=14, w=14, K=9, image_size=224), 2),
+                                     # streaming kernel: 256 pixels (all eight consumer warps), an odd number of chunks with a
+                                     # 24-channel tail, two key-point tiles (K > 32); an odd pixel count with 4-byte A loads
+                                     (dict(C=72, h=16, w=16, K=40, image_size=256), 3), (dict(C=104, h=15, w=15, K=17, image_size=240), 3)])
 def test_spair_batch_equals_oracle_per_pair(mv, syn, shape, B):
     """mv_spair_match_batch (one launch for B pairs, fp32) against the oracle pair by pair: arg-max identical
     wherever the oracle's top-2 heat-map gap exceeds 1e-5 (fp32 summation order only), errors to 1e-5, the
@@ -292,6 +295,38 @@ def test_spair_batch_equals_per_pair_path_and_edge_cases(mv, syn):
     assert e[0].shape == (5, 0)
     with pytest.raises(ValueError):
         sp.compute_errors_batch(feats[0], ki, kj, ts, 224)
+
+
+def test_spair_batch_many_pairs_per_cta(mv, syn):
+    """more pairs than resident CTAs (2 per SM): every CTA of the streaming kernel walks several pairs, its producer warp
+    running ahead across pair boundaries (ring phases, q buffers and the score matrix carry over).  Pair b of the long
+    batch must equal, bit for bit, the same pair in a batch small enough for one pair per CTA; the short batch is
+    checked against the oracle."""
+    shape = dict(C=48, h=14, w=14, K=20, image_size=224)
+    distinct = 37
+    pairs = [syn.spair_pair(100 + i, **shape) for i in range(distinct)]
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    B = 4 * sm + 45  # ragged: some CTAs take one pair more than others
+    pick = lambda key: torch.stack([pairs[b % distinct][key] for b in range(B)])
+    ts = [pairs[b % distinct]["thresh_scale"] for b in range(B)]
+    hits = torch.zeros(2, dtype=torch.int64, device="cuda")
+    long = mv.spair.compute_errors_batch(pick("feats"), pick("kps_i"), pick("kps_j"), ts, 224, hits=hits)
+    hits_s = torch.zeros(2, dtype=torch.int64, device="cuda")
+    short = mv.spair.compute_errors_batch(torch.stack([p["feats"] for p in pairs]), torch.stack([p["kps_i"] for p in pairs]),
+                                          torch.stack([p["kps_j"] for p in pairs]), ts[:distinct], 224, hits=hits_s)
+    idx = torch.arange(B, device="cuda") % distinct
+    for a, b in zip(long, short):
+        assert torch.equal(a, b[idx])
+    reps = torch.bincount(idx.cpu(), minlength=distinct)
+    per_pair_both = (short[0] >= 0).sum(1).cpu()
+    assert int(hits[0]) == int((per_pair_both * reps).sum())
+    for b, p in enumerate(pairs):
+        _, _, oisame, _, heat = restated.spair_compute_errors(p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"], 224, return_pred=True)
+        flat = heat.flatten(1)
+        top2 = torch.topk(flat, 2, dim=1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 1e-5
+        assert torch.equal(short[3][b].cpu().long()[clear], flat.argmax(1)[clear])
+        assert torch.equal((short[0][b].cpu() >= 0).nonzero().squeeze(1), oisame)
 
 
 def test_spair_paths_vs_reference_golden(mv, syn, golden):
