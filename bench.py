@@ -597,7 +597,7 @@ def k1_record(ctx):
 # --------------------------------------------------------------------------------------------------------------
 # SPair (configs[0])
 # --------------------------------------------------------------------------------------------------------------
-SPAIR_DRAM_BYTES_PER_PAIR = 1.44e6  # ncu --set full of one SPAIR_BATCH launch (dram__bytes_read.sum + dram__bytes_write.sum) / pairs
+SPAIR_DRAM_BYTES_PER_PAIR = 1.487e6  # ncu --set full of one SPAIR_BATCH launch (dram__bytes_read.sum + dram__bytes_write.sum) / pairs
 SPAIR_BATCH = 1184  # pairs per step (one launch) = 4 waves of 2 CTAs x 148 SMs; 1.2 MB of features per pair -> 1.4 GB per step
 
 
