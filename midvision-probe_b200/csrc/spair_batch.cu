@@ -254,7 +254,14 @@ __global__ void __launch_bounds__(SPB_THREADS) spair_batch_kernel(SpairBatchPara
 #endif
 constexpr int SPS_CONS = SPS_CONS_N;        // consumer threads: thread = pixel in pass N
 constexpr int SPS_WARPS = SPS_CONS / 32;    // each owns 32 pixels (two m16 tiles) in the tensor-core pass
-constexpr int SPS_THREADS = SPS_CONS + 32;  // + one producer warp
+#ifndef SPS_QWARPS
+#define SPS_QWARPS 0  // n > 0: n warps that do nothing but step Q, one chunk ahead of step H (0: the eight consumer warps do both).
+// Measured: 2 Q warps (11 warps per CTA, 80 registers) 3.48 M pairs/s, 1 Q warp (96 registers; it becomes the critical path)
+// 3.03 M, against 3.64 M for 0 -- kept behind the switch with its tests (the parity tests pass in all three builds)
+#endif
+constexpr int SPS_QW = SPS_QWARPS;
+constexpr int SPS_THREADS = SPS_CONS + 32 * SPS_QW + 32;  // + one producer warp
+constexpr int SPS_QH = SPS_CONS + 32 * SPS_QW;            // the threads that meet on the q buffers' barriers
 static_assert(SPS_CONS == 256, "32 pixels per consumer warp, h*w <= 256");
 constexpr int SPS_MAX_STAGES = 8;
 #ifndef SPS_CC_N
@@ -338,13 +345,13 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_CTAS) spair_stream_kernel(Spa
   if (tid == 0) {
     for (int s = 0; s < nstage; ++s) {
       mbar_init(smem_u32(&full[s]), 1);
-      mbar_init(smem_u32(&empty[s]), SPS_WARPS);
+      mbar_init(smem_u32(&empty[s]), SPS_WARPS + SPS_QW);
     }
     mbar_fence_init();
   }
   __syncthreads();
 
-  if (wid == SPS_WARPS) {
+  if (wid == SPS_WARPS + SPS_QW) {
     // ===================================== producer warp =====================================
     int stage = 0;
     uint32_t phase = 0;
@@ -392,10 +399,76 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_CTAS) spair_stream_kernel(Spa
     if (lane == 0) mbar_arrive(smem_u32(&empty[stage]));
     if (++stage == nstage) { stage = 0; phase ^= 1u; }
   };
+  // named barriers between the Q warps and the H warps (SPS_QW > 0): 2 = the pair's blend weights are folded, 3 + b = q buffer b
+  // is full, 5 + b = q buffer b is free again; 7 = the Q warps among themselves.  `g` counts the chunks of this CTA (the same
+  // sequence in both roles): chunk g uses buffer g & 1.
+  auto bar_sync = [](int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); };
+  auto bar_arrive = [](int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); };
+  constexpr int QF = sps_q_floats<KT, MMA>(cc);
+  unsigned g_chunk = 0;
+  const unsigned n_chunks_cta = blockIdx.x < (unsigned)p.B ? (unsigned)((p.B - 1 - blockIdx.x) / gridDim.x + 1) * nkt * nchunk : 0u;
+
+  if (SPS_QW > 0 && wid >= SPS_WARPS) {
+    // ===================================== Q warps =====================================
+    // step Q of chunk g while the H warps are still on chunk g - 1: lane = (key point, channel group), the key point's four
+    // taps and folded weights in registers for the whole tile
+    constexpr int QT = 32 * (SPS_QW > 0 ? SPS_QW : 1), G = QT / KT;
+    const int ql = tid - SPS_CONS, k = ql % KT, cg = ql / KT;
+    const bool q_on = ql < G * KT;
+    for (int i = ql; i < 2 * QF; i += QT) qbuf[i] = 0.f;
+    bar_sync(7, QT);
+    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+      for (int c0 = 0; c0 < C; c0 += 2 * cc) {  // pass N belongs to the H warps
+        mbar_wait(smem_u32(&full[stage]), phase);
+        release();
+      }
+      bar_sync(2, SPS_QH);
+      for (int k0 = 0; k0 < K; k0 += KT) {
+        const int kt = min(KT, K - k0), kk = k0 + min(k, kt - 1);
+        int tap[4];
+        float wq[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) tap[t] = s_tap[kk][t], wq[t] = s_wt[kk][t];
+        for (int cq = 0; cq < nchunk; ++cq) {
+          const int c0 = (REV ? nchunk - 1 - cq : cq) * cc, rows = min(cc, C - c0);
+          float* qb = qbuf + (g_chunk & 1) * QF;
+          mbar_wait(smem_u32(&full[stage]), phase);
+          if (g_chunk >= 2) bar_sync(5 + (g_chunk & 1), SPS_QH);
+          const float* sti = ring + (size_t)stage * slot_floats;
+          if (q_on) {
+            for (int c = cg; c < rows; c += G) {
+              const float* src = sti + c * rs;
+              float a = src[tap[0]] * wq[0];
+              a = fmaf(src[tap[1]], wq[1], a);
+              a = fmaf(src[tap[2]], wq[2], a);
+              a = fmaf(src[tap[3]], wq[3], a);
+              a = (k < kt) ? a : 0.f;
+              if constexpr (MMA) {
+                uint32_t hi, lo;
+                split_tf32(a, hi, lo);
+                float* qd = qb + sps_q_off<KT, MMA>(c, k);
+                qd[0] = __uint_as_float(hi);
+                qd[2] = __uint_as_float(lo);
+              } else {
+                qb[sps_q_off<KT, MMA>(c, k)] = a;
+              }
+            }
+          }
+          bar_arrive(3 + (g_chunk & 1), SPS_QH);
+          release();
+          ++g_chunk;
+        }
+      }
+    }
+    return;
+  }
+
   const int px = tid;
   const bool has_px = px < hw;
-  for (int i = tid; i < 2 * sps_q_floats<KT, MMA>(cc); i += SPS_CONS) qbuf[i] = 0.f;
-  cons_sync();
+  if (SPS_QW == 0) {
+    for (int i = tid; i < 2 * QF; i += SPS_CONS) qbuf[i] = 0.f;
+    cons_sync();
+  }
 
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
     const float* ki = p.kps_i + (size_t)b * K * p.stride;
@@ -445,6 +518,7 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_CTAS) spair_stream_kernel(Spa
       s_wt[k][t] = __fdiv_rn(s_wt[k][t], fmaxf(sqrtf(pix_ss[s_tap[k][t]]), SPB_NORM_EPS));
     }
     cons_sync();
+    if (SPS_QW > 0) bar_arrive(2, SPS_QH);
 
     for (int k0 = 0; k0 < K; k0 += KT) {
       const int kt = min(KT, K - k0);
@@ -472,12 +546,12 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_CTAS) spair_stream_kernel(Spa
 
       for (int cq = 0; cq < nchunk; ++cq) {
         const int c0 = (REV ? nchunk - 1 - cq : cq) * cc, rows = min(cc, C - c0);
-        float* qb = qbuf + (cq & 1) * sps_q_floats<KT, MMA>(cc);
+        float* qb = qbuf + ((SPS_QW > 0 ? g_chunk : (unsigned)cq) & 1) * QF;
         mbar_wait(smem_u32(&full[stage]), phase);
         const float* sti = ring + (size_t)stage * slot_floats;
         const float* stj = sti + cc * rs;
         // ---- step Q: q[c][k] = sum_t wt * f_i[c][tap] / max(||f_i[tap]||, eps): the grid_sample of the normalised map ----
-        for (int idx = tid; idx < rows * KT && SPS_NULL != 1 && SPS_NULL != 3; idx += SPS_CONS) {
+        for (int idx = tid; idx < rows * KT && SPS_NULL != 1 && SPS_NULL != 3 && SPS_QW == 0; idx += SPS_CONS) {
           const int c = idx / KT, k = idx - c * KT;
           const int kk = k0 + min(k, kt - 1);
           const float* src = sti + c * rs;
@@ -496,7 +570,8 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_CTAS) spair_stream_kernel(Spa
             qb[sps_q_off<KT, MMA>(c, k)] = a;
           }
         }
-        cons_sync();  // q of this chunk complete; the other buffer is free again once every warp has passed this point
+        if (SPS_QW > 0) bar_sync(3 + (g_chunk & 1), SPS_QH);  // q of this chunk complete (the Q warps have arrived)
+        else cons_sync();  // q of this chunk complete; the other buffer is free again once every warp has passed this point
         // ---- step H: heat[k][px] += sum_c q[c][k] * f_j[c][px], the pixel's norm accumulated alongside ----
         if constexpr (MMA) {
           if (warp_live && SPS_NULL != 1 && SPS_NULL != 2) {
@@ -571,6 +646,10 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_CTAS) spair_stream_kernel(Spa
               }
             }
           }
+        }
+        if (SPS_QW > 0) {
+          if (g_chunk + 2 < n_chunks_cta) bar_arrive(5 + (g_chunk & 1), SPS_QH);  // this warp is done with the q buffer
+          ++g_chunk;
         }
         release();
       }
