@@ -13,9 +13,10 @@
 //
 // Why a separate kernel: one pair is 2 * K * h*w * C = 6 MFLOP (K = 20, 14 x 14, C = 768) -- a 128-row
 // tensor-core tile would be 84 % padding and the ten launches of the per-pair path (kernels 1-3) are pure
-// launch latency.  Here each feature map is read once (1.2 MB per pair, the HBM floor) straight from the
-// backbone's (B, 2, C, h, w) output, the heat map lives in registers and nothing but K integers per pair is
-// written, so the path is bounded by HBM, not by launches.
+// launch latency.  Here the maps are read straight from the backbone's (B, 2, C, h, w) output -- 1.2 MB per
+// pair, the HBM floor; image i a second time, from L2 where it is still there (1.33-1.49 MB of DRAM reads per
+// pair measured) -- the heat map lives in registers and nothing but K integers per pair is written, so the
+// path is bounded by HBM, not by launches.
 #include <math_constants.h>
 #include <stdlib.h>
 
