@@ -20,6 +20,8 @@
 #include <math_constants.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "sm100_ptx.cuh"
 #include "spair_score.cuh"
@@ -578,6 +580,11 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_CTAS) spair_stream_kernel(Spa
           if (warp_live && SPS_NULL != 1 && SPS_NULL != 2) {
             const float* aj = stj + 32 * wid + 2 * g;
             const float4* bq = reinterpret_cast<const float4*>(qb) + lane;
+            // the two run-time facts of a K step -- 8-byte loads possible, second tile live -- are dispatched once per chunk, so
+            // that the K steps themselves are branch-free and the scheduler can lift the next step's loads above this step's MMAs
+            auto h_chunk = [&](auto vec2_c, auto tile1_c) {
+            constexpr bool VEC2 = decltype(vec2_c)::value;
+            constexpr int NTILE = decltype(tile1_c)::value ? 2 : 1;
             auto kstep = [&](int ks) {  // channels ks .. ks + 7 of the chunk
               uint32_t bh[NT8][2], bl[NT8][2];
 #pragma unroll
@@ -596,9 +603,8 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_CTAS) spair_stream_kernel(Spa
               const float* r1 = r0 + 4 * rs;
               float av[2][4];
 #pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                if (i == 1 && !tile1_live) break;  // warp-uniform: the warp's second 16 pixels lie beyond the map
-                if (vec2) {
+              for (int i = 0; i < NTILE; ++i) {  // NTILE == 1: the warp's second 16 pixels lie beyond the map
+                if constexpr (VEC2) {
                   const float2 x0 = *reinterpret_cast<const float2*>(r0 + 16 * i), x1 = *reinterpret_cast<const float2*>(r1 + 16 * i);
                   av[i][0] = x0.x, av[i][1] = x0.y, av[i][2] = x1.x, av[i][3] = x1.y;
                 } else {
@@ -606,8 +612,7 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_CTAS) spair_stream_kernel(Spa
                 }
               }
 #pragma unroll
-              for (int i = 0; i < 2; ++i) {
-                if (i == 1 && !tile1_live) break;
+              for (int i = 0; i < NTILE; ++i) {
                 ssr[i][0] = fmaf(av[i][0], av[i][0], ssr[i][0]);
                 ssr[i][0] = fmaf(av[i][2], av[i][2], ssr[i][0]);
                 ssr[i][1] = fmaf(av[i][1], av[i][1], ssr[i][1]);
@@ -628,6 +633,16 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_CTAS) spair_stream_kernel(Spa
               for (int ks = 0; ks < cc; ks += 8) kstep(ks);
             } else {
               for (int ks = 0; ks < rows; ks += 8) kstep(ks);
+            }
+            };
+            using T = std::true_type;
+            using F = std::false_type;
+            if (vec2) {
+              if (tile1_live) h_chunk(T{}, T{});
+              else h_chunk(T{}, F{});
+            } else {
+              if (tile1_live) h_chunk(F{}, T{});
+              else h_chunk(F{}, F{});
             }
           }
         } else {
