@@ -382,6 +382,13 @@ int mv_spair_match_batch(const float* feats, int B, int C, int h, int w, const f
                          int32_t* pred_flat, float* error_same, float* error_nn, int32_t* index_nn,
                          unsigned long long* hits, unsigned long long* confusion, int conf_dim, mv_stream_t stream);
 
+/* Precision of the batched kernel's heat map (the einsum of evaluate_spair_correspondence.py:82) on the tensor cores:
+ * 3 (default) = every product as three tf32 MMAs (hi*hi + hi*lo + lo*hi, ~21 mantissa bits: the arg-max equals the fp32
+ * reference's wherever the top-2 heat-map gap exceeds 1e-5); 1 = one tf32 MMA, operands rounded to 10 mantissa bits with
+ * fp32 accumulation (arg-max equal wherever the gap exceeds 1e-3, the tolerance of the matching path's tf32 operand type).
+ * Returns the previous setting; any other value only queries.  Takes effect for launches issued afterwards. */
+int mv_spair_set_heatmap_terms(int terms);
+
 #ifdef __cplusplus
 }
 #endif

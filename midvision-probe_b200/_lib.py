@@ -47,6 +47,7 @@ PROTOTYPES = {
     "mv_affinity_threshold": (c_int, [P, c_int, c_int, c_int, c_float, c_float, P, P, P]),
     "mv_cosine_2afc": (c_int, [P, P, P, c_int, c_int, P, P, P, P]),
     "mv_k2_set_streamk": (c_int, [c_int]),
+    "mv_spair_set_heatmap_terms": (c_int, [c_int]),
     "mv_k2_profile_begin": (c_int, [c_int]),
     "mv_k2_profile_read": (c_int, [P, c_int]),
     "mv_k2_profile_dims": (c_int, [P, c_int]),

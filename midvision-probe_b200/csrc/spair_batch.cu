@@ -320,7 +320,10 @@ constexpr int sps_q_floats(int cc) {  // one q buffer
 
 // MMA: the heat-map step on the tensor cores -- pixels on M (16 per tile, 2 tiles per warp), key points on N (8 per tile),
 // 8 channels per K step, 3xTF32 -- instead of 21 FFMA + 6 LDS per channel and pixel.
-template <int KT, bool MMA>
+// TERMS: 3 = 3xTF32 (fp32-grade heat map, the default), 1 = one tf32 MMA per tile (mv_spair_set_heatmap_terms(1): operands
+// rounded to 10 mantissa bits, the north star's "tf32 inputs, fp32 accumulation" -- arg-max equal wherever the fp32 top-2 gap
+// of the heat map exceeds 1e-3)
+template <int KT, bool MMA, int TERMS = 3>
 __global__ void __launch_bounds__(SPS_THREADS, SPS_CTAS) spair_stream_kernel(SpairBatchParams p) {
   using namespace sm100;
   extern __shared__ __align__(16) float4 sps_dyn[];
@@ -622,8 +625,8 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_CTAS) spair_stream_kernel(Spa
                 for (int e = 0; e < 4; ++e) split_tf32(av[i][e], ah[e], al[e]);
 #pragma unroll
                 for (int j = 0; j < NT8; ++j) {
-                  if (SPS_NULL != 4 && SPS_NULL != 5) mma_tf32(d[i][j], al, bh[j][0], bh[j][1]);
-                  if (SPS_NULL != 4 && SPS_NULL != 5) mma_tf32(d[i][j], ah, bl[j][0], bl[j][1]);
+                  if (SPS_NULL != 4 && SPS_NULL != 5 && TERMS == 3) mma_tf32(d[i][j], al, bh[j][0], bh[j][1]);
+                  if (SPS_NULL != 4 && SPS_NULL != 5 && TERMS == 3) mma_tf32(d[i][j], ah, bl[j][0], bl[j][1]);
                   if (SPS_NULL != 5) mma_tf32(d[i][j], ah, bh[j][0], bh[j][1]);
                 }
               }
@@ -767,6 +770,8 @@ __global__ void __launch_bounds__(SPS_THREADS, SPS_CTAS) spair_stream_kernel(Spa
   }
 }
 
+int g_spair_terms = 3;  // mv_spair_set_heatmap_terms
+
 // shared-memory plan of the streaming form
 struct SpsPlan {
   int cc, rs, stages;
@@ -801,9 +806,10 @@ template <int KT>
 int launch_spair_stream(const SpairBatchParams& p, const SpsPlan& pl, cudaStream_t st) {
   // MVMATCH_SPAIR_MMA=0: the heat-map step on the CUDA cores (the arithmetic of the first form)
   static const bool mma = !(getenv("MVMATCH_SPAIR_MMA") && getenv("MVMATCH_SPAIR_MMA")[0] == '0');
-  auto kern = mma ? spair_stream_kernel<KT, true> : spair_stream_kernel<KT, false>;
-  static size_t opted[MV_MAX_DEVICES][2];
-  size_t& opted_in = opted[mv_device_slot()][mma ? 1 : 0];
+  const bool one_term = mma && g_spair_terms == 1;
+  auto kern = !mma ? spair_stream_kernel<KT, false> : one_term ? spair_stream_kernel<KT, true, 1> : spair_stream_kernel<KT, true, 3>;
+  static size_t opted[MV_MAX_DEVICES][3];
+  size_t& opted_in = opted[mv_device_slot()][!mma ? 0 : one_term ? 2 : 1];
   if (pl.smem > opted_in) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem);
     if (e != cudaSuccess) {
@@ -904,6 +910,12 @@ int mv_spair_match_batch(const float* feats, int B, int C, int h, int w, const f
   if (K > 12 && 16 * per_k <= budget) return launch_spair_batch<16>(p, st);
   if (K > 8 && 12 * per_k <= budget) return launch_spair_batch<12>(p, st);
   return launch_spair_batch<8>(p, st);
+}
+
+int mv_spair_set_heatmap_terms(int terms) {
+  const int prev = g_spair_terms;
+  if (terms == 1 || terms == 3) g_spair_terms = terms;
+  return prev;
 }
 
 }  // extern "C"

@@ -101,6 +101,16 @@ def compute_errors_batch(feats, kps_i, kps_j, thresh_scale, image_size, pck_thre
     return err_same, err_nn, idx_nn, pred
 
 
+def set_heatmap_precision(mode):
+    """Precision of compute_errors_batch's heat map (the einsum of evaluate_spair_correspondence.py:82) on the tensor cores:
+    "3xtf32" (default; ~21 mantissa bits, arg-max equal to the fp32 reference's wherever its top-2 gap exceeds 1e-5) or
+    "tf32" (one MMA per tile: operands rounded to 10 mantissa bits, fp32 accumulation -- equal wherever the gap exceeds
+    1e-3, the tolerance of the matching path's tf32 operand type).  Returns the previous mode."""
+    terms = {"3xtf32": 3, "tf32": 1}[mode]
+    prev = L.load().mv_spair_set_heatmap_terms(terms)
+    return "tf32" if prev == 1 else "3xtf32"
+
+
 def evaluate_batches(batches, pck_thresh=0.10, kp_max=30):
     """(recall, confusion) over an iterable of dicts with keys feats (B, 2, C, h, w), kps_i, kps_j (B, K, 3),
     thresh_scale (B), image_size: evaluate_dataset (evaluate_spair_correspondence.py:106-123) with one launch per

@@ -329,6 +329,38 @@ def test_spair_batch_many_pairs_per_cta(mv, syn):
         assert torch.equal((short[0][b].cpu() >= 0).nonzero().squeeze(1), oisame)
 
 
+def test_spair_batch_single_tf32_term(mv, syn):
+    """spair.set_heatmap_precision("tf32"): one tf32 MMA per tile instead of three.  Arg-max identical to the oracle's
+    wherever its top-2 heat-map gap exceeds 1e-3 (the tf32 tolerance of the matching path), key points kept bit-exact,
+    PCK within one key point per pair of the default mode; the default mode is back afterwards."""
+    shape = dict(C=768, h=14, w=14, K=20, image_size=224)
+    pairs = [syn.spair_pair(60 + i, **shape) for i in range(12)]
+    args = (torch.stack([p["feats"] for p in pairs]), torch.stack([p["kps_i"] for p in pairs]), torch.stack([p["kps_j"] for p in pairs]),
+            [p["thresh_scale"] for p in pairs], 224)
+    h3 = torch.zeros(2, dtype=torch.int64, device="cuda")
+    ref = mv.spair.compute_errors_batch(*args, hits=h3)
+    assert mv.spair.set_heatmap_precision("tf32") == "3xtf32"
+    try:
+        h1 = torch.zeros(2, dtype=torch.int64, device="cuda")
+        es, en, inn, pred = mv.spair.compute_errors_batch(*args, hits=h1)
+    finally:
+        assert mv.spair.set_heatmap_precision("3xtf32") == "tf32"
+    compared = total = 0
+    for b, p in enumerate(pairs):
+        _, _, oisame, _, heat = restated.spair_compute_errors(p["feats"], p["kps_i"], p["kps_j"], p["thresh_scale"], 224, return_pred=True)
+        flat = heat.flatten(1)
+        top2 = torch.topk(flat, 2, dim=1).values
+        clear = (top2[:, 0] - top2[:, 1]) > 1e-3
+        compared += int(clear.sum())
+        total += clear.numel()
+        assert torch.equal(pred[b].cpu().long()[clear], flat.argmax(1)[clear])
+        assert torch.equal((es[b].cpu() >= 0).nonzero().squeeze(1), oisame)
+    assert compared >= 0.5 * total, (compared, total)
+    assert int(h1[0]) == int(h3[0]) and abs(int(h1[1]) - int(h3[1])) <= len(pairs)
+    again = mv.spair.compute_errors_batch(*args)
+    assert torch.equal(again[3], ref[3])
+
+
 def test_spair_paths_vs_reference_golden(mv, syn, golden):
     """both SPair paths against tests/golden/spair_small.npz, the output of the reference's own compute_errors."""
     from oracle.make_golden import SPAIR_SMALL
