@@ -47,6 +47,20 @@ def test_version_and_argument_errors_without_a_gpu(mv):
         mv._lib.call("mv_compact_valid", None, 1, 4, None, None, None)
 
 
+def test_switch_entry_points_without_a_gpu(mv):
+    """the setters that only flip host-side state: previous value returned, out-of-range values only query."""
+    lib = mv.load()
+    assert lib.mv_spair_set_heatmap_terms(-1) == 3          # default: 3xTF32
+    assert lib.mv_spair_set_heatmap_terms(1) == 3
+    assert lib.mv_spair_set_heatmap_terms(2) == 1           # not a mode: query only
+    assert lib.mv_spair_set_heatmap_terms(3) == 1
+    assert mv.spair.set_heatmap_precision("3xtf32") == "3xtf32"
+    with pytest.raises(KeyError):
+        mv.spair.set_heatmap_precision("fp8")
+    prev = lib.mv_k2_set_streamk(-1)
+    assert prev in (0, 1) and lib.mv_k2_set_streamk(-1) == prev
+
+
 def test_product_has_no_oracle_import():
     pkg = os.path.join(ROOT, "midvision-probe_b200")
     for f in os.listdir(pkg):
