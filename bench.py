@@ -597,7 +597,7 @@ def k1_record(ctx):
 # --------------------------------------------------------------------------------------------------------------
 # SPair (configs[0])
 # --------------------------------------------------------------------------------------------------------------
-SPAIR_DRAM_BYTES_PER_PAIR = 1.487e6  # ncu --set full of one 1184-pair launch (dram__bytes_read.sum + dram__bytes_write.sum) / pairs
+SPAIR_DRAM_BYTES_PER_PAIR = 1.441e6  # ncu --set full of one 2368-pair launch (dram__bytes_read.sum + dram__bytes_write.sum) / pairs
 SPAIR_BATCH = 2368  # pairs per step (one launch) = 8 per CTA at 2 CTAs x 148 SMs; 1.2 MB of features per pair -> 2.85 GB per step
 SPAIR_BATCH_E2E = 1184  # pairs per step of the end-to-end arm (1.4 GB of pinned host memory per rank)
 
@@ -683,7 +683,7 @@ def run_spair(ctx, steps, warmup):
                      "frac": byts / (per_launch_ms * 1e-3) / 1e9 / hbm_peak, "traffic": SPAIR_DRAM_BYTES_PER_PAIR * B,
                      "peak_kind": f"{peak_kind} copy bandwidth",
                      "kernel": "spair_stream_kernel (one launch per step; algorithmic bytes = the (B, 2, C, h, w) features, read once; "
-                               "traffic = dram__bytes_read + write of one launch under ncu, profiles/r2_spair_stream_final.txt: image i is "
+                               "traffic = dram__bytes_read + write of one launch under ncu, profiles/r2_spair_stream_final_2368.txt: image i is "
                                "read twice and its second read hits L2 only in part)",
                      "avg_ms": per_launch_ms, "bytes_per_launch": byts},
         "recall": {"keypoints_in_both": h[0], "pck_0.10": 100.0 * h[1] / max(h[0], 1)},
