@@ -244,14 +244,16 @@ __global__ void __launch_bounds__(SPB_THREADS) spair_batch_kernel(SpairBatchPara
 // 1.2 MB algorithmic).  SPS_QREV: pass QH walks the channels from the last chunk to the first, so that its first i reads are
 // the most recently cached ones; SPS_HINTS: pass N loads with L2 evict_last, everything that is read for the last time with
 // evict_first (ncu after: 1.33 MB per pair).
-// Rows (one channel = h*w floats) land `rs` floats apart: rs = h*w rounded up to 8 mod 32 when h*w % 4 == 0 (one bulk copy
-// per row), so that the tensor-core pass reads its A fragments with conflict-free 16-byte loads -- lane (g, t) of warp w owns
-// pixels 32 w + 4 g .. + 3 of channels t and t + 4: two LDS.128 per K step where the pixel-per-row mapping took eight LDS.32
-// with two-way bank conflicts; rs = h*w (one copy per half slot, 4-byte loads) otherwise.
+// Rows (one channel = h*w floats) keep their h*w pitch in the slot (one bulk copy per half slot).  Padding them to a
+// conflict-free pitch needs one 784-byte bulk copy per row and measured 2.59 M pairs/s against 3.18 M for the unpadded rows of
+// the same build: small copies cost more than the two-way bank conflicts of the A-fragment loads.
 //
-// Measured history (SPair-shaped, 2048 pairs, one B200): round 1 per-thread global loads 1.81 M pairs/s; ring of 4 x 8
-// channels + tensor-core heat map 2.60 M; 2 x 16 channels 2.79 M; score matrix out of static shared memory, 3 x 16 channels
-// 3.17 M, 2 x 24 channels 3.35-3.42 M (63 % of the HBM copy peak); 16 consumer warps per CTA: slower (2.16 M at the 4 x 8 ring).
+// Measured history (SPair-shaped, 2048-2368 pairs per launch, one B200; profiles/r2_spair_diag.txt): round 1 per-thread global
+// loads 1.81 M pairs/s; ring of 4 x 8 channels + tensor-core heat map 2.60 M; 2 x 16 channels 2.79 M; score matrix out of static
+// shared memory, 3 x 16 channels 3.17 M, 2 x 24 channels 3.35-3.42 M; pass QH with pre-split B fragments 3.29 M; A fragments by
+// LDS.64 into the operand quads 3.57 M; dead tile skipped, branch-free K steps 3.64-3.68 M (67-68 % of the HBM copy peak; the
+// memory side alone -- consumers that only wait and release, -DSPS_NULL=1 -- runs 4.69 M); 16 consumer warps per CTA: slower
+// (2.16 M at the 4 x 8 ring).
 #ifndef SPS_CONS_N
 #define SPS_CONS_N 256
 #endif
